@@ -1,0 +1,286 @@
+"""ORACLE (test infrastructure): builds the flat robot / collision-model structs the C restatement consumes,
+following how CollisionEnvDistanceField derives them (collision_distance_field/src/...):
+
+  collision_env_distance_field.cpp:1049-1078   addLinkBodyDecompositions (BodyDecomposition per link with geometry)
+  collision_distance_field_types.cpp:59-85     determineCollisionSpheres (SPHERE shape -> one sphere at the body pose)
+  collision_distance_field_types.cpp:292-335   BodyDecomposition::init (spheres, interior points, merged bounding sphere)
+  distance_field/src/find_internal_points.cpp:39-64   interior lattice points of a convex body
+  collision_env_distance_field.cpp:710-958     generateDistanceFieldCacheEntry (enable masks, self-field points)
+  collision_detection/src/collision_matrix.cpp:67-78, 127-138   ACM from SRDF, explicit-entry lookup
+
+Third-party arithmetic restated from published geometric_shapes sources (un-vendored, NO version pin in the
+reference => parity unpinned for these two): bodies::Sphere::containsPoint (|c-p|^2 <= r^2; its semantics ARE
+pinned by test_big.df, see tests/test_oracle_df.py) and bodies::mergeBoundingSpheres.
+Only SPHERE collision geometry is supported: box/cylinder/mesh decompositions go through
+bodies::Body::computeBoundingCylinder which is not available here.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import lib
+from .robot_model import RobotModel
+
+C = ctypes
+
+
+class OrcRobot(C.Structure):
+    _fields_ = [("n_links", C.c_int32), ("n_vars", C.c_int32),
+                ("parent", C.POINTER(C.c_int32)), ("joint_type", C.POINTER(C.c_int32)),
+                ("axis", C.POINTER(C.c_double)), ("origin", C.POINTER(C.c_double)),
+                ("origin_is_identity", C.POINTER(C.c_int32)), ("first_var", C.POINTER(C.c_int32)),
+                ("n_group_vars", C.c_int32), ("group_var_index", C.POINTER(C.c_int32)),
+                ("n_mimic", C.c_int32), ("mimic_dst", C.POINTER(C.c_int32)), ("mimic_src", C.POINTER(C.c_int32)),
+                ("mimic_factor", C.POINTER(C.c_double)), ("mimic_offset", C.POINTER(C.c_double))]
+
+
+class OrcCollisionModel(C.Structure):
+    _fields_ = [("n_glinks", C.c_int32), ("glink_index", C.POINTER(C.c_int32)),
+                ("has_geometry", C.POINTER(C.c_int32)), ("self_enabled", C.POINTER(C.c_int32)),
+                ("intra_enabled", C.POINTER(C.c_uint8)), ("sphere_start", C.POINTER(C.c_int32)),
+                ("sphere_rel", C.POINTER(C.c_double)), ("sphere_radius", C.POINTER(C.c_double)),
+                ("bs_center", C.POINTER(C.c_double)), ("bs_radius", C.POINTER(C.c_double)),
+                ("point_start", C.POINTER(C.c_int32)), ("point_rel", C.POINTER(C.c_double)),
+                ("max_propagation_distance", C.c_double), ("collision_tolerance", C.c_double)]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def find_internal_points_sphere(center, radius, resolution):
+    """findInternalPointsConvex (find_internal_points.cpp:39-64) for a bodies::Sphere: bounding sphere = the sphere,
+    accumulating `pt += resolution` loops, containsPoint = |c - p|^2 <= r^2."""
+    cx, cy, cz = (float(v) for v in center)
+    r, res = float(radius), float(resolution)
+
+    def axis(c):
+        v = math.floor((c - r - res) / res) * res
+        e = c + r + res
+        out = []
+        while v <= e:
+            out.append(v)
+            v += res
+        return np.array(out)
+
+    xs, ys, zs = axis(cx), axis(cy), axis(cz)
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    dx, dy, dz = cx - X, cy - Y, cz - Z
+    inside = (dx * dx + dy * dy + dz * dz) <= r * r
+    return np.stack([X[inside], Y[inside], Z[inside]], axis=1)
+
+
+def merge_bounding_spheres(spheres):
+    """geometric_shapes bodies::mergeBoundingSpheres, restated from the published source (parity unpinned)."""
+    if not spheres:
+        return np.zeros(3), 0.0
+    c, r = np.array(spheres[0][0], dtype=np.float64), float(spheres[0][1])
+    for ci, ri in spheres[1:]:
+        ci = np.array(ci, dtype=np.float64)
+        if ri <= 0.0:
+            continue
+        d = float(np.linalg.norm(ci - c))
+        if d + r <= ri:
+            c, r = ci, ri
+        elif d + ri > r:
+            delta = c - ci
+            new_r = (float(np.linalg.norm(delta)) + ri + r) / 2.0
+            c = delta / np.linalg.norm(delta) * (new_r - ri) + ci
+            r = new_r
+    return c, r
+
+
+class BodyDecomposition:
+    """collision_distance_field_types.cpp:292-335 for SPHERE shapes (padding 0, scale 1)."""
+
+    def __init__(self, link, resolution):
+        self.spheres = []  # (rel xyz, radius)
+        pts = []
+        bss = []
+        for s in link.shapes:
+            if s.kind != "sphere":
+                raise NotImplementedError("oracle supports SPHERE collision geometry only (link %s has %s)"
+                                          % (link.name, s.kind))
+            c, r = s.origin[:3, 3].copy(), float(s.dims[0])
+            self.spheres.append((c, r))
+            pts.append(find_internal_points_sphere(c, r, resolution))
+            bss.append((c, r))
+        self.points = np.concatenate(pts, axis=0) if pts else np.zeros((0, 3))
+        self.bs_center, self.bs_radius = merge_bounding_spheres(bss)
+
+
+class AllowedCollisionMatrix:
+    """Explicit entries only, as CollisionEnvDistanceField consults them (collision_matrix.cpp:127-138)."""
+
+    def __init__(self, srdf):
+        self.entries = {}
+        for a, b in srdf["enabled"]:
+            self.set_entry(a, b, False)
+        for a, b in srdf["disabled"]:
+            self.set_entry(a, b, True)
+
+    def set_entry(self, a, b, allowed):
+        self.entries.setdefault(a, {})[b] = allowed
+        self.entries.setdefault(b, {})[a] = allowed
+
+    def always(self, a, b):
+        return self.entries.get(a, {}).get(b, False)
+
+
+class OracleEnv:
+    """Restated CollisionEnvDistanceField for one (robot, group, ACM): owns world and self fields."""
+
+    def __init__(self, model: RobotModel, group_name, size, origin, resolution, max_propagation_distance,
+                 collision_tolerance=0.0, use_acm=True, base_positions=None):
+        self.L = lib()
+        self.model, self.group = model, model.groups[group_name]
+        g = self.group
+        self.resolution = float(resolution)
+        self.max_prop, self.tol = float(max_propagation_distance), float(collision_tolerance)
+        self.size, self.origin = tuple(float(v) for v in size), tuple(float(v) for v in origin)
+        self.base_positions = np.array(model.default_positions() if base_positions is None else base_positions,
+                                       dtype=np.float64)
+        # ---- flat robot -------------------------------------------------------------------------------
+        L = model.links
+        a = self.arr = {}
+        a["parent"] = np.array([-1 if l.parent is None else l.parent.index for l in L], np.int32)
+        a["joint_type"] = np.array([l.parent_joint.type for l in L], np.int32)
+        a["axis"] = np.array([l.parent_joint.axis for l in L], np.float64).reshape(-1)
+        a["origin"] = np.array([l.origin.T.reshape(-1) for l in L], np.float64).reshape(-1)  # column-major
+        a["origin_is_identity"] = np.array([int(l.origin_is_identity) for l in L], np.int32)
+        a["first_var"] = np.array([l.parent_joint.first_var for l in L], np.int32)
+        a["group_var_index"] = np.array(g.variable_index_list, np.int32)
+        a["mimic_dst"] = np.array([m[0] for m in g.mimic_updates] + [0], np.int32)
+        a["mimic_src"] = np.array([m[1] for m in g.mimic_updates] + [0], np.int32)
+        a["mimic_factor"] = np.array([m[2] for m in g.mimic_updates] + [0], np.float64)
+        a["mimic_offset"] = np.array([m[3] for m in g.mimic_updates] + [0], np.float64)
+        self.robot = OrcRobot(len(L), model.n_vars, _p(a["parent"], C.c_int32), _p(a["joint_type"], C.c_int32),
+                              _p(a["axis"], C.c_double), _p(a["origin"], C.c_double),
+                              _p(a["origin_is_identity"], C.c_int32), _p(a["first_var"], C.c_int32),
+                              len(g.variable_index_list), _p(a["group_var_index"], C.c_int32),
+                              len(g.mimic_updates), _p(a["mimic_dst"], C.c_int32), _p(a["mimic_src"], C.c_int32),
+                              _p(a["mimic_factor"], C.c_double), _p(a["mimic_offset"], C.c_double))
+        # ---- body decompositions for every link with geometry (addLinkBodyDecompositions) --------------
+        self.decomp = {l.name: BodyDecomposition(l, self.resolution) for l in L if l.shapes}
+        # ---- DistanceFieldCacheEntry masks (generateDistanceFieldCacheEntry :735-838) -------------------
+        acm = AllowedCollisionMatrix(model.srdf) if use_acm else None
+        gl = g.updated_links
+        n = len(gl)
+        has_geom = np.array([int(bool(l.shapes)) for l in gl], np.int32)
+        self_en = np.ones(n, np.int32)
+        intra = np.zeros((n, n), np.uint8)
+        for i, li in enumerate(gl):
+            if not li.shapes:
+                self_en[i] = 0
+                continue
+            intra[i, :] = 1
+            if acm is not None:
+                if acm.always(li.name, li.name):
+                    self_en[i] = 0
+                for j in range(i + 1, n):
+                    if gl[j].name == li.name or acm.always(li.name, gl[j].name):
+                        intra[i, j] = 0
+        sph_start, sph_rel, sph_rad, bs_c, bs_r, pt_start, pt_rel = [0], [], [], [], [], [0], []
+        for l in gl:
+            d = self.decomp.get(l.name)
+            if d is not None:
+                for c, r in d.spheres:
+                    sph_rel.append(c)
+                    sph_rad.append(r)
+                pt_rel.append(d.points)
+                bs_c.append(d.bs_center)
+                bs_r.append(d.bs_radius)
+            else:
+                bs_c.append(np.zeros(3))
+                bs_r.append(0.0)
+            sph_start.append(len(sph_rad))
+            pt_start.append(pt_start[-1] + (len(d.points) if d is not None else 0))
+        a["glink_index"] = np.array([l.index for l in gl], np.int32)
+        a["has_geometry"], a["self_enabled"], a["intra_enabled"] = has_geom, self_en, intra.reshape(-1).copy()
+        a["sphere_start"] = np.array(sph_start, np.int32)
+        a["sphere_rel"] = np.array(sph_rel + [np.zeros(3)], np.float64).reshape(-1)
+        a["sphere_radius"] = np.array(sph_rad + [0.0], np.float64)
+        a["bs_center"] = np.array(bs_c + [np.zeros(3)], np.float64).reshape(-1)
+        a["bs_radius"] = np.array(bs_r + [0.0], np.float64)
+        a["point_start"] = np.array(pt_start, np.int32)
+        a["point_rel"] = (np.concatenate(pt_rel + [np.zeros((1, 3))], axis=0)).astype(np.float64).reshape(-1)
+        self.n_spheres = len(sph_rad)
+        self.cm = OrcCollisionModel(n, _p(a["glink_index"], C.c_int32), _p(a["has_geometry"], C.c_int32),
+                                    _p(a["self_enabled"], C.c_int32), _p(a["intra_enabled"], C.c_uint8),
+                                    _p(a["sphere_start"], C.c_int32), _p(a["sphere_rel"], C.c_double),
+                                    _p(a["sphere_radius"], C.c_double), _p(a["bs_center"], C.c_double),
+                                    _p(a["bs_radius"], C.c_double), _p(a["point_start"], C.c_int32),
+                                    _p(a["point_rel"], C.c_double), self.max_prop, self.tol)
+        # ---- fields: same geometry for world and self (:931-933, :1785-1787): corner = origin - size/2 ---
+        from .df import PropagationDistanceField
+        sx, sy, sz = self.size
+        ox, oy, oz = self.origin
+        geo = (sx, sy, sz, self.resolution, ox - 0.5 * sx, oy - 0.5 * sy, oz - 0.5 * sz, self.max_prop)
+        self.world = PropagationDistanceField(*geo)
+        self.self_field = PropagationDistanceField(*geo)
+        self.self_points = self.compute_self_points()
+        self.self_field.add_points(self.self_points)
+
+    def compute_self_points(self):
+        """:907-953 -- interior points of links with geometry that are NOT updated by the group, posed at the
+        cached state (here: the base state), in getLinkModelsWithCollisionGeometry (= link index) order."""
+        T = self.fk(self.group_values_of(self.base_positions)[None, :])[0]
+        updated = {l.name for l in self.group.updated_links_with_geometry}
+        pts = []
+        for l in self.model.links:
+            if not l.shapes or l.name in updated:
+                continue
+            P = self.decomp[l.name].points
+            M = T[l.index]
+            # Isometry3d * Vector3d, k in order
+            pts.append((M[:3, 0] * P[:, 0:1] + M[:3, 1] * P[:, 1:2]) + M[:3, 2] * P[:, 2:3] + M[:3, 3])
+        return np.concatenate(pts, axis=0) if pts else np.zeros((0, 3))
+
+    def group_values_of(self, positions):
+        return np.array([positions[i] for i in self.group.variable_index_list], np.float64)
+
+    def fk(self, q):
+        """Global link transforms [N, n_links, 4, 4] (row, col) for N group-state vectors."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, max(self.group.variable_count, 1))
+        n = q.shape[0]
+        out = np.zeros((n, len(self.model.links), 16))
+        self.L.orc_fk_batch(C.byref(self.robot), _p(self.base_positions, C.c_double), _p(q, C.c_double), n,
+                            _p(out, C.c_double))
+        return out.reshape(n, -1, 4, 4).transpose(0, 1, 3, 2)  # column-major -> [row, col]
+
+    def check(self, q, flags=7, faithful=False, threads=0):
+        """collision byte per state (1 = in collision); returns (array, threads used)."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, max(self.group.variable_count, 1))
+        n = q.shape[0]
+        out = np.zeros(n, np.uint8)
+        used = self.L.orc_check_batch(C.byref(self.robot), C.byref(self.cm), self.world.h, self.self_field.h,
+                                      _p(self.base_positions, C.c_double), _p(q, C.c_double), n, int(flags),
+                                      int(faithful), int(threads), _p(out, C.c_uint8))
+        return out, used
+
+    def margin(self, q1, flags=7):
+        q1 = np.ascontiguousarray(q1, np.float64)
+        return self.L.orc_state_margin(C.byref(self.robot), C.byref(self.cm), self.world.h, self.self_field.h,
+                                       _p(self.base_positions, C.c_double), _p(q1, C.c_double), int(flags))
+
+    def sphere_centers(self, q1):
+        q1 = np.ascontiguousarray(q1, np.float64)
+        out = np.zeros((self.n_spheres, 3))
+        self.L.orc_state_spheres(C.byref(self.robot), C.byref(self.cm), _p(self.base_positions, C.c_double),
+                                 _p(q1, C.c_double), _p(out, C.c_double))
+        return out
+
+    def joint_bounds(self):
+        """Bounds of the group's variables, as setToRandomPositions samples them (soft & hard limits)."""
+        lo, hi = [], []
+        for j in self.group.joints:
+            if j.n_vars == 1:
+                lo.append(j.bounds[0])
+                hi.append(j.bounds[1])
+            elif j.n_vars == 3:  # planar: benchmark samples a 1 m box and full yaw
+                lo += [-0.5, -0.5, -math.pi]
+                hi += [0.5, 0.5, math.pi]
+            elif j.n_vars == 7:
+                raise NotImplementedError("floating joints in a planning group are not sampled")
+        return np.array(lo), np.array(hi)
