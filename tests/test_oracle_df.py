@@ -1,0 +1,158 @@
+"""Pins the ORACLE's distance-field restatement on the reference's own golden data and test properties
+(moveit_core/distance_field/test/test_distance_field.cpp, test_voxel_grid.cpp).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.collision_model import find_internal_points_sphere
+from oracle.df import PropagationDistanceField, read_df_occupancy, write_df_occupancy
+
+# test_distance_field.cpp:48-60
+WIDTH = HEIGHT = DEPTH = 1.0
+RESOLUTION = 0.1
+MAX_DIST = 0.3
+POINT1, POINT2, POINT3 = (0.1, 0.0, 0.0), (0.0, 0.1, 0.2), (0.4, 0.0, 0.0)
+
+
+def golden_occ(golden, name):
+    g = np.load(os.path.join(golden, "df_golden.npz"))
+    dims = tuple(int(v) for v in g[name + "_dims"])
+    occ = np.unpackbits(g[name + "_occ_bits"])[: dims[0] * dims[1] * dims[2]].reshape(dims).astype(bool)
+    return g[name + "_header"], dims, occ
+
+
+def small():
+    return PropagationDistanceField(WIDTH, HEIGHT, DEPTH, RESOLUTION, 0, 0, 0, MAX_DIST)
+
+
+def check_distance_field(df, points):
+    """checkDistanceField (test_distance_field.cpp:294-337): every d2==0 cell is one of `points`."""
+    idx = {df.world_to_grid(*p)[0] for p in points}
+    for c in np.argwhere(df.d2() == 0):
+        assert tuple(int(v) for v in c) in idx
+
+
+def test_voxel_grid_dims():
+    # test_voxel_grid.cpp:48-57: VoxelGrid(0.02^3 @ 0.01) has 2x2x2 cells
+    f = PropagationDistanceField(0.02, 0.02, 0.02, 0.01, 0, 0, 0, 0.01)
+    assert f.num_cells == (2, 2, 2)
+    # test_distance_field.cpp:344-351 and PERF sizes :62-70
+    assert small().num_cells == (10, 10, 10) and small().max_distance_sq == 9
+    big = PropagationDistanceField(3.0, 3.0, 4.0, 0.02, 0, 0, 0, 0.25)
+    assert big.num_cells == (150, 150, 200) and big.max_distance_sq == 169
+
+
+def test_out_of_bounds_query():
+    # test_distance_field.cpp:353-358
+    df = small()
+    assert abs(df.get_distance(1000.0, 1000.0, 1000.0) - MAX_DIST) < 1e-4
+    d, g, inb = df.get_distance_gradient(1000.0, 1000.0, 1000.0)
+    assert abs(d - MAX_DIST) < 1e-4 and not inb and not g.any()
+
+
+def test_add_update_remove_points():
+    # test_distance_field.cpp:360-386
+    df = small()
+    df.add_points([POINT1, POINT2])
+    df.update_points([POINT1], [POINT2, POINT3])
+    check_distance_field(df, [POINT2, POINT3])
+    assert (df.d2() == 0).sum() == 2
+    df.remove_points([POINT2])
+    check_distance_field(df, [POINT3])
+    assert (df.d2() == 0).sum() == 1
+    # removal == fresh build without that point (test_distance_field.cpp:508 asserts this for the signed field)
+    fresh = small()
+    fresh.add_points([POINT3])
+    assert np.array_equal(fresh.d2(), df.d2())
+
+
+def test_gradient_points_to_obstacle():
+    # test_distance_field.cpp:388-438
+    df = small()
+    df.add_points([POINT1])
+    n = df.num_cells
+    seen = False
+    for z in range(1, n[2] - 1):
+        for x in range(1, n[0] - 1):
+            for y in range(1, n[1] - 1):
+                dist = df.get_cell_distance(x, y, z)
+                w = df.grid_to_world(x, y, z)
+                dg, grad, inb = df.get_distance_gradient(*w)
+                assert inb
+                assert abs(dist - dg) < 1e-4
+                if 0 < dist < MAX_DIST:
+                    seen = True
+                    comp = w - grad / np.linalg.norm(grad) * dist
+                    assert np.all(np.abs(comp - np.array(POINT1)) <= RESOLUTION + 1e-12)
+    assert seen
+
+
+def test_small_df_golden(golden):
+    # TestReadWrite (test_distance_field.cpp:937-955): test_small.df holds exactly the voxels of POINT1-3
+    hdr, dims, occ = golden_occ(golden, "test_small")
+    assert dims == (10, 10, 10) and occ.sum() == 3
+    df = small()
+    df.add_points([POINT1, POINT2, POINT3])
+    assert np.array_equal(df.d2() == 0, occ)
+    # reading the file back == building from points (areDistanceFieldsDistancesEqual, :950-951)
+    df2 = small()
+    df2.add_voxels(np.argwhere(occ))
+    assert np.array_equal(df.d2(), df2.d2())
+
+
+def test_big_df_golden(golden):
+    # test_big.df = addShapeToField(sphere r=.5 @ (.5,.5,.5)) in a 150x150x200 grid (:957-963).  Pins
+    # findInternalPointsConvex + Sphere::containsPoint + worldToGrid: 65 126 voxels, symmetric difference 0.
+    hdr, dims, occ = golden_occ(golden, "test_big")
+    assert dims == (150, 150, 200) and occ.sum() == 65126
+    pts = find_internal_points_sphere((0.5, 0.5, 0.5), 0.5, 0.02)
+    df = PropagationDistanceField(3.0, 3.0, 4.0, 0.02, 0, 0, 0, 0.25)
+    df.add_points(pts)
+    d2 = df.d2()
+    assert np.array_equal(d2 == 0, occ)
+    # distances equal whether built from points or from the file's voxel list (:966-969)
+    df2 = PropagationDistanceField(3.0, 3.0, 4.0, 0.02, 0, 0, 0, 0.25)
+    df2.add_voxels(np.argwhere(occ))
+    assert np.array_equal(d2, df2.d2())
+    # a different max distance gives a different field (:976-979)
+    df3 = PropagationDistanceField(3.0, 3.0, 4.0, 0.02, 0, 0, 0, 0.27)
+    df3.add_voxels(np.argwhere(occ))
+    assert not np.array_equal(d2, df3.d2())
+    # sanity against the definition: min(true d2, max_d2) for a sample of voxels
+    rng = np.random.default_rng(0)
+    occ_idx = np.argwhere(occ)
+    for c in rng.integers(0, [150, 150, 200], size=(200, 3)):
+        true = int(((occ_idx - c) ** 2).sum(axis=1).min())
+        assert d2[tuple(c)] >= min(true, 169)  # the reference never under-estimates
+        assert d2[tuple(c)] <= 169
+
+
+def test_df_stream_roundtrip(golden):
+    hdr, dims, occ = golden_occ(golden, "test_small")
+    keys = ("resolution", "size_x", "size_y", "size_z", "origin_x", "origin_y", "origin_z")
+    raw = write_df_occupancy(dict(zip(keys, hdr)), occ)
+    h2, n2, idx = read_df_occupancy(raw)
+    assert n2 == list(dims) and np.array_equal(idx, np.argwhere(occ))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/moveit_core/test_big.df"), reason="reference tree absent")
+def test_golden_npz_matches_reference_files(golden):
+    for name in ("test_small", "test_big"):
+        _, n, idx = read_df_occupancy(open("/root/reference/moveit_core/%s.df" % name, "rb").read())
+        _, dims, occ = golden_occ(golden, name)
+        assert list(dims) == n and np.array_equal(np.argwhere(occ), idx)
+
+
+def test_propagation_matches_exact_edt_dense():
+    """Dense clouds: the reference's vector propagation equals the exact truncated EDT."""
+    from scipy import ndimage
+    rng = np.random.default_rng(7)
+    df = PropagationDistanceField(0.4, 0.4, 0.4, 0.01, 0, 0, 0, 0.13)
+    pts = rng.uniform(0, 0.4, size=(10000, 3))
+    df.add_points(pts)
+    d2 = df.d2()
+    exact = ndimage.distance_transform_edt(d2 != 0) ** 2
+    exact = np.minimum(np.rint(exact).astype(np.int64), df.max_distance_sq)
+    assert (d2 >= exact).all()
+    assert (d2 != exact).sum() <= 2
