@@ -1,0 +1,207 @@
+/*
+ * b200sv -- B200-native batched state-validity engine: the C-ABI drop-in boundary.
+ *
+ * libb200sv.so replaces ONE path of MoveIt 2 (reference paths relative to moveit_core/):
+ *   RobotState::setJointGroupPositions + updateLinkTransforms        robot_state/src/robot_state.cpp:571-584, 793-848
+ *   CollisionEnvDistanceField::checkSelfCollision / checkRobotCollision / checkCollision
+ *                                                                    collision_distance_field/src/collision_env_distance_field.cpp:235-272, 1382-1500
+ *   PropagationDistanceField::addPointsToField / removePointsFromField / reset
+ *                                                                    distance_field/src/propagation_distance_field.cpp:177-219, 506-524
+ * A MoveIt-side CollisionEnv subclass (moveit2_b200/adapter/) binds exactly these entry points; INTEGRATION.md
+ * shows the binding.  Plain C types only: no STL, Eigen or torch types cross this boundary.
+ *
+ * Conventions
+ *   - All matrices are 4x4 column-major doubles, the memory layout of Eigen::Isometry3d.
+ *   - Link order is the RobotModel link index (DFS pre-order, RobotModel::getLinkModels()).
+ *   - A state is the JointModelGroup's variable vector, exactly what RobotState::setJointGroupPositions(group,
+ *     const double*) takes: the group's joints sorted by joint index, each joint's variables in declaration
+ *     order, mimic-joint slots present but overwritten (joint_model_group.cpp:127-171, robot_state.cpp:210-220).
+ *   - Every function returns B200SV_OK (0) or a negative error; b200sv_last_error() has the message.  There is no
+ *     CPU fallback: without a usable CUDA device creation fails with B200SV_ERR_NO_DEVICE.
+ *   - Calls on one context are serialised by an internal mutex; separate contexts are independent.
+ */
+#ifndef B200SV_H
+#define B200SV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SV_OK 0
+#define B200SV_ERR_INVALID (-1)     /* bad argument / inconsistent model */
+#define B200SV_ERR_CUDA (-2)        /* a CUDA call failed */
+#define B200SV_ERR_UNSUPPORTED (-3) /* valid in the reference, not implemented here (signed fields, ...) */
+#define B200SV_ERR_NO_DEVICE (-4)   /* no CUDA device: the product path never falls back to the CPU */
+#define B200SV_ERR_PARSE (-5)       /* URDF / SRDF text could not be parsed */
+
+/* device ordinal for a HOST-ONLY context: the model is parsed and the lookup tables are built so they can be
+ * inspected (b200sv_get_*), but every compute entry point returns B200SV_ERR_NO_DEVICE. */
+#define B200SV_DEVICE_NONE (-1)
+
+typedef struct b200sv_ctx b200sv_ctx;
+
+/* moveit::core::JointModel::JointType, the subset with a computeTransform (robot_model/src/{revolute,prismatic,planar,floating,fixed}_joint_model.cpp) */
+enum
+{
+  B200SV_JOINT_FIXED = 0,
+  B200SV_JOINT_REVOLUTE = 1, /* also URDF "continuous" */
+  B200SV_JOINT_PRISMATIC = 2,
+  B200SV_JOINT_PLANAR = 3,
+  B200SV_JOINT_FLOATING = 4
+};
+
+/* Flat view of moveit::core::RobotModel + one JointModelGroup + the RobotState that supplies every variable the
+ * group does not own.  Arrays are indexed by link index; entry i describes link i and its parent joint. */
+typedef struct b200sv_robot
+{
+  int32_t n_links;              /* RobotModel::getLinkModelCount() */
+  int32_t n_vars;               /* RobotModel::getVariableCount() */
+  const int32_t* parent;        /* LinkModel::getParentLinkModel()->getLinkIndex(), -1 for the root link */
+  const int32_t* joint_type;    /* type of LinkModel::getParentJointModel() */
+  const double* joint_axis;     /* [n_links*3] RevoluteJointModel/PrismaticJointModel::getAxis() (revolute: normalised) */
+  const double* joint_origin;   /* [n_links*16] LinkModel::getJointOriginTransform(), column-major */
+  const int32_t* first_var;     /* JointModel::getFirstVariableIndex() of the parent joint */
+  const double* base_positions; /* [n_vars] RobotState::getVariablePositions() for everything outside the group */
+  int32_t n_group_vars;         /* JointModelGroup::getVariableCount() */
+  const int32_t* group_var_index; /* [n_group_vars] JointModelGroup::getVariableIndexList() */
+  int32_t n_mimic;              /* JointModelGroup::getMimicJointModels().size() */
+  const int32_t* mimic_dst;     /* first variable index of each group mimic joint */
+  const int32_t* mimic_src;     /* first variable index of the joint it mimics */
+  const double* mimic_factor;   /* JointModel::getMimicFactor() */
+  const double* mimic_offset;   /* JointModel::getMimicOffset() */
+} b200sv_robot;
+
+/* Flat view of DistanceFieldCacheEntry + the BodyDecompositions of the group's updated links
+ * (collision_distance_field/include/moveit/collision_distance_field/collision_common_distance_field.hpp:89-124,
+ *  collision_env_distance_field.cpp:735-838). */
+typedef struct b200sv_collision_model
+{
+  int32_t n_glinks;             /* dfce->link_names_.size() = group->getUpdatedLinkModelNames() */
+  const int32_t* glink_index;   /* model link index of each */
+  const uint8_t* self_enabled;  /* dfce->self_collision_enabled_ [n_glinks] */
+  const uint8_t* intra_enabled; /* dfce->intra_group_collision_enabled_ [n_glinks*n_glinks]; only j > i is read */
+  const int32_t* sphere_start;  /* [n_glinks+1] range of each link's collision spheres; empty range = no geometry */
+  const double* sphere_xyzr;    /* [n_spheres*4] CollisionSphere::relative_vec_ (link frame) and radius_ */
+  const double* bounding_sphere; /* [n_glinks*4] BodyDecomposition::getRelativeBoundingSphere() centre, radius */
+} b200sv_collision_model;
+
+/* Constructor arguments of CollisionEnvDistanceField (collision_env_distance_field.hpp:49-84): the world and the
+ * self field share this geometry; the grid corner is origin - size/2 (collision_env_distance_field.cpp:1786-1787). */
+typedef struct b200sv_field_cfg
+{
+  double size[3];
+  double origin[3];
+  double resolution;
+  double max_propagation_distance;
+  double collision_tolerance;
+  int32_t use_signed_distance_field; /* must be 0 (reference default); 1 returns B200SV_ERR_UNSUPPORTED */
+} b200sv_field_cfg;
+
+typedef struct b200sv_info
+{
+  int32_t n_links, n_vars, n_group_vars, n_glinks, n_spheres, n_link_pairs;
+  int32_t num_cells[3]; /* VoxelGrid::getNumCells */
+  int32_t max_distance_sq;
+  int32_t device;
+  int32_t field_bytes_per_voxel; /* compact field the check kernel gathers from: 1 or 2 */
+  int32_t sm_count;
+} b200sv_info;
+
+typedef struct b200sv_stats
+{
+  uint64_t n_states;    /* states in the last check call */
+  uint64_t n_valid;     /* collision-free states */
+  uint64_t n_rechecked; /* states the FP32 pass could not decide and the FP64 pass recomputed */
+  float check_ms;       /* device time of the last check call's kernels (CUDA events) */
+  float edt_ms;         /* device time of the last field rebuild */
+} b200sv_stats;
+
+enum { B200SV_FIELD_WORLD = 0, B200SV_FIELD_SELF = 1 };
+
+/* flags of b200sv_check_batch */
+#define B200SV_CHECK_WORLD 1u /* getEnvironmentCollisions  (checkRobotCollision) */
+#define B200SV_CHECK_SELF 2u  /* getSelfCollisions         (checkSelfCollision, field part) */
+#define B200SV_CHECK_INTRA 4u /* getIntraGroupCollisions   (checkSelfCollision, sphere pairs) */
+#define B200SV_CHECK_ALL 7u   /* PlanningScene::checkCollision */
+#define B200SV_CHECK_FP64 256u /* run every state through the FP64 kernel (default: FP32 pass + FP64 recheck of
+                                  the states whose result could depend on FP32 rounding) */
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+/* Replaces the CollisionEnvDistanceField constructor (collision_env_distance_field.cpp:59-96). */
+int b200sv_create(int device, const b200sv_robot* robot, const b200sv_collision_model* model,
+                  const b200sv_field_cfg* field, b200sv_ctx** out);
+/* Same, from URDF + SRDF text, for hosts without a RobotModel (tests, bench): restates RobotModel construction
+ * (robot_model/src/robot_model.cpp:848-890, 1173-1254; joint_model_group.cpp:114-300), the SRDF-derived ACM
+ * (collision_detection/src/collision_matrix.cpp:67-78) and, for SPHERE collision geometry, BodyDecomposition
+ * (collision_distance_field_types.cpp:59-85, 292-335).  The self field is built from the non-group links as
+ * generateDistanceFieldCacheEntry does (collision_env_distance_field.cpp:907-953). */
+int b200sv_create_from_urdf(int device, const char* urdf_xml, const char* srdf_xml, const char* group_name,
+                            const b200sv_field_cfg* field, b200sv_ctx** out);
+void b200sv_destroy(b200sv_ctx* ctx);
+/* ctx == NULL returns the message of the last failed create on this thread. */
+const char* b200sv_last_error(const b200sv_ctx* ctx);
+int b200sv_get_info(const b200sv_ctx* ctx, b200sv_info* info);
+int b200sv_get_stats(b200sv_ctx* ctx, b200sv_stats* stats);
+/* Flat model accessors for the URDF path (so a caller can cross-check against its own RobotModel). Arrays may be
+ * NULL to skip. link_names: '\n'-joined, written into buf (cap bytes). */
+int b200sv_get_robot_arrays(const b200sv_ctx* ctx, int32_t* parent, int32_t* joint_type, double* joint_axis,
+                            double* joint_origin, int32_t* first_var, double* base_positions,
+                            int32_t* group_var_index);
+int b200sv_get_model_arrays(const b200sv_ctx* ctx, int32_t* glink_index, uint8_t* self_enabled,
+                            uint8_t* intra_enabled, int32_t* sphere_start, double* sphere_xyzr,
+                            double* bounding_sphere);
+int b200sv_get_link_names(const b200sv_ctx* ctx, char* buf, size_t cap);
+/* Variable bounds of the group, as RobotState::setToRandomPositions(group) samples them. */
+int b200sv_get_group_bounds(const b200sv_ctx* ctx, double* lower, double* upper);
+/* Integer collision thresholds the check kernel compares voxel d^2 against, one per sphere (dfce order):
+ * collide iff d2 < threshold -- the exact integer form of collision_distance_field_types.cpp:229. */
+int b200sv_get_sphere_thresholds(const b200sv_ctx* ctx, int32_t* thresholds);
+
+/* ---- distance fields: PropagationDistanceField (distance_field/src/propagation_distance_field.cpp) -------- */
+/* reset(): :506-524 */
+int b200sv_field_reset(b200sv_ctx* ctx, int which);
+/* addPointsToField(): :177-196 + propagatePositive :390-444, as ONE parallel exact truncated EDT.  xyz: host. */
+int b200sv_field_add_points(b200sv_ctx* ctx, int which, const double* xyz, size_t n_points);
+/* removePointsFromField(): :198-219 (result equals a fresh build without those voxels, test_distance_field.cpp:508) */
+int b200sv_field_remove_points(b200sv_ctx* ctx, int which, const double* xyz, size_t n_points);
+/* Same two with xyz already in device memory, asynchronous on `cuda_stream` (a cudaStream_t). */
+int b200sv_field_add_points_device(b200sv_ctx* ctx, int which, const double* d_xyz, size_t n_points,
+                                   void* cuda_stream);
+/* int32 squared cell distances, [nx*ny*nz], index x*ny*nz + y*nz + z (voxel_grid.hpp:425); host buffers. */
+int b200sv_field_get_d2(b200sv_ctx* ctx, int which, int32_t* d2_out);
+/* Inject an externally built field (e.g. the reference's own propagation result) so check parity can be tested
+ * independently of EDT parity. */
+int b200sv_field_set_d2(b200sv_ctx* ctx, int which, const int32_t* d2);
+/* The self field's generating points (URDF path only): n_out receives the count; xyz may be NULL. */
+int b200sv_get_self_points(const b200sv_ctx* ctx, double* xyz, size_t cap_points, size_t* n_out);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------ */
+/* Batched RobotState::setJointGroupPositions + updateLinkTransforms: q [n*n_group_vars] (host) ->
+ * link_T [n*n_links*16] (host), global link transforms, column-major.  precision_bits: 32 or 64. */
+int b200sv_fk_batch(b200sv_ctx* ctx, const double* q, size_t n_states, int precision_bits, double* link_T);
+/* Batched PlanningScene::checkCollision over n group-state vectors.  valid_bitmap: ceil(n/8) bytes (host),
+ * bit (i % 8) of byte (i / 8) is 1 iff state i is collision-free under the selected checks.
+ * Timed region of the end-to-end benchmark: H2D of q, kernels, D2H of the bitmap. */
+int b200sv_check_batch(b200sv_ctx* ctx, const double* q, size_t n_states, uint32_t flags, uint8_t* valid_bitmap);
+/* Same with q and the bitmap resident in device memory; asynchronous on `cuda_stream`.
+ * d_valid_bitmap must hold 4*ceil(n/32) bytes (whole 32-bit words are written). */
+int b200sv_check_batch_device(b200sv_ctx* ctx, const double* d_q, size_t n_states, uint32_t flags,
+                              uint8_t* d_valid_bitmap, void* cuda_stream);
+/* Posed collision-sphere centres of ONE state, FP64 kernel: [n_spheres*3] (host).  Parity hook for
+ * PosedBodySphereDecomposition::updatePose (collision_distance_field_types.cpp:388-395). */
+int b200sv_sphere_centers(b200sv_ctx* ctx, const double* q_one, double* centers);
+
+/* ---- measurement helpers ------------------------------------------------------------------------------------ */
+/* Random 32-byte-sector gather over the world field's footprint: the "gather-bandwidth roofline" the check
+ * kernel is compared against.  Reports sectors/s * 32 B as GB/s. */
+int b200sv_gather_roofline(b200sv_ctx* ctx, size_t n_reads, int iters, double* gbytes_per_s);
+/* Tuning knobs (0 keeps the default): FP32 sphere-centre error bound in metres, warps per block, blocks per SM. */
+int b200sv_set_tuning(b200sv_ctx* ctx, double fp32_eps_m, int warps_per_block, int blocks_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SV_H */

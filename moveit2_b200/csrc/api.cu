@@ -1,0 +1,1193 @@
+// The C-ABI of libb200sv.so (include/b200sv.h): context, device tables, field management, batch entry points.
+// Host logic only -- kernels live in check_kernels.cu and edt_kernels.cu.  There is no CPU compute path here:
+// every entry point either runs on the CUDA device or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sv.h"
+#include "device_model.hpp"
+#include "host_model.hpp"
+#include "kernels.hpp"
+
+using namespace b200sv;
+
+namespace
+{
+thread_local std::string g_create_error;
+
+struct Field
+{
+  uint32_t* occ = nullptr;    // occupancy bits
+  uint16_t* d2 = nullptr;     // min(d^2, max_d2)
+  void* compact = nullptr;    // what the check kernel gathers (uint8 clamp, or == d2)
+  bool dirty = false;
+};
+
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n)
+  {
+    if (n <= cap)
+      return cudaSuccess;
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max<size_t>(n, 1024);
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess)
+      cap = want;
+    return e;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+}  // namespace
+
+struct b200sv_ctx
+{
+  int device = 0;
+  std::mutex mu;
+  mutable std::string err;
+  HostRobot robot;
+  HostCollisionModel cm;
+  b200sv_field_cfg cfg{};
+  std::vector<double> self_points;
+  // grid
+  GridDev grid{};
+  int compact_bytes = 1;
+  size_t n_voxels = 0;
+  // device tables
+  std::vector<uint8_t> blob_f, blob_d;
+  uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr;
+  int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0;
+  int state_stride = 0;
+  std::vector<int> link_slot;      // model link -> device slot
+  std::vector<double> const_T;     // model links * 16 (base state)
+  int* d_link_slot = nullptr;
+  double* d_const_T = nullptr;
+  Field fields[2];
+  uint16_t* d_tmp = nullptr;  // EDT intermediate
+  // launch config
+  int sm_count = 148, smem_optin = 0;
+  int warps_f = 0, warps_d = 0, blocks_per_sm = 1;
+  double fp32_eps = 4e-6;
+  int tune_warps = 0;
+  // streams / staging
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf<double> d_q;
+  DevBuf<uint32_t> d_bitmap, d_list;
+  DevBuf<double> d_points;
+  DevBuf<double> d_fk;
+  DevBuf<int32_t> d_i32;
+  unsigned* d_count = nullptr;
+  unsigned* d_sink = nullptr;
+  b200sv_stats stats{};
+  bool stats_pending = false;
+};
+
+namespace
+{
+int fail(b200sv_ctx* c, int code, const std::string& msg)
+{
+  if (c)
+    c->err = msg;
+  else
+    g_create_error = msg;
+  return code;
+}
+
+// Compute entry points call this first: a host-only context has no device and there is no CPU path to fall back to.
+int needDevice(b200sv_ctx* c)
+{
+  if (c->device < 0)
+    return fail(c, B200SV_ERR_NO_DEVICE, "host-only context (B200SV_DEVICE_NONE): no CUDA device, and no CPU fallback exists");
+  return B200SV_OK;
+}
+
+#define CU(ctx, expr)                                                                                              \
+  do                                                                                                               \
+  {                                                                                                                \
+    cudaError_t e__ = (expr);                                                                                      \
+    if (e__ != cudaSuccess)                                                                                        \
+      return fail(ctx, B200SV_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                      \
+  } while (0)
+
+inline int align16(int x) { return (x + 15) & ~15; }
+
+// Integer form of the reference predicate (collision_distance_field_types.cpp:229):
+//   collide = (maximum_value > dist) && (radius - dist > tolerance),  dist = sqrt_table[d2] (unsigned field)
+// with sqrt_table[i] = sqrt(double(i)) * resolution (propagation_distance_field.cpp:99-101).  dist grows with d2,
+// so the predicate is true exactly for d2 < T.  T in [0, max_d2 + 1].
+int sphereThreshold(double radius, double res, double max_prop, double tol, int max_d2)
+{
+  for (int i = 0; i <= max_d2; ++i)
+  {
+    const double dist = sqrt(double(i)) * res - sqrt(double(0)) * res;  // getDistance(): sqrt_table[d2] - sqrt_table[neg d2 = 0]
+    if (!((max_prop > dist) && (radius - dist > tol)))
+      return i;
+  }
+  return max_d2 + 1;
+}
+
+template <typename R>
+void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, const std::vector<VarRec>& vars,
+               const std::vector<SphereRec<double>>& spheres, const std::vector<BsRec<double>>& bs,
+               const std::vector<PairRec>& pairs, double margin, double pair_eps, double bs_eps, std::vector<uint8_t>& out)
+{
+  ModelHeader<R> h{};
+  h.n_links = (int)links.size();
+  h.n_vars = (int)vars.size();
+  h.n_spheres = (int)spheres.size();
+  h.n_bs = (int)bs.size();
+  h.n_pairs = (int)pairs.size();
+  h.n_group_vars = (int)c.robot.group_var_index.size();
+  int off = align16(sizeof(ModelHeader<R>));
+  h.off_links = off;
+  off = align16(off + (int)(links.size() * sizeof(LinkRec<R>)));
+  h.off_vars = off;
+  off = align16(off + (int)(vars.size() * sizeof(VarRec)));
+  h.off_spheres = off;
+  off = align16(off + (int)(spheres.size() * sizeof(SphereRec<R>)));
+  h.off_bs = off;
+  off = align16(off + (int)(bs.size() * sizeof(BsRec<R>)));
+  h.off_pairs = off;
+  off = align16(off + (int)(pairs.size() * sizeof(PairRec)));
+  h.total_bytes = off;
+  h.state_stride = c.state_stride;
+  h.link_stride = kLinkStrideWords;
+  h.nx = c.grid.nx;
+  h.ny = c.grid.ny;
+  h.nz = c.grid.nz;
+  for (int k = 0; k < 3; ++k)
+    h.om[k] = (R)c.grid.om[k];
+  h.oo_res = (R)c.grid.oo;
+  h.margin = (R)margin;
+  h.pair_eps = (R)pair_eps;
+  h.bs_eps = (R)bs_eps;
+  out.assign(off, 0);
+  memcpy(out.data(), &h, sizeof(h));
+  auto* L = reinterpret_cast<LinkRec<R>*>(out.data() + h.off_links);
+  for (size_t i = 0; i < links.size(); ++i)
+  {
+    for (int k = 0; k < 12; ++k)
+      L[i].o[k] = (R)links[i].o[k];
+    for (int k = 0; k < 3; ++k)
+      L[i].ax[k] = (R)links[i].ax[k];
+    L[i].parent = links[i].parent;
+    L[i].type = links[i].type;
+    L[i].var = links[i].var;
+    L[i].has_origin = links[i].has_origin;
+  }
+  if (!vars.empty())
+    memcpy(out.data() + h.off_vars, vars.data(), vars.size() * sizeof(VarRec));
+  auto* S = reinterpret_cast<SphereRec<R>*>(out.data() + h.off_spheres);
+  for (size_t i = 0; i < spheres.size(); ++i)
+  {
+    S[i].x = (R)spheres[i].x;
+    S[i].y = (R)spheres[i].y;
+    S[i].z = (R)spheres[i].z;
+    S[i].r = (R)spheres[i].r;
+    S[i].slot = spheres[i].slot;
+    S[i].thr = spheres[i].thr;
+    S[i].thr_self = spheres[i].thr_self;
+  }
+  auto* B = reinterpret_cast<BsRec<R>*>(out.data() + h.off_bs);
+  for (size_t i = 0; i < bs.size(); ++i)
+  {
+    B[i].x = (R)bs[i].x;
+    B[i].y = (R)bs[i].y;
+    B[i].z = (R)bs[i].z;
+    B[i].r = (R)bs[i].r;
+    B[i].slot = bs[i].slot;
+    B[i].s0 = bs[i].s0;
+    B[i].s1 = bs[i].s1;
+  }
+  if (!pairs.empty())
+    memcpy(out.data() + h.off_pairs, pairs.data(), pairs.size() * sizeof(PairRec));
+}
+
+// column-major 4x4 -> row-major 3x4
+void toRow34(const Mat4& m, double* o)
+{
+  for (int r = 0; r < 3; ++r)
+    for (int col = 0; col < 4; ++col)
+      o[r * 4 + col] = m[col * 4 + r];
+}
+
+int validateModel(b200sv_ctx* c)
+{
+  const HostRobot& r = c->robot;
+  const HostCollisionModel& m = c->cm;
+  if (r.n_links <= 0 || r.n_vars < 0)
+    return fail(c, B200SV_ERR_INVALID, "robot has no links");
+  for (int l = 0; l < r.n_links; ++l)
+  {
+    if (r.parent[l] >= l)
+      return fail(c, B200SV_ERR_INVALID, "links must be in DFS order: parent index must be smaller than the link's");
+    if (r.joint_type[l] < FIXED || r.joint_type[l] > FLOATING)
+      return fail(c, B200SV_ERR_INVALID, "unknown joint type");
+    const int nv = jointVarCount(r.joint_type[l]);
+    if (nv && (r.first_var[l] < 0 || r.first_var[l] + nv > r.n_vars))
+      return fail(c, B200SV_ERR_INVALID, "joint variable index out of range");
+  }
+  for (int v : r.group_var_index)
+    if (v < 0 || v >= r.n_vars)
+      return fail(c, B200SV_ERR_INVALID, "group variable index out of range");
+  if (r.group_var_index.empty())
+    return fail(c, B200SV_ERR_INVALID, "the group has no variables");
+  for (size_t i = 0; i < r.mimic_dst.size(); ++i)
+    if (r.mimic_dst[i] < 0 || r.mimic_dst[i] >= r.n_vars || r.mimic_src[i] < 0 || r.mimic_src[i] >= r.n_vars)
+      return fail(c, B200SV_ERR_INVALID, "mimic variable index out of range");
+  if ((int)m.sphere_start.size() != m.n_glinks + 1)
+    return fail(c, B200SV_ERR_INVALID, "sphere_start must have n_glinks + 1 entries");
+  for (int i = 0; i < m.n_glinks; ++i)
+  {
+    if (m.glink_index[i] < 0 || m.glink_index[i] >= r.n_links)
+      return fail(c, B200SV_ERR_INVALID, "glink_index out of range");
+    if (m.sphere_start[i + 1] < m.sphere_start[i])
+      return fail(c, B200SV_ERR_INVALID, "sphere_start must be non-decreasing");
+  }
+  return B200SV_OK;
+}
+
+int buildTables(b200sv_ctx* c)
+{
+  const HostRobot& r = c->robot;
+  const HostCollisionModel& m = c->cm;
+  // ---- variable map: setJointGroupPositions then updateMimicJoints(group) ----------------------------------
+  std::vector<VarRec> vmap(r.n_vars);
+  for (int v = 0; v < r.n_vars; ++v)
+    vmap[v] = VarRec{ 0.0, r.base_positions[v], -1, 0 };
+  for (size_t i = 0; i < r.group_var_index.size(); ++i)
+    vmap[r.group_var_index[i]] = VarRec{ 1.0, 0.0, (int)i, 0 };
+  for (size_t i = 0; i < r.mimic_dst.size(); ++i)
+  {
+    const VarRec s = vmap[r.mimic_src[i]];
+    VarRec d;
+    d.pad = 0;
+    if (s.k >= 0)
+    {  // factor * (a q + b) + offset; a == 1, b == 0 for a group variable, so this is factor * q + offset exactly
+      d.k = s.k;
+      d.a = r.mimic_factor[i] * s.a;
+      d.b = r.mimic_factor[i] * s.b + r.mimic_offset[i];
+    }
+    else
+    {
+      d.k = -1;
+      d.a = 0.0;
+      d.b = r.mimic_factor[i] * s.b + r.mimic_offset[i];
+    }
+    vmap[r.mimic_dst[i]] = d;
+  }
+  // positions of the base state after the same update (mimic joints of the group follow their sources)
+  std::vector<double> base = r.base_positions;
+  for (size_t i = 0; i < r.mimic_dst.size(); ++i)
+    if (vmap[r.mimic_dst[i]].k < 0)
+      base[r.mimic_dst[i]] = vmap[r.mimic_dst[i]].b;
+  std::vector<Mat4> T0;
+  hostForwardKinematics(r, base, T0);
+  c->const_T.resize((size_t)r.n_links * 16);
+  for (int l = 0; l < r.n_links; ++l)
+    std::copy(T0[l].begin(), T0[l].end(), c->const_T.begin() + 16 * l);
+  // ---- which links move with the group ------------------------------------------------------------------------
+  std::vector<char> dynamic(r.n_links, 0), needed(r.n_links, 0);
+  for (int l = 0; l < r.n_links; ++l)
+  {
+    bool dyn = r.parent[l] >= 0 && dynamic[r.parent[l]];
+    const int nv = jointVarCount(r.joint_type[l]);
+    for (int k = 0; k < nv; ++k)
+      dyn |= vmap[r.first_var[l] + k].k >= 0;
+    dynamic[l] = dyn;
+  }
+  for (int i = 0; i < m.n_glinks; ++i)
+    if (m.sphere_start[i + 1] > m.sphere_start[i])
+      needed[m.glink_index[i]] = 1;
+  c->link_slot.assign(r.n_links, -1);
+  std::vector<LinkRec<double>> links;
+  std::vector<VarRec> vars;
+  for (int l = 0; l < r.n_links; ++l)
+  {
+    if (!dynamic[l] && !needed[l])
+      continue;
+    LinkRec<double> L{};
+    Mat4 origin;
+    std::copy(r.joint_origin.begin() + 16 * l, r.joint_origin.begin() + 16 * (l + 1), origin.begin());
+    L.var = (int)vars.size();
+    L.pad = 0;
+    for (int k = 0; k < 3; ++k)
+      L.ax[k] = r.joint_axis[3 * l + k];
+    if (!dynamic[l])
+    {  // a checked link that does not move: its base-state transform, as a fixed root
+      toRow34(T0[l], L.o);
+      L.parent = -1;
+      L.type = FIXED;
+      L.has_origin = 1;
+    }
+    else
+    {
+      L.type = r.joint_type[l];
+      const int nv = jointVarCount(L.type);
+      for (int k = 0; k < nv; ++k)
+        vars.push_back(vmap[r.first_var[l] + k]);
+      const int p = r.parent[l];
+      if (p >= 0 && c->link_slot[p] >= 0 && dynamic[p])
+      {
+        L.parent = c->link_slot[p];
+        toRow34(origin, L.o);
+        L.has_origin = isIdentityTransform(origin.data()) ? 0 : 1;
+      }
+      else
+      {  // parent does not move: fold its base-state transform into the origin (same product order as the reference)
+        L.parent = -1;
+        Mat4 g = p >= 0 ? mulAffine(T0[p], origin) : origin;
+        if (p >= 0 && isIdentityTransform(origin.data()))
+          g = T0[p];
+        toRow34(g, L.o);
+        L.has_origin = 1;
+      }
+    }
+    c->link_slot[l] = (int)links.size();
+    links.push_back(L);
+  }
+  c->n_dev_links = (int)links.size();
+  if (links.empty())
+    return fail(c, B200SV_ERR_INVALID, "no link moves with the group and none carries spheres");
+  c->state_stride = c->n_dev_links * kLinkStrideWords;
+  if ((c->state_stride & 1) == 0)
+    c->state_stride += 1;
+  // ---- spheres, bounding spheres, pairs -----------------------------------------------------------------------------
+  std::vector<SphereRec<double>> spheres;
+  std::vector<BsRec<double>> bs;
+  std::vector<int> bs_of_glink(m.n_glinks, -1);
+  int max_thr = 0;
+  for (int i = 0; i < m.n_glinks; ++i)
+  {
+    const int a = m.sphere_start[i], b = m.sphere_start[i + 1];
+    if (b <= a)
+      continue;
+    const int slot = c->link_slot[m.glink_index[i]];
+    BsRec<double> B{};
+    B.x = m.bounding_sphere[4 * i + 0];
+    B.y = m.bounding_sphere[4 * i + 1];
+    B.z = m.bounding_sphere[4 * i + 2];
+    B.r = m.bounding_sphere[4 * i + 3];
+    B.slot = slot;
+    B.s0 = (int)spheres.size();
+    for (int k = a; k < b; ++k)
+    {
+      SphereRec<double> S{};
+      S.x = m.sphere_xyzr[4 * k + 0];
+      S.y = m.sphere_xyzr[4 * k + 1];
+      S.z = m.sphere_xyzr[4 * k + 2];
+      S.r = m.sphere_xyzr[4 * k + 3];
+      S.slot = slot;
+      S.thr = sphereThreshold(S.r, c->cfg.resolution, c->cfg.max_propagation_distance, c->cfg.collision_tolerance,
+                              c->grid.max_d2);
+      S.thr_self = m.self_enabled[i] ? S.thr : 0;
+      max_thr = std::max(max_thr, S.thr);
+      spheres.push_back(S);
+    }
+    B.s1 = (int)spheres.size();
+    bs_of_glink[i] = (int)bs.size();
+    bs.push_back(B);
+  }
+  std::vector<PairRec> pairs;
+  double max_rs = 0.0;
+  for (int i = 0; i < m.n_glinks; ++i)
+    for (int j = i + 1; j < m.n_glinks; ++j)
+      if (bs_of_glink[i] >= 0 && bs_of_glink[j] >= 0 && m.intra_enabled[(size_t)i * m.n_glinks + j])
+      {
+        pairs.push_back(PairRec{ bs_of_glink[i], bs_of_glink[j] });
+        max_rs = std::max(max_rs, bs[bs_of_glink[i]].r + bs[bs_of_glink[j]].r);
+      }
+  c->n_spheres = (int)spheres.size();
+  c->n_bs = (int)bs.size();
+  c->n_pairs = (int)pairs.size();
+  c->compact_bytes = max_thr <= 255 ? 1 : 2;
+  // ---- FP32 uncertainty budget (see DESIGN.md "precision") -------------------------------------------------------------
+  const double eps = c->fp32_eps;
+  const int nmax = std::max(c->grid.nx, std::max(c->grid.ny, c->grid.nz));
+  const double margin = eps * c->grid.oo + nmax * ldexp(1.0, -22);
+  const double pair_eps = 2.0 * eps + 1e-7;
+  const double bs_eps = 4.0 * eps * (sqrt(max_rs) + 0.05) + 1e-7;
+  buildBlob<float>(*c, links, vars, spheres, bs, pairs, margin, pair_eps, bs_eps, c->blob_f);
+  buildBlob<double>(*c, links, vars, spheres, bs, pairs, 0.0, 0.0, 0.0, c->blob_d);
+  return B200SV_OK;
+}
+
+int chooseWarps(const b200sv_ctx* c, int blob_bytes, int elem, int cap)
+{
+  const int per_warp = (32 * c->state_stride + 3 * c->n_spheres + 3 * c->n_bs + 1) * elem;
+  const int avail = c->smem_optin / std::max(1, c->blocks_per_sm) - 1024 - align16(blob_bytes) - 16;
+  int w = avail / per_warp;
+  w = std::min(w, cap);
+  return w;
+}
+
+size_t smemFor(const b200sv_ctx* c, int blob_bytes, int elem, int warps)
+{
+  const size_t per_warp = (size_t)(32 * c->state_stride + 3 * c->n_spheres + 3 * c->n_bs + 1) * elem;
+  return align16(blob_bytes) + per_warp * warps + 16;
+}
+
+int uploadTables(b200sv_ctx* c)
+{
+  if (c->d_blob_f)
+    cudaFree(c->d_blob_f);
+  if (c->d_blob_d)
+    cudaFree(c->d_blob_d);
+  c->d_blob_f = c->d_blob_d = nullptr;
+  CU(c, cudaMalloc(&c->d_blob_f, c->blob_f.size()));
+  CU(c, cudaMalloc(&c->d_blob_d, c->blob_d.size()));
+  CU(c, cudaMemcpy(c->d_blob_f, c->blob_f.data(), c->blob_f.size(), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(c->d_blob_d, c->blob_d.data(), c->blob_d.size(), cudaMemcpyHostToDevice));
+  if (!c->d_link_slot)
+  {
+    CU(c, cudaMalloc(&c->d_link_slot, c->link_slot.size() * sizeof(int)));
+    CU(c, cudaMalloc(&c->d_const_T, c->const_T.size() * sizeof(double)));
+  }
+  CU(c, cudaMemcpy(c->d_link_slot, c->link_slot.data(), c->link_slot.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU(c, cudaMemcpy(c->d_const_T, c->const_T.data(), c->const_T.size() * sizeof(double), cudaMemcpyHostToDevice));
+  const int cap = c->tune_warps > 0 ? c->tune_warps : 16;
+  c->warps_f = chooseWarps(c, (int)c->blob_f.size(), 4, cap);
+  c->warps_d = chooseWarps(c, (int)c->blob_d.size(), 8, cap);
+  if (c->warps_f < 1 || c->warps_d < 1)
+    return fail(c, B200SV_ERR_UNSUPPORTED,
+                "robot too large for the shared-memory tile: " + std::to_string(c->n_dev_links) + " moving links need " +
+                    std::to_string(32 * c->state_stride * 8) + " bytes per warp");
+  return B200SV_OK;
+}
+
+int initGrid(b200sv_ctx* c)
+{
+  const b200sv_field_cfg& f = c->cfg;
+  if (!(f.resolution > 0.0) || !(f.max_propagation_distance > 0.0))
+    return fail(c, B200SV_ERR_INVALID, "resolution and max_propagation_distance must be positive");
+  if (f.use_signed_distance_field)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "signed distance fields (propagate_negative) are not implemented");
+  // corner = origin - size / 2 (collision_env_distance_field.cpp:1786-1787); VoxelGrid::resize (voxel_grid.hpp:364-396)
+  const double res = f.resolution;
+  const double oo = 1.0 / res;
+  GridDev& g = c->grid;
+  int n[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    const double corner = f.origin[k] - 0.5 * f.size[k];
+    g.om[k] = corner - 0.5 * res;
+    n[k] = (int)(f.size[k] * oo);
+    if (n[k] < 1)
+      return fail(c, B200SV_ERR_INVALID, "field has no cells along one axis");
+  }
+  g.oo = oo;
+  g.nx = n[0];
+  g.ny = n[1];
+  g.nz = n[2];
+  g.wz = (g.nz + 31) / 32;
+  const double rc = ceil(f.max_propagation_distance / res);  // propagation_distance_field.cpp:88
+  if (rc > 254.0)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "max_propagation_distance / resolution exceeds 254 cells");
+  g.R = (int)rc;
+  g.max_d2 = (int)(rc * rc);
+  c->n_voxels = (size_t)g.nx * g.ny * g.nz;
+  if (c->n_voxels >= (1ull << 31))
+    return fail(c, B200SV_ERR_UNSUPPORTED, "more than 2^31 voxels");
+  return B200SV_OK;
+}
+
+int allocFields(b200sv_ctx* c)
+{
+  const GridDev& g = c->grid;
+  const size_t occ_bytes = (size_t)g.nx * g.ny * g.wz * 4;
+  for (int w = 0; w < 2; ++w)
+  {
+    Field& F = c->fields[w];
+    CU(c, cudaMalloc(&F.occ, occ_bytes));
+    CU(c, cudaMalloc(&F.d2, c->n_voxels * 2));
+    if (c->compact_bytes == 1)
+      CU(c, cudaMalloc(&F.compact, c->n_voxels));
+    else
+      F.compact = F.d2;
+    CU(c, cudaMemsetAsync(F.occ, 0, occ_bytes, c->stream));
+    CU(c, launchFillField(g, F.d2, F.compact, c->compact_bytes, c->stream));
+  }
+  CU(c, cudaMalloc(&c->d_tmp, c->n_voxels * 2));
+  return B200SV_OK;
+}
+
+int rebuildField(b200sv_ctx* c, int which)
+{
+  Field& F = c->fields[which];
+  CU(c, cudaEventRecord(c->ev0, c->stream));
+  CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.d2, F.compact, c->compact_bytes, c->sm_count, c->stream));
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  CU(c, cudaEventSynchronize(c->ev1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->stats.edt_ms = ms;
+  return B200SV_OK;
+}
+
+int finishCreate(b200sv_ctx* c, int device, b200sv_ctx** out)
+{
+  if (device == B200SV_DEVICE_NONE)
+  {  // host-only context: model + tables for inspection; every compute entry point refuses
+    c->device = B200SV_DEVICE_NONE;
+    int rc0 = validateModel(c);
+    if (rc0 == B200SV_OK)
+      rc0 = initGrid(c);
+    if (rc0 == B200SV_OK)
+      rc0 = buildTables(c);
+    if (rc0 != B200SV_OK)
+    {
+      g_create_error = c->err;
+      delete c;
+      return rc0;
+    }
+    *out = c;
+    return B200SV_OK;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+  {
+    fail(nullptr, B200SV_ERR_NO_DEVICE,
+         std::string("no CUDA device (") + (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)) +
+             "); libb200sv has no CPU fallback");
+    cudaGetLastError();
+    delete c;
+    return B200SV_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n_dev)
+  {
+    fail(nullptr, B200SV_ERR_INVALID, "device ordinal out of range");
+    delete c;
+    return B200SV_ERR_INVALID;
+  }
+  c->device = device;
+  int rc = B200SV_OK;
+  auto bail = [&](int code) {
+    g_create_error = c->err;
+    b200sv_destroy(c);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess)
+    return bail(fail(c, B200SV_ERR_CUDA, "cudaSetDevice failed"));
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if ((rc = validateModel(c)) != B200SV_OK)
+    return bail(rc);
+  if ((rc = initGrid(c)) != B200SV_OK)
+    return bail(rc);
+  if ((rc = buildTables(c)) != B200SV_OK)
+    return bail(rc);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess)
+    return bail(fail(c, B200SV_ERR_CUDA, "stream/event creation failed"));
+  if ((rc = uploadTables(c)) != B200SV_OK)
+    return bail(rc);
+  if ((rc = allocFields(c)) != B200SV_OK)
+    return bail(rc);
+  if (cudaMalloc(&c->d_count, sizeof(unsigned)) != cudaSuccess || cudaMalloc(&c->d_sink, sizeof(unsigned)) != cudaSuccess)
+    return bail(fail(c, B200SV_ERR_CUDA, "cudaMalloc failed"));
+  cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess)
+    return bail(fail(c, B200SV_ERR_CUDA, std::string("device initialisation failed: ") + cudaGetErrorString(cudaGetLastError())));
+  *out = c;
+  return B200SV_OK;
+}
+
+int addOrRemove(b200sv_ctx* c, int which, const double* d_xyz, size_t n, bool set, cudaStream_t s)
+{
+  CU(c, launchScatter(d_xyz, n, c->grid, c->fields[which].occ, set, s));
+  return B200SV_OK;
+}
+
+template <typename FT>
+int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_t* d_bitmap, cudaStream_t s)
+{
+  CheckArgs<FT> a{};
+  a.q = d_q;
+  a.n_states = n;
+  a.world = static_cast<const FT*>(c->fields[0].compact);
+  a.self = static_cast<const FT*>(c->fields[1].compact);
+  a.flags = flags & 7u;
+  a.bitmap = d_bitmap;
+  a.flag_list = c->d_list.p;
+  a.flag_count = c->d_count;
+  a.list_cap = (unsigned)std::min<size_t>(c->d_list.cap, 0xffffffffu);
+  a.list = c->d_list.p;
+  a.list_count = c->d_count;
+  const int grid = c->sm_count * c->blocks_per_sm;
+  if (flags & B200SV_CHECK_FP64)
+  {
+    a.model = c->d_blob_d;
+    a.model_bytes = (int)c->blob_d.size();
+    CU(c, launchCheck<FT>(a, true, false, grid, c->warps_d * 32, smemFor(c, a.model_bytes, 8, c->warps_d), s));
+    return B200SV_OK;
+  }
+  CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), s));
+  a.model = c->d_blob_f;
+  a.model_bytes = (int)c->blob_f.size();
+  CU(c, launchCheck<FT>(a, false, false, grid, c->warps_f * 32, smemFor(c, a.model_bytes, 4, c->warps_f), s));
+  // exact pass over the undecided states; the count stays on the device, so the launch is unconditional
+  a.model = c->d_blob_d;
+  a.model_bytes = (int)c->blob_d.size();
+  CU(c, launchCheck<FT>(a, true, true, grid, c->warps_d * 32, smemFor(c, a.model_bytes, 8, c->warps_d), s));
+  return B200SV_OK;
+}
+
+int checkDevice(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_t* d_bitmap, cudaStream_t s)
+{
+  if ((flags & 7u) == 0)
+    return fail(c, B200SV_ERR_INVALID, "flags select no check");
+  if (n >= (1ull << 32))
+    return fail(c, B200SV_ERR_INVALID, "more than 2^32 - 1 states in one call");
+  CU(c, c->d_list.ensure(n));
+  return c->compact_bytes == 1 ? runCheck<uint8_t>(c, d_q, n, flags, d_bitmap, s) :
+                                 runCheck<uint16_t>(c, d_q, n, flags, d_bitmap, s);
+}
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int b200sv_create(int device, const b200sv_robot* robot, const b200sv_collision_model* model,
+                  const b200sv_field_cfg* field, b200sv_ctx** out)
+{
+  if (!robot || !model || !field || !out)
+    return fail(nullptr, B200SV_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (robot->n_links <= 0 || robot->n_vars < 0 || robot->n_group_vars <= 0 || model->n_glinks < 0)
+    return fail(nullptr, B200SV_ERR_INVALID, "empty robot or group");
+  auto* c = new b200sv_ctx();
+  HostRobot& r = c->robot;
+  r.n_links = robot->n_links;
+  r.n_vars = robot->n_vars;
+  r.parent.assign(robot->parent, robot->parent + r.n_links);
+  r.joint_type.assign(robot->joint_type, robot->joint_type + r.n_links);
+  r.first_var.assign(robot->first_var, robot->first_var + r.n_links);
+  r.joint_axis.assign(robot->joint_axis, robot->joint_axis + 3 * r.n_links);
+  r.joint_origin.assign(robot->joint_origin, robot->joint_origin + 16 * r.n_links);
+  r.base_positions.assign(robot->base_positions, robot->base_positions + r.n_vars);
+  r.group_var_index.assign(robot->group_var_index, robot->group_var_index + robot->n_group_vars);
+  if (robot->n_mimic > 0)
+  {
+    r.mimic_dst.assign(robot->mimic_dst, robot->mimic_dst + robot->n_mimic);
+    r.mimic_src.assign(robot->mimic_src, robot->mimic_src + robot->n_mimic);
+    r.mimic_factor.assign(robot->mimic_factor, robot->mimic_factor + robot->n_mimic);
+    r.mimic_offset.assign(robot->mimic_offset, robot->mimic_offset + robot->n_mimic);
+  }
+  HostCollisionModel& m = c->cm;
+  m.n_glinks = model->n_glinks;
+  const int n = m.n_glinks;
+  m.glink_index.assign(model->glink_index, model->glink_index + n);
+  m.self_enabled.assign(model->self_enabled, model->self_enabled + n);
+  m.intra_enabled.assign(model->intra_enabled, model->intra_enabled + (size_t)n * n);
+  m.sphere_start.assign(model->sphere_start, model->sphere_start + n + 1);
+  const int ns = n ? m.sphere_start[n] : 0;
+  if (ns < 0)
+  {
+    delete c;
+    return fail(nullptr, B200SV_ERR_INVALID, "negative sphere count");
+  }
+  m.sphere_xyzr.assign(model->sphere_xyzr, model->sphere_xyzr + 4 * (size_t)ns);
+  m.bounding_sphere.assign(model->bounding_sphere, model->bounding_sphere + 4 * (size_t)n);
+  c->cfg = *field;
+  return finishCreate(c, device, out);
+}
+
+int b200sv_create_from_urdf(int device, const char* urdf_xml, const char* srdf_xml, const char* group_name,
+                            const b200sv_field_cfg* field, b200sv_ctx** out)
+{
+  if (!urdf_xml || !group_name || !field || !out)
+    return fail(nullptr, B200SV_ERR_INVALID, "null argument");
+  *out = nullptr;
+  auto* c = new b200sv_ctx();
+  std::string err;
+  bool parse_error = false;
+  if (!loadUrdfSrdf(urdf_xml, srdf_xml ? srdf_xml : "", group_name, field->resolution, c->robot, c->cm, c->self_points,
+                    err, parse_error))
+  {
+    delete c;
+    return fail(nullptr, parse_error ? B200SV_ERR_PARSE : B200SV_ERR_INVALID, err);
+  }
+  c->cfg = *field;
+  int rc = finishCreate(c, device, out);
+  if (rc != B200SV_OK)
+    return rc;
+  // self field from the non-group links (generateDistanceFieldCacheEntry :907-953)
+  if (!c->self_points.empty() && c->device >= 0)
+  {
+    rc = b200sv_field_add_points(c, B200SV_FIELD_SELF, c->self_points.data(), c->self_points.size() / 3);
+    if (rc != B200SV_OK)
+    {
+      g_create_error = c->err;
+      b200sv_destroy(c);
+      *out = nullptr;
+    }
+  }
+  return rc;
+}
+
+void b200sv_destroy(b200sv_ctx* c)
+{
+  if (!c)
+    return;
+  if (c->device < 0)
+  {
+    delete c;
+    return;
+  }
+  cudaSetDevice(c->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  for (int w = 0; w < 2; ++w)
+  {
+    Field& F = c->fields[w];
+    if (F.compact && F.compact != F.d2)
+      cudaFree(F.compact);
+    if (F.d2)
+      cudaFree(F.d2);
+    if (F.occ)
+      cudaFree(F.occ);
+  }
+  if (c->d_tmp) cudaFree(c->d_tmp);
+  if (c->d_blob_f) cudaFree(c->d_blob_f);
+  if (c->d_blob_d) cudaFree(c->d_blob_d);
+  if (c->d_link_slot) cudaFree(c->d_link_slot);
+  if (c->d_const_T) cudaFree(c->d_const_T);
+  if (c->d_count) cudaFree(c->d_count);
+  if (c->d_sink) cudaFree(c->d_sink);
+  c->d_q.release();
+  c->d_bitmap.release();
+  c->d_list.release();
+  c->d_points.release();
+  c->d_fk.release();
+  c->d_i32.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* b200sv_last_error(const b200sv_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int b200sv_get_info(const b200sv_ctx* c, b200sv_info* info)
+{
+  if (!c || !info)
+    return B200SV_ERR_INVALID;
+  info->n_links = c->robot.n_links;
+  info->n_vars = c->robot.n_vars;
+  info->n_group_vars = (int)c->robot.group_var_index.size();
+  info->n_glinks = c->cm.n_glinks;
+  info->n_spheres = c->n_spheres;
+  info->n_link_pairs = c->n_pairs;
+  info->num_cells[0] = c->grid.nx;
+  info->num_cells[1] = c->grid.ny;
+  info->num_cells[2] = c->grid.nz;
+  info->max_distance_sq = c->grid.max_d2;
+  info->device = c->device;
+  info->field_bytes_per_voxel = c->compact_bytes;
+  info->sm_count = c->sm_count;
+  return B200SV_OK;
+}
+
+int b200sv_get_stats(b200sv_ctx* c, b200sv_stats* stats)
+{
+  if (!c || !stats)
+    return B200SV_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->device < 0)
+  {
+    *stats = c->stats;
+    return B200SV_OK;
+  }
+  cudaSetDevice(c->device);
+  if (c->stats_pending)
+  {
+    CU(c, cudaStreamSynchronize(c->stream));
+    unsigned cnt = 0;
+    CU(c, cudaMemcpy(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    c->stats.n_rechecked = cnt;
+    c->stats_pending = false;
+  }
+  *stats = c->stats;
+  return B200SV_OK;
+}
+
+int b200sv_get_robot_arrays(const b200sv_ctx* c, int32_t* parent, int32_t* joint_type, double* joint_axis,
+                            double* joint_origin, int32_t* first_var, double* base_positions, int32_t* group_var_index)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  const HostRobot& r = c->robot;
+  if (parent) std::copy(r.parent.begin(), r.parent.end(), parent);
+  if (joint_type) std::copy(r.joint_type.begin(), r.joint_type.end(), joint_type);
+  if (joint_axis) std::copy(r.joint_axis.begin(), r.joint_axis.end(), joint_axis);
+  if (joint_origin) std::copy(r.joint_origin.begin(), r.joint_origin.end(), joint_origin);
+  if (first_var) std::copy(r.first_var.begin(), r.first_var.end(), first_var);
+  if (base_positions) std::copy(r.base_positions.begin(), r.base_positions.end(), base_positions);
+  if (group_var_index) std::copy(r.group_var_index.begin(), r.group_var_index.end(), group_var_index);
+  return B200SV_OK;
+}
+
+int b200sv_get_model_arrays(const b200sv_ctx* c, int32_t* glink_index, uint8_t* self_enabled, uint8_t* intra_enabled,
+                            int32_t* sphere_start, double* sphere_xyzr, double* bounding_sphere)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  const HostCollisionModel& m = c->cm;
+  if (glink_index) std::copy(m.glink_index.begin(), m.glink_index.end(), glink_index);
+  if (self_enabled) std::copy(m.self_enabled.begin(), m.self_enabled.end(), self_enabled);
+  if (intra_enabled) std::copy(m.intra_enabled.begin(), m.intra_enabled.end(), intra_enabled);
+  if (sphere_start) std::copy(m.sphere_start.begin(), m.sphere_start.end(), sphere_start);
+  if (sphere_xyzr) std::copy(m.sphere_xyzr.begin(), m.sphere_xyzr.end(), sphere_xyzr);
+  if (bounding_sphere) std::copy(m.bounding_sphere.begin(), m.bounding_sphere.end(), bounding_sphere);
+  return B200SV_OK;
+}
+
+int b200sv_get_link_names(const b200sv_ctx* c, char* buf, size_t cap)
+{
+  if (!c || !buf || cap == 0)
+    return B200SV_ERR_INVALID;
+  std::string s;
+  for (size_t i = 0; i < c->robot.link_names.size(); ++i)
+    s += (i ? "\n" : "") + c->robot.link_names[i];
+  if (s.size() + 1 > cap)
+    return B200SV_ERR_INVALID;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return B200SV_OK;
+}
+
+int b200sv_get_group_bounds(const b200sv_ctx* c, double* lower, double* upper)
+{
+  if (!c || !lower || !upper)
+    return B200SV_ERR_INVALID;
+  if (c->robot.group_lower.size() != c->robot.group_var_index.size())
+    return fail(const_cast<b200sv_ctx*>(c), B200SV_ERR_UNSUPPORTED, "bounds are only known on the URDF path");
+  std::copy(c->robot.group_lower.begin(), c->robot.group_lower.end(), lower);
+  std::copy(c->robot.group_upper.begin(), c->robot.group_upper.end(), upper);
+  return B200SV_OK;
+}
+
+int b200sv_get_sphere_thresholds(const b200sv_ctx* c, int32_t* thresholds)
+{
+  if (!c || !thresholds)
+    return B200SV_ERR_INVALID;
+  const auto* h = reinterpret_cast<const ModelHeader<double>*>(c->blob_d.data());
+  const auto* S = reinterpret_cast<const SphereRec<double>*>(c->blob_d.data() + h->off_spheres);
+  for (int i = 0; i < h->n_spheres; ++i)
+    thresholds[i] = S[i].thr;
+  return B200SV_OK;
+}
+
+int b200sv_get_self_points(const b200sv_ctx* c, double* xyz, size_t cap_points, size_t* n_out)
+{
+  if (!c || !n_out)
+    return B200SV_ERR_INVALID;
+  *n_out = c->self_points.size() / 3;
+  if (xyz)
+  {
+    if (cap_points < *n_out)
+      return B200SV_ERR_INVALID;
+    std::copy(c->self_points.begin(), c->self_points.end(), xyz);
+  }
+  return B200SV_OK;
+}
+
+// ---- fields ------------------------------------------------------------------------------------------------------
+static int checkWhich(b200sv_ctx* c, int which)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (which != B200SV_FIELD_WORLD && which != B200SV_FIELD_SELF)
+    return fail(c, B200SV_ERR_INVALID, "field selector must be B200SV_FIELD_WORLD or B200SV_FIELD_SELF");
+  return needDevice(c);
+}
+
+int b200sv_field_reset(b200sv_ctx* c, int which)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  Field& F = c->fields[which];
+  CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
+  CU(c, launchFillField(c->grid, F.d2, F.compact, c->compact_bytes, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return B200SV_OK;
+}
+
+static int pointsHost(b200sv_ctx* c, int which, const double* xyz, size_t n, bool set)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (n && !xyz)
+    return fail(c, B200SV_ERR_INVALID, "null point array");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  if (n)
+  {
+    CU(c, c->d_points.ensure(3 * n));
+    CU(c, cudaMemcpyAsync(c->d_points.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = addOrRemove(c, which, c->d_points.p, n, set, c->stream)) != B200SV_OK)
+      return rc;
+  }
+  return rebuildField(c, which);
+}
+
+int b200sv_field_add_points(b200sv_ctx* c, int which, const double* xyz, size_t n)
+{
+  return pointsHost(c, which, xyz, n, true);
+}
+
+int b200sv_field_remove_points(b200sv_ctx* c, int which, const double* xyz, size_t n)
+{
+  return pointsHost(c, which, xyz, n, false);
+}
+
+int b200sv_field_add_points_device(b200sv_ctx* c, int which, const double* d_xyz, size_t n, void* cuda_stream)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  if ((rc = addOrRemove(c, which, d_xyz, n, true, s)) != B200SV_OK)
+    return rc;
+  Field& F = c->fields[which];
+  CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.d2, F.compact, c->compact_bytes, c->sm_count, s));
+  return B200SV_OK;
+}
+
+int b200sv_field_get_d2(b200sv_ctx* c, int which, int32_t* out)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!out)
+    return fail(c, B200SV_ERR_INVALID, "null output");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  std::vector<uint16_t> h(c->n_voxels);
+  CU(c, cudaMemcpyAsync(h.data(), c->fields[which].d2, c->n_voxels * 2, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < c->n_voxels; ++i)
+    out[i] = h[i];
+  return B200SV_OK;
+}
+
+int b200sv_field_set_d2(b200sv_ctx* c, int which, const int32_t* d2)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!d2)
+    return fail(c, B200SV_ERR_INVALID, "null input");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  Field& F = c->fields[which];
+  CU(c, c->d_i32.ensure(c->n_voxels));
+  CU(c, cudaMemcpyAsync(c->d_i32.p, d2, c->n_voxels * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
+  CU(c, launchInjectD2(c->grid, c->d_i32.p, F.occ, F.d2, F.compact, c->compact_bytes, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return B200SV_OK;
+}
+
+// ---- hot path --------------------------------------------------------------------------------------------------------
+int b200sv_fk_batch(b200sv_ctx* c, const double* q, size_t n, int precision_bits, double* link_T)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if ((n && (!q || !link_T)) || (precision_bits != 32 && precision_bits != 64))
+    return fail(c, B200SV_ERR_INVALID, "bad arguments to b200sv_fk_batch");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t V = c->robot.group_var_index.size();
+  const size_t out_n = n * (size_t)c->robot.n_links * 16;
+  CU(c, c->d_q.ensure(n * V));
+  CU(c, c->d_fk.ensure(out_n));
+  CU(c, cudaMemcpyAsync(c->d_q.p, q, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  FkArgs a{};
+  const bool fp64 = precision_bits == 64;
+  a.model = fp64 ? c->d_blob_d : c->d_blob_f;
+  a.model_bytes = (int)(fp64 ? c->blob_d.size() : c->blob_f.size());
+  a.q = c->d_q.p;
+  a.n_states = n;
+  a.n_model_links = c->robot.n_links;
+  a.link_slot = c->d_link_slot;
+  a.const_T = c->d_const_T;
+  a.out = c->d_fk.p;
+  const int elem = fp64 ? 8 : 4;
+  const int warps = std::max(1, std::min(4, fp64 ? c->warps_d : c->warps_f));
+  const size_t smem = align16(a.model_bytes) + (size_t)warps * 32 * c->state_stride * elem + 16;
+  const int grid = (int)std::min<size_t>((n + 32 * warps - 1) / (32 * warps), (size_t)c->sm_count * 4);
+  CU(c, launchFk(a, fp64, grid, warps * 32, smem, c->stream));
+  CU(c, cudaMemcpyAsync(link_T, c->d_fk.p, out_n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return B200SV_OK;
+}
+
+int b200sv_sphere_centers(b200sv_ctx* c, const double* q_one, double* centers)
+{
+  if (!c || !q_one || !centers)
+    return B200SV_ERR_INVALID;
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t V = c->robot.group_var_index.size();
+  CU(c, c->d_q.ensure(V));
+  CU(c, c->d_fk.ensure((size_t)c->n_spheres * 3 + 1));
+  CU(c, cudaMemcpyAsync(c->d_q.p, q_one, V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  FkArgs a{};
+  a.model = c->d_blob_d;
+  a.model_bytes = (int)c->blob_d.size();
+  a.q = c->d_q.p;
+  a.n_states = 1;
+  const size_t smem = align16(a.model_bytes) + (size_t)c->state_stride * 8 + 16;
+  CU(c, launchSphereCenters(a, c->d_fk.p, smem, c->stream));
+  CU(c, cudaMemcpyAsync(centers, c->d_fk.p, (size_t)c->n_spheres * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return B200SV_OK;
+}
+
+int b200sv_check_batch_device(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint8_t* d_valid_bitmap,
+                              void* cuda_stream)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (n && (!d_q || !d_valid_bitmap))
+    return fail(c, B200SV_ERR_INVALID, "null device pointer");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  int rc = checkDevice(c, d_q, n, flags, reinterpret_cast<uint32_t*>(d_valid_bitmap), static_cast<cudaStream_t>(cuda_stream));
+  c->stats.n_states = n;
+  c->stats.n_valid = 0;
+  c->stats.check_ms = 0.f;
+  c->stats_pending = true;
+  return rc;
+}
+
+int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags, uint8_t* valid_bitmap)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (n && (!q || !valid_bitmap))
+    return fail(c, B200SV_ERR_INVALID, "null host pointer");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t V = c->robot.group_var_index.size();
+  const size_t words = (n + 31) / 32;
+  CU(c, c->d_q.ensure(n * V));
+  CU(c, c->d_bitmap.ensure(words));
+  CU(c, cudaMemcpyAsync(c->d_q.p, q, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaEventRecord(c->ev0, c->stream));
+  int rc = checkDevice(c, c->d_q.p, n, flags, c->d_bitmap.p, c->stream);
+  if (rc != B200SV_OK)
+    return rc;
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  // bitmap back: whole bytes of the caller's buffer; the device words are little-endian, bit i%8 of byte i/8
+  CU(c, cudaMemcpyAsync(valid_bitmap, c->d_bitmap.p, (n + 7) / 8, cudaMemcpyDeviceToHost, c->stream));
+  unsigned cnt = 0;
+  CU(c, cudaMemcpyAsync(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  uint64_t valid = 0;
+  for (size_t i = 0; i < (n + 7) / 8; ++i)
+    valid += __builtin_popcount(valid_bitmap[i]);
+  c->stats.n_states = n;
+  c->stats.n_valid = valid;
+  c->stats.n_rechecked = (flags & B200SV_CHECK_FP64) ? 0 : cnt;
+  c->stats.check_ms = ms;
+  c->stats_pending = false;
+  return B200SV_OK;
+}
+
+int b200sv_gather_roofline(b200sv_ctx* c, size_t n_reads, int iters, double* gbs)
+{
+  if (!c || !gbs || iters < 1)
+    return B200SV_ERR_INVALID;
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t field_bytes = c->n_voxels * (size_t)c->compact_bytes;
+  const unsigned long long n_sectors = field_bytes / 32;
+  if (n_sectors == 0)
+    return fail(c, B200SV_ERR_INVALID, "field smaller than one sector");
+  const int block = 256, per_thread = 64;
+  const int grid = (int)std::min<size_t>((n_reads + (size_t)block * per_thread - 1) / ((size_t)block * per_thread), 1u << 20);
+  const uint8_t* f = static_cast<const uint8_t*>(c->fields[0].compact);
+  CU(c, launchGather(f, n_sectors, per_thread, grid, block, c->d_sink, c->stream));  // warm-up
+  float best = 1e30f;
+  for (int i = 0; i < iters; ++i)
+  {
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    CU(c, launchGather(f, n_sectors, per_thread, grid, block, c->d_sink, c->stream));
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    best = std::min(best, ms);
+  }
+  const double reads = (double)grid * block * per_thread;
+  *gbs = reads * 32.0 / (best * 1e-3) / 1e9;
+  return B200SV_OK;
+}
+
+int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int warps_per_block, int blocks_per_sm)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  if (fp32_eps_m > 0.0)
+    c->fp32_eps = fp32_eps_m;
+  if (warps_per_block > 0)
+    c->tune_warps = warps_per_block;
+  if (blocks_per_sm > 0)
+    c->blocks_per_sm = blocks_per_sm;
+  CU(c, cudaStreamSynchronize(c->stream));
+  int rc = buildTables(c);
+  if (rc != B200SV_OK)
+    return rc;
+  return uploadTables(c);
+}
+
+}  // extern "C"

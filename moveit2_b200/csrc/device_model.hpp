@@ -1,0 +1,70 @@
+// Records shared by the host table builder and the kernels.  One blob per precision (float for the fast pass,
+// double for the exact pass) lives in global memory; every CTA copies it into shared memory once.
+#pragma once
+#include <cstdint>
+
+namespace b200sv
+{
+// moveit::core::JointModel::JointType subset; values match B200SV_JOINT_* in include/b200sv.h
+enum JointType : int32_t { FIXED = 0, REVOLUTE = 1, PRISMATIC = 2, PLANAR = 3, FLOATING = 4 };
+
+// 3x4 row-major affine transforms everywhere on the device (the last row of an isometry is implicit).
+template <typename R>
+struct LinkRec
+{
+  R o[12];     // joint origin; for a link whose parent does not move with the group: T_parent(base state) * origin
+  R ax[3];     // joint axis
+  int parent;  // device-link slot of the parent, -1 if `o` is already global
+  int type;    // JointType
+  int var;     // first VarRec of the joint
+  int has_origin;  // 0: `o` is the identity (LinkModel::jointOriginTransformIsIdentity), skip the product
+  int pad;
+};
+
+// Value of one full-state variable as an affine function of the group state: v = a * q[k] + b (k < 0: v = b).
+// Encodes setJointGroupPositions + updateMimicJoints(group) (robot_state.cpp:571-584, 210-220).
+struct VarRec
+{
+  double a, b;
+  int k, pad;
+};
+
+template <typename R>
+struct SphereRec
+{
+  R x, y, z, r;  // CollisionSphere::relative_vec_ / radius_
+  int slot;      // device-link slot
+  int thr;       // collide with the WORLD field iff d2[voxel] < thr  (integer form of types.cpp:229)
+  int thr_self;  // same for the SELF field; 0 when dfce->self_collision_enabled_ is false for the link
+  int pad;
+};
+
+template <typename R>
+struct BsRec  // posed per link for doBoundingSpheresIntersect (types.cpp:408-418)
+{
+  R x, y, z, r;
+  int slot, s0, s1, pad;  // device-link slot, sphere range [s0, s1)
+};
+
+struct PairRec  // enabled intra-group link pair (indices into the BsRec table), i < j in dfce order
+{
+  int a, b;
+};
+
+template <typename R>
+struct ModelHeader
+{
+  int n_links, n_vars, n_spheres, n_bs, n_pairs, n_group_vars;
+  int off_links, off_vars, off_spheres, off_bs, off_pairs, total_bytes;
+  int state_stride, link_stride;  // shared-memory strides (in R) of a state's / a link's transform
+  int nx, ny, nz, pad0;
+  R om[3];      // VoxelGrid::origin_minus_
+  R oo_res;     // VoxelGrid::oo_resolution_
+  R margin;     // FP32 pass: voxel-coordinate uncertainty (cells); 0 in the FP64 pass
+  R pair_eps;   // FP32 pass: uncertainty of a centre distance (m)
+  R bs_eps;     // FP32 pass: uncertainty of a SQUARED bounding-centre distance (m^2)
+  R pad1;
+};
+
+constexpr int kLinkStrideWords = 13;  // 12 + 1: odd stride => distinct links hit distinct banks
+}  // namespace b200sv

@@ -1,0 +1,68 @@
+// Launchers of the CUDA kernels (definitions in check_kernels.cu / edt_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace b200sv
+{
+template <typename FT>
+struct CheckArgs
+{
+  const uint8_t* model;  // ModelHeader<R> blob (float blob for the fast pass, double blob for the exact pass)
+  int model_bytes;
+  const double* q;       // [n_states * n_group_vars]
+  unsigned long long n_states;
+  const FT* world;       // compact d^2 fields, index x*ny*nz + y*nz + z
+  const FT* self;
+  uint32_t flags;
+  uint32_t* bitmap;      // validity words
+  uint32_t* flag_list;   // fast pass: states to recheck (out)
+  unsigned* flag_count;
+  unsigned list_cap;
+  const uint32_t* list;  // exact pass from list (in)
+  const unsigned* list_count;
+};
+
+struct FkArgs
+{
+  const uint8_t* model;
+  int model_bytes;
+  const double* q;
+  unsigned long long n_states;
+  int n_model_links;
+  const int* link_slot;   // [n_model_links] device-link slot or -1
+  const double* const_T;  // [n_model_links*16] base-state global transforms (column-major)
+  double* out;            // [n_states * n_model_links * 16]
+};
+
+template <typename FT>
+cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int grid, int block, size_t smem_bytes,
+                        cudaStream_t stream);
+cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launchGather(const uint8_t* field, unsigned long long n_sectors, int per_thread, int grid, int block,
+                         unsigned* sink, cudaStream_t stream);
+
+// ---- distance field ------------------------------------------------------------------------------------
+struct GridDev
+{
+  double om[3];  // VoxelGrid::origin_minus_
+  double oo;     // VoxelGrid::oo_resolution_
+  int nx, ny, nz;
+  int wz;        // 32-bit occupancy words per z row
+  int R;         // ceil(max_distance / resolution): propagation radius in cells
+  int max_d2;    // R*R = PropagationDistanceField::max_distance_sq_
+};
+
+// occupancy bitmap: word ((x*ny + y)*wz + z/32), bit z%32
+cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint32_t* occ, bool set, cudaStream_t s);
+// exact truncated EDT of the occupancy bitmap -> d2 (uint16, min(d^2, max_d2)) and the compact field FT
+// (uint8: min(d^2, 255); uint16: same as d2).  tmp: uint16 [nx*ny*nz] scratch.
+cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
+                      int compact_bytes, int sm_count, cudaStream_t s);
+cudaError_t launchFillField(const GridDev& g, uint16_t* d2, void* compact, int compact_bytes, cudaStream_t s);
+cudaError_t launchInjectD2(const GridDev& g, const int32_t* d_in, uint32_t* occ, uint16_t* d2, void* compact,
+                           int compact_bytes, cudaStream_t s);
+}  // namespace b200sv

@@ -1,0 +1,265 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test calls the CUDA path through the C-ABI
+(moveit2_b200.StateValidityEngine -> libb200sv.so) and compares with the oracle on the same seeded inputs.
+Bar: bit-exact for integer voxel distances and validity booleans; link poses within 1e-5 m (FP32 pass) and
+1e-12 m (FP64 pass)."""
+import os
+
+import numpy as np
+import pytest
+
+import moveit2_b200 as mb
+from moveit2_b200 import workloads
+from oracle.collision_model import find_internal_points_sphere
+from oracle.df import PropagationDistanceField
+
+from util import config_pair, make_pair, unpack
+
+pytestmark = pytest.mark.gpu
+
+W, S, I, ALL, FP64 = mb.CHECK_WORLD, mb.CHECK_SELF, mb.CHECK_INTRA, mb.CHECK_ALL, mb.CHECK_FP64
+
+
+@pytest.fixture(scope="module")
+def c1():
+    eng, env, cloud, q = config_pair("C1")
+    env.world.add_points(cloud)
+    eng.field_add_points(cloud)
+    yield eng, env, cloud, q
+    eng.close()
+
+
+# ---- K3 + K4: distance field ----------------------------------------------------------------------------
+def test_edt_bit_exact_c1_world_and_self(c1):
+    eng, env, cloud, q = c1
+    assert eng.num_cells == env.world.num_cells and eng.max_distance_sq == env.world.max_distance_sq
+    gw, ow = eng.field_get_d2(mb.FIELD_WORLD), env.world.d2()
+    assert np.array_equal(gw == 0, ow == 0)          # identical occupancy (worldToGrid parity)
+    assert (gw <= ow).all()                          # the exact EDT never exceeds the reference's propagation
+    assert int((gw != ow).sum()) == 0                # and on this cloud they agree voxel for voxel
+    assert np.array_equal(eng.field_get_d2(mb.FIELD_SELF), env.self_field.d2())
+
+
+def test_edt_is_exact_against_scipy(c1):
+    from scipy import ndimage
+    eng = c1[0]
+    g = eng.field_get_d2()
+    exact = np.rint(ndimage.distance_transform_edt(g != 0) ** 2).astype(np.int64)
+    assert np.array_equal(g, np.minimum(exact, eng.max_distance_sq))
+
+
+def test_edt_golden_test_big(golden):
+    """test_big.df (reference fixture): sphere r=.5 at (.5,.5,.5) in 150x150x200 @ 2 cm."""
+    gz = np.load(os.path.join(golden, "df_golden.npz"))
+    dims = tuple(int(v) for v in gz["test_big_dims"])
+    occ = np.unpackbits(gz["test_big_occ_bits"])[: dims[0] * dims[1] * dims[2]].reshape(dims).astype(bool)
+    eng, env = make_pair("panda", "panda_arm", (3.0, 3.0, 4.0), (1.5, 1.5, 2.0), 0.02, 0.25)
+    pts = find_internal_points_sphere((0.5, 0.5, 0.5), 0.5, 0.02)
+    eng.field_add_points(pts)
+    g = eng.field_get_d2()
+    assert np.array_equal(g == 0, occ)
+    ref = PropagationDistanceField(3.0, 3.0, 4.0, 0.02, 0, 0, 0, 0.25)
+    ref.add_points(pts)
+    o = ref.d2()
+    assert (g <= o).all()
+    assert int((g != o).sum()) == 0
+    eng.close()
+
+
+def test_edt_sparse_scene_mismatch_is_one_sided_and_counted():
+    """Sparse scenes: the reference's propagation over-estimates a few voxels (insertion-order dependent,
+    SURVEY.md section 7); the GPU field is exact, so every mismatch must be GPU < reference."""
+    from scipy import ndimage
+    eng, env = make_pair("panda", "panda_arm", (0.8, 0.8, 0.8), (0, 0, 0.4), 0.02, 0.25)
+    pts = np.random.default_rng(11).uniform([-0.4, -0.4, 0], [0.4, 0.4, 0.8], size=(60, 3))
+    eng.field_add_points(pts)
+    env.world.add_points(pts)
+    g, o = eng.field_get_d2(), env.world.d2()
+    exact = np.minimum(np.rint(ndimage.distance_transform_edt(g != 0) ** 2).astype(np.int64), eng.max_distance_sq)
+    assert np.array_equal(g, exact)
+    assert (g <= o).all()
+    assert (g != o).mean() < 1e-3
+    eng.close()
+
+
+def test_field_add_remove_reset_equals_fresh_build():
+    eng, env = make_pair("panda", "panda_arm", (1, 1, 1), (0, 0, 0.5), 0.05, 0.25)
+    rng = np.random.default_rng(3)
+    a = rng.uniform([-0.5, -0.5, 0], [0.5, 0.5, 1], size=(300, 3))
+    b = rng.uniform([-0.5, -0.5, 0], [0.5, 0.5, 1], size=(200, 3))
+    eng.field_add_points(a)
+    eng.field_add_points(b)          # incremental add == union
+    env.world.add_points(np.concatenate([a, b]))
+    assert np.array_equal(eng.field_get_d2() == 0, env.world.d2() == 0)
+    eng.field_remove_points(a)       # removal == fresh build without those voxels (test_distance_field.cpp:508)
+    env.world.remove_points(a)
+    fresh, _ = make_pair("panda", "panda_arm", (1, 1, 1), (0, 0, 0.5), 0.05, 0.25)
+    occ_b = env.world.d2() == 0
+    g = eng.field_get_d2()
+    assert np.array_equal(g == 0, occ_b)
+    fresh.field_set_d2(np.where(occ_b, 0, eng.max_distance_sq))
+    # points outside the grid and empty inputs are ignored
+    eng.field_add_points(np.array([[100.0, 0, 0], [0, -100.0, 0]]))
+    eng.field_add_points(np.zeros((0, 3)))
+    assert np.array_equal(eng.field_get_d2(), g)
+    eng.field_reset()
+    assert (eng.field_get_d2() == eng.max_distance_sq).all()
+    eng.close()
+    fresh.close()
+
+
+def test_field_set_get_roundtrip(c1):
+    eng, env = make_pair("panda", "panda_arm", (1, 1, 1), (0, 0, 0.5), 0.02, 0.25)
+    o = c1[1].world.d2()
+    eng.field_set_d2(o)
+    assert np.array_equal(eng.field_get_d2(), o)
+    eng.close()
+
+
+# ---- K1: forward kinematics ------------------------------------------------------------------------------
+@pytest.mark.parametrize("robot,group", [("panda", "panda_arm"), ("panda", "panda_arm_hand"), ("dualarm", "arms"),
+                                         ("dualarm", "whole_body")])
+def test_fk_parity(robot, group):
+    eng, env = make_pair(robot, group, (1, 1, 1), (0, 0, 0.5), 0.05, 0.25)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(5, 1000, lo, hi)
+    ref = env.fk(q)
+    t64 = eng.fk_batch(q, 64)
+    t32 = eng.fk_batch(q, 32)
+    assert np.abs(t64 - ref).max() < 1e-12       # FP64 pass: same arithmetic, sin/cos within an ulp
+    assert np.abs(t32 - ref).max() < 1e-5        # north_star: link poses within 1e-5 m
+    assert np.array_equal(t64[:, :, 3, :], np.broadcast_to([0, 0, 0, 1.0], t64[:, :, 3, :].shape))
+    # ragged sizes
+    for n in (1, 31, 33):
+        assert np.abs(eng.fk_batch(q[:n], 64) - ref[:n]).max() < 1e-12
+    eng.close()
+
+
+def test_sphere_centers_parity(c1):
+    eng, env, _, q = c1
+    for i in range(5):
+        assert np.abs(eng.sphere_centers(q[i]) - env.sphere_centers(q[i])).max() < 1e-12
+
+
+# ---- K2: validity -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [W, S, I, W | S, ALL])
+def test_validity_bit_exact_c1(c1, flags):
+    eng, env, _, q = c1
+    ref, _ = env.check(q, flags)
+    for mode in (0, FP64):
+        valid = eng.check_batch(q, flags | mode)
+        mism = np.nonzero(valid == ref.astype(bool))[0]   # valid must be the negation of collision
+        assert len(mism) == 0, "mode %d: %d mismatches, first %s" % (mode, len(mism), mism[:5])
+    st = eng.stats()
+    assert st["n_states"] == len(q) and st["n_valid"] == int((ref == 0).sum())
+
+
+def test_validity_with_injected_reference_field(c1):
+    """Check parity independent of EDT parity: both sides read the reference's own propagation result."""
+    eng, env, _, q = c1
+    eng2, _ = make_pair("panda", "panda_arm", (1, 1, 1), (0, 0, 0.5), 0.02, 0.25)
+    eng2.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng2.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    ref, _ = env.check(q, ALL)
+    assert np.array_equal(eng2.check_batch(q, ALL), ref == 0)
+    eng2.close()
+
+
+def test_fp32_pass_rechecks_only_a_small_fraction(c1):
+    eng, env, _, q = c1
+    eng.check_batch(q, ALL)
+    st = eng.stats()
+    assert st["n_rechecked"] < 0.05 * len(q)
+
+
+def test_bitmap_layout_and_ragged_batches(c1):
+    eng, env, _, q = c1
+    ref, _ = env.check(q[:100], ALL)
+    for n in (1, 7, 8, 9, 31, 32, 33, 63, 64, 65, 100):
+        bm = eng.check_batch_bitmap(q[:n], ALL)
+        assert bm.shape == ((n + 7) // 8,)
+        assert np.array_equal(unpack(bm, n), ref[:n] == 0)
+        if n % 8:
+            assert (bm[-1] >> (n % 8)) == 0        # padding bits are zero
+    assert eng.check_batch(np.zeros((0, 7)), ALL).shape == (0,)
+
+
+def test_states_leaving_the_field_are_free():
+    """Out-of-bounds spheres read max_distance and never collide (distance_field.cpp:82, types.cpp:229)."""
+    eng, env = make_pair("panda", "panda_arm", (0.3, 0.3, 0.3), (2.0, 2.0, 2.0), 0.02, 0.25)
+    pts = np.random.default_rng(0).uniform(1.85, 2.15, size=(500, 3))
+    eng.field_add_points(pts)
+    env.world.add_points(pts)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(1, 2000, lo, hi)
+    ref, _ = env.check(q, W)
+    assert ref.sum() == 0
+    assert eng.check_batch(q, W).all()
+    eng.close()
+
+
+def test_tolerance_and_other_resolution():
+    eng, env = make_pair("panda", "panda_arm", (1.2, 1.2, 1.2), (0, 0, 0.5), 0.025, 0.3, tolerance=0.01)
+    cloud = workloads.clutter_cloud(9, 3000, 8, (-0.5, -0.5, 0.0), (0.5, 0.5, 1.0), 0.22)
+    eng.field_add_points(cloud)
+    env.world.add_points(cloud)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(2, 5000, lo, hi)
+    ref, _ = env.check(q, ALL)
+    assert 0.05 < ref.mean() < 0.95
+    assert np.array_equal(eng.check_batch(q, ALL), ref == 0)
+    assert np.array_equal(eng.check_batch(q, ALL | FP64), ref == 0)
+    eng.close()
+
+
+@pytest.mark.parametrize("group", ["arms", "left_arm", "whole_body"])
+def test_validity_dualarm(group):
+    cfg = workloads.CONFIGS["C3"]
+    eng, env = make_pair("dualarm", group, cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    cloud = workloads.make_cloud("C3")
+    eng.field_add_points(cloud)
+    env.world.add_points(cloud)
+    assert np.array_equal(eng.field_get_d2() == 0, env.world.d2() == 0)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(4, 20000, lo, hi)
+    for flags in (W, S, I, ALL):
+        ref, _ = env.check(q, flags)
+        assert np.array_equal(eng.check_batch(q, flags), ref == 0), flags
+    eng.close()
+
+
+def test_reference_interface_mirror(c1):
+    eng, env, _, q = c1
+    cenv = mb.CollisionEnvB200(eng, "panda_arm")
+    req = mb.CollisionRequest(group_name="panda_arm")
+    ref_all, _ = env.check(q[:50], ALL)
+    ref_self, _ = env.check(q[:50], S | I)
+    ref_world, _ = env.check(q[:50], W)
+    for i in range(50):
+        r = mb.CollisionResult()
+        cenv.checkCollision(req, r, q[i])
+        assert r.collision == bool(ref_all[i])
+        r = mb.CollisionResult()
+        cenv.checkSelfCollision(req, r, q[i])
+        assert r.collision == bool(ref_self[i])
+        r = mb.CollisionResult()
+        cenv.checkRobotCollision(req, r, q[i])
+        assert r.collision == bool(ref_world[i])
+    bm = cenv.checkCollisionBatch(req, q[:50])
+    assert np.array_equal(unpack(bm, 50), ref_all == 0)
+
+
+def test_device_resident_entry_point(c1):
+    import torch
+    eng, env, _, q = c1
+    dq = torch.from_numpy(q).cuda()
+    bm = torch.zeros(4 * ((len(q) + 31) // 32), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream()
+    eng.check_batch_device(dq.data_ptr(), len(q), ALL, bm.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    ref, _ = env.check(q, ALL)
+    assert np.array_equal(unpack(bm.cpu().numpy(), len(q)), ref == 0)
+    assert eng.stats()["n_rechecked"] < 0.05 * len(q)
+
+
+def test_gather_roofline_runs(c1):
+    assert c1[0].gather_roofline(1 << 24, 2) > 1.0
