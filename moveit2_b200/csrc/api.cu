@@ -148,7 +148,8 @@ int sphereThreshold(double radius, double res, double max_prop, double tol, int 
 template <typename R>
 void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, const std::vector<VarRec>& vars,
                const std::vector<SphereRec<double>>& spheres, const std::vector<BsRec<double>>& bs,
-               const std::vector<PairRec>& pairs, double margin, double pair_eps, double bs_eps, std::vector<uint8_t>& out)
+               const std::vector<PairRec>& pairs, double margin, double pair_eps, double bs_eps, double tight_eps,
+               std::vector<uint8_t>& out)
 {
   ModelHeader<R> h{};
   h.n_links = (int)links.size();
@@ -180,6 +181,7 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
   h.margin = (R)margin;
   h.pair_eps = (R)pair_eps;
   h.bs_eps = (R)bs_eps;
+  h.tight_eps = (R)tight_eps;
   out.assign(off, 0);
   memcpy(out.data(), &h, sizeof(h));
   auto* L = reinterpret_cast<LinkRec<R>*>(out.data() + h.off_links);
@@ -214,6 +216,10 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
     B[i].y = (R)bs[i].y;
     B[i].z = (R)bs[i].z;
     B[i].r = (R)bs[i].r;
+    B[i].tx = (R)bs[i].tx;
+    B[i].ty = (R)bs[i].ty;
+    B[i].tz = (R)bs[i].tz;
+    B[i].tr = (R)bs[i].tr;
     B[i].slot = bs[i].slot;
     B[i].s0 = bs[i].s0;
     B[i].s1 = bs[i].s1;
@@ -404,6 +410,24 @@ int buildTables(b200sv_ctx* c)
       spheres.push_back(S);
     }
     B.s1 = (int)spheres.size();
+    {  // tight sphere around the link's collision spheres: centroid, then the farthest sphere surface (+ 1 nm)
+      double cx = 0, cy = 0, cz = 0;
+      for (int k = B.s0; k < B.s1; ++k)
+      {
+        cx += spheres[k].x;
+        cy += spheres[k].y;
+        cz += spheres[k].z;
+      }
+      const double inv = 1.0 / (B.s1 - B.s0);
+      cx *= inv; cy *= inv; cz *= inv;
+      double rr = 0.0;
+      for (int k = B.s0; k < B.s1; ++k)
+      {
+        const double ex = spheres[k].x - cx, ey = spheres[k].y - cy, ez = spheres[k].z - cz;
+        rr = std::max(rr, sqrt(ex * ex + ey * ey + ez * ez) + spheres[k].r);
+      }
+      B.tx = cx; B.ty = cy; B.tz = cz; B.tr = rr + 1e-9;
+    }
     bs_of_glink[i] = (int)bs.size();
     bs.push_back(B);
   }
@@ -413,8 +437,21 @@ int buildTables(b200sv_ctx* c)
     for (int j = i + 1; j < m.n_glinks; ++j)
       if (bs_of_glink[i] >= 0 && bs_of_glink[j] >= 0 && m.intra_enabled[(size_t)i * m.n_glinks + j])
       {
-        pairs.push_back(PairRec{ bs_of_glink[i], bs_of_glink[j] });
-        max_rs = std::max(max_rs, bs[bs_of_glink[i]].r + bs[bs_of_glink[j]].r);
+        const BsRec<double>&A = bs[bs_of_glink[i]], &Bb = bs[bs_of_glink[j]];
+        PairRec P{};
+        P.a = bs_of_glink[i];
+        P.b = bs_of_glink[j];
+        P.sa0 = A.s0;
+        P.sb0 = Bb.s0;
+        P.nb = Bb.s1 - Bb.s0;
+        P.tot = (A.s1 - A.s0) * P.nb;
+        P.magic = (65536u + P.nb - 1) / P.nb;
+        // exactness of the multiply-shift division over [0, tot): checked here, not assumed
+        for (int t = 0; t < P.tot; ++t)
+          if ((int)(((unsigned)t * P.magic) >> 16) != t / P.nb)
+            return fail(c, B200SV_ERR_UNSUPPORTED, "link pair with too many sphere pairs for the 16-bit index split");
+        pairs.push_back(P);
+        max_rs = std::max(max_rs, A.r + Bb.r);
       }
   c->n_spheres = (int)spheres.size();
   c->n_bs = (int)bs.size();
@@ -426,14 +463,18 @@ int buildTables(b200sv_ctx* c)
   const double margin = eps * c->grid.oo + nmax * ldexp(1.0, -22);
   const double pair_eps = 2.0 * eps + 1e-7;
   const double bs_eps = 4.0 * eps * (sqrt(max_rs) + 0.05) + 1e-7;
-  buildBlob<float>(*c, links, vars, spheres, bs, pairs, margin, pair_eps, bs_eps, c->blob_f);
-  buildBlob<double>(*c, links, vars, spheres, bs, pairs, 0.0, 0.0, 0.0, c->blob_d);
+  const double tight_eps = 4.0 * eps + 1e-6;
+  buildBlob<float>(*c, links, vars, spheres, bs, pairs, margin, pair_eps, bs_eps, tight_eps, c->blob_f);
+  buildBlob<double>(*c, links, vars, spheres, bs, pairs, 0.0, 0.0, 0.0, 1e-9, c->blob_d);
   return B200SV_OK;
 }
 
+// per-warp shared memory in units of R: transforms of 32 states | sphere centres + radius (4) | bounding centres (3 + 3)
+int perWarpWords(const b200sv_ctx* c) { return 32 * c->state_stride + 4 * c->n_spheres + 6 * c->n_bs + 4; }
+
 int chooseWarps(const b200sv_ctx* c, int blob_bytes, int elem, int cap)
 {
-  const int per_warp = (32 * c->state_stride + 3 * c->n_spheres + 3 * c->n_bs + 1) * elem;
+  const int per_warp = perWarpWords(c) * elem;
   const int avail = c->smem_optin / std::max(1, c->blocks_per_sm) - 1024 - align16(blob_bytes) - 16;
   int w = avail / per_warp;
   w = std::min(w, cap);
@@ -442,7 +483,7 @@ int chooseWarps(const b200sv_ctx* c, int blob_bytes, int elem, int cap)
 
 size_t smemFor(const b200sv_ctx* c, int blob_bytes, int elem, int warps)
 {
-  const size_t per_warp = (size_t)(32 * c->state_stride + 3 * c->n_spheres + 3 * c->n_bs + 1) * elem;
+  const size_t per_warp = (size_t)perWarpWords(c) * elem;
   return align16(blob_bytes) + per_warp * warps + 16;
 }
 

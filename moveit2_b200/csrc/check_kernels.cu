@@ -303,9 +303,10 @@ __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent
       const SphereRec<R> sp = m.spheres[k];
       R cx, cy, cz;
       posePoint<R>(T + sp.slot * kLinkStrideWords, sp.x, sp.y, sp.z, cx, cy, cz);
-      cent[k * 3 + 0] = cx;
-      cent[k * 3 + 1] = cy;
-      cent[k * 3 + 2] = cz;
+      cent[k * 4 + 0] = cx;
+      cent[k * 4 + 1] = cy;
+      cent[k * 4 + 2] = cz;
+      cent[k * 4 + 3] = sp.r;
       const int thr_w = do_world ? sp.thr : 0;
       const int thr_s = do_self ? sp.thr_self : 0;
       if (thr_w | thr_s)
@@ -368,15 +369,21 @@ __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent
   hit = __any_sync(kFull, hit);
   if (!hit && do_intra && h.n_pairs > 0)
   {
-    // bounding-sphere centres of the links (PosedBodySphereDecomposition::updatePose, types.cpp:391)
+    // bounding-sphere centres of the links (PosedBodySphereDecomposition::updatePose, types.cpp:391) and the
+    // centres of our tight spheres
     for (int b = lane; b < h.n_bs; b += 32)
     {
       const BsRec<R> r = m.bs[b];
+      const R* Tl = T + r.slot * kLinkStrideWords;
       R x, y, z;
-      posePoint<R>(T + r.slot * kLinkStrideWords, r.x, r.y, r.z, x, y, z);
-      bsc[b * 3 + 0] = x;
-      bsc[b * 3 + 1] = y;
-      bsc[b * 3 + 2] = z;
+      posePoint<R>(Tl, r.x, r.y, r.z, x, y, z);
+      bsc[b * 6 + 0] = x;
+      bsc[b * 6 + 1] = y;
+      bsc[b * 6 + 2] = z;
+      posePoint<R>(Tl, r.tx, r.ty, r.tz, x, y, z);
+      bsc[b * 6 + 3] = x;
+      bsc[b * 6 + 4] = y;
+      bsc[b * 6 + 5] = z;
     }
     __syncwarp();
     bool phit = false;
@@ -387,16 +394,23 @@ __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent
       if (p < h.n_pairs)
       {
         const PairRec pr = m.pairs[p];
-        const R ex = bsc[pr.a * 3 + 0] - bsc[pr.b * 3 + 0], ey = bsc[pr.a * 3 + 1] - bsc[pr.b * 3 + 1],
-                ez = bsc[pr.a * 3 + 2] - bsc[pr.b * 3 + 2];
+        const R* ca = bsc + pr.a * 6;
+        const R* cb = bsc + pr.b * 6;
+        const R ex = ca[0] - cb[0], ey = ca[1] - cb[1], ez = ca[2] - cb[2];
         const R d2 = ex * ex + ey * ey + ez * ez;
         // reference quirk kept: SQUARED centre distance against the plain radius sum (types.cpp:416-417)
         const R rs = m.bs[pr.a].r + m.bs[pr.b].r;
+        // conservative cull: every sphere of a link lies inside its tight sphere, so separated tight spheres
+        // (with slack for rounding) mean no sphere pair of the two links can touch
+        const R fx = ca[3] - cb[3], fy = ca[4] - cb[4], fz = ca[5] - cb[5];
+        const R t2 = fx * fx + fy * fy + fz * fz;
+        const R rt = m.bs[pr.a].tr + m.bs[pr.b].tr + h.tight_eps;
+        const bool near = t2 < rt * rt;
         if (kExact)
-          live = live_certain = d2 < rs;
+          live = live_certain = near && (d2 < rs);
         else
         {
-          live = d2 < rs + h.bs_eps;
+          live = near && (d2 < rs + h.bs_eps);
           live_certain = d2 < rs - h.bs_eps;
         }
       }
@@ -408,23 +422,22 @@ __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent
         mask &= mask - 1;
         const bool cert = (cmask >> bit) & 1u;
         const PairRec pr = m.pairs[p0 + bit];
-        const BsRec<R> ba = m.bs[pr.a], bb = m.bs[pr.b];
-        const int nb = bb.s1 - bb.s0;
-        const int tot = (ba.s1 - ba.s0) * nb;
-        for (int t = lane; t < tot; t += 32)
+        for (int t = lane; t < pr.tot; t += 32)
         {
-          const int ia = t / nb;
-          const int ka = ba.s0 + ia, kb = bb.s0 + (t - ia * nb);
-          const R gx2 = cent[ka * 3 + 0] - cent[kb * 3 + 0], gy2 = cent[ka * 3 + 1] - cent[kb * 3 + 1],
-                  gz2 = cent[ka * 3 + 2] - cent[kb * 3 + 2];
-          const R dist = sqrtR<R>(gx2 * gx2 + gy2 * gy2 + gz2 * gz2);  // gradient.norm()
-          const R rsum = m.spheres[ka].r + m.spheres[kb].r;
+          const int ia = static_cast<int>((static_cast<unsigned>(t) * pr.magic) >> 16);  // t / nb (range checked on the host)
+          const R* pa = cent + (pr.sa0 + ia) * 4;
+          const R* pb = cent + (pr.sb0 + (t - ia * pr.nb)) * 4;
+          const R gx2 = pa[0] - pb[0], gy2 = pa[1] - pb[1], gz2 = pa[2] - pb[2];
+          const R dd = gx2 * gx2 + gy2 * gy2 + gz2 * gz2;
+          const R rsum = pa[3] + pb[3];
           if (kExact)
-            phit |= dist < rsum;  // collision_env_distance_field.cpp:583
+            phit |= sqrtR<R>(dd) < rsum;  // gradient.norm() < r1 + r2 (collision_env_distance_field.cpp:577-583)
           else
           {
-            const bool c_cert = dist < rsum - h.pair_eps;
-            const bool c_maybe = dist < rsum + h.pair_eps;
+            // squared form of dist < rsum -+ eps (both sides positive); the 1e-7 in pair_eps covers its rounding
+            const R lo = rsum - h.pair_eps, hi = rsum + h.pair_eps;
+            const bool c_cert = (lo > R(0)) && (dd < lo * lo);
+            const bool c_maybe = dd < hi * hi;
             phit |= (cert && c_cert);
             amb |= (c_maybe && !(cert && c_cert));
           }
@@ -446,21 +459,23 @@ __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
   const Smem<R> m = loadModel<R>(a.model, a.model_bytes, smem);
   const ModelHeader<R>& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  const int per_warp = 32 * h.state_stride + 3 * h.n_spheres + 3 * h.n_bs + 1;
+  const int per_warp = 32 * h.state_stride + 4 * h.n_spheres + 6 * h.n_bs + 4;
   R* wbase = reinterpret_cast<R*>(smem + ((h.total_bytes + 15) & ~15)) + static_cast<size_t>(warp) * per_warp;
-  R* Ts = wbase;
-  R* cent = Ts + 32 * h.state_stride;
-  R* bsc = cent + 3 * h.n_spheres;
+  R* cent = wbase;
+  R* bsc = cent + 4 * h.n_spheres;
+  R* Ts = bsc + 6 * h.n_bs;
 
   unsigned long long n = a.n_states;
   if (kFromList)
     n = *a.list_count < a.list_cap ? *a.list_count : a.list_cap;
-  const unsigned long long n_tiles = (n + 31) / 32;
+  // The recheck list is short: one state per warp keeps its latency at one FK + one check instead of 32 in a row.
+  constexpr int kTile = kFromList ? 1 : 32;
+  const unsigned long long n_tiles = (n + kTile - 1) / kTile;
   for (unsigned long long tile = static_cast<unsigned long long>(blockIdx.x) * warps + warp; tile < n_tiles;
        tile += static_cast<unsigned long long>(gridDim.x) * warps)
   {
-    const unsigned long long first = tile * 32;
-    const int cnt = static_cast<int>(n - first < 32 ? n - first : 32);
+    const unsigned long long first = tile * kTile;
+    const int cnt = static_cast<int>(n - first < kTile ? n - first : kTile);
     unsigned long long my_state = first + lane;
     if (kFromList && lane < cnt)
       my_state = a.list[first + lane];
@@ -587,32 +602,39 @@ __global__ void gatherKernel(const uint8_t* __restrict__ field, unsigned long lo
 }
 }  // namespace
 
+// cudaFuncSetAttribute is a host-side driver call: do it when the requirement grows, not on every launch.
+template <typename K>
+cudaError_t ensureSmem(K kernel, size_t smem_bytes, size_t& granted)
+{
+  if (smem_bytes <= granted)
+    return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e == cudaSuccess)
+    granted = smem_bytes;
+  return e;
+}
+
 template <typename FT>
 cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int grid, int block, size_t smem_bytes,
                         cudaStream_t stream)
 {
+  static size_t g_dl = 0, g_d = 0, g_f = 0;  // per FT instantiation
   cudaError_t e;
-  if (fp64)
+  if (fp64 && from_list)
   {
-    if (from_list)
-    {
-      e = cudaFuncSetAttribute(checkKernel<double, FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-      if (e != cudaSuccess)
-        return e;
-      checkKernel<double, FT, true><<<grid, block, smem_bytes, stream>>>(a);
-    }
-    else
-    {
-      e = cudaFuncSetAttribute(checkKernel<double, FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-      if (e != cudaSuccess)
-        return e;
-      checkKernel<double, FT, false><<<grid, block, smem_bytes, stream>>>(a);
-    }
+    if ((e = ensureSmem(checkKernel<double, FT, true>, smem_bytes, g_dl)) != cudaSuccess)
+      return e;
+    checkKernel<double, FT, true><<<grid, block, smem_bytes, stream>>>(a);
+  }
+  else if (fp64)
+  {
+    if ((e = ensureSmem(checkKernel<double, FT, false>, smem_bytes, g_d)) != cudaSuccess)
+      return e;
+    checkKernel<double, FT, false><<<grid, block, smem_bytes, stream>>>(a);
   }
   else
   {
-    e = cudaFuncSetAttribute(checkKernel<float, FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess)
+    if ((e = ensureSmem(checkKernel<float, FT, false>, smem_bytes, g_f)) != cudaSuccess)
       return e;
     checkKernel<float, FT, false><<<grid, block, smem_bytes, stream>>>(a);
   }

@@ -40,15 +40,21 @@ struct SphereRec
 };
 
 template <typename R>
-struct BsRec  // posed per link for doBoundingSpheresIntersect (types.cpp:408-418)
+struct BsRec  // per link with spheres
 {
-  R x, y, z, r;
+  R x, y, z, r;      // BodyDecomposition::getRelativeBoundingSphere(): posed for doBoundingSpheresIntersect (types.cpp:408-418)
+  R tx, ty, tz, tr;  // OUR tight bounding sphere of the link's collision spheres (centroid, max |c_k - c| + r_k):
+                     // a conservative extra cull, it can only skip pairs that cannot collide
   int slot, s0, s1, pad;  // device-link slot, sphere range [s0, s1)
 };
 
 struct PairRec  // enabled intra-group link pair (indices into the BsRec table), i < j in dfce order
 {
   int a, b;
+  int sa0, sb0;    // first sphere of each link
+  int nb, tot;     // spheres of link b, na * nb
+  unsigned magic;  // ceil(2^16 / nb): t / nb == (t * magic) >> 16 for t < 2^16 / nb... (host checks the range)
+  int pad;
 };
 
 template <typename R>
@@ -63,7 +69,7 @@ struct ModelHeader
   R margin;     // FP32 pass: voxel-coordinate uncertainty (cells); 0 in the FP64 pass
   R pair_eps;   // FP32 pass: uncertainty of a centre distance (m)
   R bs_eps;     // FP32 pass: uncertainty of a SQUARED bounding-centre distance (m^2)
-  R pad1;
+  R tight_eps;  // slack (m) of the conservative tight-sphere cull (FP32: covers rounding; FP64: 1e-9)
 };
 
 constexpr int kLinkStrideWords = 13;  // 12 + 1: odd stride => distinct links hit distinct banks
