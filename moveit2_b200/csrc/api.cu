@@ -75,7 +75,7 @@ struct b200sv_ctx
   std::vector<uint8_t> blob_f, blob_d;
   uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0;
-  int state_stride = 0;
+  int state_stride_f = 0, state_stride_d = 0;  // shared-memory words per state (float / double blob)
   std::vector<int> link_slot;      // model link -> device slot
   std::vector<double> const_T;     // model links * 16 (base state)
   int* d_link_slot = nullptr;
@@ -84,9 +84,14 @@ struct b200sv_ctx
   uint16_t* d_tmp = nullptr;  // EDT intermediate
   // launch config
   int sm_count = 148, smem_optin = 0;
-  int warps_f = 0, warps_d = 0, blocks_per_sm = 1;
+  struct LaunchCfg
+  {
+    int tile = 32, warps = 0, blocks_per_sm = 1;
+    size_t smem = 0;
+  };
+  LaunchCfg cfg_f, cfg_d, cfg_list;  // fast pass, exact pass over all states, exact pass over the recheck list
+  int tune_tile = 0, tune_blocks = 0;
   double fp32_eps = 4e-6;
-  int tune_warps = 0;
   // streams / staging
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -170,7 +175,7 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
   h.off_pairs = off;
   off = align16(off + (int)(pairs.size() * sizeof(PairRec)));
   h.total_bytes = off;
-  h.state_stride = c.state_stride;
+  h.state_stride = sizeof(R) == 4 ? c.state_stride_f : c.state_stride_d;
   h.link_stride = kLinkStrideWords;
   h.nx = c.grid.nx;
   h.ny = c.grid.ny;
@@ -374,9 +379,14 @@ int buildTables(b200sv_ctx* c)
   c->n_dev_links = (int)links.size();
   if (links.empty())
     return fail(c, B200SV_ERR_INVALID, "no link moves with the group and none carries spheres");
-  c->state_stride = c->n_dev_links * kLinkStrideWords;
-  if ((c->state_stride & 1) == 0)
-    c->state_stride += 1;
+  // FP32: state stride = 4 (mod 32) words so the 8 lanes of a quarter-warp store to 8 distinct 16-byte bank groups;
+  // FP64: 2 (mod 16) doubles, the same condition for 16-byte accesses of 8-byte words.
+  c->state_stride_f = c->n_dev_links * kLinkStrideWords;
+  while (c->state_stride_f % 32 != 4)
+    c->state_stride_f += 4;
+  c->state_stride_d = c->n_dev_links * kLinkStrideWords;
+  while (c->state_stride_d % 16 != 2)
+    c->state_stride_d += 2;
   // ---- spheres, bounding spheres, pairs -----------------------------------------------------------------------------
   std::vector<SphereRec<double>> spheres;
   std::vector<BsRec<double>> bs;
@@ -443,8 +453,9 @@ int buildTables(b200sv_ctx* c)
         P.b = bs_of_glink[j];
         P.sa0 = A.s0;
         P.sb0 = Bb.s0;
+        P.na = A.s1 - A.s0;
         P.nb = Bb.s1 - Bb.s0;
-        P.tot = (A.s1 - A.s0) * P.nb;
+        P.tot = P.na * P.nb;
         P.magic = (65536u + P.nb - 1) / P.nb;
         // exactness of the multiply-shift division over [0, tot): checked here, not assumed
         for (int t = 0; t < P.tot; ++t)
@@ -469,22 +480,54 @@ int buildTables(b200sv_ctx* c)
   return B200SV_OK;
 }
 
-// per-warp shared memory in units of R: transforms of 32 states | sphere centres + radius (4) | bounding centres (3 + 3)
-int perWarpWords(const b200sv_ctx* c) { return 32 * c->state_stride + 4 * c->n_spheres + 6 * c->n_bs + 4; }
-
-int chooseWarps(const b200sv_ctx* c, int blob_bytes, int elem, int cap)
+// per-warp shared memory in units of R: sphere centres + radius (4) | bounding + tight centres and radii (8) |
+// transforms of `tile` states -- must match perWarpWords() in check_kernels.cu
+size_t perWarpBytes(const b200sv_ctx* c, int elem, int tile)
 {
-  const int per_warp = perWarpWords(c) * elem;
-  const int avail = c->smem_optin / std::max(1, c->blocks_per_sm) - 1024 - align16(blob_bytes) - 16;
-  int w = avail / per_warp;
-  w = std::min(w, cap);
-  return w;
+  const int ss = elem == 4 ? c->state_stride_f : c->state_stride_d;
+  return (size_t)(4 * c->n_spheres + 8 * c->n_bs + tile * ss) * elem;
 }
 
-size_t smemFor(const b200sv_ctx* c, int blob_bytes, int elem, int warps)
+// Pick (tile, warps per block, blocks per SM): the largest tile that still keeps >= 16 warps resident per SM
+// (the FK phase only uses `tile` lanes, so a smaller tile trades FK lane efficiency for latency hiding), else the
+// configuration with the most resident warps.  Limits: 227 KB of shared memory per CTA / 228 KB per SM with 1 KB
+// reserved per CTA, 64 K registers per SM, 512 threads per CTA (__launch_bounds__).
+b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, int blob_bytes)
 {
-  const size_t per_warp = (size_t)perWarpWords(c) * elem;
-  return align16(blob_bytes) + per_warp * warps + 16;
+  const int elem = fp64 ? 8 : 4;
+  b200sv_ctx::LaunchCfg best;
+  const int tiles[3] = { 32, 16, 8 };
+  for (int ti = 0; ti < 3; ++ti)
+  {
+    const int tile = from_list ? 1 : tiles[ti];
+    if (!from_list && c->tune_tile > 0 && tile != c->tune_tile)
+      continue;
+    const int regs = (checkKernelRegs(fp64, from_list, tile, c->compact_bytes) + 7) & ~7;
+    const int reg_warps = 65536 / (regs * 32);
+    const size_t pw = perWarpBytes(c, elem, tile);
+    b200sv_ctx::LaunchCfg cand;
+    for (int b = 1; b <= 4; ++b)
+    {
+      if (c->tune_blocks > 0 && b != c->tune_blocks)
+        continue;
+      const long per_block = std::min<long>(c->smem_optin, (233472L - 1024L * b) / b) - align16(blob_bytes);
+      int w = per_block > 0 ? (int)(per_block / (long)pw) : 0;
+      w = std::min(w, 16);
+      w = std::min(w, reg_warps / b);
+      if (w * b > cand.warps * cand.blocks_per_sm)
+      {
+        cand.tile = tile;
+        cand.warps = w;
+        cand.blocks_per_sm = b;
+        cand.smem = align16(blob_bytes) + pw * w;
+      }
+    }
+    if (cand.warps * cand.blocks_per_sm > best.warps * best.blocks_per_sm)
+      best = cand;
+    if (from_list || best.warps * best.blocks_per_sm >= 16)
+      break;
+  }
+  return best;
 }
 
 int uploadTables(b200sv_ctx* c)
@@ -505,13 +548,13 @@ int uploadTables(b200sv_ctx* c)
   }
   CU(c, cudaMemcpy(c->d_link_slot, c->link_slot.data(), c->link_slot.size() * sizeof(int), cudaMemcpyHostToDevice));
   CU(c, cudaMemcpy(c->d_const_T, c->const_T.data(), c->const_T.size() * sizeof(double), cudaMemcpyHostToDevice));
-  const int cap = c->tune_warps > 0 ? c->tune_warps : 16;
-  c->warps_f = chooseWarps(c, (int)c->blob_f.size(), 4, cap);
-  c->warps_d = chooseWarps(c, (int)c->blob_d.size(), 8, cap);
-  if (c->warps_f < 1 || c->warps_d < 1)
+  c->cfg_f = chooseCfg(c, false, false, (int)c->blob_f.size());
+  c->cfg_d = chooseCfg(c, true, false, (int)c->blob_d.size());
+  c->cfg_list = chooseCfg(c, true, true, (int)c->blob_d.size());
+  if (c->cfg_f.warps < 1 || c->cfg_d.warps < 1 || c->cfg_list.warps < 1)
     return fail(c, B200SV_ERR_UNSUPPORTED,
                 "robot too large for the shared-memory tile: " + std::to_string(c->n_dev_links) + " moving links need " +
-                    std::to_string(32 * c->state_stride * 8) + " bytes per warp");
+                    std::to_string(8 * c->state_stride_d * 8) + " bytes per warp");
   return B200SV_OK;
 }
 
@@ -631,6 +674,11 @@ int finishCreate(b200sv_ctx* c, int device, b200sv_ctx** out)
     return bail(fail(c, B200SV_ERR_CUDA, "cudaSetDevice failed"));
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  // profiling knobs (same meaning as b200sv_set_tuning), so a bench run under ncu can pin a configuration
+  if (const char* e = getenv("B200SV_TILE"))
+    c->tune_tile = atoi(e);
+  if (const char* e = getenv("B200SV_BLOCKS"))
+    c->tune_blocks = atoi(e);
   if ((rc = validateModel(c)) != B200SV_OK)
     return bail(rc);
   if ((rc = initGrid(c)) != B200SV_OK)
@@ -674,22 +722,24 @@ int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_
   a.list_cap = (unsigned)std::min<size_t>(c->d_list.cap, 0xffffffffu);
   a.list = c->d_list.p;
   a.list_count = c->d_count;
-  const int grid = c->sm_count * c->blocks_per_sm;
   if (flags & B200SV_CHECK_FP64)
   {
     a.model = c->d_blob_d;
     a.model_bytes = (int)c->blob_d.size();
-    CU(c, launchCheck<FT>(a, true, false, grid, c->warps_d * 32, smemFor(c, a.model_bytes, 8, c->warps_d), s));
+    CU(c, launchCheck<FT>(a, true, false, c->cfg_d.tile, c->sm_count * c->cfg_d.blocks_per_sm, c->cfg_d.warps * 32,
+                          c->cfg_d.smem, s));
     return B200SV_OK;
   }
   CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), s));
   a.model = c->d_blob_f;
   a.model_bytes = (int)c->blob_f.size();
-  CU(c, launchCheck<FT>(a, false, false, grid, c->warps_f * 32, smemFor(c, a.model_bytes, 4, c->warps_f), s));
+  CU(c, launchCheck<FT>(a, false, false, c->cfg_f.tile, c->sm_count * c->cfg_f.blocks_per_sm, c->cfg_f.warps * 32,
+                        c->cfg_f.smem, s));
   // exact pass over the undecided states; the count stays on the device, so the launch is unconditional
   a.model = c->d_blob_d;
   a.model_bytes = (int)c->blob_d.size();
-  CU(c, launchCheck<FT>(a, true, true, grid, c->warps_d * 32, smemFor(c, a.model_bytes, 8, c->warps_d), s));
+  CU(c, launchCheck<FT>(a, true, true, 1, c->sm_count * c->cfg_list.blocks_per_sm, c->cfg_list.warps * 32,
+                        c->cfg_list.smem, s));
   return B200SV_OK;
 }
 
@@ -1084,8 +1134,11 @@ int b200sv_fk_batch(b200sv_ctx* c, const double* q, size_t n, int precision_bits
   a.const_T = c->d_const_T;
   a.out = c->d_fk.p;
   const int elem = fp64 ? 8 : 4;
-  const int warps = std::max(1, std::min(4, fp64 ? c->warps_d : c->warps_f));
-  const size_t smem = align16(a.model_bytes) + (size_t)warps * 32 * c->state_stride * elem + 16;
+  const int ss = fp64 ? c->state_stride_d : c->state_stride_f;
+  int warps = 4;
+  while (warps > 1 && align16(a.model_bytes) + (size_t)warps * 32 * ss * elem > (size_t)c->smem_optin)
+    --warps;
+  const size_t smem = align16(a.model_bytes) + (size_t)warps * 32 * ss * elem;
   const int grid = (int)std::min<size_t>((n + 32 * warps - 1) / (32 * warps), (size_t)c->sm_count * 4);
   CU(c, launchFk(a, fp64, grid, warps * 32, smem, c->stream));
   CU(c, cudaMemcpyAsync(link_T, c->d_fk.p, out_n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1110,7 +1163,7 @@ int b200sv_sphere_centers(b200sv_ctx* c, const double* q_one, double* centers)
   a.model_bytes = (int)c->blob_d.size();
   a.q = c->d_q.p;
   a.n_states = 1;
-  const size_t smem = align16(a.model_bytes) + (size_t)c->state_stride * 8 + 16;
+  const size_t smem = align16(a.model_bytes) + (size_t)c->state_stride_d * 8;
   CU(c, launchSphereCenters(a, c->d_fk.p, smem, c->stream));
   CU(c, cudaMemcpyAsync(centers, c->d_fk.p, (size_t)c->n_spheres * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -1210,7 +1263,7 @@ int b200sv_gather_roofline(b200sv_ctx* c, size_t n_reads, int iters, double* gbs
   return B200SV_OK;
 }
 
-int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int warps_per_block, int blocks_per_sm)
+int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int tile, int blocks_per_sm)
 {
   if (!c)
     return B200SV_ERR_INVALID;
@@ -1220,10 +1273,10 @@ int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int warps_per_block, int
   cudaSetDevice(c->device);
   if (fp32_eps_m > 0.0)
     c->fp32_eps = fp32_eps_m;
-  if (warps_per_block > 0)
-    c->tune_warps = warps_per_block;
+  if (tile == 8 || tile == 16 || tile == 32)
+    c->tune_tile = tile;
   if (blocks_per_sm > 0)
-    c->blocks_per_sm = blocks_per_sm;
+    c->tune_blocks = blocks_per_sm;
   CU(c, cudaStreamSynchronize(c->stream));
   int rc = buildTables(c);
   if (rc != B200SV_OK)

@@ -4,26 +4,27 @@
 //   RobotState::setJointGroupPositions / updateMimicJoints / updateLinkTransformsInternal
 //                                                  robot_state/src/robot_state.cpp:571-584, 210-220, 793-848
 //   {Revolute,Prismatic,Planar,Floating,Fixed}JointModel::computeTransform
-//                                                  robot_model/src/*_joint_model.cpp
+//                                                  robot_model/src/{revolute,prismatic,planar,floating,fixed}_joint_model.cpp
 //   PosedBodySphereDecomposition::updatePose       collision_distance_field/src/collision_distance_field_types.cpp:388-395
 //   getCollisionSphereCollision + DistanceField::getDistanceGradient (centre voxel only: the gradient never
 //   influences the boolean)                        types.cpp:211-236, distance_field/src/distance_field.cpp:73-97
 //   getEnvironmentCollisions / getSelfCollisions / getIntraGroupCollisions + doBoundingSpheresIntersect
 //                                                  collision_env_distance_field.cpp:1561-1643, 274-353, 430-642; types.cpp:408-418
 //
-// Mapping (B200, sm_100a): persistent CTAs, one per SM slot.  Each warp owns a tile of 32 consecutive states.
-//   phase 1  thread-per-state FK: lane s walks the device links in index order (parents first); link transforms
-//            go to shared memory as 3x4 row-major, state stride odd, link stride 13 => conflict-free for both the
-//            per-lane writes of phase 1 and the per-link reads of phase 2.
-//   phase 2  warp-per-state checks: lanes own spheres; each lane poses its sphere, converts the centre to a voxel
-//            and gathers ONE byte from the world field and one from the self field (L2-resident compact d^2),
-//            compares against the sphere's integer threshold; early exit is warp-uniform.  Intra-group: lanes
-//            test link pairs' bounding spheres, the surviving pairs are expanded into sphere pairs over lanes.
+// Mapping (B200, sm_100a): persistent CTAs.  Each warp owns a tile of kTile consecutive states.
+//   phase 1  thread-per-state FK: lane s (< kTile) walks the device links in index order (parents first); link
+//            transforms go to shared memory as 3x4 row-major rows of 16 bytes (one 128-bit access per row).
+//   phase 2  warp-per-state checks: lanes own spheres (two per lane per pass, for memory-level parallelism); each
+//            lane poses its sphere, converts the centre to a voxel and gathers ONE byte from the world field and one
+//            from the self field (L2-resident compact d^2), compares against the sphere's integer threshold; early
+//            exit is warp-uniform.  Intra-group: lanes test link pairs (the reference's bounding-sphere cull plus a
+//            conservative tight-sphere cull), then for each surviving link pair the spheres of either link are
+//            tested against the other link's tight sphere, and only the survivors meet sphere against sphere.
 // Precision: the fast pass is FP32 (template R = float).  A sphere whose voxel coordinate is within `margin` of a
 // cell face, or a pair whose distance is within eps of its threshold, is evaluated for BOTH outcomes; if the
 // state's boolean could depend on that, the state index is appended to a recheck list and the exact pass
 // (R = double, same code) recomputes it.  The FP64 pass restates the reference's double arithmetic
-// operation by operation.
+// operation by operation.  The conservative culls only ever skip pairs that cannot collide, so they change no result.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -48,41 +49,66 @@ struct Smem
   const PairRec* pairs;
 };
 
-template <typename R>
-__device__ __forceinline__ void sincosR(R x, R* s, R* c);
-template <>
-__device__ __forceinline__ void sincosR<float>(float x, float* s, float* c)
+__device__ __forceinline__ void sincosR(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincosR(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ float sqrtR(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrtR(double x) { return sqrt(x); }
+__device__ __forceinline__ float floorR(float x) { return floorf(x); }
+__device__ __forceinline__ double floorR(double x) { return floor(x); }
+
+// 12 consecutive, 16-byte aligned values <-> registers with 128-bit shared-memory accesses
+__device__ __forceinline__ void load12(const float* p, float* o)
 {
-  sincosf(x, s, c);
+  const float4* v = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    const float4 t = v[i];
+    o[4 * i + 0] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
+  }
 }
-template <>
-__device__ __forceinline__ void sincosR<double>(double x, double* s, double* c)
+__device__ __forceinline__ void load12(const double* p, double* o)
 {
-  sincos(x, s, c);
+  const double2* v = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+  {
+    const double2 t = v[i];
+    o[2 * i + 0] = t.x; o[2 * i + 1] = t.y;
+  }
 }
-template <typename R>
-__device__ __forceinline__ R sqrtR(R x);
-template <>
-__device__ __forceinline__ float sqrtR<float>(float x)
+__device__ __forceinline__ void store12(float* p, const float* o)
 {
-  return sqrtf(x);
+  float4* v = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    v[i] = make_float4(o[4 * i + 0], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
 }
-template <>
-__device__ __forceinline__ double sqrtR<double>(double x)
+__device__ __forceinline__ void store12(double* p, const double* o)
 {
-  return sqrt(x);
+  double2* v = reinterpret_cast<double2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    v[i] = make_double2(o[2 * i + 0], o[2 * i + 1]);
 }
-template <typename R>
-__device__ __forceinline__ R floorR(R x);
-template <>
-__device__ __forceinline__ float floorR<float>(float x)
+__device__ __forceinline__ void load4(const float* p, float* o)
 {
-  return floorf(x);
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
 }
-template <>
-__device__ __forceinline__ double floorR<double>(double x)
+__device__ __forceinline__ void load4(const double* p, double* o)
 {
-  return floor(x);
+  const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d)
+{
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(double* p, double a, double b, double c, double d)
+{
+  reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+  reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
 }
 
 // A(3x4) * B(3x4) with implicit (0,0,0,1) rows; accumulation order k = 0..3 as Eigen's fixed-size product.
@@ -142,16 +168,14 @@ __device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restri
   for (int l = 0; l < n_links; ++l)
   {
     const LinkRec<R>& L = m.links[l];
-    R A[12];
+    R A[12], Lo[12];
+    load12(L.o, Lo);
     if (L.parent >= 0)
     {
       R P[12];
-      const R* src = T + L.parent * kLinkStrideWords;
-#pragma unroll
-      for (int i = 0; i < 12; ++i)
-        P[i] = src[i];
+      load12(T + L.parent * kLinkStrideWords, P);
       if (L.has_origin)
-        mulAffine<R>(P, L.o, A);
+        mulAffine<R>(P, Lo, A);
       else
       {
 #pragma unroll
@@ -163,7 +187,7 @@ __device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restri
     {
 #pragma unroll
       for (int i = 0; i < 12; ++i)
-        A[i] = L.o[i];
+        A[i] = Lo[i];
     }
     R O[12];
     switch (L.type)
@@ -172,7 +196,7 @@ __device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restri
       {  // revolute_joint_model.cpp:250-287
         const R q = varValue<R>(m.vars[L.var], qrow);
         R s, c;
-        sincosR<R>(q, &s, &c);
+        sincosR(q, &s, &c);
         const R x = L.ax[0], y = L.ax[1], z = L.ax[2];
         const R t = R(1) - c;
         const R txy = t * (x * y), txz = t * (x * z), tyz = t * (y * z);
@@ -206,7 +230,7 @@ __device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restri
         const R px = varValue<R>(m.vars[L.var], qrow), py = varValue<R>(m.vars[L.var + 1], qrow);
         const R th = varValue<R>(m.vars[L.var + 2], qrow);
         R s, c;
-        sincosR<R>(th, &s, &c);
+        sincosR(th, &s, &c);
         R J[12] = { c, -s, R(0), px, s, c, R(0), py, R(0), R(0), (R(1) - c) + c, R(0) };
         mulAffine<R>(A, J, O);
         break;
@@ -217,7 +241,7 @@ __device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restri
                 pz = varValue<R>(m.vars[L.var + 2], qrow);
         R x = varValue<R>(m.vars[L.var + 3], qrow), y = varValue<R>(m.vars[L.var + 4], qrow),
           z = varValue<R>(m.vars[L.var + 5], qrow), w = varValue<R>(m.vars[L.var + 6], qrow);
-        const R n = sqrtR<R>(x * x + y * y + z * z + w * w);
+        const R n = sqrtR(x * x + y * y + z * z + w * w);
         x /= n; y /= n; z /= n; w /= n;
         const R tx = R(2) * x, ty = R(2) * y, tz = R(2) * z;
         const R twx = tx * w, twy = ty * w, twz = tz * w;
@@ -235,16 +259,14 @@ __device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restri
           O[i] = A[i];
         break;
     }
-    R* dst = T + l * kLinkStrideWords;
-#pragma unroll
-    for (int i = 0; i < 12; ++i)
-      dst[i] = O[i];
+    store12(T + l * kLinkStrideWords, O);
   }
 }
 
+// Isometry3d * Vector3d from a 3x4 row-major transform held in registers: linear * p + translation
 template <typename R>
 __device__ __forceinline__ void posePoint(const R* T, R x, R y, R z, R& ox, R& oy, R& oz)
-{  // Isometry3d * Vector3d: linear * p + translation
+{
   R s = T[0] * x;
   s += T[1] * y;
   s += T[2] * z;
@@ -257,12 +279,6 @@ __device__ __forceinline__ void posePoint(const R* T, R x, R y, R z, R& ox, R& o
   s += T[9] * y;
   s += T[10] * z;
   oz = s + T[11];
-}
-
-template <typename FT>
-__device__ __forceinline__ int ldField(const FT* __restrict__ f, long idx)
-{
-  return static_cast<int>(__ldg(f + idx));
 }
 
 template <typename R>
@@ -284,6 +300,88 @@ __device__ __forceinline__ Smem<R> loadModel(const uint8_t* __restrict__ g_model
   return m;
 }
 
+// What one lane knows about one of its spheres after posing it: where to read the fields, and whether FP32
+// rounding leaves the voxel undetermined.
+struct Probe
+{
+  int idx;         // voxel index of the certain cell, -1: nothing to read (no thresholds / outside the 1-cell margin)
+  int thr_w, thr_s;
+  bool risky;      // FP32 only: the centre is within `margin` of a cell face
+  int gx, gy, gz, hx, hy, hz;
+};
+
+template <typename R>
+__device__ __forceinline__ Probe probeSphere(const Smem<R>& m, const R* T, R* cent, int k, bool do_world, bool do_self)
+{
+  constexpr bool kExact = sizeof(R) == 8;
+  const ModelHeader<R>& h = *m.h;
+  Probe p;
+  p.idx = -1;
+  p.risky = false;
+  p.thr_w = p.thr_s = 0;
+  p.gx = p.gy = p.gz = p.hx = p.hy = p.hz = 0;
+  if (k >= h.n_spheres)
+    return p;
+  const SphereRec<R> sp = m.spheres[k];
+  R Tl[12];
+  load12(T + sp.slot * kLinkStrideWords, Tl);
+  R cx, cy, cz;
+  posePoint<R>(Tl, sp.x, sp.y, sp.z, cx, cy, cz);
+  store4(cent + k * 4, cx, cy, cz, sp.r);
+  p.thr_w = do_world ? sp.thr : 0;
+  p.thr_s = do_self ? sp.thr_self : 0;
+  if ((p.thr_w | p.thr_s) == 0)
+    return p;
+  // VoxelGrid::getCellFromLocation (voxel_grid.hpp:522): floor((loc - origin_minus) * oo_resolution)
+  const R fx = (cx - h.om[0]) * h.oo_res, fy = (cy - h.om[1]) * h.oo_res, fz = (cz - h.om[2]) * h.oo_res;
+  if (kExact)
+  {
+    p.gx = p.hx = static_cast<int>(floorR(fx));
+    p.gy = p.hy = static_cast<int>(floorR(fy));
+    p.gz = p.hz = static_cast<int>(floorR(fz));
+  }
+  else
+  {
+    p.gx = static_cast<int>(floorR(fx - h.margin));
+    p.hx = static_cast<int>(floorR(fx + h.margin));
+    p.gy = static_cast<int>(floorR(fy - h.margin));
+    p.hy = static_cast<int>(floorR(fy + h.margin));
+    p.gz = static_cast<int>(floorR(fz - h.margin));
+    p.hz = static_cast<int>(floorR(fz + h.margin));
+    p.risky = (p.gx != p.hx) | (p.gy != p.hy) | (p.gz != p.hz);
+  }
+  // DistanceField::getDistanceGradient bounds (distance_field.cpp:82): a 1-cell margin is "out of bounds", which
+  // reads as max_distance and therefore never collides (types.cpp:229).
+  if (!p.risky && p.gx >= 1 && p.gy >= 1 && p.gz >= 1 && p.gx < h.nx - 1 && p.gy < h.ny - 1 && p.gz < h.nz - 1)
+    p.idx = (p.gx * h.ny + p.gy) * h.nz + p.gz;  // VoxelGrid::ref (voxel_grid.hpp:425); < 2^31 voxels (host checks)
+  return p;
+}
+
+// FP32 only, rare: evaluate every candidate cell of a sphere whose voxel is uncertain.
+template <typename R, typename FT>
+__device__ __noinline__ void riskySphere(const ModelHeader<R>& h, const Probe& p, const FT* __restrict__ world,
+                                         const FT* __restrict__ self, bool& hit, bool& amb)
+{
+  bool any = false, all = true;
+  for (int ix = p.gx; ix <= p.hx; ++ix)
+    for (int iy = p.gy; iy <= p.hy; ++iy)
+      for (int iz = p.gz; iz <= p.hz; ++iz)
+      {
+        bool c = false;
+        if (ix >= 1 && iy >= 1 && iz >= 1 && ix < h.nx - 1 && iy < h.ny - 1 && iz < h.nz - 1)
+        {
+          const int idx = (ix * h.ny + iy) * h.nz + iz;
+          const int dw = p.thr_w ? static_cast<int>(__ldg(world + idx)) : 0x7fffffff;
+          const int ds = p.thr_s ? static_cast<int>(__ldg(self + idx)) : 0x7fffffff;
+          c = (dw < p.thr_w) | (ds < p.thr_s);
+        }
+        any |= c;
+        all &= c;
+      }
+  hit |= all;
+  amb |= (any && !all);
+}
+
 // One state, warp-cooperative.  Returns (via uniform bools) whether it certainly collides / is undecidable in R.
 template <typename R, typename FT>
 __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent, R* bsc, const FT* __restrict__ world,
@@ -294,96 +392,44 @@ __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent
   const ModelHeader<R>& h = *m.h;
   const bool do_world = (flags & 1u) != 0, do_self = (flags & 2u) != 0, do_intra = (flags & 4u) != 0;
   bool hit = false, amb = false;
-  const int nx = h.nx, ny = h.ny, nz = h.nz;
-  for (int base = 0; base < h.n_spheres; base += 32)
+  for (int base = 0; base < h.n_spheres; base += 64)
   {
-    const int k = base + lane;
-    if (k < h.n_spheres)
+    // two spheres per lane: both poses, then all four gathers in flight, then the compares
+    const Probe p0 = probeSphere<R>(m, T, cent, base + lane, do_world, do_self);
+    const Probe p1 = probeSphere<R>(m, T, cent, base + 32 + lane, do_world, do_self);
+    int dw0 = 0x7fffffff, ds0 = 0x7fffffff, dw1 = 0x7fffffff, ds1 = 0x7fffffff;
+    if (p0.idx >= 0)
     {
-      const SphereRec<R> sp = m.spheres[k];
-      R cx, cy, cz;
-      posePoint<R>(T + sp.slot * kLinkStrideWords, sp.x, sp.y, sp.z, cx, cy, cz);
-      cent[k * 4 + 0] = cx;
-      cent[k * 4 + 1] = cy;
-      cent[k * 4 + 2] = cz;
-      cent[k * 4 + 3] = sp.r;
-      const int thr_w = do_world ? sp.thr : 0;
-      const int thr_s = do_self ? sp.thr_self : 0;
-      if (thr_w | thr_s)
-      {
-        // VoxelGrid::getCellFromLocation (voxel_grid.hpp:522): floor((loc - origin_minus) * oo_resolution)
-        const R fx = (cx - h.om[0]) * h.oo_res, fy = (cy - h.om[1]) * h.oo_res, fz = (cz - h.om[2]) * h.oo_res;
-        int gx, gy, gz, hx, hy, hz;
-        if (kExact)
-        {
-          gx = hx = static_cast<int>(floorR<R>(fx));
-          gy = hy = static_cast<int>(floorR<R>(fy));
-          gz = hz = static_cast<int>(floorR<R>(fz));
-        }
-        else
-        {
-          gx = static_cast<int>(floorR<R>(fx - h.margin));
-          hx = static_cast<int>(floorR<R>(fx + h.margin));
-          gy = static_cast<int>(floorR<R>(fy - h.margin));
-          hy = static_cast<int>(floorR<R>(fy + h.margin));
-          gz = static_cast<int>(floorR<R>(fz - h.margin));
-          hz = static_cast<int>(floorR<R>(fz + h.margin));
-        }
-        if (kExact || (gx == hx && gy == hy && gz == hz))
-        {
-          // DistanceField::getDistanceGradient bounds (distance_field.cpp:82): a 1-cell margin is "out of bounds",
-          // which reads as max_distance and therefore never collides (types.cpp:229).
-          if (gx >= 1 && gy >= 1 && gz >= 1 && gx < nx - 1 && gy < ny - 1 && gz < nz - 1)
-          {
-            const long idx = (static_cast<long>(gx) * ny + gy) * nz + gz;  // VoxelGrid::ref (voxel_grid.hpp:425)
-            const int dw = thr_w ? ldField<FT>(world, idx) : 0x7fffffff;
-            const int ds = thr_s ? ldField<FT>(self, idx) : 0x7fffffff;
-            hit |= (dw < thr_w) | (ds < thr_s);
-          }
-        }
-        else
-        {
-          // FP32 only: the centre is within `margin` of a cell face.  Evaluate every candidate cell.
-          bool any = false, all = true;
-          for (int ix = gx; ix <= hx; ++ix)
-            for (int iy = gy; iy <= hy; ++iy)
-              for (int iz = gz; iz <= hz; ++iz)
-              {
-                bool c = false;
-                if (ix >= 1 && iy >= 1 && iz >= 1 && ix < nx - 1 && iy < ny - 1 && iz < nz - 1)
-                {
-                  const long idx = (static_cast<long>(ix) * ny + iy) * nz + iz;
-                  const int dw = thr_w ? ldField<FT>(world, idx) : 0x7fffffff;
-                  const int ds = thr_s ? ldField<FT>(self, idx) : 0x7fffffff;
-                  c = (dw < thr_w) | (ds < thr_s);
-                }
-                any |= c;
-                all &= c;
-              }
-          hit |= all;
-          amb |= (any && !all);
-        }
-      }
+      if (p0.thr_w) dw0 = static_cast<int>(__ldg(world + p0.idx));
+      if (p0.thr_s) ds0 = static_cast<int>(__ldg(self + p0.idx));
+    }
+    if (p1.idx >= 0)
+    {
+      if (p1.thr_w) dw1 = static_cast<int>(__ldg(world + p1.idx));
+      if (p1.thr_s) ds1 = static_cast<int>(__ldg(self + p1.idx));
+    }
+    hit |= (dw0 < p0.thr_w) | (ds0 < p0.thr_s) | (dw1 < p1.thr_w) | (ds1 < p1.thr_s);
+    if (!kExact)
+    {
+      if (p0.risky) riskySphere<R, FT>(h, p0, world, self, hit, amb);
+      if (p1.risky) riskySphere<R, FT>(h, p1, world, self, hit, amb);
     }
   }
   hit = __any_sync(kFull, hit);
   if (!hit && do_intra && h.n_pairs > 0)
   {
-    // bounding-sphere centres of the links (PosedBodySphereDecomposition::updatePose, types.cpp:391) and the
-    // centres of our tight spheres
+    // Per link with spheres: the reference's bounding-sphere centre (PosedBodySphereDecomposition::updatePose,
+    // types.cpp:391) and the centre of our tight sphere; radii alongside so pair tests read one place.
     for (int b = lane; b < h.n_bs; b += 32)
     {
       const BsRec<R> r = m.bs[b];
-      const R* Tl = T + r.slot * kLinkStrideWords;
+      R Tl[12];
+      load12(T + r.slot * kLinkStrideWords, Tl);
       R x, y, z;
       posePoint<R>(Tl, r.x, r.y, r.z, x, y, z);
-      bsc[b * 6 + 0] = x;
-      bsc[b * 6 + 1] = y;
-      bsc[b * 6 + 2] = z;
+      store4(bsc + b * 8, x, y, z, r.r);
       posePoint<R>(Tl, r.tx, r.ty, r.tz, x, y, z);
-      bsc[b * 6 + 3] = x;
-      bsc[b * 6 + 4] = y;
-      bsc[b * 6 + 5] = z;
+      store4(bsc + b * 8 + 4, x, y, z, r.tr);
     }
     __syncwarp();
     bool phit = false;
@@ -394,17 +440,20 @@ __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent
       if (p < h.n_pairs)
       {
         const PairRec pr = m.pairs[p];
-        const R* ca = bsc + pr.a * 6;
-        const R* cb = bsc + pr.b * 6;
+        R ca[4], cb[4], ta[4], tb[4];
+        load4(bsc + pr.a * 8, ca);
+        load4(bsc + pr.b * 8, cb);
+        load4(bsc + pr.a * 8 + 4, ta);
+        load4(bsc + pr.b * 8 + 4, tb);
         const R ex = ca[0] - cb[0], ey = ca[1] - cb[1], ez = ca[2] - cb[2];
         const R d2 = ex * ex + ey * ey + ez * ez;
         // reference quirk kept: SQUARED centre distance against the plain radius sum (types.cpp:416-417)
-        const R rs = m.bs[pr.a].r + m.bs[pr.b].r;
+        const R rs = ca[3] + cb[3];
         // conservative cull: every sphere of a link lies inside its tight sphere, so separated tight spheres
         // (with slack for rounding) mean no sphere pair of the two links can touch
-        const R fx = ca[3] - cb[3], fy = ca[4] - cb[4], fz = ca[5] - cb[5];
+        const R fx = ta[0] - tb[0], fy = ta[1] - tb[1], fz = ta[2] - tb[2];
         const R t2 = fx * fx + fy * fy + fz * fz;
-        const R rt = m.bs[pr.a].tr + m.bs[pr.b].tr + h.tight_eps;
+        const R rt = ta[3] + tb[3] + h.tight_eps;
         const bool near = t2 < rt * rt;
         if (kExact)
           live = live_certain = near && (d2 < rs);
@@ -422,24 +471,74 @@ __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent
         mask &= mask - 1;
         const bool cert = (cmask >> bit) & 1u;
         const PairRec pr = m.pairs[p0 + bit];
-        for (int t = lane; t < pr.tot; t += 32)
+        if (pr.na + pr.nb <= 32)
         {
-          const int ia = static_cast<int>((static_cast<unsigned>(t) * pr.magic) >> 16);  // t / nb (range checked on the host)
-          const R* pa = cent + (pr.sa0 + ia) * 4;
-          const R* pb = cent + (pr.sb0 + (t - ia * pr.nb)) * 4;
-          const R gx2 = pa[0] - pb[0], gy2 = pa[1] - pb[1], gz2 = pa[2] - pb[2];
-          const R dd = gx2 * gx2 + gy2 * gy2 + gz2 * gz2;
-          const R rsum = pa[3] + pb[3];
-          if (kExact)
-            phit |= sqrtR<R>(dd) < rsum;  // gradient.norm() < r1 + r2 (collision_env_distance_field.cpp:577-583)
-          else
+          // level 2: lanes [0, na) hold the spheres of link a and test them against b's tight sphere, lanes
+          // [na, na + nb) hold b's spheres and test against a's.  Only survivors can be part of a touching pair.
+          R me[4] = { R(0), R(0), R(0), R(0) };
+          bool inside = false;
+          if (lane < pr.na + pr.nb)
           {
-            // squared form of dist < rsum -+ eps (both sides positive); the 1e-7 in pair_eps covers its rounding
-            const R lo = rsum - h.pair_eps, hi = rsum + h.pair_eps;
-            const bool c_cert = (lo > R(0)) && (dd < lo * lo);
-            const bool c_maybe = dd < hi * hi;
-            phit |= (cert && c_cert);
-            amb |= (c_maybe && !(cert && c_cert));
+            const bool is_a = lane < pr.na;
+            load4(cent + (is_a ? pr.sa0 + lane : pr.sb0 + lane - pr.na) * 4, me);
+            R ot[4];
+            load4(bsc + (is_a ? pr.b : pr.a) * 8 + 4, ot);
+            const R gx = me[0] - ot[0], gy = me[1] - ot[1], gz = me[2] - ot[2];
+            const R lim = me[3] + ot[3] + h.tight_eps;
+            inside = (gx * gx + gy * gy + gz * gz) < lim * lim;
+          }
+          const unsigned mk = __ballot_sync(kFull, inside);
+          unsigned ma = mk & ((1u << pr.na) - 1u);
+          const bool is_b = inside && lane >= pr.na;
+          if ((mk >> pr.na) == 0u)
+            ma = 0u;
+          while (ma)
+          {
+            const int ia = __ffs(ma) - 1;
+            ma &= ma - 1;
+            R pa[4];
+            load4(cent + (pr.sa0 + ia) * 4, pa);  // broadcast read
+            if (is_b)
+            {
+              const R gx2 = pa[0] - me[0], gy2 = pa[1] - me[1], gz2 = pa[2] - me[2];
+              const R dd = gx2 * gx2 + gy2 * gy2 + gz2 * gz2;
+              const R rsum = pa[3] + me[3];
+              if (kExact)
+                phit |= sqrtR(dd) < rsum;  // gradient.norm() < r1 + r2 (collision_env_distance_field.cpp:577-583)
+              else
+              {
+                // squared form of dist < rsum -+ eps (both sides positive); the 1e-7 in pair_eps covers its rounding
+                const R lo = rsum - h.pair_eps, hi = rsum + h.pair_eps;
+                const bool c_cert = (lo > R(0)) && (dd < lo * lo);
+                const bool c_maybe = dd < hi * hi;
+                phit |= (cert && c_cert);
+                amb |= (c_maybe && !(cert && c_cert));
+              }
+            }
+          }
+        }
+        else
+        {
+          // links with more than 32 spheres between them: plain enumeration of the na * nb sphere pairs
+          for (int t = lane; t < pr.tot; t += 32)
+          {
+            const int ia = static_cast<int>((static_cast<unsigned>(t) * pr.magic) >> 16);  // t / nb
+            R pa[4], pb[4];
+            load4(cent + (pr.sa0 + ia) * 4, pa);
+            load4(cent + (pr.sb0 + (t - ia * pr.nb)) * 4, pb);
+            const R gx2 = pa[0] - pb[0], gy2 = pa[1] - pb[1], gz2 = pa[2] - pb[2];
+            const R dd = gx2 * gx2 + gy2 * gy2 + gz2 * gz2;
+            const R rsum = pa[3] + pb[3];
+            if (kExact)
+              phit |= sqrtR(dd) < rsum;
+            else
+            {
+              const R lo = rsum - h.pair_eps, hi = rsum + h.pair_eps;
+              const bool c_cert = (lo > R(0)) && (dd < lo * lo);
+              const bool c_maybe = dd < hi * hi;
+              phit |= (cert && c_cert);
+              amb |= (c_maybe && !(cert && c_cert));
+            }
           }
         }
       }
@@ -451,25 +550,31 @@ __device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent
   amb_out = amb && !hit;
 }
 
-// Dynamic shared memory: [model blob][per warp: transforms 32 * state_stride | sphere centres | bounding centres]
-template <typename R, typename FT, bool kFromList>
+// Per-warp shared memory, in units of R (all 16-byte aligned): sphere centres + radius | link bounding / tight
+// centres + radii | transforms of kTile states
+template <typename R>
+__device__ __forceinline__ int perWarpWords(const ModelHeader<R>& h, int tile)
+{
+  return 4 * h.n_spheres + 8 * h.n_bs + tile * h.state_stride;
+}
+
+// Dynamic shared memory: [model blob][per warp: cent | bsc | Ts]
+template <typename R, typename FT, bool kFromList, int kTile>
 __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   const Smem<R> m = loadModel<R>(a.model, a.model_bytes, smem);
   const ModelHeader<R>& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  const int per_warp = 32 * h.state_stride + 4 * h.n_spheres + 6 * h.n_bs + 4;
-  R* wbase = reinterpret_cast<R*>(smem + ((h.total_bytes + 15) & ~15)) + static_cast<size_t>(warp) * per_warp;
-  R* cent = wbase;
+  R* cent = reinterpret_cast<R*>(smem + h.total_bytes) + static_cast<size_t>(warp) * perWarpWords<R>(h, kTile);
   R* bsc = cent + 4 * h.n_spheres;
-  R* Ts = bsc + 6 * h.n_bs;
+  R* Ts = bsc + 8 * h.n_bs;
 
   unsigned long long n = a.n_states;
   if (kFromList)
     n = *a.list_count < a.list_cap ? *a.list_count : a.list_cap;
-  // The recheck list is short: one state per warp keeps its latency at one FK + one check instead of 32 in a row.
-  constexpr int kTile = kFromList ? 1 : 32;
+  // kFromList runs with kTile = 1: the recheck list is short, and one state per warp keeps its latency at one FK +
+  // one check instead of a tile of them in a row.
   const unsigned long long n_tiles = (n + kTile - 1) / kTile;
   for (unsigned long long tile = static_cast<unsigned long long>(blockIdx.x) * warps + warp; tile < n_tiles;
        tile += static_cast<unsigned long long>(gridDim.x) * warps)
@@ -502,7 +607,14 @@ __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
     else
     {
       if (lane == 0)
-        a.bitmap[tile] = valid_word;
+      {
+        if (kTile == 32)
+          a.bitmap[tile] = valid_word;
+        else if (kTile == 16)
+          reinterpret_cast<uint16_t*>(a.bitmap)[tile] = static_cast<uint16_t>(valid_word);
+        else
+          reinterpret_cast<uint8_t*>(a.bitmap)[tile] = static_cast<uint8_t>(valid_word);
+      }
       if (flag_word)
       {
         const int c = __popc(flag_word);
@@ -529,7 +641,7 @@ __global__ void __launch_bounds__(128) fkKernel(FkArgs a)
   const Smem<R> m = loadModel<R>(a.model, a.model_bytes, smem);
   const ModelHeader<R>& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  R* Ts = reinterpret_cast<R*>(smem + ((h.total_bytes + 15) & ~15)) + static_cast<size_t>(warp) * 32 * h.state_stride;
+  R* Ts = reinterpret_cast<R*>(smem + h.total_bytes) + static_cast<size_t>(warp) * 32 * h.state_stride;
   const unsigned long long n_tiles = (a.n_states + 31) / 32;
   for (unsigned long long tile = static_cast<unsigned long long>(blockIdx.x) * warps + warp; tile < n_tiles;
        tile += static_cast<unsigned long long>(gridDim.x) * warps)
@@ -565,7 +677,7 @@ __global__ void sphereCentersKernel(FkArgs a, double* centers)
   extern __shared__ __align__(16) uint8_t smem[];
   const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
   const ModelHeader<double>& h = *m.h;
-  double* Ts = reinterpret_cast<double*>(smem + ((h.total_bytes + 15) & ~15));
+  double* Ts = reinterpret_cast<double*>(smem + h.total_bytes);
   if (threadIdx.x == 0)
     fkState<double>(m, a.q, Ts);
   __syncthreads();
@@ -600,63 +712,91 @@ __global__ void gatherKernel(const uint8_t* __restrict__ field, unsigned long lo
   if (acc == 0xffffffffu)
     *sink = acc;
 }
-}  // namespace
 
 // cudaFuncSetAttribute is a host-side driver call: do it when the requirement grows, not on every launch.
-template <typename K>
-cudaError_t ensureSmem(K kernel, size_t smem_bytes, size_t& granted)
+struct SmemGrant
 {
-  if (smem_bytes <= granted)
+  size_t granted[16] = { 0 };
+};
+
+template <typename K>
+cudaError_t ensureSmem(K kernel, size_t smem_bytes, SmemGrant& g)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (smem_bytes <= g.granted[dev])
     return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e == cudaSuccess)
-    granted = smem_bytes;
+    g.granted[dev] = smem_bytes;
   return e;
 }
 
-template <typename FT>
-cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int grid, int block, size_t smem_bytes,
-                        cudaStream_t stream)
+template <typename R, typename FT, bool kList, int kTile>
+cudaError_t launchOne(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-  static size_t g_dl = 0, g_d = 0, g_f = 0;  // per FT instantiation
-  cudaError_t e;
-  if (fp64 && from_list)
-  {
-    if ((e = ensureSmem(checkKernel<double, FT, true>, smem_bytes, g_dl)) != cudaSuccess)
-      return e;
-    checkKernel<double, FT, true><<<grid, block, smem_bytes, stream>>>(a);
-  }
-  else if (fp64)
-  {
-    if ((e = ensureSmem(checkKernel<double, FT, false>, smem_bytes, g_d)) != cudaSuccess)
-      return e;
-    checkKernel<double, FT, false><<<grid, block, smem_bytes, stream>>>(a);
-  }
-  else
-  {
-    if ((e = ensureSmem(checkKernel<float, FT, false>, smem_bytes, g_f)) != cudaSuccess)
-      return e;
-    checkKernel<float, FT, false><<<grid, block, smem_bytes, stream>>>(a);
-  }
+  static SmemGrant g;
+  cudaError_t e = ensureSmem(checkKernel<R, FT, kList, kTile>, smem_bytes, g);
+  if (e != cudaSuccess)
+    return e;
+  checkKernel<R, FT, kList, kTile><<<grid, block, smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
-template cudaError_t launchCheck<uint8_t>(const CheckArgs<uint8_t>&, bool, bool, int, int, size_t, cudaStream_t);
-template cudaError_t launchCheck<uint16_t>(const CheckArgs<uint16_t>&, bool, bool, int, int, size_t, cudaStream_t);
+
+template <typename R, typename FT, bool kList, int kTile>
+int regsOf()
+{
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, checkKernel<R, FT, kList, kTile>) != cudaSuccess)
+    return 128;
+  return fa.numRegs;
+}
+}  // namespace
+
+template <typename FT>
+cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int tile, int grid, int block,
+                        size_t smem_bytes, cudaStream_t stream)
+{
+  if (fp64 && from_list)
+    return launchOne<double, FT, true, 1>(a, grid, block, smem_bytes, stream);
+  if (fp64)
+    return tile == 32 ? launchOne<double, FT, false, 32>(a, grid, block, smem_bytes, stream) :
+           tile == 16 ? launchOne<double, FT, false, 16>(a, grid, block, smem_bytes, stream) :
+                        launchOne<double, FT, false, 8>(a, grid, block, smem_bytes, stream);
+  return tile == 32 ? launchOne<float, FT, false, 32>(a, grid, block, smem_bytes, stream) :
+         tile == 16 ? launchOne<float, FT, false, 16>(a, grid, block, smem_bytes, stream) :
+                      launchOne<float, FT, false, 8>(a, grid, block, smem_bytes, stream);
+}
+template cudaError_t launchCheck<uint8_t>(const CheckArgs<uint8_t>&, bool, bool, int, int, int, size_t, cudaStream_t);
+template cudaError_t launchCheck<uint16_t>(const CheckArgs<uint16_t>&, bool, bool, int, int, int, size_t, cudaStream_t);
+
+int checkKernelRegs(bool fp64, bool from_list, int tile, int field_bytes)
+{
+  if (field_bytes == 1)
+  {
+    if (fp64 && from_list) return regsOf<double, uint8_t, true, 1>();
+    if (fp64) return tile == 32 ? regsOf<double, uint8_t, false, 32>() : tile == 16 ? regsOf<double, uint8_t, false, 16>() : regsOf<double, uint8_t, false, 8>();
+    return tile == 32 ? regsOf<float, uint8_t, false, 32>() : tile == 16 ? regsOf<float, uint8_t, false, 16>() : regsOf<float, uint8_t, false, 8>();
+  }
+  if (fp64 && from_list) return regsOf<double, uint16_t, true, 1>();
+  if (fp64) return tile == 32 ? regsOf<double, uint16_t, false, 32>() : tile == 16 ? regsOf<double, uint16_t, false, 16>() : regsOf<double, uint16_t, false, 8>();
+  return tile == 32 ? regsOf<float, uint16_t, false, 32>() : tile == 16 ? regsOf<float, uint16_t, false, 16>() : regsOf<float, uint16_t, false, 8>();
+}
 
 cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
+  static SmemGrant gd, gf;
   cudaError_t e;
   if (fp64)
   {
-    e = cudaFuncSetAttribute(fkKernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess)
+    if ((e = ensureSmem(fkKernel<double>, smem_bytes, gd)) != cudaSuccess)
       return e;
     fkKernel<double><<<grid, block, smem_bytes, stream>>>(a);
   }
   else
   {
-    e = cudaFuncSetAttribute(fkKernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess)
+    if ((e = ensureSmem(fkKernel<float>, smem_bytes, gf)) != cudaSuccess)
       return e;
     fkKernel<float><<<grid, block, smem_bytes, stream>>>(a);
   }
@@ -665,7 +805,8 @@ cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t sme
 
 cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_bytes, cudaStream_t stream)
 {
-  cudaError_t e = cudaFuncSetAttribute(sphereCentersKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  static SmemGrant g;
+  cudaError_t e = ensureSmem(sphereCentersKernel, smem_bytes, g);
   if (e != cudaSuccess)
     return e;
   sphereCentersKernel<<<1, 128, smem_bytes, stream>>>(a, d_centers);

@@ -10,7 +10,7 @@ enum JointType : int32_t { FIXED = 0, REVOLUTE = 1, PRISMATIC = 2, PLANAR = 3, F
 
 // 3x4 row-major affine transforms everywhere on the device (the last row of an isometry is implicit).
 template <typename R>
-struct LinkRec
+struct alignas(16) LinkRec
 {
   R o[12];     // joint origin; for a link whose parent does not move with the group: T_parent(base state) * origin
   R ax[3];     // joint axis
@@ -30,7 +30,7 @@ struct VarRec
 };
 
 template <typename R>
-struct SphereRec
+struct alignas(16) SphereRec
 {
   R x, y, z, r;  // CollisionSphere::relative_vec_ / radius_
   int slot;      // device-link slot
@@ -40,7 +40,7 @@ struct SphereRec
 };
 
 template <typename R>
-struct BsRec  // per link with spheres
+struct alignas(16) BsRec  // per link with spheres
 {
   R x, y, z, r;      // BodyDecomposition::getRelativeBoundingSphere(): posed for doBoundingSpheresIntersect (types.cpp:408-418)
   R tx, ty, tz, tr;  // OUR tight bounding sphere of the link's collision spheres (centroid, max |c_k - c| + r_k):
@@ -48,13 +48,13 @@ struct BsRec  // per link with spheres
   int slot, s0, s1, pad;  // device-link slot, sphere range [s0, s1)
 };
 
-struct PairRec  // enabled intra-group link pair (indices into the BsRec table), i < j in dfce order
+struct alignas(16) PairRec  // enabled intra-group link pair (indices into the BsRec table), i < j in dfce order
 {
   int a, b;
   int sa0, sb0;    // first sphere of each link
-  int nb, tot;     // spheres of link b, na * nb
-  unsigned magic;  // ceil(2^16 / nb): t / nb == (t * magic) >> 16 for t < 2^16 / nb... (host checks the range)
-  int pad;
+  int na, nb;      // sphere counts
+  unsigned magic;  // ceil(2^16 / nb): t / nb == (t * magic) >> 16 over [0, na * nb) (the host verifies the range)
+  int tot;         // na * nb
 };
 
 template <typename R>
@@ -72,5 +72,9 @@ struct ModelHeader
   R tight_eps;  // slack (m) of the conservative tight-sphere cull (FP32: covers rounding; FP64: 1e-9)
 };
 
-constexpr int kLinkStrideWords = 13;  // 12 + 1: odd stride => distinct links hit distinct banks
+// Shared-memory layout of one state's transforms: link stride 12 words (3x4 row-major), every row 16-byte aligned
+// so a row is ONE 128-bit access.  The state stride is padded to 4 (mod 32) words in the FP32 blob: the 8 lanes of a
+// quarter-warp then write 8 distinct 16-byte bank groups (conflict-free STS.128 in the FK phase); in the check phase
+// the lanes of a quarter-warp mostly read the same link (broadcast).
+constexpr int kLinkStrideWords = 12;
 }  // namespace b200sv
