@@ -198,9 +198,8 @@ int b200sv_sphere_centers(b200sv_ctx* ctx, const double* q_one, double* centers)
 /* Random 32-byte-sector gather over the world field's footprint: the "gather-bandwidth roofline" the check
  * kernel is compared against.  Reports sectors/s * 32 B as GB/s. */
 int b200sv_gather_roofline(b200sv_ctx* ctx, size_t n_reads, int iters, double* gbytes_per_s);
-/* Tuning knobs (0 keeps the default): FP32 sphere-centre error bound in metres, states per warp per FK pass
- * (8, 16 or 32), CTAs per SM. */
-int b200sv_set_tuning(b200sv_ctx* ctx, double fp32_eps_m, int tile, int blocks_per_sm);
+/* Tuning knobs (0 keeps the default): FP32 sphere-centre error bound in metres, warps per CTA cap, CTAs per SM. */
+int b200sv_set_tuning(b200sv_ctx* ctx, double fp32_eps_m, int warps_per_block, int blocks_per_sm);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,8 @@ struct b200sv_ctx
   // device tables
   std::vector<uint8_t> blob_f, blob_d;
   uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr;
-  int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0;
+  int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
+  double cluster_radius = 0.09;  // max tight-sphere radius of a sphere cluster (m)
   int state_stride_f = 0, state_stride_d = 0;  // shared-memory words per state (float / double blob)
   std::vector<int> link_slot;      // model link -> device slot
   std::vector<double> const_T;     // model links * 16 (base state)
@@ -86,11 +87,11 @@ struct b200sv_ctx
   int sm_count = 148, smem_optin = 0;
   struct LaunchCfg
   {
-    int tile = 32, warps = 0, blocks_per_sm = 1;
+    int warps = 0, blocks_per_sm = 1;
     size_t smem = 0;
   };
   LaunchCfg cfg_f, cfg_d, cfg_list;  // fast pass, exact pass over all states, exact pass over the recheck list
-  int tune_tile = 0, tune_blocks = 0;
+  int tune_warps = 0, tune_blocks = 0;
   double fp32_eps = 4e-6;
   // streams / staging
   cudaStream_t stream = nullptr;
@@ -153,13 +154,15 @@ int sphereThreshold(double radius, double res, double max_prop, double tol, int 
 template <typename R>
 void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, const std::vector<VarRec>& vars,
                const std::vector<SphereRec<double>>& spheres, const std::vector<BsRec<double>>& bs,
-               const std::vector<PairRec>& pairs, double margin, double pair_eps, double bs_eps, double tight_eps,
-               std::vector<uint8_t>& out)
+               const std::vector<PairRec>& pairs, const std::vector<GroupRec>& groups, double margin, double pair_eps,
+               double bs_eps, double tight_eps, std::vector<uint8_t>& out)
 {
   ModelHeader<R> h{};
   h.n_links = (int)links.size();
   h.n_vars = (int)vars.size();
-  h.n_spheres = (int)spheres.size();
+  h.n_spheres = c.n_spheres;
+  h.n_spheres_padded = (int)spheres.size();
+  h.n_groups = (int)groups.size();
   h.n_bs = (int)bs.size();
   h.n_pairs = (int)pairs.size();
   h.n_group_vars = (int)c.robot.group_var_index.size();
@@ -174,6 +177,8 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
   off = align16(off + (int)(bs.size() * sizeof(BsRec<R>)));
   h.off_pairs = off;
   off = align16(off + (int)(pairs.size() * sizeof(PairRec)));
+  h.off_groups = off;
+  off = align16(off + (int)(groups.size() * sizeof(GroupRec)));
   h.total_bytes = off;
   h.state_stride = sizeof(R) == 4 ? c.state_stride_f : c.state_stride_d;
   h.link_stride = kLinkStrideWords;
@@ -200,6 +205,8 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
     L[i].type = links[i].type;
     L[i].var = links[i].var;
     L[i].has_origin = links[i].has_origin;
+    L[i].s0 = links[i].s0;
+    L[i].s1 = links[i].s1;
   }
   if (!vars.empty())
     memcpy(out.data() + h.off_vars, vars.data(), vars.size() * sizeof(VarRec));
@@ -231,6 +238,8 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
   }
   if (!pairs.empty())
     memcpy(out.data() + h.off_pairs, pairs.data(), pairs.size() * sizeof(PairRec));
+  if (!groups.empty())
+    memcpy(out.data() + h.off_groups, groups.data(), groups.size() * sizeof(GroupRec));
 }
 
 // column-major 4x4 -> row-major 3x4
@@ -273,6 +282,8 @@ int validateModel(b200sv_ctx* c)
       return fail(c, B200SV_ERR_INVALID, "glink_index out of range");
     if (m.sphere_start[i + 1] < m.sphere_start[i])
       return fail(c, B200SV_ERR_INVALID, "sphere_start must be non-decreasing");
+    if (i > 0 && m.glink_index[i] <= m.glink_index[i - 1])
+      return fail(c, B200SV_ERR_INVALID, "glink_index must be strictly increasing (getUpdatedLinkModels() order)");
   }
   return B200SV_OK;
 }
@@ -340,7 +351,7 @@ int buildTables(b200sv_ctx* c)
     Mat4 origin;
     std::copy(r.joint_origin.begin() + 16 * l, r.joint_origin.begin() + 16 * (l + 1), origin.begin());
     L.var = (int)vars.size();
-    L.pad = 0;
+    L.s0 = L.s1 = 0;
     for (int k = 0; k < 3; ++k)
       L.ax[k] = r.joint_axis[3 * l + k];
     if (!dynamic[l])
@@ -389,8 +400,8 @@ int buildTables(b200sv_ctx* c)
     c->state_stride_d += 2;
   // ---- spheres, bounding spheres, pairs -----------------------------------------------------------------------------
   std::vector<SphereRec<double>> spheres;
-  std::vector<BsRec<double>> bs;
-  std::vector<int> bs_of_glink(m.n_glinks, -1);
+  std::vector<BsRec<double>> bs;                                 // clusters
+  std::vector<std::vector<int>> clusters_of_glink(m.n_glinks);  // BsRec indices per dfce link
   int max_thr = 0;
   for (int i = 0; i < m.n_glinks; ++i)
   {
@@ -398,13 +409,7 @@ int buildTables(b200sv_ctx* c)
     if (b <= a)
       continue;
     const int slot = c->link_slot[m.glink_index[i]];
-    BsRec<double> B{};
-    B.x = m.bounding_sphere[4 * i + 0];
-    B.y = m.bounding_sphere[4 * i + 1];
-    B.z = m.bounding_sphere[4 * i + 2];
-    B.r = m.bounding_sphere[4 * i + 3];
-    B.slot = slot;
-    B.s0 = (int)spheres.size();
+    const int first = (int)spheres.size();
     for (int k = a; k < b; ++k)
     {
       SphereRec<double> S{};
@@ -419,54 +424,93 @@ int buildTables(b200sv_ctx* c)
       max_thr = std::max(max_thr, S.thr);
       spheres.push_back(S);
     }
-    B.s1 = (int)spheres.size();
-    {  // tight sphere around the link's collision spheres: centroid, then the farthest sphere surface (+ 1 nm)
+    links[slot].s0 = first;
+    links[slot].s1 = (int)spheres.size();
+    // Clusters: greedy contiguous runs of the link's spheres whose tight sphere (centroid, farthest sphere surface,
+    // + 1 nm) stays within cluster_radius.  Sphere lists are usually laid out along the link, so runs are compact.
+    auto tight = [&](int s0, int s1, double* out4) {
       double cx = 0, cy = 0, cz = 0;
-      for (int k = B.s0; k < B.s1; ++k)
+      for (int k = s0; k < s1; ++k)
       {
         cx += spheres[k].x;
         cy += spheres[k].y;
         cz += spheres[k].z;
       }
-      const double inv = 1.0 / (B.s1 - B.s0);
+      const double inv = 1.0 / (s1 - s0);
       cx *= inv; cy *= inv; cz *= inv;
       double rr = 0.0;
-      for (int k = B.s0; k < B.s1; ++k)
+      for (int k = s0; k < s1; ++k)
       {
         const double ex = spheres[k].x - cx, ey = spheres[k].y - cy, ez = spheres[k].z - cz;
         rr = std::max(rr, sqrt(ex * ex + ey * ey + ez * ez) + spheres[k].r);
       }
-      B.tx = cx; B.ty = cy; B.tz = cz; B.tr = rr + 1e-9;
-    }
-    bs_of_glink[i] = (int)bs.size();
-    bs.push_back(B);
-  }
-  std::vector<PairRec> pairs;
-  double max_rs = 0.0;
-  for (int i = 0; i < m.n_glinks; ++i)
-    for (int j = i + 1; j < m.n_glinks; ++j)
-      if (bs_of_glink[i] >= 0 && bs_of_glink[j] >= 0 && m.intra_enabled[(size_t)i * m.n_glinks + j])
+      out4[0] = cx; out4[1] = cy; out4[2] = cz; out4[3] = rr + 1e-9;
+    };
+    int s0 = first;
+    while (s0 < (int)spheres.size())
+    {
+      int s1 = s0 + 1;
+      double t4[4], best4[4];
+      tight(s0, s1, best4);
+      while (s1 < (int)spheres.size() && s1 - s0 < 64)
       {
-        const BsRec<double>&A = bs[bs_of_glink[i]], &Bb = bs[bs_of_glink[j]];
-        PairRec P{};
-        P.a = bs_of_glink[i];
-        P.b = bs_of_glink[j];
-        P.sa0 = A.s0;
-        P.sb0 = Bb.s0;
-        P.na = A.s1 - A.s0;
-        P.nb = Bb.s1 - Bb.s0;
-        P.tot = P.na * P.nb;
-        P.magic = (65536u + P.nb - 1) / P.nb;
-        // exactness of the multiply-shift division over [0, tot): checked here, not assumed
-        for (int t = 0; t < P.tot; ++t)
-          if ((int)(((unsigned)t * P.magic) >> 16) != t / P.nb)
-            return fail(c, B200SV_ERR_UNSUPPORTED, "link pair with too many sphere pairs for the 16-bit index split");
-        pairs.push_back(P);
-        max_rs = std::max(max_rs, A.r + Bb.r);
+        tight(s0, s1 + 1, t4);
+        if (t4[3] > c->cluster_radius)
+          break;
+        std::copy(t4, t4 + 4, best4);
+        ++s1;
       }
+      BsRec<double> B{};
+      B.x = m.bounding_sphere[4 * i + 0];
+      B.y = m.bounding_sphere[4 * i + 1];
+      B.z = m.bounding_sphere[4 * i + 2];
+      B.r = m.bounding_sphere[4 * i + 3];
+      B.tx = best4[0]; B.ty = best4[1]; B.tz = best4[2]; B.tr = best4[3];
+      B.slot = slot;
+      B.s0 = s0;
+      B.s1 = s1;
+      clusters_of_glink[i].push_back((int)bs.size());
+      bs.push_back(B);
+      s0 = s1;
+    }
+  }
+  // cluster pairs of every enabled link pair, grouped by the first cluster
+  std::vector<PairRec> pairs;
+  std::vector<GroupRec> groups;
+  double max_rs = 0.0;
+  int n_link_pairs = 0;
+  for (int i = 0; i < m.n_glinks; ++i)
+  {
+    for (int j = i + 1; j < m.n_glinks; ++j)
+      if (!clusters_of_glink[i].empty() && !clusters_of_glink[j].empty() && m.intra_enabled[(size_t)i * m.n_glinks + j])
+      {
+        ++n_link_pairs;
+        max_rs = std::max(max_rs, bs[clusters_of_glink[i][0]].r + bs[clusters_of_glink[j][0]].r);
+      }
+    for (int ca : clusters_of_glink[i])
+    {
+      GroupRec G{ ca, (int)pairs.size(), 0, 0 };
+      for (int j = i + 1; j < m.n_glinks; ++j)
+        if (!clusters_of_glink[j].empty() && m.intra_enabled[(size_t)i * m.n_glinks + j])
+          for (int cb : clusters_of_glink[j])
+            pairs.push_back(PairRec{ ca, cb });
+      G.p1 = (int)pairs.size();
+      if (G.p1 > G.p0)
+        groups.push_back(G);
+    }
+  }
+  c->n_link_pairs = n_link_pairs;
   c->n_spheres = (int)spheres.size();
   c->n_bs = (int)bs.size();
   c->n_pairs = (int)pairs.size();
+  if (c->n_pairs >= (1 << 26))
+    return fail(c, B200SV_ERR_UNSUPPORTED, "too many enabled cluster pairs for the work-queue item format");
+  while (spheres.size() % 4)
+  {  // pad to a multiple of 4 (the field loop works in chunks of 4): thresholds 0 => never read, never collide
+    SphereRec<double> S{};
+    S.slot = spheres.empty() ? 0 : spheres.back().slot;
+    spheres.push_back(S);
+  }
   c->compact_bytes = max_thr <= 255 ? 1 : 2;
   // ---- FP32 uncertainty budget (see DESIGN.md "precision") -------------------------------------------------------------
   const double eps = c->fp32_eps;
@@ -475,57 +519,36 @@ int buildTables(b200sv_ctx* c)
   const double pair_eps = 2.0 * eps + 1e-7;
   const double bs_eps = 4.0 * eps * (sqrt(max_rs) + 0.05) + 1e-7;
   const double tight_eps = 4.0 * eps + 1e-6;
-  buildBlob<float>(*c, links, vars, spheres, bs, pairs, margin, pair_eps, bs_eps, tight_eps, c->blob_f);
-  buildBlob<double>(*c, links, vars, spheres, bs, pairs, 0.0, 0.0, 0.0, 1e-9, c->blob_d);
+  buildBlob<float>(*c, links, vars, spheres, bs, pairs, groups, margin, pair_eps, bs_eps, tight_eps, c->blob_f);
+  buildBlob<double>(*c, links, vars, spheres, bs, pairs, groups, 0.0, 0.0, 0.0, 1e-9, c->blob_d);
   return B200SV_OK;
 }
 
-// per-warp shared memory in units of R: sphere centres + radius (4) | bounding + tight centres and radii (8) |
-// transforms of `tile` states -- must match perWarpWords() in check_kernels.cu
-size_t perWarpBytes(const b200sv_ctx* c, int elem, int tile)
-{
-  const int ss = elem == 4 ? c->state_stride_f : c->state_stride_d;
-  return (size_t)(4 * c->n_spheres + 8 * c->n_bs + tile * ss) * elem;
-}
-
-// Pick (tile, warps per block, blocks per SM): the largest tile that still keeps >= 16 warps resident per SM
-// (the FK phase only uses `tile` lanes, so a smaller tile trades FK lane efficiency for latency hiding), else the
-// configuration with the most resident warps.  Limits: 227 KB of shared memory per CTA / 228 KB per SM with 1 KB
-// reserved per CTA, 64 K registers per SM, 512 threads per CTA (__launch_bounds__).
+// Pick (warps per CTA, CTAs per SM) for the thread-per-state check kernel: as many resident warps as shared memory
+// (32 states of link transforms per warp) and registers allow.  Limits: 227 KB of shared memory per CTA / 228 KB per
+// SM with 1 KB reserved per CTA, 64 K registers per SM, 512 threads per CTA (__launch_bounds__).
 b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, int blob_bytes)
 {
-  const int elem = fp64 ? 8 : 4;
   b200sv_ctx::LaunchCfg best;
-  const int tiles[3] = { 32, 16, 8 };
-  for (int ti = 0; ti < 3; ++ti)
+  const int regs = (checkKernelRegs(fp64, from_list, c->compact_bytes) + 7) & ~7;
+  const int reg_warps = 65536 / (regs * 32);
+  const long pw = checkPerWarpBytes(fp64, fp64 ? c->state_stride_d : c->state_stride_f);
+  for (int b = 1; b <= 4; ++b)
   {
-    const int tile = from_list ? 1 : tiles[ti];
-    if (!from_list && c->tune_tile > 0 && tile != c->tune_tile)
+    if (c->tune_blocks > 0 && b != c->tune_blocks)
       continue;
-    const int regs = (checkKernelRegs(fp64, from_list, tile, c->compact_bytes) + 7) & ~7;
-    const int reg_warps = 65536 / (regs * 32);
-    const size_t pw = perWarpBytes(c, elem, tile);
-    b200sv_ctx::LaunchCfg cand;
-    for (int b = 1; b <= 4; ++b)
+    const long per_block = std::min<long>(c->smem_optin, (233472L - 1024L * b) / b) - align16(blob_bytes);
+    int w = per_block > 0 ? (int)(per_block / pw) : 0;
+    w = std::min(w, 16);
+    w = std::min(w, reg_warps / b);
+    if (c->tune_warps > 0)
+      w = std::min(w, c->tune_warps);
+    if (w * b > best.warps * best.blocks_per_sm)
     {
-      if (c->tune_blocks > 0 && b != c->tune_blocks)
-        continue;
-      const long per_block = std::min<long>(c->smem_optin, (233472L - 1024L * b) / b) - align16(blob_bytes);
-      int w = per_block > 0 ? (int)(per_block / (long)pw) : 0;
-      w = std::min(w, 16);
-      w = std::min(w, reg_warps / b);
-      if (w * b > cand.warps * cand.blocks_per_sm)
-      {
-        cand.tile = tile;
-        cand.warps = w;
-        cand.blocks_per_sm = b;
-        cand.smem = align16(blob_bytes) + pw * w;
-      }
+      best.warps = w;
+      best.blocks_per_sm = b;
+      best.smem = align16(blob_bytes) + (size_t)pw * w;
     }
-    if (cand.warps * cand.blocks_per_sm > best.warps * best.blocks_per_sm)
-      best = cand;
-    if (from_list || best.warps * best.blocks_per_sm >= 16)
-      break;
   }
   return best;
 }
@@ -554,7 +577,7 @@ int uploadTables(b200sv_ctx* c)
   if (c->cfg_f.warps < 1 || c->cfg_d.warps < 1 || c->cfg_list.warps < 1)
     return fail(c, B200SV_ERR_UNSUPPORTED,
                 "robot too large for the shared-memory tile: " + std::to_string(c->n_dev_links) + " moving links need " +
-                    std::to_string(8 * c->state_stride_d * 8) + " bytes per warp");
+                    std::to_string(32 * c->state_stride_d * 8) + " bytes per warp");
   return B200SV_OK;
 }
 
@@ -675,8 +698,10 @@ int finishCreate(b200sv_ctx* c, int device, b200sv_ctx** out)
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   // profiling knobs (same meaning as b200sv_set_tuning), so a bench run under ncu can pin a configuration
-  if (const char* e = getenv("B200SV_TILE"))
-    c->tune_tile = atoi(e);
+  if (const char* e = getenv("B200SV_WARPS"))
+    c->tune_warps = atoi(e);
+  if (const char* e = getenv("B200SV_CLUSTER_R"))
+    c->cluster_radius = atof(e);
   if (const char* e = getenv("B200SV_BLOCKS"))
     c->tune_blocks = atoi(e);
   if ((rc = validateModel(c)) != B200SV_OK)
@@ -726,19 +751,19 @@ int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_
   {
     a.model = c->d_blob_d;
     a.model_bytes = (int)c->blob_d.size();
-    CU(c, launchCheck<FT>(a, true, false, c->cfg_d.tile, c->sm_count * c->cfg_d.blocks_per_sm, c->cfg_d.warps * 32,
+    CU(c, launchCheck<FT>(a, true, false, c->sm_count * c->cfg_d.blocks_per_sm, c->cfg_d.warps * 32,
                           c->cfg_d.smem, s));
     return B200SV_OK;
   }
   CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), s));
   a.model = c->d_blob_f;
   a.model_bytes = (int)c->blob_f.size();
-  CU(c, launchCheck<FT>(a, false, false, c->cfg_f.tile, c->sm_count * c->cfg_f.blocks_per_sm, c->cfg_f.warps * 32,
+  CU(c, launchCheck<FT>(a, false, false, c->sm_count * c->cfg_f.blocks_per_sm, c->cfg_f.warps * 32,
                         c->cfg_f.smem, s));
   // exact pass over the undecided states; the count stays on the device, so the launch is unconditional
   a.model = c->d_blob_d;
   a.model_bytes = (int)c->blob_d.size();
-  CU(c, launchCheck<FT>(a, true, true, 1, c->sm_count * c->cfg_list.blocks_per_sm, c->cfg_list.warps * 32,
+  CU(c, launchCheck<FT>(a, true, true, c->sm_count * c->cfg_list.blocks_per_sm, c->cfg_list.warps * 32,
                         c->cfg_list.smem, s));
   return B200SV_OK;
 }
@@ -888,7 +913,7 @@ int b200sv_get_info(const b200sv_ctx* c, b200sv_info* info)
   info->n_group_vars = (int)c->robot.group_var_index.size();
   info->n_glinks = c->cm.n_glinks;
   info->n_spheres = c->n_spheres;
-  info->n_link_pairs = c->n_pairs;
+  info->n_link_pairs = c->n_link_pairs;
   info->num_cells[0] = c->grid.nx;
   info->num_cells[1] = c->grid.ny;
   info->num_cells[2] = c->grid.nz;
@@ -1263,7 +1288,7 @@ int b200sv_gather_roofline(b200sv_ctx* c, size_t n_reads, int iters, double* gbs
   return B200SV_OK;
 }
 
-int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int tile, int blocks_per_sm)
+int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int warps_per_block, int blocks_per_sm)
 {
   if (!c)
     return B200SV_ERR_INVALID;
@@ -1273,8 +1298,8 @@ int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int tile, int blocks_per
   cudaSetDevice(c->device);
   if (fp32_eps_m > 0.0)
     c->fp32_eps = fp32_eps_m;
-  if (tile == 8 || tile == 16 || tile == 32)
-    c->tune_tile = tile;
+  if (warps_per_block > 0)
+    c->tune_warps = warps_per_block;
   if (blocks_per_sm > 0)
     c->tune_blocks = blocks_per_sm;
   CU(c, cudaStreamSynchronize(c->stream));

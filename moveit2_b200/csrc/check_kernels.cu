@@ -11,15 +11,19 @@
 //   getEnvironmentCollisions / getSelfCollisions / getIntraGroupCollisions + doBoundingSpheresIntersect
 //                                                  collision_env_distance_field.cpp:1561-1643, 274-353, 430-642; types.cpp:408-418
 //
-// Mapping (B200, sm_100a): persistent CTAs.  Each warp owns a tile of kTile consecutive states.
-//   phase 1  thread-per-state FK: lane s (< kTile) walks the device links in index order (parents first); link
-//            transforms go to shared memory as 3x4 row-major rows of 16 bytes (one 128-bit access per row).
-//   phase 2  warp-per-state checks: lanes own spheres (two per lane per pass, for memory-level parallelism); each
-//            lane poses its sphere, converts the centre to a voxel and gathers ONE byte from the world field and one
-//            from the self field (L2-resident compact d^2), compares against the sphere's integer threshold; early
-//            exit is warp-uniform.  Intra-group: lanes test link pairs (the reference's bounding-sphere cull plus a
-//            conservative tight-sphere cull), then for each surviving link pair the spheres of either link are
-//            tested against the other link's tight sphere, and only the survivors meet sphere against sphere.
+// Mapping (B200, sm_100a): persistent CTAs; every warp owns tiles of 32 consecutive states and works THREAD-PER-STATE,
+// so each instruction serves 32 states (the first, warp-per-state version spent ~900 warp instructions per state on
+// per-state scalar overhead; see profiles/r1_check_v2_tile8.txt).
+//   phase 1  FK: lane s walks the device links in index order (parents first); link transforms go to shared memory as
+//            3x4 row-major rows of 16 bytes.  State stride = 4 (mod 32) words: conflict-free 128-bit accesses.
+//   phase 2  field checks: uniform loop over the spheres in chunks of 4; each lane poses the sphere for ITS state,
+//            converts the centre to a voxel and gathers one byte from the world field and one from the self field
+//            (L2-resident compact d^2): 8 independent gathers in flight per lane; compare against the sphere's integer
+//            threshold.  Lanes whose state already collides stop gathering.
+//   phase 3  intra-group pairs: uniform loop over the enabled link pairs; each lane applies the reference's
+//            bounding-sphere cull plus a conservative tight-sphere cull for its state; surviving (state, pair) items
+//            are compacted into a per-warp queue and processed one item per lane: spheres of either link against
+//            the other link's tight sphere, survivors sphere against sphere.
 // Precision: the fast pass is FP32 (template R = float).  A sphere whose voxel coordinate is within `margin` of a
 // cell face, or a pair whose distance is within eps of its threshold, is evaluated for BOTH outcomes; if the
 // state's boolean could depend on that, the state index is appended to a recheck list and the exact pass
@@ -47,6 +51,7 @@ struct Smem
   const SphereRec<R>* spheres;
   const BsRec<R>* bs;
   const PairRec* pairs;
+  const GroupRec* groups;
 };
 
 __device__ __forceinline__ void sincosR(float x, float* s, float* c) { sincosf(x, s, c); }
@@ -297,83 +302,38 @@ __device__ __forceinline__ Smem<R> loadModel(const uint8_t* __restrict__ g_model
   m.spheres = reinterpret_cast<const SphereRec<R>*>(smem + m.h->off_spheres);
   m.bs = reinterpret_cast<const BsRec<R>*>(smem + m.h->off_bs);
   m.pairs = reinterpret_cast<const PairRec*>(smem + m.h->off_pairs);
+  m.groups = reinterpret_cast<const GroupRec*>(smem + m.h->off_groups);
   return m;
 }
 
-// What one lane knows about one of its spheres after posing it: where to read the fields, and whether FP32
-// rounding leaves the voxel undetermined.
-struct Probe
+// FP32 only, rare: the centre of sphere k is within `margin` of a cell face.  Evaluate every candidate cell.
+template <typename R, typename FT>
+__device__ __noinline__ void riskySphere(const Smem<R>& m, const R* T, int k, bool do_world, bool do_self,
+                                         const FT* __restrict__ world, const FT* __restrict__ self, bool& hit, bool& amb)
 {
-  int idx;         // voxel index of the certain cell, -1: nothing to read (no thresholds / outside the 1-cell margin)
-  int thr_w, thr_s;
-  bool risky;      // FP32 only: the centre is within `margin` of a cell face
-  int gx, gy, gz, hx, hy, hz;
-};
-
-template <typename R>
-__device__ __forceinline__ Probe probeSphere(const Smem<R>& m, const R* T, R* cent, int k, bool do_world, bool do_self)
-{
-  constexpr bool kExact = sizeof(R) == 8;
   const ModelHeader<R>& h = *m.h;
-  Probe p;
-  p.idx = -1;
-  p.risky = false;
-  p.thr_w = p.thr_s = 0;
-  p.gx = p.gy = p.gz = p.hx = p.hy = p.hz = 0;
-  if (k >= h.n_spheres)
-    return p;
   const SphereRec<R> sp = m.spheres[k];
   R Tl[12];
   load12(T + sp.slot * kLinkStrideWords, Tl);
   R cx, cy, cz;
   posePoint<R>(Tl, sp.x, sp.y, sp.z, cx, cy, cz);
-  store4(cent + k * 4, cx, cy, cz, sp.r);
-  p.thr_w = do_world ? sp.thr : 0;
-  p.thr_s = do_self ? sp.thr_self : 0;
-  if ((p.thr_w | p.thr_s) == 0)
-    return p;
-  // VoxelGrid::getCellFromLocation (voxel_grid.hpp:522): floor((loc - origin_minus) * oo_resolution)
   const R fx = (cx - h.om[0]) * h.oo_res, fy = (cy - h.om[1]) * h.oo_res, fz = (cz - h.om[2]) * h.oo_res;
-  if (kExact)
-  {
-    p.gx = p.hx = static_cast<int>(floorR(fx));
-    p.gy = p.hy = static_cast<int>(floorR(fy));
-    p.gz = p.hz = static_cast<int>(floorR(fz));
-  }
-  else
-  {
-    p.gx = static_cast<int>(floorR(fx - h.margin));
-    p.hx = static_cast<int>(floorR(fx + h.margin));
-    p.gy = static_cast<int>(floorR(fy - h.margin));
-    p.hy = static_cast<int>(floorR(fy + h.margin));
-    p.gz = static_cast<int>(floorR(fz - h.margin));
-    p.hz = static_cast<int>(floorR(fz + h.margin));
-    p.risky = (p.gx != p.hx) | (p.gy != p.hy) | (p.gz != p.hz);
-  }
-  // DistanceField::getDistanceGradient bounds (distance_field.cpp:82): a 1-cell margin is "out of bounds", which
-  // reads as max_distance and therefore never collides (types.cpp:229).
-  if (!p.risky && p.gx >= 1 && p.gy >= 1 && p.gz >= 1 && p.gx < h.nx - 1 && p.gy < h.ny - 1 && p.gz < h.nz - 1)
-    p.idx = (p.gx * h.ny + p.gy) * h.nz + p.gz;  // VoxelGrid::ref (voxel_grid.hpp:425); < 2^31 voxels (host checks)
-  return p;
-}
-
-// FP32 only, rare: evaluate every candidate cell of a sphere whose voxel is uncertain.
-template <typename R, typename FT>
-__device__ __noinline__ void riskySphere(const ModelHeader<R>& h, const Probe& p, const FT* __restrict__ world,
-                                         const FT* __restrict__ self, bool& hit, bool& amb)
-{
+  const int gx = static_cast<int>(floorR(fx - h.margin)), hx = static_cast<int>(floorR(fx + h.margin));
+  const int gy = static_cast<int>(floorR(fy - h.margin)), hy = static_cast<int>(floorR(fy + h.margin));
+  const int gz = static_cast<int>(floorR(fz - h.margin)), hz = static_cast<int>(floorR(fz + h.margin));
+  const int thr_w = do_world ? sp.thr : 0, thr_s = do_self ? sp.thr_self : 0;
   bool any = false, all = true;
-  for (int ix = p.gx; ix <= p.hx; ++ix)
-    for (int iy = p.gy; iy <= p.hy; ++iy)
-      for (int iz = p.gz; iz <= p.hz; ++iz)
+  for (int ix = gx; ix <= hx; ++ix)
+    for (int iy = gy; iy <= hy; ++iy)
+      for (int iz = gz; iz <= hz; ++iz)
       {
         bool c = false;
         if (ix >= 1 && iy >= 1 && iz >= 1 && ix < h.nx - 1 && iy < h.ny - 1 && iz < h.nz - 1)
         {
           const int idx = (ix * h.ny + iy) * h.nz + iz;
-          const int dw = p.thr_w ? static_cast<int>(__ldg(world + idx)) : 0x7fffffff;
-          const int ds = p.thr_s ? static_cast<int>(__ldg(self + idx)) : 0x7fffffff;
-          c = (dw < p.thr_w) | (ds < p.thr_s);
+          const int dw = thr_w ? static_cast<int>(__ldg(world + idx)) : 0x7fffffff;
+          const int ds = thr_s ? static_cast<int>(__ldg(self + idx)) : 0x7fffffff;
+          c = (dw < thr_w) | (ds < thr_s);
         }
         any |= c;
         all &= c;
@@ -382,249 +342,325 @@ __device__ __noinline__ void riskySphere(const ModelHeader<R>& h, const Probe& p
   amb |= (any && !all);
 }
 
-// One state, warp-cooperative.  Returns (via uniform bools) whether it certainly collides / is undecidable in R.
-template <typename R, typename FT>
-__device__ __forceinline__ void checkState(const Smem<R>& m, const R* T, R* cent, R* bsc, const FT* __restrict__ world,
-                                           const FT* __restrict__ self, uint32_t flags, int lane, bool& hit_out,
-                                           bool& amb_out)
+// Phase 2 for kU consecutive spheres of this lane's state: pose, voxel, gather (all loads first), compare.
+template <typename R, typename FT, int kU>
+__device__ __forceinline__ void sphereChunk(const Smem<R>& m, const R* T, int k0, bool do_world, bool do_self,
+                                            const FT* __restrict__ world, const FT* __restrict__ self, bool live_lane,
+                                            bool& hit, bool& amb)
 {
   constexpr bool kExact = sizeof(R) == 8;
   const ModelHeader<R>& h = *m.h;
-  const bool do_world = (flags & 1u) != 0, do_self = (flags & 2u) != 0, do_intra = (flags & 4u) != 0;
-  bool hit = false, amb = false;
-  for (int base = 0; base < h.n_spheres; base += 64)
+  int idx[kU], tw[kU], ts[kU];
+  unsigned risky = 0;
+#pragma unroll
+  for (int u = 0; u < kU; ++u)
   {
-    // two spheres per lane: both poses, then all four gathers in flight, then the compares
-    const Probe p0 = probeSphere<R>(m, T, cent, base + lane, do_world, do_self);
-    const Probe p1 = probeSphere<R>(m, T, cent, base + 32 + lane, do_world, do_self);
-    int dw0 = 0x7fffffff, ds0 = 0x7fffffff, dw1 = 0x7fffffff, ds1 = 0x7fffffff;
-    if (p0.idx >= 0)
+    idx[u] = -1;
+    tw[u] = ts[u] = 0;
+    const int k = k0 + u;  // the table is padded to a multiple of kU with thr = 0 entries
     {
-      if (p0.thr_w) dw0 = static_cast<int>(__ldg(world + p0.idx));
-      if (p0.thr_s) ds0 = static_cast<int>(__ldg(self + p0.idx));
-    }
-    if (p1.idx >= 0)
-    {
-      if (p1.thr_w) dw1 = static_cast<int>(__ldg(world + p1.idx));
-      if (p1.thr_s) ds1 = static_cast<int>(__ldg(self + p1.idx));
-    }
-    hit |= (dw0 < p0.thr_w) | (ds0 < p0.thr_s) | (dw1 < p1.thr_w) | (ds1 < p1.thr_s);
-    if (!kExact)
-    {
-      if (p0.risky) riskySphere<R, FT>(h, p0, world, self, hit, amb);
-      if (p1.risky) riskySphere<R, FT>(h, p1, world, self, hit, amb);
-    }
-  }
-  hit = __any_sync(kFull, hit);
-  if (!hit && do_intra && h.n_pairs > 0)
-  {
-    // Per link with spheres: the reference's bounding-sphere centre (PosedBodySphereDecomposition::updatePose,
-    // types.cpp:391) and the centre of our tight sphere; radii alongside so pair tests read one place.
-    for (int b = lane; b < h.n_bs; b += 32)
-    {
-      const BsRec<R> r = m.bs[b];
+      const SphereRec<R> sp = m.spheres[k];  // uniform address: one broadcast read for the warp
+      tw[u] = do_world ? sp.thr : 0;
+      ts[u] = do_self ? sp.thr_self : 0;
       R Tl[12];
-      load12(T + r.slot * kLinkStrideWords, Tl);
-      R x, y, z;
-      posePoint<R>(Tl, r.x, r.y, r.z, x, y, z);
-      store4(bsc + b * 8, x, y, z, r.r);
-      posePoint<R>(Tl, r.tx, r.ty, r.tz, x, y, z);
-      store4(bsc + b * 8 + 4, x, y, z, r.tr);
-    }
-    __syncwarp();
-    bool phit = false;
-    for (int p0 = 0; p0 < h.n_pairs; p0 += 32)
-    {
-      const int p = p0 + lane;
-      bool live = false, live_certain = false;
-      if (p < h.n_pairs)
+      load12(T + sp.slot * kLinkStrideWords, Tl);
+      R cx, cy, cz;
+      posePoint<R>(Tl, sp.x, sp.y, sp.z, cx, cy, cz);
+      // VoxelGrid::getCellFromLocation (voxel_grid.hpp:522): floor((loc - origin_minus) * oo_resolution)
+      const R fx = (cx - h.om[0]) * h.oo_res, fy = (cy - h.om[1]) * h.oo_res, fz = (cz - h.om[2]) * h.oo_res;
+      int gx, gy, gz;
+      bool r = false;
+      if constexpr (kExact)
       {
-        const PairRec pr = m.pairs[p];
-        R ca[4], cb[4], ta[4], tb[4];
-        load4(bsc + pr.a * 8, ca);
-        load4(bsc + pr.b * 8, cb);
-        load4(bsc + pr.a * 8 + 4, ta);
-        load4(bsc + pr.b * 8 + 4, tb);
-        const R ex = ca[0] - cb[0], ey = ca[1] - cb[1], ez = ca[2] - cb[2];
-        const R d2 = ex * ex + ey * ey + ez * ez;
-        // reference quirk kept: SQUARED centre distance against the plain radius sum (types.cpp:416-417)
-        const R rs = ca[3] + cb[3];
-        // conservative cull: every sphere of a link lies inside its tight sphere, so separated tight spheres
-        // (with slack for rounding) mean no sphere pair of the two links can touch
-        const R fx = ta[0] - tb[0], fy = ta[1] - tb[1], fz = ta[2] - tb[2];
-        const R t2 = fx * fx + fy * fy + fz * fz;
-        const R rt = ta[3] + tb[3] + h.tight_eps;
-        const bool near = t2 < rt * rt;
-        if (kExact)
-          live = live_certain = near && (d2 < rs);
-        else
-        {
-          live = near && (d2 < rs + h.bs_eps);
-          live_certain = d2 < rs - h.bs_eps;
-        }
+        gx = static_cast<int>(floorR(fx));
+        gy = static_cast<int>(floorR(fy));
+        gz = static_cast<int>(floorR(fz));
       }
-      unsigned mask = __ballot_sync(kFull, live);
-      const unsigned cmask = __ballot_sync(kFull, live_certain);
-      while (mask)
+      else
       {
-        const int bit = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const bool cert = (cmask >> bit) & 1u;
-        const PairRec pr = m.pairs[p0 + bit];
-        if (pr.na + pr.nb <= 32)
-        {
-          // level 2: lanes [0, na) hold the spheres of link a and test them against b's tight sphere, lanes
-          // [na, na + nb) hold b's spheres and test against a's.  Only survivors can be part of a touching pair.
-          R me[4] = { R(0), R(0), R(0), R(0) };
-          bool inside = false;
-          if (lane < pr.na + pr.nb)
-          {
-            const bool is_a = lane < pr.na;
-            load4(cent + (is_a ? pr.sa0 + lane : pr.sb0 + lane - pr.na) * 4, me);
-            R ot[4];
-            load4(bsc + (is_a ? pr.b : pr.a) * 8 + 4, ot);
-            const R gx = me[0] - ot[0], gy = me[1] - ot[1], gz = me[2] - ot[2];
-            const R lim = me[3] + ot[3] + h.tight_eps;
-            inside = (gx * gx + gy * gy + gz * gz) < lim * lim;
-          }
-          const unsigned mk = __ballot_sync(kFull, inside);
-          unsigned ma = mk & ((1u << pr.na) - 1u);
-          const bool is_b = inside && lane >= pr.na;
-          if ((mk >> pr.na) == 0u)
-            ma = 0u;
-          while (ma)
-          {
-            const int ia = __ffs(ma) - 1;
-            ma &= ma - 1;
-            R pa[4];
-            load4(cent + (pr.sa0 + ia) * 4, pa);  // broadcast read
-            if (is_b)
-            {
-              const R gx2 = pa[0] - me[0], gy2 = pa[1] - me[1], gz2 = pa[2] - me[2];
-              const R dd = gx2 * gx2 + gy2 * gy2 + gz2 * gz2;
-              const R rsum = pa[3] + me[3];
-              if (kExact)
-                phit |= sqrtR(dd) < rsum;  // gradient.norm() < r1 + r2 (collision_env_distance_field.cpp:577-583)
-              else
-              {
-                // squared form of dist < rsum -+ eps (both sides positive); the 1e-7 in pair_eps covers its rounding
-                const R lo = rsum - h.pair_eps, hi = rsum + h.pair_eps;
-                const bool c_cert = (lo > R(0)) && (dd < lo * lo);
-                const bool c_maybe = dd < hi * hi;
-                phit |= (cert && c_cert);
-                amb |= (c_maybe && !(cert && c_cert));
-              }
-            }
-          }
-        }
-        else
-        {
-          // links with more than 32 spheres between them: plain enumeration of the na * nb sphere pairs
-          for (int t = lane; t < pr.tot; t += 32)
-          {
-            const int ia = static_cast<int>((static_cast<unsigned>(t) * pr.magic) >> 16);  // t / nb
-            R pa[4], pb[4];
-            load4(cent + (pr.sa0 + ia) * 4, pa);
-            load4(cent + (pr.sb0 + (t - ia * pr.nb)) * 4, pb);
-            const R gx2 = pa[0] - pb[0], gy2 = pa[1] - pb[1], gz2 = pa[2] - pb[2];
-            const R dd = gx2 * gx2 + gy2 * gy2 + gz2 * gz2;
-            const R rsum = pa[3] + pb[3];
-            if (kExact)
-              phit |= sqrtR(dd) < rsum;
-            else
-            {
-              const R lo = rsum - h.pair_eps, hi = rsum + h.pair_eps;
-              const bool c_cert = (lo > R(0)) && (dd < lo * lo);
-              const bool c_maybe = dd < hi * hi;
-              phit |= (cert && c_cert);
-              amb |= (c_maybe && !(cert && c_cert));
-            }
-          }
-        }
+        const R ffx = floorR(fx), ffy = floorR(fy), ffz = floorR(fz);
+        gx = static_cast<int>(ffx);
+        gy = static_cast<int>(ffy);
+        gz = static_cast<int>(ffz);
+        // within `margin` of a cell face on any axis <=> floor(f - margin) != floor(f + margin)
+        const R lo = fminf(fminf(fx - ffx, fy - ffy), fz - ffz), hi = fmaxf(fmaxf(fx - ffx, fy - ffy), fz - ffz);
+        r = (lo < h.margin) | (hi >= R(1) - h.margin);
+      }
+      // DistanceField::getDistanceGradient bounds (distance_field.cpp:82): a 1-cell margin is "out of bounds", which
+      // reads as max_distance and therefore never collides (types.cpp:229).
+      const bool inb = (static_cast<unsigned>(gx - 1) < static_cast<unsigned>(h.nx - 2)) &
+                       (static_cast<unsigned>(gy - 1) < static_cast<unsigned>(h.ny - 2)) &
+                       (static_cast<unsigned>(gz - 1) < static_cast<unsigned>(h.nz - 2));
+      if ((tw[u] | ts[u]) && live_lane)
+      {
+        if (r)
+          risky |= 1u << u;
+        else if (inb)
+          idx[u] = (gx * h.ny + gy) * h.nz + gz;  // VoxelGrid::ref (voxel_grid.hpp:425); < 2^31 voxels (host checks)
       }
     }
-    hit = __any_sync(kFull, phit);
   }
-  amb = __any_sync(kFull, amb);
-  hit_out = hit;
-  amb_out = amb && !hit;
+  int dw[kU], ds[kU];
+#pragma unroll
+  for (int u = 0; u < kU; ++u)
+  {
+    dw[u] = ds[u] = 0x7fffffff;
+    if (idx[u] >= 0)
+    {
+      if (tw[u]) dw[u] = static_cast<int>(__ldg(world + idx[u]));
+      if (ts[u]) ds[u] = static_cast<int>(__ldg(self + idx[u]));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kU; ++u)
+    hit |= (dw[u] < tw[u]) | (ds[u] < ts[u]);
+  if (!kExact && risky)
+  {
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if ((risky >> u) & 1u)
+        riskySphere<R, FT>(m, T, k0 + u, do_world, do_self, world, self, hit, amb);
+  }
 }
 
-// Per-warp shared memory, in units of R (all 16-byte aligned): sphere centres + radius | link bounding / tight
-// centres + radii | transforms of kTile states
+// Phase 3, level 1 for this lane's state and one cluster pair (a, b): our conservative tight-sphere cull first, and
+// only when that says "near" the reference's own link-level cull with its quirk.  (ax, ay, az): posed tight centre
+// of cluster a, Ta: its link transform (both shared by the whole group of pairs).
 template <typename R>
-__device__ __forceinline__ int perWarpWords(const ModelHeader<R>& h, int tile)
+__device__ __forceinline__ void pairCull(const Smem<R>& m, const R* T, const BsRec<R>& A, const R* Ta, R ax, R ay, R az,
+                                         const BsRec<R>& B, bool& live, bool& certain)
 {
-  return 4 * h.n_spheres + 8 * h.n_bs + tile * h.state_stride;
+  constexpr bool kExact = sizeof(R) == 8;
+  const ModelHeader<R>& h = *m.h;
+  R Tb[12];
+  load12(T + B.slot * kLinkStrideWords, Tb);
+  R bx, by, bz;
+  // conservative cull: every sphere of a cluster lies inside its tight sphere, so separated tight spheres (with
+  // slack for rounding) mean no sphere pair of the two clusters can touch
+  posePoint<R>(Tb, B.tx, B.ty, B.tz, bx, by, bz);
+  const R fx = ax - bx, fy = ay - by, fz = az - bz;
+  const R rt = A.tr + B.tr + h.tight_eps;
+  live = certain = false;
+  if ((fx * fx + fy * fy + fz * fz) < rt * rt)
+  {
+    // doBoundingSpheresIntersect (types.cpp:408-418) on the LINKS' bounding spheres, quirk kept: SQUARED centre
+    // distance against the plain radius sum
+    R px, py, pz, qx, qy, qz;
+    posePoint<R>(Ta, A.x, A.y, A.z, px, py, pz);
+    posePoint<R>(Tb, B.x, B.y, B.z, qx, qy, qz);
+    const R ex = px - qx, ey = py - qy, ez = pz - qz;
+    const R d2 = ex * ex + ey * ey + ez * ez;
+    const R rs = A.r + B.r;
+    if (kExact)
+      live = certain = d2 < rs;
+    else
+    {
+      live = d2 < rs + h.bs_eps;
+      certain = d2 < rs - h.bs_eps;
+    }
+  }
 }
 
-// Dynamic shared memory: [model blob][per warp: cent | bsc | Ts]
-template <typename R, typename FT, bool kFromList, int kTile>
+// Phase 3, levels 2 and 3 for one (state, cluster pair) item: spheres of either cluster against the other cluster's
+// tight sphere, then the survivors sphere against sphere (getIntraGroupCollisions,
+// collision_env_distance_field.cpp:571-638).  Clusters hold at most 64 spheres (host guarantees it).
+template <typename R>
+__device__ __forceinline__ void pairItem(const Smem<R>& m, const R* T, const PairRec& pr, bool cert, bool& hit, bool& amb)
+{
+  constexpr bool kExact = sizeof(R) == 8;
+  const ModelHeader<R>& h = *m.h;
+  const BsRec<R>& A = m.bs[pr.a];
+  const BsRec<R>& B = m.bs[pr.b];
+  const int na = A.s1 - A.s0, nb = B.s1 - B.s0;
+  R Ta[12], Tb[12];
+  load12(T + A.slot * kLinkStrideWords, Ta);
+  load12(T + B.slot * kLinkStrideWords, Tb);
+  unsigned long long ma = ~0ull >> (64 - na), mb = ~0ull >> (64 - nb);
+  if (na * nb > 4)
+  {
+    // level 2 pays off only when there is more than a handful of sphere pairs
+    R tax, tay, taz, tbx, tby, tbz;
+    posePoint<R>(Ta, A.tx, A.ty, A.tz, tax, tay, taz);
+    posePoint<R>(Tb, B.tx, B.ty, B.tz, tbx, tby, tbz);
+    ma = 0ull;
+    for (int i = 0; i < na; ++i)
+    {
+      const SphereRec<R>& sp = m.spheres[A.s0 + i];
+      R x, y, z;
+      posePoint<R>(Ta, sp.x, sp.y, sp.z, x, y, z);
+      const R gx = x - tbx, gy = y - tby, gz = z - tbz;
+      const R lim = sp.r + B.tr + h.tight_eps;
+      if ((gx * gx + gy * gy + gz * gz) < lim * lim)
+        ma |= 1ull << i;
+    }
+    if (ma == 0ull)
+      return;
+    mb = 0ull;
+    for (int j = 0; j < nb; ++j)
+    {
+      const SphereRec<R>& sp = m.spheres[B.s0 + j];
+      R x, y, z;
+      posePoint<R>(Tb, sp.x, sp.y, sp.z, x, y, z);
+      const R gx = x - tax, gy = y - tay, gz = z - taz;
+      const R lim = sp.r + A.tr + h.tight_eps;
+      if ((gx * gx + gy * gy + gz * gz) < lim * lim)
+        mb |= 1ull << j;
+    }
+    if (mb == 0ull)
+      return;
+  }
+  while (ma)
+  {
+    const int i = __ffsll(static_cast<long long>(ma)) - 1;
+    ma &= ma - 1;
+    const SphereRec<R>& sa = m.spheres[A.s0 + i];
+    R axp, ayp, azp;
+    posePoint<R>(Ta, sa.x, sa.y, sa.z, axp, ayp, azp);
+    unsigned long long mj = mb;
+    while (mj)
+    {
+      const int j = __ffsll(static_cast<long long>(mj)) - 1;
+      mj &= mj - 1;
+      const SphereRec<R>& sb = m.spheres[B.s0 + j];
+      R bxp, byp, bzp;
+      posePoint<R>(Tb, sb.x, sb.y, sb.z, bxp, byp, bzp);
+      const R gx2 = axp - bxp, gy2 = ayp - byp, gz2 = azp - bzp;
+      const R dd = gx2 * gx2 + gy2 * gy2 + gz2 * gz2;
+      const R rsum = sa.r + sb.r;
+      if (kExact)
+        hit |= sqrtR(dd) < rsum;  // gradient.norm() < r1 + r2 (collision_env_distance_field.cpp:577-583)
+      else
+      {
+        // squared form of dist < rsum -+ eps (both sides positive); the 1e-7 in pair_eps covers its rounding
+        const R lo = rsum - h.pair_eps, hi = rsum + h.pair_eps;
+        const bool c_cert = (lo > R(0)) && (dd < lo * lo);
+        const bool c_maybe = dd < hi * hi;
+        hit |= (cert && c_cert);
+        amb |= (c_maybe && !(cert && c_cert));
+      }
+    }
+  }
+}
+
+constexpr int kQueueCap = 512;  // (state, pair) work items per warp; flushed when fewer than 32 slots remain
+
+// Per-warp shared memory in bytes (16-byte aligned): transforms of 32 states | work queue | result words
+template <typename R>
+__device__ __host__ inline int perWarpBytes(int state_stride)
+{
+  return 32 * state_stride * static_cast<int>(sizeof(R)) + kQueueCap * 4 + 16;
+}
+
+// Dynamic shared memory: [model blob][per warp: Ts | queue | hit word, amb word]
+template <typename R, typename FT, bool kFromList>
 __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   const Smem<R> m = loadModel<R>(a.model, a.model_bytes, smem);
   const ModelHeader<R>& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  R* cent = reinterpret_cast<R*>(smem + h.total_bytes) + static_cast<size_t>(warp) * perWarpWords<R>(h, kTile);
-  R* bsc = cent + 4 * h.n_spheres;
-  R* Ts = bsc + 8 * h.n_bs;
+  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * perWarpBytes<R>(h.state_stride);
+  R* Ts = reinterpret_cast<R*>(wbase);
+  uint32_t* queue = reinterpret_cast<uint32_t*>(wbase + 32 * h.state_stride * sizeof(R));
+  unsigned* words = reinterpret_cast<unsigned*>(queue + kQueueCap);  // [0] hit, [1] amb
+  const bool do_world = (a.flags & 1u) != 0, do_self = (a.flags & 2u) != 0, do_intra = (a.flags & 4u) != 0;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   unsigned long long n = a.n_states;
   if (kFromList)
     n = *a.list_count < a.list_cap ? *a.list_count : a.list_cap;
-  // kFromList runs with kTile = 1: the recheck list is short, and one state per warp keeps its latency at one FK +
-  // one check instead of a tile of them in a row.
-  const unsigned long long n_tiles = (n + kTile - 1) / kTile;
+  const unsigned long long n_tiles = (n + 31) / 32;
   for (unsigned long long tile = static_cast<unsigned long long>(blockIdx.x) * warps + warp; tile < n_tiles;
        tile += static_cast<unsigned long long>(gridDim.x) * warps)
   {
-    const unsigned long long first = tile * kTile;
-    const int cnt = static_cast<int>(n - first < kTile ? n - first : kTile);
-    unsigned long long my_state = first + lane;
-    if (kFromList && lane < cnt)
-      my_state = a.list[first + lane];
-    if (lane < cnt)
-      fkState<R>(m, a.q + my_state * h.n_group_vars, Ts + lane * h.state_stride);
-    __syncwarp();
-    uint32_t valid_word = 0, flag_word = 0;
-    for (int s = 0; s < cnt; ++s)
+    const unsigned long long first = tile * 32;
+    const int cnt = static_cast<int>(n - first < 32 ? n - first : 32);
+    const bool active = lane < cnt;
+    unsigned long long my_state = first + (active ? lane : 0);  // idle lanes shadow lane 0; their result is dropped
+    if (kFromList)
+      my_state = a.list[my_state];
+    R* T = Ts + lane * h.state_stride;
+    // ---- phase 1: FK -------------------------------------------------------------------------------------------
+    fkState<R>(m, a.q + my_state * h.n_group_vars, T);
+    // ---- phase 2: world / self field ----------------------------------------------------------------------------
+    bool hit = false, amb = false;
+    if (do_world | do_self)
+      for (int k0 = 0; k0 < h.n_spheres_padded; k0 += 4)
+        sphereChunk<R, FT, 4>(m, T, k0, do_world, do_self, a.world, a.self, active && !hit, hit, amb);
+    // ---- phase 3: intra-group sphere pairs ----------------------------------------------------------------------
+    if (do_intra && h.n_pairs > 0 && __any_sync(kFull, active && !hit))
     {
-      bool hit, amb;
-      checkState<R, FT>(m, Ts + s * h.state_stride, cent, bsc, a.world, a.self, a.flags, lane, hit, amb);
-      __syncwarp();
-      if (amb)
-        flag_word |= 1u << s;
-      else if (!hit)
-        valid_word |= 1u << s;
+      if (lane == 0)
+        words[0] = words[1] = 0u;
+      __syncwarp();  // the queue consumers read other lanes' transforms
+      int qn = 0;
+      const bool mine = active && !hit;
+      // one (state, cluster pair) item per lane: levels 2 and 3; results OR-ed into the warp's hit / amb words
+      auto flush = [&]() {
+        __syncwarp();
+        for (int i = lane; i < qn; i += 32)
+        {
+          const unsigned item = queue[i];
+          const int s = item & 31;
+          bool ihit = false, iamb = false;
+          pairItem<R>(m, Ts + s * h.state_stride, m.pairs[item >> 6], (item & 32u) != 0, ihit, iamb);
+          if (ihit)
+            atomicOr(&words[0], 1u << s);
+          if (iamb)
+            atomicOr(&words[1], 1u << s);
+        }
+        __syncwarp();
+        qn = 0;
+      };
+      for (int g = 0; g < h.n_groups; ++g)
+      {
+        const GroupRec G = m.groups[g];
+        const BsRec<R>& A = m.bs[G.a];
+        R Ta[12], ax, ay, az;
+        load12(T + A.slot * kLinkStrideWords, Ta);
+        posePoint<R>(Ta, A.tx, A.ty, A.tz, ax, ay, az);
+        for (int p = G.p0; p < G.p1; ++p)
+        {
+          bool live = false, certain = false;
+          if (mine)
+            pairCull<R>(m, T, A, Ta, ax, ay, az, m.bs[m.pairs[p].b], live, certain);
+          const unsigned mk = __ballot_sync(kFull, live);
+          if (live)
+            queue[qn + __popc(mk & lt_mask)] = static_cast<uint32_t>(lane | (certain ? 32 : 0) | (p << 6));
+          qn += __popc(mk);
+          if (qn > kQueueCap - 32)
+            flush();
+        }
+      }
+      if (qn > 0)
+        flush();
+      hit |= ((words[0] >> lane) & 1u) != 0;
+      amb |= ((words[1] >> lane) & 1u) != 0;
     }
+    __syncwarp();  // transforms and words are rewritten by the next tile
+    const bool valid = active && !hit && !amb;
+    const bool flagged = active && amb && !hit;  // FP32 could not decide: the exact pass will
     if (kFromList)
     {
       // patch the bits of the rechecked states (the fast pass left them 0)
-      if (lane < cnt && ((valid_word >> lane) & 1u))
+      if (valid)
         atomicOr(a.bitmap + (my_state >> 5), 1u << (my_state & 31));
     }
     else
     {
+      const unsigned valid_word = __ballot_sync(kFull, valid);
+      const unsigned flag_word = __ballot_sync(kFull, flagged);
       if (lane == 0)
-      {
-        if (kTile == 32)
-          a.bitmap[tile] = valid_word;
-        else if (kTile == 16)
-          reinterpret_cast<uint16_t*>(a.bitmap)[tile] = static_cast<uint16_t>(valid_word);
-        else
-          reinterpret_cast<uint8_t*>(a.bitmap)[tile] = static_cast<uint8_t>(valid_word);
-      }
+        a.bitmap[tile] = valid_word;
       if (flag_word)
       {
-        const int c = __popc(flag_word);
         unsigned base = 0;
         if (lane == 0)
-          base = atomicAdd(a.flag_count, static_cast<unsigned>(c));
+          base = atomicAdd(a.flag_count, static_cast<unsigned>(__popc(flag_word)));
         base = __shfl_sync(kFull, base, 0);
-        if ((flag_word >> lane) & 1u)
+        if (flagged)
         {
-          const unsigned rank = __popc(flag_word & ((1u << lane) - 1u));
+          const unsigned rank = __popc(flag_word & lt_mask);
           if (base + rank < a.list_cap)
             a.flag_list[base + rank] = static_cast<uint32_t>(first + lane);
         }
@@ -733,55 +769,52 @@ cudaError_t ensureSmem(K kernel, size_t smem_bytes, SmemGrant& g)
   return e;
 }
 
-template <typename R, typename FT, bool kList, int kTile>
+template <typename R, typename FT, bool kList>
 cudaError_t launchOne(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
   static SmemGrant g;
-  cudaError_t e = ensureSmem(checkKernel<R, FT, kList, kTile>, smem_bytes, g);
+  cudaError_t e = ensureSmem(checkKernel<R, FT, kList>, smem_bytes, g);
   if (e != cudaSuccess)
     return e;
-  checkKernel<R, FT, kList, kTile><<<grid, block, smem_bytes, stream>>>(a);
+  checkKernel<R, FT, kList><<<grid, block, smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
 
-template <typename R, typename FT, bool kList, int kTile>
+template <typename R, typename FT, bool kList>
 int regsOf()
 {
   cudaFuncAttributes fa{};
-  if (cudaFuncGetAttributes(&fa, checkKernel<R, FT, kList, kTile>) != cudaSuccess)
+  if (cudaFuncGetAttributes(&fa, checkKernel<R, FT, kList>) != cudaSuccess)
     return 128;
   return fa.numRegs;
 }
 }  // namespace
 
+int checkPerWarpBytes(bool fp64, int state_stride)
+{
+  return fp64 ? perWarpBytes<double>(state_stride) : perWarpBytes<float>(state_stride);
+}
+
 template <typename FT>
-cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int tile, int grid, int block,
-                        size_t smem_bytes, cudaStream_t stream)
+cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int grid, int block, size_t smem_bytes,
+                        cudaStream_t stream)
 {
   if (fp64 && from_list)
-    return launchOne<double, FT, true, 1>(a, grid, block, smem_bytes, stream);
+    return launchOne<double, FT, true>(a, grid, block, smem_bytes, stream);
   if (fp64)
-    return tile == 32 ? launchOne<double, FT, false, 32>(a, grid, block, smem_bytes, stream) :
-           tile == 16 ? launchOne<double, FT, false, 16>(a, grid, block, smem_bytes, stream) :
-                        launchOne<double, FT, false, 8>(a, grid, block, smem_bytes, stream);
-  return tile == 32 ? launchOne<float, FT, false, 32>(a, grid, block, smem_bytes, stream) :
-         tile == 16 ? launchOne<float, FT, false, 16>(a, grid, block, smem_bytes, stream) :
-                      launchOne<float, FT, false, 8>(a, grid, block, smem_bytes, stream);
+    return launchOne<double, FT, false>(a, grid, block, smem_bytes, stream);
+  return launchOne<float, FT, false>(a, grid, block, smem_bytes, stream);
 }
-template cudaError_t launchCheck<uint8_t>(const CheckArgs<uint8_t>&, bool, bool, int, int, int, size_t, cudaStream_t);
-template cudaError_t launchCheck<uint16_t>(const CheckArgs<uint16_t>&, bool, bool, int, int, int, size_t, cudaStream_t);
+template cudaError_t launchCheck<uint8_t>(const CheckArgs<uint8_t>&, bool, bool, int, int, size_t, cudaStream_t);
+template cudaError_t launchCheck<uint16_t>(const CheckArgs<uint16_t>&, bool, bool, int, int, size_t, cudaStream_t);
 
-int checkKernelRegs(bool fp64, bool from_list, int tile, int field_bytes)
+int checkKernelRegs(bool fp64, bool from_list, int field_bytes)
 {
   if (field_bytes == 1)
-  {
-    if (fp64 && from_list) return regsOf<double, uint8_t, true, 1>();
-    if (fp64) return tile == 32 ? regsOf<double, uint8_t, false, 32>() : tile == 16 ? regsOf<double, uint8_t, false, 16>() : regsOf<double, uint8_t, false, 8>();
-    return tile == 32 ? regsOf<float, uint8_t, false, 32>() : tile == 16 ? regsOf<float, uint8_t, false, 16>() : regsOf<float, uint8_t, false, 8>();
-  }
-  if (fp64 && from_list) return regsOf<double, uint16_t, true, 1>();
-  if (fp64) return tile == 32 ? regsOf<double, uint16_t, false, 32>() : tile == 16 ? regsOf<double, uint16_t, false, 16>() : regsOf<double, uint16_t, false, 8>();
-  return tile == 32 ? regsOf<float, uint16_t, false, 32>() : tile == 16 ? regsOf<float, uint16_t, false, 16>() : regsOf<float, uint16_t, false, 8>();
+    return fp64 ? (from_list ? regsOf<double, uint8_t, true>() : regsOf<double, uint8_t, false>()) :
+                  regsOf<float, uint8_t, false>();
+  return fp64 ? (from_list ? regsOf<double, uint16_t, true>() : regsOf<double, uint16_t, false>()) :
+                regsOf<float, uint16_t, false>();
 }
 
 cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream)

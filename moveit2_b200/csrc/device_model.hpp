@@ -18,6 +18,7 @@ struct alignas(16) LinkRec
   int type;    // JointType
   int var;     // first VarRec of the joint
   int has_origin;  // 0: `o` is the identity (LinkModel::jointOriginTransformIsIdentity), skip the product
+  int s0, s1;      // collision spheres carried by this link: SphereRec range [s0, s1) (spheres are sorted by link)
   int pad;
 };
 
@@ -39,22 +40,28 @@ struct alignas(16) SphereRec
   int pad;
 };
 
+// A CLUSTER: a contiguous run of one link's collision spheres.  Carries the LINK's reference bounding sphere (for
+// the reference's own cull, identical for every cluster of the link) and the cluster's tight sphere (ours).
 template <typename R>
-struct alignas(16) BsRec  // per link with spheres
+struct alignas(16) BsRec
 {
-  R x, y, z, r;      // BodyDecomposition::getRelativeBoundingSphere(): posed for doBoundingSpheresIntersect (types.cpp:408-418)
-  R tx, ty, tz, tr;  // OUR tight bounding sphere of the link's collision spheres (centroid, max |c_k - c| + r_k):
-                     // a conservative extra cull, it can only skip pairs that cannot collide
+  R x, y, z, r;      // BodyDecomposition::getRelativeBoundingSphere() of the link: doBoundingSpheresIntersect (types.cpp:408-418)
+  R tx, ty, tz, tr;  // tight bounding sphere of the cluster's spheres (centroid, max |c_k - c| + r_k): a conservative
+                     // extra cull -- it can only skip pairs that cannot collide
   int slot, s0, s1, pad;  // device-link slot, sphere range [s0, s1)
 };
 
-struct alignas(16) PairRec  // enabled intra-group link pair (indices into the BsRec table), i < j in dfce order
+// Enabled pair of clusters of two different links whose link pair is enabled in
+// dfce->intra_group_collision_enabled_ (i < j in dfce order).
+struct alignas(8) PairRec
 {
-  int a, b;
-  int sa0, sb0;    // first sphere of each link
-  int na, nb;      // sphere counts
-  unsigned magic;  // ceil(2^16 / nb): t / nb == (t * magic) >> 16 over [0, na * nb) (the host verifies the range)
-  int tot;         // na * nb
+  int a, b;  // BsRec indices
+};
+
+// Pairs [p0, p1) share cluster `a`: the level-1 loop poses it once.
+struct alignas(16) GroupRec
+{
+  int a, p0, p1, pad;
 };
 
 template <typename R>
@@ -63,7 +70,8 @@ struct ModelHeader
   int n_links, n_vars, n_spheres, n_bs, n_pairs, n_group_vars;
   int off_links, off_vars, off_spheres, off_bs, off_pairs, total_bytes;
   int state_stride, link_stride;  // shared-memory strides (in R) of a state's / a link's transform
-  int nx, ny, nz, pad0;
+  int nx, ny, nz, n_groups;
+  int off_groups, n_spheres_padded, pad1, pad2;  // spheres are padded to a multiple of 4 with thr = 0 dummies
   R om[3];      // VoxelGrid::origin_minus_
   R oo_res;     // VoxelGrid::oo_resolution_
   R margin;     // FP32 pass: voxel-coordinate uncertainty (cells); 0 in the FP64 pass
@@ -74,7 +82,6 @@ struct ModelHeader
 
 // Shared-memory layout of one state's transforms: link stride 12 words (3x4 row-major), every row 16-byte aligned
 // so a row is ONE 128-bit access.  The state stride is padded to 4 (mod 32) words in the FP32 blob: the 8 lanes of a
-// quarter-warp then write 8 distinct 16-byte bank groups (conflict-free STS.128 in the FK phase); in the check phase
-// the lanes of a quarter-warp mostly read the same link (broadcast).
+// quarter-warp then touch 8 distinct 16-byte bank groups (conflict-free 128-bit accesses).
 constexpr int kLinkStrideWords = 12;
 }  // namespace b200sv

@@ -37,11 +37,11 @@ struct FkArgs
   double* out;            // [n_states * n_model_links * 16]
 };
 
-// tile: states per warp per FK pass (32, 16 or 8; the list variant always uses 1)
 template <typename FT>
-cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int tile, int grid, int block,
-                        size_t smem_bytes, cudaStream_t stream);
-int checkKernelRegs(bool fp64, bool from_list, int tile, int field_bytes);
+cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int grid, int block, size_t smem_bytes,
+                        cudaStream_t stream);
+int checkKernelRegs(bool fp64, bool from_list, int field_bytes);
+int checkPerWarpBytes(bool fp64, int state_stride);  // shared memory one warp of the check kernel needs
 cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launchGather(const uint8_t* field, unsigned long long n_sectors, int per_thread, int grid, int block,

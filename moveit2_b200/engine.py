@@ -269,8 +269,8 @@ class StateValidityEngine:
         self._check(self.L.b200sv_gather_roofline(self.h, n_reads, iters, C.byref(g)))
         return g.value
 
-    def set_tuning(self, fp32_eps_m=0.0, tile=0, blocks_per_sm=0):
-        self._check(self.L.b200sv_set_tuning(self.h, float(fp32_eps_m), int(tile), int(blocks_per_sm)))
+    def set_tuning(self, fp32_eps_m=0.0, warps_per_block=0, blocks_per_sm=0):
+        self._check(self.L.b200sv_set_tuning(self.h, float(fp32_eps_m), int(warps_per_block), int(blocks_per_sm)))
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -35,19 +35,20 @@ def run(flags, reps=10):
 
 
 ref = None
-for tile in (32, 16, 8):
-    for blocks in (1, 2, 3, 4):
+for warps in (16, 12, 8, 6, 4):
+    for blocks in (1, 2, 3):
         try:
-            eng.set_tuning(0.0, tile, blocks)
+            eng.set_tuning(0.0, warps, blocks)
         except mb.B200svError as e:
-            print("tile %2d blocks %d: %s" % (tile, blocks, e))
+            print("warps %2d blocks %d: %s" % (warps, blocks, e))
             continue
         ms = run(mb.CHECK_ALL)
         out = bm.cpu().numpy().copy()
         if ref is None:
             ref = out
         same = np.array_equal(ref, out)
-        print("tile %2d blocks/SM %d: %.3f ms  %.3g states/s  world-only %.3f ms  intra-only %.3f ms  %s" %
-              (tile, blocks, ms, n / ms * 1e3, run(mb.CHECK_WORLD), run(mb.CHECK_INTRA), "" if same else "RESULT DIFFERS"))
-eng.set_tuning(0.0, 16, 2)
+        print("warps/CTA cap %2d CTAs/SM %d: %.3f ms  %.3g states/s  world+self %.3f ms  intra-only %.3f ms  %s" %
+              (warps, blocks, ms, n / ms * 1e3, run(mb.CHECK_WORLD | mb.CHECK_SELF), run(mb.CHECK_INTRA),
+               "" if same else "RESULT DIFFERS"))
+eng.set_tuning(0.0, 16, 1)
 print("fp64 all states: %.3f ms" % run(mb.CHECK_ALL | mb.CHECK_FP64, 3))
