@@ -25,7 +25,7 @@ struct Field
 {
   uint32_t* occ = nullptr;    // occupancy bits
   uint16_t* d2 = nullptr;     // min(d^2, max_d2)
-  void* compact = nullptr;    // what the check kernel gathers (uint8 clamp, or == d2)
+  void* compact = nullptr;    // this field's half of the interleaved compact field (base + which elements)
   bool dirty = false;
 };
 
@@ -75,7 +75,7 @@ struct b200sv_ctx
   std::vector<uint8_t> blob_f, blob_d;
   uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
-  double cluster_radius = 0.09;  // max tight-sphere radius of a sphere cluster (m)
+  double cluster_radius = 0.12;  // max tight-sphere radius of a sphere cluster (m)
   int state_stride_f = 0, state_stride_d = 0;  // shared-memory words per state (float / double blob)
   std::vector<int> link_slot;      // model link -> device slot
   std::vector<double> const_T;     // model links * 16 (base state)
@@ -83,6 +83,7 @@ struct b200sv_ctx
   double* d_const_T = nullptr;
   Field fields[2];
   uint16_t* d_tmp = nullptr;  // EDT intermediate
+  void* d_combined = nullptr; // interleaved compact field {world, self} per voxel
   // launch config
   int sm_count = 148, smem_optin = 0;
   struct LaunchCfg
@@ -493,7 +494,18 @@ int buildTables(b200sv_ctx* c)
       for (int j = i + 1; j < m.n_glinks; ++j)
         if (!clusters_of_glink[j].empty() && m.intra_enabled[(size_t)i * m.n_glinks + j])
           for (int cb : clusters_of_glink[j])
-            pairs.push_back(PairRec{ ca, cb });
+          {
+            // The reference culls a link pair unless |Ci - Cj|^2 < Ri + Rj on the links' bounding spheres
+            // (types.cpp:416-417).  If our tight spheres are near, |Ci - Cj| <= (tr_a + tr_b + slack) + |Ci - ta| +
+            // |Cj - tb| (rigid offsets inside each link).  When that bound, squared, is safely below Ri + Rj the
+            // reference's test cannot fail, and the kernel skips evaluating it.
+            const BsRec<double>&A = bs[ca], &B = bs[cb];
+            const double oa = sqrt((A.x - A.tx) * (A.x - A.tx) + (A.y - A.ty) * (A.y - A.ty) + (A.z - A.tz) * (A.z - A.tz));
+            const double ob = sqrt((B.x - B.tx) * (B.x - B.tx) + (B.y - B.ty) * (B.y - B.ty) + (B.z - B.tz) * (B.z - B.tz));
+            const double dmax = A.tr + B.tr + oa + ob + 1e-3;
+            const int quirk_free = dmax * dmax < (A.r + B.r) - 1e-3 ? 1 : 0;
+            pairs.push_back(PairRec{ ca, cb, quirk_free, 0 });
+          }
       G.p1 = (int)pairs.size();
       if (G.p1 > G.p0)
         groups.push_back(G);
@@ -621,15 +633,14 @@ int allocFields(b200sv_ctx* c)
 {
   const GridDev& g = c->grid;
   const size_t occ_bytes = (size_t)g.nx * g.ny * g.wz * 4;
+  // what the check kernel gathers: [voxel] = { world, self } side by side, so one load serves both checks
+  CU(c, cudaMalloc(&c->d_combined, c->n_voxels * 2 * (size_t)c->compact_bytes));
   for (int w = 0; w < 2; ++w)
   {
     Field& F = c->fields[w];
     CU(c, cudaMalloc(&F.occ, occ_bytes));
     CU(c, cudaMalloc(&F.d2, c->n_voxels * 2));
-    if (c->compact_bytes == 1)
-      CU(c, cudaMalloc(&F.compact, c->n_voxels));
-    else
-      F.compact = F.d2;
+    F.compact = static_cast<uint8_t*>(c->d_combined) + (size_t)w * c->compact_bytes;
     CU(c, cudaMemsetAsync(F.occ, 0, occ_bytes, c->stream));
     CU(c, launchFillField(g, F.d2, F.compact, c->compact_bytes, c->stream));
   }
@@ -738,8 +749,7 @@ int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_
   CheckArgs<FT> a{};
   a.q = d_q;
   a.n_states = n;
-  a.world = static_cast<const FT*>(c->fields[0].compact);
-  a.self = static_cast<const FT*>(c->fields[1].compact);
+  a.field = c->d_combined;
   a.flags = flags & 7u;
   a.bitmap = d_bitmap;
   a.flag_list = c->d_list.p;
@@ -876,13 +886,12 @@ void b200sv_destroy(b200sv_ctx* c)
   for (int w = 0; w < 2; ++w)
   {
     Field& F = c->fields[w];
-    if (F.compact && F.compact != F.d2)
-      cudaFree(F.compact);
     if (F.d2)
       cudaFree(F.d2);
     if (F.occ)
       cudaFree(F.occ);
   }
+  if (c->d_combined) cudaFree(c->d_combined);
   if (c->d_tmp) cudaFree(c->d_tmp);
   if (c->d_blob_f) cudaFree(c->d_blob_f);
   if (c->d_blob_d) cudaFree(c->d_blob_d);
@@ -1264,13 +1273,13 @@ int b200sv_gather_roofline(b200sv_ctx* c, size_t n_reads, int iters, double* gbs
     return B200SV_ERR_NO_DEVICE;
   std::lock_guard<std::mutex> lk(c->mu);
   cudaSetDevice(c->device);
-  const size_t field_bytes = c->n_voxels * (size_t)c->compact_bytes;
+  const size_t field_bytes = c->n_voxels * 2 * (size_t)c->compact_bytes;
   const unsigned long long n_sectors = field_bytes / 32;
   if (n_sectors == 0)
     return fail(c, B200SV_ERR_INVALID, "field smaller than one sector");
   const int block = 256, per_thread = 64;
   const int grid = (int)std::min<size_t>((n_reads + (size_t)block * per_thread - 1) / ((size_t)block * per_thread), 1u << 20);
-  const uint8_t* f = static_cast<const uint8_t*>(c->fields[0].compact);
+  const uint8_t* f = static_cast<const uint8_t*>(c->d_combined);
   CU(c, launchGather(f, n_sectors, per_thread, grid, block, c->d_sink, c->stream));  // warm-up
   float best = 1e30f;
   for (int i = 0; i < iters; ++i)

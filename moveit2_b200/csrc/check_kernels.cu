@@ -42,6 +42,18 @@ namespace
 {
 constexpr unsigned kFull = 0xffffffffu;
 
+// One element of the interleaved compact field holds both fields of a voxel: world in the low half, self in the high.
+template <typename FT> struct Combined;
+template <> struct Combined<uint8_t> { using type = uint16_t; };
+template <> struct Combined<uint16_t> { using type = uint32_t; };
+template <typename FT>
+__device__ __forceinline__ void gatherBoth(const typename Combined<FT>::type* __restrict__ field, int idx, int& dw, int& ds)
+{
+  const unsigned v = static_cast<unsigned>(__ldg(field + idx));
+  dw = static_cast<int>(v & ((1u << (8 * sizeof(FT))) - 1u));
+  ds = static_cast<int>(v >> (8 * sizeof(FT)));
+}
+
 template <typename R>
 struct Smem
 {
@@ -309,7 +321,7 @@ __device__ __forceinline__ Smem<R> loadModel(const uint8_t* __restrict__ g_model
 // FP32 only, rare: the centre of sphere k is within `margin` of a cell face.  Evaluate every candidate cell.
 template <typename R, typename FT>
 __device__ __noinline__ void riskySphere(const Smem<R>& m, const R* T, int k, bool do_world, bool do_self,
-                                         const FT* __restrict__ world, const FT* __restrict__ self, bool& hit, bool& amb)
+                                         const typename Combined<FT>::type* __restrict__ field, bool& hit, bool& amb)
 {
   const ModelHeader<R>& h = *m.h;
   const SphereRec<R> sp = m.spheres[k];
@@ -330,10 +342,9 @@ __device__ __noinline__ void riskySphere(const Smem<R>& m, const R* T, int k, bo
         bool c = false;
         if (ix >= 1 && iy >= 1 && iz >= 1 && ix < h.nx - 1 && iy < h.ny - 1 && iz < h.nz - 1)
         {
-          const int idx = (ix * h.ny + iy) * h.nz + iz;
-          const int dw = thr_w ? static_cast<int>(__ldg(world + idx)) : 0x7fffffff;
-          const int ds = thr_s ? static_cast<int>(__ldg(self + idx)) : 0x7fffffff;
-          c = (dw < thr_w) | (ds < thr_s);
+          int dw, ds;
+          gatherBoth<FT>(field, (ix * h.ny + iy) * h.nz + iz, dw, ds);
+          c = (dw < thr_w) | (ds < thr_s);  // a threshold of 0 disables that field
         }
         any |= c;
         all &= c;
@@ -345,7 +356,7 @@ __device__ __noinline__ void riskySphere(const Smem<R>& m, const R* T, int k, bo
 // Phase 2 for kU consecutive spheres of this lane's state: pose, voxel, gather (all loads first), compare.
 template <typename R, typename FT, int kU>
 __device__ __forceinline__ void sphereChunk(const Smem<R>& m, const R* T, int k0, bool do_world, bool do_self,
-                                            const FT* __restrict__ world, const FT* __restrict__ self, bool live_lane,
+                                            const typename Combined<FT>::type* __restrict__ field, bool live_lane,
                                             bool& hit, bool& amb)
 {
   constexpr bool kExact = sizeof(R) == 8;
@@ -406,10 +417,7 @@ __device__ __forceinline__ void sphereChunk(const Smem<R>& m, const R* T, int k0
   {
     dw[u] = ds[u] = 0x7fffffff;
     if (idx[u] >= 0)
-    {
-      if (tw[u]) dw[u] = static_cast<int>(__ldg(world + idx[u]));
-      if (ts[u]) ds[u] = static_cast<int>(__ldg(self + idx[u]));
-    }
+      gatherBoth<FT>(field, idx[u], dw[u], ds[u]);  // ONE gather: both fields of the voxel sit side by side
   }
 #pragma unroll
   for (int u = 0; u < kU; ++u)
@@ -419,7 +427,7 @@ __device__ __forceinline__ void sphereChunk(const Smem<R>& m, const R* T, int k0
 #pragma unroll
     for (int u = 0; u < kU; ++u)
       if ((risky >> u) & 1u)
-        riskySphere<R, FT>(m, T, k0 + u, do_world, do_self, world, self, hit, amb);
+        riskySphere<R, FT>(m, T, k0 + u, do_world, do_self, field, hit, amb);
   }
 }
 
@@ -428,7 +436,7 @@ __device__ __forceinline__ void sphereChunk(const Smem<R>& m, const R* T, int k0
 // of cluster a, Ta: its link transform (both shared by the whole group of pairs).
 template <typename R>
 __device__ __forceinline__ void pairCull(const Smem<R>& m, const R* T, const BsRec<R>& A, const R* Ta, R ax, R ay, R az,
-                                         const BsRec<R>& B, bool& live, bool& certain)
+                                         const BsRec<R>& B, bool quirk_free, bool& live, bool& certain)
 {
   constexpr bool kExact = sizeof(R) == 8;
   const ModelHeader<R>& h = *m.h;
@@ -443,6 +451,11 @@ __device__ __forceinline__ void pairCull(const Smem<R>& m, const R* T, const BsR
   live = certain = false;
   if ((fx * fx + fy * fy + fz * fz) < rt * rt)
   {
+    if (quirk_free)
+    {  // the host proved: whenever these two tight spheres are this close, the reference's cull below passes
+      live = certain = true;
+      return;
+    }
     // doBoundingSpheresIntersect (types.cpp:408-418) on the LINKS' bounding spheres, quirk kept: SQUARED centre
     // distance against the plain radius sum
     R px, py, pz, qx, qy, qz;
@@ -564,6 +577,7 @@ __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
   uint32_t* queue = reinterpret_cast<uint32_t*>(wbase + 32 * h.state_stride * sizeof(R));
   unsigned* words = reinterpret_cast<unsigned*>(queue + kQueueCap);  // [0] hit, [1] amb
   const bool do_world = (a.flags & 1u) != 0, do_self = (a.flags & 2u) != 0, do_intra = (a.flags & 4u) != 0;
+  const typename Combined<FT>::type* __restrict__ field = static_cast<const typename Combined<FT>::type*>(a.field);
   const unsigned lt_mask = (1u << lane) - 1u;
 
   unsigned long long n = a.n_states;
@@ -586,7 +600,7 @@ __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
     bool hit = false, amb = false;
     if (do_world | do_self)
       for (int k0 = 0; k0 < h.n_spheres_padded; k0 += 4)
-        sphereChunk<R, FT, 4>(m, T, k0, do_world, do_self, a.world, a.self, active && !hit, hit, amb);
+        sphereChunk<R, FT, 4>(m, T, k0, do_world, do_self, field, active && !hit, hit, amb);
     // ---- phase 3: intra-group sphere pairs ----------------------------------------------------------------------
     if (do_intra && h.n_pairs > 0 && __any_sync(kFull, active && !hit))
     {
@@ -623,7 +637,10 @@ __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
         {
           bool live = false, certain = false;
           if (mine)
-            pairCull<R>(m, T, A, Ta, ax, ay, az, m.bs[m.pairs[p].b], live, certain);
+          {
+            const PairRec pr = m.pairs[p];
+            pairCull<R>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr.quirk_free != 0, live, certain);
+          }
           const unsigned mk = __ballot_sync(kFull, live);
           if (live)
             queue[qn + __popc(mk & lt_mask)] = static_cast<uint32_t>(lane | (certain ? 32 : 0) | (p << 6));

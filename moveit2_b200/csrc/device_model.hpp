@@ -53,9 +53,11 @@ struct alignas(16) BsRec
 
 // Enabled pair of clusters of two different links whose link pair is enabled in
 // dfce->intra_group_collision_enabled_ (i < j in dfce order).
-struct alignas(8) PairRec
+struct alignas(16) PairRec
 {
-  int a, b;  // BsRec indices
+  int a, b;         // BsRec indices
+  int quirk_free;   // 1: tight spheres this close imply the reference's link-level cull passes (proved on the host)
+  int pad;
 };
 
 // Pairs [p0, p1) share cluster `a`: the level-1 loop poses it once.

@@ -148,10 +148,8 @@ __global__ void __launch_bounds__(256) edtXKernel(GridDev g, const uint16_t* __r
     }
     best = min(best, max_d2);
     d2[i] = static_cast<uint16_t>(best);
-    if (sizeof(FT) == 1)
-      compact[i] = static_cast<FT>(min(best, 255));
-    else if (reinterpret_cast<const void*>(compact) != reinterpret_cast<const void*>(d2))
-      compact[i] = static_cast<FT>(best);
+    // interleaved compact field: element 2 * i + which (the caller passes compact already offset by `which`)
+    compact[2 * i] = static_cast<FT>(sizeof(FT) == 1 ? min(best, 255) : best);
   }
 }
 
@@ -162,7 +160,7 @@ __global__ void fillKernel(size_t total, int max_d2, uint16_t* d2, FT* compact)
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
   {
     d2[i] = static_cast<uint16_t>(max_d2);
-    compact[i] = static_cast<FT>(sizeof(FT) == 1 ? min(max_d2, 255) : max_d2);
+    compact[2 * i] = static_cast<FT>(sizeof(FT) == 1 ? min(max_d2, 255) : max_d2);
   }
 }
 
@@ -175,7 +173,7 @@ __global__ void injectKernel(GridDev g, const int32_t* __restrict__ in, uint32_t
   {
     const int v = min(max(in[i], 0), g.max_d2);
     d2[i] = static_cast<uint16_t>(v);
-    compact[i] = static_cast<FT>(sizeof(FT) == 1 ? min(v, 255) : v);
+    compact[2 * i] = static_cast<FT>(sizeof(FT) == 1 ? min(v, 255) : v);
     if (v == 0)
     {
       const int z = static_cast<int>(i % g.nz);

@@ -14,8 +14,8 @@ struct CheckArgs
   int model_bytes;
   const double* q;       // [n_states * n_group_vars]
   unsigned long long n_states;
-  const FT* world;       // compact d^2 fields, index x*ny*nz + y*nz + z
-  const FT* self;
+  const void* field;     // interleaved compact d^2: element [voxel] = world | self << (8 * sizeof(FT)),
+                         // voxel = x*ny*nz + y*nz + z; one gather serves both checks
   uint32_t flags;
   uint32_t* bitmap;      // validity words
   uint32_t* flag_list;   // fast pass: states to recheck (out)
@@ -60,8 +60,9 @@ struct GridDev
 
 // occupancy bitmap: word ((x*ny + y)*wz + z/32), bit z%32
 cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint32_t* occ, bool set, cudaStream_t s);
-// exact truncated EDT of the occupancy bitmap -> d2 (uint16, min(d^2, max_d2)) and the compact field FT
-// (uint8: min(d^2, 255); uint16: same as d2).  tmp: uint16 [nx*ny*nz] scratch.
+// exact truncated EDT of the occupancy bitmap -> d2 (uint16, min(d^2, max_d2)) and this field's half of the
+// INTERLEAVED compact field (element 2 * voxel; `compact` arrives offset by 0 = world / 1 = self; uint8:
+// min(d^2, 255), uint16: d^2).  tmp: uint16 [nx*ny*nz] scratch.
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
                       int compact_bytes, int sm_count, cudaStream_t s);
 cudaError_t launchFillField(const GridDev& g, uint16_t* d2, void* compact, int compact_bytes, cudaStream_t s);
