@@ -36,7 +36,7 @@ METRIC = "collision_checked_states_per_sec"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--states", type=int, default=0, help="states per GPU per step (default: the config's 1 000 000)")
@@ -195,17 +195,22 @@ def main():
     flags = mb.CHECK_ALL | (mb.CHECK_FP64 if args.fp64 else 0)
 
     # ---- device-resident step ---------------------------------------------------------------------------
+    from moveit2_b200.sharding import ShardedStateValidity
     d_q = torch.from_numpy(q_host).to(dev)
-    words = (n + 31) // 32
-    d_bm = torch.zeros(words * 4, dtype=torch.uint8, device=dev)
-    d_all = torch.zeros(world * words * 4, dtype=torch.uint8, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
+    def check_local(q_local, bitmap):
+        eng.check_batch_device(q_local.data_ptr(), q_local.shape[0], flags, bitmap.data_ptr(), stream.cuda_stream)
+
+    # weak scaling: n states per rank; the global batch is world * n states, sharded contiguously (n is a multiple of
+    # 32 or the single-GPU tail), bitmap slices all-gathered (NCCL over NVLink) at the end of every step
+    sv = ShardedStateValidity(check_local, world * n, dev)
+    assert sv.hi - sv.lo == n or world == 1
+    d_bm = sv.local
+
     def step():
-        eng.check_batch_device(d_q.data_ptr(), n, flags, d_bm.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_gather_into_tensor(d_all, d_bm)
+        sv.check(d_q)
 
     def barrier():
         if world > 1:
@@ -276,7 +281,8 @@ def main():
                                "cloud, 2 m^3 field @ 1 cm (200^3 voxels, uint8 compact d^2), checks world+self+intra" % (S, n),
                    "l2": "flushed between timed steps (256 MiB write)", "fp32_pass_with_fp64_recheck": not args.fp64,
                    "valid_fraction": valid_frac, "rechecked_states_per_step": st["n_rechecked"],
-                   "sharding": "states sharded contiguously, fields replicated, bitmap all_gather (NCCL) per step"
+                   "sharding": "states sharded contiguously (moveit2_b200/sharding.py), fields replicated, one NCCL "
+                               "all_gather of the bitmap slices per step"
                    if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": "states/s", "h2d_bytes_per_step": n * V * 8, "d2h_bytes_per_step": (n + 7) // 8,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "kernel_ms_inside": e2e_kernel_ms},

@@ -1,0 +1,411 @@
+// See collision_env_b200.hpp.  Everything numerical happens behind the C-ABI; this file only flattens MoveIt's
+// objects into the plain arrays of include/b200sv.h, exactly where CollisionEnvDistanceField builds its own
+// DistanceFieldCacheEntry / GroupStateRepresentation (collision_env_distance_field.cpp:710-958, 1157-1252).
+#include "collision_env_b200.hpp"
+
+#include <moveit/robot_model/robot_model.hpp>
+#include <moveit/robot_state/robot_state.hpp>
+#include <moveit/utils/logger.hpp>
+#include <geometric_shapes/shapes.h>
+
+namespace collision_detection
+{
+namespace
+{
+rclcpp::Logger getLogger()
+{
+  return moveit::getLogger("moveit.core.collision_env_b200");
+}
+const double STATE_EPSILON = 0.001;  // EPSILON of collision_env_distance_field.cpp:55
+
+b200sv_field_cfg fieldCfg(const Eigen::Vector3d& size, const Eigen::Vector3d& origin, double res, double max_prop,
+                          double tol)
+{
+  b200sv_field_cfg f{};
+  for (int k = 0; k < 3; ++k)
+  {
+    f.size[k] = size[k];
+    f.origin[k] = origin[k];
+  }
+  f.resolution = res;
+  f.max_propagation_distance = max_prop;
+  f.collision_tolerance = tol;
+  f.use_signed_distance_field = 0;
+  return f;
+}
+}  // namespace
+
+CollisionEnvB200::CollisionEnvB200(const moveit::core::RobotModelConstPtr& robot_model, double padding, double scale)
+  : CollisionEnv(robot_model, padding, scale)
+{
+  initialize();
+  observer_handle_ = getWorld()->addObserver(
+      [this](const World::ObjectConstPtr& object, World::Action action) { notifyObjectChange(object, action); });
+}
+
+CollisionEnvB200::CollisionEnvB200(const moveit::core::RobotModelConstPtr& robot_model, const WorldPtr& world,
+                                   double padding, double scale)
+  : CollisionEnv(robot_model, world, padding, scale)
+{
+  initialize();
+  observer_handle_ = getWorld()->addObserver(
+      [this](const World::ObjectConstPtr& object, World::Action action) { notifyObjectChange(object, action); });
+  getWorld()->notifyObserverAllObjects(observer_handle_, World::CREATE);
+}
+
+CollisionEnvB200::CollisionEnvB200(const CollisionEnvB200& other, const WorldPtr& world) : CollisionEnv(other, world)
+{
+  size_ = other.size_;
+  origin_ = other.origin_;
+  resolution_ = other.resolution_;
+  collision_tolerance_ = other.collision_tolerance_;
+  max_propogation_distance_ = other.max_propogation_distance_;
+  link_body_decomposition_vector_ = other.link_body_decomposition_vector_;
+  link_body_decomposition_index_map_ = other.link_body_decomposition_index_map_;
+  // contexts are per (group, non-group state, ACM) and own device memory: a child scene builds its own lazily and
+  // replays its world into them, as the reference rebuilds its world field (:111, :118)
+  observer_handle_ = getWorld()->addObserver(
+      [this](const World::ObjectConstPtr& object, World::Action action) { notifyObjectChange(object, action); });
+  getWorld()->notifyObserverAllObjects(observer_handle_, World::CREATE);
+}
+
+CollisionEnvB200::~CollisionEnvB200()
+{
+  getWorld()->removeObserver(observer_handle_);
+  for (auto& kv : contexts_)
+    if (kv.second && kv.second->ctx)
+      b200sv_destroy(kv.second->ctx);
+}
+
+void CollisionEnvB200::initialize()
+{
+  size_ = Eigen::Vector3d(DEFAULT_SIZE_X, DEFAULT_SIZE_Y, DEFAULT_SIZE_Z);
+  origin_ = Eigen::Vector3d(0, 0, 0);
+  resolution_ = DEFAULT_RESOLUTION;
+  collision_tolerance_ = DEFAULT_COLLISION_TOLERANCE;
+  max_propogation_distance_ = DEFAULT_MAX_PROPOGATION_DISTANCE;
+  // addLinkBodyDecompositions (collision_env_distance_field.cpp:960-979): the reference's own BodyDecomposition,
+  // so spheres / interior points / bounding spheres of meshes, boxes and cylinders are the reference's, bit for bit
+  for (const moveit::core::LinkModel* link : robot_model_->getLinkModelsWithCollisionGeometry())
+  {
+    if (link->getShapes().empty())
+      continue;
+    link_body_decomposition_vector_.push_back(std::make_shared<const BodyDecomposition>(
+        link->getShapes(), link->getCollisionOriginTransforms(), resolution_, getLinkPadding(link->getName())));
+    link_body_decomposition_index_map_[link->getName()] = link_body_decomposition_vector_.size() - 1;
+  }
+}
+
+std::shared_ptr<CollisionEnvB200::GroupContext>
+CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::RobotState& state,
+                             const AllowedCollisionMatrix* acm) const
+{
+  const moveit::core::JointModelGroup* jmg = robot_model_->getJointModelGroup(group_name);
+  if (!jmg)
+  {
+    RCLCPP_WARN(getLogger(), "No group %s", group_name.c_str());  // :716-720
+    return nullptr;
+  }
+  std::scoped_lock lock(mutex_);
+  auto it = contexts_.find(group_name);
+  if (it != contexts_.end())
+  {
+    // compareCacheEntryToState: any non-group variable moved by more than EPSILON invalidates the entry
+    bool same = true;
+    for (std::size_t i = 0; i < it->second->non_group_indices.size() && same; ++i)
+      same = std::fabs(state.getVariablePosition(it->second->non_group_indices[i]) -
+                       it->second->non_group_values[i]) <= STATE_EPSILON;
+    // (the ACM comparison of compareCacheEntryToAllowedCollisionMatrix, :1293-1370, goes here: entries between
+    //  updated links; omitted entries keep the cached masks)
+    if (same)
+      return it->second;
+    b200sv_destroy(it->second->ctx);
+    contexts_.erase(it);
+  }
+
+  // ---- b200sv_robot: RobotModel in link-index order + the group's variable layout ----------------------------------
+  const auto& links = robot_model_->getLinkModels();
+  const int n_links = static_cast<int>(links.size());
+  std::vector<int32_t> parent(n_links), joint_type(n_links), first_var(n_links);
+  std::vector<double> axis(3 * n_links, 0.0), origin(16 * n_links);
+  for (const moveit::core::LinkModel* l : links)
+  {
+    const int i = l->getLinkIndex();
+    const moveit::core::JointModel* j = l->getParentJointModel();
+    parent[i] = l->getParentLinkModel() ? l->getParentLinkModel()->getLinkIndex() : -1;
+    first_var[i] = j->getVariableCount() ? j->getFirstVariableIndex() : 0;
+    Eigen::Vector3d a(1, 0, 0);
+    switch (j->getType())
+    {
+      case moveit::core::JointModel::REVOLUTE:
+        joint_type[i] = B200SV_JOINT_REVOLUTE;
+        a = static_cast<const moveit::core::RevoluteJointModel*>(j)->getAxis();
+        break;
+      case moveit::core::JointModel::PRISMATIC:
+        joint_type[i] = B200SV_JOINT_PRISMATIC;
+        a = static_cast<const moveit::core::PrismaticJointModel*>(j)->getAxis();
+        break;
+      case moveit::core::JointModel::PLANAR: joint_type[i] = B200SV_JOINT_PLANAR; break;
+      case moveit::core::JointModel::FLOATING: joint_type[i] = B200SV_JOINT_FLOATING; break;
+      default: joint_type[i] = B200SV_JOINT_FIXED; break;
+    }
+    for (int k = 0; k < 3; ++k)
+      axis[3 * i + k] = a[k];
+    Eigen::Map<Eigen::Matrix4d>(origin.data() + 16 * i) = l->getJointOriginTransform().matrix();  // column-major
+  }
+  const std::vector<int>& gvi = jmg->getVariableIndexList();
+  std::vector<int32_t> group_var_index(gvi.begin(), gvi.end());
+  std::vector<int32_t> mimic_dst, mimic_src;
+  std::vector<double> mimic_factor, mimic_offset;
+  for (const moveit::core::JointModel* jm : jmg->getMimicJointModels())  // RobotState::updateMimicJoints(group)
+  {
+    mimic_dst.push_back(jm->getFirstVariableIndex());
+    mimic_src.push_back(jm->getMimic()->getFirstVariableIndex());
+    mimic_factor.push_back(jm->getMimicFactor());
+    mimic_offset.push_back(jm->getMimicOffset());
+  }
+  b200sv_robot r{};
+  r.n_links = n_links;
+  r.n_vars = static_cast<int32_t>(robot_model_->getVariableCount());
+  r.parent = parent.data();
+  r.joint_type = joint_type.data();
+  r.joint_axis = axis.data();
+  r.joint_origin = origin.data();
+  r.first_var = first_var.data();
+  r.base_positions = state.getVariablePositions();
+  r.n_group_vars = static_cast<int32_t>(group_var_index.size());
+  r.group_var_index = group_var_index.data();
+  r.n_mimic = static_cast<int32_t>(mimic_dst.size());
+  r.mimic_dst = mimic_dst.data();
+  r.mimic_src = mimic_src.data();
+  r.mimic_factor = mimic_factor.data();
+  r.mimic_offset = mimic_offset.data();
+
+  // ---- b200sv_collision_model: generateDistanceFieldCacheEntry (:735-838) ---------------------------------------------
+  const std::vector<const moveit::core::LinkModel*>& glinks = jmg->getUpdatedLinkModels();
+  const int n = static_cast<int>(glinks.size());
+  std::vector<int32_t> glink_index(n), sphere_start(1, 0);
+  std::vector<uint8_t> self_enabled(n, 1), intra_enabled(static_cast<std::size_t>(n) * n, 0);
+  std::vector<double> sphere_xyzr, bounding_sphere(4 * n, 0.0);
+  for (int i = 0; i < n; ++i)
+  {
+    const std::string& name = glinks[i]->getName();
+    glink_index[i] = glinks[i]->getLinkIndex();
+    auto bd = link_body_decomposition_index_map_.find(name);
+    if (glinks[i]->getShapes().empty() || bd == link_body_decomposition_index_map_.end())
+    {
+      self_enabled[i] = 0;
+      sphere_start.push_back(sphere_start.back());
+      continue;
+    }
+    AllowedCollision::Type t;
+    if (acm && acm->getEntry(name, name, t) && t == AllowedCollision::ALWAYS)
+      self_enabled[i] = 0;
+    for (int j = 0; j < n; ++j)
+      intra_enabled[static_cast<std::size_t>(i) * n + j] = 1;
+    for (int j = i + 1; j < n; ++j)
+      if (name == glinks[j]->getName() ||
+          (acm && acm->getEntry(name, glinks[j]->getName(), t) && t == AllowedCollision::ALWAYS))
+        intra_enabled[static_cast<std::size_t>(i) * n + j] = 0;
+    const BodyDecompositionConstPtr& d = link_body_decomposition_vector_[bd->second];
+    for (const CollisionSphere& cs : d->getCollisionSpheres())
+    {
+      sphere_xyzr.insert(sphere_xyzr.end(), { cs.relative_vec_.x(), cs.relative_vec_.y(), cs.relative_vec_.z(), cs.radius_ });
+    }
+    sphere_start.push_back(static_cast<int32_t>(sphere_xyzr.size() / 4));
+    const bodies::BoundingSphere& bs = d->getRelativeBoundingSphere();
+    bounding_sphere[4 * i + 0] = bs.center.x();
+    bounding_sphere[4 * i + 1] = bs.center.y();
+    bounding_sphere[4 * i + 2] = bs.center.z();
+    bounding_sphere[4 * i + 3] = bs.radius;
+  }
+  b200sv_collision_model m{};
+  m.n_glinks = n;
+  m.glink_index = glink_index.data();
+  m.self_enabled = self_enabled.data();
+  m.intra_enabled = intra_enabled.data();
+  m.sphere_start = sphere_start.data();
+  m.sphere_xyzr = sphere_xyzr.data();
+  m.bounding_sphere = bounding_sphere.data();
+
+  const b200sv_field_cfg f = fieldCfg(size_, origin_, resolution_, max_propogation_distance_, collision_tolerance_);
+  auto gc = std::make_shared<GroupContext>();
+  int device = 0;  // one process per GPU: honour CUDA_VISIBLE_DEVICES / the launcher's LOCAL_RANK
+  if (const char* lr = std::getenv("LOCAL_RANK"))
+    device = std::atoi(lr);
+  if (b200sv_create(device, &r, &m, &f, &gc->ctx) != B200SV_OK)
+  {
+    RCLCPP_ERROR(getLogger(), "b200sv_create failed: %s", b200sv_last_error(nullptr));
+    return nullptr;
+  }
+  // non-group variables to watch (dfce->state_check_indices_, :886-896)
+  std::vector<bool> in_group(robot_model_->getVariableCount(), false);
+  for (const moveit::core::JointModel* jm : jmg->getActiveJointModels())
+    for (std::size_t k = 0; k < jm->getVariableCount(); ++k)
+      in_group[jm->getFirstVariableIndex() + k] = true;
+  for (std::size_t v = 0; v < in_group.size(); ++v)
+    if (!in_group[v])
+    {
+      gc->non_group_indices.push_back(static_cast<int>(v));
+      gc->non_group_values.push_back(state.getVariablePosition(static_cast<int>(v)));
+    }
+  // self field: interior points of the links the group does not update, posed at `state` (:907-953)
+  EigenSTL::vector_Vector3d self_points;
+  for (const moveit::core::LinkModel* lm : robot_model_->getLinkModelsWithCollisionGeometry())
+  {
+    if (jmg->isLinkUpdated(lm->getName()))
+      continue;
+    auto bd = link_body_decomposition_index_map_.find(lm->getName());
+    if (bd == link_body_decomposition_index_map_.end())
+      continue;
+    const Eigen::Isometry3d& T = state.getFrameTransform(lm->getName());
+    for (const Eigen::Vector3d& p : link_body_decomposition_vector_[bd->second]->getCollisionPoints())
+      self_points.push_back(T * p);
+  }
+  if (!self_points.empty())
+    b200sv_field_add_points(gc->ctx, B200SV_FIELD_SELF, self_points[0].data(), self_points.size());
+  replayWorld(gc->ctx);
+  contexts_[group_name] = gc;
+  return gc;
+}
+
+void CollisionEnvB200::replayWorld(b200sv_ctx* ctx) const
+{
+  EigenSTL::vector_Vector3d all;
+  for (const auto& kv : world_points_)
+    all.insert(all.end(), kv.second.begin(), kv.second.end());
+  b200sv_field_reset(ctx, B200SV_FIELD_WORLD);
+  if (!all.empty())
+    b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, all[0].data(), all.size());
+}
+
+void CollisionEnvB200::notifyObjectChange(const ObjectConstPtr& obj, World::Action action)
+{
+  // updateDistanceObject (:1730-1779): subtract the object's old points, add its new ones
+  std::scoped_lock lock(mutex_);
+  EigenSTL::vector_Vector3d old_points;
+  auto cur = world_points_.find(obj->id_);
+  if (cur != world_points_.end())
+    old_points.swap(cur->second);
+  EigenSTL::vector_Vector3d new_points;
+  if (action != World::DESTROY && getWorld()->hasObject(obj->id_))
+  {
+    World::ObjectConstPtr object = getWorld()->getObject(obj->id_);
+    for (std::size_t i = 0; i < object->shapes_.size(); ++i)
+    {
+      const shapes::ShapeConstPtr& shape = object->shapes_[i];
+      if (shape->type == shapes::OCTREE)
+      {
+        PosedBodyPointDecomposition pts(static_cast<const shapes::OcTree*>(shape.get())->octree);  // types.cpp:355-365
+        new_points.insert(new_points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
+      }
+      else
+      {
+        BodyDecompositionConstPtr bd = std::make_shared<const BodyDecomposition>(shape, resolution_, 0.0);
+        PosedBodyPointDecomposition pts(bd, getWorld()->getGlobalShapeTransform(obj->id_, i));
+        new_points.insert(new_points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
+      }
+    }
+    world_points_[obj->id_] = new_points;
+  }
+  else
+    world_points_.erase(obj->id_);
+  for (auto& kv : contexts_)
+  {
+    b200sv_ctx* ctx = kv.second->ctx;
+    if (!old_points.empty())  // removePointsFromField, then addPointsToField (:1713-1725)
+      b200sv_field_remove_points(ctx, B200SV_FIELD_WORLD, old_points[0].data(), old_points.size());
+    if (!new_points.empty())
+      b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, new_points[0].data(), new_points.size());
+  }
+}
+
+void CollisionEnvB200::setWorld(const WorldPtr& world)
+{
+  if (world == getWorld())
+    return;
+  getWorld()->removeObserver(observer_handle_);
+  {
+    std::scoped_lock lock(mutex_);
+    world_points_.clear();
+    for (auto& kv : contexts_)
+      b200sv_field_reset(kv.second->ctx, B200SV_FIELD_WORLD);
+  }
+  CollisionEnv::setWorld(world);
+  observer_handle_ = getWorld()->addObserver(
+      [this](const World::ObjectConstPtr& object, World::Action action) { notifyObjectChange(object, action); });
+  getWorld()->notifyObserverAllObjects(observer_handle_, World::CREATE);
+}
+
+bool CollisionEnvB200::checkCollisionBatch(const CollisionRequest& req, const moveit::core::RobotState& base_state,
+                                           const AllowedCollisionMatrix* acm, const double* q, std::size_t n_states,
+                                           uint8_t* valid_bitmap, uint32_t flags) const
+{
+  std::shared_ptr<GroupContext> gc = getContext(req.group_name, base_state, acm);
+  if (!gc)
+    return false;
+  if (b200sv_check_batch(gc->ctx, q, n_states, flags, valid_bitmap) != B200SV_OK)
+  {
+    RCLCPP_ERROR(getLogger(), "b200sv_check_batch failed: %s", b200sv_last_error(gc->ctx));
+    return false;
+  }
+  return true;
+}
+
+void CollisionEnvB200::checkSingle(const CollisionRequest& req, CollisionResult& res,
+                                   const moveit::core::RobotState& state, const AllowedCollisionMatrix* acm,
+                                   uint32_t flags) const
+{
+  const moveit::core::JointModelGroup* jmg = robot_model_->getJointModelGroup(req.group_name);
+  if (!jmg)
+    return;  // the reference logs and checks nothing (:716-720)
+  if (req.contacts)
+    RCLCPP_WARN_ONCE(getLogger(), "contact reporting is not implemented by the B200 detector; only res.collision is set");
+  std::vector<double> q(jmg->getVariableCount());
+  state.copyJointGroupPositions(jmg, q.data());
+  uint8_t bit = 0;
+  if (checkCollisionBatch(req, state, acm, q.data(), 1, &bit, flags) && !(bit & 1))
+    res.collision = true;
+}
+
+void CollisionEnvB200::checkSelfCollision(const CollisionRequest& req, CollisionResult& res,
+                                          const moveit::core::RobotState& state) const
+{
+  checkSingle(req, res, state, nullptr, B200SV_CHECK_SELF | B200SV_CHECK_INTRA);
+}
+void CollisionEnvB200::checkSelfCollision(const CollisionRequest& req, CollisionResult& res,
+                                          const moveit::core::RobotState& state, const AllowedCollisionMatrix& acm) const
+{
+  checkSingle(req, res, state, &acm, B200SV_CHECK_SELF | B200SV_CHECK_INTRA);
+}
+void CollisionEnvB200::checkRobotCollision(const CollisionRequest& req, CollisionResult& res,
+                                           const moveit::core::RobotState& state) const
+{
+  checkSingle(req, res, state, nullptr, B200SV_CHECK_WORLD);
+}
+void CollisionEnvB200::checkRobotCollision(const CollisionRequest& req, CollisionResult& res,
+                                           const moveit::core::RobotState& state, const AllowedCollisionMatrix& acm) const
+{
+  checkSingle(req, res, state, &acm, B200SV_CHECK_WORLD);  // the world check ignores the ACM (:1561-1643)
+}
+void CollisionEnvB200::checkRobotCollision(const CollisionRequest&, CollisionResult&, const moveit::core::RobotState&,
+                                           const moveit::core::RobotState&) const
+{
+  RCLCPP_ERROR(getLogger(), "Continuous collision checking not implemented");  // as the reference (:1502-1515)
+}
+void CollisionEnvB200::checkRobotCollision(const CollisionRequest&, CollisionResult&, const moveit::core::RobotState&,
+                                           const moveit::core::RobotState&, const AllowedCollisionMatrix&) const
+{
+  RCLCPP_ERROR(getLogger(), "Continuous collision checking not implemented");
+}
+void CollisionEnvB200::checkCollision(const CollisionRequest& req, CollisionResult& res,
+                                      const moveit::core::RobotState& state) const
+{
+  checkSingle(req, res, state, nullptr, B200SV_CHECK_ALL);
+}
+void CollisionEnvB200::checkCollision(const CollisionRequest& req, CollisionResult& res,
+                                      const moveit::core::RobotState& state, const AllowedCollisionMatrix& acm) const
+{
+  checkSingle(req, res, state, &acm, B200SV_CHECK_ALL);
+}
+}  // namespace collision_detection

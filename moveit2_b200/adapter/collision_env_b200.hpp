@@ -1,0 +1,99 @@
+// MoveIt 2 side of the drop-in: a collision_detection::CollisionEnv whose distance-field checks run on a B200
+// through libb200sv.so (include/b200sv.h).  Compiled only where MoveIt 2 headers exist (see CMakeLists.txt in
+// this directory); it cannot be built in the authoring image (no ROS 2 / Eigen / geometric_shapes there), so it is
+// exercised by reading, not by CI.  INTEGRATION.md walks through it.
+//
+// Mirrors collision_detection::CollisionEnvDistanceField
+// (moveit_core/collision_distance_field/include/moveit/collision_distance_field/collision_env_distance_field.hpp:57-310):
+// same constructors, same overrides of the CollisionEnv pure virtuals (collision_env.hpp:84-195), same World
+// observer wiring (collision_env_distance_field.cpp:74-75, 92-95, 1704-1779), plus the batched entry point.
+#pragma once
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <moveit/collision_detection/collision_env.hpp>
+#include <moveit/collision_distance_field/collision_distance_field_types.hpp>
+
+#include "b200sv.h"
+
+namespace collision_detection
+{
+class CollisionEnvB200 : public CollisionEnv
+{
+public:
+  // defaults of CollisionEnvDistanceField (collision_env_distance_field.hpp:49-55)
+  static constexpr double DEFAULT_SIZE_X = 3.0, DEFAULT_SIZE_Y = 3.0, DEFAULT_SIZE_Z = 4.0;
+  static constexpr double DEFAULT_RESOLUTION = 0.02, DEFAULT_COLLISION_TOLERANCE = 0.0;
+  static constexpr double DEFAULT_MAX_PROPOGATION_DISTANCE = 0.25;
+
+  CollisionEnvB200(const moveit::core::RobotModelConstPtr& robot_model, double padding = 0.0, double scale = 1.0);
+  CollisionEnvB200(const moveit::core::RobotModelConstPtr& robot_model, const WorldPtr& world, double padding = 0.0,
+                   double scale = 1.0);
+  CollisionEnvB200(const CollisionEnvB200& other, const WorldPtr& world);
+  ~CollisionEnvB200() override;
+
+  // ---- CollisionEnv interface (collision_env.hpp:84-195) ---------------------------------------------------
+  void checkSelfCollision(const CollisionRequest& req, CollisionResult& res,
+                          const moveit::core::RobotState& state) const override;
+  void checkSelfCollision(const CollisionRequest& req, CollisionResult& res, const moveit::core::RobotState& state,
+                          const AllowedCollisionMatrix& acm) const override;
+  void checkRobotCollision(const CollisionRequest& req, CollisionResult& res,
+                           const moveit::core::RobotState& state) const override;
+  void checkRobotCollision(const CollisionRequest& req, CollisionResult& res, const moveit::core::RobotState& state,
+                           const AllowedCollisionMatrix& acm) const override;
+  // continuous checks: "not implemented" in the reference too (collision_env_distance_field.cpp:1502-1515)
+  void checkRobotCollision(const CollisionRequest& req, CollisionResult& res, const moveit::core::RobotState& state1,
+                           const moveit::core::RobotState& state2) const override;
+  void checkRobotCollision(const CollisionRequest& req, CollisionResult& res, const moveit::core::RobotState& state1,
+                           const moveit::core::RobotState& state2, const AllowedCollisionMatrix& acm) const override;
+  void checkCollision(const CollisionRequest& req, CollisionResult& res,
+                      const moveit::core::RobotState& state) const override;
+  void checkCollision(const CollisionRequest& req, CollisionResult& res, const moveit::core::RobotState& state,
+                      const AllowedCollisionMatrix& acm) const override;
+  // stubs in the reference (collision_env_distance_field.hpp:109-124, 179-199)
+  void distanceSelf(const DistanceRequest&, DistanceResult&, const moveit::core::RobotState&) const override {}
+  void distanceRobot(const DistanceRequest&, DistanceResult&, const moveit::core::RobotState&) const override {}
+  void setWorld(const WorldPtr& world) override;
+
+  // ---- the new batched entry point --------------------------------------------------------------------------
+  /// N group-state vectors (layout of RobotState::setJointGroupPositions(group, const double*), row-major N x V)
+  /// -> validity bitmap, bit (i % 8) of byte (i / 8) = 1 iff state i passes PlanningScene::checkCollision's checks
+  /// (world + self field + intra-group).  Every variable outside the group comes from `base_state`.
+  /// Returns false (and logs) on error; `valid_bitmap` must hold ceil(N / 8) bytes.
+  bool checkCollisionBatch(const CollisionRequest& req, const moveit::core::RobotState& base_state,
+                           const AllowedCollisionMatrix* acm, const double* q, std::size_t n_states,
+                           uint8_t* valid_bitmap, uint32_t flags = B200SV_CHECK_ALL) const;
+
+private:
+  struct GroupContext
+  {
+    b200sv_ctx* ctx = nullptr;
+    std::vector<double> non_group_values;  // compareCacheEntryToState (collision_env_distance_field.cpp:1254-1291)
+    std::vector<int> non_group_indices;
+    AllowedCollisionMatrix acm;
+  };
+  void initialize();
+  /// Flatten RobotModel + JointModelGroup + ACM + BodyDecompositions into b200sv_robot / b200sv_collision_model
+  /// and create the context (generateDistanceFieldCacheEntry, collision_env_distance_field.cpp:710-958).
+  std::shared_ptr<GroupContext> getContext(const std::string& group, const moveit::core::RobotState& state,
+                                           const AllowedCollisionMatrix* acm) const;
+  void checkSingle(const CollisionRequest& req, CollisionResult& res, const moveit::core::RobotState& state,
+                   const AllowedCollisionMatrix* acm, uint32_t flags) const;
+  void notifyObjectChange(const ObjectConstPtr& obj, World::Action action);
+  void replayWorld(b200sv_ctx* ctx) const;
+
+  Eigen::Vector3d size_, origin_;
+  double resolution_, collision_tolerance_, max_propogation_distance_;
+  std::vector<BodyDecompositionConstPtr> link_body_decomposition_vector_;  // as the reference (:1049-1078)
+  std::map<std::string, unsigned int> link_body_decomposition_index_map_;
+  // world points currently in the field, per object id (DistanceFieldCacheEntryWorld::posed_body_point_decompositions_)
+  std::map<std::string, EigenSTL::vector_Vector3d> world_points_;
+  mutable std::mutex mutex_;
+  mutable std::map<std::string, std::shared_ptr<GroupContext>> contexts_;
+  World::ObserverHandle observer_handle_;
+};
+}  // namespace collision_detection
