@@ -278,7 +278,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.fp64 else "f32", "data": "synthetic",
         "config": {"workload": "C2: Panda panda_arm (7 DoF, %d spheres), %d states per GPU per step, 500k-point clutter "
-                               "cloud, 2 m^3 field @ 1 cm (200^3 voxels, uint8 compact d^2), checks world+self+intra" % (S, n),
+                               "cloud, 2 m^3 field @ 1 cm (200^3 voxels; world+self uint8 d^2 interleaved, 16 MB), checks world+self+intra" % (S, n),
                    "l2": "flushed between timed steps (256 MiB write)", "fp32_pass_with_fp64_recheck": not args.fp64,
                    "valid_fraction": valid_frac, "rechecked_states_per_step": st["n_rechecked"],
                    "sharding": "states sharded contiguously (moveit2_b200/sharding.py), fields replicated, one NCCL "
