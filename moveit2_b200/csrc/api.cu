@@ -95,8 +95,10 @@ struct b200sv_ctx
   int tune_warps = 0, tune_blocks = 0;
   double fp32_eps = 4e-6;
   // streams / staging
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  static constexpr int kMaxChunks = 32;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_go = nullptr;
+  cudaEvent_t ev_chunk[kMaxChunks] = { nullptr };
   DevBuf<double> d_q;
   DevBuf<uint32_t> d_bitmap, d_list;
   DevBuf<double> d_points;
@@ -722,8 +724,13 @@ int finishCreate(b200sv_ctx* c, int device, b200sv_ctx** out)
   if ((rc = buildTables(c)) != B200SV_OK)
     return bail(rc);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess)
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(c, B200SV_ERR_CUDA, "stream/event creation failed"));
+  for (int i = 0; i < b200sv_ctx::kMaxChunks; ++i)
+    if (cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(c, B200SV_ERR_CUDA, "event creation failed"));
   if ((rc = uploadTables(c)) != B200SV_OK)
     return bail(rc);
   if ((rc = allocFields(c)) != B200SV_OK)
@@ -744,11 +751,12 @@ int addOrRemove(b200sv_ctx* c, int which, const double* d_xyz, size_t n, bool se
 }
 
 template <typename FT>
-int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_t* d_bitmap, cudaStream_t s)
+CheckArgs<FT> baseArgs(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_t* d_bitmap)
 {
   CheckArgs<FT> a{};
   a.q = d_q;
   a.n_states = n;
+  a.state_base = 0;
   a.field = c->d_combined;
   a.flags = flags & 7u;
   a.bitmap = d_bitmap;
@@ -757,24 +765,77 @@ int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_
   a.list_cap = (unsigned)std::min<size_t>(c->d_list.cap, 0xffffffffu);
   a.list = c->d_list.p;
   a.list_count = c->d_count;
-  if (flags & B200SV_CHECK_FP64)
-  {
-    a.model = c->d_blob_d;
-    a.model_bytes = (int)c->blob_d.size();
-    CU(c, launchCheck<FT>(a, true, false, c->sm_count * c->cfg_d.blocks_per_sm, c->cfg_d.warps * 32,
-                          c->cfg_d.smem, s));
-    return B200SV_OK;
-  }
-  CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), s));
-  a.model = c->d_blob_f;
-  a.model_bytes = (int)c->blob_f.size();
-  CU(c, launchCheck<FT>(a, false, false, c->sm_count * c->cfg_f.blocks_per_sm, c->cfg_f.warps * 32,
-                        c->cfg_f.smem, s));
-  // exact pass over the undecided states; the count stays on the device, so the launch is unconditional
+  return a;
+}
+
+// fast (FP32) or exact-for-all (FP64) pass over states [base, base + n) of the batch that starts at d_q0 / d_bitmap0
+template <typename FT>
+int launchMain(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t base, size_t n, uint32_t flags, cudaStream_t s)
+{
+  const size_t V = c->robot.group_var_index.size();
+  CheckArgs<FT> a = baseArgs<FT>(c, d_q0 + base * V, n, flags, d_bitmap0 + base / 32);
+  a.state_base = base;
+  const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
+  const b200sv_ctx::LaunchCfg& k = fp64 ? c->cfg_d : c->cfg_f;
+  a.model = fp64 ? c->d_blob_d : c->d_blob_f;
+  a.model_bytes = (int)(fp64 ? c->blob_d.size() : c->blob_f.size());
+  CU(c, launchCheck<FT>(a, fp64, false, c->sm_count * k.blocks_per_sm, k.warps * 32, k.smem, s));
+  return B200SV_OK;
+}
+
+// exact pass over the states the fast pass could not decide; the count stays on the device, so the launch is
+// unconditional
+template <typename FT>
+int launchRecheck(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t n_total, uint32_t flags, cudaStream_t s)
+{
+  CheckArgs<FT> a = baseArgs<FT>(c, d_q0, n_total, flags, d_bitmap0);
   a.model = c->d_blob_d;
   a.model_bytes = (int)c->blob_d.size();
   CU(c, launchCheck<FT>(a, true, true, c->sm_count * c->cfg_list.blocks_per_sm, c->cfg_list.warps * 32,
                         c->cfg_list.smem, s));
+  return B200SV_OK;
+}
+
+template <typename FT>
+int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_t* d_bitmap, cudaStream_t s)
+{
+  if (flags & B200SV_CHECK_FP64)
+    return launchMain<FT>(c, d_q, d_bitmap, 0, n, flags, s);
+  CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), s));
+  int rc = launchMain<FT>(c, d_q, d_bitmap, 0, n, flags, s);
+  if (rc != B200SV_OK)
+    return rc;
+  return launchRecheck<FT>(c, d_q, d_bitmap, n, flags, s);
+}
+
+// Host-buffer entry: the H2D copy of the states is cut into chunks on a second stream so the check of chunk i
+// overlaps the copy of chunk i + 1 (PCIe is the longer of the two for 56-byte states).
+template <typename FT>
+int runCheckHost(b200sv_ctx* c, const double* h_q, size_t n, uint32_t flags)
+{
+  const size_t V = c->robot.group_var_index.size();
+  size_t chunk = 131072;                               // states; a multiple of 32 so bitmap words do not straddle
+  while ((n + chunk - 1) / chunk > b200sv_ctx::kMaxChunks)
+    chunk *= 2;
+  const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
+  if (!fp64)
+    CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream));
+  CU(c, cudaEventRecord(c->ev_go, c->stream));
+  CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_go, 0));  // earlier work on the compute stream may still read d_q
+  int i = 0;
+  for (size_t base = 0; base < n; base += chunk, ++i)
+  {
+    const size_t m = std::min(chunk, n - base);
+    CU(c, cudaMemcpyAsync(c->d_q.p + base * V, h_q + base * V, m * V * sizeof(double), cudaMemcpyHostToDevice,
+                          c->copy_stream));
+    CU(c, cudaEventRecord(c->ev_chunk[i], c->copy_stream));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[i], 0));
+    int rc = launchMain<FT>(c, c->d_q.p, c->d_bitmap.p, base, m, flags, c->stream);
+    if (rc != B200SV_OK)
+      return rc;
+  }
+  if (!fp64)
+    return launchRecheck<FT>(c, c->d_q.p, c->d_bitmap.p, n, flags, c->stream);
   return B200SV_OK;
 }
 
@@ -905,6 +966,10 @@ void b200sv_destroy(b200sv_ctx* c)
   c->d_points.release();
   c->d_fk.release();
   c->d_i32.release();
+  for (int i = 0; i < b200sv_ctx::kMaxChunks; ++i)
+    if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+  if (c->ev_go) cudaEventDestroy(c->ev_go);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1241,9 +1306,13 @@ int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags,
   const size_t words = (n + 31) / 32;
   CU(c, c->d_q.ensure(n * V));
   CU(c, c->d_bitmap.ensure(words));
-  CU(c, cudaMemcpyAsync(c->d_q.p, q, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if ((flags & 7u) == 0)
+    return fail(c, B200SV_ERR_INVALID, "flags select no check");
+  if (n >= (1ull << 32))
+    return fail(c, B200SV_ERR_INVALID, "more than 2^32 - 1 states in one call");
+  CU(c, c->d_list.ensure(n));
   CU(c, cudaEventRecord(c->ev0, c->stream));
-  int rc = checkDevice(c, c->d_q.p, n, flags, c->d_bitmap.p, c->stream);
+  int rc = c->compact_bytes == 1 ? runCheckHost<uint8_t>(c, q, n, flags) : runCheckHost<uint16_t>(c, q, n, flags);
   if (rc != B200SV_OK)
     return rc;
   CU(c, cudaEventRecord(c->ev1, c->stream));

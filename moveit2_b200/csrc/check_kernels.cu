@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
         {
           const unsigned rank = __popc(flag_word & lt_mask);
           if (base + rank < a.list_cap)
-            a.flag_list[base + rank] = static_cast<uint32_t>(first + lane);
+            a.flag_list[base + rank] = static_cast<uint32_t>(a.state_base + first + lane);
         }
       }
     }

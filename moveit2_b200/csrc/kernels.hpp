@@ -14,6 +14,7 @@ struct CheckArgs
   int model_bytes;
   const double* q;       // [n_states * n_group_vars]
   unsigned long long n_states;
+  unsigned long long state_base;  // index of q[0] within the caller's batch (chunked launches); list entries are global
   const void* field;     // interleaved compact d^2: element [voxel] = world | self << (8 * sizeof(FT)),
                          // voxel = x*ny*nz + y*nz + z; one gather serves both checks
   uint32_t flags;
