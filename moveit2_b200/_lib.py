@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200sv.so")
+LIB_PATH = os.environ.get("B200SV_LIB", os.path.join(HERE, "libb200sv.so"))  # override: experimental variants
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_PARSE = 0, -1, -2, -3, -4, -5
 DEVICE_NONE = -1

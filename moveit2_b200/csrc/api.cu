@@ -519,8 +519,8 @@ int buildTables(b200sv_ctx* c)
   c->n_pairs = (int)pairs.size();
   if (c->n_pairs >= (1 << 26))
     return fail(c, B200SV_ERR_UNSUPPORTED, "too many enabled cluster pairs for the work-queue item format");
-  while (spheres.size() % 4)
-  {  // pad to a multiple of 4 (the field loop works in chunks of 4): thresholds 0 => never read, never collide
+  while (spheres.size() % B200SV_SPHERE_CHUNK)
+  {  // pad to a multiple of the chunk the field loop is unrolled by: thresholds 0 => never read, never collide
     SphereRec<double> S{};
     S.slot = spheres.empty() ? 0 : spheres.back().slot;
     spheres.push_back(S);

@@ -366,8 +366,6 @@ __device__ __forceinline__ void sphereChunk(const Smem<R>& m, const R* T, int k0
 #pragma unroll
   for (int u = 0; u < kU; ++u)
   {
-    idx[u] = -1;
-    tw[u] = ts[u] = 0;
     const int k = k0 + u;  // the table is padded to a multiple of kU with thr = 0 entries
     {
       const SphereRec<R> sp = m.spheres[k];  // uniform address: one broadcast read for the warp
@@ -402,22 +400,22 @@ __device__ __forceinline__ void sphereChunk(const Smem<R>& m, const R* T, int k0
       const bool inb = (static_cast<unsigned>(gx - 1) < static_cast<unsigned>(h.nx - 2)) &
                        (static_cast<unsigned>(gy - 1) < static_cast<unsigned>(h.ny - 2)) &
                        (static_cast<unsigned>(gz - 1) < static_cast<unsigned>(h.nz - 2));
-      if ((tw[u] | ts[u]) && live_lane)
-      {
-        if (r)
-          risky |= 1u << u;
-        else if (inb)
-          idx[u] = (gx * h.ny + gy) * h.nz + gz;  // VoxelGrid::ref (voxel_grid.hpp:425); < 2^31 voxels (host checks)
-      }
+      const bool want = ((tw[u] | ts[u]) != 0) & live_lane;
+      if (want & r)
+        risky |= 1u << u;
+      // VoxelGrid::ref (voxel_grid.hpp:425); < 2^31 voxels (host checks).  Lanes with nothing to read gather voxel 0
+      // with both thresholds 0: no branch around the load.
+      const bool ok = want & inb & !r;
+      idx[u] = ok ? (gx * h.ny + gy) * h.nz + gz : 0;
+      tw[u] = ok ? tw[u] : 0;
+      ts[u] = ok ? ts[u] : 0;
     }
   }
   int dw[kU], ds[kU];
 #pragma unroll
   for (int u = 0; u < kU; ++u)
   {
-    dw[u] = ds[u] = 0x7fffffff;
-    if (idx[u] >= 0)
-      gatherBoth<FT>(field, idx[u], dw[u], ds[u]);  // ONE gather: both fields of the voxel sit side by side
+    gatherBoth<FT>(field, idx[u], dw[u], ds[u]);  // ONE gather: both fields of the voxel sit side by side
   }
 #pragma unroll
   for (int u = 0; u < kU; ++u)
@@ -555,6 +553,7 @@ __device__ __forceinline__ void pairItem(const Smem<R>& m, const R* T, const Pai
   }
 }
 
+constexpr int kSphereChunk = B200SV_SPHERE_CHUNK;  // spheres per unrolled pass of the field loop (host pads the table)
 constexpr int kQueueCap = 512;  // (state, pair) work items per warp; flushed when fewer than 32 slots remain
 
 // Per-warp shared memory in bytes (16-byte aligned): transforms of 32 states | work queue | result words
@@ -599,8 +598,8 @@ __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
     // ---- phase 2: world / self field ----------------------------------------------------------------------------
     bool hit = false, amb = false;
     if (do_world | do_self)
-      for (int k0 = 0; k0 < h.n_spheres_padded; k0 += 4)
-        sphereChunk<R, FT, 4>(m, T, k0, do_world, do_self, field, active && !hit, hit, amb);
+      for (int k0 = 0; k0 < h.n_spheres_padded; k0 += kSphereChunk)
+        sphereChunk<R, FT, kSphereChunk>(m, T, k0, do_world, do_self, field, active && !hit, hit, amb);
     // ---- phase 3: intra-group sphere pairs ----------------------------------------------------------------------
     if (do_intra && h.n_pairs > 0 && __any_sync(kFull, active && !hit))
     {

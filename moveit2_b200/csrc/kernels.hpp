@@ -5,6 +5,10 @@
 #include <cstddef>
 #include <cstdint>
 
+#ifndef B200SV_SPHERE_CHUNK
+#define B200SV_SPHERE_CHUNK 4  // spheres per unrolled pass of the field loop; the sphere table is padded to a multiple
+#endif
+
 namespace b200sv
 {
 template <typename FT>
