@@ -16,6 +16,7 @@
 // intermediate and the outputs touch HBM.  Integer arithmetic throughout: results are exact.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "kernels.hpp"
@@ -85,42 +86,144 @@ __device__ __forceinline__ int zDistance(const uint32_t* row, int wz, int z, int
   return min(best, R + 1);
 }
 
-// One CTA per (x plane, y chunk).  Shared memory: occupancy words of rows [y0-R, y1+R), then their z distances.
-__global__ void __launch_bounds__(512) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
+// One CTA per (x plane, y chunk).  Shared memory: occupancy words of rows [y0-R, y1+R), then their z distances
+// (row stride nzp = nz rounded up to 4 so a thread can take 4 consecutive z with one 32-bit access).
+__global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
                                                   int chunk, int n_chunks)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   const int x = blockIdx.x / n_chunks, ci = blockIdx.x % n_chunks;
   const int y0 = ci * chunk, y1 = min(g.ny, y0 + chunk);
   const int ya = y0 - g.R, rows = (y1 - y0) + 2 * g.R;  // haloed row range [ya, ya + rows)
+  const int nzp = (g.nz + 3) & ~3;
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem);
-  uint8_t* gz = smem + static_cast<size_t>(rows) * g.wz * 4;
+  uint8_t* gz = smem + ((static_cast<size_t>(rows) * g.wz * 4 + 15) & ~static_cast<size_t>(15));
   for (int i = threadIdx.x; i < rows * g.wz; i += blockDim.x)
   {
     const int y = ya + i / g.wz;
     bits[i] = (y >= 0 && y < g.ny) ? occ[(static_cast<size_t>(x) * g.ny + y) * g.wz + (i % g.wz)] : 0u;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < rows * g.nz; i += blockDim.x)
+  for (int i = threadIdx.x; i < rows * nzp; i += blockDim.x)
   {
-    const int r = i / g.nz, z = i - r * g.nz;
-    gz[i] = static_cast<uint8_t>(zDistance(bits + r * g.wz, g.wz, z, g.R));
+    const int r = i / nzp, z = i - r * nzp;
+    gz[i] = z < g.nz ? static_cast<uint8_t>(zDistance(bits + r * g.wz, g.wz, z, g.R)) : static_cast<uint8_t>(g.R + 1);
   }
   __syncthreads();
   const int R = g.R, max_d2 = g.max_d2;
-  for (int i = threadIdx.x; i < (y1 - y0) * g.nz; i += blockDim.x)
+  const int nz4 = nzp >> 2;
+  const bool vec_out = (g.nz & 3) == 0;  // then every (x, y) row of `out` starts 8-byte aligned
+  for (int i = threadIdx.x; i < (y1 - y0) * nz4; i += blockDim.x)
   {
-    const int yy = i / g.nz, z = i - yy * g.nz;
+    const int yy = i / nz4, z = (i - yy * nz4) << 2;
     const int r = yy + R;  // row index inside the haloed block
-    int c = gz[r * g.nz + z];
-    int best = c * c;
-    for (int k = 1; k <= R && k * k < best; ++k)
+    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(gz + r * nzp + z);
+    int best[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
     {
-      const int a = gz[(r - k) * g.nz + z], b = gz[(r + k) * g.nz + z];
-      const int m = min(a, b);
-      best = min(best, m * m + k * k);
+      const int c = (c4 >> (8 * j)) & 0xff;
+      best[j] = c * c;
     }
-    out[(static_cast<size_t>(x) * g.ny + (y0 + yy)) * g.nz + z] = best <= max_d2 ? static_cast<uint16_t>(best) : kInf16;
+    for (int k = 1; k <= R; ++k)
+    {
+      const int k2 = k * k;
+      if (k2 >= max(max(best[0], best[1]), max(best[2], best[3])))
+        break;  // every further candidate is at least k^2 away
+      const uint32_t a4 = *reinterpret_cast<const uint32_t*>(gz + (r - k) * nzp + z);
+      const uint32_t b4 = *reinterpret_cast<const uint32_t*>(gz + (r + k) * nzp + z);
+      const uint32_t m4 = __vminu4(a4, b4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+      {
+        const int m = (m4 >> (8 * j)) & 0xff;
+        best[j] = min(best[j], m * m + k2);
+      }
+    }
+    uint16_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = best[j] <= max_d2 ? static_cast<uint16_t>(best[j]) : kInf16;
+    uint16_t* dst = out + (static_cast<size_t>(x) * g.ny + (y0 + yy)) * g.nz + z;
+    if (vec_out)
+      *reinterpret_cast<uint2*>(dst) = make_uint2(o[0] | (static_cast<uint32_t>(o[1]) << 16), o[2] | (static_cast<uint32_t>(o[3]) << 16));
+    else
+      for (int j = 0; j < 4 && z + j < g.nz; ++j)
+        dst[j] = o[j];
+  }
+}
+
+// x pass, 8 consecutive z per thread (16-byte loads / stores); requires nz % 8 == 0.  The compact field is
+// interleaved {world, self} per voxel: this field owns every other element, so its 8 elements are merged into the
+// 16 (uint8) or 32 (uint16) bytes they share with the other field (read-modify-write; fields are built one at a time
+// on one stream).
+template <typename FT>
+__global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* __restrict__ in, uint16_t* __restrict__ d2,
+                                                    FT* compact)
+{
+  const size_t plane8 = static_cast<size_t>(g.ny) * g.nz / 8;
+  const size_t total8 = plane8 * g.nx;
+  const int R = g.R, max_d2 = g.max_d2;
+  const uint4* in4 = reinterpret_cast<const uint4*>(in);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    const int x = static_cast<int>(i / plane8);
+    const uint4 c = in4[i];
+    int best[8];
+    const uint32_t cw[4] = { c.x, c.y, c.z, c.w };
+    int worst = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+      best[j] = min(static_cast<int>((cw[j >> 1] >> (16 * (j & 1))) & 0xffff), max_d2 + 1);  // kInf16 acts as +inf
+      worst = max(worst, best[j]);
+    }
+    for (int k = 1; k <= R && k * k < worst; ++k)
+    {
+      const int k2 = k * k;
+      uint4 a = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), b = a;
+      if (x - k >= 0)
+        a = in4[i - k * plane8];
+      if (x + k < g.nx)
+        b = in4[i + k * plane8];
+      const uint32_t mw[4] = { __vminu2(a.x, b.x), __vminu2(a.y, b.y), __vminu2(a.z, b.z), __vminu2(a.w, b.w) };
+      worst = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+      {
+        const int m = static_cast<int>((mw[j >> 1] >> (16 * (j & 1))) & 0xffff);
+        best[j] = min(best[j], m + k2);
+        worst = max(worst, best[j]);
+      }
+    }
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      ow[j] = static_cast<uint32_t>(min(best[2 * j], max_d2)) | (static_cast<uint32_t>(min(best[2 * j + 1], max_d2)) << 16);
+    reinterpret_cast<uint4*>(d2)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    // our 8 elements of the interleaved compact field: element 2 * (8 i + j) counted from `compact` (already offset)
+    if (sizeof(FT) == 1)
+    {
+      const bool second = (reinterpret_cast<uintptr_t>(compact) & 1u) != 0;  // offset by one element: the self half
+      uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(compact) - (second ? 1 : 0)) + i;
+      uint4 v = *p;
+      uint32_t vw[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+      {
+        const uint32_t val = static_cast<uint32_t>(min(min(best[j], max_d2), 255));
+        const int sh = 16 * (j & 1) + (second ? 8 : 0);
+        vw[j >> 1] = (vw[j >> 1] & ~(0xffu << sh)) | (val << sh);
+      }
+      *p = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+    }
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        compact[2 * (8 * i + j)] = static_cast<FT>(min(best[j], max_d2));
+    }
   }
 }
 
@@ -203,27 +306,40 @@ cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint3
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
                       int compact_bytes, int sm_count, cudaStream_t s)
 {
-  // y chunking so a haloed slab (occupancy words + z distances) fits the 227 KB of shared memory per CTA
-  const size_t per_row = static_cast<size_t>(g.wz) * 4 + g.nz;
-  const size_t budget = 200 * 1024;
-  long max_rows = static_cast<long>(budget / per_row);
-  int chunk = g.ny;
-  if (max_rows < g.ny + 2L * g.R)
-  {
-    chunk = static_cast<int>(max_rows - 2L * g.R);
-    if (chunk < 1)
-      return cudaErrorInvalidConfiguration;  // a single z row does not fit: grid too deep for this kernel
-  }
+  // y chunks: small enough for several CTAs per SM (a haloed slab = occupancy words + z distances in shared memory),
+  // large enough that the 2R halo rows stay a modest overhead
+  const int nzp = (g.nz + 3) & ~3;
+  const size_t per_row = static_cast<size_t>(g.wz) * 4 + nzp;
+  const long max_rows = static_cast<long>((200 * 1024) / per_row);
+  if (max_rows < 2L * g.R + 1)
+    return cudaErrorInvalidConfiguration;  // a haloed row block does not fit: grid too deep for this kernel
+  int chunk = std::min<long>(g.ny, std::max<long>(4L * g.R, 64));
+  chunk = static_cast<int>(std::min<long>(chunk, max_rows - 2L * g.R));
   const int n_chunks = (g.ny + chunk - 1) / chunk;
-  const size_t smem = static_cast<size_t>(chunk + 2 * g.R) * per_row;
-  cudaError_t e = cudaFuncSetAttribute(edtZYKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess)
-    return e;
-  edtZYKernel<<<g.nx * n_chunks, 512, smem, s>>>(g, occ, tmp, chunk, n_chunks);
-  e = cudaGetLastError();
+  const size_t smem = ((static_cast<size_t>(chunk + 2 * g.R) * g.wz * 4 + 15) & ~static_cast<size_t>(15)) +
+                      static_cast<size_t>(chunk + 2 * g.R) * nzp;
+  static size_t granted = 0;
+  if (smem > granted)
+  {
+    cudaError_t e = cudaFuncSetAttribute(edtZYKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess)
+      return e;
+    granted = smem;
+  }
+  edtZYKernel<<<g.nx * n_chunks, 256, smem, s>>>(g, occ, tmp, chunk, n_chunks);
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
   const size_t total = static_cast<size_t>(g.nx) * g.ny * g.nz;
+  if (g.nz % 8 == 0)
+  {
+    const int grid = gridFor(total / 8, 256, sm_count * 16);
+    if (compact_bytes == 1)
+      edtXKernelVec<uint8_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint8_t*>(compact));
+    else
+      edtXKernelVec<uint16_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint16_t*>(compact));
+    return cudaGetLastError();
+  }
   const int grid = gridFor(total, 256, sm_count * 32);
   if (compact_bytes == 1)
     edtXKernel<uint8_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint8_t*>(compact));
