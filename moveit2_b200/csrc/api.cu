@@ -72,8 +72,11 @@ struct b200sv_ctx
   int compact_bytes = 1;
   size_t n_voxels = 0;
   // device tables
-  std::vector<uint8_t> blob_f, blob_d;
-  uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr;
+  std::vector<uint8_t> blob_f, blob_d, blob_fast;
+  uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr, *d_blob_fast = nullptr;
+  bool fast_ok = false;      // the group's joints are all FIXED / REVOLUTE / PRISMATIC: fast_check.cu runs the FP32 pass
+  bool fast_disabled = false;  // B200SV_FAST=0: force the generic FP32 kernel (A/B measurements)
+  int state_stride_fast = 0;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
   double cluster_radius = 0.12;  // max tight-sphere radius of a sphere cluster (m)
   int state_stride_f = 0, state_stride_d = 0;  // shared-memory words per state (float / double blob)
@@ -91,7 +94,8 @@ struct b200sv_ctx
     int warps = 0, blocks_per_sm = 1;
     size_t smem = 0;
   };
-  LaunchCfg cfg_f, cfg_d, cfg_list;  // fast pass, exact pass over all states, exact pass over the recheck list
+  LaunchCfg cfg_f, cfg_d, cfg_list;  // generic FP32 pass, exact pass over all states, exact pass over the recheck list
+  LaunchCfg cfg_fast;                // fast_check.cu
   int tune_warps = 0, tune_blocks = 0;
   double fp32_eps = 4e-6;
   // streams / staging
@@ -243,6 +247,252 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
     memcpy(out.data() + h.off_pairs, pairs.data(), pairs.size() * sizeof(PairRec));
   if (!groups.empty())
     memcpy(out.data() + h.off_groups, groups.data(), groups.size() * sizeof(GroupRec));
+}
+
+// Tables of fast_check.cu (device_model.hpp, namespace fast), from the same links / spheres / clusters / pairs the
+// generic blobs are built from.  All constants are evaluated in double and narrowed once.
+bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, const std::vector<VarRec>& vars,
+                   const std::vector<SphereRec<double>>& spheres, int n_spheres, const std::vector<BsRec<double>>& bs,
+                   const std::vector<PairRec>& pairs, const std::vector<GroupRec>& groups, double margin, double pair_eps,
+                   double bs_eps, double tight_eps)
+{
+  c.blob_fast.clear();
+  for (const auto& L : links)
+    if (L.type != FIXED && L.type != REVOLUTE && L.type != PRISMATIC)
+      return false;
+  const int unroll = fastCheckUnroll();
+  const double oo = c.grid.oo;
+  const int nl = (int)links.size();
+  // which transforms go to shared memory: parents that are not the previous link, and links whose clusters are in pairs
+  std::vector<char> stored(nl, 0);
+  for (int l = 0; l < nl; ++l)
+    if (links[l].parent >= 0 && links[l].parent != l - 1)
+      stored[links[l].parent] = 1;
+  for (const auto& P : pairs)
+  {
+    stored[bs[P.a].slot] = 1;
+    stored[bs[P.b].slot] = 1;
+  }
+  std::vector<int> store_off(nl, -1);
+  int n_stored = 0;
+  for (int l = 0; l < nl; ++l)
+    if (stored[l])
+      store_off[l] = kLinkStrideWords * n_stored++;
+  c.state_stride_fast = std::max(1, n_stored) * kLinkStrideWords;
+  while (c.state_stride_fast % 32 != 4)
+    c.state_stride_fast += 4;
+  // spheres -> Hot entries, per link padded to the unroll
+  std::vector<fast::Hot> hot;
+  std::vector<float> rad;
+  std::vector<int> hot_of_sphere(n_spheres, -1);
+  std::vector<fast::Link> fl(nl);
+  const bool bytes8 = c.compact_bytes == 1;
+  for (int l = 0; l < nl; ++l)
+  {
+    const LinkRec<double>& L = links[l];
+    fast::Link F{};
+    F.type = L.type;
+    F.k = -1;
+    F.a = 0.0;
+    F.b = 0.0;
+    if (L.type != FIXED)
+    {
+      const VarRec& v = vars[L.var];
+      F.k = v.k;
+      F.a = v.a;
+      F.b = v.b;
+    }
+    const bool root = L.parent < 0;
+    F.parent_off = root ? fast::kParentRoot : (L.parent == l - 1 ? fast::kParentPrev : store_off[L.parent]);
+    F.store_off = store_off[l];
+    // O: origin rotation (rows), scaled into the voxel frame for a root
+    double O[9], ot[3];
+    for (int r = 0; r < 3; ++r)
+    {
+      for (int col = 0; col < 3; ++col)
+        O[3 * r + col] = L.has_origin ? L.o[4 * r + col] : (r == col ? 1.0 : 0.0);
+      ot[r] = L.has_origin ? L.o[4 * r + 3] : 0.0;
+    }
+    if (root)
+    {
+      for (int i = 0; i < 9; ++i)
+        O[i] *= oo;
+      for (int r = 0; r < 3; ++r)
+        ot[r] = (ot[r] - c.grid.om[r]) * oo;
+    }
+    const double x = L.ax[0], y = L.ax[1], z = L.ax[2];
+    const double K[9] = { 0, -z, y, z, 0, -x, -y, x, 0 };
+    double K2[9], OK[9], OK2[9];
+    for (int r = 0; r < 3; ++r)
+      for (int col = 0; col < 3; ++col)
+      {
+        double s2 = 0;
+        for (int k = 0; k < 3; ++k)
+          s2 += K[3 * r + k] * K[3 * k + col];
+        K2[3 * r + col] = s2;
+      }
+    for (int r = 0; r < 3; ++r)
+      for (int col = 0; col < 3; ++col)
+      {
+        double s1 = 0, s2 = 0;
+        for (int k = 0; k < 3; ++k)
+        {
+          s1 += O[3 * r + k] * K[3 * k + col];
+          s2 += O[3 * r + k] * K2[3 * k + col];
+        }
+        OK[3 * r + col] = s1;
+        OK2[3 * r + col] = s2;
+      }
+    for (int i = 0; i < 9; ++i)
+    {
+      F.a0[i] = (float)O[i];
+      F.a1[i] = 0.f;
+      F.a2[i] = 0.f;
+    }
+    for (int r = 0; r < 3; ++r)
+      F.ot[r] = (float)ot[r];
+    if (L.type == REVOLUTE)
+      for (int i = 0; i < 9; ++i)
+      {
+        F.a1[i] = (float)OK[i];
+        F.a2[i] = (float)OK2[i];
+      }
+    else if (L.type == PRISMATIC)
+      for (int r = 0; r < 3; ++r)
+        F.a1[r] = (float)(O[3 * r + 0] * x + O[3 * r + 1] * y + O[3 * r + 2] * z);
+    F.h0 = (int)hot.size();
+    for (int k = L.s0; k < L.s1 && k < n_spheres; ++k)
+    {
+      const SphereRec<double>& S = spheres[k];
+      fast::Hot H{};
+      H.x = (float)S.x;
+      H.y = (float)S.y;
+      H.z = (float)S.z;
+      const unsigned t = (unsigned)S.thr | ((unsigned)S.thr_self << 16);
+      H.t = bytes8 ? 0x01000100u - t : t;
+      hot_of_sphere[k] = (int)hot.size();
+      hot.push_back(H);
+      rad.push_back((float)(S.r * oo));
+    }
+    while (((int)hot.size() - F.h0) % unroll)
+    {  // padding: posed like a real sphere (at the link origin), thresholds 0: never collides
+      fast::Hot H{};
+      H.t = bytes8 ? 0x01000100u : 0u;
+      hot.push_back(H);
+      rad.push_back(0.f);
+    }
+    F.h1 = (int)hot.size();
+    fl[l] = F;
+  }
+  std::vector<fast::Cluster> cl(bs.size());
+  for (size_t i = 0; i < bs.size(); ++i)
+  {
+    fast::Cluster C{};
+    C.tx = (float)bs[i].tx;
+    C.ty = (float)bs[i].ty;
+    C.tz = (float)bs[i].tz;
+    C.tr_v = (float)(bs[i].tr * oo);
+    C.off = store_off[bs[i].slot];
+    C.h0 = hot_of_sphere[bs[i].s0];
+    C.h1 = C.h0 + (bs[i].s1 - bs[i].s0);
+    cl[i] = C;
+  }
+  std::vector<fast::Group> fg(groups.size());
+  std::vector<fast::Pair> fp(pairs.size());
+  std::vector<fast::Quirk> fq;
+  for (size_t g = 0; g < groups.size(); ++g)
+  {
+    const BsRec<double>& A = bs[groups[g].a];
+    fast::Group G{};
+    G.ax = (float)A.tx;
+    G.ay = (float)A.ty;
+    G.az = (float)A.tz;
+    G.a_off = store_off[A.slot];
+    G.p0 = groups[g].p0;
+    G.p1 = groups[g].p1;
+    G.a = groups[g].a;
+    fg[g] = G;
+  }
+  for (size_t p = 0; p < pairs.size(); ++p)
+  {
+    const BsRec<double>&A = bs[pairs[p].a], &B = bs[pairs[p].b];
+    fast::Pair P{};
+    P.bx = (float)B.tx;
+    P.by = (float)B.ty;
+    P.bz = (float)B.tz;
+    const double rt = (A.tr + B.tr + tight_eps) * oo;
+    P.rt2_v = (float)(rt * rt * (1.0 + 1e-6));  // narrowed upwards: the cull stays conservative
+    P.b_off = store_off[B.slot];
+    P.a = pairs[p].a;
+    P.b = pairs[p].b;
+    P.quirk = -1;
+    if (!pairs[p].quirk_free)
+    {
+      fast::Quirk Q{};
+      Q.ax = (float)A.x; Q.ay = (float)A.y; Q.az = (float)A.z;
+      Q.bx = (float)B.x; Q.by = (float)B.y; Q.bz = (float)B.z;
+      Q.lim_v2 = (float)((A.r + B.r) * oo * oo);
+      Q.eps_v2 = (float)(bs_eps * oo * oo);
+      Q.a_off = store_off[A.slot];
+      Q.b_off = store_off[B.slot];
+      P.quirk = (int)fq.size();
+      fq.push_back(Q);
+    }
+    fp[p] = P;
+  }
+  fast::Header h{};
+  h.n_links = nl;
+  h.n_groups = (int)fg.size();
+  h.n_pairs = (int)fp.size();
+  h.n_group_vars = (int)c.robot.group_var_index.size();
+  int off = align16(sizeof(fast::Header));
+  h.off_links = off;
+  off = align16(off + (int)(fl.size() * sizeof(fast::Link)));
+  h.off_hot = off;
+  off = align16(off + (int)(hot.size() * sizeof(fast::Hot)));
+  h.off_rad = off;
+  off = align16(off + (int)(rad.size() * sizeof(float)));
+  h.off_clusters = off;
+  off = align16(off + (int)(cl.size() * sizeof(fast::Cluster)));
+  h.off_groups = off;
+  off = align16(off + (int)(fg.size() * sizeof(fast::Group)));
+  h.off_pairs = off;
+  off = align16(off + (int)(fp.size() * sizeof(fast::Pair)));
+  h.off_quirks = off;
+  off = align16(off + (int)(fq.size() * sizeof(fast::Quirk)));
+  h.total_bytes = off;
+  h.state_stride = c.state_stride_fast;
+  h.nz = c.grid.nz;
+  h.nynz = c.grid.ny * c.grid.nz;
+  h.idx_bias = 0u - 0x4B400000u * (unsigned)(h.nynz + h.nz + 1);
+  const int n[3] = { c.grid.nx, c.grid.ny, c.grid.nz };
+  for (int k = 0; k < 3; ++k)
+  {
+    h.lo[k] = (float)(0.5 - margin);
+    h.hi[k] = (float)(n[k] - 0.5 - margin);
+  }
+  h.margin = (float)margin;
+  h.two_margin = (float)(2.0 * margin);
+  h.pair_eps_v = (float)(pair_eps * oo);
+  h.tight_eps_v = (float)(tight_eps * oo);
+  c.blob_fast.assign(off, 0);
+  uint8_t* o = c.blob_fast.data();
+  memcpy(o, &h, sizeof(h));
+  memcpy(o + h.off_links, fl.data(), fl.size() * sizeof(fast::Link));
+  if (!hot.empty())
+  {
+    memcpy(o + h.off_hot, hot.data(), hot.size() * sizeof(fast::Hot));
+    memcpy(o + h.off_rad, rad.data(), rad.size() * sizeof(float));
+  }
+  if (!cl.empty())
+    memcpy(o + h.off_clusters, cl.data(), cl.size() * sizeof(fast::Cluster));
+  if (!fg.empty())
+    memcpy(o + h.off_groups, fg.data(), fg.size() * sizeof(fast::Group));
+  if (!fp.empty())
+    memcpy(o + h.off_pairs, fp.data(), fp.size() * sizeof(fast::Pair));
+  if (!fq.empty())
+    memcpy(o + h.off_quirks, fq.data(), fq.size() * sizeof(fast::Quirk));
+  return true;
 }
 
 // column-major 4x4 -> row-major 3x4
@@ -526,6 +776,9 @@ int buildTables(b200sv_ctx* c)
     spheres.push_back(S);
   }
   c->compact_bytes = max_thr <= 255 ? 1 : 2;
+  if (getenv("B200SV_VERBOSE"))
+    fprintf(stderr, "b200sv: %d device links, %d spheres, %d clusters, %d cluster pairs in %d groups (%d link pairs)\n",
+            c->n_dev_links, c->n_spheres, c->n_bs, c->n_pairs, (int)groups.size(), n_link_pairs);
   // ---- FP32 uncertainty budget (see DESIGN.md "precision") -------------------------------------------------------------
   const double eps = c->fp32_eps;
   const int nmax = std::max(c->grid.nx, std::max(c->grid.ny, c->grid.nz));
@@ -535,18 +788,20 @@ int buildTables(b200sv_ctx* c)
   const double tight_eps = 4.0 * eps + 1e-6;
   buildBlob<float>(*c, links, vars, spheres, bs, pairs, groups, margin, pair_eps, bs_eps, tight_eps, c->blob_f);
   buildBlob<double>(*c, links, vars, spheres, bs, pairs, groups, 0.0, 0.0, 0.0, 1e-9, c->blob_d);
+  c->fast_ok = buildFastBlob(*c, links, vars, spheres, c->n_spheres, bs, pairs, groups, margin, pair_eps, bs_eps, tight_eps);
   return B200SV_OK;
 }
 
 // Pick (warps per CTA, CTAs per SM) for the thread-per-state check kernel: as many resident warps as shared memory
 // (32 states of link transforms per warp) and registers allow.  Limits: 227 KB of shared memory per CTA / 228 KB per
 // SM with 1 KB reserved per CTA, 64 K registers per SM, 512 threads per CTA (__launch_bounds__).
-b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, int blob_bytes)
+b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, int blob_bytes, bool fast = false)
 {
   b200sv_ctx::LaunchCfg best;
-  const int regs = (checkKernelRegs(fp64, from_list, c->compact_bytes) + 7) & ~7;
+  const int regs = ((fast ? fastCheckKernelRegs(c->compact_bytes) : checkKernelRegs(fp64, from_list, c->compact_bytes)) + 7) & ~7;
   const int reg_warps = 65536 / (regs * 32);
-  const long pw = checkPerWarpBytes(fp64, fp64 ? c->state_stride_d : c->state_stride_f);
+  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast) :
+                         checkPerWarpBytes(fp64, fp64 ? c->state_stride_d : c->state_stride_f);
   for (int b = 1; b <= 4; ++b)
   {
     if (c->tune_blocks > 0 && b != c->tune_blocks)
@@ -573,7 +828,18 @@ int uploadTables(b200sv_ctx* c)
     cudaFree(c->d_blob_f);
   if (c->d_blob_d)
     cudaFree(c->d_blob_d);
-  c->d_blob_f = c->d_blob_d = nullptr;
+  if (c->d_blob_fast)
+    cudaFree(c->d_blob_fast);
+  c->d_blob_f = c->d_blob_d = c->d_blob_fast = nullptr;
+  c->cfg_fast = b200sv_ctx::LaunchCfg();
+  if (c->fast_ok)
+  {
+    CU(c, cudaMalloc(&c->d_blob_fast, c->blob_fast.size()));
+    CU(c, cudaMemcpy(c->d_blob_fast, c->blob_fast.data(), c->blob_fast.size(), cudaMemcpyHostToDevice));
+    c->cfg_fast = chooseCfg(c, false, false, (int)c->blob_fast.size(), true);
+    if (c->cfg_fast.warps < 1)
+      c->fast_ok = false;  // the generic kernel's limits decide below whether the robot fits at all
+  }
   CU(c, cudaMalloc(&c->d_blob_f, c->blob_f.size()));
   CU(c, cudaMalloc(&c->d_blob_d, c->blob_d.size()));
   CU(c, cudaMemcpy(c->d_blob_f, c->blob_f.data(), c->blob_f.size(), cudaMemcpyHostToDevice));
@@ -717,6 +983,8 @@ int finishCreate(b200sv_ctx* c, int device, b200sv_ctx** out)
     c->cluster_radius = atof(e);
   if (const char* e = getenv("B200SV_BLOCKS"))
     c->tune_blocks = atoi(e);
+  if (const char* e = getenv("B200SV_FAST"))
+    c->fast_disabled = atoi(e) == 0;
   if ((rc = validateModel(c)) != B200SV_OK)
     return bail(rc);
   if ((rc = initGrid(c)) != B200SV_OK)
@@ -776,6 +1044,14 @@ int launchMain(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t ba
   CheckArgs<FT> a = baseArgs<FT>(c, d_q0 + base * V, n, flags, d_bitmap0 + base / 32);
   a.state_base = base;
   const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
+  if (!fp64 && c->fast_ok && !c->fast_disabled)
+  {
+    const b200sv_ctx::LaunchCfg& k = c->cfg_fast;
+    a.model = c->d_blob_fast;
+    a.model_bytes = (int)c->blob_fast.size();
+    CU(c, launchFastCheck<FT>(a, c->sm_count * k.blocks_per_sm, k.warps * 32, k.smem, s));
+    return B200SV_OK;
+  }
   const b200sv_ctx::LaunchCfg& k = fp64 ? c->cfg_d : c->cfg_f;
   a.model = fp64 ? c->d_blob_d : c->d_blob_f;
   a.model_bytes = (int)(fp64 ? c->blob_d.size() : c->blob_f.size());
@@ -956,6 +1232,7 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->d_tmp) cudaFree(c->d_tmp);
   if (c->d_blob_f) cudaFree(c->d_blob_f);
   if (c->d_blob_d) cudaFree(c->d_blob_d);
+  if (c->d_blob_fast) cudaFree(c->d_blob_fast);
   if (c->d_link_slot) cudaFree(c->d_link_slot);
   if (c->d_const_T) cudaFree(c->d_const_T);
   if (c->d_count) cudaFree(c->d_count);

@@ -87,3 +87,91 @@ struct ModelHeader
 // quarter-warp then touch 8 distinct 16-byte bank groups (conflict-free 128-bit accesses).
 constexpr int kLinkStrideWords = 12;
 }  // namespace b200sv
+
+// ======================================================================================================================
+// Tables of the FAST (FP32) pass, fast_check.cu.  One blob, copied to shared memory by every CTA.  The fast pass works
+// in VOXEL coordinates: the host folds f = (p - origin_minus) * oo_resolution (VoxelGrid::getCellFromLocation,
+// voxel_grid.hpp:522) into every root transform, so a posed sphere centre IS its (fractional) cell coordinate and all
+// lengths below carry the suffix _v (cells).  Joint types: FIXED, REVOLUTE, PRISMATIC (a group with a planar or
+// floating joint runs the generic checkKernel<float> instead).
+namespace b200sv
+{
+namespace fast
+{
+constexpr int kParentRoot = -1;  // the link's transform is [M | m] itself (constants already in the voxel frame)
+constexpr int kParentPrev = -2;  // parent = the previous link of the table: its transform is still in registers
+
+// T_link = T_parent * [M | m]
+//   REVOLUTE   M = a0 + sin(q) * a1 + (1 - cos(q)) * a2,  m = ot        (a0 = O, a1 = O*K, a2 = O*K^2: Rodrigues)
+//   PRISMATIC  M = a0,                                     m = ot + q * a1[0..2]   (a1[0..2] = O * axis)
+//   FIXED      M = a0,                                     m = ot
+// O = rotation of the joint origin, K = cross-product matrix of the axis, q = a * group_q[k] + b evaluated in double
+// (setJointGroupPositions + updateMimicJoints) and narrowed.
+struct alignas(16) Link
+{
+  int type, k;     // JointType; index into the group state (k < 0: the joint value is the constant b)
+  int parent_off;  // kParentRoot, kParentPrev or the word offset of the parent's transform in the state's block
+  int store_off;   // word offset this link's transform is stored at, -1: nobody reads it back
+  int h0, h1;      // Hot range of the link's spheres, padded to a multiple of the field loop's unroll
+  int pad0, pad1;
+  double a, b;
+  float ot[3], pad2;
+  float a0[9], a1[9], a2[9], pad3;
+};
+static_assert(sizeof(Link) == 176, "fast::Link layout");
+
+// One collision sphere of the field loop, ONE 16-byte broadcast read.
+struct alignas(16) Hot
+{
+  float x, y, z;  // CollisionSphere::relative_vec_ (link frame, metres)
+  unsigned t;     // 8-bit fields: 0x01000100 - (thr | thr_self << 16); 16-bit fields: thr | thr_self << 16.
+                  // thr = 0 never collides (padding, or the self check disabled for the link)
+};
+
+struct alignas(16) Cluster
+{
+  float tx, ty, tz;  // tight-sphere centre (link frame, metres)
+  float tr_v;        // tight radius (cells)
+  int off;           // word offset of the link's transform
+  int h0, h1;        // Hot range of the cluster's spheres (no padding inside)
+  int pad;
+};
+
+struct alignas(16) Group  // pairs [p0, p1) share cluster a
+{
+  float ax, ay, az, pad0;
+  int a_off, p0, p1, a;
+};
+
+struct alignas(16) Pair
+{
+  float bx, by, bz;  // tight centre of cluster b (link frame)
+  float rt2_v;       // (tr_a + tr_b + tight_eps)^2 in cells^2
+  int b_off, a, b;   // transform offset of b's link; Cluster indices
+  int quirk;         // -1: the reference's link-level cull provably passes whenever the tight spheres are this close;
+                     // else index of the Quirk record to evaluate
+};
+
+// doBoundingSpheresIntersect on the LINKS' bounding spheres (types.cpp:408-418), quirk kept: squared centre distance
+// (m^2) against the plain radius sum (m).  In cells: |Ca - Cb|_v^2 < (Ra + Rb) * oo^2.
+struct alignas(16) Quirk
+{
+  float ax, ay, az, lim_v2;
+  float bx, by, bz, eps_v2;
+  int a_off, b_off, pad0, pad1;
+};
+
+struct alignas(16) Header
+{
+  int n_links, n_groups, n_pairs, n_group_vars;
+  int off_links, off_hot, off_rad, off_clusters;
+  int off_groups, off_pairs, off_quirks, total_bytes;
+  int state_stride;  // words of shared memory per state
+  int nz, nynz;
+  unsigned idx_bias;  // -(0x4B400000 * (nynz + nz + 1)) mod 2^32: undoes the float-magic bias of the three cell indices
+  float lo[3], margin;      // clamp of (centre - margin) to [0.5 - margin, n - 0.5 - margin]: a centre outside the
+  float hi[3], two_margin;  // field lands in the 1-cell border shell, where nothing collides
+  float pair_eps_v, tight_eps_v, pad0, pad1;
+};
+}  // namespace fast
+}  // namespace b200sv

@@ -153,6 +153,15 @@ __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __
   }
 }
 
+// voxel i = (x * ny + y) * nz + z lies in the outermost cell layer of the grid
+__device__ __forceinline__ bool onShell(const GridDev& g, size_t i)
+{
+  const size_t row = i / g.nz;
+  const int z = static_cast<int>(i - row * g.nz);
+  const int x = static_cast<int>(row / g.ny), y = static_cast<int>(row - static_cast<size_t>(x) * g.ny);
+  return x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1 || z == 0 || z == g.nz - 1;
+}
+
 // x pass, 8 consecutive z per thread (16-byte loads / stores); requires nz % 8 == 0.  The compact field is
 // interleaved {world, self} per voxel: this field owns every other element, so its 8 elements are merged into the
 // 16 (uint8) or 32 (uint16) bytes they share with the other field (read-modify-write; fields are built one at a time
@@ -202,7 +211,19 @@ __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* 
     for (int j = 0; j < 4; ++j)
       ow[j] = static_cast<uint32_t>(min(best[2 * j], max_d2)) | (static_cast<uint32_t>(min(best[2 * j + 1], max_d2)) << 16);
     reinterpret_cast<uint4*>(d2)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    // our 8 elements of the interleaved compact field: element 2 * (8 i + j) counted from `compact` (already offset)
+    // our 8 elements of the interleaved compact field: element 2 * (8 i + j) counted from `compact` (already offset).
+    // The 1-cell border shell of the COMPACT field is kept at "free": DistanceField::getDistanceGradient
+    // (distance_field.cpp:82) answers max_distance for those cells, and the fast check kernel clamps to them.
+    {
+      const int nz8 = g.nz / 8;
+      const int rem = static_cast<int>(i - static_cast<size_t>(x) * plane8);
+      const int y = rem / nz8, z0 = (rem - y * nz8) * 8;
+      const bool shell_xy = x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (shell_xy || z0 + j == 0 || z0 + j == g.nz - 1)
+          best[j] = max_d2;
+    }
     if (sizeof(FT) == 1)
     {
       const bool second = (reinterpret_cast<uintptr_t>(compact) & 1u) != 0;  // offset by one element: the self half
@@ -251,7 +272,10 @@ __global__ void __launch_bounds__(256) edtXKernel(GridDev g, const uint16_t* __r
     }
     best = min(best, max_d2);
     d2[i] = static_cast<uint16_t>(best);
-    // interleaved compact field: element 2 * i + which (the caller passes compact already offset by `which`)
+    // interleaved compact field: element 2 * i + which (the caller passes compact already offset by `which`); its
+    // 1-cell border shell is kept at "free" (see edtXKernelVec)
+    if (onShell(g, i))
+      best = max_d2;
     compact[2 * i] = static_cast<FT>(sizeof(FT) == 1 ? min(best, 255) : best);
   }
 }
@@ -276,7 +300,8 @@ __global__ void injectKernel(GridDev g, const int32_t* __restrict__ in, uint32_t
   {
     const int v = min(max(in[i], 0), g.max_d2);
     d2[i] = static_cast<uint16_t>(v);
-    compact[2 * i] = static_cast<FT>(sizeof(FT) == 1 ? min(v, 255) : v);
+    const int vc = onShell(g, i) ? g.max_d2 : v;
+    compact[2 * i] = static_cast<FT>(sizeof(FT) == 1 ? min(vc, 255) : vc);
     if (v == 0)
     {
       const int z = static_cast<int>(i % g.nz);

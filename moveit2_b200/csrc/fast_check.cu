@@ -1,0 +1,507 @@
+// K1 + K2, FAST pass: batched forward kinematics fused with the sphere-decomposition checks, FP32, thread-per-state.
+//
+// Same reference functions as check_kernels.cu (RobotState::updateLinkTransforms, PosedBodySphereDecomposition::
+// updatePose, getCollisionSphereCollision, getEnvironmentCollisions / getSelfCollisions / getIntraGroupCollisions:
+// robot_state/src/robot_state.cpp:793-848, collision_distance_field/src/collision_distance_field_types.cpp:211-236,
+// 388-418, collision_env_distance_field.cpp:274-353, 430-642, 1561-1643), restructured around the instruction
+// count per state instead of around the reference's data structures:
+//
+//   * Everything is computed in VOXEL coordinates: the host folds VoxelGrid::getCellFromLocation's affine map
+//     (voxel_grid.hpp:522) into the root transforms, so a posed sphere centre is its fractional cell coordinate and no
+//     per-sphere conversion is left.
+//   * A joint's transform is ONE affine combination of host-built constants (origin * Rodrigues terms) followed by
+//     ONE 3x4 product with the parent, and the link loop keeps the current transform in registers: the spheres of a
+//     link are posed from registers right after its FK step (no shared-memory round trip, no second sphere phase).
+//   * The cell index comes from a round-down float add (no F2I), both cells `margin` either side of the centre
+//     are indexed, and a sphere whose two indices differ (its FP32 centre is within `margin` of a cell face) is parked
+//     in a one-entry per-lane slot and resolved by reading BOTH cells; nothing else branches.  Centres are clamped to
+//     the field's 1-cell border shell, which the field builders keep at "free": DistanceField::getDistanceGradient
+//     (distance_field.cpp:82) reports every such cell, and everything outside, as max_distance.
+//   * Gathers are software pipelined: the loads of one sphere chunk are consumed while the next chunk is posed.
+//   * Link transforms also go to shared memory (3x4 rows of 16 bytes) for the intra-group pair phase, which is the
+//     queue-compacted three-level test of check_kernels.cu in voxel units.
+//
+// A state whose boolean could depend on FP32 rounding is appended to the recheck list; the exact pass
+// (checkKernel<double, ., true>, the reference's arithmetic operation by operation) decides it.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_model.hpp"
+#include "kernels.hpp"
+
+namespace b200sv
+{
+namespace
+{
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kU = B200SV_FAST_UNROLL;  // spheres per unrolled chunk of the field loop (Hot ranges are padded to it)
+constexpr int kQueueCap = 256;          // (state, pair) work items per warp; flushed when fewer than 32 slots remain
+constexpr float kMagic = 12582912.f;    // 1.5 * 2^23: x + kMagic rounded down has floor(x) in its low mantissa bits
+constexpr unsigned kGuard = 0x01000100u;
+
+struct FModel
+{
+  const fast::Header* h;
+  const fast::Link* links;
+  const fast::Hot* hot;
+  const float* rad;
+  const fast::Cluster* cl;
+  const fast::Group* groups;
+  const fast::Pair* pairs;
+  const fast::Quirk* quirks;
+};
+
+// Field element = { world, self } of one voxel.  8-bit fields: both compares in one add (per 16-bit lane
+// 0x100 - thr + d has bit 8 set iff d >= thr).  16-bit fields: plain compares.
+template <typename FT> struct Cmp;
+template <> struct Cmp<uint8_t>
+{
+  using Elem = uint16_t;
+  static constexpr unsigned kNever = kGuard;
+  static __device__ __forceinline__ unsigned mask(unsigned t, unsigned fmask) { return (t & fmask) | (kGuard & ~fmask); }
+  static __device__ __forceinline__ bool hit(unsigned v, unsigned t)
+  {
+    const unsigned z = __byte_perm(v, 0u, 0x3120) + t;
+    return (z & kGuard) != kGuard;
+  }
+};
+template <> struct Cmp<uint16_t>
+{
+  using Elem = uint32_t;
+  static constexpr unsigned kNever = 0u;
+  static __device__ __forceinline__ unsigned mask(unsigned t, unsigned fmask) { return t & fmask; }
+  static __device__ __forceinline__ bool hit(unsigned v, unsigned t)
+  {
+    return ((v & 0xffffu) < (t & 0xffffu)) | ((v >> 16) < (t >> 16));
+  }
+};
+
+__device__ __forceinline__ void load12(const float* p, float* o)
+{
+  const float4* v = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    const float4 t = v[i];
+    o[4 * i + 0] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void store12(float* p, const float* o)
+{
+  float4* v = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    v[i] = make_float4(o[4 * i + 0], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+}
+__device__ __forceinline__ void pose(const float* T, float x, float y, float z, float& ox, float& oy, float& oz)
+{
+  ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+  oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+  oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+}
+
+__device__ __forceinline__ FModel loadFast(const uint8_t* __restrict__ g_model, int model_bytes, uint8_t* smem)
+{
+  const int4* src = reinterpret_cast<const int4*>(g_model);
+  int4* dst = reinterpret_cast<int4*>(smem);
+  for (int i = threadIdx.x; i < model_bytes / 16; i += blockDim.x)
+    dst[i] = src[i];
+  __syncthreads();
+  FModel m;
+  m.h = reinterpret_cast<const fast::Header*>(smem);
+  m.links = reinterpret_cast<const fast::Link*>(smem + m.h->off_links);
+  m.hot = reinterpret_cast<const fast::Hot*>(smem + m.h->off_hot);
+  m.rad = reinterpret_cast<const float*>(smem + m.h->off_rad);
+  m.cl = reinterpret_cast<const fast::Cluster*>(smem + m.h->off_clusters);
+  m.groups = reinterpret_cast<const fast::Group*>(smem + m.h->off_groups);
+  m.pairs = reinterpret_cast<const fast::Pair*>(smem + m.h->off_pairs);
+  m.quirks = reinterpret_cast<const fast::Quirk*>(smem + m.h->off_quirks);
+  return m;
+}
+
+// One (state, cluster pair) item that survived the level-1 cull: [the reference's link-level cull when the host could
+// not prove it away,] spheres of either cluster against the other cluster's tight sphere, survivors sphere against
+// sphere (getIntraGroupCollisions, collision_env_distance_field.cpp:571-638).  T: the state's transform block.
+__device__ __forceinline__ void pairItem(const FModel& m, const float* T, unsigned p, bool& hit, bool& amb)
+{
+  const fast::Header& h = *m.h;
+  const fast::Pair P = m.pairs[p];
+  bool cert = true;
+  if (P.quirk >= 0)
+  {
+    const fast::Quirk Q = m.quirks[P.quirk];
+    float Ta[12], Tb[12], ax, ay, az, bx, by, bz;
+    load12(T + Q.a_off, Ta);
+    load12(T + Q.b_off, Tb);
+    pose(Ta, Q.ax, Q.ay, Q.az, ax, ay, az);
+    pose(Tb, Q.bx, Q.by, Q.bz, bx, by, bz);
+    const float ex = ax - bx, ey = ay - by, ez = az - bz;
+    const float d2 = ex * ex + ey * ey + ez * ez;
+    if (!(d2 < Q.lim_v2 + Q.eps_v2))
+      return;
+    cert = d2 < Q.lim_v2 - Q.eps_v2;
+  }
+  const fast::Cluster A = m.cl[P.a], B = m.cl[P.b];
+  const int na = A.h1 - A.h0, nb = B.h1 - B.h0;
+  float Ta[12], Tb[12];
+  load12(T + A.off, Ta);
+  load12(T + B.off, Tb);
+  unsigned long long ma = ~0ull >> (64 - na), mb = ~0ull >> (64 - nb);
+  if (na * nb > 4)
+  {
+    float tax, tay, taz, tbx, tby, tbz;
+    pose(Ta, A.tx, A.ty, A.tz, tax, tay, taz);
+    pose(Tb, B.tx, B.ty, B.tz, tbx, tby, tbz);
+    ma = 0ull;
+    for (int i = 0; i < na; ++i)
+    {
+      const fast::Hot sp = m.hot[A.h0 + i];
+      float x, y, z;
+      pose(Ta, sp.x, sp.y, sp.z, x, y, z);
+      const float gx = x - tbx, gy = y - tby, gz = z - tbz;
+      const float lim = m.rad[A.h0 + i] + B.tr_v + h.tight_eps_v;
+      if ((gx * gx + gy * gy + gz * gz) < lim * lim)
+        ma |= 1ull << i;
+    }
+    if (ma == 0ull)
+      return;
+    mb = 0ull;
+    for (int j = 0; j < nb; ++j)
+    {
+      const fast::Hot sp = m.hot[B.h0 + j];
+      float x, y, z;
+      pose(Tb, sp.x, sp.y, sp.z, x, y, z);
+      const float gx = x - tax, gy = y - tay, gz = z - taz;
+      const float lim = m.rad[B.h0 + j] + A.tr_v + h.tight_eps_v;
+      if ((gx * gx + gy * gy + gz * gz) < lim * lim)
+        mb |= 1ull << j;
+    }
+    if (mb == 0ull)
+      return;
+  }
+  while (ma)
+  {
+    const int i = __ffsll(static_cast<long long>(ma)) - 1;
+    ma &= ma - 1;
+    const fast::Hot sa = m.hot[A.h0 + i];
+    const float ra = m.rad[A.h0 + i];
+    float axp, ayp, azp;
+    pose(Ta, sa.x, sa.y, sa.z, axp, ayp, azp);
+    unsigned long long mj = mb;
+    while (mj)
+    {
+      const int j = __ffsll(static_cast<long long>(mj)) - 1;
+      mj &= mj - 1;
+      const fast::Hot sb = m.hot[B.h0 + j];
+      float bxp, byp, bzp;
+      pose(Tb, sb.x, sb.y, sb.z, bxp, byp, bzp);
+      const float gx = axp - bxp, gy = ayp - byp, gz = azp - bzp;
+      const float dd = gx * gx + gy * gy + gz * gz;
+      const float rsum = ra + m.rad[B.h0 + j];
+      // gradient.norm() < r1 + r2 (collision_env_distance_field.cpp:577-583) with the FP32 uncertainty either side
+      const float lo = rsum - h.pair_eps_v, hi = rsum + h.pair_eps_v;
+      const bool c_cert = (lo > 0.f) && (dd < lo * lo);
+      const bool c_maybe = dd < hi * hi;
+      hit |= (cert && c_cert);
+      amb |= (c_maybe && !(cert && c_cert));
+    }
+  }
+}
+
+__device__ __host__ inline int fastPerWarpBytes(int state_stride) { return 32 * state_stride * 4 + kQueueCap * 4 + 16; }
+
+// Dynamic shared memory: [fast blob][per warp: transforms of 32 states | work queue | hit word, amb word]
+template <typename FT>
+__global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
+{
+  using Elem = typename Cmp<FT>::Elem;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const FModel m = loadFast(a.model, a.model_bytes, smem);
+  const fast::Header& h = *m.h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * fastPerWarpBytes(h.state_stride);
+  float* Ts = reinterpret_cast<float*>(wbase);
+  uint32_t* queue = reinterpret_cast<uint32_t*>(wbase + 32 * h.state_stride * 4);
+  unsigned* words = reinterpret_cast<unsigned*>(queue + kQueueCap);  // [0] hit, [1] amb
+  const bool do_fields = (a.flags & 3u) != 0, do_intra = (a.flags & 4u) != 0;
+  const unsigned fmask = ((a.flags & 1u) ? 0x0000ffffu : 0u) | ((a.flags & 2u) ? 0xffff0000u : 0u);
+  const Elem* __restrict__ field = static_cast<const Elem*>(a.field);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int nz = h.nz, nynz = h.nynz;
+  const unsigned idx_bias = h.idx_bias;
+  const float two_m = h.two_margin;
+  float* T_state = Ts + lane * h.state_stride;
+
+  const unsigned long long n = a.n_states;
+  const unsigned long long n_tiles = (n + 31) / 32;
+  for (unsigned long long tile = static_cast<unsigned long long>(blockIdx.x) * warps + warp; tile < n_tiles;
+       tile += static_cast<unsigned long long>(gridDim.x) * warps)
+  {
+    const unsigned long long first = tile * 32;
+    const int cnt = static_cast<int>(n - first < 32 ? n - first : 32);
+    const bool active = lane < cnt;
+    const unsigned long long my_state = first + (active ? lane : 0);  // idle lanes shadow lane 0; result dropped
+    const double* __restrict__ qrow = a.q + my_state * h.n_group_vars;
+    bool hit = false, amb = false;
+    unsigned pv[kU], pt[kU];  // gathers in flight: field element, thresholds
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+    {
+      pv[u] = 0u;
+      pt[u] = Cmp<FT>::kNever;
+    }
+    int slot_a = -1, slot_b = 0;  // parked sphere: the two candidate cells and its thresholds
+    unsigned slot_t = 0u;
+    auto resolveSlot = [&]() {
+      const unsigned va = __ldg(field + slot_a), vb = __ldg(field + slot_b);
+      const bool ha = Cmp<FT>::hit(va, slot_t), hb = Cmp<FT>::hit(vb, slot_t);
+      hit |= ha & hb;
+      amb |= ha ^ hb;
+      slot_a = -1;
+    };
+    float T[12];
+    // ---- FK, and the field checks of every link as soon as its transform exists --------------------------------------
+    for (int l = 0; l < h.n_links; ++l)
+    {
+      const int4* Li = reinterpret_cast<const int4*>(m.links + l);
+      const float4* Lf = reinterpret_cast<const float4*>(m.links + l);
+      const int4 m0 = Li[0];  // type, k, parent_off, store_off
+      const int4 m1 = Li[1];  // h0, h1
+      const float4 o = Lf[3];
+      const float4 c0 = Lf[4], c1 = Lf[5], c2 = Lf[6];  // a0[0..8], a1[0..2]
+      float M[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x };
+      float mt[3] = { o.x, o.y, o.z };
+      if (m0.x != FIXED)
+      {
+        const double2 ab = reinterpret_cast<const double2*>(m.links + l)[2];
+        double v = ab.y;
+        if (m0.y >= 0)
+          v = ab.x * qrow[m0.y] + ab.y;  // setJointGroupPositions / updateMimicJoints in double, then narrowed
+        const float qf = static_cast<float>(v);
+        if (m0.x == REVOLUTE)
+        {
+          const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];  // a1[3..8], a2[0..8]
+          const float A1[9] = { c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w, c4.x, c4.y };
+          const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
+          float s, c;
+          sincosf(qf, &s, &c);
+          const float t = 1.f - c;
+#pragma unroll
+          for (int i = 0; i < 9; ++i)
+            M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
+        }
+        else
+        {  // PRISMATIC
+          mt[0] = fmaf(qf, c2.y, mt[0]);
+          mt[1] = fmaf(qf, c2.z, mt[1]);
+          mt[2] = fmaf(qf, c2.w, mt[2]);
+        }
+      }
+      if (m0.z == fast::kParentRoot)
+      {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+        {
+          T[4 * r + 0] = M[3 * r + 0];
+          T[4 * r + 1] = M[3 * r + 1];
+          T[4 * r + 2] = M[3 * r + 2];
+          T[4 * r + 3] = mt[r];
+        }
+      }
+      else
+      {
+        if (m0.z >= 0)
+          load12(T_state + m0.z, T);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+        {
+          const float p0 = T[4 * r + 0], p1 = T[4 * r + 1], p2 = T[4 * r + 2];
+          T[4 * r + 0] = fmaf(p0, M[0], fmaf(p1, M[3], p2 * M[6]));
+          T[4 * r + 1] = fmaf(p0, M[1], fmaf(p1, M[4], p2 * M[7]));
+          T[4 * r + 2] = fmaf(p0, M[2], fmaf(p1, M[5], p2 * M[8]));
+          T[4 * r + 3] = fmaf(p0, mt[0], fmaf(p1, mt[1], fmaf(p2, mt[2], T[4 * r + 3])));
+        }
+      }
+      if (m0.w >= 0)
+        store12(T_state + m0.w, T);
+      if (!do_fields)
+        continue;
+      // the centre minus `margin` per axis, from a translation column lowered by margin (clamp bounds likewise)
+      const float tmx = T[3] - h.margin, tmy = T[7] - h.margin, tmz = T[11] - h.margin;
+      for (int k0 = m1.x; k0 < m1.y; k0 += kU)
+      {
+        unsigned idx[kU], tt[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+        {
+          const float4 hr = reinterpret_cast<const float4*>(m.hot)[k0 + u];  // uniform address: one broadcast read
+          float fx = fmaf(T[0], hr.x, fmaf(T[1], hr.y, fmaf(T[2], hr.z, tmx)));
+          float fy = fmaf(T[4], hr.x, fmaf(T[5], hr.y, fmaf(T[6], hr.z, tmy)));
+          float fz = fmaf(T[8], hr.x, fmaf(T[9], hr.y, fmaf(T[10], hr.z, tmz)));
+          fx = fminf(fmaxf(fx, h.lo[0]), h.hi[0]);
+          fy = fminf(fmaxf(fy, h.lo[1]), h.hi[1]);
+          fz = fminf(fmaxf(fz, h.lo[2]), h.hi[2]);
+          const int ax = __float_as_int(__fadd_rd(fx, kMagic)), bx = __float_as_int(__fadd_rd(fx + two_m, kMagic));
+          const int ay = __float_as_int(__fadd_rd(fy, kMagic)), by = __float_as_int(__fadd_rd(fy + two_m, kMagic));
+          const int az = __float_as_int(__fadd_rd(fz, kMagic)), bz = __float_as_int(__fadd_rd(fz + two_m, kMagic));
+          const unsigned ia = static_cast<unsigned>(ax * nynz + (ay * nz + az));  // VoxelGrid::ref (voxel_grid.hpp:425)
+          const unsigned ib = static_cast<unsigned>(bx * nynz + (by * nz + bz));
+          const unsigned t = Cmp<FT>::mask(__float_as_uint(hr.w), fmask);
+          idx[u] = ia + idx_bias;
+          tt[u] = t;
+          if (ia != ib)
+          {
+            tt[u] = Cmp<FT>::kNever;
+            if (t != Cmp<FT>::kNever)
+            {  // within `margin` of a cell face: the outcome is certain only if both candidate cells agree
+              const unsigned d = ib - ia;
+              if (d == 1u || d == static_cast<unsigned>(nz) || d == static_cast<unsigned>(nynz))
+              {
+                if (slot_a >= 0)
+                  resolveSlot();
+                slot_a = static_cast<int>(idx[u]);
+                slot_b = static_cast<int>(idx[u] + d);
+                slot_t = t;
+              }
+              else
+                amb = true;  // near an edge or corner of the cell: leave it to the exact pass
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          hit |= Cmp<FT>::hit(pv[u], pt[u]);
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+        {
+          pv[u] = __ldg(field + idx[u]);
+          pt[u] = tt[u];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      hit |= Cmp<FT>::hit(pv[u], pt[u]);
+    if (slot_a >= 0)
+      resolveSlot();
+    // ---- intra-group sphere pairs ---------------------------------------------------------------------------------------
+    if (do_intra && h.n_pairs > 0 && __any_sync(kFull, active && !hit))
+    {
+      if (lane == 0)
+        words[0] = words[1] = 0u;
+      __syncwarp();  // the queue consumers read other lanes' transforms
+      int qn = 0;
+      const bool mine = active && !hit;
+      auto flush = [&]() {
+        __syncwarp();
+        for (int i = lane; i < qn; i += 32)
+        {
+          const unsigned item = queue[i];
+          const int s = item & 31;
+          bool ihit = false, iamb = false;
+          pairItem(m, Ts + s * h.state_stride, item >> 5, ihit, iamb);
+          if (ihit)
+            atomicOr(&words[0], 1u << s);
+          if (iamb)
+            atomicOr(&words[1], 1u << s);
+        }
+        __syncwarp();
+        qn = 0;
+      };
+      for (int g = 0; g < h.n_groups; ++g)
+      {
+        const float4 gc = reinterpret_cast<const float4*>(m.groups + g)[0];
+        const int4 gi = reinterpret_cast<const int4*>(m.groups + g)[1];  // a_off, p0, p1, a
+        float Ta[12], ax, ay, az;
+        load12(T_state + gi.x, Ta);
+        pose(Ta, gc.x, gc.y, gc.z, ax, ay, az);
+        for (int p = gi.y; p < gi.z; ++p)
+        {
+          const float4 pc = reinterpret_cast<const float4*>(m.pairs + p)[0];
+          const int b_off = reinterpret_cast<const int*>(m.pairs + p)[4];
+          float Tb[12], bx, by, bz;
+          load12(T_state + b_off, Tb);
+          pose(Tb, pc.x, pc.y, pc.z, bx, by, bz);
+          // conservative cull: every sphere of a cluster lies inside its tight sphere
+          const float ex = ax - bx, ey = ay - by, ez = az - bz;
+          const bool live = mine && (ex * ex + ey * ey + ez * ez) < pc.w;
+          const unsigned mk = __ballot_sync(kFull, live);
+          if (live)
+            queue[qn + __popc(mk & lt_mask)] = static_cast<uint32_t>(lane | (p << 5));
+          qn += __popc(mk);
+          if (qn > kQueueCap - 32)
+            flush();
+        }
+      }
+      if (qn > 0)
+        flush();
+      hit |= ((words[0] >> lane) & 1u) != 0;
+      amb |= ((words[1] >> lane) & 1u) != 0;
+    }
+    __syncwarp();  // transforms and words are rewritten by the next tile
+    const bool valid = active && !hit && !amb;
+    const bool flagged = active && amb && !hit;  // FP32 could not decide: the exact pass will
+    const unsigned valid_word = __ballot_sync(kFull, valid);
+    const unsigned flag_word = __ballot_sync(kFull, flagged);
+    if (lane == 0)
+      a.bitmap[tile] = valid_word;
+    if (flag_word)
+    {
+      unsigned base = 0;
+      if (lane == 0)
+        base = atomicAdd(a.flag_count, static_cast<unsigned>(__popc(flag_word)));
+      base = __shfl_sync(kFull, base, 0);
+      if (flagged)
+      {
+        const unsigned rank = __popc(flag_word & lt_mask);
+        if (base + rank < a.list_cap)
+          a.flag_list[base + rank] = static_cast<uint32_t>(a.state_base + first + lane);
+      }
+    }
+  }
+}
+
+struct Grant
+{
+  size_t granted[16] = { 0 };
+};
+template <typename K>
+cudaError_t ensure(K kernel, size_t smem_bytes, Grant& g)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (smem_bytes <= g.granted[dev])
+    return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e == cudaSuccess)
+    g.granted[dev] = smem_bytes;
+  return e;
+}
+}  // namespace
+
+int fastCheckPerWarpBytes(int state_stride) { return fastPerWarpBytes(state_stride); }
+int fastCheckUnroll() { return kU; }
+
+int fastCheckKernelRegs(int field_bytes)
+{
+  cudaFuncAttributes fa{};
+  cudaError_t e = field_bytes == 1 ? cudaFuncGetAttributes(&fa, fastCheckKernel<uint8_t>) :
+                                     cudaFuncGetAttributes(&fa, fastCheckKernel<uint16_t>);
+  return e == cudaSuccess ? fa.numRegs : 128;
+}
+
+template <typename FT>
+cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+{
+  static Grant g;
+  cudaError_t e = ensure(fastCheckKernel<FT>, smem_bytes, g);
+  if (e != cudaSuccess)
+    return e;
+  fastCheckKernel<FT><<<grid, block, smem_bytes, stream>>>(a);
+  return cudaGetLastError();
+}
+template cudaError_t launchFastCheck<uint8_t>(const CheckArgs<uint8_t>&, int, int, size_t, cudaStream_t);
+template cudaError_t launchFastCheck<uint16_t>(const CheckArgs<uint16_t>&, int, int, size_t, cudaStream_t);
+}  // namespace b200sv

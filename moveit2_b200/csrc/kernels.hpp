@@ -9,6 +9,10 @@
 #define B200SV_SPHERE_CHUNK 4  // spheres per unrolled pass of the field loop; the sphere table is padded to a multiple
 #endif
 
+#ifndef B200SV_FAST_UNROLL
+#define B200SV_FAST_UNROLL 2  // spheres per unrolled chunk of the fast pass's field loop; Hot ranges are padded per link
+#endif
+
 namespace b200sv
 {
 template <typename FT>
@@ -47,6 +51,12 @@ cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int g
                         cudaStream_t stream);
 int checkKernelRegs(bool fp64, bool from_list, int field_bytes);
 int checkPerWarpBytes(bool fp64, int state_stride);  // shared memory one warp of the check kernel needs
+// fast_check.cu: the FP32 pass for groups of fixed / revolute / prismatic joints (a.model = the fast blob)
+template <typename FT>
+cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+int fastCheckKernelRegs(int field_bytes);
+int fastCheckPerWarpBytes(int state_stride);
+int fastCheckUnroll();
 cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launchGather(const uint8_t* field, unsigned long long n_sectors, int per_thread, int grid, int block,
