@@ -249,6 +249,33 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
     memcpy(out.data() + h.off_groups, groups.data(), groups.size() * sizeof(GroupRec));
 }
 
+// Smallest IEEE half >= x (x > 0), as bits; +inf when x exceeds the half range.
+unsigned halfBitsUp(double x)
+{
+  if (!(x > 0.0))
+    return 0u;
+  if (x > 65504.0)
+    return 0x7c00u;
+  int e = 0;
+  frexp(x, &e);  // x = f * 2^e, f in [0.5, 1)
+  int E = e - 1;  // x in [2^E, 2^(E+1))
+  if (E < -14)
+    E = -14;  // subnormal range shares the spacing 2^-24
+  const double step = ldexp(1.0, E - 10);
+  double q = ceil(x / step) * step;
+  if (q >= ldexp(1.0, E + 1) && E >= -14)
+  {
+    ++E;
+    q = ldexp(1.0, E);
+  }
+  if (E > 15)
+    return 0x7c00u;
+  const int mant = (int)llround(q / ldexp(1.0, E - 10)) - 1024;
+  if (q < ldexp(1.0, -14))
+    return (unsigned)llround(q / ldexp(1.0, -24));  // subnormal
+  return ((unsigned)(E + 15) << 10) | (unsigned)mant;
+}
+
 // Tables of fast_check.cu (device_model.hpp, namespace fast), from the same links / spheres / clusters / pairs the
 // generic blobs are built from.  All constants are evaluated in double and narrowed once.
 bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, const std::vector<VarRec>& vars,
@@ -283,8 +310,6 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
     c.state_stride_fast += 4;
   // spheres -> Hot entries, per link padded to the unroll
   std::vector<fast::Hot> hot;
-  std::vector<float> rad;
-  std::vector<int> hot_of_sphere(n_spheres, -1);
   std::vector<fast::Link> fl(nl);
   const bool bytes8 = c.compact_bytes == 1;
   for (int l = 0; l < nl; ++l)
@@ -370,58 +395,101 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
       H.z = (float)S.z;
       const unsigned t = (unsigned)S.thr | ((unsigned)S.thr_self << 16);
       H.t = bytes8 ? 0x01000100u - t : t;
-      hot_of_sphere[k] = (int)hot.size();
       hot.push_back(H);
-      rad.push_back((float)(S.r * oo));
     }
     while (((int)hot.size() - F.h0) % unroll)
     {  // padding: posed like a real sphere (at the link origin), thresholds 0: never collides
       fast::Hot H{};
       H.t = bytes8 ? 0x01000100u : 0u;
       hot.push_back(H);
-      rad.push_back(0.f);
     }
     F.h1 = (int)hot.size();
+    F.c0 = F.c1 = 0;
     fl[l] = F;
   }
-  std::vector<fast::Cluster> cl(bs.size());
+  // Level-1 cull in half precision: cluster centres are parked relative to rep_base (the first root's origin).
+  // |centre - rep_base| <= reach: the longest chain of |origin translation| + prismatic travel unknown => bounded by
+  // the group's joint limits is not available here, so prismatic joints count with 2 m.  Spacing of half at that
+  // magnitude bounds the rounding of each coordinate; the slack covers both centres, all three axes.
+  double rep_base[3] = { 0, 0, 0 };
+  std::vector<double> reach(nl, 0.0);
+  bool have_base = false;
+  double max_reach = 0.0;
+  for (int l = 0; l < nl; ++l)
+  {
+    const LinkRec<double>& L = links[l];
+    double ot[3] = { L.has_origin ? L.o[3] : 0.0, L.has_origin ? L.o[7] : 0.0, L.has_origin ? L.o[11] : 0.0 };
+    if (L.parent < 0 && !have_base)
+    {
+      for (int k = 0; k < 3; ++k)
+        rep_base[k] = (ot[k] - c.grid.om[k]) * oo;
+      have_base = true;
+    }
+    double r;
+    if (L.parent < 0)
+    {
+      const double dx = (ot[0] - c.grid.om[0]) * oo - rep_base[0], dy = (ot[1] - c.grid.om[1]) * oo - rep_base[1],
+                   dz = (ot[2] - c.grid.om[2]) * oo - rep_base[2];
+      r = sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    else
+      r = reach[L.parent] + sqrt(ot[0] * ot[0] + ot[1] * ot[1] + ot[2] * ot[2]) * oo;
+    if (L.type == PRISMATIC)
+      r += 2.0 * oo;  // assumed travel; the kernel verifies it (Link::range_check) and defers to the exact pass beyond
+    reach[l] = r;
+    fl[l].range_check = (L.type == PRISMATIC || (L.parent >= 0 && fl[L.parent].range_check)) ? 1 : 0;
+  }
   for (size_t i = 0; i < bs.size(); ++i)
   {
+    const double cr = sqrt(bs[i].tx * bs[i].tx + bs[i].ty * bs[i].ty + bs[i].tz * bs[i].tz) * oo;
+    max_reach = std::max(max_reach, reach[bs[i].slot] + cr);
+  }
+  int e2 = 0;
+  frexp(std::max(max_reach, 1.0), &e2);                    // max_reach < 2^e2
+  const double half_spacing = ldexp(1.0, e2 - 11);         // spacing of half values below 2^e2
+  const double half_slack = 2.0 * sqrt(3.0) * half_spacing + 0.01;
+  std::vector<fast::Cluster> cl(bs.size());
+  std::vector<fast::PSphere> ps(bs.size() * fast::kClusterSpheres);
+  for (size_t i = 0; i < bs.size(); ++i)
+  {
+    if (bs[i].s1 - bs[i].s0 > fast::kClusterSpheres)
+      return false;  // cannot happen: buildTables caps clusters at kClusterSpheres
     fast::Cluster C{};
     C.tx = (float)bs[i].tx;
     C.ty = (float)bs[i].ty;
     C.tz = (float)bs[i].tz;
-    C.tr_v = (float)(bs[i].tr * oo);
-    C.off = store_off[bs[i].slot];
-    C.h0 = hot_of_sphere[bs[i].s0];
-    C.h1 = C.h0 + (bs[i].s1 - bs[i].s0);
     cl[i] = C;
+    fast::Link& F = fl[bs[i].slot];  // clusters are created link by link: a link's clusters are contiguous
+    if (F.c1 == 0)
+      F.c0 = (int)i;
+    F.c1 = (int)i + 1;
+    for (int k = 0; k < fast::kClusterSpheres; ++k)
+    {
+      fast::PSphere Q{};
+      Q.r_v = -1e30f;
+      if (bs[i].s0 + k < bs[i].s1)
+      {
+        const SphereRec<double>& S = spheres[bs[i].s0 + k];
+        Q.x = (float)S.x;
+        Q.y = (float)S.y;
+        Q.z = (float)S.z;
+        Q.r_v = (float)(S.r * oo);
+      }
+      ps[i * fast::kClusterSpheres + k] = Q;
+    }
   }
   std::vector<fast::Group> fg(groups.size());
   std::vector<fast::Pair> fp(pairs.size());
   std::vector<fast::Quirk> fq;
   for (size_t g = 0; g < groups.size(); ++g)
-  {
-    const BsRec<double>& A = bs[groups[g].a];
-    fast::Group G{};
-    G.ax = (float)A.tx;
-    G.ay = (float)A.ty;
-    G.az = (float)A.tz;
-    G.a_off = store_off[A.slot];
-    G.p0 = groups[g].p0;
-    G.p1 = groups[g].p1;
-    G.a = groups[g].a;
-    fg[g] = G;
-  }
+    fg[g] = fast::Group{ groups[g].a, groups[g].p0, groups[g].p1, 0 };
   for (size_t p = 0; p < pairs.size(); ++p)
   {
     const BsRec<double>&A = bs[pairs[p].a], &B = bs[pairs[p].b];
     fast::Pair P{};
-    P.bx = (float)B.tx;
-    P.by = (float)B.ty;
-    P.bz = (float)B.tz;
-    const double rt = (A.tr + B.tr + tight_eps) * oo;
-    P.rt2_v = (float)(rt * rt * (1.0 + 1e-6));  // narrowed upwards: the cull stays conservative
+    const double rt = (A.tr + B.tr + tight_eps) * oo + half_slack;
+    P.rt2_h = halfBitsUp(rt * rt * (1.0 + 4.0 / 1024.0));  // + the half rounding of the squared sum itself
+    P.a_off = store_off[A.slot];
     P.b_off = store_off[B.slot];
     P.a = pairs[p].a;
     P.b = pairs[p].b;
@@ -450,8 +518,8 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   off = align16(off + (int)(fl.size() * sizeof(fast::Link)));
   h.off_hot = off;
   off = align16(off + (int)(hot.size() * sizeof(fast::Hot)));
-  h.off_rad = off;
-  off = align16(off + (int)(rad.size() * sizeof(float)));
+  h.off_psphere = off;
+  off = align16(off + (int)(ps.size() * sizeof(fast::PSphere)));
   h.off_clusters = off;
   off = align16(off + (int)(cl.size() * sizeof(fast::Cluster)));
   h.off_groups = off;
@@ -462,6 +530,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   off = align16(off + (int)(fq.size() * sizeof(fast::Quirk)));
   h.total_bytes = off;
   h.state_stride = c.state_stride_fast;
+  h.n_clusters = (int)cl.size();
   h.nz = c.grid.nz;
   h.nynz = c.grid.ny * c.grid.nz;
   h.idx_bias = 0u - 0x4B400000u * (unsigned)(h.nynz + h.nz + 1);
@@ -473,6 +542,9 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   }
   h.margin = (float)margin;
   h.two_margin = (float)(2.0 * margin);
+  for (int k = 0; k < 3; ++k)
+    h.rep_base[k] = (float)rep_base[k];
+  h.rep_limit = (float)ldexp(1.0, e2);
   h.pair_eps_v = (float)(pair_eps * oo);
   h.tight_eps_v = (float)(tight_eps * oo);
   c.blob_fast.assign(off, 0);
@@ -482,10 +554,12 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   if (!hot.empty())
   {
     memcpy(o + h.off_hot, hot.data(), hot.size() * sizeof(fast::Hot));
-    memcpy(o + h.off_rad, rad.data(), rad.size() * sizeof(float));
   }
   if (!cl.empty())
+  {
     memcpy(o + h.off_clusters, cl.data(), cl.size() * sizeof(fast::Cluster));
+    memcpy(o + h.off_psphere, ps.data(), ps.size() * sizeof(fast::PSphere));
+  }
   if (!fg.empty())
     memcpy(o + h.off_groups, fg.data(), fg.size() * sizeof(fast::Group));
   if (!fp.empty())
@@ -705,7 +779,7 @@ int buildTables(b200sv_ctx* c)
       int s1 = s0 + 1;
       double t4[4], best4[4];
       tight(s0, s1, best4);
-      while (s1 < (int)spheres.size() && s1 - s0 < 64)
+      while (s1 < (int)spheres.size() && s1 - s0 < fast::kClusterSpheres)
       {
         tight(s0, s1 + 1, t4);
         if (t4[3] > c->cluster_radius)
@@ -800,7 +874,7 @@ b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, 
   b200sv_ctx::LaunchCfg best;
   const int regs = ((fast ? fastCheckKernelRegs(c->compact_bytes) : checkKernelRegs(fp64, from_list, c->compact_bytes)) + 7) & ~7;
   const int reg_warps = 65536 / (regs * 32);
-  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast) :
+  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast, c->n_bs) :
                          checkPerWarpBytes(fp64, fp64 ? c->state_stride_d : c->state_stride_f);
   for (int b = 1; b <= 4; ++b)
   {

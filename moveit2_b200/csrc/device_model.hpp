@@ -113,9 +113,10 @@ struct alignas(16) Link
   int parent_off;  // kParentRoot, kParentPrev or the word offset of the parent's transform in the state's block
   int store_off;   // word offset this link's transform is stored at, -1: nobody reads it back
   int h0, h1;      // Hot range of the link's spheres, padded to a multiple of the field loop's unroll
-  int pad0, pad1;
+  int c0, c1;      // Cluster range of the link
   double a, b;
-  float ot[3], pad2;
+  float ot[3];
+  int range_check;  // 1: a prismatic joint upstream: verify the parked cluster centres stay within Header::rep_limit
   float a0[9], a1[9], a2[9], pad3;
 };
 static_assert(sizeof(Link) == 176, "fast::Link layout");
@@ -128,28 +129,36 @@ struct alignas(16) Hot
                   // thr = 0 never collides (padding, or the self check disabled for the link)
 };
 
+constexpr int kClusterSpheres = 4;  // a cluster holds at most this many spheres; PSphere rows are padded to it
+
+// A cluster's tight-sphere centre in its link frame: posed in the link loop and parked in shared memory
+// ([cluster][x, y, z][lane]) for the level-1 cull of the pair phase.
 struct alignas(16) Cluster
 {
-  float tx, ty, tz;  // tight-sphere centre (link frame, metres)
-  float tr_v;        // tight radius (cells)
-  int off;           // word offset of the link's transform
-  int h0, h1;        // Hot range of the cluster's spheres (no padding inside)
-  int pad;
+  float tx, ty, tz, pad;
+};
+
+// Pair phase: sphere k of cluster c is PSphere[kClusterSpheres * c + k].  Padding entries have r_v = -1e30: their
+// distance test can never pass.
+struct alignas(16) PSphere
+{
+  float x, y, z;  // link frame, metres
+  float r_v;      // radius in cells
 };
 
 struct alignas(16) Group  // pairs [p0, p1) share cluster a
 {
-  float ax, ay, az, pad0;
-  int a_off, p0, p1, a;
+  int a, p0, p1, pad;
 };
 
 struct alignas(16) Pair
 {
-  float bx, by, bz;  // tight centre of cluster b (link frame)
-  float rt2_v;       // (tr_a + tr_b + tight_eps)^2 in cells^2
-  int b_off, a, b;   // transform offset of b's link; Cluster indices
+  unsigned rt2_h;    // (tr_a + tr_b + slack)^2 in cells^2 as half bits, rounded up (the level-1 cull runs in half)
+  int a, b;          // Cluster indices
+  int a_off, b_off;  // transform offsets of the two links
   int quirk;         // -1: the reference's link-level cull provably passes whenever the tight spheres are this close;
                      // else index of the Quirk record to evaluate
+  int pad0, pad1;
 };
 
 // doBoundingSpheresIntersect on the LINKS' bounding spheres (types.cpp:408-418), quirk kept: squared centre distance
@@ -164,14 +173,18 @@ struct alignas(16) Quirk
 struct alignas(16) Header
 {
   int n_links, n_groups, n_pairs, n_group_vars;
-  int off_links, off_hot, off_rad, off_clusters;
+  int off_links, off_hot, off_psphere, off_clusters;
   int off_groups, off_pairs, off_quirks, total_bytes;
-  int state_stride;  // words of shared memory per state
+  int state_stride;  // words of shared memory per state (transforms)
+  int n_clusters;
   int nz, nynz;
   unsigned idx_bias;  // -(0x4B400000 * (nynz + nz + 1)) mod 2^32: undoes the float-magic bias of the three cell indices
+  int pad2, pad3, pad4;
   float lo[3], margin;      // clamp of (centre - margin) to [0.5 - margin, n - 0.5 - margin]: a centre outside the
   float hi[3], two_margin;  // field lands in the 1-cell border shell, where nothing collides
   float pair_eps_v, tight_eps_v, pad0, pad1;
+  float rep_base[3];  // cluster centres are parked relative to this point (cells): small magnitudes for half
+  float rep_limit;    // the level-1 slack assumes |centre - rep_base| < rep_limit per axis
 };
 }  // namespace fast
 }  // namespace b200sv

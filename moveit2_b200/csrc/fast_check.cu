@@ -23,9 +23,11 @@
 //
 // A state whose boolean could depend on FP32 rounding is appended to the recheck list; the exact pass
 // (checkKernel<double, ., true>, the reference's arithmetic operation by operation) decides it.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "device_model.hpp"
 #include "kernels.hpp"
@@ -35,7 +37,8 @@ namespace b200sv
 namespace
 {
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kU = B200SV_FAST_UNROLL;  // spheres per unrolled chunk of the field loop (Hot ranges are padded to it)
+constexpr int kU = B200SV_FAST_UNROLL;  // Hot ranges are padded per link to a multiple of this (the tail chunk)
+constexpr int kP = 4;                   // gathers in flight per lane = spheres of the main chunk
 constexpr int kQueueCap = 256;          // (state, pair) work items per warp; flushed when fewer than 32 slots remain
 constexpr float kMagic = 12582912.f;    // 1.5 * 2^23: x + kMagic rounded down has floor(x) in its low mantissa bits
 constexpr unsigned kGuard = 0x01000100u;
@@ -45,7 +48,7 @@ struct FModel
   const fast::Header* h;
   const fast::Link* links;
   const fast::Hot* hot;
-  const float* rad;
+  const fast::PSphere* ps;
   const fast::Cluster* cl;
   const fast::Group* groups;
   const fast::Pair* pairs;
@@ -60,10 +63,10 @@ template <> struct Cmp<uint8_t>
   using Elem = uint16_t;
   static constexpr unsigned kNever = kGuard;
   static __device__ __forceinline__ unsigned mask(unsigned t, unsigned fmask) { return (t & fmask) | (kGuard & ~fmask); }
-  static __device__ __forceinline__ bool hit(unsigned v, unsigned t)
+  // nonzero iff either field's distance is below its threshold
+  static __device__ __forceinline__ unsigned hit(unsigned v, unsigned t)
   {
-    const unsigned z = __byte_perm(v, 0u, 0x3120) + t;
-    return (z & kGuard) != kGuard;
+    return ((__byte_perm(v, 0u, 0x3120) + t) & kGuard) ^ kGuard;
   }
 };
 template <> struct Cmp<uint16_t>
@@ -71,9 +74,9 @@ template <> struct Cmp<uint16_t>
   using Elem = uint32_t;
   static constexpr unsigned kNever = 0u;
   static __device__ __forceinline__ unsigned mask(unsigned t, unsigned fmask) { return t & fmask; }
-  static __device__ __forceinline__ bool hit(unsigned v, unsigned t)
+  static __device__ __forceinline__ unsigned hit(unsigned v, unsigned t)
   {
-    return ((v & 0xffffu) < (t & 0xffffu)) | ((v >> 16) < (t >> 16));
+    return static_cast<unsigned>(((v & 0xffffu) < (t & 0xffffu)) | ((v >> 16) < (t >> 16)));
   }
 };
 
@@ -112,7 +115,7 @@ __device__ __forceinline__ FModel loadFast(const uint8_t* __restrict__ g_model, 
   m.h = reinterpret_cast<const fast::Header*>(smem);
   m.links = reinterpret_cast<const fast::Link*>(smem + m.h->off_links);
   m.hot = reinterpret_cast<const fast::Hot*>(smem + m.h->off_hot);
-  m.rad = reinterpret_cast<const float*>(smem + m.h->off_rad);
+  m.ps = reinterpret_cast<const fast::PSphere*>(smem + m.h->off_psphere);
   m.cl = reinterpret_cast<const fast::Cluster*>(smem + m.h->off_clusters);
   m.groups = reinterpret_cast<const fast::Group*>(smem + m.h->off_groups);
   m.pairs = reinterpret_cast<const fast::Pair*>(smem + m.h->off_pairs);
@@ -120,20 +123,32 @@ __device__ __forceinline__ FModel loadFast(const uint8_t* __restrict__ g_model, 
   return m;
 }
 
+__device__ __forceinline__ float sqrtApprox(float x)
+{
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // One (state, cluster pair) item that survived the level-1 cull: [the reference's link-level cull when the host could
-// not prove it away,] spheres of either cluster against the other cluster's tight sphere, survivors sphere against
-// sphere (getIntraGroupCollisions, collision_env_distance_field.cpp:571-638).  T: the state's transform block.
+// not prove it away,] then every sphere of cluster a against every sphere of cluster b, dist < r1 + r2
+// (getIntraGroupCollisions, collision_env_distance_field.cpp:571-638).  Clusters are padded to kClusterSpheres
+// entries whose radius is -1e30, so the 4 x 4 block is branch-free.  T: the state's transform block.
 __device__ __forceinline__ void pairItem(const FModel& m, const float* T, unsigned p, bool& hit, bool& amb)
 {
+  constexpr int kC = fast::kClusterSpheres;
   const fast::Header& h = *m.h;
-  const fast::Pair P = m.pairs[p];
+  const float4 p0 = reinterpret_cast<const float4*>(m.pairs + p)[0];  // rt2, a, b, a_off
+  const int4 p1 = reinterpret_cast<const int4*>(m.pairs + p)[1];      // b_off, quirk
+  const int ca = __float_as_int(p0.y), cb = __float_as_int(p0.z), a_off = __float_as_int(p0.w), b_off = p1.x;
+  float Ta[12], Tb[12];
+  load12(T + a_off, Ta);
+  load12(T + b_off, Tb);
   bool cert = true;
-  if (P.quirk >= 0)
+  if (p1.y >= 0)
   {
-    const fast::Quirk Q = m.quirks[P.quirk];
-    float Ta[12], Tb[12], ax, ay, az, bx, by, bz;
-    load12(T + Q.a_off, Ta);
-    load12(T + Q.b_off, Tb);
+    const fast::Quirk Q = m.quirks[p1.y];
+    float ax, ay, az, bx, by, bz;
     pose(Ta, Q.ax, Q.ay, Q.az, ax, ay, az);
     pose(Tb, Q.bx, Q.by, Q.bz, bx, by, bz);
     const float ex = ax - bx, ey = ay - by, ez = az - bz;
@@ -142,76 +157,49 @@ __device__ __forceinline__ void pairItem(const FModel& m, const float* T, unsign
       return;
     cert = d2 < Q.lim_v2 - Q.eps_v2;
   }
-  const fast::Cluster A = m.cl[P.a], B = m.cl[P.b];
-  const int na = A.h1 - A.h0, nb = B.h1 - B.h0;
-  float Ta[12], Tb[12];
-  load12(T + A.off, Ta);
-  load12(T + B.off, Tb);
-  unsigned long long ma = ~0ull >> (64 - na), mb = ~0ull >> (64 - nb);
-  if (na * nb > 4)
+  float bx[kC], by[kC], bz[kC], br[kC];
+#pragma unroll
+  for (int j = 0; j < kC; ++j)
   {
-    float tax, tay, taz, tbx, tby, tbz;
-    pose(Ta, A.tx, A.ty, A.tz, tax, tay, taz);
-    pose(Tb, B.tx, B.ty, B.tz, tbx, tby, tbz);
-    ma = 0ull;
-    for (int i = 0; i < na; ++i)
-    {
-      const fast::Hot sp = m.hot[A.h0 + i];
-      float x, y, z;
-      pose(Ta, sp.x, sp.y, sp.z, x, y, z);
-      const float gx = x - tbx, gy = y - tby, gz = z - tbz;
-      const float lim = m.rad[A.h0 + i] + B.tr_v + h.tight_eps_v;
-      if ((gx * gx + gy * gy + gz * gz) < lim * lim)
-        ma |= 1ull << i;
-    }
-    if (ma == 0ull)
-      return;
-    mb = 0ull;
-    for (int j = 0; j < nb; ++j)
-    {
-      const fast::Hot sp = m.hot[B.h0 + j];
-      float x, y, z;
-      pose(Tb, sp.x, sp.y, sp.z, x, y, z);
-      const float gx = x - tax, gy = y - tay, gz = z - taz;
-      const float lim = m.rad[B.h0 + j] + A.tr_v + h.tight_eps_v;
-      if ((gx * gx + gy * gy + gz * gz) < lim * lim)
-        mb |= 1ull << j;
-    }
-    if (mb == 0ull)
-      return;
+    const float4 sp = reinterpret_cast<const float4*>(m.ps)[kC * cb + j];
+    pose(Tb, sp.x, sp.y, sp.z, bx[j], by[j], bz[j]);
+    br[j] = sp.w;
   }
-  while (ma)
+  bool any_cert = false, any_maybe = false;
+  const float eps = h.pair_eps_v;
+#pragma unroll
+  for (int i = 0; i < kC; ++i)
   {
-    const int i = __ffsll(static_cast<long long>(ma)) - 1;
-    ma &= ma - 1;
-    const fast::Hot sa = m.hot[A.h0 + i];
-    const float ra = m.rad[A.h0 + i];
-    float axp, ayp, azp;
-    pose(Ta, sa.x, sa.y, sa.z, axp, ayp, azp);
-    unsigned long long mj = mb;
-    while (mj)
+    const float4 sp = reinterpret_cast<const float4*>(m.ps)[kC * ca + i];
+    float ax, ay, az;
+    pose(Ta, sp.x, sp.y, sp.z, ax, ay, az);
+#pragma unroll
+    for (int j = 0; j < kC; ++j)
     {
-      const int j = __ffsll(static_cast<long long>(mj)) - 1;
-      mj &= mj - 1;
-      const fast::Hot sb = m.hot[B.h0 + j];
-      float bxp, byp, bzp;
-      pose(Tb, sb.x, sb.y, sb.z, bxp, byp, bzp);
-      const float gx = axp - bxp, gy = ayp - byp, gz = azp - bzp;
-      const float dd = gx * gx + gy * gy + gz * gz;
-      const float rsum = ra + m.rad[B.h0 + j];
-      // gradient.norm() < r1 + r2 (collision_env_distance_field.cpp:577-583) with the FP32 uncertainty either side
-      const float lo = rsum - h.pair_eps_v, hi = rsum + h.pair_eps_v;
-      const bool c_cert = (lo > 0.f) && (dd < lo * lo);
-      const bool c_maybe = dd < hi * hi;
-      hit |= (cert && c_cert);
-      amb |= (c_maybe && !(cert && c_cert));
+      const float gx = ax - bx[j], gy = ay - by[j], gz = az - bz[j];
+      // gradient.norm() - r1 - r2 < 0 (collision_env_distance_field.cpp:577-583) with the FP32 uncertainty either side
+      const float gap = (sqrtApprox(fmaf(gx, gx, fmaf(gy, gy, gz * gz))) - sp.w) - br[j];
+      any_cert |= gap < -eps;
+      any_maybe |= gap < eps;
     }
   }
+  hit = cert && any_cert;
+  amb = any_maybe && !hit;
 }
 
-__device__ __host__ inline int fastPerWarpBytes(int state_stride) { return 32 * state_stride * 4 + kQueueCap * 4 + 16; }
+// Row length (elements) of one state's posed cluster centres: odd, so the 32 lanes of the link loop (one state each)
+// store to 32 distinct banks and the 32 lanes of the level-1 cull (one pair each, same state) load conflict-free.
+__device__ __host__ inline int repStride(int n_clusters) { return n_clusters | 1; }
 
-// Dynamic shared memory: [fast blob][per warp: transforms of 32 states | work queue | hit word, amb word]
+// Per-warp shared memory in bytes: transforms of 32 states | cluster centres (x, y) half2 [state][cluster] |
+// cluster centres z half [state][cluster] | queue | words
+__device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters)
+{
+  const int rs = repStride(n_clusters);
+  return 32 * state_stride * 4 + 32 * rs * 4 + ((32 * rs * 2 + 15) & ~15) + kQueueCap * 4 + 16;
+}
+
+// Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
 template <typename FT>
 __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
 {
@@ -220,9 +208,12 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
   const FModel m = loadFast(a.model, a.model_bytes, smem);
   const fast::Header& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * fastPerWarpBytes(h.state_stride);
+  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * fastPerWarpBytes(h.state_stride, h.n_clusters);
   float* Ts = reinterpret_cast<float*>(wbase);
-  uint32_t* queue = reinterpret_cast<uint32_t*>(wbase + 32 * h.state_stride * 4);
+  const int rs = repStride(h.n_clusters);
+  uint32_t* rep_xy = reinterpret_cast<uint32_t*>(Ts + 32 * h.state_stride);  // [state][cluster] half2 (x, y)
+  uint16_t* rep_z = reinterpret_cast<uint16_t*>(rep_xy + 32 * rs);           // [state][cluster] half z
+  uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_z) + ((32 * rs * 2 + 15) & ~15));
   unsigned* words = reinterpret_cast<unsigned*>(queue + kQueueCap);  // [0] hit, [1] amb
   const bool do_fields = (a.flags & 3u) != 0, do_intra = (a.flags & 4u) != 0;
   const unsigned fmask = ((a.flags & 1u) ? 0x0000ffffu : 0u) | ((a.flags & 2u) ? 0xffff0000u : 0u);
@@ -243,10 +234,20 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
     const bool active = lane < cnt;
     const unsigned long long my_state = first + (active ? lane : 0);  // idle lanes shadow lane 0; result dropped
     const double* __restrict__ qrow = a.q + my_state * h.n_group_vars;
-    bool hit = false, amb = false;
-    unsigned pv[kU], pt[kU];  // gathers in flight: field element, thresholds
+    {  // the states of this warp's NEXT tile: pull their lines into L2 now (they stream from HBM exactly once)
+      const unsigned long long nt = tile + static_cast<unsigned long long>(gridDim.x) * warps;
+      if (nt < n_tiles)
+      {
+        const unsigned long long ns = nt * 32 + lane < n ? nt * 32 + lane : n - 1;
+        const char* pq = reinterpret_cast<const char*>(a.q + ns * h.n_group_vars);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pq));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pq + h.n_group_vars * 8 - 1));
+      }
+    }
+    unsigned hacc = 0u, aacc = 0u;  // nonzero: certainly colliding / FP32 cannot decide
+    unsigned pv[kP], pt[kP];      // gathers in flight: field element, thresholds
 #pragma unroll
-    for (int u = 0; u < kU; ++u)
+    for (int u = 0; u < kP; ++u)
     {
       pv[u] = 0u;
       pt[u] = Cmp<FT>::kNever;
@@ -255,10 +256,67 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
     unsigned slot_t = 0u;
     auto resolveSlot = [&]() {
       const unsigned va = __ldg(field + slot_a), vb = __ldg(field + slot_b);
-      const bool ha = Cmp<FT>::hit(va, slot_t), hb = Cmp<FT>::hit(vb, slot_t);
-      hit |= ha & hb;
-      amb |= ha ^ hb;
+      const bool ha = Cmp<FT>::hit(va, slot_t) != 0u, hb = Cmp<FT>::hit(vb, slot_t) != 0u;
+      hacc |= static_cast<unsigned>(ha & hb);
+      aacc |= static_cast<unsigned>(ha ^ hb);
       slot_a = -1;
+    };
+    // N consecutive spheres of the current link (transform Tl in registers, translation lowered by margin): pose,
+    // clamp, both candidate cells, gather; branch-free except for the rare "centre within margin of a cell face".
+    auto chunk = [&](int k0, const float* Tl, float tmx, float tmy, float tmz, auto n_tag) {
+      constexpr int N = decltype(n_tag)::value;
+      unsigned idx[N], tt[N], dd[N];
+      unsigned rmask = 0u;
+#pragma unroll
+      for (int u = 0; u < N; ++u)
+      {
+        const float4 hr = reinterpret_cast<const float4*>(m.hot)[k0 + u];  // uniform address: one broadcast read
+        float fx = fmaf(Tl[0], hr.x, fmaf(Tl[1], hr.y, fmaf(Tl[2], hr.z, tmx)));
+        float fy = fmaf(Tl[4], hr.x, fmaf(Tl[5], hr.y, fmaf(Tl[6], hr.z, tmy)));
+        float fz = fmaf(Tl[8], hr.x, fmaf(Tl[9], hr.y, fmaf(Tl[10], hr.z, tmz)));
+        fx = fminf(fmaxf(fx, h.lo[0]), h.hi[0]);
+        fy = fminf(fmaxf(fy, h.lo[1]), h.hi[1]);
+        fz = fminf(fmaxf(fz, h.lo[2]), h.hi[2]);
+        const int ax = __float_as_int(__fadd_rd(fx, kMagic)), bx = __float_as_int(__fadd_rd(fx + two_m, kMagic));
+        const int ay = __float_as_int(__fadd_rd(fy, kMagic)), by = __float_as_int(__fadd_rd(fy + two_m, kMagic));
+        const int az = __float_as_int(__fadd_rd(fz, kMagic)), bz = __float_as_int(__fadd_rd(fz + two_m, kMagic));
+        const unsigned ia = static_cast<unsigned>(ax * nynz + (ay * nz + az));  // VoxelGrid::ref (voxel_grid.hpp:425)
+        const unsigned ib = static_cast<unsigned>(bx * nynz + (by * nz + bz));
+        const unsigned t = Cmp<FT>::mask(__float_as_uint(hr.w), fmask);
+        const bool r = ia != ib;  // within `margin` of a cell face
+        idx[u] = ia + idx_bias;
+        dd[u] = ib - ia;
+        tt[u] = r ? Cmp<FT>::kNever : t;
+        rmask |= (r && t != Cmp<FT>::kNever) ? (1u << u) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < N; ++u)
+        hacc |= Cmp<FT>::hit(pv[u], pt[u]);
+#pragma unroll
+      for (int u = 0; u < N; ++u)
+      {
+        pv[u] = __ldg(field + idx[u]);
+        pt[u] = tt[u];
+      }
+      if (rmask)
+      {  // rare: the outcome is certain only if both candidate cells agree; park the sphere, read both cells later
+#pragma unroll
+        for (int u = 0; u < N; ++u)
+          if ((rmask >> u) & 1u)
+          {
+            const unsigned d = dd[u];
+            if (d == 1u || d == static_cast<unsigned>(nz) || d == static_cast<unsigned>(nynz))
+            {
+              if (slot_a >= 0)
+                resolveSlot();
+              slot_a = static_cast<int>(idx[u]);
+              slot_b = static_cast<int>(idx[u] + d);
+              slot_t = Cmp<FT>::mask(m.hot[k0 + u].t, fmask);
+            }
+            else
+              aacc = 1u;  // near an edge or corner of the cell: leave it to the exact pass
+          }
+      }
     };
     float T[12];
     // ---- FK, and the field checks of every link as soon as its transform exists --------------------------------------
@@ -267,7 +325,7 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
       const int4* Li = reinterpret_cast<const int4*>(m.links + l);
       const float4* Lf = reinterpret_cast<const float4*>(m.links + l);
       const int4 m0 = Li[0];  // type, k, parent_off, store_off
-      const int4 m1 = Li[1];  // h0, h1
+      const int4 m1 = Li[1];  // h0, h1, c0, c1
       const float4 o = Lf[3];
       const float4 c0 = Lf[4], c1 = Lf[5], c2 = Lf[6];  // a0[0..8], a1[0..2]
       float M[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x };
@@ -325,66 +383,39 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
       }
       if (m0.w >= 0)
         store12(T_state + m0.w, T);
+      if (do_intra && m1.z < m1.w)
+      {  // tight-sphere centres of the link's clusters, relative to rep_base and narrowed to half: the level-1 cull of
+         // the pair phase is conservative, its slack (host) covers the rounding
+        const float tbx = T[3] - h.rep_base[0], tby = T[7] - h.rep_base[1], tbz = T[11] - h.rep_base[2];
+        for (int c = m1.z; c < m1.w; ++c)
+        {
+          const float4 cc = reinterpret_cast<const float4*>(m.cl)[c];
+          const float x = fmaf(T[0], cc.x, fmaf(T[1], cc.y, fmaf(T[2], cc.z, tbx)));
+          const float y = fmaf(T[4], cc.x, fmaf(T[5], cc.y, fmaf(T[6], cc.z, tby)));
+          const float z = fmaf(T[8], cc.x, fmaf(T[9], cc.y, fmaf(T[10], cc.z, tbz)));
+          if (__float_as_int(o.w) != 0 && fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) >= h.rep_limit)
+            aacc = 1u;  // beyond the travel the host assumed for prismatic joints: the exact pass decides
+          const __half2 xy = __floats2half2_rn(x, y);
+          rep_xy[lane * rs + c] = *reinterpret_cast<const uint32_t*>(&xy);
+          rep_z[lane * rs + c] = __half_as_ushort(__float2half_rn(z));
+        }
+      }
       if (!do_fields)
         continue;
       // the centre minus `margin` per axis, from a translation column lowered by margin (clamp bounds likewise)
       const float tmx = T[3] - h.margin, tmy = T[7] - h.margin, tmz = T[11] - h.margin;
-      for (int k0 = m1.x; k0 < m1.y; k0 += kU)
-      {
-        unsigned idx[kU], tt[kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-        {
-          const float4 hr = reinterpret_cast<const float4*>(m.hot)[k0 + u];  // uniform address: one broadcast read
-          float fx = fmaf(T[0], hr.x, fmaf(T[1], hr.y, fmaf(T[2], hr.z, tmx)));
-          float fy = fmaf(T[4], hr.x, fmaf(T[5], hr.y, fmaf(T[6], hr.z, tmy)));
-          float fz = fmaf(T[8], hr.x, fmaf(T[9], hr.y, fmaf(T[10], hr.z, tmz)));
-          fx = fminf(fmaxf(fx, h.lo[0]), h.hi[0]);
-          fy = fminf(fmaxf(fy, h.lo[1]), h.hi[1]);
-          fz = fminf(fmaxf(fz, h.lo[2]), h.hi[2]);
-          const int ax = __float_as_int(__fadd_rd(fx, kMagic)), bx = __float_as_int(__fadd_rd(fx + two_m, kMagic));
-          const int ay = __float_as_int(__fadd_rd(fy, kMagic)), by = __float_as_int(__fadd_rd(fy + two_m, kMagic));
-          const int az = __float_as_int(__fadd_rd(fz, kMagic)), bz = __float_as_int(__fadd_rd(fz + two_m, kMagic));
-          const unsigned ia = static_cast<unsigned>(ax * nynz + (ay * nz + az));  // VoxelGrid::ref (voxel_grid.hpp:425)
-          const unsigned ib = static_cast<unsigned>(bx * nynz + (by * nz + bz));
-          const unsigned t = Cmp<FT>::mask(__float_as_uint(hr.w), fmask);
-          idx[u] = ia + idx_bias;
-          tt[u] = t;
-          if (ia != ib)
-          {
-            tt[u] = Cmp<FT>::kNever;
-            if (t != Cmp<FT>::kNever)
-            {  // within `margin` of a cell face: the outcome is certain only if both candidate cells agree
-              const unsigned d = ib - ia;
-              if (d == 1u || d == static_cast<unsigned>(nz) || d == static_cast<unsigned>(nynz))
-              {
-                if (slot_a >= 0)
-                  resolveSlot();
-                slot_a = static_cast<int>(idx[u]);
-                slot_b = static_cast<int>(idx[u] + d);
-                slot_t = t;
-              }
-              else
-                amb = true;  // near an edge or corner of the cell: leave it to the exact pass
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-          hit |= Cmp<FT>::hit(pv[u], pt[u]);
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-        {
-          pv[u] = __ldg(field + idx[u]);
-          pt[u] = tt[u];
-        }
-      }
+      int k0 = m1.x;
+      for (; k0 + 4 <= m1.y; k0 += 4)
+        chunk(k0, T, tmx, tmy, tmz, std::integral_constant<int, 4>());
+      if (k0 < m1.y)
+        chunk(k0, T, tmx, tmy, tmz, std::integral_constant<int, 2>());  // Hot ranges are padded to a multiple of 2
     }
 #pragma unroll
-    for (int u = 0; u < kU; ++u)
-      hit |= Cmp<FT>::hit(pv[u], pt[u]);
+    for (int u = 0; u < kP; ++u)
+      hacc |= Cmp<FT>::hit(pv[u], pt[u]);
     if (slot_a >= 0)
       resolveSlot();
+    bool hit = hacc != 0u, amb = aacc != 0u;
     // ---- intra-group sphere pairs ---------------------------------------------------------------------------------------
     if (do_intra && h.n_pairs > 0 && __any_sync(kFull, active && !hit))
     {
@@ -409,29 +440,57 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
         __syncwarp();
         qn = 0;
       };
-      for (int g = 0; g < h.n_groups; ++g)
+      // level 1, TRANSPOSED: lane = cluster pair, loop over the warp's live states.  Conservative cull on the tight
+      // spheres (every sphere of a cluster lies inside its tight sphere), in half precision on the parked centres.
+      const unsigned mine_mask = __ballot_sync(kFull, mine);
+      for (int p0 = 0; p0 < h.n_pairs; p0 += 32)
       {
-        const float4 gc = reinterpret_cast<const float4*>(m.groups + g)[0];
-        const int4 gi = reinterpret_cast<const int4*>(m.groups + g)[1];  // a_off, p0, p1, a
-        float Ta[12], ax, ay, az;
-        load12(T_state + gi.x, Ta);
-        pose(Ta, gc.x, gc.y, gc.z, ax, ay, az);
-        for (int p = gi.y; p < gi.z; ++p)
-        {
-          const float4 pc = reinterpret_cast<const float4*>(m.pairs + p)[0];
-          const int b_off = reinterpret_cast<const int*>(m.pairs + p)[4];
-          float Tb[12], bx, by, bz;
-          load12(T_state + b_off, Tb);
-          pose(Tb, pc.x, pc.y, pc.z, bx, by, bz);
-          // conservative cull: every sphere of a cluster lies inside its tight sphere
-          const float ex = ax - bx, ey = ay - by, ez = az - bz;
-          const bool live = mine && (ex * ex + ey * ey + ez * ez) < pc.w;
-          const unsigned mk = __ballot_sync(kFull, live);
-          if (live)
-            queue[qn + __popc(mk & lt_mask)] = static_cast<uint32_t>(lane | (p << 5));
-          qn += __popc(mk);
-          if (qn > kQueueCap - 32)
+        const int p = p0 + lane;
+        const bool have = p < h.n_pairs;
+        const float4 pc = reinterpret_cast<const float4*>(m.pairs + (have ? p : 0))[0];  // rt2 (half bits), a, b, a_off
+        const int ca = __float_as_int(pc.y), cb = __float_as_int(pc.z);
+        const __half rt2 = __ushort_as_half(static_cast<unsigned short>(__float_as_uint(pc.x)));
+        unsigned todo = mine_mask;
+        while (todo)
+        {  // chunks of 8 states: at most 256 new items, the queue's capacity
+          unsigned live_states = 0u;
+#pragma unroll 2
+          for (int it = 0; it < 8 && todo; ++it)
+          {
+            const int s = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t* rxy = rep_xy + s * rs;
+            const uint16_t* rz = rep_z + s * rs;
+            const uint32_t axy = rxy[ca], bxy = rxy[cb];
+            const uint32_t az = rz[ca], bz = rz[cb];  // zero-extended: (z, 0)
+            const __half2 d1 = __hsub2(*reinterpret_cast<const __half2*>(&axy), *reinterpret_cast<const __half2*>(&bxy));
+            const __half2 d2 = __hsub2(*reinterpret_cast<const __half2*>(&az), *reinterpret_cast<const __half2*>(&bz));
+            const __half2 sq = __hfma2(d2, d2, __hmul2(d1, d1));
+            const __half dd = __hadd(__low2half(sq), __high2half(sq));
+            if (__hlt(dd, rt2) && have)
+              live_states |= 1u << s;
+          }
+          // append (state, pair) items: exclusive scan of the per-lane counts, then every lane writes its own
+          const int cnt = __popc(live_states);
+          int pos = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
+          {
+            const int t = __shfl_up_sync(kFull, pos, d);
+            if (lane >= d)
+              pos += t;
+          }
+          const int total = __shfl_sync(kFull, pos, 31);
+          if (qn + total > kQueueCap)
             flush();
+          pos += qn - cnt;
+          while (live_states)
+          {
+            const int s = __ffs(live_states) - 1;
+            live_states &= live_states - 1;
+            queue[pos++] = static_cast<uint32_t>(s | (p << 5));
+          }
+          qn += total;
         }
       }
       if (qn > 0)
@@ -481,7 +540,7 @@ cudaError_t ensure(K kernel, size_t smem_bytes, Grant& g)
 }
 }  // namespace
 
-int fastCheckPerWarpBytes(int state_stride) { return fastPerWarpBytes(state_stride); }
+int fastCheckPerWarpBytes(int state_stride, int n_clusters) { return fastPerWarpBytes(state_stride, n_clusters); }
 int fastCheckUnroll() { return kU; }
 
 int fastCheckKernelRegs(int field_bytes)
