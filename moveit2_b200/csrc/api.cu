@@ -287,6 +287,8 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   for (const auto& L : links)
     if (L.type != FIXED && L.type != REVOLUTE && L.type != PRISMATIC)
       return false;
+  if ((int)c.robot.group_var_index.size() > fastCheckMaxVars())
+    return false;
   const int unroll = fastCheckUnroll();
   const double oo = c.grid.oo;
   const int nl = (int)links.size();
@@ -508,6 +510,11 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
     }
     fp[p] = P;
   }
+  {  // sentinel after the last link: the kernel reads link l + 1's variable index one link ahead
+    fast::Link S{};
+    S.k = -1;
+    fl.push_back(S);
+  }
   fast::Header h{};
   h.n_links = nl;
   h.n_groups = (int)fg.size();
@@ -545,6 +552,9 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   for (int k = 0; k < 3; ++k)
     h.rep_base[k] = (float)rep_base[k];
   h.rep_limit = (float)ldexp(1.0, e2);
+  for (int r = 0; r < 3; ++r)
+    h.ident[4 * r + r] = 1.f;
+
   h.pair_eps_v = (float)(pair_eps * oo);
   h.tight_eps_v = (float)(tight_eps * oo);
   c.blob_fast.assign(off, 0);
@@ -874,7 +884,7 @@ b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, 
   b200sv_ctx::LaunchCfg best;
   const int regs = ((fast ? fastCheckKernelRegs(c->compact_bytes) : checkKernelRegs(fp64, from_list, c->compact_bytes)) + 7) & ~7;
   const int reg_warps = 65536 / (regs * 32);
-  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast, c->n_bs) :
+  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast, c->n_bs, (int)c->robot.group_var_index.size()) :
                          checkPerWarpBytes(fp64, fp64 ? c->state_stride_d : c->state_stride_f);
   for (int b = 1; b <= 4; ++b)
   {
@@ -882,7 +892,7 @@ b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, 
       continue;
     const long per_block = std::min<long>(c->smem_optin, (233472L - 1024L * b) / b) - align16(blob_bytes);
     int w = per_block > 0 ? (int)(per_block / pw) : 0;
-    w = std::min(w, 16);
+    w = std::min(w, fast ? 12 : 16);  // __launch_bounds__ of the kernels
     w = std::min(w, reg_warps / b);
     if (c->tune_warps > 0)
       w = std::min(w, c->tune_warps);

@@ -185,6 +185,7 @@ struct alignas(16) Header
   float pair_eps_v, tight_eps_v, pad0, pad1;
   float rep_base[3];  // cluster centres are parked relative to this point (cells): small magnitudes for half
   float rep_limit;    // the level-1 slack assumes |centre - rep_base| < rep_limit per axis
+  float ident[12];    // identity 3x4: the "parent transform" of a root link
 };
 }  // namespace fast
 }  // namespace b200sv

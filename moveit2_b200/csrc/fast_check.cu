@@ -38,6 +38,7 @@ namespace
 {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kU = B200SV_FAST_UNROLL;  // Hot ranges are padded per link to a multiple of this (the tail chunk)
+constexpr int kMaxVars = 16;             // group variables the register prefetch covers (the host checks)
 constexpr int kP = 4;                   // gathers in flight per lane = spheres of the main chunk
 constexpr int kQueueCap = 256;          // (state, pair) work items per warp; flushed when fewer than 32 slots remain
 constexpr float kMagic = 12582912.f;    // 1.5 * 2^23: x + kMagic rounded down has floor(x) in its low mantissa bits
@@ -192,29 +193,37 @@ __device__ __forceinline__ void pairItem(const FModel& m, const float* T, unsign
 __device__ __host__ inline int repStride(int n_clusters) { return n_clusters | 1; }
 
 // Per-warp shared memory in bytes: transforms of 32 states | cluster centres (x, y) half2 [state][cluster] |
-// cluster centres z half [state][cluster] | queue | words
-__device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters)
+// cluster centres z half [state][cluster] | queue / staged states | words
+// The work queue of the pair phase and the staged states of the FK phase share one region (never live together).
+__device__ __host__ inline int queueBytes(int n_group_vars)
+{
+  const int stage = 32 * n_group_vars * 8;
+  return stage > kQueueCap * 4 ? stage : kQueueCap * 4;
+}
+
+__device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters, int n_group_vars)
 {
   const int rs = repStride(n_clusters);
-  return 32 * state_stride * 4 + 32 * rs * 4 + ((32 * rs * 2 + 15) & ~15) + kQueueCap * 4 + 16;
+  return 32 * state_stride * 4 + 32 * rs * 4 + ((32 * rs * 2 + 15) & ~15) + queueBytes(n_group_vars) + 16;
 }
 
 // Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
 template <typename FT>
-__global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
+__global__ void __launch_bounds__(384, 1) fastCheckKernel(CheckArgs<FT> a)
 {
   using Elem = typename Cmp<FT>::Elem;
   extern __shared__ __align__(16) uint8_t smem[];
   const FModel m = loadFast(a.model, a.model_bytes, smem);
   const fast::Header& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * fastPerWarpBytes(h.state_stride, h.n_clusters);
+  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * fastPerWarpBytes(h.state_stride, h.n_clusters, h.n_group_vars);
   float* Ts = reinterpret_cast<float*>(wbase);
   const int rs = repStride(h.n_clusters);
   uint32_t* rep_xy = reinterpret_cast<uint32_t*>(Ts + 32 * h.state_stride);  // [state][cluster] half2 (x, y)
   uint16_t* rep_z = reinterpret_cast<uint16_t*>(rep_xy + 32 * rs);           // [state][cluster] half z
   uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_z) + ((32 * rs * 2 + 15) & ~15));
-  unsigned* words = reinterpret_cast<unsigned*>(queue + kQueueCap);  // [0] hit, [1] amb
+  double* stage = reinterpret_cast<double*>(queue);  // the tile's states [state][var], FK phase only
+  unsigned* words = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(queue) + queueBytes(h.n_group_vars));  // [0] hit, [1] amb
   const bool do_fields = (a.flags & 3u) != 0, do_intra = (a.flags & 4u) != 0;
   const unsigned fmask = ((a.flags & 1u) ? 0x0000ffffu : 0u) | ((a.flags & 2u) ? 0xffff0000u : 0u);
   const Elem* __restrict__ field = static_cast<const Elem*>(a.field);
@@ -226,24 +235,40 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
 
   const unsigned long long n = a.n_states;
   const unsigned long long n_tiles = (n + 31) / 32;
-  for (unsigned long long tile = static_cast<unsigned long long>(blockIdx.x) * warps + warp; tile < n_tiles;
-       tile += static_cast<unsigned long long>(gridDim.x) * warps)
+  const int V = h.n_group_vars;
+  // The states of a tile are ONE contiguous run of 32 * V doubles: every lane reads V of them, coalesced, one tile
+  // AHEAD (they stream from HBM exactly once), and parks them in shared memory when their tile starts.
+  double qn[kMaxVars];
+  auto fetchTile = [&](unsigned long long t) {
+    const double* __restrict__ src = a.q + t * 32 * V;
+    const unsigned long long left = n - t * 32;
+    const int avail = static_cast<int>(left < 32 ? left : 32) * V;
+#pragma unroll
+    for (int j = 0; j < kMaxVars; ++j)
+    {
+      const int e = j * 32 + lane;
+      qn[j] = (j < V && e < avail) ? __ldg(src + e) : 0.0;
+    }
+  };
+  const unsigned long long tile0 = static_cast<unsigned long long>(blockIdx.x) * warps + warp;
+  if (tile0 < n_tiles)
+    fetchTile(tile0);
+  for (unsigned long long tile = tile0; tile < n_tiles; tile += static_cast<unsigned long long>(gridDim.x) * warps)
   {
+#pragma unroll
+    for (int j = 0; j < kMaxVars; ++j)
+      if (j < V)
+        stage[j * 32 + lane] = qn[j];
+    __syncwarp();
+    {
+      const unsigned long long nt = tile + static_cast<unsigned long long>(gridDim.x) * warps;
+      if (nt < n_tiles)
+        fetchTile(nt);
+    }
     const unsigned long long first = tile * 32;
     const int cnt = static_cast<int>(n - first < 32 ? n - first : 32);
     const bool active = lane < cnt;
-    const unsigned long long my_state = first + (active ? lane : 0);  // idle lanes shadow lane 0; result dropped
-    const double* __restrict__ qrow = a.q + my_state * h.n_group_vars;
-    {  // the states of this warp's NEXT tile: pull their lines into L2 now (they stream from HBM exactly once)
-      const unsigned long long nt = tile + static_cast<unsigned long long>(gridDim.x) * warps;
-      if (nt < n_tiles)
-      {
-        const unsigned long long ns = nt * 32 + lane < n ? nt * 32 + lane : n - 1;
-        const char* pq = reinterpret_cast<const char*>(a.q + ns * h.n_group_vars);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pq));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pq + h.n_group_vars * 8 - 1));
-      }
-    }
+    const double* qrow = stage + (active ? lane : 0) * V;
     unsigned hacc = 0u, aacc = 0u;  // nonzero: certainly colliding / FP32 cannot decide
     unsigned pv[kP], pt[kP];      // gathers in flight: field element, thresholds
 #pragma unroll
@@ -291,11 +316,16 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
       }
 #pragma unroll
       for (int u = 0; u < N; ++u)
+      {
+        // the gathers of the previous chunk are consumed as late as possible: not before this chunk's indices exist
+        asm volatile("" : "+r"(pv[u]) : "r"(idx[u]));
         hacc |= Cmp<FT>::hit(pv[u], pt[u]);
+      }
 #pragma unroll
       for (int u = 0; u < N; ++u)
       {
-        pv[u] = __ldg(field + idx[u]);
+        // nothing to learn for padding / parked spheres, nor for a state that already collides: no L1 wavefront
+        pv[u] = (tt[u] != Cmp<FT>::kNever && hacc == 0u) ? __ldg(field + idx[u]) : 0u;
         pt[u] = tt[u];
       }
       if (rmask)
@@ -319,24 +349,32 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
       }
     };
     float T[12];
+    int4 n0 = reinterpret_cast<const int4*>(m.links)[0], n1 = reinterpret_cast<const int4*>(m.links)[1];
+    double2 nab = reinterpret_cast<const double2*>(m.links)[2];
+    float4 no = reinterpret_cast<const float4*>(m.links)[3];
+    double q_next = n0.y >= 0 ? qrow[n0.y] : 0.0;
     // ---- FK, and the field checks of every link as soon as its transform exists --------------------------------------
     for (int l = 0; l < h.n_links; ++l)
     {
       const int4* Li = reinterpret_cast<const int4*>(m.links + l);
       const float4* Lf = reinterpret_cast<const float4*>(m.links + l);
-      const int4 m0 = Li[0];  // type, k, parent_off, store_off
-      const int4 m1 = Li[1];  // h0, h1, c0, c1
-      const float4 o = Lf[3];
+      const int4 m0 = n0;  // type, k, parent_off, store_off     (read one link ahead: the type branch never waits)
+      const int4 m1 = n1;  // h0, h1, c0, c1
+      const double2 ab = nab;
+      const float4 o = no;
+      n0 = Li[11];  // the table ends with a sentinel record
+      n1 = Li[12];
+      nab = reinterpret_cast<const double2*>(Li)[13];
+      no = Lf[14];
       const float4 c0 = Lf[4], c1 = Lf[5], c2 = Lf[6];  // a0[0..8], a1[0..2]
       float M[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x };
       float mt[3] = { o.x, o.y, o.z };
+      const double q_cur = q_next;
+      q_next = n0.y >= 0 ? qrow[n0.y] : 0.0;  // the NEXT link's joint value
       if (m0.x != FIXED)
       {
-        const double2 ab = reinterpret_cast<const double2*>(m.links + l)[2];
-        double v = ab.y;
-        if (m0.y >= 0)
-          v = ab.x * qrow[m0.y] + ab.y;  // setJointGroupPositions / updateMimicJoints in double, then narrowed
-        const float qf = static_cast<float>(v);
+        // setJointGroupPositions / updateMimicJoints in double, then narrowed (k < 0: a = 0, the value is b)
+        const float qf = static_cast<float>(ab.x * q_cur + ab.y);
         if (m0.x == REVOLUTE)
         {
           const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];  // a1[3..8], a2[0..8]
@@ -356,30 +394,17 @@ __global__ void __launch_bounds__(512, 1) fastCheckKernel(CheckArgs<FT> a)
           mt[2] = fmaf(qf, c2.w, mt[2]);
         }
       }
-      if (m0.z == fast::kParentRoot)
-      {
+      // T = T_parent * [M | mt]; a root's "parent" is the identity block of the header (one code path, no merge)
+      if (m0.z != fast::kParentPrev)
+        load12(m0.z == fast::kParentRoot ? h.ident : T_state + m0.z, T);
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-        {
-          T[4 * r + 0] = M[3 * r + 0];
-          T[4 * r + 1] = M[3 * r + 1];
-          T[4 * r + 2] = M[3 * r + 2];
-          T[4 * r + 3] = mt[r];
-        }
-      }
-      else
+      for (int r = 0; r < 3; ++r)
       {
-        if (m0.z >= 0)
-          load12(T_state + m0.z, T);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-        {
-          const float p0 = T[4 * r + 0], p1 = T[4 * r + 1], p2 = T[4 * r + 2];
-          T[4 * r + 0] = fmaf(p0, M[0], fmaf(p1, M[3], p2 * M[6]));
-          T[4 * r + 1] = fmaf(p0, M[1], fmaf(p1, M[4], p2 * M[7]));
-          T[4 * r + 2] = fmaf(p0, M[2], fmaf(p1, M[5], p2 * M[8]));
-          T[4 * r + 3] = fmaf(p0, mt[0], fmaf(p1, mt[1], fmaf(p2, mt[2], T[4 * r + 3])));
-        }
+        const float p0 = T[4 * r + 0], p1 = T[4 * r + 1], p2 = T[4 * r + 2];
+        T[4 * r + 0] = fmaf(p0, M[0], fmaf(p1, M[3], p2 * M[6]));
+        T[4 * r + 1] = fmaf(p0, M[1], fmaf(p1, M[4], p2 * M[7]));
+        T[4 * r + 2] = fmaf(p0, M[2], fmaf(p1, M[5], p2 * M[8]));
+        T[4 * r + 3] = fmaf(p0, mt[0], fmaf(p1, mt[1], fmaf(p2, mt[2], T[4 * r + 3])));
       }
       if (m0.w >= 0)
         store12(T_state + m0.w, T);
@@ -540,7 +565,11 @@ cudaError_t ensure(K kernel, size_t smem_bytes, Grant& g)
 }
 }  // namespace
 
-int fastCheckPerWarpBytes(int state_stride, int n_clusters) { return fastPerWarpBytes(state_stride, n_clusters); }
+int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars)
+{
+  return fastPerWarpBytes(state_stride, n_clusters, n_group_vars);
+}
+int fastCheckMaxVars() { return kMaxVars; }
 int fastCheckUnroll() { return kU; }
 
 int fastCheckKernelRegs(int field_bytes)

@@ -55,7 +55,8 @@ int checkPerWarpBytes(bool fp64, int state_stride);  // shared memory one warp o
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 int fastCheckKernelRegs(int field_bytes);
-int fastCheckPerWarpBytes(int state_stride, int n_clusters);
+int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars);
+int fastCheckMaxVars();
 int fastCheckUnroll();
 cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_bytes, cudaStream_t stream);
