@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-edt", action="store_true", help="skip the C4 EDT rebuild measurement")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against the oracle")
     ap.add_argument("--fp64", action="store_true", help="force every state through the FP64 kernel")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["C2", "C3"],
+                    help="C2 (default, the config the metric is quoted on) or C3 (dual-arm, 10 M states over all ranks)")
     return ap.parse_args()
 
 
@@ -114,7 +116,7 @@ def oracle_env(cfg, cloud):
     return env
 
 
-def cpu_rate(env, q, seconds=4.0):
+def cpu_rate(env, q, seconds=10.0):
     """states/s of the oracle port on all host threads, on a bounded sample sized for ~`seconds` of wall time."""
     n0 = min(len(q), 20000)
     t = time.perf_counter()
@@ -137,8 +139,8 @@ def run_reference(args):
     from moveit2_b200 import workloads
     import oracle
     oracle.build(force=True)
-    cfg = workloads.CONFIGS[WORKLOAD]
-    cloud = workloads.make_cloud(WORKLOAD)
+    cfg = workloads.CONFIGS[args.workload]
+    cloud = workloads.make_cloud(args.workload)
     env = oracle_env(cfg, cloud)
     lo, hi = env.joint_bounds()
     n_full = args.states or cfg["states"]["n"]
@@ -155,8 +157,9 @@ def run_reference(args):
     line = {"metric": METRIC, "value": rate, "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "C2: Panda panda_arm, %d states/step (bounded sample of 1M), 500k-point clutter cloud, "
-                                   "2 m^3 field @ 1 cm" % sample},
+            "config": {"workload": "%s: %s %s, %d states/step (bounded sample of the batch), %d-point clutter cloud, "
+                                   "%g m field edge @ %g m" % (args.workload, cfg["robot"], cfg["group"], sample, len(cloud),
+                                                               cfg["size"][0], cfg["resolution"])},
             "cpu_baseline": {"value": rate, "unit": "states/s", "cores": used, "kind": "port",
                              "sample": "%d states per step, lean flavour (centre voxel only), OpenMP" % sample},
             "e2e": {"value": rate, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -182,12 +185,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    cfg = workloads.CONFIGS[WORKLOAD]
-    n = args.states or cfg["states"]["n"]
+    cfg = workloads.CONFIGS[args.workload]
+    n = args.states or (cfg["states"]["n"] if args.workload == "C2" else cfg["states"]["n"] // world)
     eng = mb.StateValidityEngine.for_robot(cfg["robot"], cfg["group"], size=cfg["size"], origin=cfg["origin"],
                                            resolution=cfg["resolution"], max_distance=cfg["max_distance"], device=local)
     V, S = eng.n_group_vars, eng.n_spheres
-    cloud = workloads.make_cloud(WORKLOAD)                     # replicated scene: every rank builds the same field
+    cloud = workloads.make_cloud(args.workload)                # replicated scene: every rank builds the same field
     eng.field_add_points(cloud)
     edt_ms_c2 = eng.stats()["edt_ms"]
     lo, hi = eng.group_bounds()
@@ -277,8 +280,13 @@ def main():
         "metric": METRIC, "value": value, "unit": "states/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.fp64 else "f32", "data": "synthetic",
-        "config": {"workload": "C2: Panda panda_arm (7 DoF, %d spheres), %d states per GPU per step, 500k-point clutter "
-                               "cloud, 2 m^3 field @ 1 cm (200^3 voxels; world+self uint8 d^2 interleaved, 16 MB), checks world+self+intra" % (S, n),
+        "config": {"workload": "%s: %s %s (%d DoF, %d spheres), %d states per GPU per step, %d-point clutter cloud, "
+                               "%g x %g x %g m field @ %g m (%d x %d x %d voxels; world+self uint%d d^2 interleaved, %.0f MB), "
+                               "checks world+self+intra" % (args.workload, cfg["robot"], cfg["group"], V, S, n, len(cloud),
+                                                            cfg["size"][0], cfg["size"][1], cfg["size"][2], cfg["resolution"],
+                                                            eng.num_cells[0], eng.num_cells[1], eng.num_cells[2],
+                                                            8 * eng.info.field_bytes_per_voxel,
+                                                            2e-6 * eng.info.field_bytes_per_voxel * eng.num_cells[0] * eng.num_cells[1] * eng.num_cells[2]),
                    "l2": "flushed between timed steps (256 MiB write)", "fp32_pass_with_fp64_recheck": not args.fp64,
                    "valid_fraction": valid_frac, "rechecked_states_per_step": st["n_rechecked"],
                    "sharding": "states sharded contiguously (moveit2_b200/sharding.py), fields replicated, one NCCL "
@@ -288,8 +296,13 @@ def main():
                 "ms_per_step": 1e3 * e2e_s / args.steps, "kernel_ms_inside": e2e_kernel_ms},
         "gpu_launches": 2 * args.steps if not args.fp64 else args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_state": b_state,
-                     "kernel": "checkKernel<float,uint8_t,false> (+ FP64 recheck launch)"},
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch over 1 M states, from the committed
+                     # ncu --set full capture (profiles/r1_fast_v6_summary.txt: 65.54 MB + 1.09 MB), scaled to n: the
+                     # 16 MB field is L2-resident, so DRAM only sees the states streaming in once
+                     "traffic": 66.63 * n if args.workload == "C2" else None,
+                     "traffic_source": "profiles/r1_fast_v6_summary.txt (ncu --set full, 1 launch)",
+                     "peak_source": peak_src, "algorithmic_bytes_per_state": b_state,
+                     "kernel": "fastCheckKernel<uint8_t> (+ FP64 recheck launch checkKernel<double,uint8_t,true>)"},
         "gather_roofline": {"achieved": gather_achieved, "peak": gather_gbs, "unit": "GB/s (32 B sectors)",
                             "frac": gather_achieved / gather_gbs,
                             "how": "b200sv_gather_roofline: random 32 B sector reads over the same 16 MB field footprint"},

@@ -78,7 +78,7 @@ struct b200sv_ctx
   bool fast_disabled = false;  // B200SV_FAST=0: force the generic FP32 kernel (A/B measurements)
   int state_stride_fast = 0;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
-  double cluster_radius = 0.12;  // max tight-sphere radius of a sphere cluster (m)
+  double cluster_radius = 0.2;   // max tight-sphere radius of a sphere cluster (m); clusters also hold <= 4 spheres
   int state_stride_f = 0, state_stride_d = 0;  // shared-memory words per state (float / double blob)
   std::vector<int> link_slot;      // model link -> device slot
   std::vector<double> const_T;     // model links * 16 (base state)
