@@ -46,46 +46,6 @@ __global__ void scatterKernel(const double* __restrict__ xyz, size_t n, GridDev 
   }
 }
 
-// distance (in cells) from z to the nearest set bit of `row` within +-R; R + 1 if there is none
-__device__ __forceinline__ int zDistance(const uint32_t* row, int wz, int z, int R)
-{
-  const int w = z >> 5, b = z & 31;
-  int best = R + 1;
-  const uint32_t cur = row[w] >> b;
-  if (cur)
-    best = __ffs(cur) - 1;
-  else
-  {
-    int off = 32 - b;
-    for (int ww = w + 1; ww < wz && off <= R; ++ww, off += 32)
-    {
-      const uint32_t v = row[ww];
-      if (v)
-      {
-        best = off + __ffs(v) - 1;
-        break;
-      }
-    }
-  }
-  const uint32_t low = b ? (row[w] & ((1u << b) - 1u)) : 0u;
-  if (low)
-    best = min(best, b - (31 - __clz(low)));
-  else
-  {
-    int off = b + 1;
-    for (int ww = w - 1; ww >= 0 && off <= R; --ww, off += 32)
-    {
-      const uint32_t v = row[ww];
-      if (v)
-      {
-        best = min(best, off + __clz(v));
-        break;
-      }
-    }
-  }
-  return min(best, R + 1);
-}
-
 // One CTA per (x plane, y chunk).  Shared memory: occupancy words of rows [y0-R, y1+R), then their z distances
 // (row stride nzp = nz rounded up to 4 so a thread can take 4 consecutive z with one 32-bit access).
 __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
@@ -104,10 +64,61 @@ __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __
     bits[i] = (y >= 0 && y < g.ny) ? occ[(static_cast<size_t>(x) * g.ny + y) * g.wz + (i % g.wz)] : 0u;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < rows * nzp; i += blockDim.x)
+  // z pass, one thread per 32-bit occupancy word: the distance of the word's two ends to the nearest set bit outside
+  // it (clz / ffs on the neighbouring words), then one forward and one backward sweep over its 32 bits
   {
-    const int r = i / nzp, z = i - r * nzp;
-    gz[i] = z < g.nz ? static_cast<uint8_t>(zDistance(bits + r * g.wz, g.wz, z, g.R)) : static_cast<uint8_t>(g.R + 1);
+    const int cap = g.R + 1;
+    for (int i = threadIdx.x; i < rows * g.wz; i += blockDim.x)
+    {
+      const int r = i / g.wz, w = i - r * g.wz;
+      const uint32_t* row = bits + r * g.wz;
+      const uint32_t cur = row[w];
+      int dl = cap, dr = cap;  // distance of bit 0 / bit 31 to the nearest set bit in the words below / above
+      for (int ww = w - 1, off = 1; ww >= 0 && off <= g.R; --ww, off += 32)
+      {
+        const uint32_t v = row[ww];
+        if (v)
+        {
+          dl = min(cap, off + __clz(v));
+          break;
+        }
+      }
+      for (int ww = w + 1, off = 1; ww < g.wz && off <= g.R; ++ww, off += 32)
+      {
+        const uint32_t v = row[ww];
+        if (v)
+        {
+          dr = min(cap, off + __ffs(v) - 1);
+          break;
+        }
+      }
+      uint32_t f[8];
+      int d = dl - 1;
+#pragma unroll
+      for (int b = 0; b < 32; ++b)
+      {
+        d = ((cur >> b) & 1u) ? 0 : min(d + 1, cap);
+        if ((b & 3) == 0)
+          f[b >> 2] = static_cast<uint32_t>(d);
+        else
+          f[b >> 2] |= static_cast<uint32_t>(d) << (8 * (b & 3));
+      }
+      d = dr - 1;
+#pragma unroll
+      for (int b = 31; b >= 0; --b)
+      {
+        d = ((cur >> b) & 1u) ? 0 : min(d + 1, cap);
+        const uint32_t sh = 8 * (b & 3);
+        const uint32_t fw = (f[b >> 2] >> sh) & 0xffu;
+        if (static_cast<uint32_t>(d) < fw)
+          f[b >> 2] = (f[b >> 2] & ~(0xffu << sh)) | (static_cast<uint32_t>(d) << sh);
+      }
+      uint32_t* dst = reinterpret_cast<uint32_t*>(gz + r * nzp + w * 32);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (w * 32 + 4 * k < nzp)
+          dst[k] = f[k];  // bytes at z >= nz (occupancy bits there are 0) are never read as centres, only as padding
+    }
   }
   __syncthreads();
   const int R = g.R, max_d2 = g.max_d2;
