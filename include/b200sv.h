@@ -190,6 +190,26 @@ int b200sv_check_batch(b200sv_ctx* ctx, const double* q, size_t n_states, uint32
  * d_valid_bitmap must hold 4*ceil(n/32) bytes (whole 32-bit words are written). */
 int b200sv_check_batch_device(b200sv_ctx* ctx, const double* d_q, size_t n_states, uint32_t flags,
                               uint8_t* d_valid_bitmap, void* cuda_stream);
+/* Batched edge ("motion") validation -- new; the consumer is ompl::base::MotionValidator::checkMotion as MoveIt
+ * configures it (DiscreteMotionValidator over ModelBasedStateSpace; longest_valid_segment_fraction:
+ * moveit_planners/ompl/ompl_interface/src/model_based_planning_context.cpp:294-317).  For edge e the states checked are
+ * JointModelGroup::interpolate(from, to, j / nd) (robot_model/src/joint_model_group.cpp:474-486; continuous revolute
+ * joints along the shorter arc, revolute_joint_model.cpp:138-171) for j = 1 .. nd - 1, then `to` itself, with
+ * nd = ceil(JointModelGroup::distance(from, to) / max_segment_length) (:462-472; max_segment_length =
+ * longest_valid_segment_fraction * JointModelGroup::getMaximumExtent, :451-460).  `from` is assumed valid, as OMPL does.
+ *   var_continuous        [n_group_vars] 1 for the variable of a continuous revolute joint; NULL = none
+ *   var_distance_factor   [n_group_vars] JointModel::getDistanceFactor of the variable's joint, 0 for variables that
+ *                         are not active (mimic); NULL = all 1
+ *   max_states_per_edge   0 = no cap; otherwise an edge is checked at no more than this many states
+ *   valid_bitmap          ceil(n_edges / 8) bytes, bit e = 1 iff every checked state of edge e is collision-free
+ *   first_invalid         [n_edges] or NULL: j of the first colliding state (1 .. nd, nd = `to`), -1 if the edge is valid
+ *   n_states_checked      or NULL: total states the call expanded to and checked
+ * OMPL is not vendored in the reference tree (moveit_planners/ompl/package.xml:25, no version pin): the discretisation
+ * follows its published algorithm; parity for it is pinned by this repository's own tests only. */
+int b200sv_check_motions(b200sv_ctx* ctx, const double* q_from, const double* q_to, size_t n_edges,
+                         double max_segment_length, const uint8_t* var_continuous, const double* var_distance_factor,
+                         uint32_t max_states_per_edge, uint32_t flags, uint8_t* valid_bitmap, int32_t* first_invalid,
+                         uint64_t* n_states_checked);
 /* Posed collision-sphere centres of ONE state, FP64 kernel: [n_spheres*3] (host).  Parity hook for
  * PosedBodySphereDecomposition::updatePose (collision_distance_field_types.cpp:388-395). */
 int b200sv_sphere_centers(b200sv_ctx* ctx, const double* q_one, double* centers);

@@ -84,6 +84,8 @@ def load():
         "b200sv_check_batch": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp]),
         "b200sv_check_batch_device": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp, vp]),
         "b200sv_sphere_centers": (C.c_int, [vp, dp, dp]),
+        "b200sv_check_motions": (C.c_int, [vp, dp, dp, C.c_size_t, C.c_double, u8p, dp, C.c_uint32, C.c_uint32, u8p,
+                                           ip, C.POINTER(C.c_uint64)]),
         "b200sv_gather_roofline": (C.c_int, [vp, C.c_size_t, C.c_int, dp]),
         "b200sv_set_tuning": (C.c_int, [vp, C.c_double, C.c_int, C.c_int]),
     }

@@ -108,6 +108,13 @@ struct b200sv_ctx
   DevBuf<double> d_points;
   DevBuf<double> d_fk;
   DevBuf<int32_t> d_i32;
+  // batched edge validation
+  DevBuf<double> d_edges, d_edge_q, d_edge_aux;
+  DevBuf<unsigned> d_edge_count;
+  DevBuf<unsigned long long> d_edge_offset;
+  DevBuf<uint32_t> d_edge_state_bits, d_edge_bits;
+  DevBuf<int32_t> d_edge_first;
+  DevBuf<uint8_t> d_edge_cont;
   unsigned* d_count = nullptr;
   unsigned* d_sink = nullptr;
   b200sv_stats stats{};
@@ -1317,6 +1324,9 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->d_blob_f) cudaFree(c->d_blob_f);
   if (c->d_blob_d) cudaFree(c->d_blob_d);
   if (c->d_blob_fast) cudaFree(c->d_blob_fast);
+  c->d_edges.release(); c->d_edge_q.release(); c->d_edge_aux.release(); c->d_edge_count.release();
+  c->d_edge_offset.release(); c->d_edge_state_bits.release(); c->d_edge_bits.release(); c->d_edge_first.release();
+  c->d_edge_cont.release();
   if (c->d_link_slot) cudaFree(c->d_link_slot);
   if (c->d_const_T) cudaFree(c->d_const_T);
   if (c->d_count) cudaFree(c->d_count);
@@ -1689,6 +1699,85 @@ int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags,
     valid += __builtin_popcount(valid_bitmap[i]);
   c->stats.n_states = n;
   c->stats.n_valid = valid;
+  c->stats.n_rechecked = (flags & B200SV_CHECK_FP64) ? 0 : cnt;
+  c->stats.check_ms = ms;
+  c->stats_pending = false;
+  return B200SV_OK;
+}
+
+int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to, size_t n_edges, double max_segment_length,
+                         const uint8_t* var_continuous, const double* var_distance_factor, uint32_t max_states_per_edge,
+                         uint32_t flags, uint8_t* valid_bitmap, int32_t* first_invalid, uint64_t* n_states_checked)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (n_edges && (!q_from || !q_to || !valid_bitmap))
+    return fail(c, B200SV_ERR_INVALID, "null host pointer");
+  if (!(max_segment_length > 0.0))
+    return fail(c, B200SV_ERR_INVALID, "max_segment_length must be positive");
+  if ((flags & 7u) == 0)
+    return fail(c, B200SV_ERR_INVALID, "flags select no check");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (n_states_checked)
+    *n_states_checked = 0;
+  if (n_edges == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t V = c->robot.group_var_index.size();
+  cudaStream_t s = c->stream;
+  CU(c, c->d_edges.ensure(2 * n_edges * V));
+  CU(c, c->d_edge_count.ensure(n_edges));
+  CU(c, c->d_edge_offset.ensure(n_edges + 1));
+  CU(c, c->d_edge_aux.ensure(V));
+  CU(c, c->d_edge_cont.ensure(V));
+  CU(c, c->d_edge_bits.ensure((n_edges + 31) / 32));
+  CU(c, c->d_edge_first.ensure(n_edges));
+  CU(c, cudaEventRecord(c->ev0, s));
+  CU(c, cudaMemcpyAsync(c->d_edges.p, q_from, n_edges * V * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(c, cudaMemcpyAsync(c->d_edges.p + n_edges * V, q_to, n_edges * V * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (var_distance_factor)
+    CU(c, cudaMemcpyAsync(c->d_edge_aux.p, var_distance_factor, V * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (var_continuous)
+    CU(c, cudaMemcpyAsync(c->d_edge_cont.p, var_continuous, V, cudaMemcpyHostToDevice, s));
+  MotionArgs a{};
+  a.q_from = c->d_edges.p;
+  a.q_to = c->d_edges.p + n_edges * V;
+  a.n_edges = n_edges;
+  a.n_vars = (int)V;
+  a.continuous = var_continuous ? c->d_edge_cont.p : nullptr;
+  a.factor = var_distance_factor ? c->d_edge_aux.p : nullptr;
+  a.max_segment = max_segment_length;
+  a.max_states_per_edge = max_states_per_edge;
+  a.count = c->d_edge_count.p;
+  a.offset = c->d_edge_offset.p;
+  CU(c, launchMotionCount(a, s));
+  unsigned long long total = 0;
+  CU(c, cudaMemcpyAsync(&total, c->d_edge_offset.p + n_edges, sizeof(total), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));  // the state batch is sized by the edges' lengths
+  if (total >= (1ull << 32))
+    return fail(c, B200SV_ERR_INVALID, "edges expand to more than 2^32 - 1 states; lower n_edges or set max_states_per_edge");
+  CU(c, c->d_edge_q.ensure((size_t)total * V));
+  CU(c, c->d_edge_state_bits.ensure((size_t)(total + 31) / 32));
+  CU(c, launchMotionExpand(a, c->d_edge_q.p, total, s));
+  int rc = checkDevice(c, c->d_edge_q.p, (size_t)total, flags, c->d_edge_state_bits.p, s);
+  if (rc != B200SV_OK)
+    return rc;
+  CU(c, launchMotionReduce(a, c->d_edge_state_bits.p, c->d_edge_bits.p, first_invalid ? c->d_edge_first.p : nullptr, s));
+  CU(c, cudaEventRecord(c->ev1, s));
+  CU(c, cudaMemcpyAsync(valid_bitmap, c->d_edge_bits.p, (n_edges + 7) / 8, cudaMemcpyDeviceToHost, s));
+  if (first_invalid)
+    CU(c, cudaMemcpyAsync(first_invalid, c->d_edge_first.p, n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  unsigned cnt = 0;
+  CU(c, cudaMemcpyAsync(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  if (n_states_checked)
+    *n_states_checked = total;
+  c->stats.n_states = total;
+  c->stats.n_valid = 0;
   c->stats.n_rechecked = (flags & B200SV_CHECK_FP64) ? 0 : cnt;
   c->stats.check_ms = ms;
   c->stats_pending = false;

@@ -63,6 +63,25 @@ cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_
 cudaError_t launchGather(const uint8_t* field, unsigned long long n_sectors, int per_thread, int grid, int block,
                          unsigned* sink, cudaStream_t stream);
 
+// ---- batched edge validation (motion_kernels.cu) ------------------------------------------------------------
+struct MotionArgs
+{
+  const double* q_from;  // [n_edges * n_vars] device
+  const double* q_to;
+  size_t n_edges;
+  int n_vars;
+  const uint8_t* continuous;  // [n_vars] or null
+  const double* factor;       // [n_vars] JointModel::getDistanceFactor, 0 for variables of mimic joints; or null (all 1)
+  double max_segment;         // longest valid segment = fraction * maximum extent
+  unsigned max_states_per_edge;
+  unsigned* count;            // [n_edges] states checked per edge
+  unsigned long long* offset; // [n_edges + 1] exclusive scan of count
+};
+cudaError_t launchMotionCount(const MotionArgs& a, cudaStream_t s);  // count + scan
+cudaError_t launchMotionExpand(const MotionArgs& a, double* d_q, unsigned long long n_states, cudaStream_t s);
+cudaError_t launchMotionReduce(const MotionArgs& a, const uint32_t* state_bits, uint32_t* edge_bits, int32_t* first_invalid,
+                               cudaStream_t s);
+
 // ---- distance field ------------------------------------------------------------------------------------
 struct GridDev
 {

@@ -264,6 +264,26 @@ class StateValidityEngine:
         self._check(self.L.b200sv_check_batch_device(self.h, C.c_void_p(d_q_ptr), n, int(flags),
                                                      C.c_void_p(d_bitmap_ptr), C.c_void_p(stream)))
 
+    def check_motions(self, q_from, q_to, max_segment_length, continuous=None, distance_factor=None,
+                      max_states_per_edge=0, flags=CHECK_ALL):
+        """Batched edge validation (b200sv_check_motions): (valid bool [M], first_invalid int32 [M], n_states)."""
+        V = self.n_group_vars
+        a = np.ascontiguousarray(q_from, np.float64).reshape(-1, V)
+        b = np.ascontiguousarray(q_to, np.float64).reshape(-1, V)
+        if a.shape != b.shape:
+            raise ValueError("q_from and q_to differ in shape")
+        m = a.shape[0]
+        bm = np.zeros((m + 7) // 8 + 1, np.uint8)
+        first = np.full(max(m, 1), -1, np.int32)
+        cont = None if continuous is None else np.ascontiguousarray(continuous, np.uint8).reshape(V)
+        fac = None if distance_factor is None else np.ascontiguousarray(distance_factor, np.float64).reshape(V)
+        n = C.c_uint64(0)
+        self._check(self.L.b200sv_check_motions(self.h, _dp(a), _dp(b), m, float(max_segment_length),
+                                                _u8p(cont) if cont is not None else None,
+                                                _dp(fac) if fac is not None else None, int(max_states_per_edge),
+                                                int(flags), _u8p(bm), _ip(first), C.byref(n)))
+        return np.unpackbits(bm, bitorder="little")[:m].astype(bool), first[:m], int(n.value)
+
     def gather_roofline(self, n_reads=1 << 28, iters=3):
         g = C.c_double(0.0)
         self._check(self.L.b200sv_gather_roofline(self.h, n_reads, iters, C.byref(g)))

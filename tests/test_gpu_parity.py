@@ -309,3 +309,65 @@ def test_device_resident_entry_point(c1):
 
 def test_gather_roofline_runs(c1):
     assert c1[0].gather_roofline(1 << 24, 2) > 1.0
+
+
+# ---- batched edge validation ---------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("fraction", [0.01, 0.002])
+def test_check_motions_equals_oracle_edge_by_edge(c1, fraction):
+    from oracle import motion
+    eng, env, cloud, q = c1
+    lo, hi = eng.group_bounds()
+    L = fraction * float(np.sum(hi - lo))
+    rng = np.random.default_rng(7)
+    m = 1500
+    a = q[:m]
+    # a mix of long edges (random targets) and short ones (RRT-style steps), plus a zero-length edge
+    b = np.where(rng.random((m, 1)) < 0.5, rng.uniform(lo, hi, size=(m, len(lo))), a + rng.normal(0, 0.05, size=(m, len(lo))))
+    b = np.clip(b, lo, hi)
+    b[0] = a[0]
+    valid, first, n = eng.check_motions(a, b, L)
+    rv, rf, rn = motion.check_motions(env, a, b, L)
+    assert n == rn
+    assert np.array_equal(valid, rv)
+    assert np.array_equal(first, rf)
+    assert 0 < valid.sum() < m
+
+
+@pytest.mark.gpu
+def test_check_motions_continuous_joints_and_cap(c1):
+    from oracle import motion
+    eng, env, cloud, q = c1
+    lo, hi = eng.group_bounds()
+    V = len(lo)
+    cont = np.zeros(V, np.uint8)
+    cont[0] = 1  # treat joint 1 as continuous: edges across +-pi take the short way round
+    fac = np.ones(V)
+    fac[3] = 0.0  # and one variable as passive (no contribution to the distance)
+    rng = np.random.default_rng(8)
+    m = 400
+    a = rng.uniform(lo, hi, size=(m, V))
+    b = rng.uniform(lo, hi, size=(m, V))
+    a[:, 0] = rng.uniform(-np.pi, np.pi, m)
+    b[:, 0] = rng.uniform(-np.pi, np.pi, m)
+    L = 0.01 * float(np.sum(hi - lo))
+    for cap in (0, 5):
+        valid, first, n = eng.check_motions(a, b, L, cont, fac, cap)
+        rv, rf, rn = motion.check_motions(env, a, b, L, cont, fac, cap)
+        assert n == rn and np.array_equal(valid, rv) and np.array_equal(first, rf)
+
+
+@pytest.mark.gpu
+def test_motion_validator_mirror(c1):
+    from moveit2_b200.ompl_interface import ModelBasedStateSpace, MotionValidator, StateValidityChecker
+    eng, env, cloud, q = c1
+    lo, hi = eng.group_bounds()
+    space = ModelBasedStateSpace(lo, hi)
+    svc, mv = StateValidityChecker(eng, space), MotionValidator(eng, space)
+    ok = svc.isValidBatch(q[:256])
+    assert svc.isValid(q[0]) == bool(ok[0])
+    starts = q[:256][ok]
+    valid, frac = mv.checkMotions(starts[:-1], starts[1:])
+    assert mv.checkMotion(starts[0], starts[1]) == bool(valid[0])
+    assert np.all(frac[valid] == 1.0) and np.all(frac[~valid] < 1.0)
+    assert not svc.isValid(hi + 1.0)  # out of bounds is invalid before any collision check

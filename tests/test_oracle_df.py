@@ -156,3 +156,18 @@ def test_propagation_matches_exact_edt_dense():
     exact = np.minimum(np.rint(exact).astype(np.int64), df.max_distance_sq)
     assert (d2 >= exact).all()
     assert (d2 != exact).sum() <= 2
+
+
+def test_motion_restatement_discretisation():
+    """oracle/motion.py against hand-computed cases of validSegmentCount / interpolate (OMPL's published algorithm)."""
+    from oracle import motion
+    a, b = np.array([0.0, 0.0]), np.array([1.0, 0.5])
+    s = motion.edge_states(a, b, 0.5)  # distance 1.5 -> nd = 3: t = 1/3, 2/3, then b
+    assert len(s) == 3 and np.allclose(s[0], [1 / 3, 0.5 / 3]) and np.array_equal(s[-1], b)
+    assert len(motion.edge_states(a, a, 0.5)) == 1  # zero-length edge: only s2 is checked
+    # continuous joint: 3.0 -> -3.0 goes through pi, not through 0 (revolute_joint_model.cpp:147-167)
+    s = motion.edge_states(np.array([3.0]), np.array([-3.0]), 0.1, continuous=[1])
+    assert len(s) == 3 and np.all(np.abs(s[:-1]) > 3.0)
+    assert abs(motion.distance([3.0], [-3.0], continuous=[1]) - (2 * np.pi - 6.0)) < 1e-12
+    # passive variable (factor 0) does not lengthen the edge
+    assert motion.distance([0.0, 0.0], [1.0, 9.0], factor=[1.0, 0.0]) == 1.0
