@@ -1182,6 +1182,8 @@ int runCheckHost(b200sv_ctx* c, const double* h_q, size_t n, uint32_t flags)
 {
   const size_t V = c->robot.group_var_index.size();
   size_t chunk = 131072;                               // states; a multiple of 32 so bitmap words do not straddle
+  if (const char* e = getenv("B200SV_CHUNK"))
+    chunk = std::max<size_t>(32, (size_t)atol(e) & ~(size_t)31);
   while ((n + chunk - 1) / chunk > b200sv_ctx::kMaxChunks)
     chunk *= 2;
   const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
@@ -1695,8 +1697,18 @@ int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags,
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   uint64_t valid = 0;
-  for (size_t i = 0; i < (n + 7) / 8; ++i)
-    valid += __builtin_popcount(valid_bitmap[i]);
+  {  // bits beyond n are 0 (the kernels write whole words from ballots of active lanes)
+    const size_t nb = (n + 7) / 8;
+    size_t i = 0;
+    for (; i + 8 <= nb; i += 8)
+    {
+      uint64_t w;
+      memcpy(&w, valid_bitmap + i, 8);
+      valid += (uint64_t)__builtin_popcountll(w);
+    }
+    for (; i < nb; ++i)
+      valid += (uint64_t)__builtin_popcount(valid_bitmap[i]);
+  }
   c->stats.n_states = n;
   c->stats.n_valid = valid;
   c->stats.n_rechecked = (flags & B200SV_CHECK_FP64) ? 0 : cnt;

@@ -371,3 +371,69 @@ def test_motion_validator_mirror(c1):
     assert mv.checkMotion(starts[0], starts[1]) == bool(valid[0])
     assert np.all(frac[valid] == 1.0) and np.all(frac[~valid] < 1.0)
     assert not svc.isValid(hi + 1.0)  # out of bounds is invalid before any collision check
+
+
+# ---- paths of the fast kernel the default configs do not reach -------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["hand", "panda_arm_hand"])
+def test_validity_prismatic_groups(group):
+    """Groups with the (prismatic, mimic) finger joints: the PRISMATIC branch and the parked-centre range check."""
+    cfg = workloads.CONFIGS["C1"]
+    eng, env = make_pair("panda", group, cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    cloud = workloads.make_cloud("C1")
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(11, 20000, lo, hi)
+    q[:50] *= 40.0  # far outside the joint limits: fingers metres away, beyond the travel the host assumed
+    for flags in (W, S, I, ALL):
+        ref, _ = env.check(q, flags)
+        assert np.array_equal(eng.check_batch(q, flags), ref == 0), (group, flags)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_validity_field_covering_part_of_the_workspace():
+    """Centres that leave the field on any side read the 1-cell border shell (free); centres just inside do not."""
+    eng, env = make_pair("panda", "panda_arm", (0.6, 0.7, 0.5), (0.35, 0.1, 0.45), 0.02, 0.25)
+    cloud = workloads.clutter_cloud(21, 4000, 10, (0.08, -0.22, 0.22), (0.62, 0.42, 0.68), 0.0)
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(12, 50000, lo, hi)
+    ref, _ = env.check(q, ALL)
+    assert 0.02 < ref.mean() < 0.98
+    assert np.array_equal(eng.check_batch(q, ALL), ref == 0)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_validity_fine_resolution_uses_16_bit_fields():
+    """Thresholds above 255 (sphere radius > 16 cells) switch the compact field to 16 bits per field."""
+    eng, env = make_pair("panda", "panda_arm", (0.6, 0.6, 0.6), (0.4, 0.0, 0.5), 0.003, 0.1)
+    assert eng.info.field_bytes_per_voxel == 2
+    cloud = workloads.clutter_cloud(22, 20000, 6, (0.15, -0.25, 0.25), (0.65, 0.25, 0.75), 0.0)
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(13, 20000, lo, hi)
+    ref, _ = env.check(q, ALL)
+    assert 0.02 < ref.mean() < 0.98
+    assert np.array_equal(eng.check_batch(q, ALL), ref == 0)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_generic_fp32_kernel_agrees_with_fast_kernel(monkeypatch):
+    """B200SV_FAST=0 routes the FP32 pass through the generic checkKernel<float> (planar / floating groups use it)."""
+    monkeypatch.setenv("B200SV_FAST", "0")
+    eng, env, cloud, q = config_pair("C1")
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    ref, _ = env.check(q, ALL)
+    assert np.array_equal(eng.check_batch(q, ALL), ref == 0)
+    eng.close()
