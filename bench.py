@@ -164,11 +164,26 @@ def run_reference(args):
                              "sample": "%d states per step, lean flavour (centre voxel only), OpenMP" % sample},
             "e2e": {"value": rate, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else any library prints to fd 1 (NCCL's
+    version banner, build chatter) was diverted to stderr at start-up."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -186,7 +201,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     cfg = workloads.CONFIGS[args.workload]
-    n = args.states or (cfg["states"]["n"] if args.workload == "C2" else cfg["states"]["n"] // world)
+    # C3 is a fixed 10 M-state batch cut over the ranks (whole 32-state tiles per rank); C2 is 1 M states per rank
+    n = args.states or (cfg["states"]["n"] if args.workload == "C2" else cfg["states"]["n"] // world // 32 * 32)
     eng = mb.StateValidityEngine.for_robot(cfg["robot"], cfg["group"], size=cfg["size"], origin=cfg["origin"],
                                            resolution=cfg["resolution"], max_distance=cfg["max_distance"], device=local)
     V, S = eng.n_group_vars, eng.n_spheres
@@ -362,7 +378,7 @@ def main():
                        "roofline": {"bound": "hbm", "achieved": b_edt / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": b_edt / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_edt}}
         e4.close()
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

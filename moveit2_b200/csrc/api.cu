@@ -928,6 +928,10 @@ int uploadTables(b200sv_ctx* c)
     CU(c, cudaMalloc(&c->d_blob_fast, c->blob_fast.size()));
     CU(c, cudaMemcpy(c->d_blob_fast, c->blob_fast.data(), c->blob_fast.size(), cudaMemcpyHostToDevice));
     c->cfg_fast = chooseCfg(c, false, false, (int)c->blob_fast.size(), true);
+    if (getenv("B200SV_VERBOSE"))
+      fprintf(stderr, "b200sv: fast kernel: %d words of transforms per state, %d bytes per warp, %d warps x %d CTAs per SM, blob %zu bytes\n",
+              c->state_stride_fast, fastCheckPerWarpBytes(c->state_stride_fast, c->n_bs, (int)c->robot.group_var_index.size()),
+              c->cfg_fast.warps, c->cfg_fast.blocks_per_sm, c->blob_fast.size());
     if (c->cfg_fast.warps < 1)
       c->fast_ok = false;  // the generic kernel's limits decide below whether the robot fits at all
   }
