@@ -210,6 +210,22 @@ int b200sv_check_motions(b200sv_ctx* ctx, const double* q_from, const double* q_
                          double max_segment_length, const uint8_t* var_continuous, const double* var_distance_factor,
                          uint32_t max_states_per_edge, uint32_t flags, uint8_t* valid_bitmap, int32_t* first_invalid,
                          uint64_t* n_states_checked);
+/* Batched CollisionEnvDistanceField::getCollisionGradients (collision_env_distance_field.cpp:1517-1538), the call
+ * CHOMP's optimisation loop makes per waypoint (moveit_planners/chomp/chomp_motion_planner/src/chomp_optimizer.cpp:881-915,
+ * acm = nullptr): per collision sphere the smallest distance seen, its gradient and what produced it, in the reference's
+ * order -- self field (SELF = 1, :355-428), every sphere pair of every enabled link pair (INTRA = 2, gradient = the
+ * un-normalised centre difference, :644-709), world field (ENVIRONMENT = 3, :1645-1681); field distances are
+ * sqrt(d2) * resolution with central-difference gradients times the reference's INTEGER inv_twice_resolution_
+ * (distance_field.cpp:73-97, distance_field.hpp:614); distances >= max_propagation_distance are not recorded.
+ * FP64, the reference's operation order.  Not restated: the per-link PosedDistanceFields of getSelfProximityGradients,
+ * which the reference consults only when an ACM was passed (:386).
+ *   distances         [n * n_spheres]      DBL_MAX where nothing was recorded (GradientInfo::distances)
+ *   gradients         [n * n_spheres * 3]  0 where nothing was recorded (the reference leaves those uninitialised)
+ *   types             [n * n_spheres]      CollisionType: NONE 0, SELF 1, INTRA 2, ENVIRONMENT 3
+ *   closest_distance  [n * n_glinks] or NULL   GradientInfo::closest_distance per link (field reads only)
+ *   sphere_locations  [n * n_spheres * 3] or NULL   posed sphere centres (GradientInfo::sphere_locations) */
+int b200sv_collision_gradients(b200sv_ctx* ctx, const double* q, size_t n_states, double* distances, double* gradients,
+                               uint8_t* types, double* closest_distance, double* sphere_locations);
 /* Posed collision-sphere centres of ONE state, FP64 kernel: [n_spheres*3] (host).  Parity hook for
  * PosedBodySphereDecomposition::updatePose (collision_distance_field_types.cpp:388-395). */
 int b200sv_sphere_centers(b200sv_ctx* ctx, const double* q_one, double* centers);

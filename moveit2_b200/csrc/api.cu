@@ -115,6 +115,9 @@ struct b200sv_ctx
   DevBuf<uint32_t> d_edge_state_bits, d_edge_bits;
   DevBuf<int32_t> d_edge_first;
   DevBuf<uint8_t> d_edge_cont;
+  // K5 outputs
+  DevBuf<double> d_g_dist, d_g_grad, d_g_closest, d_g_centers;
+  DevBuf<uint8_t> d_g_types, d_g_self;
   unsigned* d_count = nullptr;
   unsigned* d_sink = nullptr;
   b200sv_stats stats{};
@@ -249,6 +252,7 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
     B[i].slot = bs[i].slot;
     B[i].s0 = bs[i].s0;
     B[i].s1 = bs[i].s1;
+    B[i].pad = bs[i].pad;
   }
   if (!pairs.empty())
     memcpy(out.data() + h.off_pairs, pairs.data(), pairs.size() * sizeof(PairRec));
@@ -813,6 +817,7 @@ int buildTables(b200sv_ctx* c)
       B.slot = slot;
       B.s0 = s0;
       B.s1 = s1;
+      B.pad = i;
       clusters_of_glink[i].push_back((int)bs.size());
       bs.push_back(B);
       s0 = s1;
@@ -1333,6 +1338,8 @@ void b200sv_destroy(b200sv_ctx* c)
   c->d_edges.release(); c->d_edge_q.release(); c->d_edge_aux.release(); c->d_edge_count.release();
   c->d_edge_offset.release(); c->d_edge_state_bits.release(); c->d_edge_bits.release(); c->d_edge_first.release();
   c->d_edge_cont.release();
+  c->d_g_dist.release(); c->d_g_grad.release(); c->d_g_closest.release(); c->d_g_centers.release();
+  c->d_g_types.release(); c->d_g_self.release();
   if (c->d_link_slot) cudaFree(c->d_link_slot);
   if (c->d_const_T) cudaFree(c->d_const_T);
   if (c->d_count) cudaFree(c->d_count);
@@ -1797,6 +1804,73 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
   c->stats.n_rechecked = (flags & B200SV_CHECK_FP64) ? 0 : cnt;
   c->stats.check_ms = ms;
   c->stats_pending = false;
+  return B200SV_OK;
+}
+
+int b200sv_collision_gradients(b200sv_ctx* c, const double* q, size_t n, double* distances, double* gradients, uint8_t* types,
+                               double* closest_distance, double* sphere_locations)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (n && (!q || !distances || !gradients || !types))
+    return fail(c, B200SV_ERR_INVALID, "null host pointer");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t V = c->robot.group_var_index.size(), S = (size_t)c->n_spheres, L = (size_t)c->cm.n_glinks;
+  cudaStream_t s = c->stream;
+  CU(c, c->d_q.ensure(n * V));
+  CU(c, c->d_g_dist.ensure(n * S));
+  CU(c, c->d_g_grad.ensure(n * S * 3));
+  CU(c, c->d_g_centers.ensure(n * S * 3));
+  CU(c, c->d_g_types.ensure(n * S));
+  CU(c, c->d_g_closest.ensure(n * L));
+  CU(c, c->d_g_self.ensure(L));
+  CU(c, cudaMemcpyAsync(c->d_q.p, q, n * V * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(c, cudaMemcpyAsync(c->d_g_self.p, c->cm.self_enabled.data(), L, cudaMemcpyHostToDevice, s));
+  GradArgs a{};
+  a.model = c->d_blob_d;
+  a.model_bytes = (int)c->blob_d.size();
+  a.q = c->d_q.p;
+  a.n_states = n;
+  a.d2_world = c->fields[0].d2;
+  a.d2_self = c->fields[1].d2;
+  a.self_enabled = c->d_g_self.p;
+  a.n_glinks = (int)L;
+  a.resolution = c->cfg.resolution;
+  // DistanceField::inv_twice_resolution_ is declared int (distance_field.hpp:614): 1 / (2 res) truncated
+  a.inv_twice_resolution = (double)(int)(1.0 / (2.0 * c->cfg.resolution));
+  a.max_distance = c->cfg.max_propagation_distance;  // getUninitializedDistance()
+  a.max_propagation = c->cfg.max_propagation_distance;
+  a.distances = c->d_g_dist.p;
+  a.gradients = c->d_g_grad.p;
+  a.types = c->d_g_types.p;
+  a.closest = c->d_g_closest.p;
+  a.centers = c->d_g_centers.p;
+  int block = 64;
+  while (block > 32 && align16(a.model_bytes) + (size_t)block * c->state_stride_d * 8 > (size_t)c->smem_optin)
+    block -= 32;
+  const size_t smem = align16(a.model_bytes) + (size_t)block * c->state_stride_d * 8;
+  if (smem > (size_t)c->smem_optin)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "robot too large for the gradient kernel's shared-memory tile");
+  CU(c, cudaEventRecord(c->ev0, s));
+  CU(c, launchGradients(a, (int)((n + block - 1) / block), block, smem, s));
+  CU(c, cudaEventRecord(c->ev1, s));
+  CU(c, cudaMemcpyAsync(distances, a.distances, n * S * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaMemcpyAsync(gradients, a.gradients, n * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaMemcpyAsync(types, a.types, n * S, cudaMemcpyDeviceToHost, s));
+  if (closest_distance)
+    CU(c, cudaMemcpyAsync(closest_distance, a.closest, n * L * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (sphere_locations)
+    CU(c, cudaMemcpyAsync(sphere_locations, a.centers, n * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->stats.n_states = n;
+  c->stats.check_ms = ms;
   return B200SV_OK;
 }
 

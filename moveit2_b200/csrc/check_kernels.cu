@@ -765,6 +765,113 @@ __global__ void gatherKernel(const uint8_t* __restrict__ field, unsigned long lo
     *sink = acc;
 }
 
+// K5: CollisionEnvDistanceField::getCollisionGradients (collision_env_distance_field.cpp:1517-1538) for n states, in the
+// reference's order and arithmetic (FP64): self field (type SELF, :355-428 -- the dfce distance_field_ part; the per-link
+// PosedDistanceFields are consulted by the reference only when an ACM is present, :386, which CHOMP's optimisation loop
+// does not pass, chomp_optimizer.cpp:890), every sphere pair of every enabled link pair (INTRA, :644-709), world field
+// (ENVIRONMENT, :1645-1681).  getCollisionSphereGradients: collision_distance_field_types.cpp:149-209 with
+// subtract_radii = false; DistanceField::getDistanceGradient: distance_field.cpp:73-97 (1-cell margin, central
+// differences times inv_twice_resolution_); PropagationDistanceField::getDistance = sqrt(d2) * resolution.
+// One thread per state; sphere centres live in shared memory ([sphere][xyz] per thread, 24 B each).
+__device__ __forceinline__ double cellDistance(const uint16_t* __restrict__ d2, size_t idx, double res)
+{
+  return sqrt(static_cast<double>(__ldg(d2 + idx))) * res;  // sqrt_table_[d2] (propagation_distance_field.cpp:99-101)
+}
+
+__device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t* __restrict__ d2, const Smem<double>& m,
+                                               const BsRec<double>& C, const double* cen, int type, double* dist_out,
+                                               double* grad_out, uint8_t* type_out, double& closest)
+{
+  const ModelHeader<double>& h = *m.h;
+  for (int k = C.s0; k < C.s1; ++k)
+  {
+    const double x = cen[3 * k], y = cen[3 * k + 1], z = cen[3 * k + 2];
+    const int gx = static_cast<int>(floor((x - h.om[0]) * h.oo_res)), gy = static_cast<int>(floor((y - h.om[1]) * h.oo_res)),
+              gz = static_cast<int>(floor((z - h.om[2]) * h.oo_res));
+    double dist = a.max_distance, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    if (!(gx < 1 || gy < 1 || gz < 1 || gx >= h.nx - 1 || gy >= h.ny - 1 || gz >= h.nz - 1))
+    {
+      const size_t sy = static_cast<size_t>(h.nz), sx = sy * h.ny;
+      const size_t i0 = (static_cast<size_t>(gx) * h.ny + gy) * h.nz + gz;
+      g0 = (cellDistance(d2, i0 + sx, a.resolution) - cellDistance(d2, i0 - sx, a.resolution)) * a.inv_twice_resolution;
+      g1 = (cellDistance(d2, i0 + sy, a.resolution) - cellDistance(d2, i0 - sy, a.resolution)) * a.inv_twice_resolution;
+      g2 = (cellDistance(d2, i0 + 1, a.resolution) - cellDistance(d2, i0 - 1, a.resolution)) * a.inv_twice_resolution;
+      dist = cellDistance(d2, i0, a.resolution);
+    }
+    if (dist < a.max_propagation)
+    {
+      if (dist < closest)
+        closest = dist;
+      if (dist < dist_out[k])
+      {
+        type_out[k] = static_cast<uint8_t>(type);
+        dist_out[k] = dist;
+        grad_out[3 * k] = g0;
+        grad_out[3 * k + 1] = g1;
+        grad_out[3 * k + 2] = g2;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
+  const ModelHeader<double>& h = *m.h;
+  double* T = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(threadIdx.x) * h.state_stride;
+  const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i >= a.n_states)
+    return;
+  const int S = h.n_spheres;
+  double* D = a.distances + i * S;
+  double* G = a.gradients + i * S * 3;
+  uint8_t* Ty = a.types + i * S;
+  double* cen = a.centers + i * S * 3;  // scratch: posed sphere centres
+  fkState<double>(m, a.q + i * h.n_group_vars, T);
+  for (int k = 0; k < S; ++k)
+  {
+    const SphereRec<double>& sp = m.spheres[k];
+    posePoint<double>(T + sp.slot * kLinkStrideWords, sp.x, sp.y, sp.z, cen[3 * k], cen[3 * k + 1], cen[3 * k + 2]);
+    D[k] = 1.7976931348623157e308;  // DBL_MAX
+    Ty[k] = 0;
+    G[3 * k] = G[3 * k + 1] = G[3 * k + 2] = 0.0;
+  }
+  // closest_distance per dfce link; links are runs of clusters with the same glink id (BsRec::pad)
+  for (int g = 0; g < a.n_glinks; ++g)
+    a.closest[i * a.n_glinks + g] = 1.7976931348623157e308;
+  for (int c = 0; c < h.n_bs; ++c)
+  {  // self field
+    const BsRec<double>& C = m.bs[c];
+    if (a.self_enabled[C.pad])
+      fieldGradients(a, a.d2_self, m, C, cen, 1, D, G, Ty, a.closest[i * a.n_glinks + C.pad]);
+  }
+  for (int p = 0; p < h.n_pairs; ++p)
+  {  // intra-group: every sphere pair of the two clusters (all cluster pairs of a link pair = all its sphere pairs)
+    const BsRec<double>&A = m.bs[m.pairs[p].a], &B = m.bs[m.pairs[p].b];
+    for (int k = A.s0; k < A.s1; ++k)
+      for (int l = B.s0; l < B.s1; ++l)
+      {
+        const double gx = cen[3 * k] - cen[3 * l], gy = cen[3 * k + 1] - cen[3 * l + 1], gz = cen[3 * k + 2] - cen[3 * l + 2];
+        const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
+        if (dist < D[k])
+        {
+          D[k] = dist;
+          G[3 * k] = gx; G[3 * k + 1] = gy; G[3 * k + 2] = gz;
+          Ty[k] = 2;
+        }
+        if (dist < D[l])
+        {
+          D[l] = dist;
+          G[3 * l] = -gx; G[3 * l + 1] = -gy; G[3 * l + 2] = -gz;
+          Ty[l] = 2;
+        }
+      }
+  }
+  for (int c = 0; c < h.n_bs; ++c)  // world field
+    fieldGradients(a, a.d2_world, m, m.bs[c], cen, 3, D, G, Ty, a.closest[i * a.n_glinks + m.bs[c].pad]);
+}
+
 // cudaFuncSetAttribute is a host-side driver call: do it when the requirement grows, not on every launch.
 struct SmemGrant
 {
@@ -859,6 +966,16 @@ cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_
   if (e != cudaSuccess)
     return e;
   sphereCentersKernel<<<1, 128, smem_bytes, stream>>>(a, d_centers);
+  return cudaGetLastError();
+}
+
+cudaError_t launchGradients(const GradArgs& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+{
+  static SmemGrant g;
+  cudaError_t e = ensureSmem(gradientKernel, smem_bytes, g);
+  if (e != cudaSuccess)
+    return e;
+  gradientKernel<<<grid, block, smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
 

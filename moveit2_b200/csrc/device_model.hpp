@@ -48,7 +48,7 @@ struct alignas(16) BsRec
   R x, y, z, r;      // BodyDecomposition::getRelativeBoundingSphere() of the link: doBoundingSpheresIntersect (types.cpp:408-418)
   R tx, ty, tz, tr;  // tight bounding sphere of the cluster's spheres (centroid, max |c_k - c| + r_k): a conservative
                      // extra cull -- it can only skip pairs that cannot collide
-  int slot, s0, s1, pad;  // device-link slot, sphere range [s0, s1)
+  int slot, s0, s1, pad;  // device-link slot, sphere range [s0, s1), pad = index of the link in dfce order (glink)
 };
 
 // Enabled pair of clusters of two different links whose link pair is enabled in

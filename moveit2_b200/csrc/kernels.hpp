@@ -51,6 +51,26 @@ cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int g
                         cudaStream_t stream);
 int checkKernelRegs(bool fp64, bool from_list, int field_bytes);
 int checkPerWarpBytes(bool fp64, int state_stride);  // shared memory one warp of the check kernel needs
+// K5: per-sphere distance / gradient / type (getCollisionGradients), FP64, exact blob
+struct GradArgs
+{
+  const uint8_t* model;  // double blob
+  int model_bytes;
+  const double* q;
+  unsigned long long n_states;
+  const uint16_t* d2_world;  // min(d^2, max_d2) per voxel
+  const uint16_t* d2_self;
+  const uint8_t* self_enabled;  // [n_glinks]
+  int n_glinks;
+  double resolution, inv_twice_resolution, max_distance, max_propagation;
+  double* distances;  // [n * n_spheres]
+  double* gradients;  // [n * n_spheres * 3]
+  uint8_t* types;     // [n * n_spheres]
+  double* closest;    // [n * n_glinks]
+  double* centers;    // [n * n_spheres * 3] scratch / output: posed sphere centres (GradientInfo::sphere_locations)
+};
+cudaError_t launchGradients(const GradArgs& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+
 // fast_check.cu: the FP32 pass for groups of fixed / revolute / prismatic joints (a.model = the fast blob)
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);

@@ -284,6 +284,16 @@ class StateValidityEngine:
                                                 int(flags), _u8p(bm), _ip(first), C.byref(n)))
         return np.unpackbits(bm, bitorder="little")[:m].astype(bool), first[:m], int(n.value)
 
+    def collision_gradients(self, q):
+        """Batched getCollisionGradients: (distances [n, S], gradients [n, S, 3], types [n, S], closest [n, n_glinks],
+        sphere_locations [n, S, 3])."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, self.n_group_vars)
+        n, S, L = q.shape[0], self.n_spheres, self.n_glinks
+        d, g = np.zeros((n, S)), np.zeros((n, S, 3))
+        t, c, loc = np.zeros((n, S), np.uint8), np.zeros((n, L)), np.zeros((n, S, 3))
+        self._check(self.L.b200sv_collision_gradients(self.h, _dp(q), n, _dp(d), _dp(g), _u8p(t), _dp(c), _dp(loc)))
+        return d, g, t, c, loc
+
     def gather_roofline(self, n_reads=1 << 28, iters=3):
         g = C.c_double(0.0)
         self._check(self.L.b200sv_gather_roofline(self.h, n_reads, iters, C.byref(g)))

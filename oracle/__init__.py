@@ -74,4 +74,6 @@ def _declare(L):
     L.orc_state_spheres.argtypes = [vp, vp, dp, dp, dp]
     L.orc_state_margin.restype = c.c_double
     L.orc_state_margin.argtypes = [vp, vp, vp, vp, dp, dp, c.c_int]
+    L.orc_collision_gradients.argtypes = [vp, vp, vp, vp, dp, dp, c.c_size_t, dp, dp, c.POINTER(c.c_uint8), dp]
+    L.orc_collision_gradients.restype = None
     L.orc_num_threads.restype = c.c_int

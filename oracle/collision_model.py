@@ -264,6 +264,17 @@ class OracleEnv:
         return self.L.orc_state_margin(C.byref(self.robot), C.byref(self.cm), self.world.h, self.self_field.h,
                                        _p(self.base_positions, C.c_double), _p(q1, C.c_double), int(flags))
 
+    def collision_gradients(self, q):
+        """getCollisionGradients for every state: (distances [n, S], gradients [n, S, 3], types [n, S], closest [n, L])."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, max(self.group.variable_count, 1))
+        n, S, L = q.shape[0], self.n_spheres, int(self.cm.n_glinks)
+        d, g = np.zeros((n, S)), np.zeros((n, S, 3))
+        t, c = np.zeros((n, S), np.uint8), np.zeros((n, L))
+        self.L.orc_collision_gradients(C.byref(self.robot), C.byref(self.cm), self.world.h, self.self_field.h,
+                                       _p(self.base_positions, C.c_double), _p(q, C.c_double), C.c_size_t(n),
+                                       _p(d, C.c_double), _p(g, C.c_double), _p(t, C.c_uint8), _p(c, C.c_double))
+        return d, g, t, c
+
     def sphere_centers(self, q1):
         q1 = np.ascontiguousarray(q1, np.float64)
         out = np.zeros((self.n_spheres, 3))

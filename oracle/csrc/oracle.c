@@ -14,6 +14,7 @@
  * Floating point: compiled with -ffp-contract=off so every product/sum rounds once, in the order written.
  * Eigen's fixed-size products (affine 3x4 * 4x4) accumulate k = 0..3 in order; that order is used here.
  */
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -944,6 +945,110 @@ double orc_state_margin(const orc_robot* r, const orc_collision_model* cm, const
       }
   scratch_free(&s);
   return best;
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * CollisionEnvDistanceField::getCollisionGradients (collision_env_distance_field.cpp:1517-1538) for n states:
+ *   getSelfProximityGradients        :355-428   -- the dfce distance_field_ part (type SELF).  The per-link
+ *                                                  PosedDistanceFields are consulted only when dfce->acm_.getSize() > 0
+ *                                                  (:386), i.e. never in CHOMP's optimisation loop, which passes
+ *                                                  acm = nullptr (chomp_optimizer.cpp:890); they are NOT restated here.
+ *   getIntraGroupProximityGradients  :644-709   -- every sphere pair of every enabled link pair (type INTRA)
+ *   getEnvironmentProximityGradients :1645-1681 -- world field (type ENVIRONMENT)
+ * with getCollisionSphereGradients (collision_distance_field_types.cpp:149-209; subtract_radii = false,
+ * maximum_value = max_propogation_distance_, stop_at_first_collision = false).
+ * Outputs per state: distances [n_spheres] (DBL_MAX where nothing was recorded), gradients [n_spheres*3] (0 where
+ * nothing was recorded; the reference leaves them uninitialised), types [n_spheres] (CollisionType: NONE 0, SELF 1,
+ * INTRA 2, ENVIRONMENT 3), closest [n_glinks] (GradientInfo::closest_distance).
+ * ---------------------------------------------------------------------------------------------------- */
+static void sphere_gradients(const orc_pdf* f, const orc_collision_model* cm, int i, const double* centers, int type,
+                             double* dist_out, double* grad_out, uint8_t* type_out, double* closest)
+{
+  for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1]; ++k)
+  {
+    double grad[3];
+    int inb;
+    const double* c = centers + 3 * k;
+    double dist = orc_pdf_get_distance_gradient(f, c[0], c[1], c[2], grad, &inb);
+    /* (!in_bounds && grad.norm() > EPSILON) cannot happen: the gradient is zero when out of bounds */
+    if (dist < cm->max_propagation_distance)
+    {
+      if (dist < closest[i])
+        closest[i] = dist;
+      if (dist < dist_out[k])
+      {
+        type_out[k] = (uint8_t)type;
+        dist_out[k] = dist;
+        grad_out[3 * k] = grad[0];
+        grad_out[3 * k + 1] = grad[1];
+        grad_out[3 * k + 2] = grad[2];
+      }
+    }
+  }
+}
+
+void orc_collision_gradients(const orc_robot* r, const orc_collision_model* cm, const orc_pdf* world, const orc_pdf* self,
+                             const double* base_positions, const double* q, size_t n, double* distances, double* gradients,
+                             uint8_t* types, double* closest)
+{
+  const int L = cm->n_glinks, S = cm->sphere_start[L];
+  orc_scratch s;
+  scratch_alloc(&s, r, cm);
+  for (size_t st = 0; st < n; ++st)
+  {
+    double* D = distances + st * (size_t)S;
+    double* G = gradients + st * (size_t)S * 3;
+    uint8_t* Ty = types + st * (size_t)S;
+    double* Cl = closest + st * (size_t)L;
+    memcpy(s.positions, base_positions, (size_t)r->n_vars * sizeof(double));
+    set_group_positions(r, s.positions, q + st * (size_t)r->n_group_vars);
+    fk_links(r, s.positions, s.link_T);
+    for (int i = 0; i < L; ++i)
+    {
+      Cl[i] = DBL_MAX;
+      const double* T = s.link_T + 16 * cm->glink_index[i];
+      for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1]; ++k)
+      {
+        transform_point(T, cm->sphere_rel + 3 * k, s.centers + 3 * k);
+        D[k] = DBL_MAX;
+        Ty[k] = 0;
+        G[3 * k] = G[3 * k + 1] = G[3 * k + 2] = 0.0;
+      }
+    }
+    for (int i = 0; i < L; ++i)
+      if (cm->has_geometry[i] && cm->self_enabled[i] && self)
+        sphere_gradients(self, cm, i, s.centers, 1, D, G, Ty, Cl);
+    for (int i = 0; i < L; ++i)
+      for (int j = i + 1; j < L; ++j)
+      {
+        if (!cm->has_geometry[i] || !cm->has_geometry[j] || !cm->intra_enabled[(size_t)i * L + j])
+          continue;
+        for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1]; ++k)
+          for (int l = cm->sphere_start[j]; l < cm->sphere_start[j + 1]; ++l)
+          {
+            const double gx = s.centers[3 * k] - s.centers[3 * l];
+            const double gy = s.centers[3 * k + 1] - s.centers[3 * l + 1];
+            const double gz = s.centers[3 * k + 2] - s.centers[3 * l + 2];
+            const double dist = sqrt(gx * gx + gy * gy + gz * gz);
+            if (dist < D[k])
+            {
+              D[k] = dist;
+              G[3 * k] = gx; G[3 * k + 1] = gy; G[3 * k + 2] = gz;
+              Ty[k] = 2;
+            }
+            if (dist < D[l])
+            {
+              D[l] = dist;
+              G[3 * l] = -gx; G[3 * l + 1] = -gy; G[3 * l + 2] = -gz;
+              Ty[l] = 2;
+            }
+          }
+      }
+    for (int i = 0; i < L; ++i)
+      if (cm->has_geometry[i] && world)
+        sphere_gradients(world, cm, i, s.centers, 3, D, G, Ty, Cl);
+  }
+  scratch_free(&s);
 }
 
 int orc_num_threads(void)

@@ -437,3 +437,30 @@ def test_generic_fp32_kernel_agrees_with_fast_kernel(monkeypatch):
     ref, _ = env.check(q, ALL)
     assert np.array_equal(eng.check_batch(q, ALL), ref == 0)
     eng.close()
+
+
+# ---- K5: getCollisionGradients -----------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_collision_gradients_equal_oracle(c1):
+    """Per sphere: distance, gradient, CollisionType and per link closest_distance, in the reference's update order."""
+    eng, env, cloud, q = c1
+    n = 2000
+    d, g, t, c, loc = eng.collision_gradients(q[:n])
+    rd, rg, rt, rc = env.collision_gradients(q[:n])
+    assert d.shape == rd.shape and g.shape == rg.shape
+    # sphere centres agree to rounding (the device contracts a*b+c into FMA, the oracle does not), so a centre that sits on a
+    # cell face within 1e-15 m may read the neighbouring voxel: such entries are counted, everything else must agree
+    both_none = (t == 0) & (rt == 0)
+    assert np.array_equal(d[both_none], rd[both_none])          # DBL_MAX
+    close = np.isclose(d, rd, rtol=0, atol=1e-9) | both_none
+    assert close.mean() > 0.9999, "%d of %d sphere distances differ" % ((~close).sum(), close.size)
+    assert np.array_equal(t[close], rt[close])
+    assert np.allclose(g[close], rg[close], rtol=0, atol=1e-9)
+    assert np.isclose(c, rc, rtol=0, atol=1e-9).mean() > 0.999
+    for k in (1, 2, 3):
+        assert (rt == k).any(), "the test scene should exercise CollisionType %d" % k
+    # sphere_locations are the posed centres
+    assert np.allclose(loc[0], env.sphere_centers(q[0]), atol=1e-12)
+    # intra gradients are un-normalised centre differences: their norm is the recorded distance
+    intra = t == 2
+    assert np.allclose(np.linalg.norm(g[intra], axis=1), d[intra], atol=1e-12)
