@@ -76,7 +76,9 @@ struct b200sv_ctx
   uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr, *d_blob_fast = nullptr;
   bool fast_ok = false;      // the group's joints are all FIXED / REVOLUTE / PRISMATIC: fast_check.cu runs the FP32 pass
   bool fast_disabled = false;  // B200SV_FAST=0: force the generic FP32 kernel (A/B measurements)
-  int state_stride_fast = 0;
+  int state_stride_fast = 0, fast_t_rows = 0;
+  bool fast_t_global = false;  // link transforms in an L2-resident scratch instead of shared memory (large robots)
+  float* d_t_scratch = nullptr;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
   double cluster_radius = 0.2;   // max tight-sphere radius of a sphere cluster (m); clusters also hold <= 4 spheres
   int state_stride_f = 0, state_stride_d = 0;  // shared-memory words per state (float / double blob)
@@ -548,6 +550,8 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   off = align16(off + (int)(fq.size() * sizeof(fast::Quirk)));
   h.total_bytes = off;
   h.state_stride = c.state_stride_fast;
+  h.t_rows = 3 * std::max(1, n_stored);
+  c.fast_t_rows = h.t_rows;
   h.n_clusters = (int)cl.size();
   h.nz = c.grid.nz;
   h.nynz = c.grid.ny * c.grid.nz;
@@ -904,7 +908,7 @@ b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, 
       continue;
     const long per_block = std::min<long>(c->smem_optin, (233472L - 1024L * b) / b) - align16(blob_bytes);
     int w = per_block > 0 ? (int)(per_block / pw) : 0;
-    w = std::min(w, fast ? 12 : 16);  // __launch_bounds__ of the kernels
+    w = std::min(w, fast ? fastCheckMaxWarps() : 16);  // __launch_bounds__ of the kernels
     w = std::min(w, reg_warps / b);
     if (c->tune_warps > 0)
       w = std::min(w, c->tune_warps);
@@ -933,9 +937,32 @@ int uploadTables(b200sv_ctx* c)
     CU(c, cudaMalloc(&c->d_blob_fast, c->blob_fast.size()));
     CU(c, cudaMemcpy(c->d_blob_fast, c->blob_fast.data(), c->blob_fast.size(), cudaMemcpyHostToDevice));
     c->cfg_fast = chooseCfg(c, false, false, (int)c->blob_fast.size(), true);
+    c->fast_t_global = false;
+    {  // large robots: with the transforms in shared memory only a few warps fit; move them to an L2-resident scratch
+      const int keep = c->state_stride_fast;
+      c->state_stride_fast = 0;
+      const b200sv_ctx::LaunchCfg g = chooseCfg(c, false, false, (int)c->blob_fast.size(), true);
+      c->state_stride_fast = keep;
+      const char* e = getenv("B200SV_T_GLOBAL");
+      // measured on B200: the scratch variant is also the faster one when shared memory would fit 12 warps
+      // (Panda C2: 0.546 vs 0.624 ms per million states) -- fewer shared-memory wavefronts on the L1 pipe the
+      // gathers share, coalesced 512-byte stores.  B200SV_T_GLOBAL=0 keeps the transforms in shared memory.
+      const bool want = e ? atoi(e) != 0 : g.warps * g.blocks_per_sm >= c->cfg_fast.warps * c->cfg_fast.blocks_per_sm;
+      if (want && g.warps >= 1)
+      {
+        c->cfg_fast = g;
+        c->fast_t_global = true;
+      }
+    }
+    if (c->d_t_scratch)
+      cudaFree(c->d_t_scratch);
+    c->d_t_scratch = nullptr;
+    if (c->fast_t_global)
+      CU(c, cudaMalloc(&c->d_t_scratch, (size_t)c->sm_count * c->cfg_fast.blocks_per_sm * c->cfg_fast.warps *
+                                            (size_t)c->fast_t_rows * 128 * sizeof(float)));
     if (getenv("B200SV_VERBOSE"))
       fprintf(stderr, "b200sv: fast kernel: %d words of transforms per state, %d bytes per warp, %d warps x %d CTAs per SM, blob %zu bytes\n",
-              c->state_stride_fast, fastCheckPerWarpBytes(c->state_stride_fast, c->n_bs, (int)c->robot.group_var_index.size()),
+              c->state_stride_fast, fastCheckPerWarpBytes(c->fast_t_global ? 0 : c->state_stride_fast, c->n_bs, (int)c->robot.group_var_index.size()),
               c->cfg_fast.warps, c->cfg_fast.blocks_per_sm, c->blob_fast.size());
     if (c->cfg_fast.warps < 1)
       c->fast_ok = false;  // the generic kernel's limits decide below whether the robot fits at all
@@ -1149,6 +1176,7 @@ int launchMain(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t ba
     const b200sv_ctx::LaunchCfg& k = c->cfg_fast;
     a.model = c->d_blob_fast;
     a.model_bytes = (int)c->blob_fast.size();
+    a.t_scratch = c->fast_t_global ? c->d_t_scratch : nullptr;
     CU(c, launchFastCheck<FT>(a, c->sm_count * k.blocks_per_sm, k.warps * 32, k.smem, s));
     return B200SV_OK;
   }
@@ -1335,6 +1363,7 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->d_blob_f) cudaFree(c->d_blob_f);
   if (c->d_blob_d) cudaFree(c->d_blob_d);
   if (c->d_blob_fast) cudaFree(c->d_blob_fast);
+  if (c->d_t_scratch) cudaFree(c->d_t_scratch);
   c->d_edges.release(); c->d_edge_q.release(); c->d_edge_aux.release(); c->d_edge_count.release();
   c->d_edge_offset.release(); c->d_edge_state_bits.release(); c->d_edge_bits.release(); c->d_edge_first.release();
   c->d_edge_cont.release();

@@ -179,7 +179,8 @@ struct alignas(16) Header
   int n_clusters;
   int nz, nynz;
   unsigned idx_bias;  // -(0x4B400000 * (nynz + nz + 1)) mod 2^32: undoes the float-magic bias of the three cell indices
-  int pad2, pad3, pad4;
+  int t_rows;  // float4 rows of transforms per state (3 per stored link): size of a warp's global-memory region / 32
+  int pad3, pad4;
   float lo[3], margin;      // clamp of (centre - margin) to [0.5 - margin, n - 0.5 - margin]: a centre outside the
   float hi[3], two_margin;  // field lands in the 1-cell border shell, where nothing collides
   float pair_eps_v, tight_eps_v, pad0, pad1;

@@ -38,7 +38,16 @@ namespace
 {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kU = B200SV_FAST_UNROLL;  // Hot ranges are padded per link to a multiple of this (the tail chunk)
-constexpr int kMaxVars = 16;             // group variables the register prefetch covers (the host checks)
+#ifndef B200SV_FAST_THREADS
+#define B200SV_FAST_THREADS 256
+#endif
+#ifndef B200SV_FAST_MINBLOCKS
+#define B200SV_FAST_MINBLOCKS 2
+#endif
+#ifndef B200SV_MAXVARS
+#define B200SV_MAXVARS 16
+#endif
+constexpr int kMaxVars = B200SV_MAXVARS;             // group variables the register prefetch covers (the host checks)
 constexpr int kP = 4;                   // gathers in flight per lane = spheres of the main chunk
 constexpr int kQueueCap = 256;          // (state, pair) work items per warp; flushed when fewer than 32 slots remain
 constexpr float kMagic = 12582912.f;    // 1.5 * 2^23: x + kMagic rounded down has floor(x) in its low mantissa bits
@@ -98,6 +107,44 @@ __device__ __forceinline__ void store12(float* p, const float* o)
   for (int i = 0; i < 3; ++i)
     v[i] = make_float4(o[4 * i + 0], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
 }
+// Where the per-state link transforms of a warp's tile live.  kGlobal = false: shared memory, one block of
+// `stride` words per state (3x4 rows of 16 bytes).  kGlobal = true (robots whose transforms would leave shared memory
+// for only a few warps): a per-warp region of an L2-resident scratch buffer, laid out [link row][state] so the
+// 32 lanes of the link loop store and load 512 contiguous bytes.
+template <bool kGlobal>
+struct TStore
+{
+  float* base;
+  int stride;
+  __device__ __forceinline__ void load(int off, int state, float* o) const
+  {
+    if (kGlobal)
+    {
+      const float4* v = reinterpret_cast<const float4*>(base) + (off >> 2) * 32 + state;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        const float4 t = v[i * 32];
+        o[4 * i + 0] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
+      }
+    }
+    else
+      load12(base + state * stride + off, o);
+  }
+  __device__ __forceinline__ void store(int off, int state, const float* o) const
+  {
+    if (kGlobal)
+    {
+      float4* v = reinterpret_cast<float4*>(base) + (off >> 2) * 32 + state;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        v[i * 32] = make_float4(o[4 * i + 0], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
+    else
+      store12(base + state * stride + off, o);
+  }
+};
+
 __device__ __forceinline__ void pose(const float* T, float x, float y, float z, float& ox, float& oy, float& oz)
 {
   ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
@@ -135,7 +182,8 @@ __device__ __forceinline__ float sqrtApprox(float x)
 // not prove it away,] then every sphere of cluster a against every sphere of cluster b, dist < r1 + r2
 // (getIntraGroupCollisions, collision_env_distance_field.cpp:571-638).  Clusters are padded to kClusterSpheres
 // entries whose radius is -1e30, so the 4 x 4 block is branch-free.  T: the state's transform block.
-__device__ __forceinline__ void pairItem(const FModel& m, const float* T, unsigned p, bool& hit, bool& amb)
+template <bool kGlobal>
+__device__ __forceinline__ void pairItem(const FModel& m, const TStore<kGlobal>& ts, int state, unsigned p, bool& hit, bool& amb)
 {
   constexpr int kC = fast::kClusterSpheres;
   const fast::Header& h = *m.h;
@@ -143,8 +191,8 @@ __device__ __forceinline__ void pairItem(const FModel& m, const float* T, unsign
   const int4 p1 = reinterpret_cast<const int4*>(m.pairs + p)[1];      // b_off, quirk
   const int ca = __float_as_int(p0.y), cb = __float_as_int(p0.z), a_off = __float_as_int(p0.w), b_off = p1.x;
   float Ta[12], Tb[12];
-  load12(T + a_off, Ta);
-  load12(T + b_off, Tb);
+  ts.load(a_off, state, Ta);
+  ts.load(b_off, state, Tb);
   bool cert = true;
   if (p1.y >= 0)
   {
@@ -208,18 +256,22 @@ __device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters
 }
 
 // Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
-template <typename FT>
-__global__ void __launch_bounds__(384, 1) fastCheckKernel(CheckArgs<FT> a)
+template <typename FT, bool kTG>
+__global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fastCheckKernel(CheckArgs<FT> a)
 {
   using Elem = typename Cmp<FT>::Elem;
   extern __shared__ __align__(16) uint8_t smem[];
   const FModel m = loadFast(a.model, a.model_bytes, smem);
   const fast::Header& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * fastPerWarpBytes(h.state_stride, h.n_clusters, h.n_group_vars);
+  const int t_words = kTG ? 0 : h.state_stride;  // shared-memory words of transforms per state
+  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * fastPerWarpBytes(t_words, h.n_clusters, h.n_group_vars);
   float* Ts = reinterpret_cast<float*>(wbase);
+  TStore<kTG> ts;
+  ts.base = kTG ? a.t_scratch + (static_cast<size_t>(blockIdx.x) * warps + warp) * (static_cast<size_t>(h.t_rows) * 128) : Ts;
+  ts.stride = h.state_stride;
   const int rs = repStride(h.n_clusters);
-  uint32_t* rep_xy = reinterpret_cast<uint32_t*>(Ts + 32 * h.state_stride);  // [state][cluster] half2 (x, y)
+  uint32_t* rep_xy = reinterpret_cast<uint32_t*>(Ts + 32 * t_words);  // [state][cluster] half2 (x, y)
   uint16_t* rep_z = reinterpret_cast<uint16_t*>(rep_xy + 32 * rs);           // [state][cluster] half z
   uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_z) + ((32 * rs * 2 + 15) & ~15));
   double* stage = reinterpret_cast<double*>(queue);  // the tile's states [state][var], FK phase only
@@ -231,7 +283,6 @@ __global__ void __launch_bounds__(384, 1) fastCheckKernel(CheckArgs<FT> a)
   const int nz = h.nz, nynz = h.nynz;
   const unsigned idx_bias = h.idx_bias;
   const float two_m = h.two_margin;
-  float* T_state = Ts + lane * h.state_stride;
 
   const unsigned long long n = a.n_states;
   const unsigned long long n_tiles = (n + 31) / 32;
@@ -395,8 +446,10 @@ __global__ void __launch_bounds__(384, 1) fastCheckKernel(CheckArgs<FT> a)
         }
       }
       // T = T_parent * [M | mt]; a root's "parent" is the identity block of the header (one code path, no merge)
-      if (m0.z != fast::kParentPrev)
-        load12(m0.z == fast::kParentRoot ? h.ident : T_state + m0.z, T);
+      if (m0.z == fast::kParentRoot)
+        load12(h.ident, T);
+      else if (m0.z != fast::kParentPrev)
+        ts.load(m0.z, lane, T);
 #pragma unroll
       for (int r = 0; r < 3; ++r)
       {
@@ -407,7 +460,7 @@ __global__ void __launch_bounds__(384, 1) fastCheckKernel(CheckArgs<FT> a)
         T[4 * r + 3] = fmaf(p0, mt[0], fmaf(p1, mt[1], fmaf(p2, mt[2], T[4 * r + 3])));
       }
       if (m0.w >= 0)
-        store12(T_state + m0.w, T);
+        ts.store(m0.w, lane, T);
       if (do_intra && m1.z < m1.w)
       {  // tight-sphere centres of the link's clusters, relative to rep_base and narrowed to half: the level-1 cull of
          // the pair phase is conservative, its slack (host) covers the rounding
@@ -456,7 +509,7 @@ __global__ void __launch_bounds__(384, 1) fastCheckKernel(CheckArgs<FT> a)
           const unsigned item = queue[i];
           const int s = item & 31;
           bool ihit = false, iamb = false;
-          pairItem(m, Ts + s * h.state_stride, item >> 5, ihit, iamb);
+          pairItem<kTG>(m, ts, s, item >> 5, ihit, iamb);
           if (ihit)
             atomicOr(&words[0], 1u << s);
           if (iamb)
@@ -570,24 +623,40 @@ int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars)
   return fastPerWarpBytes(state_stride, n_clusters, n_group_vars);
 }
 int fastCheckMaxVars() { return kMaxVars; }
+int fastCheckMaxWarps() { return B200SV_FAST_THREADS / 32; }
 int fastCheckUnroll() { return kU; }
 
 int fastCheckKernelRegs(int field_bytes)
 {
   cudaFuncAttributes fa{};
-  cudaError_t e = field_bytes == 1 ? cudaFuncGetAttributes(&fa, fastCheckKernel<uint8_t>) :
-                                     cudaFuncGetAttributes(&fa, fastCheckKernel<uint16_t>);
-  return e == cudaSuccess ? fa.numRegs : 128;
+  cudaError_t e = field_bytes == 1 ? cudaFuncGetAttributes(&fa, fastCheckKernel<uint8_t, false>) :
+                                     cudaFuncGetAttributes(&fa, fastCheckKernel<uint16_t, false>);
+  int regs = e == cudaSuccess ? fa.numRegs : 128;
+  e = field_bytes == 1 ? cudaFuncGetAttributes(&fa, fastCheckKernel<uint8_t, true>) :
+                         cudaFuncGetAttributes(&fa, fastCheckKernel<uint16_t, true>);
+  if (e == cudaSuccess && fa.numRegs > regs)
+    regs = fa.numRegs;
+  return regs;
 }
 
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-  static Grant g;
-  cudaError_t e = ensure(fastCheckKernel<FT>, smem_bytes, g);
-  if (e != cudaSuccess)
-    return e;
-  fastCheckKernel<FT><<<grid, block, smem_bytes, stream>>>(a);
+  static Grant g0, g1;
+  if (a.t_scratch)
+  {
+    cudaError_t e = ensure(fastCheckKernel<FT, true>, smem_bytes, g1);
+    if (e != cudaSuccess)
+      return e;
+    fastCheckKernel<FT, true><<<grid, block, smem_bytes, stream>>>(a);
+  }
+  else
+  {
+    cudaError_t e = ensure(fastCheckKernel<FT, false>, smem_bytes, g0);
+    if (e != cudaSuccess)
+      return e;
+    fastCheckKernel<FT, false><<<grid, block, smem_bytes, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 template cudaError_t launchFastCheck<uint8_t>(const CheckArgs<uint8_t>&, int, int, size_t, cudaStream_t);

@@ -32,6 +32,7 @@ struct CheckArgs
   unsigned list_cap;
   const uint32_t* list;  // exact pass from list (in)
   const unsigned* list_count;
+  float* t_scratch;      // fast pass only: global-memory home of the link transforms (null: shared memory)
 };
 
 struct FkArgs
@@ -77,6 +78,7 @@ cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t 
 int fastCheckKernelRegs(int field_bytes);
 int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars);
 int fastCheckMaxVars();
+int fastCheckMaxWarps();  // __launch_bounds__ of the fast kernel
 int fastCheckUnroll();
 cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_bytes, cudaStream_t stream);
