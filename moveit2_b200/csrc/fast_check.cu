@@ -252,7 +252,7 @@ __device__ __host__ inline int queueBytes(int n_group_vars)
 __device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters, int n_group_vars)
 {
   const int rs = repStride(n_clusters);
-  return 32 * state_stride * 4 + 32 * rs * 4 + ((32 * rs * 2 + 15) & ~15) + queueBytes(n_group_vars) + 16;
+  return 32 * state_stride * 4 + 32 * rs * 8 + queueBytes(n_group_vars) + 16;
 }
 
 // Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
@@ -271,9 +271,8 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
   ts.base = kTG ? a.t_scratch + (static_cast<size_t>(blockIdx.x) * warps + warp) * (static_cast<size_t>(h.t_rows) * 128) : Ts;
   ts.stride = h.state_stride;
   const int rs = repStride(h.n_clusters);
-  uint32_t* rep_xy = reinterpret_cast<uint32_t*>(Ts + 32 * t_words);  // [state][cluster] half2 (x, y)
-  uint16_t* rep_z = reinterpret_cast<uint16_t*>(rep_xy + 32 * rs);           // [state][cluster] half z
-  uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_z) + ((32 * rs * 2 + 15) & ~15));
+  uint2* reps = reinterpret_cast<uint2*>(Ts + 32 * t_words);  // [state][cluster] { half2 (x, y), (half z, 0) }
+  uint32_t* queue = reinterpret_cast<uint32_t*>(reps + 32 * rs);
   double* stage = reinterpret_cast<double*>(queue);  // the tile's states [state][var], FK phase only
   unsigned* words = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(queue) + queueBytes(h.n_group_vars));  // [0] hit, [1] amb
   const bool do_fields = (a.flags & 3u) != 0, do_intra = (a.flags & 4u) != 0;
@@ -474,8 +473,8 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
           if (__float_as_int(o.w) != 0 && fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) >= h.rep_limit)
             aacc = 1u;  // beyond the travel the host assumed for prismatic joints: the exact pass decides
           const __half2 xy = __floats2half2_rn(x, y);
-          rep_xy[lane * rs + c] = *reinterpret_cast<const uint32_t*>(&xy);
-          rep_z[lane * rs + c] = __half_as_ushort(__float2half_rn(z));
+          reps[lane * rs + c] = make_uint2(*reinterpret_cast<const uint32_t*>(&xy),
+                                           static_cast<uint32_t>(__half_as_ushort(__float2half_rn(z))));
         }
       }
       if (!do_fields)
@@ -537,12 +536,10 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
           {
             const int s = __ffs(todo) - 1;
             todo &= todo - 1;
-            const uint32_t* rxy = rep_xy + s * rs;
-            const uint16_t* rz = rep_z + s * rs;
-            const uint32_t axy = rxy[ca], bxy = rxy[cb];
-            const uint32_t az = rz[ca], bz = rz[cb];  // zero-extended: (z, 0)
-            const __half2 d1 = __hsub2(*reinterpret_cast<const __half2*>(&axy), *reinterpret_cast<const __half2*>(&bxy));
-            const __half2 d2 = __hsub2(*reinterpret_cast<const __half2*>(&az), *reinterpret_cast<const __half2*>(&bz));
+            const uint2* row = reps + s * rs;
+            const uint2 ra = row[ca], rb = row[cb];
+            const __half2 d1 = __hsub2(*reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&rb.x));
+            const __half2 d2 = __hsub2(*reinterpret_cast<const __half2*>(&ra.y), *reinterpret_cast<const __half2*>(&rb.y));
             const __half2 sq = __hfma2(d2, d2, __hmul2(d1, d1));
             const __half dd = __hadd(__low2half(sq), __high2half(sq));
             if (__hlt(dd, rt2) && have)
