@@ -79,8 +79,12 @@ typedef struct b200sv_robot
  *  collision_env_distance_field.cpp:735-838). */
 typedef struct b200sv_collision_model
 {
-  int32_t n_glinks;             /* dfce->link_names_.size() = group->getUpdatedLinkModelNames() */
-  const int32_t* glink_index;   /* model link index of each */
+  int32_t n_glinks;             /* dfce->link_names_.size() + attached-body entries */
+  const int32_t* glink_index;   /* model link index of each.  The links come first, in getUpdatedLinkModels() order; an
+                                   index that already appeared denotes an ATTACHED BODY carried by that link
+                                   (dfce->attached_body_names_, collision_env_distance_field.cpp:798-822): its spheres and
+                                   bounding sphere are given in the LINK frame (attach pose folded in), one entry per
+                                   shape of the body */
   const uint8_t* self_enabled;  /* dfce->self_collision_enabled_ [n_glinks] */
   const uint8_t* intra_enabled; /* dfce->intra_group_collision_enabled_ [n_glinks*n_glinks]; only j > i is read */
   const int32_t* sphere_start;  /* [n_glinks+1] range of each link's collision spheres; empty range = no geometry */

@@ -219,8 +219,79 @@ CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::
     bounding_sphere[4 * i + 2] = bs.center.z();
     bounding_sphere[4 * i + 3] = bs.radius;
   }
+  // ---- attached bodies: dfce->attached_body_names_ follow the links (:798-822, 840-866) -------------------------------
+  // One entry per SHAPE of each body attached to a group link; the entry repeats the link's index (that is how
+  // libb200sv recognises it), its spheres and bounding sphere are expressed in the LINK frame
+  // (AttachedBody::getShapePosesInLinkFrame() * BodyDecomposition-relative coordinates).  Masks as the reference sets
+  // them: (link, body) is disabled by an ALWAYS entry or a touch link ONLY for the link the body hangs on; body-body by
+  // an ALWAYS entry; shapes of one body never test each other.
+  struct BodyEntry
+  {
+    int link_i;  // index into glinks
+    std::string name;
+    std::vector<double> xyzr;
+    double bs[4];
+  };
+  std::vector<BodyEntry> body_entries;
+  for (int i = 0; i < n; ++i)
+  {
+    std::vector<const moveit::core::AttachedBody*> attached;
+    state.getAttachedBodies(attached, glinks[i]);
+    for (const moveit::core::AttachedBody* att : attached)
+    {
+      const EigenSTL::vector_Isometry3d& poses = att->getShapePosesInLinkFrame();
+      for (std::size_t k = 0; k < att->getShapes().size(); ++k)
+      {
+        const BodyDecomposition d(att->getShapes()[k], resolution_, 0.0);
+        BodyEntry e;
+        e.link_i = i;
+        e.name = att->getName();
+        for (const CollisionSphere& cs : d.getCollisionSpheres())
+        {
+          const Eigen::Vector3d c = poses[k] * cs.relative_vec_;
+          e.xyzr.insert(e.xyzr.end(), { c.x(), c.y(), c.z(), cs.radius_ });
+        }
+        const Eigen::Vector3d bc = poses[k] * d.getRelativeBoundingSphere().center;
+        e.bs[0] = bc.x(); e.bs[1] = bc.y(); e.bs[2] = bc.z(); e.bs[3] = d.getRelativeBoundingSphere().radius;
+        body_entries.push_back(std::move(e));
+      }
+    }
+  }
+  if (!body_entries.empty())
+  {
+    const int nb = static_cast<int>(body_entries.size()), nt = n + nb;
+    std::vector<uint8_t> intra2(static_cast<std::size_t>(nt) * nt, 0);
+    for (int i = 0; i < n; ++i)
+    {
+      for (int j = 0; j < n; ++j)
+        intra2[static_cast<std::size_t>(i) * nt + j] = intra_enabled[static_cast<std::size_t>(i) * n + j];
+      if (!glinks[i]->getShapes().empty())
+        for (int b = 0; b < nb; ++b)
+          intra2[static_cast<std::size_t>(i) * nt + n + b] = 1;  // all_true
+    }
+    for (int b = 0; b < nb; ++b)
+    {
+      const BodyEntry& e = body_entries[b];
+      const moveit::core::AttachedBody* att = state.getAttachedBody(e.name);
+      const std::string& link_name = glinks[e.link_i]->getName();
+      AllowedCollision::Type t;
+      if ((acm && acm->getEntry(link_name, e.name, t) && t == AllowedCollision::ALWAYS) ||
+          att->getTouchLinks().count(link_name))
+        intra2[static_cast<std::size_t>(e.link_i) * nt + n + b] = 0;
+      glink_index.push_back(glinks[e.link_i]->getLinkIndex());
+      self_enabled.push_back(!(acm && acm->getEntry(e.name, e.name, t) && t == AllowedCollision::ALWAYS));
+      for (int b2 = b + 1; b2 < nb; ++b2)
+        intra2[static_cast<std::size_t>(n + b) * nt + n + b2] =
+            !(body_entries[b2].name == e.name ||
+              (acm && acm->getEntry(e.name, body_entries[b2].name, t) && t == AllowedCollision::ALWAYS));
+      sphere_xyzr.insert(sphere_xyzr.end(), e.xyzr.begin(), e.xyzr.end());
+      sphere_start.push_back(static_cast<int32_t>(sphere_xyzr.size() / 4));
+      bounding_sphere.insert(bounding_sphere.end(), e.bs, e.bs + 4);
+    }
+    intra_enabled.swap(intra2);
+  }
   b200sv_collision_model m{};
-  m.n_glinks = n;
+  m.n_glinks = static_cast<int32_t>(glink_index.size());
   m.glink_index = glink_index.data();
   m.self_enabled = self_enabled.data();
   m.intra_enabled = intra_enabled.data();

@@ -634,8 +634,9 @@ int validateModel(b200sv_ctx* c)
       return fail(c, B200SV_ERR_INVALID, "glink_index out of range");
     if (m.sphere_start[i + 1] < m.sphere_start[i])
       return fail(c, B200SV_ERR_INVALID, "sphere_start must be non-decreasing");
-    if (i > 0 && m.glink_index[i] <= m.glink_index[i - 1])
-      return fail(c, B200SV_ERR_INVALID, "glink_index must be strictly increasing (getUpdatedLinkModels() order)");
+    // a link index that already appeared denotes an ATTACHED BODY carried by that link (dfce->attached_body_names_ follow
+    // dfce->link_names_, collision_env_distance_field.cpp:798-822); the link entries themselves come in
+    // getUpdatedLinkModels() order
   }
   return B200SV_OK;
 }
@@ -739,6 +740,35 @@ int buildTables(b200sv_ctx* c)
     c->link_slot[l] = (int)links.size();
     links.push_back(L);
   }
+  // Attached bodies (second and later entries of the same link): their spheres are given in the LINK frame, so a body
+  // is a pseudo link fixed to its link with an identity origin.  Appended after the real links: device sphere order
+  // stays the caller's (dfce) order.
+  std::vector<int> glink_slot(m.n_glinks, -1);
+  {
+    std::vector<char> seen(r.n_links, 0);
+    for (int i = 0; i < m.n_glinks; ++i)
+    {
+      const int li = m.glink_index[i];
+      if (!seen[li])
+      {
+        seen[li] = 1;
+        glink_slot[i] = c->link_slot[li];
+        continue;
+      }
+      if (m.sphere_start[i + 1] <= m.sphere_start[i])
+        continue;
+      if (c->link_slot[li] < 0)
+        return fail(c, B200SV_ERR_INVALID, "attached body on a link that neither moves with the group nor carries spheres");
+      LinkRec<double> L{};
+      L.o[0] = L.o[5] = L.o[10] = 1.0;
+      L.parent = c->link_slot[li];
+      L.type = FIXED;
+      L.var = (int)vars.size();
+      L.has_origin = 0;
+      glink_slot[i] = (int)links.size();
+      links.push_back(L);
+    }
+  }
   c->n_dev_links = (int)links.size();
   if (links.empty())
     return fail(c, B200SV_ERR_INVALID, "no link moves with the group and none carries spheres");
@@ -760,7 +790,7 @@ int buildTables(b200sv_ctx* c)
     const int a = m.sphere_start[i], b = m.sphere_start[i + 1];
     if (b <= a)
       continue;
-    const int slot = c->link_slot[m.glink_index[i]];
+    const int slot = glink_slot[i];
     const int first = (int)spheres.size();
     for (int k = a; k < b; ++k)
     {

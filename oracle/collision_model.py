@@ -222,6 +222,89 @@ class OracleEnv:
         self.self_points = self.compute_self_points()
         self.self_field.add_points(self.self_points)
 
+    def attach_bodies(self, bodies):
+        """Append attached bodies to the DistanceFieldCacheEntry view (dfce->attached_body_names_ follow the links,
+        collision_env_distance_field.cpp:798-822, 840-866).  bodies: list of dicts with
+          link       name of the group link the body is attached to
+          name       body name (ACM key)
+          spheres    [(centre xyz in the LINK frame, radius), ...]   (attach pose and shape pose folded in)
+          bs_center, bs_radius   bounding sphere in the link frame
+          touch_links  names; the reference consults them -- and the ACM entry (link, body) -- ONLY for the link the
+                       body is attached to (:801-822); every other link keeps all_true for the body.
+        Masks: self_collision_enabled_ false iff ACM (body, body) is ALWAYS; body-body pairs disabled iff ALWAYS."""
+        a = self.arr
+        gl = self.group.updated_links
+        n0 = len(gl)
+        names = [l.name for l in gl]
+        acm = AllowedCollisionMatrix(self.model.srdf)
+        n = n0 + len(bodies)
+        intra0 = a["intra_enabled"].reshape(n0, n0)
+        intra = np.ones((n, n), np.uint8)
+        intra[:n0, :n0] = intra0
+        for i in range(n0):
+            if not a["has_geometry"][i]:
+                intra[i, :] = 0
+        glink = list(a["glink_index"])
+        has_geom, self_en = list(a["has_geometry"]), list(a["self_enabled"])
+        S0 = self.n_spheres
+        sph_start = list(a["sphere_start"])
+        sph_rel = list(a["sphere_rel"].reshape(-1, 3)[:S0])
+        sph_rad = list(a["sphere_radius"][:S0])
+        bs_c = list(a["bs_center"].reshape(-1, 3)[:n0])
+        bs_r = list(a["bs_radius"][:n0])
+        pt_start = list(a["point_start"])
+        for b, body in enumerate(bodies):
+            ip = names.index(body["link"])
+            glink.append(gl[ip].index)
+            has_geom.append(1)
+            self_en.append(0 if acm.always(body["name"], body["name"]) else 1)
+            if acm.always(body["link"], body["name"]) or body["link"] in body.get("touch_links", ()):
+                intra[ip, n0 + b] = 0
+            for b2 in range(b + 1, len(bodies)):
+                if acm.always(body["name"], bodies[b2]["name"]):
+                    intra[n0 + b, n0 + b2] = 0
+            for cxyz, rad in body["spheres"]:
+                sph_rel.append(np.asarray(cxyz, np.float64))
+                sph_rad.append(float(rad))
+            sph_start.append(len(sph_rad))
+            bs_c.append(np.asarray(body["bs_center"], np.float64))
+            bs_r.append(float(body["bs_radius"]))
+            pt_start.append(pt_start[-1])
+        a["glink_index"] = np.array(glink, np.int32)
+        a["has_geometry"], a["self_enabled"] = np.array(has_geom, np.int32), np.array(self_en, np.int32)
+        a["intra_enabled"] = intra.reshape(-1).copy()
+        a["sphere_start"] = np.array(sph_start, np.int32)
+        a["sphere_rel"] = np.array(sph_rel + [np.zeros(3)], np.float64).reshape(-1)
+        a["sphere_radius"] = np.array(sph_rad + [0.0], np.float64)
+        a["bs_center"] = np.array(bs_c + [np.zeros(3)], np.float64).reshape(-1)
+        a["bs_radius"] = np.array(bs_r + [0.0], np.float64)
+        a["point_start"] = np.array(pt_start, np.int32)
+        self.n_spheres = len(sph_rad)
+        self.cm = OrcCollisionModel(n, _p(a["glink_index"], C.c_int32), _p(a["has_geometry"], C.c_int32),
+                                    _p(a["self_enabled"], C.c_int32), _p(a["intra_enabled"], C.c_uint8),
+                                    _p(a["sphere_start"], C.c_int32), _p(a["sphere_rel"], C.c_double),
+                                    _p(a["sphere_radius"], C.c_double), _p(a["bs_center"], C.c_double),
+                                    _p(a["bs_radius"], C.c_double), _p(a["point_start"], C.c_int32),
+                                    _p(a["point_rel"], C.c_double), self.max_prop, self.tol)
+
+    def flat_arrays(self):
+        """(robot, model) dicts in the layout of b200sv_robot / b200sv_collision_model (include/b200sv.h)."""
+        a = self.arr
+        n = int(self.cm.n_glinks)
+        S = self.n_spheres
+        robot = dict(n_links=len(self.model.links), n_vars=self.model.n_vars, parent=a["parent"], joint_type=a["joint_type"],
+                     joint_axis=a["axis"], joint_origin=a["origin"], first_var=a["first_var"],
+                     base_positions=self.base_positions, group_var_index=a["group_var_index"],
+                     mimic_dst=a["mimic_dst"][:len(self.group.mimic_updates)], mimic_src=a["mimic_src"][:len(self.group.mimic_updates)],
+                     mimic_factor=a["mimic_factor"][:len(self.group.mimic_updates)],
+                     mimic_offset=a["mimic_offset"][:len(self.group.mimic_updates)])
+        xyzr = np.concatenate([a["sphere_rel"].reshape(-1, 3)[:S], a["sphere_radius"][:S, None]], axis=1)
+        bsph = np.concatenate([a["bs_center"].reshape(-1, 3)[:n], a["bs_radius"][:n, None]], axis=1)
+        model = dict(n_glinks=n, glink_index=a["glink_index"], self_enabled=a["self_enabled"].astype(np.uint8),
+                     intra_enabled=a["intra_enabled"], sphere_start=a["sphere_start"], sphere_xyzr=xyzr,
+                     bounding_sphere=bsph)
+        return robot, model
+
     def compute_self_points(self):
         """:907-953 -- interior points of links with geometry that are NOT updated by the group, posed at the
         cached state (here: the base state), in getLinkModelsWithCollisionGeometry (= link index) order."""
