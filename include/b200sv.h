@@ -179,6 +179,13 @@ int b200sv_field_get_d2(b200sv_ctx* ctx, int which, int32_t* d2_out);
 /* Inject an externally built field (e.g. the reference's own propagation result) so check parity can be tested
  * independently of EDT parity. */
 int b200sv_field_set_d2(b200sv_ctx* ctx, int which, const int32_t* d2);
+/* PropagationDistanceField::writeToStream / readFromStream (propagation_distance_field.cpp:635-760): the ".df" format of
+ * the reference's fixtures (moveit_core/test_small.df, test_big.df) -- 7 ASCII header lines, then zlib data with the
+ * occupancy, x-major, then y, then z packed 8 voxels per byte LSB-first.  write: call with out = NULL to learn the size.
+ * read: resets the field and rebuilds it from the stream's occupied voxels; the stream's geometry must equal the
+ * context's (the reference resizes its field instead). */
+int b200sv_field_write_df(b200sv_ctx* ctx, int which, uint8_t* out, size_t cap, size_t* n_out);
+int b200sv_field_read_df(b200sv_ctx* ctx, int which, const uint8_t* bytes, size_t n_bytes);
 /* The self field's generating points (URDF path only): n_out receives the count; xyz may be NULL. */
 int b200sv_get_self_points(const b200sv_ctx* ctx, double* xyz, size_t cap_points, size_t* n_out);
 

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200sv.so")
 SOURCES = ["api.cu", "check_kernels.cu", "fast_check.cu", "edt_kernels.cu", "motion_kernels.cu", "host_model.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
-              "-fPIC,-Wall,-Wno-unknown-pragmas", "-shared", "--expt-relaxed-constexpr"]
+              "-fPIC,-Wall,-Wno-unknown-pragmas", "-shared", "--expt-relaxed-constexpr", "-lz"]
 
 
 def _stale():

@@ -2,6 +2,7 @@
 // Host logic only -- kernels live in check_kernels.cu and edt_kernels.cu.  There is no CPU compute path here:
 // every entry point either runs on the CUDA device or returns an error.
 #include <cuda_runtime.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <cmath>
@@ -1645,6 +1646,100 @@ int b200sv_field_set_d2(b200sv_ctx* c, int which, const int32_t* d2)
   CU(c, launchInjectD2(c->grid, c->d_i32.p, F.occ, F.d2, F.compact, c->compact_bytes, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return B200SV_OK;
+}
+
+// ---- .df streams: PropagationDistanceField::writeToStream / readFromStream (propagation_distance_field.cpp:635-760) -----
+// 7 ASCII header lines (resolution, size_xyz, origin_xyz = the grid CORNER), then zlib data: x-major, then y, then z packed
+// 8 voxels per byte, bit zi LSB-first, 1 = occupied (distance_square_ == 0).  Distances are not stored; reading resets
+// the field and rebuilds it from the occupied voxels.
+int b200sv_field_write_df(b200sv_ctx* c, int which, uint8_t* out, size_t cap, size_t* n_out)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!n_out)
+    return fail(c, B200SV_ERR_INVALID, "null n_out");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const GridDev& g = c->grid;
+  const size_t rows = (size_t)g.nx * g.ny, zb = (size_t)(g.nz + 7) / 8;
+  std::vector<uint32_t> occ(rows * g.wz);
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaMemcpy(occ.data(), c->fields[which].occ, occ.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> packed(rows * zb);
+  for (size_t r = 0; r < rows; ++r)
+    memcpy(packed.data() + r * zb, reinterpret_cast<const uint8_t*>(occ.data() + r * g.wz), zb);  // little-endian words
+  char head[512];
+  const b200sv_field_cfg& f = c->cfg;
+  const int hl = snprintf(head, sizeof(head),
+                          "resolution: %g\nsize_x: %g\nsize_y: %g\nsize_z: %g\norigin_x: %g\norigin_y: %g\norigin_z: %g\n",
+                          f.resolution, f.size[0], f.size[1], f.size[2], f.origin[0] - 0.5 * f.size[0],
+                          f.origin[1] - 0.5 * f.size[1], f.origin[2] - 0.5 * f.size[2]);
+  uLongf zl = compressBound((uLong)packed.size());
+  std::vector<uint8_t> z(zl);
+  if (compress(z.data(), &zl, packed.data(), (uLong)packed.size()) != Z_OK)
+    return fail(c, B200SV_ERR_INVALID, "zlib compress failed");
+  *n_out = (size_t)hl + zl;
+  if (!out || cap < *n_out)
+    return out ? fail(c, B200SV_ERR_INVALID, "output buffer too small (n_out holds the size needed)") : B200SV_OK;
+  memcpy(out, head, (size_t)hl);
+  memcpy(out + hl, z.data(), zl);
+  return B200SV_OK;
+}
+
+int b200sv_field_read_df(b200sv_ctx* c, int which, const uint8_t* bytes, size_t n_bytes)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!bytes)
+    return fail(c, B200SV_ERR_INVALID, "null input");
+  static const char* keys[7] = { "resolution:", "size_x:", "size_y:", "size_z:", "origin_x:", "origin_y:", "origin_z:" };
+  double v[7];
+  size_t pos = 0;
+  for (int k = 0; k < 7; ++k)
+  {
+    size_t end = pos;
+    while (end < n_bytes && bytes[end] != '\n')
+      ++end;
+    if (end >= n_bytes)
+      return fail(c, B200SV_ERR_PARSE, ".df header truncated");
+    const std::string line(reinterpret_cast<const char*>(bytes) + pos, end - pos);
+    const size_t kl = strlen(keys[k]);
+    if (line.compare(0, kl, keys[k]) != 0)
+      return fail(c, B200SV_ERR_PARSE, std::string(".df header: expected ") + keys[k]);
+    v[k] = atof(line.c_str() + kl);
+    pos = end + 1;
+  }
+  // readFromStream resizes the field to the stream's geometry; a context's geometry is fixed at creation, so the stream
+  // must describe the same grid
+  const b200sv_field_cfg& f = c->cfg;
+  const double want[7] = { f.resolution, f.size[0], f.size[1], f.size[2], f.origin[0] - 0.5 * f.size[0],
+                           f.origin[1] - 0.5 * f.size[1], f.origin[2] - 0.5 * f.size[2] };
+  for (int k = 0; k < 7; ++k)
+    if (fabs(v[k] - want[k]) > 1e-5 * std::max(1.0, fabs(want[k])))  // the header carries 6 significant digits
+      return fail(c, B200SV_ERR_INVALID, std::string(".df geometry differs from the context's field: ") + keys[k]);
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const GridDev& g = c->grid;
+  const size_t rows = (size_t)g.nx * g.ny, zb = (size_t)(g.nz + 7) / 8;
+  std::vector<uint8_t> packed(rows * zb);
+  uLongf got = (uLongf)packed.size();
+  const int zr = uncompress(packed.data(), &got, bytes + pos, (uLong)(n_bytes - pos));
+  if (zr != Z_OK || got != packed.size())
+    return fail(c, B200SV_ERR_PARSE, ".df payload: zlib error or wrong size for this grid");
+  std::vector<uint32_t> occ(rows * g.wz, 0u);
+  const uint8_t tail_mask = (g.nz & 7) ? (uint8_t)((1u << (g.nz & 7)) - 1u) : (uint8_t)0xff;
+  for (size_t r = 0; r < rows; ++r)
+  {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(occ.data() + r * g.wz);
+    memcpy(dst, packed.data() + r * zb, zb);
+    dst[zb - 1] &= tail_mask;  // bits beyond nz are not voxels
+  }
+  Field& F = c->fields[which];
+  CU(c, cudaMemcpyAsync(F.occ, occ.data(), occ.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return rebuildField(c, which);
 }
 
 // ---- hot path --------------------------------------------------------------------------------------------------------

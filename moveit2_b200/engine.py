@@ -294,6 +294,19 @@ class StateValidityEngine:
         self._check(self.L.b200sv_collision_gradients(self.h, _dp(q), n, _dp(d), _dp(g), _u8p(t), _dp(c), _dp(loc)))
         return d, g, t, c, loc
 
+    def field_write_df(self, which=FIELD_WORLD):
+        """PropagationDistanceField::writeToStream: the field's occupancy as .df bytes."""
+        n = C.c_size_t(0)
+        self._check(self.L.b200sv_field_write_df(self.h, int(which), None, 0, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        self._check(self.L.b200sv_field_write_df(self.h, int(which), _u8p(buf), buf.size, C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def field_read_df(self, raw, which=FIELD_WORLD):
+        """PropagationDistanceField::readFromStream: reset, then rebuild from the stream's occupied voxels."""
+        buf = np.frombuffer(bytes(raw), np.uint8).copy()
+        self._check(self.L.b200sv_field_read_df(self.h, int(which), _u8p(buf), buf.size))
+
     def gather_roofline(self, n_reads=1 << 28, iters=3):
         g = C.c_double(0.0)
         self._check(self.L.b200sv_gather_roofline(self.h, n_reads, iters, C.byref(g)))

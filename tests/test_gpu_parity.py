@@ -522,3 +522,35 @@ def test_validity_with_attached_bodies():
     assert close.mean() > 0.9999 and (t[close] == rt[close]).mean() > 0.9995
     eng.close()
     bare_eng.close()
+
+
+# ---- .df streams (writeToStream / readFromStream) -----------------------------------------------------------------------
+@pytest.mark.gpu
+def test_df_stream_round_trip_and_reference_format():
+    from oracle.df import read_df_occupancy, write_df_occupancy
+    eng, env, cloud, q = config_pair("C1", n_states=1)
+    eng.field_add_points(cloud)
+    before = eng.field_get_d2()
+    raw = eng.field_write_df()
+    hdr, n, occ = read_df_occupancy(raw)  # the oracle's reader of the reference format
+    assert tuple(n) == eng.num_cells and abs(hdr["resolution"] - 0.02) < 1e-12
+    assert abs(hdr["origin_z"] - 0.0) < 1e-12 and abs(hdr["origin_x"] + 0.5) < 1e-12  # the grid CORNER
+    mask = np.zeros(eng.num_cells, bool)
+    mask[occ[:, 0], occ[:, 1], occ[:, 2]] = True
+    assert np.array_equal(mask.reshape(-1), (before == 0).reshape(-1))
+    eng.field_reset()
+    assert (eng.field_get_d2() != 0).all()
+    eng.field_read_df(raw)
+    assert np.array_equal(eng.field_get_d2(), before)
+    # a stream produced by the Python writer of the same format (what the reference's fixtures look like)
+    occ2 = np.zeros(eng.num_cells, bool)
+    occ2[3, 4, 5] = occ2[10, 20, 49] = occ2[49, 0, 7] = True
+    eng.field_read_df(write_df_occupancy(hdr, occ2))
+    d2 = eng.field_get_d2().reshape(eng.num_cells)
+    assert np.array_equal(np.argwhere(d2 == 0), np.argwhere(occ2))
+    # geometry mismatch is an error, not a silent resize
+    bad = dict(hdr)
+    bad["resolution"] = 0.05
+    with pytest.raises(mb.B200svError):
+        eng.field_read_df(write_df_occupancy(bad, occ2))
+    eng.close()
