@@ -236,12 +236,12 @@ __device__ __forceinline__ void pairItem(const FModel& m, const TStore<kGlobal>&
   amb = any_maybe && !hit;
 }
 
-// Row length (elements) of one state's posed cluster centres: odd, so the 32 lanes of the link loop (one state each)
-// store to 32 distinct banks and the 32 lanes of the level-1 cull (one pair each, same state) load conflict-free.
-__device__ __host__ inline int repStride(int n_clusters) { return n_clusters | 1; }
+// Posed cluster centres are parked as three half arrays x, y, z of [cluster][state], cluster stride 34 halves = 17 words:
+// the 32 lanes of the level-1 cull (one pair each, same two states) then load from 32 distinct banks, and two adjacent
+// states share one 32-bit word (the cull works on half2 = two states at a time).
+constexpr int kRepStride = 34;
+__device__ __host__ inline int repBytes(int n_clusters) { return (3 * n_clusters * kRepStride * 2 + 15) & ~15; }
 
-// Per-warp shared memory in bytes: transforms of 32 states | cluster centres (x, y) half2 [state][cluster] |
-// cluster centres z half [state][cluster] | queue / staged states | words
 // The work queue of the pair phase and the staged states of the FK phase share one region (never live together).
 __device__ __host__ inline int queueBytes(int n_group_vars)
 {
@@ -251,8 +251,7 @@ __device__ __host__ inline int queueBytes(int n_group_vars)
 
 __device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters, int n_group_vars)
 {
-  const int rs = repStride(n_clusters);
-  return 32 * state_stride * 4 + 32 * rs * 8 + queueBytes(n_group_vars) + 16;
+  return 32 * state_stride * 4 + repBytes(n_clusters) + queueBytes(n_group_vars) + 16;
 }
 
 // Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
@@ -270,9 +269,10 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
   TStore<kTG> ts;
   ts.base = kTG ? a.t_scratch + (static_cast<size_t>(blockIdx.x) * warps + warp) * (static_cast<size_t>(h.t_rows) * 128) : Ts;
   ts.stride = h.state_stride;
-  const int rs = repStride(h.n_clusters);
-  uint2* reps = reinterpret_cast<uint2*>(Ts + 32 * t_words);  // [state][cluster] { half2 (x, y), (half z, 0) }
-  uint32_t* queue = reinterpret_cast<uint32_t*>(reps + 32 * rs);
+  __half* rep_x = reinterpret_cast<__half*>(Ts + 32 * t_words);  // [cluster][kRepStride]
+  __half* rep_y = rep_x + h.n_clusters * kRepStride;
+  __half* rep_z = rep_y + h.n_clusters * kRepStride;
+  uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_x) + repBytes(h.n_clusters));
   double* stage = reinterpret_cast<double*>(queue);  // the tile's states [state][var], FK phase only
   unsigned* words = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(queue) + queueBytes(h.n_group_vars));  // [0] hit, [1] amb
   const bool do_fields = (a.flags & 3u) != 0, do_intra = (a.flags & 4u) != 0;
@@ -472,9 +472,9 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
           const float z = fmaf(T[8], cc.x, fmaf(T[9], cc.y, fmaf(T[10], cc.z, tbz)));
           if (__float_as_int(o.w) != 0 && fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) >= h.rep_limit)
             aacc = 1u;  // beyond the travel the host assumed for prismatic joints: the exact pass decides
-          const __half2 xy = __floats2half2_rn(x, y);
-          reps[lane * rs + c] = make_uint2(*reinterpret_cast<const uint32_t*>(&xy),
-                                           static_cast<uint32_t>(__half_as_ushort(__float2half_rn(z))));
+          rep_x[c * kRepStride + lane] = __float2half_rn(x);
+          rep_y[c * kRepStride + lane] = __float2half_rn(y);
+          rep_z[c * kRepStride + lane] = __float2half_rn(z);
         }
       }
       if (!do_fields)
@@ -527,24 +527,31 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
         const float4 pc = reinterpret_cast<const float4*>(m.pairs + (have ? p : 0))[0];  // rt2 (half bits), a, b, a_off
         const int ca = __float_as_int(pc.y), cb = __float_as_int(pc.z);
         const __half rt2 = __ushort_as_half(static_cast<unsigned short>(__float_as_uint(pc.x)));
-        unsigned todo = mine_mask;
-        while (todo)
-        {  // chunks of 8 states: at most 256 new items, the queue's capacity
+        const __half2 rt2_2 = __half2half2(rt2);
+        const uint32_t* ax = reinterpret_cast<const uint32_t*>(rep_x + ca * kRepStride);
+        const uint32_t* bx = reinterpret_cast<const uint32_t*>(rep_x + cb * kRepStride);
+        const uint32_t* ay = reinterpret_cast<const uint32_t*>(rep_y + ca * kRepStride);
+        const uint32_t* by = reinterpret_cast<const uint32_t*>(rep_y + cb * kRepStride);
+        const uint32_t* az = reinterpret_cast<const uint32_t*>(rep_z + ca * kRepStride);
+        const uint32_t* bz = reinterpret_cast<const uint32_t*>(rep_z + cb * kRepStride);
+        for (int c8 = 0; c8 < 4; ++c8)
+        {  // chunks of 8 states (at most 256 new items, the queue's capacity), two states per half2 lane pair
+          if (((mine_mask >> (8 * c8)) & 0xffu) == 0u)
+            continue;
           unsigned live_states = 0u;
-#pragma unroll 2
-          for (int it = 0; it < 8 && todo; ++it)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
           {
-            const int s = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint2* row = reps + s * rs;
-            const uint2 ra = row[ca], rb = row[cb];
-            const __half2 d1 = __hsub2(*reinterpret_cast<const __half2*>(&ra.x), *reinterpret_cast<const __half2*>(&rb.x));
-            const __half2 d2 = __hsub2(*reinterpret_cast<const __half2*>(&ra.y), *reinterpret_cast<const __half2*>(&rb.y));
-            const __half2 sq = __hfma2(d2, d2, __hmul2(d1, d1));
-            const __half dd = __hadd(__low2half(sq), __high2half(sq));
-            if (__hlt(dd, rt2) && have)
-              live_states |= 1u << s;
+            const int w = c8 * 4 + j;  // word = states 2w, 2w + 1
+            const uint32_t wax = ax[w], wbx = bx[w], way = ay[w], wby = by[w], waz = az[w], wbz = bz[w];
+            const __half2 dx = __hsub2(*reinterpret_cast<const __half2*>(&wax), *reinterpret_cast<const __half2*>(&wbx));
+            const __half2 dy = __hsub2(*reinterpret_cast<const __half2*>(&way), *reinterpret_cast<const __half2*>(&wby));
+            const __half2 dz = __hsub2(*reinterpret_cast<const __half2*>(&waz), *reinterpret_cast<const __half2*>(&wbz));
+            const __half2 dd = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
+            const unsigned lt = __hlt2_mask(dd, rt2_2);  // 0xffff per half where dd < rt2
+            live_states |= ((lt & 1u) | ((lt >> 15) & 2u)) << (2 * w);
           }
+          live_states &= have ? mine_mask : 0u;
           // append (state, pair) items: exclusive scan of the per-lane counts, then every lane writes its own
           const int cnt = __popc(live_states);
           int pos = cnt;
