@@ -237,6 +237,26 @@ int b200sv_check_motions(b200sv_ctx* ctx, const double* q_from, const double* q_
  *   sphere_locations  [n * n_spheres * 3] or NULL   posed sphere centres (GradientInfo::sphere_locations) */
 int b200sv_collision_gradients(b200sv_ctx* ctx, const double* q, size_t n_states, double* distances, double* gradients,
                                uint8_t* types, double* closest_distance, double* sphere_locations);
+/* One reported contact (collision_detection::Contact as the distance-field detector fills it,
+ * collision_env_distance_field.cpp:313-331, 596-621, 1604-1623): pos = centre of the colliding sphere of body 1. */
+typedef struct b200sv_contact
+{
+  int32_t body_1;   /* dfce entry (link or attached body) */
+  int32_t body_2;   /* the other entry (intra-group), -1 = "self" (self field), -2 = "environment" (world field) */
+  int32_t sphere_1; /* index into body 1's sphere list */
+  int32_t sphere_2; /* index into body 2's sphere list, -1 for field contacts */
+  double pos[3];
+} b200sv_contact;
+/* Batched CollisionEnvDistanceField::checkCollision with req.contacts = true (:1389-1411): getSelfCollisions ->
+ * getIntraGroupCollisions -> getEnvironmentCollisions in that order, each bounded by max_contacts_per_pair per body pair
+ * and ending the sequence at max_contacts -- so WHICH contacts are reported is the reference's choice.  `flags` selects
+ * the passes (B200SV_CHECK_SELF | INTRA = checkSelfCollision, WORLD = checkRobotCollision).  FP64.
+ *   collision      [n]  res.collision
+ *   contact_count  [n]  res.contact_count
+ *   contacts       [n * max_contacts], the first contact_count[i] of state i are valid */
+int b200sv_check_contacts(b200sv_ctx* ctx, const double* q, size_t n_states, uint32_t flags, uint32_t max_contacts,
+                          uint32_t max_contacts_per_pair, uint8_t* collision, int32_t* contact_count,
+                          b200sv_contact* contacts);
 /* Posed collision-sphere centres of ONE state, FP64 kernel: [n_spheres*3] (host).  Parity hook for
  * PosedBodySphereDecomposition::updatePose (collision_distance_field_types.cpp:388-395). */
 int b200sv_sphere_centers(b200sv_ctx* ctx, const double* q_one, double* centers);

@@ -87,6 +87,7 @@ def load():
         "b200sv_check_batch_device": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp, vp]),
         "b200sv_sphere_centers": (C.c_int, [vp, dp, dp]),
         "b200sv_collision_gradients": (C.c_int, [vp, dp, C.c_size_t, dp, dp, u8p, dp, dp]),
+        "b200sv_check_contacts": (C.c_int, [vp, dp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, u8p, ip, vp]),
         "b200sv_check_motions": (C.c_int, [vp, dp, dp, C.c_size_t, C.c_double, u8p, dp, C.c_uint32, C.c_uint32, u8p,
                                            ip, C.POINTER(C.c_uint64)]),
         "b200sv_gather_roofline": (C.c_int, [vp, C.c_size_t, C.c_int, dp]),

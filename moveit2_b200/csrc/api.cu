@@ -84,6 +84,7 @@ struct b200sv_ctx
   double cluster_radius = 0.2;   // max tight-sphere radius of a sphere cluster (m); clusters also hold <= 4 spheres
   int state_stride_f = 0, state_stride_d = 0;  // shared-memory words per state (float / double blob)
   std::vector<int> link_slot;      // model link -> device slot
+  std::vector<int> glink_slot;     // dfce entry -> device slot (attached bodies have pseudo links)
   std::vector<double> const_T;     // model links * 16 (base state)
   int* d_link_slot = nullptr;
   double* d_const_T = nullptr;
@@ -121,6 +122,11 @@ struct b200sv_ctx
   // K5 outputs
   DevBuf<double> d_g_dist, d_g_grad, d_g_closest, d_g_centers;
   DevBuf<uint8_t> d_g_types, d_g_self;
+  // contacts
+  DevBuf<int32_t> d_c_start, d_c_slot, d_c_count;
+  DevBuf<double> d_c_bs;
+  DevBuf<uint8_t> d_c_intra, d_c_coll;
+  DevBuf<b200sv_contact_rec> d_c_out;
   unsigned* d_count = nullptr;
   unsigned* d_sink = nullptr;
   b200sv_stats stats{};
@@ -744,7 +750,8 @@ int buildTables(b200sv_ctx* c)
   // Attached bodies (second and later entries of the same link): their spheres are given in the LINK frame, so a body
   // is a pseudo link fixed to its link with an identity origin.  Appended after the real links: device sphere order
   // stays the caller's (dfce) order.
-  std::vector<int> glink_slot(m.n_glinks, -1);
+  std::vector<int>& glink_slot = c->glink_slot;
+  glink_slot.assign(m.n_glinks, -1);
   {
     std::vector<char> seen(r.n_links, 0);
     for (int i = 0; i < m.n_glinks; ++i)
@@ -1400,6 +1407,8 @@ void b200sv_destroy(b200sv_ctx* c)
   c->d_edge_cont.release();
   c->d_g_dist.release(); c->d_g_grad.release(); c->d_g_closest.release(); c->d_g_centers.release();
   c->d_g_types.release(); c->d_g_self.release();
+  c->d_c_start.release(); c->d_c_slot.release(); c->d_c_count.release(); c->d_c_bs.release(); c->d_c_intra.release();
+  c->d_c_coll.release(); c->d_c_out.release();
   if (c->d_link_slot) cudaFree(c->d_link_slot);
   if (c->d_const_T) cudaFree(c->d_const_T);
   if (c->d_count) cudaFree(c->d_count);
@@ -2025,6 +2034,78 @@ int b200sv_collision_gradients(b200sv_ctx* c, const double* q, size_t n, double*
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   c->stats.n_states = n;
   c->stats.check_ms = ms;
+  return B200SV_OK;
+}
+
+int b200sv_check_contacts(b200sv_ctx* c, const double* q, size_t n, uint32_t flags, uint32_t max_contacts,
+                          uint32_t max_contacts_per_pair, uint8_t* collision, int32_t* contact_count, b200sv_contact* contacts)
+{
+  static_assert(sizeof(b200sv_contact) == sizeof(b200sv_contact_rec), "contact record layout");
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (n && (!q || !collision || !contact_count || !contacts))
+    return fail(c, B200SV_ERR_INVALID, "null host pointer");
+  if ((flags & 7u) == 0 || max_contacts == 0)
+    return fail(c, B200SV_ERR_INVALID, "flags select no check, or max_contacts is 0");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t V = c->robot.group_var_index.size(), S = (size_t)c->n_spheres, L = (size_t)c->cm.n_glinks;
+  cudaStream_t s = c->stream;
+  std::vector<int32_t> slot(c->glink_slot.begin(), c->glink_slot.end());
+  for (auto& v : slot)
+    v = std::max(v, 0);  // entries without spheres are never dereferenced
+  CU(c, c->d_q.ensure(n * V));
+  CU(c, c->d_g_centers.ensure(n * S * 3));
+  CU(c, c->d_c_start.ensure(L + 1));
+  CU(c, c->d_c_slot.ensure(L));
+  CU(c, c->d_c_bs.ensure(L * 4));
+  CU(c, c->d_g_self.ensure(L));
+  CU(c, c->d_c_intra.ensure(L * L));
+  CU(c, c->d_c_coll.ensure(n));
+  CU(c, c->d_c_count.ensure(n));
+  CU(c, c->d_c_out.ensure(n * max_contacts));
+  CU(c, cudaMemcpyAsync(c->d_q.p, q, n * V * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(c, cudaMemcpyAsync(c->d_c_start.p, c->cm.sphere_start.data(), (L + 1) * 4, cudaMemcpyHostToDevice, s));
+  CU(c, cudaMemcpyAsync(c->d_c_slot.p, slot.data(), L * 4, cudaMemcpyHostToDevice, s));
+  CU(c, cudaMemcpyAsync(c->d_c_bs.p, c->cm.bounding_sphere.data(), L * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(c, cudaMemcpyAsync(c->d_g_self.p, c->cm.self_enabled.data(), L, cudaMemcpyHostToDevice, s));
+  CU(c, cudaMemcpyAsync(c->d_c_intra.p, c->cm.intra_enabled.data(), L * L, cudaMemcpyHostToDevice, s));
+  CU(c, cudaMemsetAsync(c->d_c_out.p, 0xff, n * max_contacts * sizeof(b200sv_contact_rec), s));
+  ContactArgs a{};
+  a.model = c->d_blob_d;
+  a.model_bytes = (int)c->blob_d.size();
+  a.q = c->d_q.p;
+  a.n_states = n;
+  a.d2_world = c->fields[0].d2;
+  a.d2_self = c->fields[1].d2;
+  a.flags = flags & 7u;
+  a.max_contacts = max_contacts;
+  a.max_per_pair = max_contacts_per_pair;
+  a.n_glinks = (int)L;
+  a.sphere_start = c->d_c_start.p;
+  a.glink_slot = c->d_c_slot.p;
+  a.glink_bs = c->d_c_bs.p;
+  a.self_enabled = c->d_g_self.p;
+  a.intra = c->d_c_intra.p;
+  a.centers = c->d_g_centers.p;
+  a.collision = c->d_c_coll.p;
+  a.contact_count = c->d_c_count.p;
+  a.contacts = c->d_c_out.p;
+  int block = 64;
+  while (block > 32 && align16(a.model_bytes) + (size_t)block * c->state_stride_d * 8 > (size_t)c->smem_optin)
+    block -= 32;
+  const size_t smem = align16(a.model_bytes) + (size_t)block * c->state_stride_d * 8;
+  if (smem > (size_t)c->smem_optin)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "robot too large for the contact kernel's shared-memory tile");
+  CU(c, launchContacts(a, (int)((n + block - 1) / block), block, smem, s));
+  CU(c, cudaMemcpyAsync(collision, a.collision, n, cudaMemcpyDeviceToHost, s));
+  CU(c, cudaMemcpyAsync(contact_count, a.contact_count, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaMemcpyAsync(contacts, a.contacts, n * max_contacts * sizeof(b200sv_contact_rec), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
   return B200SV_OK;
 }
 

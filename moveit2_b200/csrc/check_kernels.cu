@@ -872,6 +872,136 @@ __global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
     fieldGradients(a, a.d2_world, m, m.bs[c], cen, 3, D, G, Ty, a.closest[i * a.n_glinks + m.bs[c].pad]);
 }
 
+// CollisionEnvDistanceField::checkCollision with req.contacts = true (collision_env_distance_field.cpp:1389-1411), n states:
+// getSelfCollisions (:274-353) -> getIntraGroupCollisions (:430-642) -> getEnvironmentCollisions (:1561-1643), each pass
+// ending the sequence once contact_count >= max_contacts; the contact-listing getCollisionSphereCollision
+// (collision_distance_field_types.cpp:238-271) with num_coll = min(max_contacts_per_pair, max_contacts - contact_count).
+// FP64, the reference's order of links, pairs and spheres: WHICH contacts are reported depends on it.  The field
+// predicate is the integer threshold form (d2 < thr, exact: see sphereThreshold in api.cu).
+__device__ __forceinline__ bool sphereHitsField(const ModelHeader<double>& h, const uint16_t* __restrict__ d2, const double* c,
+                                                int thr)
+{
+  const int gx = static_cast<int>(floor((c[0] - h.om[0]) * h.oo_res)), gy = static_cast<int>(floor((c[1] - h.om[1]) * h.oo_res)),
+            gz = static_cast<int>(floor((c[2] - h.om[2]) * h.oo_res));
+  if (gx < 1 || gy < 1 || gz < 1 || gx >= h.nx - 1 || gy >= h.ny - 1 || gz >= h.nz - 1)
+    return false;  // reads max_distance: never collides (distance_field.cpp:82, types.cpp:256)
+  return static_cast<int>(__ldg(d2 + (static_cast<size_t>(gx) * h.ny + gy) * h.nz + gz)) < thr;
+}
+
+__global__ void __launch_bounds__(64) contactKernel(ContactArgs a)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
+  const ModelHeader<double>& h = *m.h;
+  double* T = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(threadIdx.x) * h.state_stride;
+  const unsigned long long st = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (st >= a.n_states)
+    return;
+  const int S = h.n_spheres, L = a.n_glinks;
+  double* cen = a.centers + st * S * 3;
+  b200sv_contact_rec* out = a.contacts + st * a.max_contacts;
+  fkState<double>(m, a.q + st * h.n_group_vars, T);
+  for (int k = 0; k < S; ++k)
+  {
+    const SphereRec<double>& sp = m.spheres[k];
+    posePoint<double>(T + sp.slot * kLinkStrideWords, sp.x, sp.y, sp.z, cen[3 * k], cen[3 * k + 1], cen[3 * k + 2]);
+  }
+  unsigned count = 0;
+  bool coll_any = false, done = false;
+  auto fieldPass = [&](const uint16_t* __restrict__ d2, bool self_pass) {
+    for (int i = 0; i < L && !done; ++i)
+    {
+      const int s0 = a.sphere_start[i], s1 = a.sphere_start[i + 1];
+      if (s1 <= s0 || (self_pass && !a.self_enabled[i]))
+        continue;
+      const unsigned left = a.max_contacts - count;
+      const unsigned num_coll = a.max_per_pair < left ? a.max_per_pair : left;
+      unsigned nc = 0;
+      bool coll = false;
+      for (int k = s0; k < s1; ++k)
+      {
+        // the world threshold is the sphere's threshold; the self pass uses the same predicate (self_enabled checked above)
+        if (sphereHitsField(h, d2, cen + 3 * k, m.spheres[k].thr))
+        {
+          coll = true;
+          if (num_coll == 0)
+            break;
+          b200sv_contact_rec& o = out[count + nc];
+          o.body_1 = i;
+          o.body_2 = self_pass ? -1 : -2;
+          o.sphere_1 = k - s0;
+          o.sphere_2 = -1;
+          o.pos[0] = cen[3 * k]; o.pos[1] = cen[3 * k + 1]; o.pos[2] = cen[3 * k + 2];
+          if (++nc >= num_coll)
+            break;
+        }
+      }
+      if (coll)
+      {
+        coll_any = true;
+        count += nc;
+        if (count >= a.max_contacts)
+          done = true;
+      }
+    }
+    if (count >= a.max_contacts)
+      done = true;
+  };
+  if ((a.flags & 2u) && !done)
+    fieldPass(a.d2_self, true);
+  if ((a.flags & 4u) && !done)
+  {
+    for (int i = 0; i < L && !done; ++i)
+    {
+      if (a.sphere_start[i + 1] <= a.sphere_start[i])
+        continue;
+      double ci[3];
+      posePoint<double>(T + a.glink_slot[i] * kLinkStrideWords, a.glink_bs[4 * i], a.glink_bs[4 * i + 1], a.glink_bs[4 * i + 2], ci[0],
+                        ci[1], ci[2]);
+      for (int j = i + 1; j < L && !done; ++j)
+      {
+        if (a.sphere_start[j + 1] <= a.sphere_start[j] || !a.intra[static_cast<size_t>(i) * L + j])
+          continue;
+        double cj[3];
+        posePoint<double>(T + a.glink_slot[j] * kLinkStrideWords, a.glink_bs[4 * j], a.glink_bs[4 * j + 1], a.glink_bs[4 * j + 2],
+                          cj[0], cj[1], cj[2]);
+        const double ex = ci[0] - cj[0], ey = ci[1] - cj[1], ez = ci[2] - cj[2];
+        // doBoundingSpheresIntersect, quirk kept: squared centre distance against the plain radius sum (types.cpp:416-417)
+        if (!(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)) <
+              (a.glink_bs[4 * i + 3] + a.glink_bs[4 * j + 3])))
+          continue;
+        int num_pair = 0;
+        for (int k = a.sphere_start[i]; k < a.sphere_start[i + 1] && num_pair < static_cast<int>(a.max_per_pair) && !done; ++k)
+          for (int l = a.sphere_start[j]; l < a.sphere_start[j + 1] && num_pair < static_cast<int>(a.max_per_pair); ++l)
+          {
+            const double gx = cen[3 * k] - cen[3 * l], gy = cen[3 * k + 1] - cen[3 * l + 1], gz = cen[3 * k + 2] - cen[3 * l + 2];
+            const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
+            if (dist < m.spheres[k].r + m.spheres[l].r)
+            {
+              coll_any = true;
+              b200sv_contact_rec& o = out[count++];
+              o.body_1 = i;
+              o.body_2 = j;
+              o.sphere_1 = k - a.sphere_start[i];
+              o.sphere_2 = l - a.sphere_start[j];
+              o.pos[0] = cen[3 * k]; o.pos[1] = cen[3 * k + 1]; o.pos[2] = cen[3 * k + 2];
+              ++num_pair;
+              if (count >= a.max_contacts)
+              {
+                done = true;
+                break;
+              }
+            }
+          }
+      }
+    }
+  }
+  if ((a.flags & 1u) && !done)
+    fieldPass(a.d2_world, false);
+  a.collision[st] = coll_any ? 1 : 0;
+  a.contact_count[st] = static_cast<int32_t>(count);
+}
+
 // cudaFuncSetAttribute is a host-side driver call: do it when the requirement grows, not on every launch.
 struct SmemGrant
 {
@@ -976,6 +1106,16 @@ cudaError_t launchGradients(const GradArgs& a, int grid, int block, size_t smem_
   if (e != cudaSuccess)
     return e;
   gradientKernel<<<grid, block, smem_bytes, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launchContacts(const ContactArgs& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
+{
+  static SmemGrant g;
+  cudaError_t e = ensureSmem(contactKernel, smem_bytes, g);
+  if (e != cudaSuccess)
+    return e;
+  contactKernel<<<grid, block, smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -72,6 +72,35 @@ struct GradArgs
 };
 cudaError_t launchGradients(const GradArgs& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 
+// contacts (checkCollision with req.contacts), FP64, exact blob
+struct b200sv_contact_rec  // = b200sv_contact of include/b200sv.h
+{
+  int32_t body_1, body_2, sphere_1, sphere_2;
+  double pos[3];
+};
+struct ContactArgs
+{
+  const uint8_t* model;
+  int model_bytes;
+  const double* q;
+  unsigned long long n_states;
+  const uint16_t* d2_world;
+  const uint16_t* d2_self;
+  uint32_t flags;
+  unsigned max_contacts, max_per_pair;
+  int n_glinks;
+  const int32_t* sphere_start;   // [n_glinks + 1]
+  const int32_t* glink_slot;     // [n_glinks] device-link slot
+  const double* glink_bs;        // [n_glinks * 4] link-frame bounding sphere
+  const uint8_t* self_enabled;   // [n_glinks]
+  const uint8_t* intra;          // [n_glinks * n_glinks]
+  double* centers;               // [n * n_spheres * 3] scratch
+  uint8_t* collision;            // [n]
+  int32_t* contact_count;        // [n]
+  b200sv_contact_rec* contacts;  // [n * max_contacts]
+};
+cudaError_t launchContacts(const ContactArgs& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+
 // fast_check.cu: the FP32 pass for groups of fixed / revolute / prismatic joints (a.model = the fast blob)
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);

@@ -307,6 +307,19 @@ class StateValidityEngine:
         buf = np.frombuffer(bytes(raw), np.uint8).copy()
         self._check(self.L.b200sv_field_read_df(self.h, int(which), _u8p(buf), buf.size))
 
+    CONTACT_DTYPE = np.dtype([("body_1", np.int32), ("body_2", np.int32), ("sphere_1", np.int32), ("sphere_2", np.int32),
+                              ("pos", np.float64, 3)])
+
+    def check_contacts(self, q, flags=CHECK_ALL, max_contacts=1, max_contacts_per_pair=1):
+        """Batched checkCollision with req.contacts: (collision [n], contact_count [n], contacts [n, max_contacts])."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, self.n_group_vars)
+        n = q.shape[0]
+        col, cnt = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        con = np.zeros((n, max_contacts), self.CONTACT_DTYPE)
+        self._check(self.L.b200sv_check_contacts(self.h, _dp(q), n, int(flags), int(max_contacts), int(max_contacts_per_pair),
+                                                 _u8p(col), _ip(cnt), con.ctypes.data_as(C.c_void_p)))
+        return col, cnt, con
+
     def gather_roofline(self, n_reads=1 << 28, iters=3):
         g = C.c_double(0.0)
         self._check(self.L.b200sv_gather_roofline(self.h, n_reads, iters, C.byref(g)))
@@ -328,6 +341,13 @@ class CollisionRequest:  # collision_detection/include/moveit/collision_detectio
 
 
 @dataclass
+class Contact:  # collision_common.hpp:80-145 (the fields the distance-field detector fills)
+    pos: np.ndarray = None
+    body_name_1: str = ""
+    body_name_2: str = ""
+
+
+@dataclass
 class CollisionResult:  # collision_common.hpp:334-370
     collision: bool = False
     contact_count: int = 0
@@ -344,17 +364,34 @@ class CollisionEnvB200:
     def __init__(self, engine: StateValidityEngine, group_name: str):
         self.engine, self.group_name = engine, group_name
 
-    def _single(self, res, state, flags):
-        if self.contacts_requested:
-            raise B200svError(_lib.ERR_UNSUPPORTED, "contact reporting is not implemented (SURVEY.md 8f rank 4)")
-        valid = self.engine.check_batch(np.asarray(state, np.float64).reshape(1, -1), flags)[0]
-        res.collision = res.collision or (not bool(valid))
+    def _body_name(self, i):
+        names = self.engine.link_names()
+        gi = self.engine.model_arrays()["glink_index"]
+        first = {int(g): k for k, g in reversed(list(enumerate(gi)))}
+        return names[gi[i]] if first[int(gi[i])] == i else "attached_%d" % i  # attached bodies carry no name in the ABI
 
-    contacts_requested = False
+    def _single(self, res, state, flags):
+        q = np.asarray(state, np.float64).reshape(1, -1)
+        if self._req.contacts:
+            # contact maps as the reference fills them (collision_env_distance_field.cpp:313-331, 596-621, 1604-1623)
+            left = max(int(self._req.max_contacts) - res.contact_count, 0)
+            if left == 0:
+                return
+            col, cnt, con = self.engine.check_contacts(q, flags, left, int(self._req.max_contacts_per_pair))
+            res.collision = res.collision or bool(col[0])
+            for k in range(int(cnt[0])):
+                c = con[0, k]
+                n1 = self._body_name(int(c["body_1"]))
+                n2 = {-1: "self", -2: "environment"}.get(int(c["body_2"])) or self._body_name(int(c["body_2"]))
+                res.contacts.setdefault((n1, n2), []).append(Contact(pos=np.array(c["pos"]), body_name_1=n1, body_name_2=n2))
+                res.contact_count += 1
+            return
+        valid = self.engine.check_batch(q, flags)[0]
+        res.collision = res.collision or (not bool(valid))
 
     def _gate(self, req):
         # an unknown group checks nothing (collision_env_distance_field.cpp:716-720 logs and returns)
-        self.contacts_requested = bool(req.contacts)
+        self._req = req
         return req.group_name == self.group_name
 
     def checkSelfCollision(self, req, res, state):

@@ -358,6 +358,22 @@ class OracleEnv:
                                        _p(d, C.c_double), _p(g, C.c_double), _p(t, C.c_uint8), _p(c, C.c_double))
         return d, g, t, c
 
+    CONTACT_DTYPE = np.dtype([("body_1", np.int32), ("body_2", np.int32), ("sphere_1", np.int32), ("sphere_2", np.int32),
+                              ("pos", np.float64, 3)])
+
+    def check_contacts(self, q, flags=7, max_contacts=1, max_contacts_per_pair=1):
+        """checkCollision with req.contacts = true: (collision [n], contact_count [n], contacts [n, max_contacts])."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, max(self.group.variable_count, 1))
+        n = q.shape[0]
+        col, cnt = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        con = np.zeros((n, max(max_contacts, 1)), self.CONTACT_DTYPE)
+        con["body_1"] = con["body_2"] = con["sphere_1"] = con["sphere_2"] = -9
+        self.L.orc_check_contacts(C.byref(self.robot), C.byref(self.cm), self.world.h, self.self_field.h,
+                                  _p(self.base_positions, C.c_double), _p(q, C.c_double), C.c_size_t(n), int(flags),
+                                  int(max_contacts), int(max_contacts_per_pair), _p(col, C.c_uint8), _p(cnt, C.c_int32),
+                                  con.ctypes.data_as(C.c_void_p))
+        return col, cnt, con
+
     def sphere_centers(self, q1):
         q1 = np.ascontiguousarray(q1, np.float64)
         out = np.zeros((self.n_spheres, 3))

@@ -1051,6 +1051,149 @@ void orc_collision_gradients(const orc_robot* r, const orc_collision_model* cm, 
   scratch_free(&s);
 }
 
+/* ------------------------------------------------------------------------------------------------------
+ * CollisionEnvDistanceField::checkCollision with req.contacts = true (collision_env_distance_field.cpp:1389-1411):
+ * getSelfCollisions (:274-353) -> getIntraGroupCollisions (:430-642) -> getEnvironmentCollisions (:1561-1643), each
+ * stopping the sequence once res.contact_count >= req.max_contacts; the contact-listing overload of
+ * getCollisionSphereCollision (collision_distance_field_types.cpp:238-271).
+ * A contact: pos = centre of the colliding sphere (of body 1), body_1 = dfce entry index, body_2 = the other entry
+ * (intra), -1 = "self", -2 = "environment"; sphere_1 / sphere_2 = indices into the entry's sphere list (-1: none).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct
+{
+  int32_t body_1, body_2, sphere_1, sphere_2;
+  double pos[3];
+} orc_contact;
+
+static int field_contacts(const orc_pdf* f, const orc_collision_model* cm, int i, const double* centers, unsigned num_coll,
+                          int* colls, int* n_colls)
+{ /* getCollisionSphereCollision(..., num_coll, colls): types.cpp:238-271 */
+  *n_colls = 0;
+  const double maxv = cm->max_propagation_distance, tol = cm->collision_tolerance;
+  for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1]; ++k)
+  {
+    double grad[3];
+    int inb;
+    const double* c = centers + 3 * k;
+    const double dist = orc_pdf_get_distance_gradient(f, c[0], c[1], c[2], grad, &inb);
+    if (maxv > dist && (cm->sphere_radius[k] - dist > tol))
+    {
+      if (num_coll == 0)
+        return 1;
+      colls[(*n_colls)++] = k - cm->sphere_start[i];
+      if ((unsigned)*n_colls >= num_coll)
+        return 1;
+    }
+  }
+  return *n_colls > 0;
+}
+
+void orc_check_contacts(const orc_robot* r, const orc_collision_model* cm, const orc_pdf* world, const orc_pdf* self,
+                        const double* base_positions, const double* q, size_t n, int flags, unsigned max_contacts,
+                        unsigned max_contacts_per_pair, uint8_t* collision, int32_t* contact_count, orc_contact* contacts)
+{
+  const int L = cm->n_glinks, S = cm->sphere_start[L];
+  orc_scratch s;
+  scratch_alloc(&s, r, cm);
+  int* colls = (int*)malloc((size_t)(S + 1) * sizeof(int));
+  for (size_t st = 0; st < n; ++st)
+  {
+    orc_contact* out = contacts + st * (size_t)max_contacts;
+    unsigned count = 0;
+    int coll_any = 0, done = 0;
+    memcpy(s.positions, base_positions, (size_t)r->n_vars * sizeof(double));
+    set_group_positions(r, s.positions, q + st * (size_t)r->n_group_vars);
+    fk_links(r, s.positions, s.link_T);
+    for (int i = 0; i < L; ++i)
+    {
+      const double* T = s.link_T + 16 * cm->glink_index[i];
+      transform_point(T, cm->bs_center + 3 * i, s.bs_centers + 3 * i);
+      for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1]; ++k)
+        transform_point(T, cm->sphere_rel + 3 * k, s.centers + 3 * k);
+    }
+    for (int pass = 0; pass < 3 && !done; ++pass)
+    {
+      if (pass == 0 || pass == 2)
+      { /* getSelfCollisions / getEnvironmentCollisions */
+        const orc_pdf* f = pass == 0 ? self : world;
+        if (!f || !(flags & (pass == 0 ? ORC_CHECK_SELF : ORC_CHECK_WORLD)))
+          continue;
+        for (int i = 0; i < L && !done; ++i)
+        {
+          if (!cm->has_geometry[i] || (pass == 0 && !cm->self_enabled[i]))
+            continue;
+          const unsigned left = max_contacts - count;
+          int nc = 0;
+          const int coll = field_contacts(f, cm, i, s.centers, max_contacts_per_pair < left ? max_contacts_per_pair : left,
+                                          colls, &nc);
+          if (coll)
+          {
+            coll_any = 1;
+            for (int c = 0; c < nc; ++c)
+            {
+              orc_contact* o = out + count++;
+              o->body_1 = i;
+              o->body_2 = pass == 0 ? -1 : -2;
+              o->sphere_1 = colls[c];
+              o->sphere_2 = -1;
+              memcpy(o->pos, s.centers + 3 * (cm->sphere_start[i] + colls[c]), 3 * sizeof(double));
+            }
+            if (count >= max_contacts)
+              done = 1;
+          }
+        }
+        if (count >= max_contacts)
+          done = 1;
+      }
+      else
+      { /* getIntraGroupCollisions */
+        if (!(flags & ORC_CHECK_INTRA))
+          continue;
+        for (int i = 0; i < L && !done; ++i)
+          for (int j = i + 1; j < L && !done; ++j)
+          {
+            if (!cm->has_geometry[i] || !cm->has_geometry[j] || !cm->intra_enabled[(size_t)i * L + j])
+              continue;
+            const double* ci = s.bs_centers + 3 * i;
+            const double* cj = s.bs_centers + 3 * j;
+            const double ex = ci[0] - cj[0], ey = ci[1] - cj[1], ez = ci[2] - cj[2];
+            if (!((ex * ex + ey * ey + ez * ez) < (cm->bs_radius[i] + cm->bs_radius[j])))
+              continue;
+            int num_pair = 0; /* res.contacts has no entry for this pair yet: every state starts from an empty result */
+            for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1] && num_pair < (int)max_contacts_per_pair && !done; ++k)
+              for (int l = cm->sphere_start[j]; l < cm->sphere_start[j + 1] && num_pair < (int)max_contacts_per_pair; ++l)
+              {
+                const double gx = s.centers[3 * k] - s.centers[3 * l];
+                const double gy = s.centers[3 * k + 1] - s.centers[3 * l + 1];
+                const double gz = s.centers[3 * k + 2] - s.centers[3 * l + 2];
+                const double dist = sqrt(gx * gx + gy * gy + gz * gz);
+                if (dist < cm->sphere_radius[k] + cm->sphere_radius[l])
+                {
+                  coll_any = 1;
+                  orc_contact* o = out + count++;
+                  o->body_1 = i;
+                  o->body_2 = j;
+                  o->sphere_1 = k - cm->sphere_start[i];
+                  o->sphere_2 = l - cm->sphere_start[j];
+                  memcpy(o->pos, s.centers + 3 * k, 3 * sizeof(double));
+                  num_pair++;
+                  if (count >= max_contacts)
+                  {
+                    done = 1;
+                    break;
+                  }
+                }
+              }
+          }
+      }
+    }
+    collision[st] = (uint8_t)coll_any;
+    contact_count[st] = (int32_t)count;
+  }
+  free(colls);
+  scratch_free(&s);
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

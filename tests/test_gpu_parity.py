@@ -554,3 +554,42 @@ def test_df_stream_round_trip_and_reference_format():
     with pytest.raises(mb.B200svError):
         eng.field_read_df(write_df_occupancy(bad, occ2))
     eng.close()
+
+
+# ---- contacts (checkCollision with req.contacts) ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("limits", [(1, 1), (4, 2), (10, 3), (64, 64)])
+def test_contacts_equal_oracle(c1, limits):
+    """Which contacts are reported (and how many) under max_contacts / max_contacts_per_pair is the reference's choice."""
+    eng, env, cloud, q = c1
+    mc, mp = limits
+    n = 4000
+    for flags in (ALL, S | I, W):
+        col, cnt, con = eng.check_contacts(q[:n], flags, mc, mp)
+        rcol, rcnt, rcon = env.check_contacts(q[:n], flags, mc, mp)
+        assert np.array_equal(col, rcol) and np.array_equal(cnt, rcnt), flags
+        ref, _ = env.check(q[:n], flags)
+        assert np.array_equal(col, ref)  # res.collision is the same boolean with or without contacts
+        for i in np.nonzero(cnt)[0]:
+            a, b = con[i, : cnt[i]], rcon[i, : cnt[i]]
+            for f in ("body_1", "body_2", "sphere_1", "sphere_2"):
+                assert np.array_equal(a[f], b[f]), (flags, i, f)
+            assert np.allclose(a["pos"], b["pos"], atol=1e-12)
+        assert cnt.max() <= mc and (cnt[col == 0] == 0).all()
+
+
+@pytest.mark.gpu
+def test_contact_map_of_the_mirror(c1):
+    eng, env, cloud, q = c1
+    cenv = mb.CollisionEnvB200(eng, "panda_arm")
+    req = mb.CollisionRequest(group_name="panda_arm", contacts=True, max_contacts=8, max_contacts_per_pair=2)
+    ref, _ = env.check(q[:200], ALL)
+    seen = set()
+    for i in np.nonzero(ref[:200])[0][:30]:
+        r = mb.CollisionResult()
+        cenv.checkCollision(req, r, q[i])
+        assert r.collision and 0 < r.contact_count <= 8
+        assert sum(len(v) for v in r.contacts.values()) == r.contact_count
+        assert all(len(v) <= 2 for v in r.contacts.values())
+        seen |= {k[1] for k in r.contacts}
+    assert "environment" in seen
