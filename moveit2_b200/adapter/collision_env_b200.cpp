@@ -301,6 +301,16 @@ CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::
 
   const b200sv_field_cfg f = fieldCfg(size_, origin_, resolution_, max_propogation_distance_, collision_tolerance_);
   auto gc = std::make_shared<GroupContext>();
+  for (int i = 0; i < n; ++i)
+  {
+    gc->entry_names.push_back(glinks[i]->getName());
+    gc->entry_is_attached.push_back(false);
+  }
+  for (const BodyEntry& e : body_entries)
+  {
+    gc->entry_names.push_back(e.name);
+    gc->entry_is_attached.push_back(true);
+  }
   int device = 0;  // one process per GPU: honour CUDA_VISIBLE_DEVICES / the launcher's LOCAL_RANK
   if (const char* lr = std::getenv("LOCAL_RANK"))
     device = std::atoi(lr);
@@ -430,10 +440,45 @@ void CollisionEnvB200::checkSingle(const CollisionRequest& req, CollisionResult&
   const moveit::core::JointModelGroup* jmg = robot_model_->getJointModelGroup(req.group_name);
   if (!jmg)
     return;  // the reference logs and checks nothing (:716-720)
-  if (req.contacts)
-    RCLCPP_WARN_ONCE(getLogger(), "contact reporting is not implemented by the B200 detector; only res.collision is set");
   std::vector<double> q(jmg->getVariableCount());
   state.copyJointGroupPositions(jmg, q.data());
+  if (req.contacts)
+  {  // the contacts the reference would report, in its order and under its limits (:298-339, 571-638, 1589-1629)
+    std::shared_ptr<GroupContext> gc = getContext(req.group_name, state, acm);
+    if (!gc || res.contact_count >= req.max_contacts)
+      return;
+    const uint32_t left = static_cast<uint32_t>(req.max_contacts - res.contact_count);
+    std::vector<b200sv_contact> cons(left);
+    uint8_t coll = 0;
+    int32_t count = 0;
+    if (b200sv_check_contacts(gc->ctx, q.data(), 1, flags, left, static_cast<uint32_t>(req.max_contacts_per_pair), &coll,
+                              &count, cons.data()) != B200SV_OK)
+    {
+      RCLCPP_ERROR(getLogger(), "b200sv_check_contacts failed: %s", b200sv_last_error(gc->ctx));
+      return;
+    }
+    res.collision = res.collision || coll;
+    for (int32_t k = 0; k < count; ++k)
+    {
+      Contact con;
+      con.pos = Eigen::Vector3d(cons[k].pos[0], cons[k].pos[1], cons[k].pos[2]);
+      con.body_name_1 = gc->entry_names[cons[k].body_1];
+      con.body_type_1 = gc->entry_is_attached[cons[k].body_1] ? BodyTypes::ROBOT_ATTACHED : BodyTypes::ROBOT_LINK;
+      if (cons[k].body_2 >= 0)
+      {
+        con.body_name_2 = gc->entry_names[cons[k].body_2];
+        con.body_type_2 = gc->entry_is_attached[cons[k].body_2] ? BodyTypes::ROBOT_ATTACHED : BodyTypes::ROBOT_LINK;
+      }
+      else
+      {
+        con.body_name_2 = cons[k].body_2 == -1 ? "self" : "environment";
+        con.body_type_2 = cons[k].body_2 == -1 ? BodyTypes::ROBOT_LINK : BodyTypes::WORLD_OBJECT;
+      }
+      res.contacts[std::make_pair(con.body_name_1, con.body_name_2)].push_back(con);
+      ++res.contact_count;
+    }
+    return;
+  }
   uint8_t bit = 0;
   if (checkCollisionBatch(req, state, acm, q.data(), 1, &bit, flags) && !(bit & 1))
     res.collision = true;

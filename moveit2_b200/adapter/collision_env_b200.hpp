@@ -75,6 +75,8 @@ private:
     std::vector<double> non_group_values;  // compareCacheEntryToState (collision_env_distance_field.cpp:1254-1291)
     std::vector<int> non_group_indices;
     AllowedCollisionMatrix acm;
+    std::vector<std::string> entry_names;  // dfce entries: the links, then one per shape of every attached body
+    std::vector<bool> entry_is_attached;
   };
   void initialize();
   /// Flatten RobotModel + JointModelGroup + ACM + BodyDecompositions into b200sv_robot / b200sv_collision_model
