@@ -1233,8 +1233,12 @@ int launchRecheck(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t
   CheckArgs<FT> a = baseArgs<FT>(c, d_q0, n_total, flags, d_bitmap0);
   a.model = c->d_blob_d;
   a.model_bytes = (int)c->blob_d.size();
-  CU(c, launchCheck<FT>(a, true, true, c->sm_count * c->cfg_list.blocks_per_sm, c->cfg_list.warps * 32,
-                        c->cfg_list.smem, s));
+  static const bool warp_per_state = !(getenv("B200SV_RECHECK_WARP") && atoi(getenv("B200SV_RECHECK_WARP")) == 0);
+  if (warp_per_state && (size_t)align16(a.model_bytes) + 4 * (size_t)c->state_stride_d * 8 <= (size_t)c->smem_optin)
+    CU(c, launchRecheckWarp<FT>(a, c->sm_count * 2, c->state_stride_d, s));
+  else
+    CU(c, launchCheck<FT>(a, true, true, c->sm_count * c->cfg_list.blocks_per_sm, c->cfg_list.warps * 32,
+                          c->cfg_list.smem, s));
   return B200SV_OK;
 }
 

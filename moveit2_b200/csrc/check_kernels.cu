@@ -1002,6 +1002,51 @@ __global__ void __launch_bounds__(64) contactKernel(ContactArgs a)
   a.contact_count[st] = static_cast<int32_t>(count);
 }
 
+// Exact pass over the recheck list, ONE WARP PER STATE: the list is short (about one state in 7 000), so what matters is
+// the latency of a single state, not throughput.  Lane 0 runs the FP64 forward kinematics into shared memory, then the
+// 32 lanes share the spheres and the cluster pairs of that one state.  Same device functions (same arithmetic) as
+// checkKernel<double, ., true>.
+template <typename FT>
+__global__ void __launch_bounds__(128) recheckWarpKernel(CheckArgs<FT> a)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
+  const ModelHeader<double>& h = *m.h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  double* T = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(warp) * h.state_stride;
+  const bool do_world = (a.flags & 1u) != 0, do_self = (a.flags & 2u) != 0, do_intra = (a.flags & 4u) != 0;
+  const typename Combined<FT>::type* __restrict__ field = static_cast<const typename Combined<FT>::type*>(a.field);
+  const unsigned n = *a.list_count < a.list_cap ? *a.list_count : a.list_cap;
+  for (unsigned i = blockIdx.x * warps + warp; i < n; i += gridDim.x * warps)
+  {
+    const unsigned long long state = a.list[i];
+    if (lane == 0)
+      fkState<double>(m, a.q + state * h.n_group_vars, T);
+    __syncwarp();
+    bool hit = false, amb = false;
+    if (do_world | do_self)
+      for (int k = lane; k < h.n_spheres_padded; k += 32)
+        sphereChunk<double, FT, 1>(m, T, k, do_world, do_self, field, true, hit, amb);
+    if (do_intra && !__any_sync(kFull, hit))
+      for (int p = lane; p < h.n_pairs; p += 32)
+      {
+        const PairRec pr = m.pairs[p];
+        const BsRec<double>& A = m.bs[pr.a];
+        double Ta[12], ax, ay, az;
+        load12(T + A.slot * kLinkStrideWords, Ta);
+        posePoint<double>(Ta, A.tx, A.ty, A.tz, ax, ay, az);
+        bool live = false, certain = false;
+        pairCull<double>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr.quirk_free != 0, live, certain);
+        if (live)
+          pairItem<double>(m, T, pr, certain, hit, amb);
+      }
+    const bool any = __any_sync(kFull, hit);
+    if (lane == 0 && !any)
+      atomicOr(a.bitmap + (state >> 5), 1u << (state & 31));
+    __syncwarp();  // T is rewritten for the next list entry
+  }
+}
+
 // cudaFuncSetAttribute is a host-side driver call: do it when the requirement grows, not on every launch.
 struct SmemGrant
 {
@@ -1042,6 +1087,22 @@ int regsOf()
   return fa.numRegs;
 }
 }  // namespace
+
+template <typename FT>
+cudaError_t launchRecheckWarp(const CheckArgs<FT>& a, int grid, int state_stride, cudaStream_t stream)
+{
+  static SmemGrant g;
+  const int block = 128;
+  const size_t smem = ((static_cast<size_t>(a.model_bytes) + 15) & ~static_cast<size_t>(15)) +
+                      static_cast<size_t>(block / 32) * state_stride * sizeof(double);
+  cudaError_t e = ensureSmem(recheckWarpKernel<FT>, smem, g);
+  if (e != cudaSuccess)
+    return e;
+  recheckWarpKernel<FT><<<grid, block, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+template cudaError_t launchRecheckWarp<uint8_t>(const CheckArgs<uint8_t>&, int, int, cudaStream_t);
+template cudaError_t launchRecheckWarp<uint16_t>(const CheckArgs<uint16_t>&, int, int, cudaStream_t);
 
 int checkPerWarpBytes(bool fp64, int state_stride)
 {

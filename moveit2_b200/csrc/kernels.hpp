@@ -50,6 +50,9 @@ struct FkArgs
 template <typename FT>
 cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int grid, int block, size_t smem_bytes,
                         cudaStream_t stream);
+// exact pass over the recheck list, one warp per state (latency of a short list)
+template <typename FT>
+cudaError_t launchRecheckWarp(const CheckArgs<FT>& a, int grid, int state_stride, cudaStream_t stream);
 int checkKernelRegs(bool fp64, bool from_list, int field_bytes);
 int checkPerWarpBytes(bool fp64, int state_stride);  // shared memory one warp of the check kernel needs
 // K5: per-sphere distance / gradient / type (getCollisionGradients), FP64, exact blob
