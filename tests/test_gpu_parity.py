@@ -593,3 +593,24 @@ def test_contact_map_of_the_mirror(c1):
         assert all(len(v) <= 2 for v in r.contacts.values())
         seen |= {k[1] for k in r.contacts}
     assert "environment" in seen
+
+
+@pytest.mark.gpu
+def test_empty_and_invalid_inputs_of_the_batched_entry_points(c1):
+    eng, env, cloud, q = c1
+    V = eng.n_group_vars
+    valid, first, n = eng.check_motions(np.zeros((0, V)), np.zeros((0, V)), 0.1)
+    assert valid.shape == (0,) and n == 0
+    d, g, t, c, loc = eng.collision_gradients(np.zeros((0, V)))
+    assert d.shape == (0, eng.n_spheres)
+    col, cnt, con = eng.check_contacts(np.zeros((0, V)), max_contacts=3)
+    assert col.shape == (0,) and con.shape == (0, 3)
+    with pytest.raises(mb.B200svError):
+        eng.check_motions(q[:1], q[1:2], 0.0)       # longest valid segment must be positive
+    with pytest.raises(mb.B200svError):
+        eng.check_contacts(q[:1], max_contacts=0)
+    with pytest.raises(mb.B200svError):
+        eng.check_contacts(q[:1], flags=0, max_contacts=1)
+    # one edge whose end points coincide: only s2 is checked
+    valid, first, n = eng.check_motions(q[:1], q[:1], 0.1)
+    assert n == 1 and bool(valid[0]) == bool(eng.check_batch(q[:1])[0])
