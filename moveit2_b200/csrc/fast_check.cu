@@ -399,28 +399,26 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
       }
     };
     float T[12];
-    int4 n0 = reinterpret_cast<const int4*>(m.links)[0], n1 = reinterpret_cast<const int4*>(m.links)[1];
-    double2 nab = reinterpret_cast<const double2*>(m.links)[2];
-    float4 no = reinterpret_cast<const float4*>(m.links)[3];
-    double q_next = n0.y >= 0 ? qrow[n0.y] : 0.0;
+    double q_next;
+    {
+      const int k_first = reinterpret_cast<const int*>(m.links)[1];
+      q_next = k_first >= 0 ? qrow[k_first] : 0.0;
+    }
     // ---- FK, and the field checks of every link as soon as its transform exists --------------------------------------
     for (int l = 0; l < h.n_links; ++l)
     {
       const int4* Li = reinterpret_cast<const int4*>(m.links + l);
       const float4* Lf = reinterpret_cast<const float4*>(m.links + l);
-      const int4 m0 = n0;  // type, k, parent_off, store_off     (read one link ahead: the type branch never waits)
-      const int4 m1 = n1;  // h0, h1, c0, c1
-      const double2 ab = nab;
-      const float4 o = no;
-      n0 = Li[11];  // the table ends with a sentinel record
-      n1 = Li[12];
-      nab = reinterpret_cast<const double2*>(Li)[13];
-      no = Lf[14];
+      const int4 m0 = Li[0];  // type, k, parent_off, store_off
+      const int4 m1 = Li[1];  // h0, h1, c0, c1
+      const double2 ab = reinterpret_cast<const double2*>(Li)[2];
+      const float4 o = Lf[3];
+      const int k_next = reinterpret_cast<const int*>(Li + 11)[1];  // the table ends with a sentinel record
       const float4 c0 = Lf[4], c1 = Lf[5], c2 = Lf[6];  // a0[0..8], a1[0..2]
       float M[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x };
       float mt[3] = { o.x, o.y, o.z };
       const double q_cur = q_next;
-      q_next = n0.y >= 0 ? qrow[n0.y] : 0.0;  // the NEXT link's joint value
+      q_next = k_next >= 0 ? qrow[k_next] : 0.0;  // the NEXT link's joint value: in flight during this link's work
       if (m0.x != FIXED)
       {
         // setJointGroupPositions / updateMimicJoints in double, then narrowed (k < 0: a = 0, the value is b)
