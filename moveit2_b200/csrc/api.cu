@@ -471,7 +471,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   const double half_spacing = ldexp(1.0, e2 - 11);         // spacing of half values below 2^e2
   const double half_slack = 2.0 * sqrt(3.0) * half_spacing + 0.01;
   std::vector<fast::Cluster> cl(bs.size());
-  std::vector<fast::PSphere> ps(bs.size() * fast::kClusterSpheres);
+  std::vector<fast::PSphere> ps(bs.size() * fast::kPSphereStride);
   for (size_t i = 0; i < bs.size(); ++i)
   {
     if (bs[i].s1 - bs[i].s0 > fast::kClusterSpheres)
@@ -497,7 +497,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
         Q.z = (float)S.z;
         Q.r_v = (float)(S.r * oo);
       }
-      ps[i * fast::kClusterSpheres + k] = Q;
+      ps[i * fast::kPSphereStride + k] = Q;
     }
   }
   std::vector<fast::Group> fg(groups.size());

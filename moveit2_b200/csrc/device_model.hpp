@@ -130,6 +130,8 @@ struct alignas(16) Hot
 };
 
 constexpr int kClusterSpheres = 4;  // a cluster holds at most this many spheres; PSphere rows are padded to it
+constexpr int kPSphereStride = 5;   // PSphere entries per cluster row: 80 bytes, so 8 lanes reading 8 different rows
+                                    // with one 128-bit access touch 8 distinct 16-byte bank groups
 
 // A cluster's tight-sphere centre in its link frame: posed in the link loop and parked in shared memory
 // ([cluster][x, y, z][lane]) for the level-1 cull of the pair phase.
@@ -138,7 +140,7 @@ struct alignas(16) Cluster
   float tx, ty, tz, pad;
 };
 
-// Pair phase: sphere k of cluster c is PSphere[kClusterSpheres * c + k].  Padding entries have r_v = -1e30: their
+// Pair phase: sphere k of cluster c is PSphere[kPSphereStride * c + k].  Padding entries have r_v = -1e30: their
 // distance test can never pass.
 struct alignas(16) PSphere
 {

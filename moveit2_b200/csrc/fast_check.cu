@@ -210,7 +210,7 @@ __device__ __forceinline__ void pairItem(const FModel& m, const TStore<kGlobal>&
 #pragma unroll
   for (int j = 0; j < kC; ++j)
   {
-    const float4 sp = reinterpret_cast<const float4*>(m.ps)[kC * cb + j];
+    const float4 sp = reinterpret_cast<const float4*>(m.ps)[fast::kPSphereStride * cb + j];
     pose(Tb, sp.x, sp.y, sp.z, bx[j], by[j], bz[j]);
     br[j] = sp.w;
   }
@@ -219,7 +219,7 @@ __device__ __forceinline__ void pairItem(const FModel& m, const TStore<kGlobal>&
 #pragma unroll
   for (int i = 0; i < kC; ++i)
   {
-    const float4 sp = reinterpret_cast<const float4*>(m.ps)[kC * ca + i];
+    const float4 sp = reinterpret_cast<const float4*>(m.ps)[fast::kPSphereStride * ca + i];
     float ax, ay, az;
     pose(Ta, sp.x, sp.y, sp.z, ax, ay, az);
 #pragma unroll
