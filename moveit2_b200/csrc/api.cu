@@ -511,10 +511,10 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
     fast::Pair P{};
     const double rt = (A.tr + B.tr + tight_eps) * oo + half_slack;
     P.rt2_h = halfBitsUp(rt * rt * (1.0 + 4.0 / 1024.0));  // + the half rounding of the squared sum itself
-    P.a_off = store_off[A.slot];
-    P.b_off = store_off[B.slot];
-    P.a = pairs[p].a;
-    P.b = pairs[p].b;
+    if (pairs[p].a > 0xffff || pairs[p].b > 0xffff || store_off[A.slot] > 0xffff || store_off[B.slot] > 0xffff)
+      return false;  // beyond the packed pair record: the generic kernel takes the group
+    P.ab = (unsigned)pairs[p].a | ((unsigned)pairs[p].b << 16);
+    P.offs = (unsigned)store_off[A.slot] | ((unsigned)store_off[B.slot] << 16);
     P.quirk = -1;
     if (!pairs[p].quirk_free)
     {

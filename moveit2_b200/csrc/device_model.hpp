@@ -153,15 +153,15 @@ struct alignas(16) Group  // pairs [p0, p1) share cluster a
   int a, p0, p1, pad;
 };
 
-struct alignas(16) Pair
+struct alignas(16) Pair  // 16 bytes: ONE 128-bit read per level-1 lane and per work item
 {
   unsigned rt2_h;    // (tr_a + tr_b + slack)^2 in cells^2 as half bits, rounded up (the level-1 cull runs in half)
-  int a, b;          // Cluster indices
-  int a_off, b_off;  // transform offsets of the two links
+  unsigned ab;       // Cluster indices a | b << 16
+  unsigned offs;     // transform offsets of the two links (words), a_off | b_off << 16
   int quirk;         // -1: the reference's link-level cull provably passes whenever the tight spheres are this close;
                      // else index of the Quirk record to evaluate
-  int pad0, pad1;
 };
+static_assert(sizeof(Pair) == 16, "fast::Pair layout");
 
 // doBoundingSpheresIntersect on the LINKS' bounding spheres (types.cpp:408-418), quirk kept: squared centre distance
 // (m^2) against the plain radius sum (m).  In cells: |Ca - Cb|_v^2 < (Ra + Rb) * oo^2.

@@ -187,9 +187,9 @@ __device__ __forceinline__ void pairItem(const FModel& m, const TStore<kGlobal>&
 {
   constexpr int kC = fast::kClusterSpheres;
   const fast::Header& h = *m.h;
-  const float4 p0 = reinterpret_cast<const float4*>(m.pairs + p)[0];  // rt2, a, b, a_off
-  const int4 p1 = reinterpret_cast<const int4*>(m.pairs + p)[1];      // b_off, quirk
-  const int ca = __float_as_int(p0.y), cb = __float_as_int(p0.z), a_off = __float_as_int(p0.w), b_off = p1.x;
+  const uint4 pr = reinterpret_cast<const uint4*>(m.pairs)[p];  // rt2, a | b << 16, a_off | b_off << 16, quirk
+  const int ca = pr.y & 0xffffu, cb = pr.y >> 16, a_off = pr.z & 0xffffu, b_off = pr.z >> 16;
+  const int4 p1 = make_int4(0, static_cast<int>(pr.w), 0, 0);
   float Ta[12], Tb[12];
   ts.load(a_off, state, Ta);
   ts.load(b_off, state, Tb);
@@ -522,9 +522,9 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
       {
         const int p = p0 + lane;
         const bool have = p < h.n_pairs;
-        const float4 pc = reinterpret_cast<const float4*>(m.pairs + (have ? p : 0))[0];  // rt2 (half bits), a, b, a_off
-        const int ca = __float_as_int(pc.y), cb = __float_as_int(pc.z);
-        const __half rt2 = __ushort_as_half(static_cast<unsigned short>(__float_as_uint(pc.x)));
+        const uint4 pc = reinterpret_cast<const uint4*>(m.pairs)[have ? p : 0];  // rt2 (half bits), a | b << 16, ...
+        const int ca = pc.y & 0xffffu, cb = pc.y >> 16;
+        const __half rt2 = __ushort_as_half(static_cast<unsigned short>(pc.x));
         const __half2 rt2_2 = __half2half2(rt2);
         const uint32_t* ax = reinterpret_cast<const uint32_t*>(rep_x + ca * kRepStride);
         const uint32_t* bx = reinterpret_cast<const uint32_t*>(rep_x + cb * kRepStride);
