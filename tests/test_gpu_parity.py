@@ -614,3 +614,37 @@ def test_empty_and_invalid_inputs_of_the_batched_entry_points(c1):
     # one edge whose end points coincide: only s2 is checked
     valid, first, n = eng.check_motions(q[:1], q[:1], 0.1)
     assert n == 1 and bool(valid[0]) == bool(eng.check_batch(q[:1])[0])
+
+
+@pytest.mark.gpu
+def test_two_contexts_and_threads(c1):
+    """CollisionEnv check methods are const and called concurrently (planning_scene/test/test_multi_threaded.cpp:98-140):
+    two contexts (different robots) driven from four host threads give the same answers as serial calls."""
+    import threading
+    eng, env, cloud, q = c1
+    cfg = workloads.CONFIGS["C3"]
+    eng2, env2 = make_pair("dualarm", "arms", cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    cloud2 = workloads.make_cloud("C3")
+    eng2.field_add_points(cloud2)
+    lo, hi = eng2.group_bounds()
+    q2 = workloads.random_states(5, 20000, lo, hi)
+    want1, want2 = eng.check_batch(q), eng2.check_batch(q2)
+    out, errs = {}, []
+
+    def work(name, e, qq, reps):
+        try:
+            for r in range(reps):
+                out[(name, r)] = e.check_batch(qq)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(ex)
+
+    threads = [threading.Thread(target=work, args=("a%d" % i, eng, q, 5)) for i in range(2)] + \
+              [threading.Thread(target=work, args=("b%d" % i, eng2, q2, 5)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs
+    for (name, r), v in out.items():
+        assert np.array_equal(v, want1 if name.startswith("a") else want2), (name, r)
+    eng2.close()
