@@ -171,6 +171,10 @@ int b200sv_field_reset(b200sv_ctx* ctx, int which);
 int b200sv_field_add_points(b200sv_ctx* ctx, int which, const double* xyz, size_t n_points);
 /* removePointsFromField(): :198-219 (result equals a fresh build without those voxels, test_distance_field.cpp:508) */
 int b200sv_field_remove_points(b200sv_ctx* ctx, int which, const double* xyz, size_t n_points);
+/* updatePointsInField(): :130-175 -- voxels of old_xyz that are not voxels of new_xyz are removed, voxels of new_xyz that
+ * are not voxels of old_xyz are added (a voxel in both is left as it is), then the field is rebuilt. */
+int b200sv_field_update_points(b200sv_ctx* ctx, int which, const double* old_xyz, size_t n_old, const double* new_xyz,
+                               size_t n_new);
 /* Same two with xyz already in device memory, asynchronous on `cuda_stream` (a cudaStream_t). */
 int b200sv_field_add_points_device(b200sv_ctx* ctx, int which, const double* d_xyz, size_t n_points,
                                    void* cuda_stream);

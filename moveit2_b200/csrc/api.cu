@@ -1611,6 +1611,37 @@ int b200sv_field_remove_points(b200sv_ctx* c, int which, const double* xyz, size
   return pointsHost(c, which, xyz, n, false);
 }
 
+int b200sv_field_update_points(b200sv_ctx* c, int which, const double* old_xyz, size_t n_old, const double* new_xyz, size_t n_new)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if ((n_old && !old_xyz) || (n_new && !new_xyz))
+    return fail(c, B200SV_ERR_INVALID, "null point array");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const size_t n_words = (size_t)c->grid.nx * c->grid.ny * c->grid.wz;
+  if (2 * n_words * 4 > c->n_voxels * 2)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "grid too shallow for the update scratch (nz < 16)");
+  // two scratch bitmaps in the EDT's intermediate buffer: the voxels of the old and of the new point set
+  uint32_t* old_bits = reinterpret_cast<uint32_t*>(c->d_tmp);
+  uint32_t* new_bits = old_bits + n_words;
+  CU(c, cudaMemsetAsync(old_bits, 0, 2 * n_words * 4, c->stream));
+  CU(c, c->d_points.ensure(3 * std::max(n_old, n_new) + 3));
+  if (n_old)
+  {
+    CU(c, cudaMemcpyAsync(c->d_points.p, old_xyz, 3 * n_old * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, launchScatter(c->d_points.p, n_old, c->grid, old_bits, true, c->stream));
+  }
+  if (n_new)
+  {
+    CU(c, cudaMemcpyAsync(c->d_points.p, new_xyz, 3 * n_new * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, launchScatter(c->d_points.p, n_new, c->grid, new_bits, true, c->stream));
+  }
+  CU(c, launchUpdateOcc(c->fields[which].occ, old_bits, new_bits, n_words, c->stream));
+  return rebuildField(c, which);
+}
+
 int b200sv_field_add_points_device(b200sv_ctx* c, int which, const double* d_xyz, size_t n, void* cuda_stream)
 {
   int rc = checkWhich(c, which);

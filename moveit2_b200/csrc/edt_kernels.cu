@@ -322,6 +322,18 @@ __global__ void injectKernel(GridDev g, const int32_t* __restrict__ in, uint32_t
   }
 }
 
+// updatePointsInField (propagation_distance_field.cpp:130-175): occ' = (occ - (old \ new)) + (new \ old), word by word
+__global__ void updateOccKernel(uint32_t* __restrict__ occ, const uint32_t* __restrict__ old_bits,
+                                const uint32_t* __restrict__ new_bits, size_t n_words)
+{
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n_words;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    const uint32_t a = old_bits[i], b = new_bits[i];
+    occ[i] = (occ[i] & ~(a & ~b)) | (b & ~a);
+  }
+}
+
 int gridFor(size_t n, int block, int cap)
 {
   size_t b = (n + block - 1) / block;
@@ -336,6 +348,12 @@ cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint3
   if (n == 0)
     return cudaSuccess;
   scatterKernel<<<gridFor(n, 256, 148 * 16), 256, 0, s>>>(d_xyz, n, g, occ, set ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint32_t* new_bits, size_t n_words, cudaStream_t s)
+{
+  updateOccKernel<<<gridFor(n_words, 256, 148 * 8), 256, 0, s>>>(occ, old_bits, new_bits, n_words);
   return cudaGetLastError();
 }
 

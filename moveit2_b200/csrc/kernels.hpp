@@ -149,6 +149,8 @@ struct GridDev
 
 // occupancy bitmap: word ((x*ny + y)*wz + z/32), bit z%32
 cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint32_t* occ, bool set, cudaStream_t s);
+// occ' = (occ - (old \\ new)) + (new \\ old): updatePointsInField on bitmaps of the same layout
+cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint32_t* new_bits, size_t n_words, cudaStream_t s);
 // exact truncated EDT of the occupancy bitmap -> d2 (uint16, min(d^2, max_d2)) and this field's half of the
 // INTERLEAVED compact field (element 2 * voxel; `compact` arrives offset by 0 = world / 1 = self; uint8:
 // min(d^2, 255), uint16: d^2).  tmp: uint16 [nx*ny*nz] scratch.

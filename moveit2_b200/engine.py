@@ -210,6 +210,13 @@ class StateValidityEngine:
         p = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
         self._check(self.L.b200sv_field_remove_points(self.h, which, _dp(p), p.shape[0]))
 
+    def field_update_points(self, old_points, new_points, which=FIELD_WORLD):
+        """PropagationDistanceField::updatePointsInField."""
+        a = np.ascontiguousarray(old_points, np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(new_points, np.float64).reshape(-1, 3)
+        self._check(self.L.b200sv_field_update_points(self.h, which, _dp(a) if len(a) else None, a.shape[0],
+                                                      _dp(b) if len(b) else None, b.shape[0]))
+
     def field_add_points_device(self, d_ptr, n_points, which=FIELD_WORLD, stream=0):
         self._check(self.L.b200sv_field_add_points_device(self.h, which, C.c_void_p(d_ptr), n_points,
                                                           C.c_void_p(stream)))

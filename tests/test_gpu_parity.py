@@ -648,3 +648,29 @@ def test_two_contexts_and_threads(c1):
     for (name, r), v in out.items():
         assert np.array_equal(v, want1 if name.startswith("a") else want2), (name, r)
     eng2.close()
+
+
+@pytest.mark.gpu
+def test_field_update_points_equals_reference_set_semantics():
+    """updatePointsInField (propagation_distance_field.cpp:130-175): occupancy afterwards = the oracle's, incl. the
+    corner case of a voxel that is in both sets but not currently occupied (left alone)."""
+    eng, env, cloud, q = config_pair("C1", n_states=1)
+    rng = np.random.default_rng(3)
+    first = cloud[:1500]
+    eng.field_add_points(first)
+    env.world.add_points(first)
+    old = np.concatenate([first[:600], rng.uniform(-0.4, 0.4, size=(50, 3)) + (0, 0, 0.5)])   # 50 never added
+    new = np.concatenate([first[400:900] + rng.normal(0, 0.03, size=(500, 3)), old[-50:-25]])  # 25 in both, unoccupied
+    eng.field_update_points(old, new)
+    env.world.update_points(old, new)
+    g, o = eng.field_get_d2(), env.world.d2()
+    assert np.array_equal(g == 0, o == 0)
+    # Distances: the GPU field is the exact transform of that occupancy.  The reference's incremental removal
+    # (removeObstacleVoxels :303-388, restated line by line in the oracle) re-propagates only through voxels it could
+    # invalidate by flooding from the removed ones, and leaves stale UNDER-estimates behind (counted here); a fresh
+    # reference build of the same occupancy never under-estimates.
+    from scipy import ndimage
+    exact = np.minimum(np.rint(ndimage.distance_transform_edt(g != 0) ** 2).astype(np.int64), eng.max_distance_sq)
+    assert np.array_equal(g, exact)
+    print("updatePointsInField: %d of %d reference voxels are stale under-estimates" % (int((o < g).sum()), g.size))
+    eng.close()
