@@ -175,6 +175,12 @@ int b200sv_field_remove_points(b200sv_ctx* ctx, int which, const double* xyz, si
  * are not voxels of old_xyz are added (a voxel in both is left as it is), then the field is rebuilt. */
 int b200sv_field_update_points(b200sv_ctx* ctx, int which, const double* old_xyz, size_t n_old, const double* new_xyz,
                                size_t n_new);
+/* DistanceField::addShapeToField for a shapes::Sphere (distance_field.cpp:208-238): the interior lattice points of
+ * findInternalPointsConvex (find_internal_points.cpp:39-64; bodies::Sphere::containsPoint = |c - p|^2 <= r^2) are marked on
+ * the device and the field is rebuilt.  This is the construction of the reference's fixture moveit_core/test_big.df
+ * (test_distance_field.cpp:957-963).  Boxes, cylinders and meshes go through the caller's bodies::Body (their
+ * containsPoint lives in the un-vendored geometric_shapes) and b200sv_field_add_points. */
+int b200sv_field_add_sphere(b200sv_ctx* ctx, int which, const double* center_xyz, double radius);
 /* Same two with xyz already in device memory, asynchronous on `cuda_stream` (a cudaStream_t). */
 int b200sv_field_add_points_device(b200sv_ctx* ctx, int which, const double* d_xyz, size_t n_points,
                                    void* cuda_stream);

@@ -76,6 +76,7 @@ def load():
         "b200sv_field_reset": (C.c_int, [vp, C.c_int]),
         "b200sv_field_add_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_field_remove_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
+        "b200sv_field_add_sphere": (C.c_int, [vp, C.c_int, dp, C.c_double]),
         "b200sv_field_update_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t, dp, C.c_size_t]),
         "b200sv_field_add_points_device": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp]),
         "b200sv_field_get_d2": (C.c_int, [vp, C.c_int, ip]),

@@ -1642,6 +1642,38 @@ int b200sv_field_update_points(b200sv_ctx* c, int which, const double* old_xyz, 
   return rebuildField(c, which);
 }
 
+int b200sv_field_add_sphere(b200sv_ctx* c, int which, const double* center, double radius)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!center || !(radius >= 0.0))
+    return fail(c, B200SV_ERR_INVALID, "null centre or negative radius");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  // findInternalPointsConvex (find_internal_points.cpp:44-54): the bounding sphere of a bodies::Sphere is the sphere;
+  // start = floor((c - r - res) / res) * res, then `pt += res` while pt <= c + r + res -- accumulated, not k * res
+  const double res = c->cfg.resolution;
+  std::vector<double> axes;
+  int cnt[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    const double e = center[k] + radius + res;
+    int n = 0;
+    for (double v = floor((center[k] - radius - res) / res) * res; v <= e; v += res, ++n)
+      axes.push_back(v);
+    cnt[k] = n;
+  }
+  if ((double)cnt[0] * cnt[1] * cnt[2] > 4.0e9)
+    return fail(c, B200SV_ERR_INVALID, "sphere spans more than 4e9 lattice points");
+  CU(c, c->d_points.ensure(axes.size() + 1));
+  CU(c, cudaMemcpyAsync(c->d_points.p, axes.data(), axes.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(c, launchSphereShape(c->d_points.p, cnt[0], cnt[1], cnt[2], center, radius * radius, c->grid, c->fields[which].occ,
+                          c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));  // `axes` lives on this stack frame
+  return rebuildField(c, which);
+}
+
 int b200sv_field_add_points_device(b200sv_ctx* c, int which, const double* d_xyz, size_t n, void* cuda_stream)
 {
   int rc = checkWhich(c, which);

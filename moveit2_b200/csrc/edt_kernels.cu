@@ -322,6 +322,32 @@ __global__ void injectKernel(GridDev g, const int32_t* __restrict__ in, uint32_t
   }
 }
 
+// DistanceField::addShapeToField for a SPHERE (distance_field.cpp:208-238): findInternalPointsConvex
+// (find_internal_points.cpp:39-64) visits the lattice xs x ys x zs -- the axis values come from the host, accumulated
+// `pt += resolution` exactly as the reference's loops do -- and keeps the points bodies::Sphere::containsPoint accepts,
+// |c - p|^2 <= r^2 (the predicate test_big.df pins); each kept point marks its voxel (addPointsToField).
+__global__ void sphereShapeKernel(const double* __restrict__ axes, int nxs, int nys, int nzs, double cx, double cy, double cz,
+                                  double r2, GridDev g, uint32_t* __restrict__ occ)
+{
+  const size_t total = static_cast<size_t>(nxs) * nys * nzs;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    const int iz = static_cast<int>(i % nzs);
+    const size_t t = i / nzs;
+    const int iy = static_cast<int>(t % nys), ix = static_cast<int>(t / nys);
+    const double px = axes[ix], py = axes[nxs + iy], pz = axes[nxs + nys + iz];
+    const double dx = cx - px, dy = cy - py, dz = cz - pz;
+    if (!(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) <= r2))
+      continue;
+    const int x = static_cast<int>(floor((px - g.om[0]) * g.oo)), y = static_cast<int>(floor((py - g.om[1]) * g.oo)),
+              z = static_cast<int>(floor((pz - g.om[2]) * g.oo));
+    if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz)
+      continue;
+    atomicOr(occ + (static_cast<size_t>(x) * g.ny + y) * g.wz + (z >> 5), 1u << (z & 31));
+  }
+}
+
 // updatePointsInField (propagation_distance_field.cpp:130-175): occ' = (occ - (old \ new)) + (new \ old), word by word
 __global__ void updateOccKernel(uint32_t* __restrict__ occ, const uint32_t* __restrict__ old_bits,
                                 const uint32_t* __restrict__ new_bits, size_t n_words)
@@ -348,6 +374,16 @@ cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint3
   if (n == 0)
     return cudaSuccess;
   scatterKernel<<<gridFor(n, 256, 148 * 16), 256, 0, s>>>(d_xyz, n, g, occ, set ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launchSphereShape(const double* d_axes, int nxs, int nys, int nzs, const double* c, double r2, const GridDev& g,
+                              uint32_t* occ, cudaStream_t s)
+{
+  const size_t total = static_cast<size_t>(nxs) * nys * nzs;
+  if (total == 0)
+    return cudaSuccess;
+  sphereShapeKernel<<<gridFor(total, 256, 148 * 16), 256, 0, s>>>(d_axes, nxs, nys, nzs, c[0], c[1], c[2], r2, g, occ);
   return cudaGetLastError();
 }
 

@@ -149,6 +149,9 @@ struct GridDev
 
 // occupancy bitmap: word ((x*ny + y)*wz + z/32), bit z%32
 cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint32_t* occ, bool set, cudaStream_t s);
+// addShapeToField for a sphere: lattice axes (host-accumulated) x containsPoint -> occupancy bits
+cudaError_t launchSphereShape(const double* d_axes, int nxs, int nys, int nzs, const double* c, double r2, const GridDev& g,
+                              uint32_t* occ, cudaStream_t s);
 // occ' = (occ - (old \\ new)) + (new \\ old): updatePointsInField on bitmaps of the same layout
 cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint32_t* new_bits, size_t n_words, cudaStream_t s);
 // exact truncated EDT of the occupancy bitmap -> d2 (uint16, min(d^2, max_d2)) and this field's half of the

@@ -210,6 +210,11 @@ class StateValidityEngine:
         p = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
         self._check(self.L.b200sv_field_remove_points(self.h, which, _dp(p), p.shape[0]))
 
+    def field_add_sphere(self, center, radius, which=FIELD_WORLD):
+        """DistanceField::addShapeToField for a sphere: interior lattice points marked on the device."""
+        c = np.ascontiguousarray(center, np.float64).reshape(3)
+        self._check(self.L.b200sv_field_add_sphere(self.h, which, _dp(c), float(radius)))
+
     def field_update_points(self, old_points, new_points, which=FIELD_WORLD):
         """PropagationDistanceField::updatePointsInField."""
         a = np.ascontiguousarray(old_points, np.float64).reshape(-1, 3)

@@ -104,6 +104,18 @@ def test_edt_golden_test_big(golden):
     assert np.array_equal(g, exact_edt(occ, 169))    # exact
     assert (g <= o).all()                            # reference over-estimates only
     assert (g != o).mean() < 1e-3 and (o - g).max() <= 8
+    # the same fixture through the device-side shape ingest (addShapeToField for a sphere): 65 126 voxels, bit for bit
+    eng.field_reset()
+    eng.field_add_sphere((0.5, 0.5, 0.5), 0.5)
+    g2 = eng.field_get_d2()
+    assert int((g2 == 0).sum()) == 65126 and np.array_equal(g2 == 0, occ) and np.array_equal(g2, g)
+    # a sphere that sticks out of the field: points outside the grid are dropped (isCellValid), as addPointsToField does
+    eng.field_reset()
+    eng.field_add_sphere((0.05, 1.5, 2.0), 0.3)
+    pts2 = find_internal_points_sphere((0.05, 1.5, 2.0), 0.3, 0.02)
+    ref2 = PropagationDistanceField(3.0, 3.0, 4.0, 0.02, 0, 0, 0, 0.25)
+    ref2.add_points(pts2)
+    assert np.array_equal(eng.field_get_d2() == 0, ref2.d2() == 0)
     eng.close()
 
 

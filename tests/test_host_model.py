@@ -50,7 +50,8 @@ def test_host_only_context_refuses_compute():
                  lambda: eng.field_get_d2(), lambda: eng.gather_roofline(1 << 20, 1),
                  lambda: eng.check_motions(q[:2], q[2:], 0.1), lambda: eng.collision_gradients(q),
                  lambda: eng.check_contacts(q, max_contacts=2), lambda: eng.field_write_df(),
-                 lambda: eng.field_read_df(b"resolution: 0.02\n")):
+                 lambda: eng.field_read_df(b"resolution: 0.02\n"), lambda: eng.field_add_sphere((0, 0, 0.5), 0.1),
+                 lambda: eng.field_update_points(np.zeros((1, 3)), np.ones((1, 3)))):
         with pytest.raises(mb.B200svError) as e:
             call()
         assert e.value.code == _lib.ERR_NO_DEVICE
