@@ -686,3 +686,43 @@ def test_field_update_points_equals_reference_set_semantics():
     assert np.array_equal(g, exact)
     print("updatePointsInField: %d of %d reference voxels are stale under-estimates" % (int((o < g).sum()), g.size))
     eng.close()
+
+
+# ---- a robot at PR2 scale: many spheres per link, thousands of cluster pairs ---------------------------------------------
+def _densified(urdf, copies):
+    """Every collision sphere of the URDF replaced by `copies` slightly smaller ones spread around it."""
+    import re
+    offs = [(0.0, 0.0, 0.0), (0.015, 0.0, 0.0), (-0.015, 0.0, 0.0), (0.0, 0.015, 0.0), (0.0, -0.015, 0.0), (0.0, 0.0, 0.015)]
+
+    def rep(m):
+        x, y, z = (float(v) for v in m.group(1).split())
+        r = float(m.group(2))
+        return "".join('<collision><origin rpy="0 0 0" xyz="%r %r %r"/><geometry><sphere radius="%r"/></geometry></collision>'
+                       % (x + o[0], y + o[1], z + o[2], r - 0.01) for o in offs[:copies])
+
+    return re.sub(r'<collision><origin rpy="0 0 0" xyz="([^"]+)"/><geometry><sphere radius="([^"]+)"/></geometry></collision>',
+                  rep, urdf)
+
+
+@pytest.mark.gpu
+def test_validity_dense_dual_arm():
+    from oracle.collision_model import OracleEnv
+    from oracle.robot_model import RobotModel
+    from util import RES, ROBOT_FILES, read
+    u, s = ROBOT_FILES["dualarm"]
+    urdf, srdf = _densified(read(RES, u), 4), read(RES, s)
+    cfg = workloads.CONFIGS["C3"]
+    eng = mb.StateValidityEngine.from_urdf(urdf, srdf, "arms", cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    env = OracleEnv(RobotModel(urdf, srdf), "arms", cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    assert eng.n_spheres == env.n_spheres >= 250
+    cloud = workloads.make_cloud("C3")
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(41, 30000, lo, hi)
+    for flags in (W, S | I, ALL):
+        ref, _ = env.check(q, flags)
+        assert np.array_equal(eng.check_batch(q, flags), ref == 0), flags
+    assert 0.05 < ref.mean() < 0.95
+    eng.close()
