@@ -77,7 +77,7 @@ struct b200sv_ctx
   uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr, *d_blob_fast = nullptr;
   bool fast_ok = false;      // the group's joints are all FIXED / REVOLUTE / PRISMATIC: fast_check.cu runs the FP32 pass
   bool fast_disabled = false;  // B200SV_FAST=0: force the generic FP32 kernel (A/B measurements)
-  int state_stride_fast = 0, fast_t_rows = 0;
+  int state_stride_fast = 0, fast_t_rows = 0, fast_n_linkpairs = 0, fast_n_reps = 0;
   bool fast_t_global = false;  // link transforms in an L2-resident scratch instead of shared memory (large robots)
   float* d_t_scratch = nullptr;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
@@ -470,50 +470,113 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   frexp(std::max(max_reach, 1.0), &e2);                    // max_reach < 2^e2
   const double half_spacing = ldexp(1.0, e2 - 11);         // spacing of half values below 2^e2
   const double half_slack = 2.0 * sqrt(3.0) * half_spacing + 0.01;
-  std::vector<fast::Cluster> cl(bs.size());
-  std::vector<fast::PSphere> ps(bs.size() * fast::kPSphereStride);
+  // Hierarchical cull for robots with many cluster pairs: a LINK-level tight sphere per body is parked next to its
+  // clusters' ("rep" = a parked centre: the body's clusters, then the body itself), link pairs are culled first.
+  // Measured on the dual-arm tree (profiles/r1_hier_cull_rates.txt): slower at 500 cluster pairs (0.94e9 vs 1.31e9
+  // states/s: too many link pairs survive for the expansion to pay), faster from ~1 700 pairs (3.6e8 vs 3.0e8).
+  bool hier = pairs.size() > 1024;
+  if (const char* e = getenv("B200SV_HIER"))
+    hier = atoi(e) != 0 && !pairs.empty();
+  const int n_bodies = c.cm.n_glinks;
+  std::vector<int> rep_of_cluster(bs.size(), -1), body_rep(n_bodies, -1);
+  std::vector<double> body_tight(4 * (size_t)n_bodies, 0.0);
+  int n_rep = 0;
+  for (size_t i = 0; i < bs.size();)
+  {
+    const int body = bs[i].pad;
+    size_t j = i;
+    while (j < bs.size() && bs[j].pad == body)
+      rep_of_cluster[j++] = n_rep++;
+    if (hier)
+    {
+      const int s0 = bs[i].s0, s1 = bs[j - 1].s1;
+      double cx = 0, cy = 0, cz = 0, rr = 0;
+      for (int k = s0; k < s1; ++k)
+      {
+        cx += spheres[k].x; cy += spheres[k].y; cz += spheres[k].z;
+      }
+      cx /= (s1 - s0); cy /= (s1 - s0); cz /= (s1 - s0);
+      for (int k = s0; k < s1; ++k)
+      {
+        const double ex = spheres[k].x - cx, ey = spheres[k].y - cy, ez = spheres[k].z - cz;
+        rr = std::max(rr, sqrt(ex * ex + ey * ey + ez * ez) + spheres[k].r);
+      }
+      body_tight[4 * body + 0] = cx; body_tight[4 * body + 1] = cy; body_tight[4 * body + 2] = cz;
+      body_tight[4 * body + 3] = rr + 1e-9;
+      body_rep[body] = n_rep++;
+    }
+    i = j;
+  }
+  if (n_rep > 0xffff)
+    return false;
+  std::vector<fast::Cluster> cl(n_rep);
+  std::vector<fast::PSphere> ps((size_t)n_rep * fast::kPSphereStride);
+  for (auto& Q : ps)
+    Q.r_v = -1e30f;
+  auto linkRange = [&](int slot, int rep) {
+    fast::Link& F = fl[slot];  // a body's reps are contiguous, and a device link carries exactly one body
+    if (F.c1 == 0)
+      F.c0 = rep;
+    F.c0 = std::min(F.c0, rep);
+    F.c1 = std::max(F.c1, rep + 1);
+  };
   for (size_t i = 0; i < bs.size(); ++i)
   {
     if (bs[i].s1 - bs[i].s0 > fast::kClusterSpheres)
       return false;  // cannot happen: buildTables caps clusters at kClusterSpheres
+    const int rep = rep_of_cluster[i];
     fast::Cluster C{};
     C.tx = (float)bs[i].tx;
     C.ty = (float)bs[i].ty;
     C.tz = (float)bs[i].tz;
-    cl[i] = C;
-    fast::Link& F = fl[bs[i].slot];  // clusters are created link by link: a link's clusters are contiguous
-    if (F.c1 == 0)
-      F.c0 = (int)i;
-    F.c1 = (int)i + 1;
+    cl[rep] = C;
+    linkRange(bs[i].slot, rep);
     for (int k = 0; k < fast::kClusterSpheres; ++k)
-    {
-      fast::PSphere Q{};
-      Q.r_v = -1e30f;
       if (bs[i].s0 + k < bs[i].s1)
       {
         const SphereRec<double>& S = spheres[bs[i].s0 + k];
+        fast::PSphere Q{};
         Q.x = (float)S.x;
         Q.y = (float)S.y;
         Q.z = (float)S.z;
         Q.r_v = (float)(S.r * oo);
+        ps[(size_t)rep * fast::kPSphereStride + k] = Q;
       }
-      ps[i * fast::kPSphereStride + k] = Q;
+    if (hier && (i + 1 == bs.size() || bs[i + 1].pad != bs[i].pad))
+    {
+      const int body = bs[i].pad;
+      fast::Cluster L{};
+      L.tx = (float)body_tight[4 * body + 0];
+      L.ty = (float)body_tight[4 * body + 1];
+      L.tz = (float)body_tight[4 * body + 2];
+      cl[body_rep[body]] = L;
+      linkRange(bs[i].slot, body_rep[body]);
     }
   }
-  std::vector<fast::Group> fg(groups.size());
+  // cluster pairs, ordered by (body a, body b) when the cull is hierarchical so a link pair's cluster pairs are contiguous
+  std::vector<int> order(pairs.size());
+  for (size_t p = 0; p < pairs.size(); ++p)
+    order[p] = (int)p;
+  if (hier)
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      const long kx = (long)bs[pairs[x].a].pad * n_bodies + bs[pairs[x].b].pad;
+      const long ky = (long)bs[pairs[y].a].pad * n_bodies + bs[pairs[y].b].pad;
+      return kx < ky;
+    });
+  std::vector<fast::Group> fg;  // the fast kernel's cull is transposed: no per-cluster groups
   std::vector<fast::Pair> fp(pairs.size());
   std::vector<fast::Quirk> fq;
-  for (size_t g = 0; g < groups.size(); ++g)
-    fg[g] = fast::Group{ groups[g].a, groups[g].p0, groups[g].p1, 0 };
-  for (size_t p = 0; p < pairs.size(); ++p)
+  std::vector<fast::LinkPair> flp;
+  for (size_t q = 0; q < order.size(); ++q)
   {
+    const size_t p = (size_t)order[q];
     const BsRec<double>&A = bs[pairs[p].a], &B = bs[pairs[p].b];
     fast::Pair P{};
     const double rt = (A.tr + B.tr + tight_eps) * oo + half_slack;
     P.rt2_h = halfBitsUp(rt * rt * (1.0 + 4.0 / 1024.0));  // + the half rounding of the squared sum itself
-    if (pairs[p].a > 0xffff || pairs[p].b > 0xffff || store_off[A.slot] > 0xffff || store_off[B.slot] > 0xffff)
+    if (store_off[A.slot] > 0xffff || store_off[B.slot] > 0xffff)
       return false;  // beyond the packed pair record: the generic kernel takes the group
-    P.ab = (unsigned)pairs[p].a | ((unsigned)pairs[p].b << 16);
+    P.ab = (unsigned)rep_of_cluster[pairs[p].a] | ((unsigned)rep_of_cluster[pairs[p].b] << 16);
     P.offs = (unsigned)store_off[A.slot] | ((unsigned)store_off[B.slot] << 16);
     P.quirk = -1;
     if (!pairs[p].quirk_free)
@@ -528,7 +591,23 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
       P.quirk = (int)fq.size();
       fq.push_back(Q);
     }
-    fp[p] = P;
+    fp[q] = P;
+    if (hier)
+    {
+      const int ba = A.pad, bb = B.pad;
+      const unsigned ab = (unsigned)body_rep[ba] | ((unsigned)body_rep[bb] << 16);
+      if (flp.empty() || flp.back().ab != ab || flp.back().ncp >= 32)
+      {
+        fast::LinkPair L{};
+        const double rl = (body_tight[4 * ba + 3] + body_tight[4 * bb + 3] + tight_eps) * oo + half_slack;
+        L.rt2_h = halfBitsUp(rl * rl * (1.0 + 4.0 / 1024.0));
+        L.ab = ab;
+        L.cp0 = (unsigned)q;
+        L.ncp = 0;
+        flp.push_back(L);
+      }
+      ++flp.back().ncp;
+    }
   }
   {  // sentinel after the last link: the kernel reads link l + 1's variable index one link ahead
     fast::Link S{};
@@ -555,6 +634,11 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   off = align16(off + (int)(fp.size() * sizeof(fast::Pair)));
   h.off_quirks = off;
   off = align16(off + (int)(fq.size() * sizeof(fast::Quirk)));
+  h.off_linkpairs = off;
+  off = align16(off + (int)(flp.size() * sizeof(fast::LinkPair)));
+  h.n_linkpairs = (int)flp.size();
+  c.fast_n_linkpairs = h.n_linkpairs;
+  c.fast_n_reps = n_rep;
   h.total_bytes = off;
   h.state_stride = c.state_stride_fast;
   h.t_rows = 3 * std::max(1, n_stored);
@@ -598,6 +682,8 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
     memcpy(o + h.off_pairs, fp.data(), fp.size() * sizeof(fast::Pair));
   if (!fq.empty())
     memcpy(o + h.off_quirks, fq.data(), fq.size() * sizeof(fast::Quirk));
+  if (!flp.empty())
+    memcpy(o + h.off_linkpairs, flp.data(), flp.size() * sizeof(fast::LinkPair));
   return true;
 }
 
@@ -938,7 +1024,7 @@ b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, 
   b200sv_ctx::LaunchCfg best;
   const int regs = ((fast ? fastCheckKernelRegs(c->compact_bytes) : checkKernelRegs(fp64, from_list, c->compact_bytes)) + 7) & ~7;
   const int reg_warps = 65536 / (regs * 32);
-  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast, c->n_bs, (int)c->robot.group_var_index.size()) :
+  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast, c->fast_n_reps, (int)c->robot.group_var_index.size(), c->fast_n_linkpairs) :
                          checkPerWarpBytes(fp64, fp64 ? c->state_stride_d : c->state_stride_f);
   for (int b = 1; b <= 4; ++b)
   {
@@ -1000,7 +1086,7 @@ int uploadTables(b200sv_ctx* c)
                                             (size_t)c->fast_t_rows * 128 * sizeof(float)));
     if (getenv("B200SV_VERBOSE"))
       fprintf(stderr, "b200sv: fast kernel: %d words of transforms per state, %d bytes per warp, %d warps x %d CTAs per SM, blob %zu bytes\n",
-              c->state_stride_fast, fastCheckPerWarpBytes(c->fast_t_global ? 0 : c->state_stride_fast, c->n_bs, (int)c->robot.group_var_index.size()),
+              c->state_stride_fast, fastCheckPerWarpBytes(c->fast_t_global ? 0 : c->state_stride_fast, c->fast_n_reps, (int)c->robot.group_var_index.size(), c->fast_n_linkpairs),
               c->cfg_fast.warps, c->cfg_fast.blocks_per_sm, c->blob_fast.size());
     if (c->cfg_fast.warps < 1)
       c->fast_ok = false;  // the generic kernel's limits decide below whether the robot fits at all
@@ -1215,6 +1301,7 @@ int launchMain(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t ba
     a.model = c->d_blob_fast;
     a.model_bytes = (int)c->blob_fast.size();
     a.t_scratch = c->fast_t_global ? c->d_t_scratch : nullptr;
+    a.hier = c->fast_n_linkpairs > 0;
     CU(c, launchFastCheck<FT>(a, c->sm_count * k.blocks_per_sm, k.warps * 32, k.smem, s));
     return B200SV_OK;
   }

@@ -163,6 +163,16 @@ struct alignas(16) Pair  // 16 bytes: ONE 128-bit read per level-1 lane and per 
 };
 static_assert(sizeof(Pair) == 16, "fast::Pair layout");
 
+// Hierarchical cull, level 0: a pair of links (bodies) whose cluster pairs [cp0, cp0 + ncp) are contiguous in the Pair
+// table.  Same first two fields as Pair (the transposed cull reads only those); la / lb index the parked LINK-level tight
+// spheres.  A link pair with more than 32 cluster pairs is split into several records.
+struct alignas(16) LinkPair
+{
+  unsigned rt2_h;
+  unsigned ab;  // la | lb << 16
+  unsigned cp0, ncp;
+};
+
 // doBoundingSpheresIntersect on the LINKS' bounding spheres (types.cpp:408-418), quirk kept: squared centre distance
 // (m^2) against the plain radius sum (m).  In cells: |Ca - Cb|_v^2 < (Ra + Rb) * oo^2.
 struct alignas(16) Quirk
@@ -182,7 +192,7 @@ struct alignas(16) Header
   int nz, nynz;
   unsigned idx_bias;  // -(0x4B400000 * (nynz + nz + 1)) mod 2^32: undoes the float-magic bias of the three cell indices
   int t_rows;  // float4 rows of transforms per state (3 per stored link): size of a warp's global-memory region / 32
-  int pad3, pad4;
+  int n_linkpairs, off_linkpairs;  // hierarchical cull (many cluster pairs): LinkPair records; 0 = level 1 directly
   float lo[3], margin;      // clamp of (centre - margin) to [0.5 - margin, n - 0.5 - margin]: a centre outside the
   float hi[3], two_margin;  // field lands in the 1-cell border shell, where nothing collides
   float pair_eps_v, tight_eps_v, pad0, pad1;

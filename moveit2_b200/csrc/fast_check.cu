@@ -63,6 +63,7 @@ struct FModel
   const fast::Group* groups;
   const fast::Pair* pairs;
   const fast::Quirk* quirks;
+  const uint4* linkpairs;
 };
 
 // Field element = { world, self } of one voxel.  8-bit fields: both compares in one add (per 16-bit lane
@@ -168,6 +169,7 @@ __device__ __forceinline__ FModel loadFast(const uint8_t* __restrict__ g_model, 
   m.groups = reinterpret_cast<const fast::Group*>(smem + m.h->off_groups);
   m.pairs = reinterpret_cast<const fast::Pair*>(smem + m.h->off_pairs);
   m.quirks = reinterpret_cast<const fast::Quirk*>(smem + m.h->off_quirks);
+  m.linkpairs = reinterpret_cast<const uint4*>(smem + m.h->off_linkpairs);
   return m;
 }
 
@@ -249,13 +251,16 @@ __device__ __host__ inline int queueBytes(int n_group_vars)
   return stage > kQueueCap * 4 ? stage : kQueueCap * 4;
 }
 
-__device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters, int n_group_vars)
+constexpr int kQcCap = 1024;  // hierarchical cull: (state, cluster pair) candidates of one batch of link-pair survivors
+
+__device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs)
 {
-  return 32 * state_stride * 4 + repBytes(n_clusters) + queueBytes(n_group_vars) + 16;
+  return 32 * state_stride * 4 + repBytes(n_clusters) + queueBytes(n_group_vars) + 16 +
+         (n_linkpairs > 0 ? (kQueueCap + kQcCap) * 4 : 0);
 }
 
 // Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
-template <typename FT, bool kTG>
+template <typename FT, bool kTG, bool kHier>
 __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fastCheckKernel(CheckArgs<FT> a)
 {
   using Elem = typename Cmp<FT>::Elem;
@@ -264,7 +269,8 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
   const fast::Header& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int t_words = kTG ? 0 : h.state_stride;  // shared-memory words of transforms per state
-  uint8_t* wbase = smem + h.total_bytes + static_cast<size_t>(warp) * fastPerWarpBytes(t_words, h.n_clusters, h.n_group_vars);
+  uint8_t* wbase = smem + h.total_bytes +
+                   static_cast<size_t>(warp) * fastPerWarpBytes(t_words, h.n_clusters, h.n_group_vars, kHier ? h.n_linkpairs : 0);
   float* Ts = reinterpret_cast<float*>(wbase);
   TStore<kTG> ts;
   ts.base = kTG ? a.t_scratch + (static_cast<size_t>(blockIdx.x) * warps + warp) * (static_cast<size_t>(h.t_rows) * 128) : Ts;
@@ -275,6 +281,8 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
   uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_x) + repBytes(h.n_clusters));
   double* stage = reinterpret_cast<double*>(queue);  // the tile's states [state][var], FK phase only
   unsigned* words = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(queue) + queueBytes(h.n_group_vars));  // [0] hit, [1] amb
+  uint32_t* q0 = words + 4;        // hierarchical cull only: (state, link pair) survivors of level 0
+  uint32_t* qc = q0 + kQueueCap;   //                         (state, cluster pair) candidates
   const bool do_fields = (a.flags & 3u) != 0, do_intra = (a.flags & 4u) != 0;
   const unsigned fmask = ((a.flags & 1u) ? 0x0000ffffu : 0u) | ((a.flags & 2u) ? 0xffff0000u : 0u);
   const Elem* __restrict__ field = static_cast<const Elem*>(a.field);
@@ -515,63 +523,187 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
         __syncwarp();
         qn = 0;
       };
-      // level 1, TRANSPOSED: lane = cluster pair, loop over the warp's live states.  Conservative cull on the tight
-      // spheres (every sphere of a cluster lies inside its tight sphere), in half precision on the parked centres.
       const unsigned mine_mask = __ballot_sync(kFull, mine);
-      for (int p0 = 0; p0 < h.n_pairs; p0 += 32)
+      if constexpr (!kHier)
       {
-        const int p = p0 + lane;
-        const bool have = p < h.n_pairs;
-        const uint4 pc = reinterpret_cast<const uint4*>(m.pairs)[have ? p : 0];  // rt2 (half bits), a | b << 16, ...
-        const int ca = pc.y & 0xffffu, cb = pc.y >> 16;
-        const __half rt2 = __ushort_as_half(static_cast<unsigned short>(pc.x));
-        const __half2 rt2_2 = __half2half2(rt2);
-        const uint32_t* ax = reinterpret_cast<const uint32_t*>(rep_x + ca * kRepStride);
-        const uint32_t* bx = reinterpret_cast<const uint32_t*>(rep_x + cb * kRepStride);
-        const uint32_t* ay = reinterpret_cast<const uint32_t*>(rep_y + ca * kRepStride);
-        const uint32_t* by = reinterpret_cast<const uint32_t*>(rep_y + cb * kRepStride);
-        const uint32_t* az = reinterpret_cast<const uint32_t*>(rep_z + ca * kRepStride);
-        const uint32_t* bz = reinterpret_cast<const uint32_t*>(rep_z + cb * kRepStride);
-        for (int c8 = 0; c8 < 4; ++c8)
-        {  // chunks of 8 states (at most 256 new items, the queue's capacity), two states per half2 lane pair
-          if (((mine_mask >> (8 * c8)) & 0xffu) == 0u)
-            continue;
-          unsigned live_states = 0u;
+        // level 1, TRANSPOSED: lane = cluster pair, loop over the warp's live states.  Conservative cull on the tight
+        // spheres (every sphere of a cluster lies inside its tight sphere), in half precision on the parked centres.
+        for (int p0 = 0; p0 < h.n_pairs; p0 += 32)
+        {
+          const int p = p0 + lane;
+          const bool have = p < h.n_pairs;
+          const uint4 pc = reinterpret_cast<const uint4*>(m.pairs)[have ? p : 0];  // rt2 (half bits), a | b << 16, ...
+          const int ca = pc.y & 0xffffu, cb = pc.y >> 16;
+          const __half rt2 = __ushort_as_half(static_cast<unsigned short>(pc.x));
+          const __half2 rt2_2 = __half2half2(rt2);
+          const uint32_t* ax = reinterpret_cast<const uint32_t*>(rep_x + ca * kRepStride);
+          const uint32_t* bx = reinterpret_cast<const uint32_t*>(rep_x + cb * kRepStride);
+          const uint32_t* ay = reinterpret_cast<const uint32_t*>(rep_y + ca * kRepStride);
+          const uint32_t* by = reinterpret_cast<const uint32_t*>(rep_y + cb * kRepStride);
+          const uint32_t* az = reinterpret_cast<const uint32_t*>(rep_z + ca * kRepStride);
+          const uint32_t* bz = reinterpret_cast<const uint32_t*>(rep_z + cb * kRepStride);
+          for (int c8 = 0; c8 < 4; ++c8)
+          {  // chunks of 8 states (at most 256 new items, the queue's capacity), two states per half2 lane pair
+            if (((mine_mask >> (8 * c8)) & 0xffu) == 0u)
+              continue;
+            unsigned live_states = 0u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-          {
-            const int w = c8 * 4 + j;  // word = states 2w, 2w + 1
-            const uint32_t wax = ax[w], wbx = bx[w], way = ay[w], wby = by[w], waz = az[w], wbz = bz[w];
-            const __half2 dx = __hsub2(*reinterpret_cast<const __half2*>(&wax), *reinterpret_cast<const __half2*>(&wbx));
-            const __half2 dy = __hsub2(*reinterpret_cast<const __half2*>(&way), *reinterpret_cast<const __half2*>(&wby));
-            const __half2 dz = __hsub2(*reinterpret_cast<const __half2*>(&waz), *reinterpret_cast<const __half2*>(&wbz));
-            const __half2 dd = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
-            const unsigned lt = __hlt2_mask(dd, rt2_2);  // 0xffff per half where dd < rt2
-            live_states |= ((lt & 1u) | ((lt >> 15) & 2u)) << (2 * w);
-          }
-          live_states &= have ? mine_mask : 0u;
-          // append (state, pair) items: exclusive scan of the per-lane counts, then every lane writes its own
-          const int cnt = __popc(live_states);
-          int pos = cnt;
+            for (int j = 0; j < 4; ++j)
+            {
+              const int w = c8 * 4 + j;  // word = states 2w, 2w + 1
+              const uint32_t wax = ax[w], wbx = bx[w], way = ay[w], wby = by[w], waz = az[w], wbz = bz[w];
+              const __half2 dx = __hsub2(*reinterpret_cast<const __half2*>(&wax), *reinterpret_cast<const __half2*>(&wbx));
+              const __half2 dy = __hsub2(*reinterpret_cast<const __half2*>(&way), *reinterpret_cast<const __half2*>(&wby));
+              const __half2 dz = __hsub2(*reinterpret_cast<const __half2*>(&waz), *reinterpret_cast<const __half2*>(&wbz));
+              const __half2 dd = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
+              const unsigned lt = __hlt2_mask(dd, rt2_2);  // 0xffff per half where dd < rt2
+              live_states |= ((lt & 1u) | ((lt >> 15) & 2u)) << (2 * w);
+            }
+            live_states &= have ? mine_mask : 0u;
+            // append (state, pair) items: exclusive scan of the per-lane counts, then every lane writes its own
+            const int cnt = __popc(live_states);
+            int pos = cnt;
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1)
-          {
-            const int t = __shfl_up_sync(kFull, pos, d);
-            if (lane >= d)
-              pos += t;
+            for (int d = 1; d < 32; d <<= 1)
+            {
+              const int t = __shfl_up_sync(kFull, pos, d);
+              if (lane >= d)
+                pos += t;
+            }
+            const int total = __shfl_sync(kFull, pos, 31);
+            if (qn + total > kQueueCap)
+              flush();
+            pos += qn - cnt;
+            while (live_states)
+            {
+              const int s = __ffs(live_states) - 1;
+              live_states &= live_states - 1;
+              queue[pos++] = static_cast<uint32_t>(s | (p << 5));
+            }
+            qn += total;
           }
-          const int total = __shfl_sync(kFull, pos, 31);
-          if (qn + total > kQueueCap)
-            flush();
-          pos += qn - cnt;
-          while (live_states)
-          {
-            const int s = __ffs(live_states) - 1;
-            live_states &= live_states - 1;
-            queue[pos++] = static_cast<uint32_t>(s | (p << 5));
-          }
-          qn += total;
         }
+      }
+      else
+      {
+        // TRANSPOSED cull: lane = pair (of clusters, or of links), loop over the warp's live states, two per half2.
+        // Conservative test on tight spheres (every sphere of a cluster / link lies inside its tight sphere), in half
+        // precision on the parked centres.  Survivors (state, pair) are appended to `dst`; `drain` empties it when full.
+        auto transposedCull = [&](const uint4* __restrict__ table, int n_entries, uint32_t* dst, int& dn, auto&& drain) {
+          for (int p0 = 0; p0 < n_entries; p0 += 32)
+          {
+            const int p = p0 + lane;
+            const bool have = p < n_entries;
+            const uint4 pc = table[have ? p : 0];  // rt2 (half bits), a | b << 16, ...
+            const int ca = pc.y & 0xffffu, cb = pc.y >> 16;
+            const __half2 rt2_2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(pc.x)));
+            const uint32_t* ax = reinterpret_cast<const uint32_t*>(rep_x + ca * kRepStride);
+            const uint32_t* bx = reinterpret_cast<const uint32_t*>(rep_x + cb * kRepStride);
+            const uint32_t* ay = reinterpret_cast<const uint32_t*>(rep_y + ca * kRepStride);
+            const uint32_t* by = reinterpret_cast<const uint32_t*>(rep_y + cb * kRepStride);
+            const uint32_t* az = reinterpret_cast<const uint32_t*>(rep_z + ca * kRepStride);
+            const uint32_t* bz = reinterpret_cast<const uint32_t*>(rep_z + cb * kRepStride);
+            for (int c8 = 0; c8 < 4; ++c8)
+            {  // chunks of 8 states (at most 256 new entries, the queue's capacity), two states per half2 lane pair
+              if (((mine_mask >> (8 * c8)) & 0xffu) == 0u)
+                continue;
+              unsigned live_states = 0u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+              {
+                const int w = c8 * 4 + j;  // word = states 2w, 2w + 1
+                const uint32_t wax = ax[w], wbx = bx[w], way = ay[w], wby = by[w], waz = az[w], wbz = bz[w];
+                const __half2 dx = __hsub2(*reinterpret_cast<const __half2*>(&wax), *reinterpret_cast<const __half2*>(&wbx));
+                const __half2 dy = __hsub2(*reinterpret_cast<const __half2*>(&way), *reinterpret_cast<const __half2*>(&wby));
+                const __half2 dz = __hsub2(*reinterpret_cast<const __half2*>(&waz), *reinterpret_cast<const __half2*>(&wbz));
+                const __half2 dd = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
+                const unsigned lt = __hlt2_mask(dd, rt2_2);  // 0xffff per half where dd < rt2
+                live_states |= ((lt & 1u) | ((lt >> 15) & 2u)) << (2 * w);
+              }
+              live_states &= have ? mine_mask : 0u;
+              // append (state, pair): exclusive scan of the per-lane counts, then every lane writes its own
+              const int cnt = __popc(live_states);
+              int pos = cnt;
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1)
+              {
+                const int t = __shfl_up_sync(kFull, pos, d);
+                if (lane >= d)
+                  pos += t;
+              }
+              const int total = __shfl_sync(kFull, pos, 31);
+              if (dn + total > kQueueCap)
+                drain();
+              pos += dn - cnt;
+              while (live_states)
+              {
+                const int s = __ffs(live_states) - 1;
+                live_states &= live_states - 1;
+                dst[pos++] = static_cast<uint32_t>(s | (p << 5));
+              }
+              dn += total;
+            }
+          }
+        };
+        // Many cluster pairs (a robot at PR2 scale has thousands): level 0 culls LINK pairs the same way, its survivors
+        // (state, link pair) are expanded to (state, cluster pair) candidates, and each candidate is tested by one lane.
+        int q0n = 0, qcn = 0;
+        auto drainC = [&]() {
+          __syncwarp();
+          for (int i0 = 0; i0 < qcn; i0 += 32)
+          {
+            const int i = i0 + lane;
+            const bool have = i < qcn;
+            const unsigned cand = have ? qc[i] : 0u;
+            const int s = cand & 31;
+            const uint4 pc = reinterpret_cast<const uint4*>(m.pairs)[cand >> 5];
+            const int ca = pc.y & 0xffffu, cb = pc.y >> 16;
+            const __half dx = __hsub(rep_x[ca * kRepStride + s], rep_x[cb * kRepStride + s]);
+            const __half dy = __hsub(rep_y[ca * kRepStride + s], rep_y[cb * kRepStride + s]);
+            const __half dz = __hsub(rep_z[ca * kRepStride + s], rep_z[cb * kRepStride + s]);
+            const __half dd = __hfma(dz, dz, __hfma(dy, dy, __hmul(dx, dx)));
+            const bool live = have && __hlt(dd, __ushort_as_half(static_cast<unsigned short>(pc.x)));
+            const unsigned mk = __ballot_sync(kFull, live);
+            if (qn + __popc(mk) > kQueueCap)
+              flush();
+            if (live)
+              queue[qn + __popc(mk & lt_mask)] = cand;
+            qn += __popc(mk);
+          }
+          __syncwarp();
+          qcn = 0;
+        };
+        auto drain0 = [&]() {
+          __syncwarp();
+          for (int i0 = 0; i0 < q0n; i0 += 32)
+          {
+            const int i = i0 + lane;
+            const bool have = i < q0n;
+            const unsigned item = have ? q0[i] : 0u;
+            const uint4 lp = reinterpret_cast<const uint4*>(m.linkpairs)[item >> 5];  // rt2, la | lb << 16, cp0, ncp
+            const int ncp = have ? static_cast<int>(lp.w) : 0;
+            int pos = ncp;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+              const int t = __shfl_up_sync(kFull, pos, d);
+              if (lane >= d)
+                pos += t;
+            }
+            const int total = __shfl_sync(kFull, pos, 31);  // <= 32 * 32: the host splits link pairs at 32 cluster pairs
+            if (qcn + total > kQcCap)
+              drainC();
+            pos += qcn - ncp;
+            for (int k = 0; k < ncp; ++k)
+              qc[pos + k] = (item & 31u) | ((lp.z + k) << 5);
+            qcn += total;
+          }
+          __syncwarp();
+          q0n = 0;
+        };
+        transposedCull(reinterpret_cast<const uint4*>(m.linkpairs), h.n_linkpairs, q0, q0n, drain0);
+        drain0();
+        drainC();
       }
       if (qn > 0)
         flush();
@@ -620,9 +752,9 @@ cudaError_t ensure(K kernel, size_t smem_bytes, Grant& g)
 }
 }  // namespace
 
-int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars)
+int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs)
 {
-  return fastPerWarpBytes(state_stride, n_clusters, n_group_vars);
+  return fastPerWarpBytes(state_stride, n_clusters, n_group_vars, n_linkpairs);
 }
 int fastCheckMaxVars() { return kMaxVars; }
 int fastCheckMaxWarps() { return B200SV_FAST_THREADS / 32; }
@@ -631,35 +763,42 @@ int fastCheckUnroll() { return kU; }
 int fastCheckKernelRegs(int field_bytes)
 {
   cudaFuncAttributes fa{};
-  cudaError_t e = field_bytes == 1 ? cudaFuncGetAttributes(&fa, fastCheckKernel<uint8_t, false>) :
-                                     cudaFuncGetAttributes(&fa, fastCheckKernel<uint16_t, false>);
-  int regs = e == cudaSuccess ? fa.numRegs : 128;
-  e = field_bytes == 1 ? cudaFuncGetAttributes(&fa, fastCheckKernel<uint8_t, true>) :
-                         cudaFuncGetAttributes(&fa, fastCheckKernel<uint16_t, true>);
-  if (e == cudaSuccess && fa.numRegs > regs)
-    regs = fa.numRegs;
+  int regs = 0;
+  auto take = [&](auto kernel) {
+    const cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    regs = std::max(regs, e == cudaSuccess ? fa.numRegs : 128);
+  };
+  if (field_bytes == 1)
+  {
+    take(fastCheckKernel<uint8_t, false, false>);
+    take(fastCheckKernel<uint8_t, true, false>);
+    take(fastCheckKernel<uint8_t, false, true>);
+    take(fastCheckKernel<uint8_t, true, true>);
+  }
+  else
+  {
+    take(fastCheckKernel<uint16_t, false, false>);
+    take(fastCheckKernel<uint16_t, true, false>);
+    take(fastCheckKernel<uint16_t, false, true>);
+    take(fastCheckKernel<uint16_t, true, true>);
+  }
   return regs;
 }
 
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-  static Grant g0, g1;
-  if (a.t_scratch)
-  {
-    cudaError_t e = ensure(fastCheckKernel<FT, true>, smem_bytes, g1);
+  static Grant g[4];
+  auto go = [&](auto kernel, Grant& gr) {
+    const cudaError_t e = ensure(kernel, smem_bytes, gr);
     if (e != cudaSuccess)
       return e;
-    fastCheckKernel<FT, true><<<grid, block, smem_bytes, stream>>>(a);
-  }
-  else
-  {
-    cudaError_t e = ensure(fastCheckKernel<FT, false>, smem_bytes, g0);
-    if (e != cudaSuccess)
-      return e;
-    fastCheckKernel<FT, false><<<grid, block, smem_bytes, stream>>>(a);
-  }
-  return cudaGetLastError();
+    kernel<<<grid, block, smem_bytes, stream>>>(a);
+    return cudaGetLastError();
+  };
+  if (a.hier)
+    return a.t_scratch ? go(fastCheckKernel<FT, true, true>, g[3]) : go(fastCheckKernel<FT, false, true>, g[2]);
+  return a.t_scratch ? go(fastCheckKernel<FT, true, false>, g[1]) : go(fastCheckKernel<FT, false, false>, g[0]);
 }
 template cudaError_t launchFastCheck<uint8_t>(const CheckArgs<uint8_t>&, int, int, size_t, cudaStream_t);
 template cudaError_t launchFastCheck<uint16_t>(const CheckArgs<uint16_t>&, int, int, size_t, cudaStream_t);

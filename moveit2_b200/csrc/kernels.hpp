@@ -33,6 +33,7 @@ struct CheckArgs
   const uint32_t* list;  // exact pass from list (in)
   const unsigned* list_count;
   float* t_scratch;      // fast pass only: global-memory home of the link transforms (null: shared memory)
+  int hier;              // fast pass only: the blob carries LinkPair records (hierarchical cull)
 };
 
 struct FkArgs
@@ -108,7 +109,7 @@ cudaError_t launchContacts(const ContactArgs& a, int grid, int block, size_t sme
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 int fastCheckKernelRegs(int field_bytes);
-int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars);
+int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs);
 int fastCheckMaxVars();
 int fastCheckMaxWarps();  // __launch_bounds__ of the fast kernel
 int fastCheckUnroll();
