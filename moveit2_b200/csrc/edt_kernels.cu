@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.hpp"
 
@@ -25,8 +26,6 @@ namespace b200sv
 {
 namespace
 {
-constexpr uint16_t kInf16 = 0xFFFF;
-
 __global__ void scatterKernel(const double* __restrict__ xyz, size_t n, GridDev g, uint32_t* __restrict__ occ, int set)
 {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
@@ -46,32 +45,39 @@ __global__ void scatterKernel(const double* __restrict__ xyz, size_t n, GridDev 
   }
 }
 
-// One CTA per (x plane, y chunk).  Shared memory: occupancy words of rows [y0-R, y1+R), then their z distances
-// (row stride nzp = nz rounded up to 4 so a thread can take 4 consecutive z with one 32-bit access).
+// One CTA per (x plane, y chunk).  Shared memory: occupancy words of rows [y0-R, y1+R), then their SQUARED z distances
+// as uint16 (row stride nzp = nz rounded up to 8: a thread takes 8 consecutive z with one 128-bit access).  Squares,
+// because the y pass then is two packed 16-bit instructions per candidate row and voxel pair: VIMNMX.U16x2 (min of the
+// rows k below and above) and VIADDMNMX.U16x2 (min(best, m + k^2)), both native on sm_100a.  "No occupied voxel within
+// R" is (R+1)^2: above max_d2, and small enough that adding k^2 <= R^2 stays below 2^16 (the launcher checks R <= 180).
+// Intermediate values above max_d2 mean "nothing within range"; the x pass treats them so.
 __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
-                                                  int chunk, int n_chunks)
+                                                  int chunk, int n_chunks, unsigned nz8_magic)
 {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int x = blockIdx.x / n_chunks, ci = blockIdx.x % n_chunks;
+  const int x = blockIdx.x / n_chunks, ci = blockIdx.x - x * n_chunks;
   const int y0 = ci * chunk, y1 = min(g.ny, y0 + chunk);
   const int ya = y0 - g.R, rows = (y1 - y0) + 2 * g.R;  // haloed row range [ya, ya + rows)
-  const int nzp = (g.nz + 3) & ~3;
+  const int nzp = (g.nz + 7) & ~7;
+  const int wz = g.wz;
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem);
-  uint8_t* gz = smem + ((static_cast<size_t>(rows) * g.wz * 4 + 15) & ~static_cast<size_t>(15));
-  for (int i = threadIdx.x; i < rows * g.wz; i += blockDim.x)
+  uint16_t* gz = reinterpret_cast<uint16_t*>(smem + ((static_cast<size_t>(rows) * wz * 4 + 15) & ~static_cast<size_t>(15)));
   {
-    const int y = ya + i / g.wz;
-    bits[i] = (y >= 0 && y < g.ny) ? occ[(static_cast<size_t>(x) * g.ny + y) * g.wz + (i % g.wz)] : 0u;
+    const uint32_t* src = occ + (static_cast<size_t>(x) * g.ny + ya) * wz;  // rows are contiguous in the bitmap
+    const int lo = max(0, -ya) * wz, hi = min(rows, g.ny - ya) * wz;
+    for (int i = threadIdx.x; i < rows * wz; i += blockDim.x)
+      bits[i] = (i >= lo && i < hi) ? src[i] : 0u;
   }
   __syncthreads();
   // z pass, one thread per 32-bit occupancy word: the distance of the word's two ends to the nearest set bit outside
   // it (clz / ffs on the neighbouring words), then one forward and one backward sweep over its 32 bits
   {
     const int cap = g.R + 1;
-    for (int i = threadIdx.x; i < rows * g.wz; i += blockDim.x)
+    int r = threadIdx.x / wz, w = threadIdx.x - r * wz;
+    const int dr_rows = blockDim.x / wz, dw = blockDim.x - dr_rows * wz;
+    for (; r < rows;)
     {
-      const int r = i / g.wz, w = i - r * g.wz;
-      const uint32_t* row = bits + r * g.wz;
+      const uint32_t* row = bits + r * wz;
       const uint32_t cur = row[w];
       int dl = cap, dr = cap;  // distance of bit 0 / bit 31 to the nearest set bit in the words below / above
       for (int ww = w - 1, off = 1; ww >= 0 && off <= g.R; --ww, off += 32)
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __
           break;
         }
       }
-      for (int ww = w + 1, off = 1; ww < g.wz && off <= g.R; ++ww, off += 32)
+      for (int ww = w + 1, off = 1; ww < wz && off <= g.R; ++ww, off += 32)
       {
         const uint32_t v = row[ww];
         if (v)
@@ -103,64 +109,67 @@ __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __
         else
           f[b >> 2] |= static_cast<uint32_t>(d) << (8 * (b & 3));
       }
+      uint32_t o[16];
       d = dr - 1;
 #pragma unroll
       for (int b = 31; b >= 0; --b)
       {
         d = ((cur >> b) & 1u) ? 0 : min(d + 1, cap);
-        const uint32_t sh = 8 * (b & 3);
-        const uint32_t fw = (f[b >> 2] >> sh) & 0xffu;
-        if (static_cast<uint32_t>(d) < fw)
-          f[b >> 2] = (f[b >> 2] & ~(0xffu << sh)) | (static_cast<uint32_t>(d) << sh);
+        const int mn = min(d, static_cast<int>((f[b >> 2] >> (8 * (b & 3))) & 0xffu));
+        const uint32_t sq = static_cast<uint32_t>(mn * mn);
+        if (b & 1)
+          o[b >> 1] = sq << 16;
+        else
+          o[b >> 1] |= sq;
       }
-      uint32_t* dst = reinterpret_cast<uint32_t*>(gz + r * nzp + w * 32);
+      uint4* dst = reinterpret_cast<uint4*>(gz + r * nzp + w * 32);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (w * 32 + 4 * k < nzp)
-          dst[k] = f[k];  // bytes at z >= nz (occupancy bits there are 0) are never read as centres, only as padding
+      for (int k = 0; k < 4; ++k)
+        if (w * 32 + 8 * k < nzp)
+          dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+      // entries at z >= nz (occupancy bits there are 0) are never read as centres, only as padding
+      r += dr_rows;
+      w += dw;
+      if (w >= wz)
+      {
+        w -= wz;
+        ++r;
+      }
     }
   }
   __syncthreads();
-  const int R = g.R, max_d2 = g.max_d2;
-  const int nz4 = nzp >> 2;
-  const bool vec_out = (g.nz & 3) == 0;  // then every (x, y) row of `out` starts 8-byte aligned
-  for (int i = threadIdx.x; i < (y1 - y0) * nz4; i += blockDim.x)
+  const int R = g.R;
+  const int nz8 = nzp >> 3;
+  const bool vec_out = (g.nz & 7) == 0;  // then every (x, y) row of `out` starts 16-byte aligned
+  const uint4* gz4 = reinterpret_cast<const uint4*>(gz);
+  for (int i = threadIdx.x; i < (y1 - y0) * nz8; i += blockDim.x)
   {
-    const int yy = i / nz4, z = (i - yy * nz4) << 2;
-    const int r = yy + R;  // row index inside the haloed block
-    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(gz + r * nzp + z);
-    int best[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-    {
-      const int c = (c4 >> (8 * j)) & 0xff;
-      best[j] = c * c;
-    }
+    const int yy = static_cast<int>(__umulhi(static_cast<unsigned>(i), nz8_magic));  // i / nz8
+    const int zc = i - yy * nz8;
+    const uint4* ctr = gz4 + (yy + R) * nz8 + zc;  // row yy + R of the haloed block
+    uint4 best = *ctr;
     for (int k = 1; k <= R; ++k)
     {
-      const int k2 = k * k;
-      if (k2 >= max(max(best[0], best[1]), max(best[2], best[3])))
+      const uint32_t k2 = static_cast<uint32_t>(k * k);
+      const uint32_t w2 = __vmaxu2(__vmaxu2(best.x, best.y), __vmaxu2(best.z, best.w));
+      if (k2 >= max(w2 & 0xffffu, w2 >> 16))
         break;  // every further candidate is at least k^2 away
-      const uint32_t a4 = *reinterpret_cast<const uint32_t*>(gz + (r - k) * nzp + z);
-      const uint32_t b4 = *reinterpret_cast<const uint32_t*>(gz + (r + k) * nzp + z);
-      const uint32_t m4 = __vminu4(a4, b4);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-      {
-        const int m = (m4 >> (8 * j)) & 0xff;
-        best[j] = min(best[j], m * m + k2);
-      }
+      const uint4 a = ctr[-k * nz8], b = ctr[k * nz8];
+      const uint32_t k2p = k2 | (k2 << 16);
+      best.x = __viaddmin_u16x2(__vminu2(a.x, b.x), k2p, best.x);
+      best.y = __viaddmin_u16x2(__vminu2(a.y, b.y), k2p, best.y);
+      best.z = __viaddmin_u16x2(__vminu2(a.z, b.z), k2p, best.z);
+      best.w = __viaddmin_u16x2(__vminu2(a.w, b.w), k2p, best.w);
     }
-    uint16_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      o[j] = best[j] <= max_d2 ? static_cast<uint16_t>(best[j]) : kInf16;
-    uint16_t* dst = out + (static_cast<size_t>(x) * g.ny + (y0 + yy)) * g.nz + z;
+    uint16_t* dst = out + (static_cast<size_t>(x) * g.ny + (y0 + yy)) * g.nz + zc * 8;
     if (vec_out)
-      *reinterpret_cast<uint2*>(dst) = make_uint2(o[0] | (static_cast<uint32_t>(o[1]) << 16), o[2] | (static_cast<uint32_t>(o[3]) << 16));
+      *reinterpret_cast<uint4*>(dst) = best;
     else
-      for (int j = 0; j < 4 && z + j < g.nz; ++j)
-        dst[j] = o[j];
+    {
+      const uint32_t bw[4] = { best.x, best.y, best.z, best.w };
+      for (int j = 0; j < 8 && zc * 8 + j < g.nz; ++j)
+        dst[j] = static_cast<uint16_t>(bw[j >> 1] >> (16 * (j & 1)));
+    }
   }
 }
 
@@ -189,39 +198,34 @@ __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* 
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
   {
     const int x = static_cast<int>(i / plane8);
+    // packed 16-bit lanes throughout; anything above max_d2 means "nothing within range".  The z+y pass writes at most
+    // (R+1)^2 + R^2, so the sums below stay far from 2^16; the centre is capped to max_d2 + 1 so the scan ends at k = R.
+    const uint32_t cap1 = static_cast<uint32_t>(max_d2 + 1) * 0x10001u;
     const uint4 c = in4[i];
-    int best[8];
-    const uint32_t cw[4] = { c.x, c.y, c.z, c.w };
-    int worst = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
+    uint32_t bw[4] = { __vminu2(c.x, cap1), __vminu2(c.y, cap1), __vminu2(c.z, cap1), __vminu2(c.w, cap1) };
+    for (int k = 1; k <= R; ++k)
     {
-      best[j] = min(static_cast<int>((cw[j >> 1] >> (16 * (j & 1))) & 0xffff), max_d2 + 1);  // kInf16 acts as +inf
-      worst = max(worst, best[j]);
-    }
-    for (int k = 1; k <= R && k * k < worst; ++k)
-    {
-      const int k2 = k * k;
-      uint4 a = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), b = a;
+      const uint32_t k2 = static_cast<uint32_t>(k * k);
+      const uint32_t w2 = __vmaxu2(__vmaxu2(bw[0], bw[1]), __vmaxu2(bw[2], bw[3]));
+      if (k2 >= max(w2 & 0xffffu, w2 >> 16))
+        break;
+      uint4 a = make_uint4(cap1, cap1, cap1, cap1), b = a;
       if (x - k >= 0)
         a = in4[i - k * plane8];
       if (x + k < g.nx)
         b = in4[i + k * plane8];
-      const uint32_t mw[4] = { __vminu2(a.x, b.x), __vminu2(a.y, b.y), __vminu2(a.z, b.z), __vminu2(a.w, b.w) };
-      worst = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-      {
-        const int m = static_cast<int>((mw[j >> 1] >> (16 * (j & 1))) & 0xffff);
-        best[j] = min(best[j], m + k2);
-        worst = max(worst, best[j]);
-      }
+      const uint32_t k2p = k2 | (k2 << 16);
+      bw[0] = __viaddmin_u16x2(__vminu2(a.x, b.x), k2p, bw[0]);
+      bw[1] = __viaddmin_u16x2(__vminu2(a.y, b.y), k2p, bw[1]);
+      bw[2] = __viaddmin_u16x2(__vminu2(a.z, b.z), k2p, bw[2]);
+      bw[3] = __viaddmin_u16x2(__vminu2(a.w, b.w), k2p, bw[3]);
     }
-    uint32_t ow[4];
+    const uint32_t capm = static_cast<uint32_t>(max_d2) * 0x10001u;
+    reinterpret_cast<uint4*>(d2)[i] = make_uint4(__vminu2(bw[0], capm), __vminu2(bw[1], capm), __vminu2(bw[2], capm), __vminu2(bw[3], capm));
+    int best[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      ow[j] = static_cast<uint32_t>(min(best[2 * j], max_d2)) | (static_cast<uint32_t>(min(best[2 * j + 1], max_d2)) << 16);
-    reinterpret_cast<uint4*>(d2)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    for (int j = 0; j < 8; ++j)
+      best[j] = static_cast<int>((bw[j >> 1] >> (16 * (j & 1))) & 0xffffu);
     // our 8 elements of the interleaved compact field: element 2 * (8 i + j) counted from `compact` (already offset).
     // The 1-cell border shell of the COMPACT field is kept at "free": DistanceField::getDistanceGradient
     // (distance_field.cpp:82) answers max_distance for those cells, and the fast check kernel clamps to them.
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(256) edtXKernel(GridDev g, const uint16_t* __r
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
   {
     const int x = static_cast<int>(i / plane);
-    int best = in[i];  // kInf16 (65535) acts as +inf: it can only lose against anything within range
+    int best = in[i];  // anything above max_d2 means "nothing within range": it can only lose
     const int limit = min(best, max_d2 + 1);
     best = limit;
     for (int k = 1; k <= R && k * k < best; ++k)
@@ -396,18 +400,21 @@ cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint3
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
                       int compact_bytes, int sm_count, cudaStream_t s)
 {
-  // y chunks: small enough for several CTAs per SM (a haloed slab = occupancy words + z distances in shared memory),
-  // large enough that the 2R halo rows stay a modest overhead
-  const int nzp = (g.nz + 3) & ~3;
-  const size_t per_row = static_cast<size_t>(g.wz) * 4 + nzp;
+  // y chunks: small enough for several CTAs per SM (a haloed slab = occupancy words + squared z distances in shared
+  // memory), large enough that the 2R halo rows stay a modest overhead
+  if (g.R > 180)
+    return cudaErrorInvalidConfiguration;  // (R+1)^2 + R^2 must fit 16 bits
+  const int nzp = (g.nz + 7) & ~7;
+  const size_t per_row = static_cast<size_t>(g.wz) * 4 + static_cast<size_t>(nzp) * 2;
   const long max_rows = static_cast<long>((200 * 1024) / per_row);
   if (max_rows < 2L * g.R + 1)
     return cudaErrorInvalidConfiguration;  // a haloed row block does not fit: grid too deep for this kernel
-  int chunk = std::min<long>(g.ny, std::max<long>(4L * g.R, 64));
-  chunk = static_cast<int>(std::min<long>(chunk, max_rows - 2L * g.R));
+  static const int chunk_env = getenv("B200SV_EDT_CHUNK") ? atoi(getenv("B200SV_EDT_CHUNK")) : 0;
+  int chunk = chunk_env > 0 ? chunk_env : std::min<long>(g.ny, std::max<long>(4L * g.R, 64));
+  chunk = static_cast<int>(std::max<long>(1, std::min<long>(std::min<long>(chunk, g.ny), max_rows - 2L * g.R)));
   const int n_chunks = (g.ny + chunk - 1) / chunk;
   const size_t smem = ((static_cast<size_t>(chunk + 2 * g.R) * g.wz * 4 + 15) & ~static_cast<size_t>(15)) +
-                      static_cast<size_t>(chunk + 2 * g.R) * nzp;
+                      static_cast<size_t>(chunk + 2 * g.R) * nzp * 2;
   static size_t granted = 0;
   if (smem > granted)
   {
@@ -416,7 +423,9 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
       return e;
     granted = smem;
   }
-  edtZYKernel<<<g.nx * n_chunks, 256, smem, s>>>(g, occ, tmp, chunk, n_chunks);
+  const unsigned nz8 = static_cast<unsigned>(nzp / 8);
+  const unsigned nz8_magic = static_cast<unsigned>(((1ull << 32) + nz8 - 1) / nz8);  // i / nz8 = umulhi(i, magic), i < 2^16
+  edtZYKernel<<<g.nx * n_chunks, 256, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
