@@ -48,6 +48,9 @@ def _declare(L):
     dp, ip, vp = c.POINTER(c.c_double), c.POINTER(c.c_int32), c.c_void_p
     L.orc_pdf_create.restype = vp
     L.orc_pdf_create.argtypes = [c.c_double] * 8
+    L.orc_pdf_create_signed.restype = vp
+    L.orc_pdf_create_signed.argtypes = [c.c_double] * 8 + [c.c_int]
+    L.orc_pdf_get_neg_d2.argtypes = [vp, ip]
     L.orc_pdf_destroy.argtypes = [vp]
     L.orc_pdf_reset.argtypes = [vp]
     L.orc_pdf_add_points.argtypes = [vp, dp, c.c_size_t]

@@ -81,7 +81,7 @@ void orc_grid_grid_to_world(const orc_grid* g, int x, int y, int z, double* w)
 }
 
 /* ------------------------------------------------------------------------------------------------------
- * PropagationDistanceField (unsigned part): distance_field/src/propagation_distance_field.cpp
+ * PropagationDistanceField (unsigned, and signed = propagate_negative_): distance_field/src/propagation_distance_field.cpp
  * The voxel record keeps the reference's 40-byte layout (propagation_distance_field.hpp:82-116).
  * ---------------------------------------------------------------------------------------------------- */
 typedef struct
@@ -115,6 +115,8 @@ typedef struct
   int max_distance_sq;
   double* sqrt_table;
   ivec3_list* bucket_queue; /* max_distance_sq + 1 buckets */
+  ivec3_list* negative_bucket_queue;
+  int propagate_negative; /* the constructor's propagate_negative_distances (:48-58) */
   ivec3 neighborhoods[2][27][26];
   int neighborhood_size[2][27];
   ivec3 direction_number_to_direction[27];
@@ -178,9 +180,11 @@ void orc_pdf_reset(orc_pdf* f) /* :506-524 and the PropDistanceFieldVoxel(int,in
       }
 }
 
-orc_pdf* orc_pdf_create(double sx, double sy, double sz, double res, double ox, double oy, double oz, double max_distance)
+orc_pdf* orc_pdf_create_signed(double sx, double sy, double sz, double res, double ox, double oy, double oz,
+                               double max_distance, int propagate_negative)
 {
   orc_pdf* f = (orc_pdf*)calloc(1, sizeof(orc_pdf));
+  f->propagate_negative = propagate_negative;
   orc_grid_init(&f->grid, sx, sy, sz, res, ox, oy, oz);
   f->max_distance = max_distance;
   f->inv_twice_resolution = (int)(1.0 / (2.0 * res)); /* distance_field.cpp:67 into an int member */
@@ -189,6 +193,7 @@ orc_pdf* orc_pdf_create(double sx, double sy, double sz, double res, double ox, 
   f->data = (orc_voxel*)malloc((size_t)f->grid.num_cells_total * sizeof(orc_voxel));
   pdf_init_neighborhoods(f);
   f->bucket_queue = (ivec3_list*)calloc((size_t)f->max_distance_sq + 1, sizeof(ivec3_list));
+  f->negative_bucket_queue = (ivec3_list*)calloc((size_t)f->max_distance_sq + 1, sizeof(ivec3_list));
   f->sqrt_table = (double*)malloc(((size_t)f->max_distance_sq + 1) * sizeof(double));
   for (int i = 0; i <= f->max_distance_sq; ++i)
     f->sqrt_table[i] = sqrt((double)i) * res;
@@ -196,13 +201,22 @@ orc_pdf* orc_pdf_create(double sx, double sy, double sz, double res, double ox, 
   return f;
 }
 
+orc_pdf* orc_pdf_create(double sx, double sy, double sz, double res, double ox, double oy, double oz, double max_distance)
+{
+  return orc_pdf_create_signed(sx, sy, sz, res, ox, oy, oz, max_distance, 0);
+}
+
 void orc_pdf_destroy(orc_pdf* f)
 {
   if (!f)
     return;
   for (int i = 0; i <= f->max_distance_sq; ++i)
+  {
     free(f->bucket_queue[i].v);
+    free(f->negative_bucket_queue[i].v);
+  }
   free(f->bucket_queue);
+  free(f->negative_bucket_queue);
   free(f->sqrt_table);
   free(f->data);
   free(f);
@@ -258,23 +272,114 @@ static void pdf_propagate_positive(orc_pdf* f) /* :390-444 */
   }
 }
 
-static void pdf_add_new_obstacle_voxels(orc_pdf* f, const ivec3* pts, size_t n) /* :221-249 (unsigned branch) */
+static void pdf_propagate_negative(orc_pdf* f) /* :446-504 */
 {
+  const orc_grid* g = &f->grid;
+  for (int i = 0; i <= f->max_distance_sq; ++i)
+  {
+    size_t end = f->negative_bucket_queue[i].n; /* list_end is captured before the loop in the reference */
+    for (size_t it = 0; it < end; ++it)
+    {
+      ivec3 loc = f->negative_bucket_queue[i].v[it];
+      orc_voxel* vptr = &f->data[grid_ref(g, loc.x, loc.y, loc.z)];
+      int d = i;
+      if (d > 1)
+        d = 1;
+      if (vptr->negative_update_direction < 0 || vptr->negative_update_direction > 26)
+        continue;
+      const ivec3* nb = f->neighborhoods[d][vptr->negative_update_direction];
+      int nn = f->neighborhood_size[d][vptr->negative_update_direction];
+      for (int k = 0; k < nn; ++k)
+      {
+        ivec3 diff = nb[k];
+        ivec3 nloc = { loc.x + diff.x, loc.y + diff.y, loc.z + diff.z };
+        if (!grid_valid(g, nloc.x, nloc.y, nloc.z))
+          continue;
+        orc_voxel* neighbor = &f->data[grid_ref(g, nloc.x, nloc.y, nloc.z)];
+        int ex = vptr->closest_negative_point[0] - nloc.x, ey = vptr->closest_negative_point[1] - nloc.y,
+            ez = vptr->closest_negative_point[2] - nloc.z;
+        int new_distance_sq = ex * ex + ey * ey + ez * ez;
+        if (new_distance_sq > f->max_distance_sq)
+          continue;
+        if (new_distance_sq < neighbor->negative_distance_square)
+        {
+          neighbor->negative_distance_square = new_distance_sq;
+          neighbor->closest_negative_point[0] = vptr->closest_negative_point[0];
+          neighbor->closest_negative_point[1] = vptr->closest_negative_point[1];
+          neighbor->closest_negative_point[2] = vptr->closest_negative_point[2];
+          neighbor->negative_update_direction = direction_number(diff.x, diff.y, diff.z);
+          list_push(&f->negative_bucket_queue[new_distance_sq], nloc);
+        }
+      }
+    }
+    f->negative_bucket_queue[i].n = 0; /* clear() */
+  }
+}
+
+static void pdf_add_new_obstacle_voxels(orc_pdf* f, const ivec3* pts, size_t n) /* :221-301 */
+{
+  const orc_grid* g = &f->grid;
   int initial_update_direction = direction_number(0, 0, 0);
+  ivec3_list negative_stack = { 0, 0, 0 };
   for (size_t i = 0; i < n; ++i)
   {
-    orc_voxel* v = &f->data[grid_ref(&f->grid, pts[i].x, pts[i].y, pts[i].z)];
+    orc_voxel* v = &f->data[grid_ref(g, pts[i].x, pts[i].y, pts[i].z)];
     v->distance_square = 0;
     v->closest_point[0] = pts[i].x;
     v->closest_point[1] = pts[i].y;
     v->closest_point[2] = pts[i].z;
     v->update_direction = initial_update_direction;
     list_push(&f->bucket_queue[0], pts[i]);
+    if (f->propagate_negative)
+    {
+      v->negative_distance_square = f->max_distance_sq;
+      v->closest_negative_point[0] = v->closest_negative_point[1] = v->closest_negative_point[2] = -1; /* UNINITIALIZED */
+      list_push(&negative_stack, pts[i]);
+    }
   }
   pdf_propagate_positive(f);
+  if (f->propagate_negative)
+  {
+    while (negative_stack.n) /* :255-298 */
+    {
+      ivec3 loc = negative_stack.v[--negative_stack.n];
+      for (int neighbor = 0; neighbor < 27; ++neighbor)
+      {
+        ivec3 diff = f->direction_number_to_direction[neighbor];
+        ivec3 nloc = { loc.x + diff.x, loc.y + diff.y, loc.z + diff.z };
+        if (!grid_valid(g, nloc.x, nloc.y, nloc.z))
+          continue;
+        orc_voxel* nvoxel = &f->data[grid_ref(g, nloc.x, nloc.y, nloc.z)];
+        int* close_point = nvoxel->closest_negative_point;
+        if (!grid_valid(g, close_point[0], close_point[1], close_point[2]))
+        {
+          close_point[0] = nloc.x;
+          close_point[1] = nloc.y;
+          close_point[2] = nloc.z;
+        }
+        orc_voxel* closest_point_voxel = &f->data[grid_ref(g, close_point[0], close_point[1], close_point[2])];
+        if (closest_point_voxel->negative_distance_square != 0)
+        { /* our closest non-obstacle cell has become an obstacle */
+          if (nvoxel->negative_distance_square != f->max_distance_sq)
+          {
+            nvoxel->negative_distance_square = f->max_distance_sq;
+            nvoxel->closest_negative_point[0] = nvoxel->closest_negative_point[1] = nvoxel->closest_negative_point[2] = -1;
+            list_push(&negative_stack, nloc);
+          }
+        }
+        else
+        { /* this cell still has a valid non-obstacle cell: propagate from it */
+          nvoxel->negative_update_direction = initial_update_direction;
+          list_push(&f->negative_bucket_queue[0], nloc);
+        }
+      }
+    }
+    pdf_propagate_negative(f);
+  }
+  free(negative_stack.v);
 }
 
-static void pdf_remove_obstacle_voxels(orc_pdf* f, const ivec3* pts, size_t n) /* :303-388 (unsigned branch) */
+static void pdf_remove_obstacle_voxels(orc_pdf* f, const ivec3* pts, size_t n) /* :303-388 */
 {
   const orc_grid* g = &f->grid;
   ivec3_list stack = { 0, 0, 0 };
@@ -288,6 +393,15 @@ static void pdf_remove_obstacle_voxels(orc_pdf* f, const ivec3* pts, size_t n) /
     v->closest_point[2] = pts[i].z;
     v->update_direction = initial_update_direction;
     list_push(&stack, pts[i]);
+    if (f->propagate_negative)
+    {
+      v->negative_distance_square = 0;
+      v->closest_negative_point[0] = pts[i].x;
+      v->closest_negative_point[1] = pts[i].y;
+      v->closest_negative_point[2] = pts[i].z;
+      v->negative_update_direction = initial_update_direction;
+      list_push(&f->negative_bucket_queue[0], pts[i]);
+    }
   }
   while (stack.n)
   {
@@ -328,6 +442,8 @@ static void pdf_remove_obstacle_voxels(orc_pdf* f, const ivec3* pts, size_t n) /
   }
   free(stack.v);
   pdf_propagate_positive(f);
+  if (f->propagate_negative)
+    pdf_propagate_negative(f);
 }
 
 void orc_pdf_add_points(orc_pdf* f, const double* xyz, size_t n) /* addPointsToField :177-196 */
@@ -449,6 +565,11 @@ void orc_pdf_get_d2(const orc_pdf* f, int32_t* out)
 {
   for (long i = 0; i < f->grid.num_cells_total; ++i)
     out[i] = f->data[i].distance_square;
+}
+void orc_pdf_get_neg_d2(const orc_pdf* f, int32_t* out)
+{
+  for (long i = 0; i < f->grid.num_cells_total; ++i)
+    out[i] = f->data[i].negative_distance_square;
 }
 const orc_grid* orc_pdf_grid(const orc_pdf* f) { return &f->grid; }
 

@@ -17,12 +17,15 @@ def _ip(a):
 
 
 class PropagationDistanceField:
-    """Mirrors distance_field::PropagationDistanceField's constructor and point API (unsigned fields)."""
+    """Mirrors distance_field::PropagationDistanceField's constructor and point API (propagation_distance_field.cpp:48-58;
+    propagate_negative_distances = the signed field)."""
 
-    def __init__(self, size_x, size_y, size_z, resolution, origin_x, origin_y, origin_z, max_distance):
+    def __init__(self, size_x, size_y, size_z, resolution, origin_x, origin_y, origin_z, max_distance,
+                 propagate_negative_distances=False):
         self._L = lib()
         self.args = (size_x, size_y, size_z, resolution, origin_x, origin_y, origin_z, max_distance)
-        self.h = ctypes.c_void_p(self._L.orc_pdf_create(*[float(a) for a in self.args]))
+        self.propagate_negative = bool(propagate_negative_distances)
+        self.h = ctypes.c_void_p(self._L.orc_pdf_create_signed(*[float(a) for a in self.args], int(self.propagate_negative)))
         n = np.zeros(3, np.int32)
         m = np.zeros(1, np.int32)
         self._L.orc_pdf_dims(self.h, _ip(n), _ip(m))
@@ -66,6 +69,12 @@ class PropagationDistanceField:
         """int32 squared cell distances, shape (nx, ny, nz) -- index x*ny*nz + y*nz + z (voxel_grid.hpp:425)."""
         out = np.zeros(self.num_cells, np.int32)
         self._L.orc_pdf_get_d2(self.h, _ip(out))
+        return out
+
+    def neg_d2(self):
+        """int32 negative_distance_square_ per voxel (0 outside obstacles; signed fields only)."""
+        out = np.zeros(self.num_cells, np.int32)
+        self._L.orc_pdf_get_neg_d2(self.h, _ip(out))
         return out
 
     def get_distance(self, x, y, z):
