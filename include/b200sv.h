@@ -101,7 +101,10 @@ typedef struct b200sv_field_cfg
   double resolution;
   double max_propagation_distance;
   double collision_tolerance;
-  int32_t use_signed_distance_field; /* must be 0 (reference default); 1 returns B200SV_ERR_UNSUPPORTED */
+  int32_t use_signed_distance_field; /* 0 = the reference default (collision_env_distance_field.hpp:52); 1 = propagate_negative_:
+                                        every rebuild also transforms the complement (distance of an occupied voxel to the
+                                        nearest free one), getDistance = sqrt(d2) * res - sqrt(neg d2) * res
+                                        (propagation_distance_field.hpp:604-607) feeds the gradients */
 } b200sv_field_cfg;
 
 typedef struct b200sv_info
@@ -189,6 +192,10 @@ int b200sv_field_get_d2(b200sv_ctx* ctx, int which, int32_t* d2_out);
 /* Inject an externally built field (e.g. the reference's own propagation result) so check parity can be tested
  * independently of EDT parity. */
 int b200sv_field_set_d2(b200sv_ctx* ctx, int which, const int32_t* d2);
+/* Signed fields (propagateNegative, propagation_distance_field.cpp:446-504): negative_distance_square_ per voxel, same
+ * layout; 0 in free voxels and in every voxel of an unsigned field.  set: inject, like b200sv_field_set_d2. */
+int b200sv_field_get_neg_d2(b200sv_ctx* ctx, int which, int32_t* neg_d2_out);
+int b200sv_field_set_neg_d2(b200sv_ctx* ctx, int which, const int32_t* neg_d2);
 /* PropagationDistanceField::writeToStream / readFromStream (propagation_distance_field.cpp:635-760): the ".df" format of
  * the reference's fixtures (moveit_core/test_small.df, test_big.df) -- 7 ASCII header lines, then zlib data with the
  * occupancy, x-major, then y, then z packed 8 voxels per byte LSB-first.  write: call with out = NULL to learn the size.

@@ -81,6 +81,8 @@ def load():
         "b200sv_field_add_points_device": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp]),
         "b200sv_field_get_d2": (C.c_int, [vp, C.c_int, ip]),
         "b200sv_field_set_d2": (C.c_int, [vp, C.c_int, ip]),
+        "b200sv_field_get_neg_d2": (C.c_int, [vp, C.c_int, ip]),
+        "b200sv_field_set_neg_d2": (C.c_int, [vp, C.c_int, ip]),
         "b200sv_field_write_df": (C.c_int, [vp, C.c_int, u8p, C.c_size_t, C.POINTER(C.c_size_t)]),
         "b200sv_field_read_df": (C.c_int, [vp, C.c_int, u8p, C.c_size_t]),
         "b200sv_get_self_points": (C.c_int, [vp, dp, C.c_size_t, C.POINTER(C.c_size_t)]),

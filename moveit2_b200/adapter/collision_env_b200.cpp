@@ -19,7 +19,7 @@ rclcpp::Logger getLogger()
 const double STATE_EPSILON = 0.001;  // EPSILON of collision_env_distance_field.cpp:55
 
 b200sv_field_cfg fieldCfg(const Eigen::Vector3d& size, const Eigen::Vector3d& origin, double res, double max_prop,
-                          double tol)
+                          double tol, bool use_signed_distance_field)
 {
   b200sv_field_cfg f{};
   for (int k = 0; k < 3; ++k)
@@ -30,7 +30,7 @@ b200sv_field_cfg fieldCfg(const Eigen::Vector3d& size, const Eigen::Vector3d& or
   f.resolution = res;
   f.max_propagation_distance = max_prop;
   f.collision_tolerance = tol;
-  f.use_signed_distance_field = 0;
+  f.use_signed_distance_field = use_signed_distance_field ? 1 : 0;
   return f;
 }
 }  // namespace
@@ -299,7 +299,8 @@ CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::
   m.sphere_xyzr = sphere_xyzr.data();
   m.bounding_sphere = bounding_sphere.data();
 
-  const b200sv_field_cfg f = fieldCfg(size_, origin_, resolution_, max_propogation_distance_, collision_tolerance_);
+  const b200sv_field_cfg f = fieldCfg(size_, origin_, resolution_, max_propogation_distance_, collision_tolerance_,
+                                      use_signed_distance_field_);
   auto gc = std::make_shared<GroupContext>();
   for (int i = 0; i < n; ++i)
   {

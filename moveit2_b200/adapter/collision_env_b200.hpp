@@ -90,6 +90,7 @@ private:
 
   Eigen::Vector3d size_, origin_;
   double resolution_, collision_tolerance_, max_propogation_distance_;
+  bool use_signed_distance_field_ = false;  // DEFAULT_USE_SIGNED_DISTANCE_FIELD (collision_env_distance_field.hpp:52)
   std::vector<BodyDecompositionConstPtr> link_body_decomposition_vector_;  // as the reference (:1049-1078)
   std::map<std::string, unsigned int> link_body_decomposition_index_map_;
   // world points currently in the field, per object id (DistanceFieldCacheEntryWorld::posed_body_point_decompositions_)

@@ -26,6 +26,7 @@ struct Field
 {
   uint32_t* occ = nullptr;    // occupancy bits
   uint16_t* d2 = nullptr;     // min(d^2, max_d2)
+  uint16_t* nd2 = nullptr;    // signed fields only: negative_distance_square_ (distance to the nearest free voxel)
   void* compact = nullptr;    // this field's half of the interleaved compact field (base + which elements)
   bool dirty = false;
 };
@@ -166,9 +167,23 @@ inline int align16(int x) { return (x + 15) & ~15; }
 //   collide = (maximum_value > dist) && (radius - dist > tolerance),  dist = sqrt_table[d2] (unsigned field)
 // with sqrt_table[i] = sqrt(double(i)) * resolution (propagation_distance_field.cpp:99-101).  dist grows with d2,
 // so the predicate is true exactly for d2 < T.  T in [0, max_d2 + 1].
-int sphereThreshold(double radius, double res, double max_prop, double tol, int max_d2)
+// Signed fields: an occupied voxel (d2 = 0) carries dist = -sqrt(neg d2) * res with neg d2 in [1, max_d2]; free voxels are as
+// in the unsigned field.  The integer form still exists when the predicate gives one answer for every such neg d2 (it does
+// unless tolerance exceeds radius + resolution); -1 = it does not.
+int sphereThreshold(double radius, double res, double max_prop, double tol, int max_d2, bool signed_field)
 {
-  for (int i = 0; i <= max_d2; ++i)
+  if (signed_field)
+  {
+    auto hit = [&](int nd2) {
+      const double dist = sqrt(double(0)) * res - sqrt(double(nd2)) * res;
+      return (max_prop > dist) && (radius - dist > tol);
+    };
+    if (hit(1) != hit(max_d2))
+      return -1;
+    if (!hit(1))
+      return 0;  // radius - dist only shrinks as d2 grows
+  }
+  for (int i = signed_field ? 1 : 0; i <= max_d2; ++i)
   {
     const double dist = sqrt(double(i)) * res - sqrt(double(0)) * res;  // getDistance(): sqrt_table[d2] - sqrt_table[neg d2 = 0]
     if (!((max_prop > dist) && (radius - dist > tol)))
@@ -895,7 +910,11 @@ int buildTables(b200sv_ctx* c)
       S.r = m.sphere_xyzr[4 * k + 3];
       S.slot = slot;
       S.thr = sphereThreshold(S.r, c->cfg.resolution, c->cfg.max_propagation_distance, c->cfg.collision_tolerance,
-                              c->grid.max_d2);
+                              c->grid.max_d2, c->cfg.use_signed_distance_field != 0);
+      if (S.thr < 0)
+        return fail(c, B200SV_ERR_UNSUPPORTED,
+                    "signed field: collision_tolerance exceeds a sphere's radius + resolution, the outcome inside obstacles "
+                    "would depend on the depth");
       S.thr_self = m.self_enabled[i] ? S.thr : 0;
       max_thr = std::max(max_thr, S.thr);
       spheres.push_back(S);
@@ -1117,8 +1136,6 @@ int initGrid(b200sv_ctx* c)
   const b200sv_field_cfg& f = c->cfg;
   if (!(f.resolution > 0.0) || !(f.max_propagation_distance > 0.0))
     return fail(c, B200SV_ERR_INVALID, "resolution and max_propagation_distance must be positive");
-  if (f.use_signed_distance_field)
-    return fail(c, B200SV_ERR_UNSUPPORTED, "signed distance fields (propagate_negative) are not implemented");
   // corner = origin - size / 2 (collision_env_distance_field.cpp:1786-1787); VoxelGrid::resize (voxel_grid.hpp:364-396)
   const double res = f.resolution;
   const double oo = 1.0 / res;
@@ -1162,8 +1179,22 @@ int allocFields(b200sv_ctx* c)
     F.compact = static_cast<uint8_t*>(c->d_combined) + (size_t)w * c->compact_bytes;
     CU(c, cudaMemsetAsync(F.occ, 0, occ_bytes, c->stream));
     CU(c, launchFillField(g, F.d2, F.compact, c->compact_bytes, c->stream));
+    if (c->cfg.use_signed_distance_field)
+    {  // reset(): negative_distance_square_ = 0 everywhere (propagation_distance_field.cpp:506-524)
+      CU(c, cudaMalloc(&F.nd2, c->n_voxels * 2));
+      CU(c, cudaMemsetAsync(F.nd2, 0, c->n_voxels * 2, c->stream));
+    }
   }
   CU(c, cudaMalloc(&c->d_tmp, c->n_voxels * 2));
+  return B200SV_OK;
+}
+
+// The positive transform, and for a signed field (propagate_negative_) the transform of the complement
+int edtPasses(b200sv_ctx* c, Field& F, cudaStream_t s)
+{
+  CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.d2, F.compact, c->compact_bytes, c->sm_count, s));
+  if (F.nd2)
+    CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.nd2, nullptr, c->compact_bytes, c->sm_count, s, true));
   return B200SV_OK;
 }
 
@@ -1171,7 +1202,8 @@ int rebuildField(b200sv_ctx* c, int which)
 {
   Field& F = c->fields[which];
   CU(c, cudaEventRecord(c->ev0, c->stream));
-  CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.d2, F.compact, c->compact_bytes, c->sm_count, c->stream));
+  if (int rc = edtPasses(c, F, c->stream))
+    return rc;
   CU(c, cudaEventRecord(c->ev1, c->stream));
   CU(c, cudaEventSynchronize(c->ev1));
   float ms = 0.f;
@@ -1484,6 +1516,8 @@ void b200sv_destroy(b200sv_ctx* c)
     Field& F = c->fields[w];
     if (F.d2)
       cudaFree(F.d2);
+    if (F.nd2)
+      cudaFree(F.nd2);
     if (F.occ)
       cudaFree(F.occ);
   }
@@ -1665,6 +1699,8 @@ int b200sv_field_reset(b200sv_ctx* c, int which)
   Field& F = c->fields[which];
   CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
   CU(c, launchFillField(c->grid, F.d2, F.compact, c->compact_bytes, c->stream));
+  if (F.nd2)
+    CU(c, cudaMemsetAsync(F.nd2, 0, c->n_voxels * 2, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return B200SV_OK;
 }
@@ -1771,9 +1807,7 @@ int b200sv_field_add_points_device(b200sv_ctx* c, int which, const double* d_xyz
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   if ((rc = addOrRemove(c, which, d_xyz, n, true, s)) != B200SV_OK)
     return rc;
-  Field& F = c->fields[which];
-  CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.d2, F.compact, c->compact_bytes, c->sm_count, s));
-  return B200SV_OK;
+  return edtPasses(c, c->fields[which], s);
 }
 
 int b200sv_field_get_d2(b200sv_ctx* c, int which, int32_t* out)
@@ -1790,6 +1824,46 @@ int b200sv_field_get_d2(b200sv_ctx* c, int which, int32_t* out)
   CU(c, cudaStreamSynchronize(c->stream));
   for (size_t i = 0; i < c->n_voxels; ++i)
     out[i] = h[i];
+  return B200SV_OK;
+}
+
+int b200sv_field_get_neg_d2(b200sv_ctx* c, int which, int32_t* out)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!out)
+    return fail(c, B200SV_ERR_INVALID, "null output");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  if (!c->fields[which].nd2)
+  {  // an unsigned field: negative_distance_square_ stays at its reset value
+    std::fill(out, out + c->n_voxels, 0);
+    return B200SV_OK;
+  }
+  std::vector<uint16_t> h(c->n_voxels);
+  CU(c, cudaMemcpyAsync(h.data(), c->fields[which].nd2, c->n_voxels * 2, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < c->n_voxels; ++i)
+    out[i] = h[i];
+  return B200SV_OK;
+}
+
+int b200sv_field_set_neg_d2(b200sv_ctx* c, int which, const int32_t* nd2)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!nd2)
+    return fail(c, B200SV_ERR_INVALID, "null input");
+  if (!c->fields[which].nd2)
+    return fail(c, B200SV_ERR_INVALID, "the context's fields are unsigned (use_signed_distance_field = 0)");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  CU(c, c->d_i32.ensure(c->n_voxels));
+  CU(c, cudaMemcpyAsync(c->d_i32.p, nd2, c->n_voxels * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, launchInjectNegD2(c->grid, c->d_i32.p, c->fields[which].nd2, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   return B200SV_OK;
 }
 
@@ -2155,6 +2229,8 @@ int b200sv_collision_gradients(b200sv_ctx* c, const double* q, size_t n, double*
   a.n_states = n;
   a.d2_world = c->fields[0].d2;
   a.d2_self = c->fields[1].d2;
+  a.nd2_world = c->fields[0].nd2;
+  a.nd2_self = c->fields[1].nd2;
   a.self_enabled = c->d_g_self.p;
   a.n_glinks = (int)L;
   a.resolution = c->cfg.resolution;

@@ -773,12 +773,17 @@ __global__ void gatherKernel(const uint8_t* __restrict__ field, unsigned long lo
 // subtract_radii = false; DistanceField::getDistanceGradient: distance_field.cpp:73-97 (1-cell margin, central
 // differences times inv_twice_resolution_); PropagationDistanceField::getDistance = sqrt(d2) * resolution.
 // One thread per state; sphere centres live in shared memory ([sphere][xyz] per thread, 24 B each).
-__device__ __forceinline__ double cellDistance(const uint16_t* __restrict__ d2, size_t idx, double res)
+__device__ __forceinline__ double cellDistance(const uint16_t* __restrict__ d2, const uint16_t* __restrict__ nd2, size_t idx,
+                                               double res)
 {
-  return sqrt(static_cast<double>(__ldg(d2 + idx))) * res;  // sqrt_table_[d2] (propagation_distance_field.cpp:99-101)
+  // getDistance (propagation_distance_field.hpp:604-607): sqrt_table_[d2] - sqrt_table_[negative d2], with
+  // sqrt_table_[i] = sqrt(i) * resolution (propagation_distance_field.cpp:99-101); the negative part is 0 in unsigned fields
+  const double pos = sqrt(static_cast<double>(__ldg(d2 + idx))) * res;
+  return nd2 ? __dsub_rn(pos, sqrt(static_cast<double>(__ldg(nd2 + idx))) * res) : pos;
 }
 
-__device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t* __restrict__ d2, const Smem<double>& m,
+__device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t* __restrict__ d2,
+                                               const uint16_t* __restrict__ nd2, const Smem<double>& m,
                                                const BsRec<double>& C, const double* cen, int type, double* dist_out,
                                                double* grad_out, uint8_t* type_out, double& closest)
 {
@@ -793,10 +798,10 @@ __device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t
     {
       const size_t sy = static_cast<size_t>(h.nz), sx = sy * h.ny;
       const size_t i0 = (static_cast<size_t>(gx) * h.ny + gy) * h.nz + gz;
-      g0 = (cellDistance(d2, i0 + sx, a.resolution) - cellDistance(d2, i0 - sx, a.resolution)) * a.inv_twice_resolution;
-      g1 = (cellDistance(d2, i0 + sy, a.resolution) - cellDistance(d2, i0 - sy, a.resolution)) * a.inv_twice_resolution;
-      g2 = (cellDistance(d2, i0 + 1, a.resolution) - cellDistance(d2, i0 - 1, a.resolution)) * a.inv_twice_resolution;
-      dist = cellDistance(d2, i0, a.resolution);
+      g0 = (cellDistance(d2, nd2, i0 + sx, a.resolution) - cellDistance(d2, nd2, i0 - sx, a.resolution)) * a.inv_twice_resolution;
+      g1 = (cellDistance(d2, nd2, i0 + sy, a.resolution) - cellDistance(d2, nd2, i0 - sy, a.resolution)) * a.inv_twice_resolution;
+      g2 = (cellDistance(d2, nd2, i0 + 1, a.resolution) - cellDistance(d2, nd2, i0 - 1, a.resolution)) * a.inv_twice_resolution;
+      dist = cellDistance(d2, nd2, i0, a.resolution);
     }
     if (dist < a.max_propagation)
     {
@@ -844,7 +849,7 @@ __global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
   {  // self field
     const BsRec<double>& C = m.bs[c];
     if (a.self_enabled[C.pad])
-      fieldGradients(a, a.d2_self, m, C, cen, 1, D, G, Ty, a.closest[i * a.n_glinks + C.pad]);
+      fieldGradients(a, a.d2_self, a.nd2_self, m, C, cen, 1, D, G, Ty, a.closest[i * a.n_glinks + C.pad]);
   }
   for (int p = 0; p < h.n_pairs; ++p)
   {  // intra-group: every sphere pair of the two clusters (all cluster pairs of a link pair = all its sphere pairs)
@@ -869,7 +874,7 @@ __global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
       }
   }
   for (int c = 0; c < h.n_bs; ++c)  // world field
-    fieldGradients(a, a.d2_world, m, m.bs[c], cen, 3, D, G, Ty, a.closest[i * a.n_glinks + m.bs[c].pad]);
+    fieldGradients(a, a.d2_world, a.nd2_world, m, m.bs[c], cen, 3, D, G, Ty, a.closest[i * a.n_glinks + m.bs[c].pad]);
 }
 
 // CollisionEnvDistanceField::checkCollision with req.contacts = true (collision_env_distance_field.cpp:1389-1411), n states:

@@ -51,8 +51,10 @@ __global__ void scatterKernel(const double* __restrict__ xyz, size_t n, GridDev 
 // rows k below and above) and VIADDMNMX.U16x2 (min(best, m + k^2)), both native on sm_100a.  "No occupied voxel within
 // R" is (R+1)^2: above max_d2, and small enough that adding k^2 <= R^2 stays below 2^16 (the launcher checks R <= 180).
 // Intermediate values above max_d2 mean "nothing within range"; the x pass treats them so.
+// `invert`: transform of the COMPLEMENT (distance to the nearest free voxel of the grid = negative_distance_square_ of the
+// signed field, propagateNegative :446-504); cells outside the grid are not free.
 __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
-                                                  int chunk, int n_chunks, unsigned nz8_magic)
+                                                  int chunk, int n_chunks, unsigned nz8_magic, int invert)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   const int x = blockIdx.x / n_chunks, ci = blockIdx.x - x * n_chunks;
@@ -65,8 +67,15 @@ __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __
   {
     const uint32_t* src = occ + (static_cast<size_t>(x) * g.ny + ya) * wz;  // rows are contiguous in the bitmap
     const int lo = max(0, -ya) * wz, hi = min(rows, g.ny - ya) * wz;
-    for (int i = threadIdx.x; i < rows * wz; i += blockDim.x)
-      bits[i] = (i >= lo && i < hi) ? src[i] : 0u;
+    if (!invert)
+      for (int i = threadIdx.x; i < rows * wz; i += blockDim.x)
+        bits[i] = (i >= lo && i < hi) ? src[i] : 0u;
+    else
+    {
+      const uint32_t last = (g.nz & 31) ? (1u << (g.nz & 31)) - 1u : 0xffffffffu;  // bits of the last word inside the grid
+      for (int i = threadIdx.x; i < rows * wz; i += blockDim.x)
+        bits[i] = (i >= lo && i < hi) ? (~src[i] & ((i % wz == wz - 1) ? last : 0xffffffffu)) : 0u;
+    }
   }
   __syncthreads();
   // z pass, one thread per 32-bit occupancy word: the distance of the word's two ends to the nearest set bit outside
@@ -226,6 +235,8 @@ __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* 
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       best[j] = static_cast<int>((bw[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+    if (compact == nullptr)
+      continue;  // the negative half of a signed field has no compact copy
     // our 8 elements of the interleaved compact field: element 2 * (8 i + j) counted from `compact` (already offset).
     // The 1-cell border shell of the COMPACT field is kept at "free": DistanceField::getDistanceGradient
     // (distance_field.cpp:82) answers max_distance for those cells, and the fast check kernel clamps to them.
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* 
 
 template <typename FT>
 __global__ void __launch_bounds__(256) edtXKernel(GridDev g, const uint16_t* __restrict__ in, uint16_t* __restrict__ d2,
-                                                 FT* __restrict__ compact)
+                                                 FT* compact)
 {
   const size_t plane = static_cast<size_t>(g.ny) * g.nz;
   const size_t total = plane * g.nx;
@@ -289,6 +300,8 @@ __global__ void __launch_bounds__(256) edtXKernel(GridDev g, const uint16_t* __r
     d2[i] = static_cast<uint16_t>(best);
     // interleaved compact field: element 2 * i + which (the caller passes compact already offset by `which`); its
     // 1-cell border shell is kept at "free" (see edtXKernelVec)
+    if (compact == nullptr)
+      continue;
     if (onShell(g, i))
       best = max_d2;
     compact[2 * i] = static_cast<FT>(sizeof(FT) == 1 ? min(best, 255) : best);
@@ -324,6 +337,13 @@ __global__ void injectKernel(GridDev g, const int32_t* __restrict__ in, uint32_t
       atomicOr(occ + row * g.wz + (z >> 5), 1u << (z & 31));
     }
   }
+}
+
+__global__ void injectNegKernel(size_t total, int max_d2, const int32_t* __restrict__ in, uint16_t* __restrict__ nd2)
+{
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    nd2[i] = static_cast<uint16_t>(min(max(in[i], 0), max_d2));
 }
 
 // DistanceField::addShapeToField for a SPHERE (distance_field.cpp:208-238): findInternalPointsConvex
@@ -398,7 +418,7 @@ cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint3
 }
 
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
-                      int compact_bytes, int sm_count, cudaStream_t s)
+                      int compact_bytes, int sm_count, cudaStream_t s, bool invert)
 {
   // y chunks: small enough for several CTAs per SM (a haloed slab = occupancy words + squared z distances in shared
   // memory), large enough that the 2R halo rows stay a modest overhead
@@ -425,7 +445,7 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
   }
   const unsigned nz8 = static_cast<unsigned>(nzp / 8);
   const unsigned nz8_magic = static_cast<unsigned>(((1ull << 32) + nz8 - 1) / nz8);  // i / nz8 = umulhi(i, magic), i < 2^16
-  edtZYKernel<<<g.nx * n_chunks, 256, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic);
+  edtZYKernel<<<g.nx * n_chunks, 256, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic, invert ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
@@ -455,6 +475,13 @@ cudaError_t launchFillField(const GridDev& g, uint16_t* d2, void* compact, int c
     fillKernel<uint8_t><<<grid, 256, 0, s>>>(total, g.max_d2, d2, static_cast<uint8_t*>(compact));
   else
     fillKernel<uint16_t><<<grid, 256, 0, s>>>(total, g.max_d2, d2, static_cast<uint16_t*>(compact));
+  return cudaGetLastError();
+}
+
+cudaError_t launchInjectNegD2(const GridDev& g, const int32_t* d_in, uint16_t* nd2, cudaStream_t s)
+{
+  const size_t total = static_cast<size_t>(g.nx) * g.ny * g.nz;
+  injectNegKernel<<<gridFor(total, 256, 148 * 16), 256, 0, s>>>(total, g.max_d2, d_in, nd2);
   return cudaGetLastError();
 }
 

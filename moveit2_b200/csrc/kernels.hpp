@@ -65,6 +65,8 @@ struct GradArgs
   unsigned long long n_states;
   const uint16_t* d2_world;  // min(d^2, max_d2) per voxel
   const uint16_t* d2_self;
+  const uint16_t* nd2_world;  // signed fields: negative_distance_square_ per voxel; nullptr for unsigned fields
+  const uint16_t* nd2_self;
   const uint8_t* self_enabled;  // [n_glinks]
   int n_glinks;
   double resolution, inv_twice_resolution, max_distance, max_propagation;
@@ -157,9 +159,11 @@ cudaError_t launchSphereShape(const double* d_axes, int nxs, int nys, int nzs, c
 cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint32_t* new_bits, size_t n_words, cudaStream_t s);
 // exact truncated EDT of the occupancy bitmap -> d2 (uint16, min(d^2, max_d2)) and this field's half of the
 // INTERLEAVED compact field (element 2 * voxel; `compact` arrives offset by 0 = world / 1 = self; uint8:
-// min(d^2, 255), uint16: d^2).  tmp: uint16 [nx*ny*nz] scratch.
+// min(d^2, 255), uint16: d^2).  tmp: uint16 [nx*ny*nz] scratch.  invert: the transform of the complement (the
+// negative half of a signed field; pass compact = nullptr, it has no compact copy).
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
-                      int compact_bytes, int sm_count, cudaStream_t s);
+                      int compact_bytes, int sm_count, cudaStream_t s, bool invert = false);
+cudaError_t launchInjectNegD2(const GridDev& g, const int32_t* d_in, uint16_t* nd2, cudaStream_t s);
 cudaError_t launchFillField(const GridDev& g, uint16_t* d2, void* compact, int compact_bytes, cudaStream_t s);
 cudaError_t launchInjectD2(const GridDev& g, const int32_t* d_in, uint32_t* occ, uint16_t* d2, void* compact,
                            int compact_bytes, cudaStream_t s);

@@ -236,6 +236,17 @@ class StateValidityEngine:
         assert a.size == self.num_cells[0] * self.num_cells[1] * self.num_cells[2]
         self._check(self.L.b200sv_field_set_d2(self.h, which, _ip(a)))
 
+    def field_get_neg_d2(self, which=FIELD_WORLD):
+        """negative_distance_square_ per voxel (signed fields; all 0 for an unsigned field)."""
+        out = np.zeros(self.num_cells, np.int32)
+        self._check(self.L.b200sv_field_get_neg_d2(self.h, which, _ip(out)))
+        return out
+
+    def field_set_neg_d2(self, neg_d2, which=FIELD_WORLD):
+        a = np.ascontiguousarray(neg_d2, np.int32).reshape(-1)
+        assert a.size == self.num_cells[0] * self.num_cells[1] * self.num_cells[2]
+        self._check(self.L.b200sv_field_set_neg_d2(self.h, which, _ip(a)))
+
     # ---- hot path -------------------------------------------------------------------------------------
     def fk_batch(self, q, precision=64):
         """[n, n_links, 4, 4] (row, col) global link transforms."""

@@ -132,7 +132,7 @@ class OracleEnv:
     """Restated CollisionEnvDistanceField for one (robot, group, ACM): owns world and self fields."""
 
     def __init__(self, model: RobotModel, group_name, size, origin, resolution, max_propagation_distance,
-                 collision_tolerance=0.0, use_acm=True, base_positions=None):
+                 collision_tolerance=0.0, use_acm=True, base_positions=None, use_signed_distance_field=False):
         self.L = lib()
         self.model, self.group = model, model.groups[group_name]
         g = self.group
@@ -217,8 +217,9 @@ class OracleEnv:
         sx, sy, sz = self.size
         ox, oy, oz = self.origin
         geo = (sx, sy, sz, self.resolution, ox - 0.5 * sx, oy - 0.5 * sy, oz - 0.5 * sz, self.max_prop)
-        self.world = PropagationDistanceField(*geo)
-        self.self_field = PropagationDistanceField(*geo)
+        # use_signed_distance_field_ (:1785-1797; default false, collision_env_distance_field.hpp:52)
+        self.world = PropagationDistanceField(*geo, use_signed_distance_field)
+        self.self_field = PropagationDistanceField(*geo, use_signed_distance_field)
         self.self_points = self.compute_self_points()
         self.self_field.add_points(self.self_points)
 

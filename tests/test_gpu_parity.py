@@ -726,3 +726,85 @@ def test_validity_dense_dual_arm():
         assert np.array_equal(eng.check_batch(q, flags), ref == 0), flags
     assert 0.05 < ref.mean() < 0.95
     eng.close()
+
+
+# ---- signed fields (use_signed_distance_field_ / propagate_negative_) ------------------------------------------------------
+def _solid_scene():
+    """Solid bodies the arm can reach into: spheres voxelised with the reference's own lattice (findInternalPointsConvex)."""
+    return [((0.45, 0.15, 0.55), 0.17), ((0.3, -0.35, 0.35), 0.14), ((-0.1, 0.4, 0.7), 0.12), ((0.42, 0.2, 0.5), 0.1)]
+
+
+@pytest.mark.gpu
+def test_signed_field_edt_is_the_exact_transform_of_the_complement():
+    from scipy import ndimage
+    cfg = workloads.CONFIGS["C1"]
+    eng, env = make_pair(cfg["robot"], cfg["group"], cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"], signed=True)
+    for c, r in _solid_scene():
+        eng.field_add_sphere(c, r)
+        env.world.add_points(find_internal_points_sphere(c, r, cfg["resolution"]))
+    g, gn, o, on = eng.field_get_d2(), eng.field_get_neg_d2(), env.world.d2(), env.world.neg_d2()
+    occ = g == 0
+    assert np.array_equal(occ, o == 0) and occ.sum() > 3000
+    exact = np.minimum(np.rint(ndimage.distance_transform_edt(occ) ** 2).astype(np.int64), eng.max_distance_sq)
+    assert np.array_equal(gn, exact)          # 0 in free voxels, distance to the nearest free voxel inside obstacles
+    assert gn.max() >= 16                     # the scene is deep enough to mean something
+    # the reference's propagateNegative never under-estimates and differs in few voxels (counted)
+    assert (on >= gn).all() and np.array_equal(on > 0, occ)
+    differing = int((on != gn).sum())
+    assert differing <= 0.05 * occ.sum()
+    print("signed field: %d occupied voxels, %d of them above the exact value in the reference's propagation" % (occ.sum(), differing))
+    # the self field (voxelised non-group links) gets its negative half too
+    sn = eng.field_get_neg_d2(mb.FIELD_SELF)
+    assert np.array_equal(sn > 0, eng.field_get_d2(mb.FIELD_SELF) == 0) and (env.self_field.neg_d2() >= sn).all()
+    # removal == fresh build (test_distance_field.cpp:508), reset clears both halves
+    c0, r0 = _solid_scene()[0]
+    eng.field_remove_points(find_internal_points_sphere(c0, r0, cfg["resolution"]))
+    fresh, _ = make_pair(cfg["robot"], cfg["group"], cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"], signed=True)
+    for c, r in _solid_scene()[1:]:
+        fresh.field_add_sphere(c, r)
+    # (sphere 3 overlaps sphere 0: the voxels they share are removed with sphere 0, as in the reference)
+    fresh.field_remove_points(find_internal_points_sphere(c0, r0, cfg["resolution"]))
+    assert np.array_equal(eng.field_get_d2(), fresh.field_get_d2()) and np.array_equal(eng.field_get_neg_d2(), fresh.field_get_neg_d2())
+    eng.field_reset()
+    assert not eng.field_get_neg_d2().any() and (eng.field_get_d2() == eng.max_distance_sq).all()
+    eng.close()
+    fresh.close()
+
+
+@pytest.mark.gpu
+def test_signed_field_validity_and_gradients_equal_oracle():
+    """Signed fields change distances and gradients inside obstacles (CHOMP's way out of a collision), not the boolean."""
+    cfg = workloads.CONFIGS["C1"]
+    eng, env = make_pair(cfg["robot"], cfg["group"], cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"], signed=True)
+    uns, _ = make_pair(cfg["robot"], cfg["group"], cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    for c, r in _solid_scene():
+        env.world.add_points(find_internal_points_sphere(c, r, cfg["resolution"]))
+    # the reference's own propagation result, both halves, so this test is independent of EDT parity
+    for which, f in ((mb.FIELD_WORLD, env.world), (mb.FIELD_SELF, env.self_field)):
+        eng.field_set_d2(f.d2(), which)
+        eng.field_set_neg_d2(f.neg_d2(), which)
+        uns.field_set_d2(f.d2(), which)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(77, 20000, lo, hi)
+    for flags in (W, S, ALL):
+        ref, _ = env.check(q, flags)
+        assert np.array_equal(eng.check_batch(q, flags), ref == 0), flags
+        assert np.array_equal(uns.check_batch(q, flags), ref == 0), flags
+    assert 0.05 < ref.mean() < 0.95
+    n = 3000
+    d, g, t, c, loc = eng.collision_gradients(q[:n])
+    rd, rg, rt, rc = env.collision_gradients(q[:n])
+    both_none = (t == 0) & (rt == 0)
+    close = np.isclose(d, rd, rtol=0, atol=1e-9) | both_none
+    assert close.mean() > 0.9999, "%d of %d sphere distances differ" % ((~close).sum(), close.size)
+    same = close & (t == rt)
+    assert same.mean() > 0.9995
+    assert np.allclose(g[same], rg[same], rtol=0, atol=1e-9)
+    assert np.isclose(c, rc, rtol=0, atol=1e-9).mean() > 0.999
+    # spheres inside an obstacle carry negative distances, which the unsigned field cannot express
+    inside = (rt == 3) & (rd < 0)
+    assert inside.sum() > 100 and (d[inside & same] < 0).all()
+    du = uns.collision_gradients(q[:n])[0]
+    assert (du[inside] >= 0).all()
+    eng.close()
+    uns.close()

@@ -66,9 +66,13 @@ def test_bad_inputs_are_errors():
         mb.StateValidityEngine.for_robot("panda", "nope", size=(1, 1, 1), origin=(0, 0, 0.5), resolution=0.02,
                                          max_distance=0.25, device=mb.DEVICE_NONE)
     assert e.value.code == _lib.ERR_INVALID
-    with pytest.raises(mb.B200svError) as e:  # signed fields are a later row
+    # signed fields: the thresholds of the integer predicate exist unless tolerance > radius + resolution
+    eng = mb.StateValidityEngine.for_robot("panda", "panda_arm", size=(1, 1, 1), origin=(0, 0, 0.5), resolution=0.02,
+                                           max_distance=0.25, device=mb.DEVICE_NONE, signed=True)
+    eng.close()
+    with pytest.raises(mb.B200svError) as e:
         mb.StateValidityEngine.for_robot("panda", "panda_arm", size=(1, 1, 1), origin=(0, 0, 0.5), resolution=0.02,
-                                         max_distance=0.25, device=mb.DEVICE_NONE, signed=True)
+                                         max_distance=0.25, tolerance=0.2, device=mb.DEVICE_NONE, signed=True)
     assert e.value.code == _lib.ERR_UNSUPPORTED
 
 

@@ -17,11 +17,12 @@ def read(*p):
         return f.read()
 
 
-def make_pair(robot, group, size, origin, resolution, max_distance, tolerance=0.0, device=0):
+def make_pair(robot, group, size, origin, resolution, max_distance, tolerance=0.0, device=0, signed=False):
     u, s = ROBOT_FILES[robot]
     eng = mb.StateValidityEngine.from_urdf(read(RES, u), read(RES, s), group, size, origin, resolution, max_distance,
-                                           tolerance, device=device)
-    env = OracleEnv(RobotModel(read(RES, u), read(RES, s)), group, size, origin, resolution, max_distance, tolerance)
+                                           tolerance, device=device, signed=signed)
+    env = OracleEnv(RobotModel(read(RES, u), read(RES, s)), group, size, origin, resolution, max_distance, tolerance,
+                    use_signed_distance_field=signed)
     return eng, env
 
 
