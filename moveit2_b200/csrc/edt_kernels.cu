@@ -26,15 +26,34 @@ namespace b200sv
 {
 namespace
 {
-__global__ void scatterKernel(const double* __restrict__ xyz, size_t n, GridDev g, uint32_t* __restrict__ occ, int set)
+__global__ void __launch_bounds__(256) scatterKernel(const double* __restrict__ xyz, size_t n, GridDev g,
+                                                     uint32_t* __restrict__ occ, int set)
 {
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  // A warp takes 32 consecutive points = 96 consecutive doubles: three coalesced 256-byte loads into shared memory, then
+  // every lane picks up its own point (stride 3 doubles: conflict-free).  Reading xyz[3 i + k] straight from global memory
+  // touched every sector three times.
+  __shared__ double sh[8][96];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t n_tiles = (n + 31) / 32;
+  for (size_t t = blockIdx.x * static_cast<size_t>(8) + warp; t < n_tiles; t += static_cast<size_t>(gridDim.x) * 8)
   {
+    const double* src = xyz + 96 * t;
+    const size_t left = 3 * n - 96 * t;
+    const int avail = left < 96 ? static_cast<int>(left) : 96;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (j * 32 + lane < avail)
+        sh[warp][j * 32 + lane] = src[j * 32 + lane];
+    __syncwarp();
+    const bool have = 3 * lane < avail;
+    const double px = sh[warp][3 * lane], py = sh[warp][3 * lane + 1], pz = sh[warp][3 * lane + 2];
+    __syncwarp();
+    if (!have)
+      continue;
     // VoxelGrid::getCellFromLocation (voxel_grid.hpp:522), in double exactly as the reference
-    const int x = static_cast<int>(floor((xyz[3 * i + 0] - g.om[0]) * g.oo));
-    const int y = static_cast<int>(floor((xyz[3 * i + 1] - g.om[1]) * g.oo));
-    const int z = static_cast<int>(floor((xyz[3 * i + 2] - g.om[2]) * g.oo));
+    const int x = static_cast<int>(floor((px - g.om[0]) * g.oo));
+    const int y = static_cast<int>(floor((py - g.om[1]) * g.oo));
+    const int z = static_cast<int>(floor((pz - g.om[2]) * g.oo));
     if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz)
       continue;  // isCellValid (voxel_grid.hpp:405-408)
     uint32_t* w = occ + (static_cast<size_t>(x) * g.ny + y) * g.wz + (z >> 5);
@@ -53,7 +72,7 @@ __global__ void scatterKernel(const double* __restrict__ xyz, size_t n, GridDev 
 // Intermediate values above max_d2 mean "nothing within range"; the x pass treats them so.
 // `invert`: transform of the COMPLEMENT (distance to the nearest free voxel of the grid = negative_distance_square_ of the
 // signed field, propagateNegative :446-504); cells outside the grid are not free.
-__global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
+__global__ void __launch_bounds__(512) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
                                                   int chunk, int n_chunks, unsigned nz8_magic, int invert)
 {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -64,6 +83,35 @@ __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __
   const int wz = g.wz;
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem);
   uint16_t* gz = reinterpret_cast<uint16_t*>(smem + ((static_cast<size_t>(rows) * wz * 4 + 15) & ~static_cast<size_t>(15)));
+  // tables of the z pass (see below), behind the slab: 256 + 2 (R + 2) rows of 8 uint16
+  uint4* lut_within = reinterpret_cast<uint4*>(gz + static_cast<size_t>(chunk + 2 * g.R) * nzp);
+  uint4* lut_below = lut_within + 256;
+  uint4* lut_above = lut_below + (g.R + 2);
+  uint32_t* ends = reinterpret_cast<uint32_t*>(lut_above + (g.R + 2));  // [rows * wz]: see the z pass, step (a)
+  {
+    const int cap = g.R + 1;
+    for (int t = threadIdx.x; t < 256 + 2 * (cap + 1); t += blockDim.x)
+    {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+      {
+        int d;
+        if (t < 256)
+        {  // nearest set bit of pattern t to bit j
+          const uint32_t lo = static_cast<uint32_t>(t) & ((2u << j) - 1u), hi = static_cast<uint32_t>(t) >> j;
+          d = min(lo ? j - 31 + __clz(lo) : cap, hi ? __ffs(hi) - 1 : cap);
+        }
+        else if (t < 256 + cap + 1)
+          d = (t - 256) + j;        // below[dL]
+        else
+          d = (t - 256 - cap - 1) + 7 - j;  // above[dR]
+        d = min(d, cap);
+        v[j] = static_cast<uint32_t>(d * d);
+      }
+      lut_within[t] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+    }
+  }
   {
     const uint32_t* src = occ + (static_cast<size_t>(x) * g.ny + ya) * wz;  // rows are contiguous in the bitmap
     const int lo = max(0, -ya) * wz, hi = min(rows, g.ny - ya) * wz;
@@ -78,72 +126,60 @@ __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __
     }
   }
   __syncthreads();
-  // z pass, one thread per 32-bit occupancy word: the distance of the word's two ends to the nearest set bit outside
-  // it (clz / ffs on the neighbouring words), then one forward and one backward sweep over its 32 bits
+  // z pass, one thread per occupancy BYTE (8 voxels), by table: squaring is monotonic, so the squared distance of a voxel
+  // is the min of three squared candidates, each one 128-bit table row of 8 uint16 --
+  //   within[byte pattern]   nearest set bit inside the byte
+  //   below[dL]              nearest set bit below the byte, dL = its distance from the byte's bit 0 (clz on the bits below)
+  //   above[dR]              nearest set bit above the byte, dR = its distance from the byte's bit 7 (ffs on the bits above)
+  // -- i.e. 3 LDS.128 + 8 VIMNMX.U16x2 + one STS.128 per 8 voxels instead of two 32-step sweeps per word.
+  const int cap = g.R + 1;
+  // (a) per word: distance of its bit 0 / bit 31 to the nearest set bit in the words below / above (capped)
+  for (int i = threadIdx.x; i < rows * wz; i += blockDim.x)
   {
-    const int cap = g.R + 1;
-    int r = threadIdx.x / wz, w = threadIdx.x - r * wz;
-    const int dr_rows = blockDim.x / wz, dw = blockDim.x - dr_rows * wz;
-    for (; r < rows;)
+    const int r = i / wz, w = i - r * wz;
+    const uint32_t* row = bits + r * wz;
+    int dl = cap, dr = cap;
+    for (int ww = w - 1, off = 1; ww >= 0 && off <= g.R; --ww, off += 32)
     {
-      const uint32_t* row = bits + r * wz;
-      const uint32_t cur = row[w];
-      int dl = cap, dr = cap;  // distance of bit 0 / bit 31 to the nearest set bit in the words below / above
-      for (int ww = w - 1, off = 1; ww >= 0 && off <= g.R; --ww, off += 32)
+      const uint32_t v = row[ww];
+      if (v)
       {
-        const uint32_t v = row[ww];
-        if (v)
-        {
-          dl = min(cap, off + __clz(v));
-          break;
-        }
+        dl = min(cap, off + __clz(v));
+        break;
       }
-      for (int ww = w + 1, off = 1; ww < wz && off <= g.R; ++ww, off += 32)
+    }
+    for (int ww = w + 1, off = 1; ww < wz && off <= g.R; ++ww, off += 32)
+    {
+      const uint32_t v = row[ww];
+      if (v)
       {
-        const uint32_t v = row[ww];
-        if (v)
-        {
-          dr = min(cap, off + __ffs(v) - 1);
-          break;
-        }
+        dr = min(cap, off + __ffs(v) - 1);
+        break;
       }
-      uint32_t f[8];
-      int d = dl - 1;
-#pragma unroll
-      for (int b = 0; b < 32; ++b)
-      {
-        d = ((cur >> b) & 1u) ? 0 : min(d + 1, cap);
-        if ((b & 3) == 0)
-          f[b >> 2] = static_cast<uint32_t>(d);
-        else
-          f[b >> 2] |= static_cast<uint32_t>(d) << (8 * (b & 3));
-      }
-      uint32_t o[16];
-      d = dr - 1;
-#pragma unroll
-      for (int b = 31; b >= 0; --b)
-      {
-        d = ((cur >> b) & 1u) ? 0 : min(d + 1, cap);
-        const int mn = min(d, static_cast<int>((f[b >> 2] >> (8 * (b & 3))) & 0xffu));
-        const uint32_t sq = static_cast<uint32_t>(mn * mn);
-        if (b & 1)
-          o[b >> 1] = sq << 16;
-        else
-          o[b >> 1] |= sq;
-      }
-      uint4* dst = reinterpret_cast<uint4*>(gz + r * nzp + w * 32);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (w * 32 + 8 * k < nzp)
-          dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
+    ends[i] = static_cast<uint32_t>(dl) | (static_cast<uint32_t>(dr) << 16);
+  }
+  __syncthreads();
+  // (b) per byte
+  {
+    const int nzb = nzp >> 3;
+    for (int i = threadIdx.x; i < rows * nzb; i += blockDim.x)
+    {
+      const int r = static_cast<int>(__umulhi(static_cast<unsigned>(i), nz8_magic));  // i / nzb
+      const int kb = i - r * nzb;
+      const int w = kb >> 2, o = (kb & 3) * 8;
+      const uint32_t cur = bits[r * wz + w], e = ends[r * wz + w];
+      const uint32_t low = o ? (cur & ((1u << o) - 1u)) : 0u, high = o < 24 ? (cur >> (o + 8)) : 0u;
+      const int dl = low ? o - 31 + __clz(low) : o + static_cast<int>(e & 0xffffu);
+      const int dr = high ? __ffs(high) : 24 - o + static_cast<int>(e >> 16);
+      const uint4 a = lut_within[(cur >> o) & 0xffu], b = lut_below[min(dl, cap)], c = lut_above[min(dr, cap)];
+      uint4 q;
+      q.x = __vminu2(__vminu2(a.x, b.x), c.x);
+      q.y = __vminu2(__vminu2(a.y, b.y), c.y);
+      q.z = __vminu2(__vminu2(a.z, b.z), c.z);
+      q.w = __vminu2(__vminu2(a.w, b.w), c.w);
+      reinterpret_cast<uint4*>(gz + r * nzp)[kb] = q;
       // entries at z >= nz (occupancy bits there are 0) are never read as centres, only as padding
-      r += dr_rows;
-      w += dw;
-      if (w >= wz)
-      {
-        w -= wz;
-        ++r;
-      }
     }
   }
   __syncthreads();
@@ -157,18 +193,22 @@ __global__ void __launch_bounds__(256) edtZYKernel(GridDev g, const uint32_t* __
     const int zc = i - yy * nz8;
     const uint4* ctr = gz4 + (yy + R) * nz8 + zc;  // row yy + R of the haloed block
     uint4 best = *ctr;
-    for (int k = 1; k <= R; ++k)
-    {
-      const uint32_t k2 = static_cast<uint32_t>(k * k);
-      const uint32_t w2 = __vmaxu2(__vmaxu2(best.x, best.y), __vmaxu2(best.z, best.w));
-      if (k2 >= max(w2 & 0xffffu, w2 >> 16))
-        break;  // every further candidate is at least k^2 away
+    auto rowPair = [&](int k) {
+      const uint32_t k2p = static_cast<uint32_t>(k * k) * 0x10001u;
       const uint4 a = ctr[-k * nz8], b = ctr[k * nz8];
-      const uint32_t k2p = k2 | (k2 << 16);
       best.x = __viaddmin_u16x2(__vminu2(a.x, b.x), k2p, best.x);
       best.y = __viaddmin_u16x2(__vminu2(a.y, b.y), k2p, best.y);
       best.z = __viaddmin_u16x2(__vminu2(a.z, b.z), k2p, best.z);
       best.w = __viaddmin_u16x2(__vminu2(a.w, b.w), k2p, best.w);
+    };
+    for (int k = 1; k <= R; k += 2)
+    {  // one termination test per two candidate distances (a candidate too many changes nothing: it is a min)
+      const uint32_t w2 = __vmaxu2(__vmaxu2(best.x, best.y), __vmaxu2(best.z, best.w));
+      if (static_cast<uint32_t>(k * k) >= max(w2 & 0xffffu, w2 >> 16))
+        break;  // every further candidate is at least k^2 away
+      rowPair(k);
+      if (k < R)
+        rowPair(k + 1);
     }
     uint16_t* dst = out + (static_cast<size_t>(x) * g.ny + (y0 + yy)) * g.nz + zc * 8;
     if (vec_out)
@@ -197,19 +237,26 @@ __device__ __forceinline__ bool onShell(const GridDev& g, size_t i)
 // on one stream).
 template <typename FT>
 __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* __restrict__ in, uint16_t* __restrict__ d2,
-                                                    FT* compact)
+                                                    FT* compact, unsigned nz8_magic)
 {
-  const size_t plane8 = static_cast<size_t>(g.ny) * g.nz / 8;
-  const size_t total8 = plane8 * g.nx;
+  // grid: x = tiles of the (y, z/8) plane, y = x planes
+  const int nz8 = g.nz >> 3;
+  const unsigned plane8 = static_cast<unsigned>(g.ny) * nz8;
+  const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= plane8)
+    return;
+  const int y = static_cast<int>(__umulhi(p, nz8_magic));  // p / nz8
+  const int zc = static_cast<int>(p) - y * nz8;
+  const bool shell_y = y == 0 || y == g.ny - 1;
   const int R = g.R, max_d2 = g.max_d2;
   const uint4* in4 = reinterpret_cast<const uint4*>(in);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total8;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  // packed 16-bit lanes throughout; anything above max_d2 means "nothing within range".  The z+y pass writes at most
+  // (R+1)^2 + R^2, so the sums below stay far from 2^16; the centre is capped to max_d2 + 1 so the scan ends at k = R.
+  const uint32_t cap1 = static_cast<uint32_t>(max_d2 + 1) * 0x10001u;
+  const uint32_t capm = static_cast<uint32_t>(max_d2) * 0x10001u;
+  for (int x = blockIdx.y; x < g.nx; x += gridDim.y)
   {
-    const int x = static_cast<int>(i / plane8);
-    // packed 16-bit lanes throughout; anything above max_d2 means "nothing within range".  The z+y pass writes at most
-    // (R+1)^2 + R^2, so the sums below stay far from 2^16; the centre is capped to max_d2 + 1 so the scan ends at k = R.
-    const uint32_t cap1 = static_cast<uint32_t>(max_d2 + 1) * 0x10001u;
+    const size_t i = static_cast<size_t>(x) * plane8 + p;
     const uint4 c = in4[i];
     uint32_t bw[4] = { __vminu2(c.x, cap1), __vminu2(c.y, cap1), __vminu2(c.z, cap1), __vminu2(c.w, cap1) };
     for (int k = 1; k <= R; ++k)
@@ -220,56 +267,51 @@ __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* 
         break;
       uint4 a = make_uint4(cap1, cap1, cap1, cap1), b = a;
       if (x - k >= 0)
-        a = in4[i - k * plane8];
+        a = in4[i - static_cast<size_t>(k) * plane8];
       if (x + k < g.nx)
-        b = in4[i + k * plane8];
+        b = in4[i + static_cast<size_t>(k) * plane8];
       const uint32_t k2p = k2 | (k2 << 16);
       bw[0] = __viaddmin_u16x2(__vminu2(a.x, b.x), k2p, bw[0]);
       bw[1] = __viaddmin_u16x2(__vminu2(a.y, b.y), k2p, bw[1]);
       bw[2] = __viaddmin_u16x2(__vminu2(a.z, b.z), k2p, bw[2]);
       bw[3] = __viaddmin_u16x2(__vminu2(a.w, b.w), k2p, bw[3]);
     }
-    const uint32_t capm = static_cast<uint32_t>(max_d2) * 0x10001u;
-    reinterpret_cast<uint4*>(d2)[i] = make_uint4(__vminu2(bw[0], capm), __vminu2(bw[1], capm), __vminu2(bw[2], capm), __vminu2(bw[3], capm));
-    int best[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      best[j] = static_cast<int>((bw[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+    for (int j = 0; j < 4; ++j)
+      bw[j] = __vminu2(bw[j], capm);
+    reinterpret_cast<uint4*>(d2)[i] = make_uint4(bw[0], bw[1], bw[2], bw[3]);
     if (compact == nullptr)
       continue;  // the negative half of a signed field has no compact copy
-    // our 8 elements of the interleaved compact field: element 2 * (8 i + j) counted from `compact` (already offset).
     // The 1-cell border shell of the COMPACT field is kept at "free": DistanceField::getDistanceGradient
     // (distance_field.cpp:82) answers max_distance for those cells, and the fast check kernel clamps to them.
+    if (shell_y || x == 0 || x == g.nx - 1)
+      bw[0] = bw[1] = bw[2] = bw[3] = capm;
+    else
     {
-      const int nz8 = g.nz / 8;
-      const int rem = static_cast<int>(i - static_cast<size_t>(x) * plane8);
-      const int y = rem / nz8, z0 = (rem - y * nz8) * 8;
-      const bool shell_xy = x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (shell_xy || z0 + j == 0 || z0 + j == g.nz - 1)
-          best[j] = max_d2;
+      if (zc == 0)
+        bw[0] = (bw[0] & 0xffff0000u) | static_cast<uint32_t>(max_d2);
+      if (zc == nz8 - 1)
+        bw[3] = (bw[3] & 0x0000ffffu) | (static_cast<uint32_t>(max_d2) << 16);
     }
+    // our 8 elements of the interleaved {world, self} compact field: element 2 * (8 i + j) counted from `compact`
+    // (already offset by 0 = world / 1 = self); the other field's elements in between are kept (read-modify-write)
     if (sizeof(FT) == 1)
     {
-      const bool second = (reinterpret_cast<uintptr_t>(compact) & 1u) != 0;  // offset by one element: the self half
-      uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(compact) - (second ? 1 : 0)) + i;
-      uint4 v = *p;
-      uint32_t vw[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-      {
-        const uint32_t val = static_cast<uint32_t>(min(min(best[j], max_d2), 255));
-        const int sh = 16 * (j & 1) + (second ? 8 : 0);
-        vw[j >> 1] = (vw[j >> 1] & ~(0xffu << sh)) | (val << sh);
-      }
-      *p = make_uint4(vw[0], vw[1], vw[2], vw[3]);
+      const bool second = (reinterpret_cast<uintptr_t>(compact) & 1u) != 0;
+      const uint32_t sh = second ? 8u : 0u, keep = ~(0x00ff00ffu << sh);
+      uint4* q = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(compact) - (second ? 1 : 0)) + i;
+      uint4 v = *q;  // voxel pair per 32-bit word: bytes { world, self, world, self }
+      v.x = (v.x & keep) | (__vminu2(bw[0], 0x00ff00ffu) << sh);
+      v.y = (v.y & keep) | (__vminu2(bw[1], 0x00ff00ffu) << sh);
+      v.z = (v.z & keep) | (__vminu2(bw[2], 0x00ff00ffu) << sh);
+      v.w = (v.w & keep) | (__vminu2(bw[3], 0x00ff00ffu) << sh);
+      *q = v;
     }
     else
     {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        compact[2 * (8 * i + j)] = static_cast<FT>(min(best[j], max_d2));
+        compact[2 * (8 * i + j)] = static_cast<FT>((bw[j >> 1] >> (16 * (j & 1))) & 0xffffu);
     }
   }
 }
@@ -425,16 +467,17 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
   if (g.R > 180)
     return cudaErrorInvalidConfiguration;  // (R+1)^2 + R^2 must fit 16 bits
   const int nzp = (g.nz + 7) & ~7;
-  const size_t per_row = static_cast<size_t>(g.wz) * 4 + static_cast<size_t>(nzp) * 2;
-  const long max_rows = static_cast<long>((200 * 1024) / per_row);
+  const size_t per_row = static_cast<size_t>(g.wz) * 8 + static_cast<size_t>(nzp) * 2;  // bits, word ends, squared z distances
+  const long max_rows = static_cast<long>((200 * 1024 - (256 + 2 * (g.R + 2)) * 16) / per_row);
   if (max_rows < 2L * g.R + 1)
     return cudaErrorInvalidConfiguration;  // a haloed row block does not fit: grid too deep for this kernel
   static const int chunk_env = getenv("B200SV_EDT_CHUNK") ? atoi(getenv("B200SV_EDT_CHUNK")) : 0;
   int chunk = chunk_env > 0 ? chunk_env : std::min<long>(g.ny, std::max<long>(4L * g.R, 64));
   chunk = static_cast<int>(std::max<long>(1, std::min<long>(std::min<long>(chunk, g.ny), max_rows - 2L * g.R)));
   const int n_chunks = (g.ny + chunk - 1) / chunk;
+  const size_t lut_bytes = (256 + 2 * static_cast<size_t>(g.R + 2)) * 16 + static_cast<size_t>(chunk + 2 * g.R) * g.wz * 4;
   const size_t smem = ((static_cast<size_t>(chunk + 2 * g.R) * g.wz * 4 + 15) & ~static_cast<size_t>(15)) +
-                      static_cast<size_t>(chunk + 2 * g.R) * nzp * 2;
+                      static_cast<size_t>(chunk + 2 * g.R) * nzp * 2 + lut_bytes;
   static size_t granted = 0;
   if (smem > granted)
   {
@@ -445,18 +488,20 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
   }
   const unsigned nz8 = static_cast<unsigned>(nzp / 8);
   const unsigned nz8_magic = static_cast<unsigned>(((1ull << 32) + nz8 - 1) / nz8);  // i / nz8 = umulhi(i, magic), i < 2^16
-  edtZYKernel<<<g.nx * n_chunks, 256, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic, invert ? 1 : 0);
+  static const int zy_threads = getenv("B200SV_EDT_THREADS") ? atoi(getenv("B200SV_EDT_THREADS")) : 512;
+  edtZYKernel<<<g.nx * n_chunks, zy_threads, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic, invert ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
   const size_t total = static_cast<size_t>(g.nx) * g.ny * g.nz;
-  if (g.nz % 8 == 0)
+  const unsigned long long plane8 = static_cast<unsigned long long>(g.ny) * nz8;
+  if (g.nz % 8 == 0 && plane8 * nz8 < (1ull << 32))  // the second condition keeps p / nz8 = umulhi(p, magic) exact
   {
-    const int grid = gridFor(total / 8, 256, sm_count * 16);
+    const dim3 grid(static_cast<unsigned>((plane8 + 255) / 256), static_cast<unsigned>(std::min(g.nx, 65535)));
     if (compact_bytes == 1)
-      edtXKernelVec<uint8_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint8_t*>(compact));
+      edtXKernelVec<uint8_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint8_t*>(compact), nz8_magic);
     else
-      edtXKernelVec<uint16_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint16_t*>(compact));
+      edtXKernelVec<uint16_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint16_t*>(compact), nz8_magic);
     return cudaGetLastError();
   }
   const int grid = gridFor(total, 256, sm_count * 32);
