@@ -129,6 +129,14 @@ def cpu_rate(env, q, seconds=10.0):
     return n / dt, used, n, col
 
 
+def workload_name(name, cfg, n_vars, n_spheres, n_states, n_points, cells):
+    """The same string in both arms: what is checked, not how."""
+    return ("%s: %s %s (%d DoF, %d spheres), %d states per GPU per step, %d-point clutter cloud, %g x %g x %g m field @ %g m "
+            "(%d x %d x %d voxels), checks world+self+intra" %
+            (name, cfg["robot"], cfg["group"], n_vars, n_spheres, n_states, n_points, cfg["size"][0], cfg["size"][1],
+             cfg["size"][2], cfg["resolution"], cells[0], cells[1], cells[2]))
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path, restated (oracle port; the reference cannot be
     compiled in this image), all host threads, each step a bounded sample of the C2 workload."""
@@ -157,9 +165,9 @@ def run_reference(args):
     line = {"metric": METRIC, "value": rate, "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "%s: %s %s, %d states/step (bounded sample of the batch), %d-point clutter cloud, "
-                                   "%g m field edge @ %g m" % (args.workload, cfg["robot"], cfg["group"], sample, len(cloud),
-                                                               cfg["size"][0], cfg["resolution"])},
+            "config": {"workload": workload_name(args.workload, cfg, q.shape[1], env.n_spheres, n_full, len(cloud),
+                                                 env.world.num_cells),
+                       "sample": "each step checks the first %d states of the batch" % sample},
             "cpu_baseline": {"value": rate, "unit": "states/s", "cores": used, "kind": "port",
                              "sample": "%d states per step, lean flavour (centre voxel only), OpenMP" % sample},
             "e2e": {"value": rate, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -296,13 +304,10 @@ def main():
         "metric": METRIC, "value": value, "unit": "states/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64" if args.fp64 else "f32", "data": "synthetic",
-        "config": {"workload": "%s: %s %s (%d DoF, %d spheres), %d states per GPU per step, %d-point clutter cloud, "
-                               "%g x %g x %g m field @ %g m (%d x %d x %d voxels; world+self uint%d d^2 interleaved, %.0f MB), "
-                               "checks world+self+intra" % (args.workload, cfg["robot"], cfg["group"], V, S, n, len(cloud),
-                                                            cfg["size"][0], cfg["size"][1], cfg["size"][2], cfg["resolution"],
-                                                            eng.num_cells[0], eng.num_cells[1], eng.num_cells[2],
-                                                            8 * eng.info.field_bytes_per_voxel,
-                                                            2e-6 * eng.info.field_bytes_per_voxel * eng.num_cells[0] * eng.num_cells[1] * eng.num_cells[2]),
+        "config": {"workload": workload_name(args.workload, cfg, V, S, n, len(cloud), eng.num_cells),
+                   "field_layout": "world+self uint%d d^2 interleaved, %.0f MB" %
+                                   (8 * eng.info.field_bytes_per_voxel,
+                                    2e-6 * eng.info.field_bytes_per_voxel * eng.num_cells[0] * eng.num_cells[1] * eng.num_cells[2]),
                    "l2": "flushed between timed steps (256 MiB write)", "fp32_pass_with_fp64_recheck": not args.fp64,
                    "valid_fraction": valid_frac, "rechecked_states_per_step": st["n_rechecked"],
                    "sharding": "states sharded contiguously (moveit2_b200/sharding.py), fields replicated, one NCCL "
