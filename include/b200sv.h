@@ -184,6 +184,30 @@ int b200sv_field_update_points(b200sv_ctx* ctx, int which, const double* old_xyz
  * (test_distance_field.cpp:957-963).  Boxes, cylinders and meshes go through the caller's bodies::Body (their
  * containsPoint lives in the un-vendored geometric_shapes) and b200sv_field_add_points. */
 int b200sv_field_add_sphere(b200sv_ctx* ctx, int which, const double* center_xyz, double radius);
+/* Spheres, cylinders and boxes decomposed into their interior lattice points ON THE DEVICE, in either of the two ways the
+ * reference does it:
+ *   B200SV_LATTICE_WORLD  DistanceField::addShapeToField / removeShapeFromField (distance_field.cpp:206-238, 316-326): the body
+ *                         is posed, the lattice of findInternalPointsConvex is laid out in the world frame;
+ *   B200SV_LATTICE_BODY   what CollisionEnvDistanceField does with world objects (updateDistanceObject :1730-1779 ->
+ *                         BodyDecomposition::init, types.cpp:292-335, + PosedBodyPointDecomposition::updatePose :388-406): the
+ *                         lattice is laid out around the body at the identity pose, the kept points are moved by `pose`.
+ * type = shapes::ShapeType; dims: sphere { radius }, cylinder { radius, length }, box { x, y, z }; pose = the top three rows of
+ * the Isometry3d, row-major [R | t].  containsPoint follows geometric_shapes' bodies.cpp (scale 1, padding 0), which the
+ * reference does not vendor: for cylinders and boxes parity is unpinned (spheres: test_big.df).  remove != 0 clears the
+ * voxels instead.  The field is rebuilt. */
+#define B200SV_SHAPE_SPHERE 1
+#define B200SV_SHAPE_CYLINDER 2
+#define B200SV_SHAPE_BOX 4
+#define B200SV_LATTICE_WORLD 0
+#define B200SV_LATTICE_BODY 1
+typedef struct b200sv_shape
+{
+  int32_t type;
+  int32_t lattice_frame;
+  double dims[3];
+  double pose[12];
+} b200sv_shape;
+int b200sv_field_add_shape(b200sv_ctx* ctx, int which, const b200sv_shape* shape, int remove);
 /* Same two with xyz already in device memory, asynchronous on `cuda_stream` (a cudaStream_t). */
 int b200sv_field_add_points_device(b200sv_ctx* ctx, int which, const double* d_xyz, size_t n_points,
                                    void* cuda_stream);

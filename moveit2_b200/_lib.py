@@ -35,6 +35,14 @@ class FieldCfg(C.Structure):
                 ("use_signed_distance_field", C.c_int32)]
 
 
+class Shape(C.Structure):
+    _fields_ = [("type", C.c_int32), ("lattice_frame", C.c_int32), ("dims", C.c_double * 3), ("pose", C.c_double * 12)]
+
+
+SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_BOX = 1, 2, 4
+LATTICE_WORLD, LATTICE_BODY = 0, 1
+
+
 class Info(C.Structure):
     _fields_ = [("n_links", C.c_int32), ("n_vars", C.c_int32), ("n_group_vars", C.c_int32),
                 ("n_glinks", C.c_int32), ("n_spheres", C.c_int32), ("n_link_pairs", C.c_int32),
@@ -77,6 +85,7 @@ def load():
         "b200sv_field_add_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_field_remove_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_field_add_sphere": (C.c_int, [vp, C.c_int, dp, C.c_double]),
+        "b200sv_field_add_shape": (C.c_int, [vp, C.c_int, C.POINTER(Shape), C.c_int]),
         "b200sv_field_update_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t, dp, C.c_size_t]),
         "b200sv_field_add_points_device": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp]),
         "b200sv_field_get_d2": (C.c_int, [vp, C.c_int, ip]),

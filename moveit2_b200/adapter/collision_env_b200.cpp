@@ -351,54 +351,99 @@ CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::
   return gc;
 }
 
+namespace
+{
+// Spheres, cylinders and boxes are decomposed on the device (same lattice and containsPoint as BodyDecomposition builds on the
+// host with padding 0); everything else keeps the reference's host path.
+bool devicePrimitive(const shapes::Shape* shape, const Eigen::Isometry3d& pose, b200sv_shape& out)
+{
+  out = b200sv_shape{};
+  out.lattice_frame = B200SV_LATTICE_BODY;
+  switch (shape->type)
+  {
+    case shapes::SPHERE:
+      out.type = B200SV_SHAPE_SPHERE;
+      out.dims[0] = static_cast<const shapes::Sphere*>(shape)->radius;
+      break;
+    case shapes::CYLINDER:
+      out.type = B200SV_SHAPE_CYLINDER;
+      out.dims[0] = static_cast<const shapes::Cylinder*>(shape)->radius;
+      out.dims[1] = static_cast<const shapes::Cylinder*>(shape)->length;
+      break;
+    case shapes::BOX:
+      out.type = B200SV_SHAPE_BOX;
+      for (int k = 0; k < 3; ++k)
+        out.dims[k] = static_cast<const shapes::Box*>(shape)->size[k];
+      break;
+    default:
+      return false;
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 4; ++k)
+      out.pose[4 * r + k] = pose(r, k);
+  return true;
+}
+}  // namespace
+
 void CollisionEnvB200::replayWorld(b200sv_ctx* ctx) const
 {
   EigenSTL::vector_Vector3d all;
   for (const auto& kv : world_points_)
-    all.insert(all.end(), kv.second.begin(), kv.second.end());
+    all.insert(all.end(), kv.second.points.begin(), kv.second.points.end());
   b200sv_field_reset(ctx, B200SV_FIELD_WORLD);
   if (!all.empty())
     b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, all[0].data(), all.size());
+  for (const auto& kv : world_points_)
+    for (const b200sv_shape& sh : kv.second.shapes)
+      b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &sh, 0);
 }
 
 void CollisionEnvB200::notifyObjectChange(const ObjectConstPtr& obj, World::Action action)
 {
-  // updateDistanceObject (:1730-1779): subtract the object's old points, add its new ones
+  // updateDistanceObject (:1730-1779): subtract what the object contributed, add its new decomposition
   std::scoped_lock lock(mutex_);
-  EigenSTL::vector_Vector3d old_points;
+  WorldObjectRecord old_rec;
   auto cur = world_points_.find(obj->id_);
   if (cur != world_points_.end())
-    old_points.swap(cur->second);
-  EigenSTL::vector_Vector3d new_points;
+    std::swap(old_rec, cur->second);
+  WorldObjectRecord new_rec;
   if (action != World::DESTROY && getWorld()->hasObject(obj->id_))
   {
     World::ObjectConstPtr object = getWorld()->getObject(obj->id_);
     for (std::size_t i = 0; i < object->shapes_.size(); ++i)
     {
       const shapes::ShapeConstPtr& shape = object->shapes_[i];
+      b200sv_shape prim;
       if (shape->type == shapes::OCTREE)
       {
         PosedBodyPointDecomposition pts(static_cast<const shapes::OcTree*>(shape.get())->octree);  // types.cpp:355-365
-        new_points.insert(new_points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
+        new_rec.points.insert(new_rec.points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
       }
+      else if (devicePrimitive(shape.get(), getWorld()->getGlobalShapeTransform(obj->id_, i), prim))
+        new_rec.shapes.push_back(prim);
       else
       {
         BodyDecompositionConstPtr bd = std::make_shared<const BodyDecomposition>(shape, resolution_, 0.0);
         PosedBodyPointDecomposition pts(bd, getWorld()->getGlobalShapeTransform(obj->id_, i));
-        new_points.insert(new_points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
+        new_rec.points.insert(new_rec.points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
       }
     }
-    world_points_[obj->id_] = new_points;
+    world_points_[obj->id_] = new_rec;
   }
   else
     world_points_.erase(obj->id_);
   for (auto& kv : contexts_)
   {
     b200sv_ctx* ctx = kv.second->ctx;
-    if (!old_points.empty())  // removePointsFromField, then addPointsToField (:1713-1725)
-      b200sv_field_remove_points(ctx, B200SV_FIELD_WORLD, old_points[0].data(), old_points.size());
-    if (!new_points.empty())
-      b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, new_points[0].data(), new_points.size());
+    // removePointsFromField, then addPointsToField (:1713-1725)
+    if (!old_rec.points.empty())
+      b200sv_field_remove_points(ctx, B200SV_FIELD_WORLD, old_rec.points[0].data(), old_rec.points.size());
+    for (const b200sv_shape& sh : old_rec.shapes)
+      b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &sh, 1);
+    if (!new_rec.points.empty())
+      b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, new_rec.points[0].data(), new_rec.points.size());
+    for (const b200sv_shape& sh : new_rec.shapes)
+      b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &sh, 0);
   }
 }
 

@@ -94,7 +94,14 @@ private:
   std::vector<BodyDecompositionConstPtr> link_body_decomposition_vector_;  // as the reference (:1049-1078)
   std::map<std::string, unsigned int> link_body_decomposition_index_map_;
   // world points currently in the field, per object id (DistanceFieldCacheEntryWorld::posed_body_point_decompositions_)
-  std::map<std::string, EigenSTL::vector_Vector3d> world_points_;
+  // per world object: what it contributed to the world field -- points decomposed on the host (meshes, cones, planes,
+  // octree node centres) and primitives decomposed on the device (b200sv_field_add_shape, B200SV_LATTICE_BODY)
+  struct WorldObjectRecord
+  {
+    EigenSTL::vector_Vector3d points;
+    std::vector<b200sv_shape> shapes;
+  };
+  std::map<std::string, WorldObjectRecord> world_points_;
   mutable std::mutex mutex_;
   mutable std::map<std::string, std::shared_ptr<GroupContext>> contexts_;
   World::ObserverHandle observer_handle_;

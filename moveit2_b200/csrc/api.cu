@@ -1797,6 +1797,91 @@ int b200sv_field_add_sphere(b200sv_ctx* c, int which, const double* center, doub
   return rebuildField(c, which);
 }
 
+int b200sv_field_add_shape(b200sv_ctx* c, int which, const b200sv_shape* sh, int remove)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!sh)
+    return fail(c, B200SV_ERR_INVALID, "null shape");
+  if (sh->lattice_frame != B200SV_LATTICE_WORLD && sh->lattice_frame != B200SV_LATTICE_BODY)
+    return fail(c, B200SV_ERR_INVALID, "lattice_frame must be B200SV_LATTICE_WORLD or B200SV_LATTICE_BODY");
+  // bodies::{Sphere,Cylinder,Box}::updateInternalData with scale 1, padding 0 (what DistanceField::getShapePoints and
+  // BodyDecomposition(shape, resolution, 0.0) use), and computeBoundingSphere: centre = pose translation, radius below
+  BodyDev b{};
+  b.type = sh->type;
+  double radius = 0.0;
+  switch (sh->type)
+  {
+    case B200SV_SHAPE_SPHERE:
+      if (!(sh->dims[0] >= 0.0))
+        return fail(c, B200SV_ERR_INVALID, "negative radius");
+      b.dims[0] = sh->dims[0] * sh->dims[0];
+      radius = sh->dims[0];
+      break;
+    case B200SV_SHAPE_CYLINDER:
+    {
+      if (!(sh->dims[0] >= 0.0) || !(sh->dims[1] >= 0.0))
+        return fail(c, B200SV_ERR_INVALID, "negative cylinder dimension");
+      const double length2 = 1.0 * sh->dims[1] / 2.0;
+      b.dims[0] = sh->dims[0] * sh->dims[0];
+      b.dims[1] = length2;
+      radius = sqrt(length2 * length2 + b.dims[0]);
+      break;
+    }
+    case B200SV_SHAPE_BOX:
+    {
+      for (int k = 0; k < 3; ++k)
+      {
+        if (!(sh->dims[k] >= 0.0))
+          return fail(c, B200SV_ERR_INVALID, "negative box dimension");
+        b.dims[k] = sh->dims[k] * (1.0 / 2.0);
+      }
+      radius = sqrt(b.dims[0] * b.dims[0] + b.dims[1] * b.dims[1] + b.dims[2] * b.dims[2]);
+      break;
+    }
+    default:
+      return fail(c, B200SV_ERR_UNSUPPORTED,
+                  "shape type: spheres, cylinders and boxes are decomposed on the device; cones, planes and meshes go through "
+                  "the caller's bodies::Body and b200sv_field_add_points, octrees through their node centres");
+  }
+  const bool body_frame = sh->lattice_frame == B200SV_LATTICE_BODY;
+  static const double ident[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int k = 0; k < 3; ++k)
+    {
+      b.R[3 * r + k] = body_frame ? ident[3 * r + k] : sh->pose[4 * r + k];
+      b.P[3 * r + k] = sh->pose[4 * r + k];
+    }
+    b.c[r] = body_frame ? 0.0 : sh->pose[4 * r + 3];
+    b.P[9 + r] = sh->pose[4 * r + 3];
+  }
+  b.posed = body_frame ? 1 : 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  // findInternalPointsConvex (find_internal_points.cpp:44-54): start = floor((c - r - res) / res) * res, then `pt += res`
+  // while pt <= c + r + res -- accumulated, not k * res
+  const double res = c->cfg.resolution;
+  std::vector<double> axes;
+  int cnt[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    const double e = b.c[k] + radius + res;
+    int n = 0;
+    for (double v = floor((b.c[k] - radius - res) / res) * res; v <= e; v += res, ++n)
+      axes.push_back(v);
+    cnt[k] = n;
+  }
+  if ((double)cnt[0] * cnt[1] * cnt[2] > 4.0e9)
+    return fail(c, B200SV_ERR_INVALID, "shape spans more than 4e9 lattice points");
+  CU(c, c->d_points.ensure(axes.size() + 1));
+  CU(c, cudaMemcpyAsync(c->d_points.p, axes.data(), axes.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(c, launchBodyLattice(c->d_points.p, cnt[0], cnt[1], cnt[2], b, c->grid, c->fields[which].occ, remove == 0, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));  // `axes` lives on this stack frame
+  return rebuildField(c, which);
+}
+
 int b200sv_field_add_points_device(b200sv_ctx* c, int which, const double* d_xyz, size_t n, void* cuda_stream)
 {
   int rc = checkWhich(c, which);

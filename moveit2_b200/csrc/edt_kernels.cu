@@ -414,6 +414,76 @@ __global__ void sphereShapeKernel(const double* __restrict__ axes, int nxs, int 
   }
 }
 
+// Interior lattice points of a bodies::Body (findInternalPointsConvex, find_internal_points.cpp:39-64) on the device: the axis
+// values come from the host, accumulated `pt += resolution` as the reference's loops do; containsPoint per body type as
+// geometric_shapes' bodies.cpp has it (restated from the published source: un-vendored, parity unpinned) in explicit
+// round-to-nearest double operations, left to right, no FMA (the order the numpy restatement in oracle/ uses):
+//   Sphere    |c - p|^2 <= r^2
+//   Box       |R^T (p - c)| <= half extents, per axis
+//   Cylinder  |(p - c) . nH| <= half length and ((p - c) . nB1)^2 <= r^2 and ((p - c) . nB2)^2 <= r^2 - ((p - c) . nB1)^2
+// A kept point is then moved by `post` (PosedBodyPointDecomposition::updatePose, types.cpp:388-406: the lattice was laid out
+// in the body frame) or left where it is (DistanceField::addShapeToField: the lattice is in the world frame), and its voxel is
+// marked (addPointsToField) or cleared (removePointsFromField).
+__device__ __forceinline__ double dot3rn(double ax, double ay, double az, double bx, double by, double bz)
+{
+  return __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
+}
+
+__global__ void bodyLatticeKernel(const double* __restrict__ axes, int nxs, int nys, int nzs, BodyDev b, GridDev g,
+                                  uint32_t* __restrict__ occ, int set)
+{
+  const size_t total = static_cast<size_t>(nxs) * nys * nzs;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    const int iz = static_cast<int>(i % nzs);
+    const size_t t = i / nzs;
+    const int iy = static_cast<int>(t % nys), ix = static_cast<int>(t / nys);
+    double px = axes[ix], py = axes[nxs + iy], pz = axes[nxs + nys + iz];
+    bool inside;
+    if (b.type == 1)
+    {  // (center_ - p).squaredNorm() <= radius2_
+      const double dx = __dsub_rn(b.c[0], px), dy = __dsub_rn(b.c[1], py), dz = __dsub_rn(b.c[2], pz);
+      inside = dot3rn(dx, dy, dz, dx, dy, dz) <= b.dims[0];
+    }
+    else
+    {
+      const double vx = __dsub_rn(px, b.c[0]), vy = __dsub_rn(py, b.c[1]), vz = __dsub_rn(pz, b.c[2]);
+      // columns of the body's rotation: R[r][k] = b.R[3 * r + k]
+      const double a0 = dot3rn(vx, vy, vz, b.R[0], b.R[3], b.R[6]);
+      const double a1 = dot3rn(vx, vy, vz, b.R[1], b.R[4], b.R[7]);
+      const double a2 = dot3rn(vx, vy, vz, b.R[2], b.R[5], b.R[8]);
+      if (b.type == 4)
+        inside = fabs(a0) <= b.dims[0] && fabs(a1) <= b.dims[1] && fabs(a2) <= b.dims[2];
+      else
+      {  // cylinder: dims = { radius^2, half length }
+        const double remaining = __dsub_rn(b.dims[0], __dmul_rn(a0, a0));
+        inside = !(fabs(a2) > b.dims[1]) && !(remaining < 0.0) && __dmul_rn(a1, a1) <= remaining;
+      }
+    }
+    if (!inside)
+      continue;
+    if (b.posed)
+    {  // trans * p: linear() * p + translation()
+      const double qx = __dadd_rn(dot3rn(b.P[0], b.P[1], b.P[2], px, py, pz), b.P[9]);
+      const double qy = __dadd_rn(dot3rn(b.P[3], b.P[4], b.P[5], px, py, pz), b.P[10]);
+      const double qz = __dadd_rn(dot3rn(b.P[6], b.P[7], b.P[8], px, py, pz), b.P[11]);
+      px = qx;
+      py = qy;
+      pz = qz;
+    }
+    const int x = static_cast<int>(floor((px - g.om[0]) * g.oo)), y = static_cast<int>(floor((py - g.om[1]) * g.oo)),
+              z = static_cast<int>(floor((pz - g.om[2]) * g.oo));
+    if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz)
+      continue;
+    uint32_t* w = occ + (static_cast<size_t>(x) * g.ny + y) * g.wz + (z >> 5);
+    if (set)
+      atomicOr(w, 1u << (z & 31));
+    else
+      atomicAnd(w, ~(1u << (z & 31)));
+  }
+}
+
 // updatePointsInField (propagation_distance_field.cpp:130-175): occ' = (occ - (old \ new)) + (new \ old), word by word
 __global__ void updateOccKernel(uint32_t* __restrict__ occ, const uint32_t* __restrict__ old_bits,
                                 const uint32_t* __restrict__ new_bits, size_t n_words)
@@ -450,6 +520,16 @@ cudaError_t launchSphereShape(const double* d_axes, int nxs, int nys, int nzs, c
   if (total == 0)
     return cudaSuccess;
   sphereShapeKernel<<<gridFor(total, 256, 148 * 16), 256, 0, s>>>(d_axes, nxs, nys, nzs, c[0], c[1], c[2], r2, g, occ);
+  return cudaGetLastError();
+}
+
+cudaError_t launchBodyLattice(const double* d_axes, int nxs, int nys, int nzs, const BodyDev& body, const GridDev& g,
+                              uint32_t* occ, bool set, cudaStream_t s)
+{
+  const size_t total = static_cast<size_t>(nxs) * nys * nzs;
+  if (total == 0)
+    return cudaSuccess;
+  bodyLatticeKernel<<<gridFor(total, 256, 148 * 16), 256, 0, s>>>(d_axes, nxs, nys, nzs, body, g, occ, set ? 1 : 0);
   return cudaGetLastError();
 }
 

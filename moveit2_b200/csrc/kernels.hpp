@@ -150,12 +150,23 @@ struct GridDev
   int max_d2;    // R*R = PropagationDistanceField::max_distance_sq_
 };
 
+// A bodies::Body for bodyLatticeKernel: type = shapes::ShapeType (1 sphere, 2 cylinder, 4 box); c, R (row-major) = the pose
+// the lattice is tested against; dims = { r^2 } / { r^2, half length } / { half extents }; posed: kept points are moved by
+// P = [R row-major (9) | t (3)] before their voxel is looked up.
+struct BodyDev
+{
+  int type, posed;
+  double c[3], R[9], dims[3], P[12];
+};
+
 // occupancy bitmap: word ((x*ny + y)*wz + z/32), bit z%32
 cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint32_t* occ, bool set, cudaStream_t s);
 // addShapeToField for a sphere: lattice axes (host-accumulated) x containsPoint -> occupancy bits
 cudaError_t launchSphereShape(const double* d_axes, int nxs, int nys, int nzs, const double* c, double r2, const GridDev& g,
                               uint32_t* occ, cudaStream_t s);
 // occ' = (occ - (old \\ new)) + (new \\ old): updatePointsInField on bitmaps of the same layout
+cudaError_t launchBodyLattice(const double* d_axes, int nxs, int nys, int nzs, const BodyDev& body, const GridDev& g,
+                              uint32_t* occ, bool set, cudaStream_t s);
 cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint32_t* new_bits, size_t n_words, cudaStream_t s);
 // exact truncated EDT of the occupancy bitmap -> d2 (uint16, min(d^2, max_d2)) and this field's half of the
 // INTERLEAVED compact field (element 2 * voxel; `compact` arrives offset by 0 = world / 1 = self; uint8:

@@ -215,6 +215,20 @@ class StateValidityEngine:
         c = np.ascontiguousarray(center, np.float64).reshape(3)
         self._check(self.L.b200sv_field_add_sphere(self.h, which, _dp(c), float(radius)))
 
+    def field_add_shape(self, shape_type, dims, pose, which=FIELD_WORLD, lattice_frame=_lib.LATTICE_WORLD, remove=False):
+        """Sphere / cylinder / box decomposed on the device.  pose: 4x4 (or 3x4) homogeneous matrix.  lattice_frame:
+        LATTICE_WORLD = DistanceField::addShapeToField, LATTICE_BODY = BodyDecomposition + PosedBodyPointDecomposition."""
+        sh = _lib.Shape()
+        sh.type, sh.lattice_frame = int(shape_type), int(lattice_frame)
+        d = list(np.asarray(dims, np.float64).reshape(-1)) + [0.0, 0.0, 0.0]
+        for k in range(3):
+            sh.dims[k] = float(d[k])
+        m = np.asarray(pose, np.float64)
+        for r in range(3):
+            for k in range(4):
+                sh.pose[4 * r + k] = float(m[r, k])
+        self._check(self.L.b200sv_field_add_shape(self.h, which, C.byref(sh), int(bool(remove))))
+
     def field_update_points(self, old_points, new_points, which=FIELD_WORLD):
         """PropagationDistanceField::updatePointsInField."""
         a = np.ascontiguousarray(old_points, np.float64).reshape(-1, 3)

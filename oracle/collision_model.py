@@ -71,6 +71,58 @@ def find_internal_points_sphere(center, radius, resolution):
     return np.stack([X[inside], Y[inside], Z[inside]], axis=1)
 
 
+def find_internal_points_body(shape_type, dims, pose, resolution, lattice_frame="world"):
+    """findInternalPointsConvex (find_internal_points.cpp:39-64) for a posed bodies::Sphere / Cylinder / Box, restated from
+    geometric_shapes' published bodies.cpp (scale 1, padding 0; un-vendored in the reference: parity unpinned for cylinders
+    and boxes, spheres are pinned by test_big.df).  shape_type = shapes::ShapeType (1 sphere, 2 cylinder, 4 box).
+    lattice_frame "world": DistanceField::addShapeToField (distance_field.cpp:206-238) -- body posed, lattice in the world.
+    lattice_frame "body": BodyDecomposition::init at the identity pose (types.cpp:292-335), then
+    PosedBodyPointDecomposition::updatePose (:388-406) moves the kept points by `pose`."""
+    pose = np.asarray(pose, np.float64)
+    R, t = pose[:3, :3], pose[:3, 3]
+    res = float(resolution)
+    d = [float(v) for v in np.asarray(dims, np.float64).reshape(-1)]
+    if shape_type == 1:
+        radius = d[0]
+    elif shape_type == 2:
+        radius2, length2 = d[0] * d[0], 1.0 * d[1] / 2.0
+        radius = math.sqrt(length2 * length2 + radius2)
+    elif shape_type == 4:
+        h = [d[0] * (1.0 / 2.0), d[1] * (1.0 / 2.0), d[2] * (1.0 / 2.0)]
+        radius = math.sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2])
+    else:
+        raise ValueError("sphere, cylinder or box")
+    body = lattice_frame == "body"
+    c = np.zeros(3) if body else t
+    Rb = np.eye(3) if body else R
+
+    def axis(ck):
+        v = math.floor((ck - radius - res) / res) * res
+        e = ck + radius + res
+        out = []
+        while v <= e:
+            out.append(v)
+            v += res
+        return np.array(out)
+
+    X, Y, Z = np.meshgrid(axis(c[0]), axis(c[1]), axis(c[2]), indexing="ij")
+    if shape_type == 1:
+        dx, dy, dz = c[0] - X, c[1] - Y, c[2] - Z
+        inside = (dx * dx + dy * dy + dz * dz) <= d[0] * d[0]
+    else:
+        vx, vy, vz = X - c[0], Y - c[1], Z - c[2]
+        a = [vx * Rb[0, k] + vy * Rb[1, k] + vz * Rb[2, k] for k in range(3)]  # v . column k
+        if shape_type == 4:
+            inside = (np.abs(a[0]) <= h[0]) & (np.abs(a[1]) <= h[1]) & (np.abs(a[2]) <= h[2])
+        else:
+            remaining = radius2 - a[0] * a[0]
+            inside = ~(np.abs(a[2]) > length2) & ~(remaining < 0.0) & (a[1] * a[1] <= remaining)
+    P = np.stack([X[inside], Y[inside], Z[inside]], axis=1)
+    if body:
+        P = np.stack([(R[r, 0] * P[:, 0] + R[r, 1] * P[:, 1] + R[r, 2] * P[:, 2]) + t[r] for r in range(3)], axis=1)
+    return P
+
+
 def merge_bounding_spheres(spheres):
     """geometric_shapes bodies::mergeBoundingSpheres, restated from the published source (parity unpinned)."""
     if not spheres:

@@ -808,3 +808,49 @@ def test_signed_field_validity_and_gradients_equal_oracle():
     assert (du[inside] >= 0).all()
     eng.close()
     uns.close()
+
+
+# ---- world ingest: spheres, cylinders and boxes decomposed on the device ---------------------------------------------------
+def _pose(rpy, xyz):
+    cr, sr, cp, sp, cy, sy = np.cos(rpy[0]), np.sin(rpy[0]), np.cos(rpy[1]), np.sin(rpy[1]), np.cos(rpy[2]), np.sin(rpy[2])
+    R = np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                  [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                  [-sp, cp * sr, cp * cr]])
+    T = np.eye(4)
+    T[:3, :3], T[:3, 3] = R, xyz
+    return T
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("frame", ["world", "body"])
+def test_field_add_shape_equals_the_restated_body_decomposition(frame):
+    from oracle.collision_model import find_internal_points_body
+    cfg = workloads.CONFIGS["C1"]
+    eng, env = make_pair(cfg["robot"], cfg["group"], cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    lf = mb.LATTICE_WORLD if frame == "world" else mb.LATTICE_BODY
+    shapes = [(mb.SHAPE_BOX, (0.21, 0.13, 0.37), _pose((0.3, -0.7, 1.1), (0.31, 0.12, 0.48))),
+              (mb.SHAPE_CYLINDER, (0.09, 0.43), _pose((1.2, 0.4, -0.5), (-0.2, 0.25, 0.6))),
+              (mb.SHAPE_SPHERE, (0.11,), _pose((0, 0, 0), (0.05, -0.33, 0.3))),
+              (mb.SHAPE_BOX, (0.3, 0.3, 0.06), _pose((0, 0, 0.4), (0.1, 0.1, 0.97)))]   # sticks out of the field: clipped
+    total = 0
+    for ty, dims, T in shapes:
+        pts = find_internal_points_body(ty, dims, T, cfg["resolution"], frame)
+        assert len(pts) > 200
+        total += len(pts)
+        env.world.add_points(pts)
+        eng.field_add_shape(ty, dims, T, lattice_frame=lf)
+        assert np.array_equal(eng.field_get_d2() == 0, env.world.d2() == 0), (ty, frame)
+    g, o = eng.field_get_d2(), env.world.d2()
+    assert (g <= o).all() and (g == 0).sum() > 0.5 * total / (1 if frame == "world" else 2)
+    # removeShapeFromField: clears exactly the voxels of the body's points
+    ty, dims, T = shapes[0]
+    env.world.remove_points(find_internal_points_body(ty, dims, T, cfg["resolution"], frame))
+    eng.field_add_shape(ty, dims, T, lattice_frame=lf, remove=True)
+    assert np.array_equal(eng.field_get_d2() == 0, env.world.d2() == 0)
+    # the sphere in the world frame is the construction the reference's test_big.df pins
+    if frame == "world":
+        ref = find_internal_points_sphere((0.05, -0.33, 0.3), 0.11, cfg["resolution"])
+        assert np.array_equal(ref, find_internal_points_body(1, (0.11,), shapes[2][2], cfg["resolution"], "world"))
+    with pytest.raises(mb.B200svError):
+        eng.field_add_shape(3, (0.1, 0.2), np.eye(4))  # cone: host side
+    eng.close()
