@@ -91,6 +91,7 @@ struct b200sv_ctx
   double* d_const_T = nullptr;
   Field fields[2];
   uint16_t* d_tmp = nullptr;  // EDT intermediate
+  double* d_sqrt_table = nullptr;  // sqrt_table_ of the reference's field (gradient kernel)
   void* d_combined = nullptr; // interleaved compact field {world, self} per voxel
   // launch config
   int sm_count = 148, smem_optin = 0;
@@ -1523,6 +1524,7 @@ void b200sv_destroy(b200sv_ctx* c)
   }
   if (c->d_combined) cudaFree(c->d_combined);
   if (c->d_tmp) cudaFree(c->d_tmp);
+  if (c->d_sqrt_table) cudaFree(c->d_sqrt_table);
   if (c->d_blob_f) cudaFree(c->d_blob_f);
   if (c->d_blob_d) cudaFree(c->d_blob_d);
   if (c->d_blob_fast) cudaFree(c->d_blob_fast);
@@ -2318,6 +2320,16 @@ int b200sv_collision_gradients(b200sv_ctx* c, const double* q, size_t n, double*
   a.nd2_self = c->fields[1].nd2;
   a.self_enabled = c->d_g_self.p;
   a.n_glinks = (int)L;
+  a.n_spheres = (int)S;
+  if (!c->d_sqrt_table)
+  {  // PropagationDistanceField::initialize (propagation_distance_field.cpp:99-101)
+    std::vector<double> table((size_t)c->grid.max_d2 + 1);
+    for (int k = 0; k <= c->grid.max_d2; ++k)
+      table[k] = sqrt(double(k)) * c->cfg.resolution;
+    CU(c, cudaMalloc(&c->d_sqrt_table, table.size() * sizeof(double)));
+    CU(c, cudaMemcpy(c->d_sqrt_table, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  a.sqrt_table = c->d_sqrt_table;
   a.resolution = c->cfg.resolution;
   // DistanceField::inv_twice_resolution_ is declared int (distance_field.hpp:614): 1 / (2 res) truncated
   a.inv_twice_resolution = (double)(int)(1.0 / (2.0 * c->cfg.resolution));

@@ -773,13 +773,14 @@ __global__ void gatherKernel(const uint8_t* __restrict__ field, unsigned long lo
 // subtract_radii = false; DistanceField::getDistanceGradient: distance_field.cpp:73-97 (1-cell margin, central
 // differences times inv_twice_resolution_); PropagationDistanceField::getDistance = sqrt(d2) * resolution.
 // One thread per state; sphere centres live in shared memory ([sphere][xyz] per thread, 24 B each).
-__device__ __forceinline__ double cellDistance(const uint16_t* __restrict__ d2, const uint16_t* __restrict__ nd2, size_t idx,
-                                               double res)
+__device__ __forceinline__ double cellDistance(const GradArgs& a, const uint16_t* __restrict__ d2,
+                                               const uint16_t* __restrict__ nd2, size_t idx)
 {
-  // getDistance (propagation_distance_field.hpp:604-607): sqrt_table_[d2] - sqrt_table_[negative d2], with
-  // sqrt_table_[i] = sqrt(i) * resolution (propagation_distance_field.cpp:99-101); the negative part is 0 in unsigned fields
-  const double pos = sqrt(static_cast<double>(__ldg(d2 + idx))) * res;
-  return nd2 ? __dsub_rn(pos, sqrt(static_cast<double>(__ldg(nd2 + idx))) * res) : pos;
+  // getDistance (propagation_distance_field.hpp:604-607): sqrt_table_[d2] - sqrt_table_[negative d2], the table being
+  // sqrt(double(i)) * resolution (propagation_distance_field.cpp:99-101), built on the host with the same expression; the
+  // negative part is 0 in unsigned fields
+  const double pos = __ldg(a.sqrt_table + __ldg(d2 + idx));
+  return nd2 ? __dsub_rn(pos, __ldg(a.sqrt_table + __ldg(nd2 + idx))) : pos;
 }
 
 __device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t* __restrict__ d2,
@@ -798,10 +799,10 @@ __device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t
     {
       const size_t sy = static_cast<size_t>(h.nz), sx = sy * h.ny;
       const size_t i0 = (static_cast<size_t>(gx) * h.ny + gy) * h.nz + gz;
-      g0 = (cellDistance(d2, nd2, i0 + sx, a.resolution) - cellDistance(d2, nd2, i0 - sx, a.resolution)) * a.inv_twice_resolution;
-      g1 = (cellDistance(d2, nd2, i0 + sy, a.resolution) - cellDistance(d2, nd2, i0 - sy, a.resolution)) * a.inv_twice_resolution;
-      g2 = (cellDistance(d2, nd2, i0 + 1, a.resolution) - cellDistance(d2, nd2, i0 - 1, a.resolution)) * a.inv_twice_resolution;
-      dist = cellDistance(d2, nd2, i0, a.resolution);
+      g0 = (cellDistance(a, d2, nd2, i0 + sx) - cellDistance(a, d2, nd2, i0 - sx)) * a.inv_twice_resolution;
+      g1 = (cellDistance(a, d2, nd2, i0 + sy) - cellDistance(a, d2, nd2, i0 - sy)) * a.inv_twice_resolution;
+      g2 = (cellDistance(a, d2, nd2, i0 + 1) - cellDistance(a, d2, nd2, i0 - 1)) * a.inv_twice_resolution;
+      dist = cellDistance(a, d2, nd2, i0);
     }
     if (dist < a.max_propagation)
     {
@@ -819,6 +820,13 @@ __device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t
   }
 }
 
+// kLocal: the per-state working arrays (distances, gradients, types, centres, closest) live in LOCAL memory -- which the
+// hardware interleaves by lane, so the warp's accesses are coalesced and L1/L2 resident -- and are copied to the caller's
+// state-major arrays once at the end.  Working on the state-major arrays directly (a warp's 32 rows are S * 8 bytes apart)
+// cost a 32-byte sector per 8-byte access in the pair loops.
+constexpr int kGradMaxSpheres = 96, kGradMaxLinks = 64;
+
+template <bool kLocal>
 __global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -829,10 +837,14 @@ __global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
   if (i >= a.n_states)
     return;
   const int S = h.n_spheres;
-  double* D = a.distances + i * S;
-  double* G = a.gradients + i * S * 3;
-  uint8_t* Ty = a.types + i * S;
-  double* cen = a.centers + i * S * 3;  // scratch: posed sphere centres
+  double Dl[kLocal ? kGradMaxSpheres : 1], Gl[kLocal ? 3 * kGradMaxSpheres : 1], Cl[kLocal ? 3 * kGradMaxSpheres : 1],
+      Ll[kLocal ? kGradMaxLinks : 1];
+  uint8_t Tl[kLocal ? kGradMaxSpheres : 1];
+  double* D = kLocal ? Dl : a.distances + i * S;
+  double* G = kLocal ? Gl : a.gradients + i * S * 3;
+  uint8_t* Ty = kLocal ? Tl : a.types + i * S;
+  double* cen = kLocal ? Cl : a.centers + i * S * 3;  // posed sphere centres (GradientInfo::sphere_locations)
+  double* closest = kLocal ? Ll : a.closest + i * a.n_glinks;
   fkState<double>(m, a.q + i * h.n_group_vars, T);
   for (int k = 0; k < S; ++k)
   {
@@ -844,12 +856,12 @@ __global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
   }
   // closest_distance per dfce link; links are runs of clusters with the same glink id (BsRec::pad)
   for (int g = 0; g < a.n_glinks; ++g)
-    a.closest[i * a.n_glinks + g] = 1.7976931348623157e308;
+    closest[g] = 1.7976931348623157e308;
   for (int c = 0; c < h.n_bs; ++c)
   {  // self field
     const BsRec<double>& C = m.bs[c];
     if (a.self_enabled[C.pad])
-      fieldGradients(a, a.d2_self, a.nd2_self, m, C, cen, 1, D, G, Ty, a.closest[i * a.n_glinks + C.pad]);
+      fieldGradients(a, a.d2_self, a.nd2_self, m, C, cen, 1, D, G, Ty, closest[C.pad]);
   }
   for (int p = 0; p < h.n_pairs; ++p)
   {  // intra-group: every sphere pair of the two clusters (all cluster pairs of a link pair = all its sphere pairs)
@@ -858,7 +870,11 @@ __global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
       for (int l = B.s0; l < B.s1; ++l)
       {
         const double gx = cen[3 * k] - cen[3 * l], gy = cen[3 * k + 1] - cen[3 * l + 1], gz = cen[3 * k + 2] - cen[3 * l + 2];
-        const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz)));
+        const double dd = __dadd_rn(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)), __dmul_rn(gz, gz));
+        const double far = fmax(D[k], D[l]);
+        if (dd > far * far * (1.0 + 1e-9))
+          continue;  // sqrt(dd) exceeds both recorded distances: neither update can happen (DBL_MAX squares to +inf)
+        const double dist = sqrt(dd);
         if (dist < D[k])
         {
           D[k] = dist;
@@ -874,7 +890,22 @@ __global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
       }
   }
   for (int c = 0; c < h.n_bs; ++c)  // world field
-    fieldGradients(a, a.d2_world, a.nd2_world, m, m.bs[c], cen, 3, D, G, Ty, a.closest[i * a.n_glinks + m.bs[c].pad]);
+    fieldGradients(a, a.d2_world, a.nd2_world, m, m.bs[c], cen, 3, D, G, Ty, closest[m.bs[c].pad]);
+  if (kLocal)
+  {
+    for (int k = 0; k < S; ++k)
+    {
+      a.distances[i * S + k] = D[k];
+      a.types[i * S + k] = Ty[k];
+    }
+    for (int k = 0; k < 3 * S; ++k)
+    {
+      a.gradients[i * S * 3 + k] = G[k];
+      a.centers[i * S * 3 + k] = cen[k];
+    }
+    for (int g = 0; g < a.n_glinks; ++g)
+      a.closest[i * a.n_glinks + g] = closest[g];
+  }
 }
 
 // CollisionEnvDistanceField::checkCollision with req.contacts = true (collision_env_distance_field.cpp:1389-1411), n states:
@@ -1167,11 +1198,21 @@ cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_
 
 cudaError_t launchGradients(const GradArgs& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-  static SmemGrant g;
-  cudaError_t e = ensureSmem(gradientKernel, smem_bytes, g);
-  if (e != cudaSuccess)
-    return e;
-  gradientKernel<<<grid, block, smem_bytes, stream>>>(a);
+  static SmemGrant gl, gg;
+  if (a.n_spheres <= kGradMaxSpheres && a.n_glinks <= kGradMaxLinks)
+  {
+    cudaError_t e = ensureSmem(gradientKernel<true>, smem_bytes, gl);
+    if (e != cudaSuccess)
+      return e;
+    gradientKernel<true><<<grid, block, smem_bytes, stream>>>(a);
+  }
+  else
+  {
+    cudaError_t e = ensureSmem(gradientKernel<false>, smem_bytes, gg);
+    if (e != cudaSuccess)
+      return e;
+    gradientKernel<false><<<grid, block, smem_bytes, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 

@@ -558,13 +558,16 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
   const size_t lut_bytes = (256 + 2 * static_cast<size_t>(g.R + 2)) * 16 + static_cast<size_t>(chunk + 2 * g.R) * g.wz * 4;
   const size_t smem = ((static_cast<size_t>(chunk + 2 * g.R) * g.wz * 4 + 15) & ~static_cast<size_t>(15)) +
                       static_cast<size_t>(chunk + 2 * g.R) * nzp * 2 + lut_bytes;
-  static size_t granted = 0;
-  if (smem > granted)
+  static size_t granted[16] = { 0 };  // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (smem > granted[dev])
   {
     cudaError_t e = cudaFuncSetAttribute(edtZYKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess)
       return e;
-    granted = smem;
+    granted[dev] = smem;
   }
   const unsigned nz8 = static_cast<unsigned>(nzp / 8);
   const unsigned nz8_magic = static_cast<unsigned>(((1ull << 32) + nz8 - 1) / nz8);  // i / nz8 = umulhi(i, magic), i < 2^16
