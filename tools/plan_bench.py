@@ -37,6 +37,34 @@ class OracleMotionValidator:
         return valid, np.where(valid, 1.0, (np.maximum(first, 1) - 1) / nd)
 
 
+def box_clutter(rng, n_boxes, home_centres, home_radii):
+    """The reference's own speed-test recipe (compare_collision_speed_checking_fcl_bullet.cpp:83-160): boxes with edges
+    U(0.05, 0.2) m at x, y in U(-1, 1), z in U(0, 1), random orientation, rejected if they touch the robot at its home pose
+    (here: any home-pose collision sphere within 3 cm of the box)."""
+    boxes = []
+    while len(boxes) < n_boxes:
+        dims = rng.uniform(0.05, 0.2, 3)
+        xyz = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(0, 1)])
+        qv = rng.normal(size=4)
+        w, x, y, z = qv / np.linalg.norm(qv)
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        local = (home_centres - xyz) @ R  # centres in the box frame
+        gap = np.linalg.norm(local - np.clip(local, -dims / 2, dims / 2), axis=1) - home_radii
+        if gap.min() < 0.03:
+            continue
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R, xyz
+        boxes.append((dims, T))
+    return boxes
+
+
+def eng_resolution(eng):
+    from moveit2_b200 import workloads
+    return workloads.CONFIGS["C2"]["resolution"]
+
+
 def summarise(times, ok):
     t = np.asarray(times)
     return {"queries": len(t), "solved": int(np.sum(ok)), "median_ms": float(np.median(t) * 1e3),
@@ -49,6 +77,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--reference-queries", type=int, default=10)
     ap.add_argument("--fraction", type=float, default=0.01, help="longest_valid_segment_fraction (OMPL default 0.01)")
+    ap.add_argument("--scene", default="cloud", choices=["cloud", "boxes"],
+                    help="cloud: the C2 clutter cloud; boxes: the reference's speed-test recipe, ingested as shapes")
+    ap.add_argument("--boxes", type=int, default=100)
     args = ap.parse_args()
     os.environ.setdefault("ORACLE_MARCH", "native")
     import oracle
@@ -58,8 +89,20 @@ def main():
     from moveit2_b200.planning import rrt_connect
     from util import config_pair
     eng, env, cloud, _ = config_pair("C2", n_states=1)
-    eng.field_add_points(cloud)
-    env.world.add_points(cloud)
+    if args.scene == "cloud":
+        eng.field_add_points(cloud)
+        env.world.add_points(cloud)
+        scene = "C2 scene (500k-point clutter cloud"
+    else:
+        from oracle.collision_model import find_internal_points_body
+        home = np.array([0.0, -0.785, 0.0, -2.356, 0.0, 1.571, 0.785])  # panda "ready" pose
+        radii = env.arr["sphere_radius"][:env.n_spheres]
+        for dims, T in box_clutter(np.random.default_rng(51), args.boxes, env.sphere_centers(home).reshape(-1, 3), radii):
+            # the way CollisionEnvDistanceField ingests world objects: body-frame lattice, then the pose
+            eng.field_add_shape(mb.SHAPE_BOX, dims, T, lattice_frame=mb.LATTICE_BODY)
+            env.world.add_points(find_internal_points_body(4, dims, T, eng_resolution(eng), "body"))
+        assert np.array_equal(eng.field_get_d2() == 0, env.world.d2() == 0), "device and restated box decomposition differ"
+        scene = "%d random boxes (reference speed-test recipe, decomposed on the device" % args.boxes
     # both arms decide on identical fields: the reference's own propagation result
     eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
     eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
@@ -67,11 +110,11 @@ def main():
     space = ModelBasedStateSpace(lo, hi, longest_valid_segment_fraction=args.fraction)
     svc = StateValidityChecker(eng, space)
     rng = np.random.default_rng(50)
-    cand = space.sampleUniform(rng, 4 * args.queries + 64)
+    cand = space.sampleUniform(rng, 16 * args.queries + 64)
     cand = cand[svc.isValidBatch(cand)]
     queries = [(cand[2 * i], cand[2 * i + 1]) for i in range(args.queries)]
-    out = {"workload": "C5: Panda panda_arm, C2 scene (500k-point clutter cloud, 2 m^3 field @ 1 cm), RRTConnect, "
-                       "batch %d edges per validator call, longest_valid_segment_fraction %g" % (args.batch, args.fraction)}
+    out = {"workload": "C5: Panda panda_arm, %s, 2 m^3 field @ 1 cm), RRTConnect, "
+                       "batch %d edges per validator call, longest_valid_segment_fraction %g" % (scene, args.batch, args.fraction)}
     for name, validator, nq in (("b200", MotionValidator(eng, space), args.queries),
                                 ("reference_cpu_port", OracleMotionValidator(env, space), args.reference_queries)):
         times, ok, paths = [], [], []
