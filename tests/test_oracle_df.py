@@ -262,3 +262,36 @@ def test_signed_field_vs_exact_complement_transform_on_solid_bodies():
     assert (n >= exact).all() and np.array_equal(n > 0, occ)
     assert (n != exact).sum() <= 0.05 * occ.sum()
     assert n.max() == exact.max() == 36
+
+
+# ---- bodies decomposed into interior lattice points (findInternalPointsConvex over geometric_shapes bodies) --------------------
+def test_find_internal_points_body_restatement():
+    from oracle.collision_model import find_internal_points_body
+    T = np.eye(4)
+    T[:3, 3] = (0.5, 0.5, 0.5)
+    # a posed sphere in the world frame IS the construction test_big.df pins
+    assert np.array_equal(find_internal_points_body(1, (0.5,), T, 0.02, "world"),
+                          find_internal_points_sphere((0.5, 0.5, 0.5), 0.5, 0.02))
+    # axis-aligned box: the lattice points inside are the lattice values within the half extents, per axis
+    res = 0.05
+    pts = find_internal_points_body(4, (0.4, 0.2, 0.3), T, res, "world")
+    for k, half in enumerate((0.2, 0.1, 0.15)):
+        assert np.all(np.abs(pts[:, k] - 0.5) <= half)
+    assert abs(len(pts) * res ** 3 / (0.4 * 0.2 * 0.3) - 1.0) < 0.5
+    # body-frame lattice + pose == world-frame lattice for a pure lattice-aligned translation (identity rotation, t = k * res)
+    T2 = np.eye(4)
+    T2[:3, 3] = (0.25, 0.5, 0.75)
+    # (extents off the lattice: a point exactly on a face is decided by the rounding of the accumulated lattice values)
+    a = find_internal_points_body(4, (0.43, 0.21, 0.33), T2, res, "world")
+    b = find_internal_points_body(4, (0.43, 0.21, 0.33), T2, res, "body")
+    assert len(a) == len(b) and np.allclose(np.sort(a, axis=0), np.sort(b, axis=0), atol=1e-12)
+    # cylinder along z: radial and axial limits
+    c = find_internal_points_body(2, (0.1, 0.5), T, 0.02, "world")
+    assert np.all(np.abs(c[:, 2] - 0.5) <= 0.25) and np.all((c[:, 0] - 0.5) ** 2 + (c[:, 1] - 0.5) ** 2 <= 0.01 + 1e-15)
+    assert abs(len(c) * 0.02 ** 3 / (np.pi * 0.01 * 0.5) - 1.0) < 0.15
+    # rotating the cylinder by 90 degrees about x swaps the roles of y and z
+    Rx = np.eye(4)
+    Rx[:3, :3] = [[1, 0, 0], [0, 0, -1], [0, 1, 0]]
+    Rx[:3, 3] = (0.5, 0.5, 0.5)
+    cr = find_internal_points_body(2, (0.1, 0.5), Rx, 0.02, "world")
+    assert np.all(np.abs(cr[:, 1] - 0.5) <= 0.25 + 1e-12) and np.abs(cr[:, 2] - 0.5).max() <= 0.1 + 1e-12
