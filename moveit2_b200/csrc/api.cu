@@ -92,6 +92,8 @@ struct b200sv_ctx
   Field fields[2];
   uint16_t* d_tmp = nullptr;  // EDT intermediate
   double* d_sqrt_table = nullptr;  // sqrt_table_ of the reference's field (gradient kernel)
+  uint8_t* h_small = nullptr;      // pinned staging of the small-batch (latency) path of b200sv_check_batch
+  size_t h_small_bytes = 0;
   void* d_combined = nullptr; // interleaved compact field {world, self} per voxel
   // launch config
   int sm_count = 148, smem_optin = 0;
@@ -1525,6 +1527,7 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->d_combined) cudaFree(c->d_combined);
   if (c->d_tmp) cudaFree(c->d_tmp);
   if (c->d_sqrt_table) cudaFree(c->d_sqrt_table);
+  if (c->h_small) cudaFreeHost(c->h_small);
   if (c->d_blob_f) cudaFree(c->d_blob_f);
   if (c->d_blob_d) cudaFree(c->d_blob_d);
   if (c->d_blob_fast) cudaFree(c->d_blob_fast);
@@ -2173,16 +2176,55 @@ int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags,
   if (n >= (1ull << 32))
     return fail(c, B200SV_ERR_INVALID, "more than 2^32 - 1 states in one call");
   CU(c, c->d_list.ensure(n));
-  CU(c, cudaEventRecord(c->ev0, c->stream));
-  int rc = c->compact_bytes == 1 ? runCheckHost<uint8_t>(c, q, n, flags) : runCheckHost<uint16_t>(c, q, n, flags);
-  if (rc != B200SV_OK)
-    return rc;
-  CU(c, cudaEventRecord(c->ev1, c->stream));
-  // bitmap back: whole bytes of the caller's buffer; the device words are little-endian, bit i%8 of byte i/8
-  CU(c, cudaMemcpyAsync(valid_bitmap, c->d_bitmap.p, (n + 7) / 8, cudaMemcpyDeviceToHost, c->stream));
   unsigned cnt = 0;
-  CU(c, cudaMemcpyAsync(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  constexpr size_t kSmallBatch = 4096;
+  if (n <= kSmallBatch)
+  {
+    // Latency path (a single-state checkCollision through the plugin is a batch of 1): everything on one stream, states and
+    // results staged through the context's own pinned buffer, so no copy falls back to the driver's pageable staging.
+    const size_t q_bytes = kSmallBatch * V * sizeof(double), out_bytes = kSmallBatch / 8 + 16;
+    if (c->h_small_bytes < q_bytes + out_bytes)
+    {
+      if (c->h_small)
+        cudaFreeHost(c->h_small);
+      c->h_small = nullptr;
+      c->h_small_bytes = 0;
+      CU(c, cudaHostAlloc(&c->h_small, q_bytes + out_bytes, cudaHostAllocDefault));
+      c->h_small_bytes = q_bytes + out_bytes;
+    }
+    uint8_t* h_out = c->h_small + q_bytes;
+    memcpy(c->h_small, q, n * V * sizeof(double));
+    const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
+    if (!fp64)
+      CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream));
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_q.p, c->h_small, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    int rc = c->compact_bytes == 1 ? launchMain<uint8_t>(c, c->d_q.p, c->d_bitmap.p, 0, n, flags, c->stream) :
+                                     launchMain<uint16_t>(c, c->d_q.p, c->d_bitmap.p, 0, n, flags, c->stream);
+    if (rc == B200SV_OK && !fp64)
+      rc = c->compact_bytes == 1 ? launchRecheck<uint8_t>(c, c->d_q.p, c->d_bitmap.p, n, flags, c->stream) :
+                                   launchRecheck<uint16_t>(c, c->d_q.p, c->d_bitmap.p, n, flags, c->stream);
+    if (rc != B200SV_OK)
+      return rc;
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaMemcpyAsync(h_out, c->d_bitmap.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h_out + kSmallBatch / 8, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    memcpy(valid_bitmap, h_out, (n + 7) / 8);
+    memcpy(&cnt, h_out + kSmallBatch / 8, sizeof(unsigned));
+  }
+  else
+  {
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    int rc = c->compact_bytes == 1 ? runCheckHost<uint8_t>(c, q, n, flags) : runCheckHost<uint16_t>(c, q, n, flags);
+    if (rc != B200SV_OK)
+      return rc;
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    // bitmap back: whole bytes of the caller's buffer; the device words are little-endian, bit i%8 of byte i/8
+    CU(c, cudaMemcpyAsync(valid_bitmap, c->d_bitmap.p, (n + 7) / 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   uint64_t valid = 0;
