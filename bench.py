@@ -120,11 +120,11 @@ def cpu_rate(env, q, seconds=10.0):
     """states/s of the oracle port on all host threads, on a bounded sample sized for ~`seconds` of wall time."""
     n0 = min(len(q), 20000)
     t = time.perf_counter()
-    _, used = env.check(q[:n0], 7, faithful=False, threads=0)
+    _, used = env.check(q[:n0], 7, faithful=False, threads=all_host_threads())
     r0 = n0 / (time.perf_counter() - t)
     n = int(min(len(q), max(n0, r0 * seconds)))
     t = time.perf_counter()
-    col, used = env.check(q[:n], 7, faithful=False, threads=0)
+    col, used = env.check(q[:n], 7, faithful=False, threads=all_host_threads())
     dt = time.perf_counter() - t
     return n / dt, used, n, col
 
@@ -135,6 +135,12 @@ def workload_name(name, cfg, n_vars, n_spheres, n_states, n_points, cells):
             "(%d x %d x %d voxels), checks world+self+intra" %
             (name, cfg["robot"], cfg["group"], n_vars, n_spheres, n_states, n_points, cfg["size"][0], cfg["size"][1],
              cfg["size"][2], cfg["resolution"], cells[0], cells[1], cells[2]))
+
+
+def all_host_threads():
+    """All the host threads the process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would otherwise
+    silently turn the CPU arm into a single-thread baseline."""
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 def run_reference(args):
@@ -154,12 +160,13 @@ def run_reference(args):
     n_full = args.states or cfg["states"]["n"]
     sample = min(n_full, 200_000)
     q = workloads.random_states(cfg["states"]["seed"], sample, lo, hi)
+    host_threads = all_host_threads()
     for _ in range(max(args.warmup, 1)):
-        env.check(q[:20000], 7)
+        env.check(q[:20000], 7, threads=host_threads)
     t = time.perf_counter()
     used = 1
     for _ in range(args.steps):
-        _, used = env.check(q, 7, faithful=False, threads=0)
+        _, used = env.check(q, 7, faithful=False, threads=host_threads)
     dt = time.perf_counter() - t
     rate = sample * args.steps / dt
     line = {"metric": METRIC, "value": rate, "unit": "states/s", "n_gpus": args.gpus, "steps": args.steps,
