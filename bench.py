@@ -43,8 +43,9 @@ def parse():
     ap.add_argument("--no-edt", action="store_true", help="skip the C4 EDT rebuild measurement")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against the oracle")
     ap.add_argument("--fp64", action="store_true", help="force every state through the FP64 kernel")
-    ap.add_argument("--workload", default=WORKLOAD, choices=["C2", "C3"],
-                    help="C2 (default, the config the metric is quoted on) or C3 (dual-arm, 10 M states over all ranks)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["C2", "C3", "C3D"],
+                    help="C2 (default, the config the metric is quoted on), C3 (dual arm, 10 M states over all ranks) or C3D (C3 with the "
+                         "dual arm at 280 spheres)")
     return ap.parse_args()
 
 
@@ -105,7 +106,8 @@ def oracle_env(cfg, cloud):
     from oracle.collision_model import OracleEnv
     from oracle.robot_model import RobotModel
     res = os.path.join(ROOT, "moveit2_b200", "resources")
-    files = {"panda": ("panda_spheres.urdf", "panda.srdf"), "dualarm": ("dualarm_spheres.urdf", "dualarm.srdf")}[cfg["robot"]]
+    files = {"panda": ("panda_spheres.urdf", "panda.srdf"), "dualarm": ("dualarm_spheres.urdf", "dualarm.srdf"),
+             "dualarm_dense": ("dualarm_dense_spheres.urdf", "dualarm.srdf")}[cfg["robot"]]
     with open(os.path.join(res, files[0])) as f:
         urdf = f.read()
     with open(os.path.join(res, files[1])) as f:

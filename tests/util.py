@@ -9,7 +9,8 @@ from oracle.collision_model import OracleEnv
 from oracle.robot_model import RobotModel
 
 RES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "moveit2_b200", "resources")
-ROBOT_FILES = {"panda": ("panda_spheres.urdf", "panda.srdf"), "dualarm": ("dualarm_spheres.urdf", "dualarm.srdf")}
+ROBOT_FILES = {"panda": ("panda_spheres.urdf", "panda.srdf"), "dualarm": ("dualarm_spheres.urdf", "dualarm.srdf"),
+             "dualarm_dense": ("dualarm_dense_spheres.urdf", "dualarm.srdf")}
 
 
 def read(*p):

@@ -16,6 +16,7 @@ Outputs (committed):
 """
 import math
 import os
+import re
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "moveit2_b200", "resources")
 
@@ -170,6 +171,25 @@ def seg_spheres(p0, p1, r, n):
             for i in range(n)]
 
 
+def gen_dualarm_dense(copies=4):
+    """dualarm_dense_spheres.urdf: the dual arm with every collision sphere replaced by `copies` slightly smaller ones
+    spread around it -- 280 spheres on 28 links, the sphere count of a PR2-class decomposition (workload C3D)."""
+    offs = [(0.0, 0.0, 0.0), (0.015, 0.0, 0.0), (-0.015, 0.0, 0.0), (0.0, 0.015, 0.0), (0.0, -0.015, 0.0), (0.0, 0.0, 0.015)]
+    with open(os.path.join(OUT, "dualarm_spheres.urdf")) as f:
+        urdf = f.read()
+
+    def rep(m):
+        x, y, z = (float(v) for v in m.group(1).split())
+        r = float(m.group(2))
+        return "".join('<collision><origin rpy="0 0 0" xyz="%r %r %r"/><geometry><sphere radius="%r"/></geometry></collision>'
+                       % (x + o[0], y + o[1], z + o[2], r - 0.01) for o in offs[:copies])
+
+    dense = re.sub(r'<collision><origin rpy="0 0 0" xyz="([^"]+)"/><geometry><sphere radius="([^"]+)"/></geometry></collision>',
+                   rep, urdf)
+    with open(os.path.join(OUT, "dualarm_dense_spheres.urdf"), "w") as f:
+        f.write(dense)
+
+
 def gen_dualarm():
     links = ["base_link", "torso_lift_link", "head_pan_link", "head_tilt_link"]
     joints = [
@@ -287,5 +307,6 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_panda()
     gen_dualarm()
+    gen_dualarm_dense()
     n = sum(len(v) for v in PANDA_SPHERES.values())
     print("panda: %d spheres (%d in group panda_arm)" % (n, n - len(PANDA_SPHERES["panda_link0"])))
