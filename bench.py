@@ -107,7 +107,8 @@ def oracle_env(cfg, cloud):
     from oracle.robot_model import RobotModel
     res = os.path.join(ROOT, "moveit2_b200", "resources")
     files = {"panda": ("panda_spheres.urdf", "panda.srdf"), "dualarm": ("dualarm_spheres.urdf", "dualarm.srdf"),
-             "dualarm_dense": ("dualarm_dense_spheres.urdf", "dualarm.srdf")}[cfg["robot"]]
+             "dualarm_dense": ("dualarm_dense_spheres.urdf", "dualarm.srdf"),
+             "panda_primitives": ("panda_primitives.urdf", "panda.srdf")}[cfg["robot"]]
     with open(os.path.join(res, files[0])) as f:
         urdf = f.read()
     with open(os.path.join(res, files[1])) as f:

@@ -199,6 +199,7 @@ struct UShape
 {
   std::string kind;
   double radius = 0;
+  double dims[3] = { 0, 0, 0 };  // cylinder: radius, length; box: x, y, z
   Mat4 origin;
 };
 struct Joint
@@ -279,6 +280,16 @@ bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::s
       s.origin = poseToMatrix(xyz, rpy);
       if (s.kind == "sphere")
         s.radius = atof(ge->children[0]->attr("radius", "0").c_str());
+      else if (s.kind == "cylinder")
+      {
+        s.dims[0] = atof(ge->children[0]->attr("radius", "0").c_str());
+        s.dims[1] = atof(ge->children[0]->attr("length", "0").c_str());
+      }
+      else if (s.kind == "box" && !parseDoubles(ge->children[0]->attr("size"), 3, s.dims))
+      {
+        err = "URDF: bad box size in link " + le->attr("name");
+        return false;
+      }
       shapes.push_back(s);
     }
     ulinks[le->attr("name")] = shapes;
@@ -729,7 +740,9 @@ bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::s
   for (int r : roots_j)
     updated.insert(joints[r].descendant_links.begin(), joints[r].descendant_links.end());
 
-  // ---- BodyDecomposition per link with geometry (SPHERE shapes) ------------------------------------------------------
+  // ---- BodyDecomposition per link with geometry (collision_distance_field_types.cpp:292-335, padding 0) --------------------
+  // Spheres, cylinders and boxes; the bodies (containsPoint, bounding sphere / cylinder) are restated from geometric_shapes'
+  // published bodies.cpp, which the reference does not vendor: parity unpinned for cylinders and boxes.
   struct Decomp { std::vector<std::array<double, 4>> spheres; std::vector<double> points; double bs[4] = { 0, 0, 0, 0 }; };
   std::map<int, Decomp> decomp;
   for (const auto& l : links)
@@ -740,17 +753,70 @@ bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::s
     bool first = true;
     for (const auto& s : l.shapes)
     {
-      if (s.kind != "sphere")
+      if (s.kind != "sphere" && s.kind != "cylinder" && s.kind != "box")
       {
         err = "link '" + l.name + "' has <" + s.kind +
-              "> collision geometry; only <sphere> is supported by the URDF path (pass explicit spheres through "
+              "> collision geometry; the URDF path decomposes <sphere>, <cylinder> and <box> (pass explicit spheres through "
               "b200sv_create for other shapes, as CollisionEnvDistanceField's link_body_decompositions argument does)";
         return false;
       }
-      const double cx = Mc(s.origin, 0, 3), cy = Mc(s.origin, 1, 3), cz = Mc(s.origin, 2, 3), r = s.radius;
-      d.spheres.push_back({ cx, cy, cz, r });  // collision_distance_field_types.cpp:63-67
-      // findInternalPointsConvex (find_internal_points.cpp:39-64), containsPoint = |c-p|^2 <= r^2
+      const double cx = Mc(s.origin, 0, 3), cy = Mc(s.origin, 1, 3), cz = Mc(s.origin, 2, 3);
       const double res = resolution;
+      double r;  // radius of the body's bounding sphere (computeBoundingSphere)
+      double half[3] = { 0, 0, 0 }, radius2 = 0.0, length2 = 0.0;
+      if (s.kind == "sphere")
+      {
+        r = s.radius;
+        d.spheres.push_back({ cx, cy, cz, r });  // collision_distance_field_types.cpp:63-67
+      }
+      else
+      {
+        // determineCollisionSpheres (:68-82) on the bounding cylinder (axis = its local z)
+        Mat4 cp = s.origin;
+        double cr, cl;
+        if (s.kind == "cylinder")
+        {
+          radius2 = s.dims[0] * s.dims[0];
+          length2 = 1.0 * s.dims[1] / 2.0;
+          r = sqrt(length2 * length2 + radius2);
+          cr = s.dims[0];
+          cl = 2.0 * length2;
+        }
+        else
+        {
+          for (int k = 0; k < 3; ++k)
+            half[k] = s.dims[k] * (1.0 / 2.0);
+          r = sqrt(half[0] * half[0] + half[1] * half[1] + half[2] * half[2]);
+          const double ang = 90.0 * (M_PI / 180.0), c = cos(ang), sn = sin(ang);
+          Mat4 rot = identity();
+          double a, b;
+          if (half[0] > half[1] && half[0] > half[2])
+          {
+            cl = half[0] * 2.0; a = half[1]; b = half[2];
+            M(rot, 0, 0) = c; M(rot, 0, 2) = sn; M(rot, 2, 0) = -sn; M(rot, 2, 2) = c;  // AngleAxis(90 deg, UnitY)
+            cp = mulAffine(s.origin, rot);
+          }
+          else if (half[1] > half[2])
+          {
+            cl = half[1] * 2.0; a = half[2]; b = half[0];
+            M(rot, 1, 1) = c; M(rot, 1, 2) = -sn; M(rot, 2, 1) = sn; M(rot, 2, 2) = c;  // AngleAxis(90 deg, UnitX)
+            cp = mulAffine(s.origin, rot);
+          }
+          else
+          {
+            cl = half[2] * 2.0; a = half[1]; b = half[0];
+          }
+          cr = sqrt(a * a + b * b);
+        }
+        const long num_points = (long)ceil(cl / (cr / 2.0));
+        const double spacing = cl / ((num_points * 1.0) - 1.0);
+        for (long i = 1; i < num_points - 1; ++i)
+        {
+          const double z = (-cl / 2.0) + i * spacing;
+          d.spheres.push_back({ Mc(cp, 0, 2) * z + Mc(cp, 0, 3), Mc(cp, 1, 2) * z + Mc(cp, 1, 3), Mc(cp, 2, 2) * z + Mc(cp, 2, 3), cr });
+        }
+      }
+      // findInternalPointsConvex (find_internal_points.cpp:39-64) around the bounding sphere, containsPoint per body type
       const double xs = std::floor((cx - r - res) / res) * res, ys = std::floor((cy - r - res) / res) * res,
                    zs = std::floor((cz - r - res) / res) * res;
       const double xe = cx + r + res, ye = cy + r + res, ze = cz + r + res;
@@ -758,8 +824,27 @@ bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::s
         for (double py = ys; py <= ye; py += res)
           for (double pz = zs; pz <= ze; pz += res)
           {
-            const double dx = cx - px, dy = cy - py, dz = cz - pz;
-            if (dx * dx + dy * dy + dz * dz <= r * r)
+            bool inside;
+            if (s.kind == "sphere")
+            {
+              const double dx = cx - px, dy = cy - py, dz = cz - pz;
+              inside = dx * dx + dy * dy + dz * dz <= r * r;
+            }
+            else
+            {
+              const double vx = px - cx, vy = py - cy, vz = pz - cz;
+              double al[3];
+              for (int k = 0; k < 3; ++k)  // v . column k of the body's rotation
+                al[k] = vx * Mc(s.origin, 0, k) + vy * Mc(s.origin, 1, k) + vz * Mc(s.origin, 2, k);
+              if (s.kind == "box")
+                inside = fabs(al[0]) <= half[0] && fabs(al[1]) <= half[1] && fabs(al[2]) <= half[2];
+              else
+              {
+                const double remaining = radius2 - al[0] * al[0];
+                inside = !(fabs(al[2]) > length2) && !(remaining < 0.0) && al[1] * al[1] <= remaining;
+              }
+            }
+            if (inside)
             {
               d.points.push_back(px);
               d.points.push_back(py);

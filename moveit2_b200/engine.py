@@ -119,7 +119,8 @@ class StateValidityEngine:
     def for_robot(cls, robot_name, group, **kw):
         """Bundled benchmark robots: 'panda' (panda_arm, hand, panda_arm_hand) and 'dualarm' (PR2-like)."""
         files = {"panda": ("panda_spheres.urdf", "panda.srdf"), "dualarm": ("dualarm_spheres.urdf", "dualarm.srdf"),
-             "dualarm_dense": ("dualarm_dense_spheres.urdf", "dualarm.srdf")}
+             "dualarm_dense": ("dualarm_dense_spheres.urdf", "dualarm.srdf"),
+             "panda_primitives": ("panda_primitives.urdf", "panda.srdf")}
         u, s = files[robot_name]
         with open(os.path.join(RESOURCES, u)) as f:
             urdf = f.read()

@@ -143,21 +143,75 @@ def merge_bounding_spheres(spheres):
     return c, r
 
 
+def bounding_cylinder(kind, dims, pose):
+    """bodies::Cylinder / bodies::Box::computeBoundingCylinder of geometric_shapes (published bodies.cpp, scale 1, padding 0;
+    un-vendored in the reference: parity unpinned).  Returns (pose 4x4, radius, length), axis = local z."""
+    if kind == "cylinder":
+        return pose.copy(), float(dims[0]), 2.0 * (1.0 * float(dims[1]) / 2.0)
+    l2, w2, h2 = (float(d) * (1.0 / 2.0) for d in dims)
+    ang = 90.0 * (math.pi / 180.0)
+    c, sn = math.cos(ang), math.sin(ang)
+    rot = np.eye(4)
+    if l2 > w2 and l2 > h2:
+        length, a, b = l2 * 2.0, w2, h2
+        rot[:3, :3] = [[c, 0.0, sn], [0.0, 1.0, 0.0], [-sn, 0.0, c]]  # AngleAxis(90 deg, UnitY)
+    elif w2 > h2:
+        length, a, b = w2 * 2.0, h2, l2
+        rot[:3, :3] = [[1.0, 0.0, 0.0], [0.0, c, -sn], [0.0, sn, c]]  # AngleAxis(90 deg, UnitX)
+    else:
+        length, a, b = h2 * 2.0, w2, l2
+    return affine_mul(pose, rot), math.sqrt(a * a + b * b), length
+
+
+def affine_mul(a, b):
+    """Eigen Isometry3d product, plain left-to-right sums (the order csrc/host_model.cpp uses too)."""
+    out = np.eye(4)
+    for r in range(3):
+        for c in range(4):
+            v = a[r, 0] * b[0, c]
+            v += a[r, 1] * b[1, c]
+            v += a[r, 2] * b[2, c]
+            v += a[r, 3] * b[3, c]
+            out[r, c] = v
+    return out
+
+
 class BodyDecomposition:
-    """collision_distance_field_types.cpp:292-335 for SPHERE shapes (padding 0, scale 1)."""
+    """collision_distance_field_types.cpp:292-335 (padding 0, scale 1): determineCollisionSpheres (:59-85) -- a SPHERE shape is
+    one sphere, anything else gets spheres of the bounding cylinder's radius along its axis (num = ceil(len / (r / 2)),
+    spacing = len / (num - 1), centres i = 1 .. num - 2: short bodies get NONE, the reference's behaviour) -- plus the interior
+    lattice points and the merged bounding sphere.  Spheres, cylinders and boxes (bodies restated from geometric_shapes)."""
 
     def __init__(self, link, resolution):
         self.spheres = []  # (rel xyz, radius)
         pts = []
         bss = []
         for s in link.shapes:
-            if s.kind != "sphere":
-                raise NotImplementedError("oracle supports SPHERE collision geometry only (link %s has %s)"
+            if s.kind == "sphere":
+                c, r = s.origin[:3, 3].copy(), float(s.dims[0])
+                self.spheres.append((c, r))
+                pts.append(find_internal_points_sphere(c, r, resolution))
+                bss.append((c, r))
+                continue
+            if s.kind not in ("cylinder", "box"):
+                raise NotImplementedError("oracle supports sphere, cylinder and box collision geometry (link %s has %s)"
                                           % (link.name, s.kind))
-            c, r = s.origin[:3, 3].copy(), float(s.dims[0])
-            self.spheres.append((c, r))
-            pts.append(find_internal_points_sphere(c, r, resolution))
-            bss.append((c, r))
+            cp, cr, cl = bounding_cylinder(s.kind, s.dims, s.origin)
+            num_points = int(math.ceil(cl / (cr / 2.0)))
+            spacing = cl / ((num_points * 1.0) - 1.0) if num_points != 1 else float("inf")
+            for i in range(1, num_points - 1):
+                z = (-cl / 2.0) + i * spacing
+                c = np.array([cp[r, 2] * z + cp[r, 3] for r in range(3)])  # pose * (0, 0, z)
+                self.spheres.append((c, cr))
+            ty = 2 if s.kind == "cylinder" else 4
+            pts.append(find_internal_points_body(ty, s.dims, s.origin, resolution, "world"))
+            if s.kind == "cylinder":
+                length2 = 1.0 * float(s.dims[1]) / 2.0
+                rb = math.sqrt(length2 * length2 + float(s.dims[0]) * float(s.dims[0]))
+            else:
+                h = [float(d) * (1.0 / 2.0) for d in s.dims]
+                rb = math.sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2])
+            bss.append((s.origin[:3, 3].copy(), rb))
         self.points = np.concatenate(pts, axis=0) if pts else np.zeros((0, 3))
         self.bs_center, self.bs_radius = merge_bounding_spheres(bss)
 

@@ -854,3 +854,29 @@ def test_field_add_shape_equals_the_restated_body_decomposition(frame):
     with pytest.raises(mb.B200svError):
         eng.field_add_shape(3, (0.1, 0.2), np.eye(4))  # cone: host side
     eng.close()
+
+
+# ---- link geometry given as cylinders and boxes (BodyDecomposition's bounding-cylinder spheres) ----------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["panda_arm", "panda_arm_hand"])
+def test_validity_with_cylinder_and_box_link_geometry(group):
+    cfg = workloads.CONFIGS["C1"]
+    eng, env = make_pair("panda_primitives", group, cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    assert eng.n_spheres == env.n_spheres == 52
+    cloud = workloads.make_cloud("C1")
+    eng.field_add_points(cloud)
+    env.world.add_points(cloud)
+    # the self field holds the voxelised BOX of panda_link0 (interior lattice of a non-sphere body)
+    assert np.array_equal(eng.field_get_d2(mb.FIELD_SELF) == 0, env.self_field.d2() == 0)
+    assert (env.self_field.d2() == 0).sum() > 300
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(9, 20000, lo, hi)
+    for flags in (W, S, I, ALL):
+        ref, _ = env.check(q, flags)
+        assert np.array_equal(eng.check_batch(q, flags), ref == 0), flags
+    assert 0.05 < ref.mean() < 0.95
+    for s in q[:8]:
+        assert np.abs(eng.sphere_centers(s) - env.sphere_centers(s).reshape(-1, 3)).max() < 1e-12
+    eng.close()

@@ -81,7 +81,9 @@ CASES = [("panda", "panda_spheres.urdf", "panda.srdf", "panda_arm"),
          ("panda", "panda_spheres.urdf", "panda.srdf", "hand"),
          ("dualarm", "dualarm_spheres.urdf", "dualarm.srdf", "arms"),
          ("dualarm", "dualarm_spheres.urdf", "dualarm.srdf", "left_arm"),
-         ("dualarm", "dualarm_spheres.urdf", "dualarm.srdf", "whole_body")]
+         ("dualarm", "dualarm_spheres.urdf", "dualarm.srdf", "whole_body"),
+         ("panda_primitives", "panda_primitives.urdf", "panda.srdf", "panda_arm"),
+         ("panda_primitives", "panda_primitives.urdf", "panda.srdf", "panda_arm_hand")]
 
 
 @pytest.mark.parametrize("robot,urdf,srdf,group", CASES)

@@ -10,7 +10,8 @@ from oracle.robot_model import RobotModel
 
 RES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "moveit2_b200", "resources")
 ROBOT_FILES = {"panda": ("panda_spheres.urdf", "panda.srdf"), "dualarm": ("dualarm_spheres.urdf", "dualarm.srdf"),
-             "dualarm_dense": ("dualarm_dense_spheres.urdf", "dualarm.srdf")}
+             "dualarm_dense": ("dualarm_dense_spheres.urdf", "dualarm.srdf"),
+             "panda_primitives": ("panda_primitives.urdf", "panda.srdf")}
 
 
 def read(*p):

@@ -171,6 +171,30 @@ def seg_spheres(p0, p1, r, n):
             for i in range(n)]
 
 
+def gen_panda_primitives():
+    """panda_primitives.urdf: the Panda kinematics with <cylinder> / <box> collision geometry on some links (link0, outside the
+    group, feeds the self field), spheres elsewhere -- exercises BodyDecomposition's bounding-cylinder spheres and the interior
+    lattice of non-sphere bodies on the URDF path."""
+    with open(os.path.join(OUT, "panda_spheres.urdf")) as f:
+        u = f.read()
+
+    def replace_link(urdf, name, collisions):
+        pat = re.compile(r'(<link name="%s">)(.*?)(</link>)' % name, re.S)
+        body = "\n" + "".join('    <collision><origin rpy="%s" xyz="%s"/><geometry>%s</geometry></collision>\n' % c
+                              for c in collisions) + "  "
+        return pat.sub(lambda m: m.group(1) + body + m.group(3), urdf)
+
+    u = replace_link(u, "panda_link0", [("0 0 0", "-0.04 0.0 0.07", '<box size="0.22 0.19 0.13"/>')])
+    u = replace_link(u, "panda_link2", [("0 0 0", "0.0 0.0 0.02", '<cylinder radius="0.055" length="0.24"/>')])
+    u = replace_link(u, "panda_link4", [("1.5707963 0 0.3", "-0.04 0.02 0.0", '<cylinder radius="0.05" length="0.21"/>')])
+    u = replace_link(u, "panda_link5", [("0.1 0.2 0", "0.0 0.04 -0.18", '<box size="0.09 0.26 0.11"/>'),
+                                        ("0 0 0", "0.0 0.06 -0.03", '<sphere radius="0.055"/>')])
+    u = replace_link(u, "panda_link6", [("0 1.5707963 0", "0.04 0.0 0.0", '<cylinder radius="0.045" length="0.17"/>')])
+    u = replace_link(u, "panda_hand", [("0 0 0", "0.0 0.0 0.03", '<box size="0.05 0.2 0.07"/>')])
+    with open(os.path.join(OUT, "panda_primitives.urdf"), "w") as f:
+        f.write(u)
+
+
 def gen_dualarm_dense(copies=4):
     """dualarm_dense_spheres.urdf: the dual arm with every collision sphere replaced by `copies` slightly smaller ones
     spread around it -- 280 spheres on 28 links, the sphere count of a PR2-class decomposition (workload C3D)."""
@@ -308,5 +332,6 @@ if __name__ == "__main__":
     gen_panda()
     gen_dualarm()
     gen_dualarm_dense()
+    gen_panda_primitives()
     n = sum(len(v) for v in PANDA_SPHERES.values())
     print("panda: %d spheres (%d in group panda_arm)" % (n, n - len(PANDA_SPHERES["panda_link0"])))
