@@ -108,25 +108,7 @@ __device__ __forceinline__ void store12(double* p, const double* o)
   for (int i = 0; i < 6; ++i)
     v[i] = make_double2(o[2 * i + 0], o[2 * i + 1]);
 }
-__device__ __forceinline__ void load4(const float* p, float* o)
-{
-  const float4 t = *reinterpret_cast<const float4*>(p);
-  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-}
-__device__ __forceinline__ void load4(const double* p, double* o)
-{
-  const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
-  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
-}
-__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d)
-{
-  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
-}
-__device__ __forceinline__ void store4(double* p, double a, double b, double c, double d)
-{
-  reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
-  reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
-}
+
 
 // A(3x4) * B(3x4) with implicit (0,0,0,1) rows; accumulation order k = 0..3 as Eigen's fixed-size product.
 template <typename R>
