@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) scatterKernel(const double* __restrict__ 
 // Intermediate values above max_d2 mean "nothing within range"; the x pass treats them so.
 // `invert`: transform of the COMPLEMENT (distance to the nearest free voxel of the grid = negative_distance_square_ of the
 // signed field, propagateNegative :446-504); cells outside the grid are not free.
-__global__ void __launch_bounds__(512) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
+__global__ void __launch_bounds__(1024) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
                                                   int chunk, int n_chunks, unsigned nz8_magic, int invert)
 {
   extern __shared__ __align__(16) uint8_t smem[];
