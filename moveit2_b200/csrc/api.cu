@@ -316,29 +316,145 @@ unsigned halfBitsUp(double x)
 
 // Tables of fast_check.cu (device_model.hpp, namespace fast), from the same links / spheres / clusters / pairs the
 // generic blobs are built from.  All constants are evaluated in double and narrowed once.
-bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, const std::vector<VarRec>& vars,
-                   const std::vector<SphereRec<double>>& spheres, int n_spheres, const std::vector<BsRec<double>>& bs,
+bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, const std::vector<VarRec>& vars,
+                   const std::vector<SphereRec<double>>& spheres_in, int n_spheres, const std::vector<BsRec<double>>& bs_in,
                    const std::vector<PairRec>& pairs, const std::vector<GroupRec>& groups, double margin, double pair_eps,
                    double bs_eps, double tight_eps)
 {
   c.blob_fast.clear();
-  for (const auto& L : links)
+  for (const auto& L : links_in)
     if (L.type != FIXED && L.type != REVOLUTE && L.type != PRISMATIC)
       return false;
   if ((int)c.robot.group_var_index.size() > fastCheckMaxVars())
     return false;
   const int unroll = fastCheckUnroll();
   const double oo = c.grid.oo;
-  const int nl = (int)links.size();
-  // which transforms go to shared memory: parents that are not the previous link, and links whose clusters are in pairs
-  std::vector<char> stored(nl, 0);
+  const int nl = (int)links_in.size();
+  // ---- constant links folded into their ancestors ("alias" links) -----------------------------------------------------------
+  // A link behind a fixed joint, or behind a joint the group does not move (its value is the base state's), is rigidly
+  // attached to its parent.  Its spheres, cluster centres and bounding sphere are re-expressed (in double) in the frame of
+  // the nearest ancestor that has a transform of its own, and a moving link behind it gets that constant transform folded
+  // into its joint origin: the kernel then spends no FK on such links (Panda: link8, hand, both fingers; the dual arm: half
+  // of its 28 links).
+  std::vector<LinkRec<double>> links = links_in;
+  std::vector<SphereRec<double>> spheres = spheres_in;
+  std::vector<BsRec<double>> bs = bs_in;
+  struct X34
+  {
+    double m[12];  // rows of [R | t]
+  };
+  auto mul34 = [](const X34& a, const X34& b) {
+    X34 o{};
+    for (int r = 0; r < 3; ++r)
+    {
+      for (int col = 0; col < 3; ++col)
+        o.m[4 * r + col] = a.m[4 * r] * b.m[col] + a.m[4 * r + 1] * b.m[4 + col] + a.m[4 * r + 2] * b.m[8 + col];
+      o.m[4 * r + 3] = a.m[4 * r] * b.m[3] + a.m[4 * r + 1] * b.m[7] + a.m[4 * r + 2] * b.m[11] + a.m[4 * r + 3];
+    }
+    return o;
+  };
+  auto originOf = [](const LinkRec<double>& L) {
+    X34 o{};
+    for (int r = 0; r < 3; ++r)
+      for (int col = 0; col < 4; ++col)
+        o.m[4 * r + col] = L.has_origin ? L.o[4 * r + col] : (r == col ? 1.0 : 0.0);
+    return o;
+  };
+  std::vector<char> alias(nl, 0);
+  std::vector<int> anchor(nl, -1);  // alias links: the ancestor whose transform they use
+  std::vector<X34> rel(nl);         // alias links: their frame in the anchor's frame
+  static const bool fold = !(getenv("B200SV_NO_FOLD") && atoi(getenv("B200SV_NO_FOLD")) != 0);
+  for (int l = 0; l < nl && fold; ++l)
+  {
+    const LinkRec<double>& L = links_in[l];
+    const int P = L.parent;  // device links are in DFS pre-order: P < l
+    const bool constant = L.type == FIXED || vars[L.var].k < 0;
+    if (constant && P >= 0)
+    {
+      // local transform origin * joint(value): Rodrigues rotation (revolute_joint_model.cpp:250-287) or a translation along
+      // the axis (prismatic_joint_model.cpp:124-146)
+      X34 J{};
+      J.m[0] = J.m[5] = J.m[10] = 1.0;
+      if (L.type != FIXED)
+      {
+        const double q = vars[L.var].b, x = L.ax[0], y = L.ax[1], z = L.ax[2];
+        if (L.type == REVOLUTE)
+        {
+          const double cs = cos(q), sn = sin(q), t = 1.0 - cs;
+          const double R[9] = { t * x * x + cs, t * x * y - z * sn, t * x * z + y * sn, t * x * y + z * sn, t * y * y + cs,
+                                t * y * z - x * sn, t * x * z - y * sn, t * y * z + x * sn, t * z * z + cs };
+          for (int r = 0; r < 3; ++r)
+            for (int col = 0; col < 3; ++col)
+              J.m[4 * r + col] = R[3 * r + col];
+        }
+        else
+        {
+          J.m[3] = x * q;
+          J.m[7] = y * q;
+          J.m[11] = z * q;
+        }
+      }
+      const X34 local = mul34(originOf(L), J);
+      alias[l] = 1;
+      anchor[l] = alias[P] ? anchor[P] : P;
+      rel[l] = alias[P] ? mul34(rel[P], local) : local;
+    }
+  }
   for (int l = 0; l < nl; ++l)
-    if (links[l].parent >= 0 && links[l].parent != l - 1)
-      stored[links[l].parent] = 1;
+  {
+    LinkRec<double>& L = links[l];
+    const int P = links_in[l].parent;
+    if (alias[l])
+    {
+      L.type = fast::kAlias;
+      L.parent = anchor[l];
+      L.has_origin = 1;
+      for (int i = 0; i < 12; ++i)
+        L.o[i] = rel[l].m[i];  // only its translation is used below (reach bound)
+    }
+    else if (P >= 0 && alias[P])
+    {
+      const X34 o = mul34(rel[P], originOf(links_in[l]));
+      L.parent = anchor[P];
+      L.has_origin = 1;
+      for (int i = 0; i < 12; ++i)
+        L.o[i] = o.m[i];
+    }
+  }
+  auto move = [&](int slot, double& x, double& y, double& z) {
+    const double* m = rel[slot].m;
+    const double nx = m[0] * x + m[1] * y + m[2] * z + m[3], ny = m[4] * x + m[5] * y + m[6] * z + m[7],
+                 nz = m[8] * x + m[9] * y + m[10] * z + m[11];
+    x = nx;
+    y = ny;
+    z = nz;
+  };
+  for (auto& S : spheres)
+    if (alias[S.slot])
+      move(S.slot, S.x, S.y, S.z);
+  for (auto& B : bs)
+    if (alias[B.slot])
+    {
+      move(B.slot, B.x, B.y, B.z);
+      move(B.slot, B.tx, B.ty, B.tz);
+    }
+  auto tslot = [&](int slot) { return alias[slot] ? anchor[slot] : slot; };  // whose transform poses this link's geometry
+  // which transforms are stored: parents that are not in registers when needed, and links whose clusters are in pairs
+  std::vector<char> stored(nl, 0);
+  {
+    int in_regs = -2;  // the link whose transform the registers hold after the previous link
+    for (int l = 0; l < nl; ++l)
+    {
+      const int P = links[l].parent;
+      if (P >= 0 && P != in_regs)
+        stored[P] = 1;
+      in_regs = alias[l] ? P : l;
+    }
+  }
   for (const auto& P : pairs)
   {
-    stored[bs[P.a].slot] = 1;
-    stored[bs[P.b].slot] = 1;
+    stored[tslot(bs[P.a].slot)] = 1;
+    stored[tslot(bs[P.b].slot)] = 1;
   }
   std::vector<int> store_off(nl, -1);
   int n_stored = 0;
@@ -352,6 +468,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
   std::vector<fast::Hot> hot;
   std::vector<fast::Link> fl(nl);
   const bool bytes8 = c.compact_bytes == 1;
+  int in_regs = -2;
   for (int l = 0; l < nl; ++l)
   {
     const LinkRec<double>& L = links[l];
@@ -360,7 +477,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
     F.k = -1;
     F.a = 0.0;
     F.b = 0.0;
-    if (L.type != FIXED)
+    if (L.type != FIXED && L.type != fast::kAlias)
     {
       const VarRec& v = vars[L.var];
       F.k = v.k;
@@ -368,8 +485,9 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
       F.b = v.b;
     }
     const bool root = L.parent < 0;
-    F.parent_off = root ? fast::kParentRoot : (L.parent == l - 1 ? fast::kParentPrev : store_off[L.parent]);
-    F.store_off = store_off[l];
+    F.parent_off = root ? fast::kParentRoot : (L.parent == in_regs ? fast::kParentPrev : store_off[L.parent]);
+    F.store_off = alias[l] ? -1 : store_off[l];
+    in_regs = alias[l] ? L.parent : l;
     // O: origin rotation (rows), scaled into the voxel frame for a root
     double O[9], ot[3];
     for (int r = 0; r < 3; ++r)
@@ -592,10 +710,11 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
     fast::Pair P{};
     const double rt = (A.tr + B.tr + tight_eps) * oo + half_slack;
     P.rt2_h = halfBitsUp(rt * rt * (1.0 + 4.0 / 1024.0));  // + the half rounding of the squared sum itself
-    if (store_off[A.slot] > 0xffff || store_off[B.slot] > 0xffff)
+    const int offA = store_off[tslot(A.slot)], offB = store_off[tslot(B.slot)];
+    if (offA > 0xffff || offB > 0xffff)
       return false;  // beyond the packed pair record: the generic kernel takes the group
     P.ab = (unsigned)rep_of_cluster[pairs[p].a] | ((unsigned)rep_of_cluster[pairs[p].b] << 16);
-    P.offs = (unsigned)store_off[A.slot] | ((unsigned)store_off[B.slot] << 16);
+    P.offs = (unsigned)offA | ((unsigned)offB << 16);
     P.quirk = -1;
     if (!pairs[p].quirk_free)
     {
@@ -604,8 +723,8 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links, con
       Q.bx = (float)B.x; Q.by = (float)B.y; Q.bz = (float)B.z;
       Q.lim_v2 = (float)((A.r + B.r) * oo * oo);
       Q.eps_v2 = (float)(bs_eps * oo * oo);
-      Q.a_off = store_off[A.slot];
-      Q.b_off = store_off[B.slot];
+      Q.a_off = offA;
+      Q.b_off = offB;
       P.quirk = (int)fq.size();
       fq.push_back(Q);
     }

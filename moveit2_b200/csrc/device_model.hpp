@@ -100,6 +100,10 @@ namespace fast
 {
 constexpr int kParentRoot = -1;  // the link's transform is [M | m] itself (constants already in the voxel frame)
 constexpr int kParentPrev = -2;  // parent = the previous link of the table: its transform is still in registers
+// Link::type of a link that does not move relative to an ancestor (fixed joint, or a joint outside the group at its base-state
+// value): the host re-expressed its spheres and clusters in that ancestor's frame, the kernel only fetches the ancestor's
+// transform -- no joint, no 3x4 product, no store.
+constexpr int kAlias = 100;
 
 // T_link = T_parent * [M | m]
 //   REVOLUTE   M = a0 + sin(q) * a1 + (1 - cos(q)) * a2,  m = ot        (a0 = O, a1 = O*K, a2 = O*K^2: Rodrigues)

@@ -419,50 +419,53 @@ __global__ void __launch_bounds__(B200SV_FAST_THREADS, B200SV_FAST_MINBLOCKS) fa
       const float4* Lf = reinterpret_cast<const float4*>(m.links + l);
       const int4 m0 = Li[0];  // type, k, parent_off, store_off
       const int4 m1 = Li[1];  // h0, h1, c0, c1
-      const double2 ab = reinterpret_cast<const double2*>(Li)[2];
       const float4 o = Lf[3];
       const int k_next = reinterpret_cast<const int*>(Li + 11)[1];  // the table ends with a sentinel record
-      const float4 c0 = Lf[4], c1 = Lf[5], c2 = Lf[6];  // a0[0..8], a1[0..2]
-      float M[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x };
-      float mt[3] = { o.x, o.y, o.z };
       const double q_cur = q_next;
       q_next = k_next >= 0 ? qrow[k_next] : 0.0;  // the NEXT link's joint value: in flight during this link's work
-      if (m0.x != FIXED)
-      {
-        // setJointGroupPositions / updateMimicJoints in double, then narrowed (k < 0: a = 0, the value is b)
-        const float qf = static_cast<float>(ab.x * q_cur + ab.y);
-        if (m0.x == REVOLUTE)
-        {
-          const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];  // a1[3..8], a2[0..8]
-          const float A1[9] = { c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w, c4.x, c4.y };
-          const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
-          float s, c;
-          sincosf(qf, &s, &c);
-          const float t = 1.f - c;
-#pragma unroll
-          for (int i = 0; i < 9; ++i)
-            M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
-        }
-        else
-        {  // PRISMATIC
-          mt[0] = fmaf(qf, c2.y, mt[0]);
-          mt[1] = fmaf(qf, c2.z, mt[1]);
-          mt[2] = fmaf(qf, c2.w, mt[2]);
-        }
-      }
       // T = T_parent * [M | mt]; a root's "parent" is the identity block of the header (one code path, no merge)
       if (m0.z == fast::kParentRoot)
         load12(h.ident, T);
       else if (m0.z != fast::kParentPrev)
         ts.load(m0.z, lane, T);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
+      if (m0.x != fast::kAlias)  // an alias link is posed by its anchor's transform as it is (host-folded geometry)
       {
-        const float p0 = T[4 * r + 0], p1 = T[4 * r + 1], p2 = T[4 * r + 2];
-        T[4 * r + 0] = fmaf(p0, M[0], fmaf(p1, M[3], p2 * M[6]));
-        T[4 * r + 1] = fmaf(p0, M[1], fmaf(p1, M[4], p2 * M[7]));
-        T[4 * r + 2] = fmaf(p0, M[2], fmaf(p1, M[5], p2 * M[8]));
-        T[4 * r + 3] = fmaf(p0, mt[0], fmaf(p1, mt[1], fmaf(p2, mt[2], T[4 * r + 3])));
+        const double2 ab = reinterpret_cast<const double2*>(Li)[2];
+        const float4 c0 = Lf[4], c1 = Lf[5], c2 = Lf[6];  // a0[0..8], a1[0..2]
+        float M[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x };
+        float mt[3] = { o.x, o.y, o.z };
+        if (m0.x != FIXED)
+        {
+          // setJointGroupPositions / updateMimicJoints in double, then narrowed (k < 0: a = 0, the value is b)
+          const float qf = static_cast<float>(ab.x * q_cur + ab.y);
+          if (m0.x == REVOLUTE)
+          {
+            const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];  // a1[3..8], a2[0..8]
+            const float A1[9] = { c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w, c4.x, c4.y };
+            const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
+            float s, c;
+            sincosf(qf, &s, &c);
+            const float t = 1.f - c;
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+              M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
+          }
+          else
+          {  // PRISMATIC
+            mt[0] = fmaf(qf, c2.y, mt[0]);
+            mt[1] = fmaf(qf, c2.z, mt[1]);
+            mt[2] = fmaf(qf, c2.w, mt[2]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+        {
+          const float p0 = T[4 * r + 0], p1 = T[4 * r + 1], p2 = T[4 * r + 2];
+          T[4 * r + 0] = fmaf(p0, M[0], fmaf(p1, M[3], p2 * M[6]));
+          T[4 * r + 1] = fmaf(p0, M[1], fmaf(p1, M[4], p2 * M[7]));
+          T[4 * r + 2] = fmaf(p0, M[2], fmaf(p1, M[5], p2 * M[8]));
+          T[4 * r + 3] = fmaf(p0, mt[0], fmaf(p1, mt[1], fmaf(p2, mt[2], T[4 * r + 3])));
+        }
       }
       if (m0.w >= 0)
         ts.store(m0.w, lane, T);
