@@ -1163,7 +1163,7 @@ int buildTables(b200sv_ctx* c)
 b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, int blob_bytes, bool fast = false)
 {
   b200sv_ctx::LaunchCfg best;
-  const int regs = ((fast ? fastCheckKernelRegs(c->compact_bytes) : checkKernelRegs(fp64, from_list, c->compact_bytes)) + 7) & ~7;
+  const int regs = ((fast ? fastCheckKernelRegs(c->compact_bytes, (int)c->robot.group_var_index.size()) : checkKernelRegs(fp64, from_list, c->compact_bytes)) + 7) & ~7;
   const int reg_warps = 65536 / (regs * 32);
   const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast, c->fast_n_reps, (int)c->robot.group_var_index.size(), c->fast_n_linkpairs) :
                          checkPerWarpBytes(fp64, fp64 ? c->state_stride_d : c->state_stride_f);
@@ -1173,7 +1173,7 @@ b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, 
       continue;
     const long per_block = std::min<long>(c->smem_optin, (233472L - 1024L * b) / b) - align16(blob_bytes);
     int w = per_block > 0 ? (int)(per_block / pw) : 0;
-    w = std::min(w, fast ? fastCheckMaxWarps() : 16);  // __launch_bounds__ of the kernels
+    w = std::min(w, fast ? fastCheckMaxWarps((int)c->robot.group_var_index.size()) : 16);  // __launch_bounds__ of the kernels
     w = std::min(w, reg_warps / b);
     if (c->tune_warps > 0)
       w = std::min(w, c->tune_warps);
@@ -1456,6 +1456,7 @@ int launchMain(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t ba
     a.model_bytes = (int)c->blob_fast.size();
     a.t_scratch = c->fast_t_global ? c->d_t_scratch : nullptr;
     a.hier = c->fast_n_linkpairs > 0;
+    a.n_group_vars = (int)c->robot.group_var_index.size();
     CU(c, launchFastCheck<FT>(a, c->sm_count * k.blocks_per_sm, k.warps * 32, k.smem, s));
     return B200SV_OK;
   }

@@ -34,6 +34,7 @@ struct CheckArgs
   const unsigned* list_count;
   float* t_scratch;      // fast pass only: global-memory home of the link transforms (null: shared memory)
   int hier;              // fast pass only: the blob carries LinkPair records (hierarchical cull)
+  int n_group_vars;      // fast pass only: selects the kernel instance (register prefetch of the states)
 };
 
 struct FkArgs
@@ -111,10 +112,10 @@ cudaError_t launchContacts(const ContactArgs& a, int grid, int block, size_t sme
 // fast_check.cu: the FP32 pass for groups of fixed / revolute / prismatic joints (a.model = the fast blob)
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
-int fastCheckKernelRegs(int field_bytes);
+int fastCheckKernelRegs(int field_bytes, int n_group_vars);
 int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs);
 int fastCheckMaxVars();
-int fastCheckMaxWarps();  // __launch_bounds__ of the fast kernel
+int fastCheckMaxWarps(int n_group_vars);  // __launch_bounds__ of the fast kernel instance that takes the group
 int fastCheckUnroll();
 cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_bytes, cudaStream_t stream);
