@@ -330,8 +330,8 @@ def main():
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch over 1 M states, from the committed
                      # ncu --set full capture (profiles/r1_fast_v13_summary.txt: 65.58 MB + 3.92 MB), scaled to n: the
                      # 16 MB field and the transform scratch are L2-resident, DRAM sees the states streaming in once
-                     "traffic": 69.51 * n if args.workload == "C2" else None,
-                     "traffic_source": "profiles/r1_fast_v13_summary.txt (ncu --set full, 1 launch)",
+                     "traffic": 69.06 * n if args.workload == "C2" else None,
+                     "traffic_source": "profiles/r1_fast_v14_summary.txt (ncu --set full, 1 launch)",
                      "peak_source": peak_src, "algorithmic_bytes_per_state": b_state,
                      "kernel": "fastCheckKernel<uint8_t,true> (+ the exact recheck launch recheckWarpKernel<uint8_t>)"},
         "gather_roofline": {"achieved": gather_achieved, "peak": gather_gbs, "unit": "GB/s (32 B sectors)",
