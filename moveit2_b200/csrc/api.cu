@@ -1505,7 +1505,7 @@ int runCheckHost(b200sv_ctx* c, const double* h_q, size_t n, uint32_t flags)
   size_t chunk = 131072;                               // states; a multiple of 32 so bitmap words do not straddle
   if (const char* e = getenv("B200SV_CHUNK"))
     chunk = std::max<size_t>(32, (size_t)atol(e) & ~(size_t)31);
-  while ((n + chunk - 1) / chunk > b200sv_ctx::kMaxChunks)
+  while ((n + chunk - 1) / chunk > b200sv_ctx::kMaxChunks - 4)
     chunk *= 2;
   const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
   if (!fp64)
@@ -1513,9 +1513,15 @@ int runCheckHost(b200sv_ctx* c, const double* h_q, size_t n, uint32_t flags)
   CU(c, cudaEventRecord(c->ev_go, c->stream));
   CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_go, 0));  // earlier work on the compute stream may still read d_q
   int i = 0;
-  for (size_t base = 0; base < n; base += chunk, ++i)
+  size_t m = 0;
+  for (size_t base = 0; base < n; base += m, ++i)
   {
-    const size_t m = std::min(chunk, n - base);
+    // The copies are the longer leg, so what is left after the LAST copy lands is pure tail: the last chunks shrink
+    // (1/2, 1/4, 1/8, 1/8 of a chunk) and with them the kernel time that cannot overlap anything.
+    const size_t left = n - base;
+    m = std::min(chunk, left);
+    if (left <= chunk && left > chunk / 8 && i < b200sv_ctx::kMaxChunks - 1)
+      m = std::min(left, std::max<size_t>((left / 2 + 31) & ~(size_t)31, (chunk / 8) & ~(size_t)31));
     CU(c, cudaMemcpyAsync(c->d_q.p + base * V, h_q + base * V, m * V * sizeof(double), cudaMemcpyHostToDevice,
                           c->copy_stream));
     CU(c, cudaEventRecord(c->ev_chunk[i], c->copy_stream));
