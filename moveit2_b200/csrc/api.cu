@@ -2489,6 +2489,7 @@ int b200sv_collision_gradients(b200sv_ctx* c, const double* q, size_t n, double*
   a.self_enabled = c->d_g_self.p;
   a.n_glinks = (int)L;
   a.n_spheres = (int)S;
+  a.state_stride = c->state_stride_d;
   if (!c->d_sqrt_table)
   {  // PropagationDistanceField::initialize (propagation_distance_field.cpp:99-101)
     std::vector<double> table((size_t)c->grid.max_d2 + 1);

@@ -806,15 +806,17 @@ __device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t
 // hardware interleaves by lane, so the warp's accesses are coalesced and L1/L2 resident -- and are copied to the caller's
 // state-major arrays once at the end.  Working on the state-major arrays directly (a warp's 32 rows are S * 8 bytes apart)
 // cost a 32-byte sector per 8-byte access in the pair loops.
-constexpr int kGradMaxSpheres = 96, kGradMaxLinks = 64;
+constexpr int kGradMaxSpheres = 96, kGradMaxLinks = 64, kGradMaxStride = 352;  // stride: 28 links x 12 words + padding
 
 template <bool kLocal>
-__global__ void __launch_bounds__(64) gradientKernel(GradArgs a)
+__global__ void __launch_bounds__(128) gradientKernel(GradArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
   const ModelHeader<double>& h = *m.h;
-  double* T = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(threadIdx.x) * h.state_stride;
+  // the state's link transforms: local memory as well (shared memory held the kernel at 8 warps per SM)
+  double Tloc[kLocal ? kGradMaxStride : 1];
+  double* T = kLocal ? Tloc : reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(threadIdx.x) * h.state_stride;
   const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
   if (i >= a.n_states)
     return;
@@ -1181,12 +1183,15 @@ cudaError_t launchSphereCenters(const FkArgs& a, double* d_centers, size_t smem_
 cudaError_t launchGradients(const GradArgs& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
   static SmemGrant gl, gg;
-  if (a.n_spheres <= kGradMaxSpheres && a.n_glinks <= kGradMaxLinks)
+  if (a.n_spheres <= kGradMaxSpheres && a.n_glinks <= kGradMaxLinks && a.state_stride <= kGradMaxStride)
   {
-    cudaError_t e = ensureSmem(gradientKernel<true>, smem_bytes, gl);
+    // everything per state in local memory: shared memory holds the model blob only, blocks of 128 threads
+    const size_t blob = (static_cast<size_t>(a.model_bytes) + 15) & ~static_cast<size_t>(15);
+    cudaError_t e = ensureSmem(gradientKernel<true>, blob, gl);
     if (e != cudaSuccess)
       return e;
-    gradientKernel<true><<<grid, block, smem_bytes, stream>>>(a);
+    const unsigned long long n = a.n_states;
+    gradientKernel<true><<<static_cast<unsigned>((n + 127) / 128), 128, blob, stream>>>(a);
   }
   else
   {

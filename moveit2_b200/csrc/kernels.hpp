@@ -69,7 +69,7 @@ struct GradArgs
   const uint16_t* nd2_world;  // signed fields: negative_distance_square_ per voxel; nullptr for unsigned fields
   const uint16_t* nd2_self;
   const uint8_t* self_enabled;  // [n_glinks]
-  int n_glinks, n_spheres;
+  int n_glinks, n_spheres, state_stride;  // state_stride: doubles of link transforms per state (the double blob's)
   const double* sqrt_table;  // [max_d2 + 1]: sqrt(double(i)) * resolution (PropagationDistanceField::sqrt_table_)
   double resolution, inv_twice_resolution, max_distance, max_propagation;
   double* distances;  // [n * n_spheres]
