@@ -115,7 +115,9 @@ def oracle_env(cfg, cloud):
         srdf = f.read()
     env = OracleEnv(RobotModel(urdf, srdf), cfg["group"], cfg["size"], cfg["origin"], cfg["resolution"],
                     cfg["max_distance"])
+    t = time.perf_counter()
     env.world.add_points(cloud)
+    env.world_build_s = time.perf_counter() - t  # the reference's bucket-queue propagation (oracle port, one thread)
     return env
 
 
@@ -350,6 +352,9 @@ def main():
         g, o = eng.field_get_d2(), env.world.d2()
         line["parity"] = {"edt_voxels": int(g.size), "edt_voxels_differing_from_reference_propagation": int((g != o).sum()),
                           "edt_gpu_above_reference": int((g > o).sum())}
+        edt_cpu = {"value": g.size / env.world_build_s, "unit": "voxels/s", "cores": 1, "kind": "port",
+                   "sample": "the %s field: %d points -> %d voxels by addPointsToField / propagatePositive (%.2f s; the "
+                             "propagation is serial by construction)" % (args.workload, len(cloud), g.size, env.world_build_s)}
         rate, used, ns, col = cpu_rate(env, q_host)
         line["cpu_baseline"] = {"value": rate, "unit": "states/s", "cores": used, "kind": "port",
                                 "sample": "first %d states of the step's batch, oracle lean flavour, OpenMP" % ns}
@@ -362,6 +367,7 @@ def main():
         eng.field_add_points(np.zeros((0, 3)))   # rebuild own field
     else:
         line["cpu_baseline"] = None
+        edt_cpu = None
 
     # ---- EDT voxels/s on C4 -----------------------------------------------------------------------------------------------
     if not args.no_edt:
@@ -389,7 +395,7 @@ def main():
         e2e_edt = time.perf_counter() - t0
         line["edt"] = {"metric": "edt_voxels_per_sec", "workload": "C4: 5M points -> 400x400x200 voxels @ 1 cm, max 25 cells",
                        "value": nv / (ms * 1e-3), "unit": "voxels/s", "ms": ms,
-                       "e2e_ms_host_points": 1e3 * e2e_edt,
+                       "e2e_ms_host_points": 1e3 * e2e_edt, "cpu_baseline": edt_cpu,
                        "roofline": {"bound": "hbm", "achieved": b_edt / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": b_edt / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_edt}}
         e4.close()
