@@ -358,6 +358,12 @@ def main():
         rate, used, ns, col = cpu_rate(env, q_host)
         line["cpu_baseline"] = {"value": rate, "unit": "states/s", "cores": used, "kind": "port",
                                 "sample": "first %d states of the step's batch, oracle lean flavour, OpenMP" % ns}
+        # the faithful flavour (what a CollisionEnvDistanceField call really does per state: GroupStateRepresentation copy,
+        # every interior point re-posed, 7-voxel reads) on a short sample, for context
+        nf = min(len(q_host), 20000)
+        t0 = time.perf_counter()
+        env.check(q_host[:nf], 7, faithful=True, threads=all_host_threads())
+        line["cpu_baseline"]["faithful_flavour_states_per_s"] = nf / (time.perf_counter() - t0)
         # validity on identical fields: inject the reference's own propagation result
         eng.field_set_d2(o, mb.FIELD_WORLD)
         eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
