@@ -608,7 +608,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
   const double half_slack = 2.0 * sqrt(3.0) * half_spacing + 0.01;
   // Hierarchical cull for robots with many cluster pairs: a LINK-level tight sphere per body is parked next to its
   // clusters' ("rep" = a parked centre: the body's clusters, then the body itself), link pairs are culled first.
-  // Measured on the dual-arm tree (profiles/r1_hier_cull_rates.txt): slower at 500 cluster pairs (0.94e9 vs 1.31e9
+  // Measured on the dual-arm tree (profiles/r1_hier_cull_rates.txt): slower at 278 cluster pairs (0.94e9 vs 1.31e9
   // states/s: too many link pairs survive for the expansion to pay), faster from ~1 700 pairs (3.6e8 vs 3.0e8).
   bool hier = pairs.size() > 1024;
   if (const char* e = getenv("B200SV_HIER"))
