@@ -80,6 +80,7 @@ struct b200sv_ctx
   bool fast_disabled = false;  // B200SV_FAST=0: force the generic FP32 kernel (A/B measurements)
   int state_stride_fast = 0, fast_t_rows = 0, fast_n_linkpairs = 0, fast_n_reps = 0;
   bool fast_t_global = false;  // link transforms in an L2-resident scratch instead of shared memory (large robots)
+  int fast_smem_blob_bytes = 0;  // bytes of the fast blob the kernel copies to shared memory
   float* d_t_scratch = nullptr;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
   double cluster_radius = 0.2;   // max tight-sphere radius of a sphere cluster (m); clusters also hold <= 4 spheres
@@ -733,7 +734,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     {
       const int ba = A.pad, bb = B.pad;
       const unsigned ab = (unsigned)body_rep[ba] | ((unsigned)body_rep[bb] << 16);
-      if (flp.empty() || flp.back().ab != ab || flp.back().ncp >= 32)
+      if (flp.empty() || flp.back().ab != ab || flp.back().ncp >= 16)
       {
         fast::LinkPair L{};
         const double rl = (body_tight[4 * ba + 3] + body_tight[4 * bb + 3] + tight_eps) * oo + half_slack;
@@ -775,6 +776,8 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
   off = align16(off + (int)(flp.size() * sizeof(fast::LinkPair)));
   h.n_linkpairs = (int)flp.size();
   c.fast_n_linkpairs = h.n_linkpairs;
+  // with the hierarchical cull the pair tables stay in global memory: shared memory holds the blob up to off_pairs
+  c.fast_smem_blob_bytes = h.n_linkpairs > 0 ? h.off_pairs : off;
   c.fast_n_reps = n_rep;
   h.total_bytes = off;
   h.state_stride = c.state_stride_fast;
@@ -1201,12 +1204,12 @@ int uploadTables(b200sv_ctx* c)
   {
     CU(c, cudaMalloc(&c->d_blob_fast, c->blob_fast.size()));
     CU(c, cudaMemcpy(c->d_blob_fast, c->blob_fast.data(), c->blob_fast.size(), cudaMemcpyHostToDevice));
-    c->cfg_fast = chooseCfg(c, false, false, (int)c->blob_fast.size(), true);
+    c->cfg_fast = chooseCfg(c, false, false, c->fast_smem_blob_bytes, true);
     c->fast_t_global = false;
     {  // large robots: with the transforms in shared memory only a few warps fit; move them to an L2-resident scratch
       const int keep = c->state_stride_fast;
       c->state_stride_fast = 0;
-      const b200sv_ctx::LaunchCfg g = chooseCfg(c, false, false, (int)c->blob_fast.size(), true);
+      const b200sv_ctx::LaunchCfg g = chooseCfg(c, false, false, c->fast_smem_blob_bytes, true);
       c->state_stride_fast = keep;
       const char* e = getenv("B200SV_T_GLOBAL");
       // measured on B200: the scratch variant is also the faster one when shared memory would fit 12 warps

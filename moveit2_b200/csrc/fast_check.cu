@@ -159,11 +159,16 @@ __device__ __forceinline__ void pose(const float* T, float x, float y, float z, 
   oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
 }
 
+// kHier (robots with thousands of cluster pairs): the pair, quirk and link-pair tables -- tens of KB, read with one index per
+// lane -- stay in global memory (L1 / L2 resident); shared memory holds the head of the blob only, which is what decides how
+// many warps fit next to it.
+template <bool kHier>
 __device__ __forceinline__ FModel loadFast(const uint8_t* __restrict__ g_model, int model_bytes, uint8_t* smem)
 {
   const int4* src = reinterpret_cast<const int4*>(g_model);
   int4* dst = reinterpret_cast<int4*>(smem);
-  for (int i = threadIdx.x; i < model_bytes / 16; i += blockDim.x)
+  const int copy_bytes = kHier ? reinterpret_cast<const fast::Header*>(g_model)->off_pairs : model_bytes;
+  for (int i = threadIdx.x; i < copy_bytes / 16; i += blockDim.x)
     dst[i] = src[i];
   __syncthreads();
   FModel m;
@@ -173,9 +178,10 @@ __device__ __forceinline__ FModel loadFast(const uint8_t* __restrict__ g_model, 
   m.ps = reinterpret_cast<const fast::PSphere*>(smem + m.h->off_psphere);
   m.cl = reinterpret_cast<const fast::Cluster*>(smem + m.h->off_clusters);
   m.groups = reinterpret_cast<const fast::Group*>(smem + m.h->off_groups);
-  m.pairs = reinterpret_cast<const fast::Pair*>(smem + m.h->off_pairs);
-  m.quirks = reinterpret_cast<const fast::Quirk*>(smem + m.h->off_quirks);
-  m.linkpairs = reinterpret_cast<const uint4*>(smem + m.h->off_linkpairs);
+  const uint8_t* tail = kHier ? g_model : smem;
+  m.pairs = reinterpret_cast<const fast::Pair*>(tail + m.h->off_pairs);
+  m.quirks = reinterpret_cast<const fast::Quirk*>(tail + m.h->off_quirks);
+  m.linkpairs = reinterpret_cast<const uint4*>(tail + m.h->off_linkpairs);
   return m;
 }
 
@@ -257,7 +263,7 @@ __device__ __host__ inline int queueBytes(int n_group_vars)
   return stage > kQueueCap * 4 ? stage : kQueueCap * 4;
 }
 
-constexpr int kQcCap = 1024;  // hierarchical cull: (state, cluster pair) candidates of one batch of link-pair survivors
+constexpr int kQcCap = 512;   // hierarchical cull: (state, cluster pair) candidates of one batch of link-pair survivors
 
 __device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs)
 {
@@ -278,11 +284,11 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
 {
   using Elem = typename Cmp<FT>::Elem;
   extern __shared__ __align__(16) uint8_t smem[];
-  const FModel m = loadFast(a.model, a.model_bytes, smem);
+  const FModel m = loadFast<kHier>(a.model, a.model_bytes, smem);
   const fast::Header& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int t_words = kTG ? 0 : h.state_stride;  // shared-memory words of transforms per state
-  uint8_t* wbase = smem + h.total_bytes +
+  uint8_t* wbase = smem + (kHier ? h.off_pairs : h.total_bytes) +
                    static_cast<size_t>(warp) * fastPerWarpBytes(t_words, h.n_clusters, h.n_group_vars, kHier ? h.n_linkpairs : 0);
   float* Ts = reinterpret_cast<float*>(wbase);
   TStore<kTG> ts;
@@ -706,7 +712,7 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
               if (lane >= d)
                 pos += t;
             }
-            const int total = __shfl_sync(kFull, pos, 31);  // <= 32 * 32: the host splits link pairs at 32 cluster pairs
+            const int total = __shfl_sync(kFull, pos, 31);  // <= 32 * 16: the host splits link pairs at 16 cluster pairs
             if (qcn + total > kQcCap)
               drainC();
             pos += qcn - ncp;
