@@ -1280,8 +1280,8 @@ int initGrid(b200sv_ctx* c)
   g.nz = n[2];
   g.wz = (g.nz + 31) / 32;
   const double rc = ceil(f.max_propagation_distance / res);  // propagation_distance_field.cpp:88
-  if (rc > 254.0)
-    return fail(c, B200SV_ERR_UNSUPPORTED, "max_propagation_distance / resolution exceeds 254 cells");
+  if (rc > 180.0)  // the EDT works in 16-bit lanes: (R + 1)^2 + R^2 must stay below 2^16 (edt_kernels.cu)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "max_propagation_distance / resolution exceeds 180 cells");
   g.R = (int)rc;
   g.max_d2 = (int)(rc * rc);
   c->n_voxels = (size_t)g.nx * g.ny * g.nz;
