@@ -66,6 +66,10 @@ def test_bad_inputs_are_errors():
         mb.StateValidityEngine.for_robot("panda", "nope", size=(1, 1, 1), origin=(0, 0, 0.5), resolution=0.02,
                                          max_distance=0.25, device=mb.DEVICE_NONE)
     assert e.value.code == _lib.ERR_INVALID
+    with pytest.raises(mb.B200svError) as e:  # 250 propagation cells: beyond the EDT's 16-bit lanes
+        mb.StateValidityEngine.for_robot("panda", "panda_arm", size=(0.2, 0.2, 0.2), origin=(0, 0, 0.5), resolution=0.001,
+                                         max_distance=0.25, device=mb.DEVICE_NONE)
+    assert e.value.code == _lib.ERR_UNSUPPORTED
     # signed fields: the thresholds of the integer predicate exist unless tolerance > radius + resolution
     eng = mb.StateValidityEngine.for_robot("panda", "panda_arm", size=(1, 1, 1), origin=(0, 0, 0.5), resolution=0.02,
                                            max_distance=0.25, device=mb.DEVICE_NONE, signed=True)
