@@ -154,3 +154,22 @@ def test_reference_interface_mirror_gates_on_group():
     assert env.distanceSelf() == 0.0 and env.distanceRobot() == 0.0
     bm = env.checkCollisionBatch(mb.CollisionRequest(group_name="other"), np.zeros((10, 7)))
     assert bm.tolist() == [0xFF, 0xFF]
+
+
+def test_header_is_plain_c_and_links(resources, tmp_path):
+    """include/b200sv.h compiles as C99 (-pedantic -Werror) and a C program drives the library through it alone."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    _lib.load()  # fails loudly if the library is not built
+    exe = str(tmp_path / "c_abi_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "c_abi_check.c"), "-L", libdir, "-lb200sv", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, os.path.join(resources, "panda_spheres.urdf"), os.path.join(resources, "panda.srdf")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c abi ok" in out.stdout and "no CPU fallback" in out.stdout
