@@ -1460,7 +1460,10 @@ int launchMain(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t ba
     a.t_scratch = c->fast_t_global ? c->d_t_scratch : nullptr;
     a.hier = c->fast_n_linkpairs > 0;
     a.n_group_vars = (int)c->robot.group_var_index.size();
-    CU(c, launchFastCheck<FT>(a, c->sm_count * k.blocks_per_sm, k.warps * 32, k.smem, s));
+    // persistent grid, but no more CTAs than there are tiles of 32 states to hand out (small batches: latency)
+    const size_t tiles = (n + 31) / 32, ctas_needed = (tiles + k.warps - 1) / k.warps;
+    const int grid = (int)std::min<size_t>((size_t)c->sm_count * k.blocks_per_sm, std::max<size_t>(1, ctas_needed));
+    CU(c, launchFastCheck<FT>(a, grid, k.warps * 32, k.smem, s));
     return B200SV_OK;
   }
   const b200sv_ctx::LaunchCfg& k = fp64 ? c->cfg_d : c->cfg_f;
@@ -1480,7 +1483,8 @@ int launchRecheck(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t
   a.model_bytes = (int)c->blob_d.size();
   static const bool warp_per_state = !(getenv("B200SV_RECHECK_WARP") && atoi(getenv("B200SV_RECHECK_WARP")) == 0);
   if (warp_per_state && (size_t)align16(a.model_bytes) + 4 * (size_t)c->state_stride_d * 8 <= (size_t)c->smem_optin)
-    CU(c, launchRecheckWarp<FT>(a, c->sm_count * 2, c->state_stride_d, s));
+    CU(c, launchRecheckWarp<FT>(a, (int)std::min<size_t>((size_t)c->sm_count * 2, std::max<size_t>(1, (n_total + 3) / 4)),
+                                c->state_stride_d, s));  // 4 warps per CTA, one listed state per warp: never more CTAs than states / 4
   else
     CU(c, launchCheck<FT>(a, true, true, c->sm_count * c->cfg_list.blocks_per_sm, c->cfg_list.warps * 32,
                           c->cfg_list.smem, s));
