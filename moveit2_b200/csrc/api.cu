@@ -81,6 +81,7 @@ struct b200sv_ctx
   int state_stride_fast = 0, fast_t_rows = 0, fast_n_linkpairs = 0, fast_n_reps = 0;
   bool fast_t_global = false;  // link transforms in an L2-resident scratch instead of shared memory (large robots)
   int fast_smem_blob_bytes = 0;  // bytes of the fast blob the kernel copies to shared memory
+  bool fast_wide = false;        // the group takes the wide instance of the fast kernel (> 16 variables or a planar joint)
   float* d_t_scratch = nullptr;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
   double cluster_radius = 0.2;   // max tight-sphere radius of a sphere cluster (m); clusters also hold <= 4 spheres
@@ -323,9 +324,24 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
                    double bs_eps, double tight_eps)
 {
   c.blob_fast.clear();
+  c.fast_wide = (int)c.robot.group_var_index.size() > fastCheckRegisterPrefetchVars();
   for (const auto& L : links_in)
-    if (L.type != FIXED && L.type != REVOLUTE && L.type != PRISMATIC)
+  {
+    if (L.type == PLANAR)
+    {
+      // a planar joint the group moves: its three variables must be plain, consecutive group variables (no mimic); one the
+      // group does not move is a constant link (folded below, or a root: converted to a fixed origin)
+      const VarRec &vx = vars[L.var], &vy = vars[L.var + 1], &vt = vars[L.var + 2];
+      const bool moving = vx.k >= 0 || vy.k >= 0 || vt.k >= 0;
+      if (moving && !(vx.k >= 0 && vy.k == vx.k + 1 && vt.k == vx.k + 2 && vx.a == 1.0 && vy.a == 1.0 && vt.a == 1.0 &&
+                      vx.b == 0.0 && vy.b == 0.0 && vt.b == 0.0))
+        return false;
+      if (moving)
+        c.fast_wide = true;
+    }
+    else if (L.type != FIXED && L.type != REVOLUTE && L.type != PRISMATIC)
       return false;
+  }
   if ((int)c.robot.group_var_index.size() > fastCheckMaxVars())
     return false;
   const int unroll = fastCheckUnroll();
@@ -369,7 +385,8 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
   {
     const LinkRec<double>& L = links_in[l];
     const int P = L.parent;  // device links are in DFS pre-order: P < l
-    const bool constant = L.type == FIXED || vars[L.var].k < 0;
+    const bool constant = L.type == FIXED || (L.type == PLANAR ? (vars[L.var].k < 0 && vars[L.var + 1].k < 0 && vars[L.var + 2].k < 0) :
+                                                                 vars[L.var].k < 0);
     if (constant && P >= 0)
     {
       // local transform origin * joint(value): Rodrigues rotation (revolute_joint_model.cpp:250-287) or a translation along
@@ -379,7 +396,14 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
       if (L.type != FIXED)
       {
         const double q = vars[L.var].b, x = L.ax[0], y = L.ax[1], z = L.ax[2];
-        if (L.type == REVOLUTE)
+        if (L.type == PLANAR)
+        {  // Translation(x, y, 0) * AngleAxis(theta, UnitZ) (planar_joint_model.cpp:345-349)
+          const double th = vars[L.var + 2].b, cs = cos(th), sn = sin(th);
+          J.m[0] = cs; J.m[1] = -sn; J.m[4] = sn; J.m[5] = cs;
+          J.m[3] = vars[L.var].b;
+          J.m[7] = vars[L.var + 1].b;
+        }
+        else if (L.type == REVOLUTE)
         {
           const double cs = cos(q), sn = sin(q), t = 1.0 - cs;
           const double R[9] = { t * x * x + cs, t * x * y - z * sn, t * x * z + y * sn, t * x * y + z * sn, t * y * y + cs,
@@ -504,7 +528,8 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
       for (int r = 0; r < 3; ++r)
         ot[r] = (ot[r] - c.grid.om[r]) * oo;
     }
-    const double x = L.ax[0], y = L.ax[1], z = L.ax[2];
+    const bool planar = L.type == PLANAR;  // its rotation is about the joint frame's z
+    const double x = planar ? 0.0 : L.ax[0], y = planar ? 0.0 : L.ax[1], z = planar ? 1.0 : L.ax[2];
     const double K[9] = { 0, -z, y, z, 0, -x, -y, x, 0 };
     double K2[9], OK[9], OK2[9];
     for (int r = 0; r < 3; ++r)
@@ -535,7 +560,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     }
     for (int r = 0; r < 3; ++r)
       F.ot[r] = (float)ot[r];
-    if (L.type == REVOLUTE)
+    if (L.type == REVOLUTE || planar)
       for (int i = 0; i < 9; ++i)
       {
         F.a1[i] = (float)OK[i];
@@ -593,10 +618,10 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     }
     else
       r = reach[L.parent] + sqrt(ot[0] * ot[0] + ot[1] * ot[1] + ot[2] * ot[2]) * oo;
-    if (L.type == PRISMATIC)
+    if (L.type == PRISMATIC || L.type == PLANAR)
       r += 2.0 * oo;  // assumed travel; the kernel verifies it (Link::range_check) and defers to the exact pass beyond
     reach[l] = r;
-    fl[l].range_check = (L.type == PRISMATIC || (L.parent >= 0 && fl[L.parent].range_check)) ? 1 : 0;
+    fl[l].range_check = (L.type == PRISMATIC || L.type == PLANAR || (L.parent >= 0 && fl[L.parent].range_check)) ? 1 : 0;
   }
   for (size_t i = 0; i < bs.size(); ++i)
   {
@@ -1460,6 +1485,7 @@ int launchMain(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t ba
     a.t_scratch = c->fast_t_global ? c->d_t_scratch : nullptr;
     a.hier = c->fast_n_linkpairs > 0;
     a.n_group_vars = (int)c->robot.group_var_index.size();
+    a.wide = c->fast_wide ? 1 : 0;
     // persistent grid, but no more CTAs than there are tiles of 32 states to hand out (small batches: latency)
     const size_t tiles = (n + 31) / 32, ctas_needed = (tiles + k.warps - 1) / k.warps;
     const int grid = (int)std::min<size_t>((size_t)c->sm_count * k.blocks_per_sm, std::max<size_t>(1, ctas_needed));

@@ -275,9 +275,13 @@ __device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters
 // kV: group variables the register prefetch covers.  Groups of at most kSmallVars variables (an arm) get their own
 // instance: 16 prefetch registers fewer, and launch bounds that fit 3 CTAs x 6 warps per SM at 96 registers instead of
 // 2 x 8 at 128 (+4.7 % on C2, measured; the 16-variable instance loses with the tighter bounds).
+// kV == 0 is the WIDE instance: groups with more than 16 variables or with a planar joint (a mobile base: the dual arm's
+// whole_body group has 18).  No register prefetch -- the next tile's states are pulled into L2 one tile ahead and read at the
+// start of their tile -- and the link loop knows PLANAR joints (Translation(x, y, 0) * Rz(theta), planar_joint_model.cpp:345-349).
 constexpr int kSmallVars = 8;
-constexpr int fastThreads(int kV) { return kV <= kSmallVars ? B200SV_FAST_THREADS_SMALL : B200SV_FAST_THREADS; }
-constexpr int fastMinBlocks(int kV) { return kV <= kSmallVars ? B200SV_FAST_MINBLOCKS_SMALL : B200SV_FAST_MINBLOCKS; }
+constexpr int kWideMaxVars = 32;
+constexpr int fastThreads(int kV) { return (kV > 0 && kV <= kSmallVars) ? B200SV_FAST_THREADS_SMALL : B200SV_FAST_THREADS; }
+constexpr int fastMinBlocks(int kV) { return (kV > 0 && kV <= kSmallVars) ? B200SV_FAST_MINBLOCKS_SMALL : B200SV_FAST_MINBLOCKS; }
 
 template <typename FT, bool kTG, bool kHier, int kV>
 __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckKernel(CheckArgs<FT> a)
@@ -315,16 +319,24 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   const int V = h.n_group_vars;
   // The states of a tile are ONE contiguous run of 32 * V doubles: every lane reads V of them, coalesced, one tile
   // AHEAD (they stream from HBM exactly once), and parks them in shared memory when their tile starts.
-  double qn[kV];
+  double qn[kV > 0 ? kV : 1];
   auto fetchTile = [&](unsigned long long t) {
     const double* __restrict__ src = a.q + t * 32 * V;
     const unsigned long long left = n - t * 32;
     const int avail = static_cast<int>(left < 32 ? left : 32) * V;
-#pragma unroll
-    for (int j = 0; j < kV; ++j)
+    if constexpr (kV > 0)
     {
-      const int e = j * 32 + lane;
-      qn[j] = (j < V && e < avail) ? __ldg(src + e) : 0.0;
+#pragma unroll
+      for (int j = 0; j < kV; ++j)
+      {
+        const int e = j * 32 + lane;
+        qn[j] = (j < V && e < avail) ? __ldg(src + e) : 0.0;
+      }
+    }
+    else
+    {  // wide instance: one 128-byte line per lane and pass, into L2
+      for (int e = lane * 16; e < avail; e += 32 * 16)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + e));
     }
   };
   const unsigned long long tile0 = static_cast<unsigned long long>(blockIdx.x) * warps + warp;
@@ -332,10 +344,21 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
     fetchTile(tile0);
   for (unsigned long long tile = tile0; tile < n_tiles; tile += static_cast<unsigned long long>(gridDim.x) * warps)
   {
+    if constexpr (kV > 0)
+    {
 #pragma unroll
-    for (int j = 0; j < kV; ++j)
-      if (j < V)
-        stage[j * 32 + lane] = qn[j];
+      for (int j = 0; j < kV; ++j)
+        if (j < V)
+          stage[j * 32 + lane] = qn[j];
+    }
+    else
+    {
+      const double* __restrict__ src = a.q + tile * 32 * V;
+      const unsigned long long left = n - tile * 32;
+      const int avail = static_cast<int>(left < 32 ? left : 32) * V;
+      for (int e = lane; e < 32 * V; e += 32)
+        stage[e] = e < avail ? __ldg(src + e) : 0.0;
+    }
     __syncwarp();
     {
       const unsigned long long nt = tile + static_cast<unsigned long long>(gridDim.x) * warps;
@@ -464,6 +487,24 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
             const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
             float s, c;
             sincosf(qf, &s, &c);
+            const float t = 1.f - c;
+#pragma unroll
+            for (int i = 0; i < 9; ++i)
+              M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
+          }
+          else if (kV == 0 && m0.x == PLANAR)
+          {  // variables k, k + 1, k + 2 of the group state = x, y, theta (the host checked a = 1, b = 0 for all three);
+             // [O | ot] * [Rz(theta) | (x, y, 0)] = [A0 + s A1 + t A2 (axis z) | ot + x O(:,0) + y O(:,1)]
+            const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];
+            const float A1[9] = { c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w, c4.x, c4.y };
+            const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
+            const float px = static_cast<float>(qrow[m0.y]), py = static_cast<float>(qrow[m0.y + 1]);
+            const float th = static_cast<float>(qrow[m0.y + 2]);
+            mt[0] = fmaf(px, M[0], fmaf(py, M[1], mt[0]));
+            mt[1] = fmaf(px, M[3], fmaf(py, M[4], mt[1]));
+            mt[2] = fmaf(px, M[6], fmaf(py, M[7], mt[2]));
+            float s, c;
+            sincosf(th, &s, &c);
             const float t = 1.f - c;
 #pragma unroll
             for (int i = 0; i < 9; ++i)
@@ -778,7 +819,8 @@ int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, in
 {
   return fastPerWarpBytes(state_stride, n_clusters, n_group_vars, n_linkpairs);
 }
-int fastCheckMaxVars() { return kMaxVars; }
+int fastCheckMaxVars() { return kWideMaxVars; }
+int fastCheckRegisterPrefetchVars() { return kMaxVars; }  // beyond this (or with a planar joint) the wide instance runs
 int fastCheckMaxWarps(int n_group_vars) { return fastThreads(n_group_vars <= kSmallVars ? kSmallVars : kMaxVars) / 32; }
 int fastCheckUnroll() { return kU; }
 
@@ -803,13 +845,20 @@ int fastCheckKernelRegs(int field_bytes, int n_group_vars)
     small ? all(uint8_t(), std::integral_constant<int, kSmallVars>()) : all(uint8_t(), std::integral_constant<int, kMaxVars>());
   else
     small ? all(uint16_t(), std::integral_constant<int, kSmallVars>()) : all(uint16_t(), std::integral_constant<int, kMaxVars>());
+  if (!small)
+  {  // the wide instance shares the launch configuration of the 16-variable one
+    if (field_bytes == 1)
+      all(uint8_t(), std::integral_constant<int, 0>());
+    else
+      all(uint16_t(), std::integral_constant<int, 0>());
+  }
   return regs;
 }
 
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-  static Grant g[8];
+  static Grant g[12];
   auto go = [&](auto kernel, Grant& gr) {
     const cudaError_t e = ensure(kernel, smem_bytes, gr);
     if (e != cudaSuccess)
@@ -823,6 +872,8 @@ cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t 
       return a.t_scratch ? go(fastCheckKernel<FT, true, true, kV>, gr[3]) : go(fastCheckKernel<FT, false, true, kV>, gr[2]);
     return a.t_scratch ? go(fastCheckKernel<FT, true, false, kV>, gr[1]) : go(fastCheckKernel<FT, false, false, kV>, gr[0]);
   };
+  if (a.wide)
+    return pick(std::integral_constant<int, 0>(), g + 8);
   return a.n_group_vars <= kSmallVars ? pick(std::integral_constant<int, kSmallVars>(), g) :
                                         pick(std::integral_constant<int, kMaxVars>(), g + 4);
 }

@@ -35,6 +35,7 @@ struct CheckArgs
   float* t_scratch;      // fast pass only: global-memory home of the link transforms (null: shared memory)
   int hier;              // fast pass only: the blob carries LinkPair records (hierarchical cull)
   int n_group_vars;      // fast pass only: selects the kernel instance (register prefetch of the states)
+  int wide;              // fast pass only: the wide instance (more than 16 variables, or a planar joint in the group)
 };
 
 struct FkArgs
@@ -115,6 +116,7 @@ cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t 
 int fastCheckKernelRegs(int field_bytes, int n_group_vars);
 int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs);
 int fastCheckMaxVars();
+int fastCheckRegisterPrefetchVars();
 int fastCheckMaxWarps(int n_group_vars);  // __launch_bounds__ of the fast kernel instance that takes the group
 int fastCheckUnroll();
 cudaError_t launchFk(const FkArgs& a, bool fp64, int grid, int block, size_t smem_bytes, cudaStream_t stream);
