@@ -43,9 +43,9 @@ def parse():
     ap.add_argument("--no-edt", action="store_true", help="skip the C4 EDT rebuild measurement")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against the oracle")
     ap.add_argument("--fp64", action="store_true", help="force every state through the FP64 kernel")
-    ap.add_argument("--workload", default=WORKLOAD, choices=["C2", "C3", "C3D"],
-                    help="C2 (default, the config the metric is quoted on), C3 (dual arm, 10 M states over all ranks) or C3D (C3 with the "
-                         "dual arm at 280 spheres)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["C2", "C3", "C3D", "C3W"],
+                    help="C2 (default, the config the metric is quoted on), C3 (dual arm, 10 M states over all ranks) C3D (C3 with the "
+                         "dual arm at 280 spheres) or C3W (C3 with the whole_body group: planar base, 18 variables)")
     return ap.parse_args()
 
 

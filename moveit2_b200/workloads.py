@@ -78,6 +78,11 @@ CONFIGS = {
                 max_distance=0.25, cloud=dict(seed=6, n_points=200_000, n_boxes=30, lo=(-1.3, -1.3, 0.1),
                                               hi=(1.3, 1.3, 2.0), keepout_radius=0.75),
                 states=dict(seed=4, n=10_000_000)),
+    # C3W: the C3 scene, the dual arm's whole_body group (planar base + torso + both arms: 18 variables, 93 spheres)
+    "C3W": dict(robot="dualarm", group="whole_body", size=(3.0, 3.0, 2.5), origin=(0.0, 0.0, 1.0), resolution=0.02,
+                max_distance=0.25, cloud=dict(seed=6, n_points=200_000, n_boxes=30, lo=(-1.3, -1.3, 0.1),
+                                              hi=(1.3, 1.3, 2.0), keepout_radius=0.75),
+                states=dict(seed=4, n=10_000_000)),
     # C4: EDT rebuild only -- 5 M points uniform in a 4 x 4 x 2 m box, 400 x 400 x 200 voxels at 1 cm
     "C4": dict(size=(4.0, 4.0, 2.0), origin=(0.0, 0.0, 1.0), resolution=0.01, max_distance=0.25,
                cloud=dict(seed=5, n_points=5_000_000)),
