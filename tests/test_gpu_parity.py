@@ -880,3 +880,32 @@ def test_validity_with_cylinder_and_box_link_geometry(group):
     for s in q[:8]:
         assert np.abs(eng.sphere_centers(s) - env.sphere_centers(s).reshape(-1, 3)).max() < 1e-12
     eng.close()
+
+
+# ---- a floating joint in the group (a free-flying base): floating_joint_model.cpp:231-236 ------------------------------------
+@pytest.mark.gpu
+def test_validity_and_fk_with_a_floating_joint_in_the_group():
+    from oracle.collision_model import OracleEnv
+    from oracle.robot_model import RobotModel
+    from util import RES, ROBOT_FILES, read
+    u, s = ROBOT_FILES["panda"]
+    urdf = read(RES, u)
+    srdf = read(RES, s).replace("</robot>", '<group name="panda_free"><joint name="virtual_joint"/><group name="panda_arm"/></group></robot>')
+    cfg = workloads.CONFIGS["C2"]
+    eng = mb.StateValidityEngine.from_urdf(urdf, srdf, "panda_free", cfg["size"], cfg["origin"], 0.02, cfg["max_distance"])
+    env = OracleEnv(RobotModel(urdf, srdf), "panda_free", cfg["size"], cfg["origin"], 0.02, cfg["max_distance"])
+    assert eng.n_group_vars == 14
+    cloud = workloads.make_cloud("C2")[::10]
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(12, 30000, lo, hi)   # translations in a 1 m box, un-normalised quaternions (the joint normalises)
+    t = eng.fk_batch(q[:64], 64)
+    assert np.abs(t - env.fk(q[:64])).max() < 1e-9
+    assert np.abs(eng.fk_batch(q[:64], 32) - env.fk(q[:64])).max() < 1e-5
+    for flags in (W, S, I, ALL):
+        ref, _ = env.check(q, flags)
+        assert np.array_equal(eng.check_batch(q, flags), ref == 0), flags
+    assert 0.05 < ref.mean() < 0.95
+    eng.close()
