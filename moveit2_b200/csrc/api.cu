@@ -339,6 +339,15 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
       if (moving)
         c.fast_wide = true;
     }
+    else if (L.type == FLOATING)
+    {  // seven plain, consecutive group variables (x, y, z, then the quaternion x, y, z, w); a constant one is not folded: generic
+      bool ok = true;
+      for (int k = 0; k < 7; ++k)
+        ok = ok && vars[L.var + k].k == vars[L.var].k + k && vars[L.var].k >= 0 && vars[L.var + k].a == 1.0 && vars[L.var + k].b == 0.0;
+      if (!ok)
+        return false;
+      c.fast_wide = true;
+    }
     else if (L.type != FIXED && L.type != REVOLUTE && L.type != PRISMATIC)
       return false;
   }
@@ -618,10 +627,11 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     }
     else
       r = reach[L.parent] + sqrt(ot[0] * ot[0] + ot[1] * ot[1] + ot[2] * ot[2]) * oo;
-    if (L.type == PRISMATIC || L.type == PLANAR)
+    if (L.type == PRISMATIC || L.type == PLANAR || L.type == FLOATING)
       r += 2.0 * oo;  // assumed travel; the kernel verifies it (Link::range_check) and defers to the exact pass beyond
     reach[l] = r;
-    fl[l].range_check = (L.type == PRISMATIC || L.type == PLANAR || (L.parent >= 0 && fl[L.parent].range_check)) ? 1 : 0;
+    fl[l].range_check =
+        (L.type == PRISMATIC || L.type == PLANAR || L.type == FLOATING || (L.parent >= 0 && fl[L.parent].range_check)) ? 1 : 0;
   }
   for (size_t i = 0; i < bs.size(); ++i)
   {

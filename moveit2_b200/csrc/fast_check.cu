@@ -510,6 +510,30 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
             for (int i = 0; i < 9; ++i)
               M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
           }
+          else if (kV == 0 && m0.x == FLOATING)
+          {  // variables k .. k + 6 = translation, then the quaternion x, y, z, w, normalised by the joint
+             // (floating_joint_model.cpp:231-236); [O | ot] * [R(q) | p] = [O R(q) | ot + O p]
+            const float px = static_cast<float>(qrow[m0.y]), py = static_cast<float>(qrow[m0.y + 1]),
+                        pz = static_cast<float>(qrow[m0.y + 2]);
+            float x = static_cast<float>(qrow[m0.y + 3]), y = static_cast<float>(qrow[m0.y + 4]),
+                  z = static_cast<float>(qrow[m0.y + 5]), w = static_cast<float>(qrow[m0.y + 6]);
+            const float inv = 1.f / sqrtf(fmaf(x, x, fmaf(y, y, fmaf(z, z, w * w))));
+            x *= inv; y *= inv; z *= inv; w *= inv;
+            const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+            const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y,
+                        tyz = tz * y, tzz = tz * z;
+            const float Rq[9] = { 1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx,
+                                  txz - twy, tyz + twx, 1.f - (txx + tyy) };
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+            {
+              const float o0 = M[3 * r], o1 = M[3 * r + 1], o2 = M[3 * r + 2];
+              mt[r] = fmaf(o0, px, fmaf(o1, py, fmaf(o2, pz, mt[r])));
+              M[3 * r + 0] = fmaf(o0, Rq[0], fmaf(o1, Rq[3], o2 * Rq[6]));
+              M[3 * r + 1] = fmaf(o0, Rq[1], fmaf(o1, Rq[4], o2 * Rq[7]));
+              M[3 * r + 2] = fmaf(o0, Rq[2], fmaf(o1, Rq[5], o2 * Rq[8]));
+            }
+          }
           else
           {  // PRISMATIC
             mt[0] = fmaf(qf, c2.y, mt[0]);
