@@ -96,6 +96,7 @@ struct b200sv_ctx
   uint16_t* d_tmp = nullptr;  // EDT intermediate
   double* d_sqrt_table = nullptr;  // sqrt_table_ of the reference's field (gradient kernel)
   uint8_t* h_small = nullptr;      // pinned staging of the small-batch (latency) path of b200sv_check_batch
+  uint32_t* d_small = nullptr;     // its device-side result: 128 bitmap words, then the recheck counter
   size_t h_small_bytes = 0;
   void* d_combined = nullptr; // interleaved compact field {world, self} per voxel
   // launch config
@@ -1698,6 +1699,7 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->d_tmp) cudaFree(c->d_tmp);
   if (c->d_sqrt_table) cudaFree(c->d_sqrt_table);
   if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->d_small) cudaFree(c->d_small);
   if (c->d_blob_f) cudaFree(c->d_blob_f);
   if (c->d_blob_d) cudaFree(c->d_blob_d);
   if (c->d_blob_fast) cudaFree(c->d_blob_fast);
@@ -2364,21 +2366,32 @@ int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags,
       c->h_small_bytes = q_bytes + out_bytes;
     }
     uint8_t* h_out = c->h_small + q_bytes;
+    // bitmap words and the recheck counter side by side in device memory: ONE copy back instead of two
+    if (!c->d_small)
+      CU(c, cudaMalloc(&c->d_small, kSmallBatch / 8 + 16));
+    uint32_t* d_small_bitmap = c->d_small;
+    unsigned* const count_saved = c->d_count;
+    c->d_count = c->d_small + kSmallBatch / 32;
+    struct Restore
+    {
+      b200sv_ctx* c;
+      unsigned* p;
+      ~Restore() { c->d_count = p; }
+    } restore{ c, count_saved };
     memcpy(c->h_small, q, n * V * sizeof(double));
     const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
     if (!fp64)
       CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream));
     const auto t_small = std::chrono::steady_clock::now();  // no timing events on the latency path: three API calls fewer
     CU(c, cudaMemcpyAsync(c->d_q.p, c->h_small, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    int rc = c->compact_bytes == 1 ? launchMain<uint8_t>(c, c->d_q.p, c->d_bitmap.p, 0, n, flags, c->stream) :
-                                     launchMain<uint16_t>(c, c->d_q.p, c->d_bitmap.p, 0, n, flags, c->stream);
+    int rc = c->compact_bytes == 1 ? launchMain<uint8_t>(c, c->d_q.p, d_small_bitmap, 0, n, flags, c->stream) :
+                                     launchMain<uint16_t>(c, c->d_q.p, d_small_bitmap, 0, n, flags, c->stream);
     if (rc == B200SV_OK && !fp64)
-      rc = c->compact_bytes == 1 ? launchRecheck<uint8_t>(c, c->d_q.p, c->d_bitmap.p, n, flags, c->stream) :
-                                   launchRecheck<uint16_t>(c, c->d_q.p, c->d_bitmap.p, n, flags, c->stream);
+      rc = c->compact_bytes == 1 ? launchRecheck<uint8_t>(c, c->d_q.p, d_small_bitmap, n, flags, c->stream) :
+                                   launchRecheck<uint16_t>(c, c->d_q.p, d_small_bitmap, n, flags, c->stream);
     if (rc != B200SV_OK)
       return rc;
-    CU(c, cudaMemcpyAsync(h_out, c->d_bitmap.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(h_out + kSmallBatch / 8, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h_out, c->d_small, kSmallBatch / 8 + sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     memcpy(valid_bitmap, h_out, (n + 7) / 8);
     memcpy(&cnt, h_out + kSmallBatch / 8, sizeof(unsigned));
