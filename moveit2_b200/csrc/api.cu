@@ -97,6 +97,8 @@ struct b200sv_ctx
   double* d_sqrt_table = nullptr;  // sqrt_table_ of the reference's field (gradient kernel)
   uint8_t* h_small = nullptr;      // pinned staging of the small-batch (latency) path of b200sv_check_batch
   uint32_t* d_small = nullptr;     // its device-side result: 128 bitmap words, then the recheck counter
+  std::vector<double> edge_factor_cached;  // what d_edge_aux / d_edge_cont hold (b200sv_check_motions re-uploads on change)
+  std::vector<uint8_t> edge_cont_cached;
   size_t h_small_bytes = 0;
   void* d_combined = nullptr; // interleaved compact field {world, self} per voxel
   // launch config
@@ -2327,6 +2329,21 @@ int b200sv_check_batch_device(b200sv_ctx* c, const double* d_q, size_t n, uint32
   return rc;
 }
 
+// pinned staging of the latency paths (single states, single edges): the context's own, so no copy of a small call falls
+// back to the driver's pageable staging
+static int ensureSmallStaging(b200sv_ctx* c, size_t bytes)
+{
+  if (c->h_small_bytes >= bytes)
+    return B200SV_OK;
+  if (c->h_small)
+    cudaFreeHost(c->h_small);
+  c->h_small = nullptr;
+  c->h_small_bytes = 0;
+  CU(c, cudaHostAlloc(&c->h_small, bytes, cudaHostAllocDefault));
+  c->h_small_bytes = bytes;
+  return B200SV_OK;
+}
+
 int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags, uint8_t* valid_bitmap)
 {
   if (!c)
@@ -2356,15 +2373,8 @@ int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags,
     // Latency path (a single-state checkCollision through the plugin is a batch of 1): everything on one stream, states and
     // results staged through the context's own pinned buffer, so no copy falls back to the driver's pageable staging.
     const size_t q_bytes = kSmallBatch * V * sizeof(double), out_bytes = kSmallBatch / 8 + 16;
-    if (c->h_small_bytes < q_bytes + out_bytes)
-    {
-      if (c->h_small)
-        cudaFreeHost(c->h_small);
-      c->h_small = nullptr;
-      c->h_small_bytes = 0;
-      CU(c, cudaHostAlloc(&c->h_small, q_bytes + out_bytes, cudaHostAllocDefault));
-      c->h_small_bytes = q_bytes + out_bytes;
-    }
+    if (int rc = ensureSmallStaging(c, q_bytes + out_bytes))
+      return rc;
     uint8_t* h_out = c->h_small + q_bytes;
     // bitmap words and the recheck counter side by side in device memory: ONE copy back instead of two
     if (!c->d_small)
@@ -2464,13 +2474,41 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
   CU(c, c->d_edge_cont.ensure(V));
   CU(c, c->d_edge_bits.ensure((n_edges + 31) / 32));
   CU(c, c->d_edge_first.ensure(n_edges));
-  CU(c, cudaEventRecord(c->ev0, s));
-  CU(c, cudaMemcpyAsync(c->d_edges.p, q_from, n_edges * V * sizeof(double), cudaMemcpyHostToDevice, s));
-  CU(c, cudaMemcpyAsync(c->d_edges.p + n_edges * V, q_to, n_edges * V * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (var_distance_factor)
-    CU(c, cudaMemcpyAsync(c->d_edge_aux.p, var_distance_factor, V * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (var_continuous)
-    CU(c, cudaMemcpyAsync(c->d_edge_cont.p, var_continuous, V, cudaMemcpyHostToDevice, s));
+  // Latency path (an OMPL MotionValidator validates ONE edge per checkMotion): both ends in one copy from the context's pinned
+  // staging, results back through it, no timing events; the group's metric (distance factors, continuous flags) is uploaded
+  // only when it changes.
+  constexpr size_t kSmallEdges = 64;
+  const bool small = n_edges <= kSmallEdges;
+  const size_t ends_bytes = 2 * n_edges * V * sizeof(double);
+  const auto t_small = std::chrono::steady_clock::now();
+  uint8_t* h_res = nullptr;  // small: [total (8) | count (4) | pad (4) | valid bits (8) | first_invalid (4 * 64)]
+  if (small)
+  {
+    const size_t stage_bytes = 2 * kSmallEdges * V * sizeof(double);
+    if (int rc = ensureSmallStaging(c, stage_bytes + 512))
+      return rc;
+    memcpy(c->h_small, q_from, ends_bytes / 2);
+    memcpy(c->h_small + ends_bytes / 2, q_to, ends_bytes / 2);
+    h_res = c->h_small + stage_bytes;
+    CU(c, cudaMemcpyAsync(c->d_edges.p, c->h_small, ends_bytes, cudaMemcpyHostToDevice, s));
+  }
+  else
+  {
+    CU(c, cudaEventRecord(c->ev0, s));
+    CU(c, cudaMemcpyAsync(c->d_edges.p, q_from, ends_bytes / 2, cudaMemcpyHostToDevice, s));
+    CU(c, cudaMemcpyAsync(c->d_edges.p + n_edges * V, q_to, ends_bytes / 2, cudaMemcpyHostToDevice, s));
+  }
+  if (var_distance_factor &&
+      (c->edge_factor_cached.size() != V || memcmp(c->edge_factor_cached.data(), var_distance_factor, V * sizeof(double)) != 0))
+  {
+    c->edge_factor_cached.assign(var_distance_factor, var_distance_factor + V);
+    CU(c, cudaMemcpyAsync(c->d_edge_aux.p, c->edge_factor_cached.data(), V * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  if (var_continuous && (c->edge_cont_cached.size() != V || memcmp(c->edge_cont_cached.data(), var_continuous, V) != 0))
+  {
+    c->edge_cont_cached.assign(var_continuous, var_continuous + V);
+    CU(c, cudaMemcpyAsync(c->d_edge_cont.p, c->edge_cont_cached.data(), V, cudaMemcpyHostToDevice, s));
+  }
   MotionArgs a{};
   a.q_from = c->d_edges.p;
   a.q_to = c->d_edges.p + n_edges * V;
@@ -2484,8 +2522,11 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
   a.offset = c->d_edge_offset.p;
   CU(c, launchMotionCount(a, s));
   unsigned long long total = 0;
-  CU(c, cudaMemcpyAsync(&total, c->d_edge_offset.p + n_edges, sizeof(total), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaMemcpyAsync(small ? static_cast<void*>(h_res) : static_cast<void*>(&total), c->d_edge_offset.p + n_edges, sizeof(total),
+                        cudaMemcpyDeviceToHost, s));
   CU(c, cudaStreamSynchronize(s));  // the state batch is sized by the edges' lengths
+  if (small)
+    memcpy(&total, h_res, sizeof(total));
   if (total >= (1ull << 32))
     return fail(c, B200SV_ERR_INVALID, "edges expand to more than 2^32 - 1 states; lower n_edges or set max_states_per_edge");
   CU(c, c->d_edge_q.ensure((size_t)total * V));
@@ -2495,15 +2536,31 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
   if (rc != B200SV_OK)
     return rc;
   CU(c, launchMotionReduce(a, c->d_edge_state_bits.p, c->d_edge_bits.p, first_invalid ? c->d_edge_first.p : nullptr, s));
-  CU(c, cudaEventRecord(c->ev1, s));
-  CU(c, cudaMemcpyAsync(valid_bitmap, c->d_edge_bits.p, (n_edges + 7) / 8, cudaMemcpyDeviceToHost, s));
-  if (first_invalid)
-    CU(c, cudaMemcpyAsync(first_invalid, c->d_edge_first.p, n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   unsigned cnt = 0;
-  CU(c, cudaMemcpyAsync(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-  CU(c, cudaStreamSynchronize(s));
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  if (small)
+  {
+    CU(c, cudaMemcpyAsync(h_res + 16, c->d_edge_bits.p, (n_edges + 7) / 8, cudaMemcpyDeviceToHost, s));
+    if (first_invalid)
+      CU(c, cudaMemcpyAsync(h_res + 24, c->d_edge_first.p, n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(h_res + 8, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    memcpy(valid_bitmap, h_res + 16, (n_edges + 7) / 8);
+    if (first_invalid)
+      memcpy(first_invalid, h_res + 24, n_edges * sizeof(int32_t));
+    memcpy(&cnt, h_res + 8, sizeof(unsigned));
+    ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_small).count();
+  }
+  else
+  {
+    CU(c, cudaEventRecord(c->ev1, s));
+    CU(c, cudaMemcpyAsync(valid_bitmap, c->d_edge_bits.p, (n_edges + 7) / 8, cudaMemcpyDeviceToHost, s));
+    if (first_invalid)
+      CU(c, cudaMemcpyAsync(first_invalid, c->d_edge_first.p, n_edges * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  }
   if (n_states_checked)
     *n_states_checked = total;
   c->stats.n_states = total;
