@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no libb200sv.so (built artefacts are git-ignored): build it once if nvcc is here; when it is
+    # up to date this is a stat() per source file.  If the build fails the tests that need the library fail loudly.
+    try:
+        from moveit2_b200 import build as _build
+        _build.build(force=False)
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("conftest: libb200sv.so not (re)built: %s\n" % e)
 
 
 @pytest.fixture(scope="session")
