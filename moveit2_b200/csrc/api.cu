@@ -2706,6 +2706,8 @@ int b200sv_check_contacts(b200sv_ctx* c, const double* q, size_t n, uint32_t fla
   a.self_enabled = c->d_g_self.p;
   a.intra = c->d_c_intra.p;
   a.centers = c->d_g_centers.p;
+  a.n_spheres = c->n_spheres;
+  a.state_stride = c->state_stride_d;
   a.collision = c->d_c_coll.p;
   a.contact_count = c->d_c_count.p;
   a.contacts = c->d_c_out.p;

@@ -908,17 +908,20 @@ __device__ __forceinline__ bool sphereHitsField(const ModelHeader<double>& h, co
   return static_cast<int>(__ldg(d2 + (static_cast<size_t>(gx) * h.ny + gy) * h.nz + gz)) < thr;
 }
 
-__global__ void __launch_bounds__(64) contactKernel(ContactArgs a)
+// kLocal: link transforms and posed centres in lane-interleaved local memory (see gradientKernel)
+template <bool kLocal>
+__global__ void __launch_bounds__(128) contactKernel(ContactArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
   const ModelHeader<double>& h = *m.h;
-  double* T = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(threadIdx.x) * h.state_stride;
+  double Tloc[kLocal ? kGradMaxStride : 1], Cl[kLocal ? 3 * kGradMaxSpheres : 1];
+  double* T = kLocal ? Tloc : reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(threadIdx.x) * h.state_stride;
   const unsigned long long st = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
   if (st >= a.n_states)
     return;
   const int S = h.n_spheres, L = a.n_glinks;
-  double* cen = a.centers + st * S * 3;
+  double* cen = kLocal ? Cl : a.centers + st * S * 3;
   b200sv_contact_rec* out = a.contacts + st * a.max_contacts;
   fkState<double>(m, a.q + st * h.n_group_vars, T);
   for (int k = 0; k < S; ++k)
@@ -1205,11 +1208,21 @@ cudaError_t launchGradients(const GradArgs& a, int grid, int block, size_t smem_
 
 cudaError_t launchContacts(const ContactArgs& a, int grid, int block, size_t smem_bytes, cudaStream_t stream)
 {
-  static SmemGrant g;
-  cudaError_t e = ensureSmem(contactKernel, smem_bytes, g);
+  static SmemGrant gl, gg;
+  if (a.n_spheres <= kGradMaxSpheres && a.state_stride <= kGradMaxStride)
+  {
+    const size_t blob = (static_cast<size_t>(a.model_bytes) + 15) & ~static_cast<size_t>(15);
+    cudaError_t e = ensureSmem(contactKernel<true>, blob, gl);
+    if (e != cudaSuccess)
+      return e;
+    const unsigned long long n = a.n_states;
+    contactKernel<true><<<static_cast<unsigned>((n + 127) / 128), 128, blob, stream>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t e = ensureSmem(contactKernel<false>, smem_bytes, gg);
   if (e != cudaSuccess)
     return e;
-  contactKernel<<<grid, block, smem_bytes, stream>>>(a);
+  contactKernel<false><<<grid, block, smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -97,7 +97,7 @@ struct ContactArgs
   const uint16_t* d2_self;
   uint32_t flags;
   unsigned max_contacts, max_per_pair;
-  int n_glinks;
+  int n_glinks, n_spheres, state_stride;  // state_stride: doubles of link transforms per state (the double blob's)
   const int32_t* sphere_start;   // [n_glinks + 1]
   const int32_t* glink_slot;     // [n_glinks] device-link slot
   const double* glink_bs;        // [n_glinks * 4] link-frame bounding sphere
