@@ -19,6 +19,9 @@
  *   - Every function returns B200SV_OK (0) or a negative error; b200sv_last_error() has the message.  There is no
  *     CPU fallback: without a usable CUDA device creation fails with B200SV_ERR_NO_DEVICE.
  *   - Calls on one context are serialised by an internal mutex; separate contexts are independent.
+ *   - The *_device entry points run on the CALLER's stream but share the context's scratch buffers: the library orders each
+ *     such call behind the context's own stream and behind the previous call on a different caller stream (events, no host
+ *     synchronisation), and orders the context's next own-stream work behind it.
  */
 #ifndef B200SV_H
 #define B200SV_H
@@ -242,6 +245,13 @@ int b200sv_check_batch(b200sv_ctx* ctx, const double* q, size_t n_states, uint32
  * d_valid_bitmap must hold 4*ceil(n/32) bytes (whole 32-bit words are written). */
 int b200sv_check_batch_device(b200sv_ctx* ctx, const double* d_q, size_t n_states, uint32_t flags,
                               uint8_t* d_valid_bitmap, void* cuda_stream);
+/* Same with float32 states -- NOT the reference's layout (RobotState holds doubles): for callers that keep their samples in
+ * float and want half the host-to-device traffic.  Every value is widened on the device, q = (double)q_f32, so the result is
+ * bit-for-bit what b200sv_check_batch returns for those widened states. */
+int b200sv_check_batch_f32(b200sv_ctx* ctx, const float* q, size_t n_states, uint32_t flags, uint8_t* valid_bitmap);
+/* b200sv_fk_batch with q and link_T resident in device memory; asynchronous on `cuda_stream`. */
+int b200sv_fk_batch_device(b200sv_ctx* ctx, const double* d_q, size_t n_states, int precision_bits, double* d_link_T,
+                           void* cuda_stream);
 /* Batched edge ("motion") validation -- new; the consumer is ompl::base::MotionValidator::checkMotion as MoveIt
  * configures it (DiscreteMotionValidator over ModelBasedStateSpace; longest_valid_segment_fraction:
  * moveit_planners/ompl/ompl_interface/src/model_based_planning_context.cpp:294-317).  For edge e the states checked are
@@ -301,6 +311,52 @@ int b200sv_check_contacts(b200sv_ctx* ctx, const double* q, size_t n_states, uin
 /* Posed collision-sphere centres of ONE state, FP64 kernel: [n_spheres*3] (host).  Parity hook for
  * PosedBodySphereDecomposition::updatePose (collision_distance_field_types.cpp:388-395). */
 int b200sv_sphere_centers(b200sv_ctx* ctx, const double* q_one, double* centers);
+
+/* ---- DistanceFieldCacheEntry updates on a live context (collision_env_distance_field.cpp:202-233, 1254-1370) --------- */
+/* The reference regenerates its cache entry when the ACM changes (compareCacheEntryToAllowedCollisionMatrix :1314-1370) or a
+ * joint outside the group moves (compareCacheEntryToState :1254-1312).  These two re-derive the same things in place -- the
+ * enable masks and everything built from them, the constant link transforms, and the self field -- without re-allocating the
+ * context or touching its world field.
+ *   self_enabled   [n_glinks]            dfce->self_collision_enabled_
+ *   intra_enabled  [n_glinks * n_glinks] dfce->intra_group_collision_enabled_ */
+int b200sv_set_acm_masks(b200sv_ctx* ctx, const uint8_t* self_enabled, const uint8_t* intra_enabled);
+/* base_positions [n_vars]: RobotState::getVariablePositions() for everything outside the group.  rebuild_self_field != 0:
+ * the self field is rebuilt from the non-group links' interior points posed at the new state (generateDistanceFieldCacheEntry
+ * :907-953) -- the points the URDF path derived, or those given with b200sv_set_self_link_points; 0: the caller rebuilds it
+ * (b200sv_field_reset + b200sv_field_add_points on B200SV_FIELD_SELF). */
+int b200sv_set_base_state(b200sv_ctx* ctx, const double* base_positions, int rebuild_self_field);
+/* Interior points of a link the group does not move, in the LINK frame (BodyDecomposition::getCollisionPoints,
+ * collision_distance_field_types.hpp:212-215), for contexts made with b200sv_create. */
+int b200sv_set_self_link_points(b200sv_ctx* ctx, int32_t link_index, const double* xyz_link_frame, size_t n_points);
+
+/* ---- field replication (the field is built on ONE GPU and broadcast) --------------------------------- */
+/* A built field as one device buffer (occupancy bits, 16-bit d^2, this field's compact elements) that another context with the
+ * same geometry imports: between the two calls the bytes can travel by ncclBroadcast (one process per GPU, see
+ * moveit2_b200/sharding.py) or a peer copy.  Asynchronous on `cuda_stream`.  Unsigned fields only. */
+int b200sv_field_export_size(const b200sv_ctx* ctx, size_t* n_bytes);
+int b200sv_field_export_device(b200sv_ctx* ctx, int which, void* d_buf, void* cuda_stream);
+int b200sv_field_import_device(b200sv_ctx* ctx, int which, const void* d_buf, void* cuda_stream);
+
+/* ---- several GPUs of one box behind one handle (one process, e.g. a C++ MoveIt node loading the plugin) ----------------- */
+/* One context per listed device (a device may be listed twice).  States are sharded in contiguous blocks of whole bitmap
+ * words, fields are built on the first device and copied to the others device-to-device, every block's bitmap lands in the
+ * caller's buffer: there is no other exchange on this path. */
+typedef struct b200sv_multi b200sv_multi;
+int b200sv_create_multi(const int* devices, int n_dev, const b200sv_robot* robot, const b200sv_collision_model* model,
+                        const b200sv_field_cfg* field, b200sv_multi** out);
+int b200sv_create_multi_from_urdf(const int* devices, int n_dev, const char* urdf_xml, const char* srdf_xml,
+                                  const char* group_name, const b200sv_field_cfg* field, b200sv_multi** out);
+void b200sv_destroy_multi(b200sv_multi* m);
+const char* b200sv_multi_last_error(const b200sv_multi* m);
+int b200sv_multi_device_count(const b200sv_multi* m);
+/* Context i, for every single-context call; after changing a field of context 0, b200sv_multi_field_sync replicates it. */
+b200sv_ctx* b200sv_multi_ctx(b200sv_multi* m, int i);
+int b200sv_multi_field_sync(b200sv_multi* m, int which);
+int b200sv_multi_field_reset(b200sv_multi* m, int which);
+int b200sv_multi_field_add_points(b200sv_multi* m, int which, const double* xyz, size_t n_points);
+/* b200sv_check_batch over all devices: block i of the states goes to context i; pinned host buffers make every copy a DMA. */
+int b200sv_check_batch_multi(b200sv_multi* m, const double* q, size_t n_states, uint32_t flags, uint8_t* valid_bitmap);
+int b200sv_multi_get_stats(b200sv_multi* m, b200sv_stats* stats);
 
 /* ---- measurement helpers ------------------------------------------------------------------------------------ */
 /* Random 32-byte-sector gather over the world field's footprint: the "gather-bandwidth roofline" the check

@@ -103,6 +103,27 @@ def load():
         "b200sv_check_contacts": (C.c_int, [vp, dp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, u8p, ip, vp]),
         "b200sv_check_motions": (C.c_int, [vp, dp, dp, C.c_size_t, C.c_double, u8p, dp, C.c_uint32, C.c_uint32, u8p,
                                            ip, C.POINTER(C.c_uint64)]),
+        "b200sv_check_batch_f32": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp]),
+        "b200sv_fk_batch_device": (C.c_int, [vp, vp, C.c_size_t, C.c_int, vp, vp]),
+        "b200sv_set_acm_masks": (C.c_int, [vp, u8p, u8p]),
+        "b200sv_set_base_state": (C.c_int, [vp, dp, C.c_int]),
+        "b200sv_set_self_link_points": (C.c_int, [vp, C.c_int32, dp, C.c_size_t]),
+        "b200sv_field_export_size": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
+        "b200sv_field_export_device": (C.c_int, [vp, C.c_int, vp, vp]),
+        "b200sv_field_import_device": (C.c_int, [vp, C.c_int, vp, vp]),
+        "b200sv_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(Robot), C.POINTER(CollisionModel),
+                                          C.POINTER(FieldCfg), C.POINTER(vp)]),
+        "b200sv_create_multi_from_urdf": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
+                                                    C.POINTER(FieldCfg), C.POINTER(vp)]),
+        "b200sv_destroy_multi": (None, [vp]),
+        "b200sv_multi_last_error": (C.c_char_p, [vp]),
+        "b200sv_multi_device_count": (C.c_int, [vp]),
+        "b200sv_multi_ctx": (vp, [vp, C.c_int]),
+        "b200sv_multi_field_sync": (C.c_int, [vp, C.c_int]),
+        "b200sv_multi_field_reset": (C.c_int, [vp, C.c_int]),
+        "b200sv_multi_field_add_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
+        "b200sv_check_batch_multi": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp]),
+        "b200sv_multi_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "b200sv_gather_roofline": (C.c_int, [vp, C.c_size_t, C.c_int, dp]),
         "b200sv_set_tuning": (C.c_int, [vp, C.c_double, C.c_int, C.c_int]),
     }

@@ -25,14 +25,26 @@ def _stale():
 
 
 def build(force=False, verbose=False, defines=(), out=None):
-    """defines / out: build an experimental variant (e.g. -DB200SV_SPHERE_CHUNK=8) next to the default library."""
+    """defines / out: build an experimental variant (e.g. -DB200SV_SPHERE_CHUNK=8) next to the default library.
+    Every source is compiled by its own nvcc process (in parallel), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
     out = out or LIB
     if not force and out == LIB and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    objdir = os.path.join(HERE, "build", os.path.basename(out) + ".obj")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f not in ("-shared", "-lz")] + ["-D" + d for d in defines] + \
+             (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        subprocess.check_call([nvcc] + cflags + ["-c", "-o", obj, os.path.join(CSRC, src)])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-lz"])
     return out
 
 

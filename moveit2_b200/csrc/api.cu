@@ -70,6 +70,7 @@ struct b200sv_ctx
   HostCollisionModel cm;
   b200sv_field_cfg cfg{};
   std::vector<double> self_points;
+  SelfLocalPoints self_local;      // URDF path: link-frame interior points of the links the group does not move
   // grid
   GridDev grid{};
   int compact_bytes = 1;
@@ -116,8 +117,15 @@ struct b200sv_ctx
   static constexpr int kMaxChunks = 32;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_go = nullptr;
+  // The *_device entry points run on the CALLER's stream but use the context's scratch (recheck list and counter, transform
+  // scratch, EDT intermediate, the fields themselves): ev_user marks the end of the last such call, and whichever stream
+  // touches the context next waits for it first (enterCtx / enterUser).
+  cudaEvent_t ev_user = nullptr;
+  cudaStream_t user_stream = nullptr;
+  bool user_pending = false;
   cudaEvent_t ev_chunk[kMaxChunks] = { nullptr };
   DevBuf<double> d_q;
+  DevBuf<float> d_qf;              // b200sv_check_batch_f32: the states as they arrive
   DevBuf<uint32_t> d_bitmap, d_list;
   DevBuf<double> d_points;
   DevBuf<double> d_fk;
@@ -139,8 +147,20 @@ struct b200sv_ctx
   DevBuf<b200sv_contact_rec> d_c_out;
   unsigned* d_count = nullptr;
   unsigned* d_sink = nullptr;
+  unsigned* h_count = nullptr;     // pinned: the recheck counter of the last large batch
+  uint8_t* h_lat = nullptr;        // mapped pinned memory of the latency path: states, then result bytes
+  uint8_t* d_lat = nullptr;        // its device-side address
+  bool latency_ok = false;         // the exact blob + 4 warps of transforms fit shared memory, V <= 32
   b200sv_stats stats{};
   bool stats_pending = false;
+};
+
+struct b200sv_multi
+{
+  std::vector<b200sv_ctx*> ctx;
+  std::mutex mu;
+  std::string err;
+  b200sv_stats stats{};
 };
 
 namespace
@@ -171,6 +191,38 @@ int needDevice(b200sv_ctx* c)
   } while (0)
 
 inline int align16(int x) { return (x + 15) & ~15; }
+
+// Every entry point that works on the context's own stream: select the device and order the stream behind the last call that
+// ran on a caller's stream (it may still be using the context's scratch buffers or rewriting a field).
+void enterCtx(b200sv_ctx* c)
+{
+  cudaSetDevice(c->device);
+  if (c->user_pending)
+  {
+    cudaStreamWaitEvent(c->stream, c->ev_user, 0);
+    c->user_pending = false;
+  }
+}
+
+// Entry points that run on the caller's stream `s`: behind the context's own stream (a field rebuild or upload may be in
+// flight there) and behind the last call on a DIFFERENT caller stream.
+int enterUser(b200sv_ctx* c, cudaStream_t s)
+{
+  cudaSetDevice(c->device);
+  if (c->user_pending && c->user_stream != s)
+    CU(c, cudaStreamWaitEvent(s, c->ev_user, 0));
+  CU(c, cudaEventRecord(c->ev_go, c->stream));
+  CU(c, cudaStreamWaitEvent(s, c->ev_go, 0));
+  return B200SV_OK;
+}
+
+int leaveUser(b200sv_ctx* c, cudaStream_t s)
+{
+  CU(c, cudaEventRecord(c->ev_user, s));
+  c->user_stream = s;
+  c->user_pending = true;
+  return B200SV_OK;
+}
 
 // Integer form of the reference predicate (collision_distance_field_types.cpp:229):
 //   collide = (maximum_value > dist) && (radius - dist > tolerance),  dist = sqrt_table[d2] (unsigned field)
@@ -1285,6 +1337,11 @@ int uploadTables(b200sv_ctx* c)
   }
   CU(c, cudaMemcpy(c->d_link_slot, c->link_slot.data(), c->link_slot.size() * sizeof(int), cudaMemcpyHostToDevice));
   CU(c, cudaMemcpy(c->d_const_T, c->const_T.data(), c->const_T.size() * sizeof(double), cudaMemcpyHostToDevice));
+  {
+    const char* e = getenv("B200SV_LATENCY");
+    c->latency_ok = !(e && atoi(e) == 0) && c->robot.group_var_index.size() <= 32 &&
+                    (size_t)align16((int)c->blob_d.size()) + 4 * ((size_t)c->state_stride_d + 32) * 8 <= (size_t)c->smem_optin;
+  }
   c->cfg_f = chooseCfg(c, false, false, (int)c->blob_f.size());
   c->cfg_d = chooseCfg(c, true, false, (int)c->blob_d.size());
   c->cfg_list = chooseCfg(c, true, true, (int)c->blob_d.size());
@@ -1441,7 +1498,8 @@ int finishCreate(b200sv_ctx* c, int device, b200sv_ctx** out)
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming) != cudaSuccess)
+      cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(c, B200SV_ERR_CUDA, "stream/event creation failed"));
   for (int i = 0; i < b200sv_ctx::kMaxChunks; ++i)
     if (cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess)
@@ -1546,8 +1604,10 @@ int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_
 // Host-buffer entry: the H2D copy of the states is cut into chunks on a second stream so the check of chunk i
 // overlaps the copy of chunk i + 1 (PCIe is the longer of the two for 56-byte states).
 template <typename FT>
-int runCheckHost(b200sv_ctx* c, const double* h_q, size_t n, uint32_t flags)
+int runCheckHost(b200sv_ctx* c, const void* h_q_any, size_t n, uint32_t flags, bool f32 = false)
 {
+  const double* h_q = static_cast<const double*>(h_q_any);
+  const float* h_qf = static_cast<const float*>(h_q_any);
   const size_t V = c->robot.group_var_index.size();
   size_t chunk = 131072;                               // states; a multiple of 32 so bitmap words do not straddle
   if (const char* e = getenv("B200SV_CHUNK"))
@@ -1569,16 +1629,47 @@ int runCheckHost(b200sv_ctx* c, const double* h_q, size_t n, uint32_t flags)
     m = std::min(chunk, left);
     if (left <= chunk && left > chunk / 8 && i < b200sv_ctx::kMaxChunks - 1)
       m = std::min(left, std::max<size_t>((left / 2 + 31) & ~(size_t)31, (chunk / 8) & ~(size_t)31));
-    CU(c, cudaMemcpyAsync(c->d_q.p + base * V, h_q + base * V, m * V * sizeof(double), cudaMemcpyHostToDevice,
-                          c->copy_stream));
+    if (f32)
+      CU(c, cudaMemcpyAsync(c->d_qf.p + base * V, h_qf + base * V, m * V * sizeof(float), cudaMemcpyHostToDevice,
+                            c->copy_stream));
+    else
+      CU(c, cudaMemcpyAsync(c->d_q.p + base * V, h_q + base * V, m * V * sizeof(double), cudaMemcpyHostToDevice,
+                            c->copy_stream));
     CU(c, cudaEventRecord(c->ev_chunk[i], c->copy_stream));
     CU(c, cudaStreamWaitEvent(c->stream, c->ev_chunk[i], 0));
+    if (f32)  // widen on the device: q = double(float), exactly what a float-holding caller would pass to the f64 entry
+      CU(c, launchWidenStates(c->d_qf.p + base * V, c->d_q.p + base * V, m * V, c->stream));
     int rc = launchMain<FT>(c, c->d_q.p, c->d_bitmap.p, base, m, flags, c->stream);
     if (rc != B200SV_OK)
       return rc;
   }
   if (!fp64)
     return launchRecheck<FT>(c, c->d_q.p, c->d_bitmap.p, n, flags, c->stream);
+  return B200SV_OK;
+}
+
+// batched FK of device-resident states into device-resident 4x4 column-major doubles, all model links
+int fkLaunch(b200sv_ctx* c, const double* d_q, size_t n, bool fp64, double* d_out, cudaStream_t s)
+{
+  FkArgs a{};
+  a.model = fp64 ? c->d_blob_d : c->d_blob_f;
+  a.model_bytes = (int)(fp64 ? c->blob_d.size() : c->blob_f.size());
+  a.q = d_q;
+  a.n_states = n;
+  a.n_model_links = c->robot.n_links;
+  a.link_slot = c->d_link_slot;
+  a.const_T = c->d_const_T;
+  a.out = d_out;
+  const int elem = fp64 ? 8 : 4;
+  const int ss = fp64 ? c->state_stride_d : c->state_stride_f;
+  int warps = 4;
+  while (warps > 1 && align16(a.model_bytes) + (size_t)warps * 32 * ss * elem > (size_t)c->smem_optin)
+    --warps;
+  const size_t smem = align16(a.model_bytes) + (size_t)warps * 32 * ss * elem;
+  // as many CTAs as fit an SM at this much shared memory, times the SM count: a persistent grid over the state tiles
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(228 * 1024) / (smem + 1024)));
+  const int grid = (int)std::min<size_t>((n + 32 * warps - 1) / (32 * warps), (size_t)c->sm_count * per_sm);
+  CU(c, launchFk(a, fp64, grid, warps * 32, smem, s));
   return B200SV_OK;
 }
 
@@ -1652,7 +1743,7 @@ int b200sv_create_from_urdf(int device, const char* urdf_xml, const char* srdf_x
   std::string err;
   bool parse_error = false;
   if (!loadUrdfSrdf(urdf_xml, srdf_xml ? srdf_xml : "", group_name, field->resolution, c->robot, c->cm, c->self_points,
-                    err, parse_error))
+                    c->self_local, err, parse_error))
   {
     delete c;
     return fail(nullptr, parse_error ? B200SV_ERR_PARSE : B200SV_ERR_INVALID, err);
@@ -1685,6 +1776,8 @@ void b200sv_destroy(b200sv_ctx* c)
     return;
   }
   cudaSetDevice(c->device);
+  if (c->user_pending)
+    cudaEventSynchronize(c->ev_user);
   if (c->stream)
     cudaStreamSynchronize(c->stream);
   for (int w = 0; w < 2; ++w)
@@ -1701,6 +1794,8 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->d_tmp) cudaFree(c->d_tmp);
   if (c->d_sqrt_table) cudaFree(c->d_sqrt_table);
   if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->h_count) cudaFreeHost(c->h_count);
+  if (c->h_lat) cudaFreeHost(c->h_lat);
   if (c->d_small) cudaFree(c->d_small);
   if (c->d_blob_f) cudaFree(c->d_blob_f);
   if (c->d_blob_d) cudaFree(c->d_blob_d);
@@ -1718,6 +1813,7 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->d_count) cudaFree(c->d_count);
   if (c->d_sink) cudaFree(c->d_sink);
   c->d_q.release();
+  c->d_qf.release();
   c->d_bitmap.release();
   c->d_list.release();
   c->d_points.release();
@@ -1726,6 +1822,7 @@ void b200sv_destroy(b200sv_ctx* c)
   for (int i = 0; i < b200sv_ctx::kMaxChunks; ++i)
     if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
   if (c->ev_go) cudaEventDestroy(c->ev_go);
+  if (c->ev_user) cudaEventDestroy(c->ev_user);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1768,6 +1865,8 @@ int b200sv_get_stats(b200sv_ctx* c, b200sv_stats* stats)
   cudaSetDevice(c->device);
   if (c->stats_pending)
   {
+    if (c->user_pending)
+      CU(c, cudaEventSynchronize(c->ev_user));
     CU(c, cudaStreamSynchronize(c->stream));
     unsigned cnt = 0;
     CU(c, cudaMemcpy(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost));
@@ -1874,7 +1973,7 @@ int b200sv_field_reset(b200sv_ctx* c, int which)
   if (rc)
     return rc;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   Field& F = c->fields[which];
   CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
   CU(c, launchFillField(c->grid, F.d2, F.compact, c->compact_bytes, c->stream));
@@ -1892,7 +1991,7 @@ static int pointsHost(b200sv_ctx* c, int which, const double* xyz, size_t n, boo
   if (n && !xyz)
     return fail(c, B200SV_ERR_INVALID, "null point array");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   if (n)
   {
     CU(c, c->d_points.ensure(3 * n));
@@ -1921,7 +2020,7 @@ int b200sv_field_update_points(b200sv_ctx* c, int which, const double* old_xyz, 
   if ((n_old && !old_xyz) || (n_new && !new_xyz))
     return fail(c, B200SV_ERR_INVALID, "null point array");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const size_t n_words = (size_t)c->grid.nx * c->grid.ny * c->grid.wz;
   if (2 * n_words * 4 > c->n_voxels * 2)
     return fail(c, B200SV_ERR_UNSUPPORTED, "grid too shallow for the update scratch (nz < 16)");
@@ -1952,7 +2051,7 @@ int b200sv_field_add_sphere(b200sv_ctx* c, int which, const double* center, doub
   if (!center || !(radius >= 0.0))
     return fail(c, B200SV_ERR_INVALID, "null centre or negative radius");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   // findInternalPointsConvex (find_internal_points.cpp:44-54): the bounding sphere of a bodies::Sphere is the sphere;
   // start = floor((c - r - res) / res) * res, then `pt += res` while pt <= c + r + res -- accumulated, not k * res
   const double res = c->cfg.resolution;
@@ -2038,7 +2137,7 @@ int b200sv_field_add_shape(b200sv_ctx* c, int which, const b200sv_shape* sh, int
   }
   b.posed = body_frame ? 1 : 0;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   // findInternalPointsConvex (find_internal_points.cpp:44-54): start = floor((c - r - res) / res) * res, then `pt += res`
   // while pt <= c + r + res -- accumulated, not k * res
   const double res = c->cfg.resolution;
@@ -2067,11 +2166,14 @@ int b200sv_field_add_points_device(b200sv_ctx* c, int which, const double* d_xyz
   if (rc)
     return rc;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  if ((rc = enterUser(c, s)) != B200SV_OK)
+    return rc;
   if ((rc = addOrRemove(c, which, d_xyz, n, true, s)) != B200SV_OK)
     return rc;
-  return edtPasses(c, c->fields[which], s);
+  if ((rc = edtPasses(c, c->fields[which], s)) != B200SV_OK)
+    return rc;
+  return leaveUser(c, s);
 }
 
 int b200sv_field_get_d2(b200sv_ctx* c, int which, int32_t* out)
@@ -2082,7 +2184,7 @@ int b200sv_field_get_d2(b200sv_ctx* c, int which, int32_t* out)
   if (!out)
     return fail(c, B200SV_ERR_INVALID, "null output");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   std::vector<uint16_t> h(c->n_voxels);
   CU(c, cudaMemcpyAsync(h.data(), c->fields[which].d2, c->n_voxels * 2, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -2099,7 +2201,7 @@ int b200sv_field_get_neg_d2(b200sv_ctx* c, int which, int32_t* out)
   if (!out)
     return fail(c, B200SV_ERR_INVALID, "null output");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   if (!c->fields[which].nd2)
   {  // an unsigned field: negative_distance_square_ stays at its reset value
     std::fill(out, out + c->n_voxels, 0);
@@ -2123,7 +2225,7 @@ int b200sv_field_set_neg_d2(b200sv_ctx* c, int which, const int32_t* nd2)
   if (!c->fields[which].nd2)
     return fail(c, B200SV_ERR_INVALID, "the context's fields are unsigned (use_signed_distance_field = 0)");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   CU(c, c->d_i32.ensure(c->n_voxels));
   CU(c, cudaMemcpyAsync(c->d_i32.p, nd2, c->n_voxels * 4, cudaMemcpyHostToDevice, c->stream));
   CU(c, launchInjectNegD2(c->grid, c->d_i32.p, c->fields[which].nd2, c->stream));
@@ -2139,7 +2241,7 @@ int b200sv_field_set_d2(b200sv_ctx* c, int which, const int32_t* d2)
   if (!d2)
     return fail(c, B200SV_ERR_INVALID, "null input");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   Field& F = c->fields[which];
   CU(c, c->d_i32.ensure(c->n_voxels));
   CU(c, cudaMemcpyAsync(c->d_i32.p, d2, c->n_voxels * 4, cudaMemcpyHostToDevice, c->stream));
@@ -2161,7 +2263,7 @@ int b200sv_field_write_df(b200sv_ctx* c, int which, uint8_t* out, size_t cap, si
   if (!n_out)
     return fail(c, B200SV_ERR_INVALID, "null n_out");
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const GridDev& g = c->grid;
   const size_t rows = (size_t)g.nx * g.ny, zb = (size_t)(g.nz + 7) / 8;
   std::vector<uint32_t> occ(rows * g.wz);
@@ -2221,7 +2323,7 @@ int b200sv_field_read_df(b200sv_ctx* c, int which, const uint8_t* bytes, size_t 
     if (fabs(v[k] - want[k]) > 1e-5 * std::max(1.0, fabs(want[k])))  // the header carries 6 significant digits
       return fail(c, B200SV_ERR_INVALID, std::string(".df geometry differs from the context's field: ") + keys[k]);
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const GridDev& g = c->grid;
   const size_t rows = (size_t)g.nx * g.ny, zb = (size_t)(g.nz + 7) / 8;
   std::vector<uint8_t> packed(rows * zb);
@@ -2255,33 +2357,36 @@ int b200sv_fk_batch(b200sv_ctx* c, const double* q, size_t n, int precision_bits
   if (n == 0)
     return B200SV_OK;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const size_t V = c->robot.group_var_index.size();
   const size_t out_n = n * (size_t)c->robot.n_links * 16;
   CU(c, c->d_q.ensure(n * V));
   CU(c, c->d_fk.ensure(out_n));
   CU(c, cudaMemcpyAsync(c->d_q.p, q, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  FkArgs a{};
-  const bool fp64 = precision_bits == 64;
-  a.model = fp64 ? c->d_blob_d : c->d_blob_f;
-  a.model_bytes = (int)(fp64 ? c->blob_d.size() : c->blob_f.size());
-  a.q = c->d_q.p;
-  a.n_states = n;
-  a.n_model_links = c->robot.n_links;
-  a.link_slot = c->d_link_slot;
-  a.const_T = c->d_const_T;
-  a.out = c->d_fk.p;
-  const int elem = fp64 ? 8 : 4;
-  const int ss = fp64 ? c->state_stride_d : c->state_stride_f;
-  int warps = 4;
-  while (warps > 1 && align16(a.model_bytes) + (size_t)warps * 32 * ss * elem > (size_t)c->smem_optin)
-    --warps;
-  const size_t smem = align16(a.model_bytes) + (size_t)warps * 32 * ss * elem;
-  const int grid = (int)std::min<size_t>((n + 32 * warps - 1) / (32 * warps), (size_t)c->sm_count * 4);
-  CU(c, launchFk(a, fp64, grid, warps * 32, smem, c->stream));
+  if (int rc = fkLaunch(c, c->d_q.p, n, precision_bits == 64, c->d_fk.p, c->stream))
+    return rc;
   CU(c, cudaMemcpyAsync(link_T, c->d_fk.p, out_n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return B200SV_OK;
+}
+
+int b200sv_fk_batch_device(b200sv_ctx* c, const double* d_q, size_t n, int precision_bits, double* d_link_T, void* cuda_stream)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if ((n && (!d_q || !d_link_T)) || (precision_bits != 32 && precision_bits != 64))
+    return fail(c, B200SV_ERR_INVALID, "bad arguments to b200sv_fk_batch_device");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  if (int rc = enterUser(c, s))
+    return rc;
+  if (int rc = fkLaunch(c, d_q, n, precision_bits == 64, d_link_T, s))
+    return rc;
+  return leaveUser(c, s);
 }
 
 int b200sv_sphere_centers(b200sv_ctx* c, const double* q_one, double* centers)
@@ -2291,7 +2396,7 @@ int b200sv_sphere_centers(b200sv_ctx* c, const double* q_one, double* centers)
   if (needDevice(c))
     return B200SV_ERR_NO_DEVICE;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const size_t V = c->robot.group_var_index.size();
   CU(c, c->d_q.ensure(V));
   CU(c, c->d_fk.ensure((size_t)c->n_spheres * 3 + 1));
@@ -2320,13 +2425,18 @@ int b200sv_check_batch_device(b200sv_ctx* c, const double* d_q, size_t n, uint32
   if (n == 0)
     return B200SV_OK;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
-  int rc = checkDevice(c, d_q, n, flags, reinterpret_cast<uint32_t*>(d_valid_bitmap), static_cast<cudaStream_t>(cuda_stream));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  int rc = enterUser(c, s);
+  if (rc != B200SV_OK)
+    return rc;
+  rc = checkDevice(c, d_q, n, flags, reinterpret_cast<uint32_t*>(d_valid_bitmap), s);
   c->stats.n_states = n;
   c->stats.n_valid = 0;
   c->stats.check_ms = 0.f;
   c->stats_pending = true;
-  return rc;
+  if (rc != B200SV_OK)
+    return rc;
+  return leaveUser(c, s);
 }
 
 // pinned staging of the latency paths (single states, single edges): the context's own, so no copy of a small call falls
@@ -2344,6 +2454,200 @@ static int ensureSmallStaging(b200sv_ctx* c, size_t bytes)
   return B200SV_OK;
 }
 
+// Popcount of a validity bitmap of n states (bits beyond n are 0: the kernels write whole words from ballots of active lanes)
+static uint64_t countValid(const uint8_t* valid_bitmap, size_t n)
+{
+  uint64_t valid = 0;
+  const size_t nb = (n + 7) / 8;
+  size_t i = 0;
+  for (; i + 8 <= nb; i += 8)
+  {
+    uint64_t w;
+    memcpy(&w, valid_bitmap + i, 8);
+    valid += (uint64_t)__builtin_popcountll(w);
+  }
+  for (; i < nb; ++i)
+    valid += (uint64_t)__builtin_popcount(valid_bitmap[i]);
+  return valid;
+}
+
+constexpr size_t kSmallBatch = 4096;   // up to here: one stream, the context's own pinned staging, no timing events
+constexpr size_t kLatencyBatch = 32;   // up to here: ONE kernel launch, no copies (latencyCheckKernel)
+
+// Small batches: everything on one stream, states and results staged through the context's own pinned buffer.
+static int checkSmall(b200sv_ctx* c, const double* q, size_t n, uint32_t flags, uint8_t* valid_bitmap)
+{
+  const size_t V = c->robot.group_var_index.size();
+  CU(c, c->d_q.ensure(n * V));
+  CU(c, c->d_list.ensure(n));
+  unsigned cnt = 0;
+  // Latency path (a single-state checkCollision through the plugin is a batch of 1): everything on one stream, states and
+  // results staged through the context's own pinned buffer, so no copy falls back to the driver's pageable staging.
+  const size_t q_bytes = kSmallBatch * V * sizeof(double), out_bytes = kSmallBatch / 8 + 16;
+  if (int rc = ensureSmallStaging(c, q_bytes + out_bytes))
+    return rc;
+  uint8_t* h_out = c->h_small + q_bytes;
+  // bitmap words and the recheck counter side by side in device memory: ONE copy back instead of two
+  if (!c->d_small)
+    CU(c, cudaMalloc(&c->d_small, kSmallBatch / 8 + 16));
+  uint32_t* d_small_bitmap = c->d_small;
+  unsigned* const count_saved = c->d_count;
+  c->d_count = c->d_small + kSmallBatch / 32;
+  struct Restore
+  {
+    b200sv_ctx* c;
+    unsigned* p;
+    ~Restore() { c->d_count = p; }
+  } restore{ c, count_saved };
+  memcpy(c->h_small, q, n * V * sizeof(double));
+  const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
+  if (!fp64)
+    CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream));
+  const auto t_small = std::chrono::steady_clock::now();  // no timing events on the latency path: three API calls fewer
+  CU(c, cudaMemcpyAsync(c->d_q.p, c->h_small, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int rc = c->compact_bytes == 1 ? launchMain<uint8_t>(c, c->d_q.p, d_small_bitmap, 0, n, flags, c->stream) :
+                                   launchMain<uint16_t>(c, c->d_q.p, d_small_bitmap, 0, n, flags, c->stream);
+  if (rc == B200SV_OK && !fp64)
+    rc = c->compact_bytes == 1 ? launchRecheck<uint8_t>(c, c->d_q.p, d_small_bitmap, n, flags, c->stream) :
+                                 launchRecheck<uint16_t>(c, c->d_q.p, d_small_bitmap, n, flags, c->stream);
+  if (rc != B200SV_OK)
+    return rc;
+  CU(c, cudaMemcpyAsync(h_out, c->d_small, kSmallBatch / 8 + sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  memcpy(valid_bitmap, h_out, (n + 7) / 8);
+  memcpy(&cnt, h_out + kSmallBatch / 8, sizeof(unsigned));
+  const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_small).count();
+  c->stats.n_states = n;
+  c->stats.n_valid = countValid(valid_bitmap, n);
+  c->stats.n_rechecked = (flags & B200SV_CHECK_FP64) ? 0 : cnt;
+  c->stats.check_ms = ms;
+  c->stats_pending = false;
+  return B200SV_OK;
+}
+
+// The latency path: n <= 32 states (OMPL's per-state isValid through the plugin is n = 1).  One kernel launch, nothing else:
+// the states travel in the kernel parameters (or mapped pinned memory), the exact FP64 check runs one warp per state, the
+// result bytes land in mapped pinned memory and the host polls them -- no memcpy, no memset, no second launch, no
+// stream synchronisation on the way.
+static int checkLatency(b200sv_ctx* c, const double* q, size_t n, uint32_t flags, uint8_t* valid_bitmap)
+{
+  const size_t V = c->robot.group_var_index.size();
+  const size_t q_bytes = kLatencyBatch * V * sizeof(double);
+  if (!c->h_lat)
+  {
+    CU(c, cudaHostAlloc(&c->h_lat, q_bytes + 64, cudaHostAllocMapped));
+    CU(c, cudaHostGetDevicePointer(&c->d_lat, c->h_lat, 0));
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  volatile uint8_t* res = c->h_lat + q_bytes;
+  for (size_t i = 0; i < n; ++i)
+    res[i] = 0xff;
+  auto fill = [&](auto& a) {
+    a.model = c->d_blob_d;
+    a.model_bytes = (int)c->blob_d.size();
+    a.field = c->d_combined;
+    a.flags = flags & 7u;
+    a.n_states = (int)n;
+    a.state_stride = c->state_stride_d;
+    a.use_inline = n * V <= 32 ? 1 : 0;
+    a.q = reinterpret_cast<const double*>(c->d_lat);
+    a.result = c->d_lat + q_bytes;
+    if (a.use_inline)
+      memcpy(a.q_inline, q, n * V * sizeof(double));
+    else
+      memcpy(c->h_lat, q, n * V * sizeof(double));
+  };
+  if (c->compact_bytes == 1)
+  {
+    LatencyArgs<uint8_t> a{};
+    fill(a);
+    CU(c, launchLatencyCheck<uint8_t>(a, c->stream));
+  }
+  else
+  {
+    LatencyArgs<uint16_t> a{};
+    fill(a);
+    CU(c, launchLatencyCheck<uint16_t>(a, c->stream));
+  }
+  // poll the result bytes; a kernel that cannot finish (launch failure, device error) is caught by the synchronise below
+  bool done = false;
+  for (long spin = 0; spin < 4000000L && !done; ++spin)
+  {
+    done = true;
+    for (size_t i = 0; i < n; ++i)
+      if (res[i] == 0xff)
+      {
+        done = false;
+        break;
+      }
+  }
+  if (!done)
+  {
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i)
+      if (res[i] == 0xff)
+        return fail(c, B200SV_ERR_CUDA, "latency path: the kernel finished without writing a result");
+  }
+  memset(valid_bitmap, 0, (n + 7) / 8);
+  uint64_t valid = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (res[i] == 1)
+    {
+      valid_bitmap[i >> 3] |= (uint8_t)(1u << (i & 7));
+      ++valid;
+    }
+  c->stats.n_states = n;
+  c->stats.n_valid = valid;
+  c->stats.n_rechecked = n;  // every state of this path is decided by the exact FP64 arithmetic
+  c->stats.check_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  c->stats_pending = false;
+  return B200SV_OK;
+}
+
+// The large-batch path in two halves, so several contexts (one per GPU, multi.cu) can be in flight at once:
+// enqueue = chunked H2D of the states overlapped with the kernels + D2H of the bitmap, all asynchronous; finish = wait + stats.
+// The caller holds c->mu across both.
+static int checkHostEnqueue(b200sv_ctx* c, const void* q, size_t n, uint32_t flags, uint8_t* valid_bitmap, bool f32 = false)
+{
+  cudaSetDevice(c->device);
+  const size_t V = c->robot.group_var_index.size();
+  const size_t words = (n + 31) / 32;
+  if ((flags & 7u) == 0)
+    return fail(c, B200SV_ERR_INVALID, "flags select no check");
+  if (n >= (1ull << 32))
+    return fail(c, B200SV_ERR_INVALID, "more than 2^32 - 1 states in one call");
+  CU(c, c->d_q.ensure(n * V));
+  if (f32)
+    CU(c, c->d_qf.ensure(n * V));
+  CU(c, c->d_bitmap.ensure(words));
+  CU(c, c->d_list.ensure(n));
+  if (!c->h_count)
+    CU(c, cudaHostAlloc(&c->h_count, sizeof(unsigned), cudaHostAllocDefault));
+  CU(c, cudaEventRecord(c->ev0, c->stream));
+  int rc = c->compact_bytes == 1 ? runCheckHost<uint8_t>(c, q, n, flags, f32) : runCheckHost<uint16_t>(c, q, n, flags, f32);
+  if (rc != B200SV_OK)
+    return rc;
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  // bitmap back: whole bytes of the caller's buffer; the device words are little-endian, bit i%8 of byte i/8
+  CU(c, cudaMemcpyAsync(valid_bitmap, c->d_bitmap.p, (n + 7) / 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(c->h_count, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  return B200SV_OK;
+}
+
+static int checkHostFinish(b200sv_ctx* c, size_t n, uint32_t flags, const uint8_t* valid_bitmap)
+{
+  cudaSetDevice(c->device);
+  CU(c, cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->stats.n_states = n;
+  c->stats.n_valid = countValid(valid_bitmap, n);
+  c->stats.n_rechecked = (flags & B200SV_CHECK_FP64) ? 0 : *c->h_count;
+  c->stats.check_ms = ms;
+  c->stats_pending = false;
+  return B200SV_OK;
+}
+
 int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags, uint8_t* valid_bitmap)
 {
   if (!c)
@@ -2355,94 +2659,16 @@ int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags,
   if (n == 0)
     return B200SV_OK;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
-  const size_t V = c->robot.group_var_index.size();
-  const size_t words = (n + 31) / 32;
-  CU(c, c->d_q.ensure(n * V));
-  CU(c, c->d_bitmap.ensure(words));
+  enterCtx(c);
   if ((flags & 7u) == 0)
     return fail(c, B200SV_ERR_INVALID, "flags select no check");
-  if (n >= (1ull << 32))
-    return fail(c, B200SV_ERR_INVALID, "more than 2^32 - 1 states in one call");
-  CU(c, c->d_list.ensure(n));
-  unsigned cnt = 0;
-  constexpr size_t kSmallBatch = 4096;
-  float small_ms = -1.f;  // latency path: copies + kernels by the host clock
+  if (n <= kLatencyBatch && !(flags & B200SV_CHECK_FP64) && c->latency_ok)
+    return checkLatency(c, q, n, flags, valid_bitmap);
   if (n <= kSmallBatch)
-  {
-    // Latency path (a single-state checkCollision through the plugin is a batch of 1): everything on one stream, states and
-    // results staged through the context's own pinned buffer, so no copy falls back to the driver's pageable staging.
-    const size_t q_bytes = kSmallBatch * V * sizeof(double), out_bytes = kSmallBatch / 8 + 16;
-    if (int rc = ensureSmallStaging(c, q_bytes + out_bytes))
-      return rc;
-    uint8_t* h_out = c->h_small + q_bytes;
-    // bitmap words and the recheck counter side by side in device memory: ONE copy back instead of two
-    if (!c->d_small)
-      CU(c, cudaMalloc(&c->d_small, kSmallBatch / 8 + 16));
-    uint32_t* d_small_bitmap = c->d_small;
-    unsigned* const count_saved = c->d_count;
-    c->d_count = c->d_small + kSmallBatch / 32;
-    struct Restore
-    {
-      b200sv_ctx* c;
-      unsigned* p;
-      ~Restore() { c->d_count = p; }
-    } restore{ c, count_saved };
-    memcpy(c->h_small, q, n * V * sizeof(double));
-    const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
-    if (!fp64)
-      CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream));
-    const auto t_small = std::chrono::steady_clock::now();  // no timing events on the latency path: three API calls fewer
-    CU(c, cudaMemcpyAsync(c->d_q.p, c->h_small, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    int rc = c->compact_bytes == 1 ? launchMain<uint8_t>(c, c->d_q.p, d_small_bitmap, 0, n, flags, c->stream) :
-                                     launchMain<uint16_t>(c, c->d_q.p, d_small_bitmap, 0, n, flags, c->stream);
-    if (rc == B200SV_OK && !fp64)
-      rc = c->compact_bytes == 1 ? launchRecheck<uint8_t>(c, c->d_q.p, d_small_bitmap, n, flags, c->stream) :
-                                   launchRecheck<uint16_t>(c, c->d_q.p, d_small_bitmap, n, flags, c->stream);
-    if (rc != B200SV_OK)
-      return rc;
-    CU(c, cudaMemcpyAsync(h_out, c->d_small, kSmallBatch / 8 + sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    memcpy(valid_bitmap, h_out, (n + 7) / 8);
-    memcpy(&cnt, h_out + kSmallBatch / 8, sizeof(unsigned));
-    small_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_small).count();
-  }
-  else
-  {
-    CU(c, cudaEventRecord(c->ev0, c->stream));
-    int rc = c->compact_bytes == 1 ? runCheckHost<uint8_t>(c, q, n, flags) : runCheckHost<uint16_t>(c, q, n, flags);
-    if (rc != B200SV_OK)
-      return rc;
-    CU(c, cudaEventRecord(c->ev1, c->stream));
-    // bitmap back: whole bytes of the caller's buffer; the device words are little-endian, bit i%8 of byte i/8
-    CU(c, cudaMemcpyAsync(valid_bitmap, c->d_bitmap.p, (n + 7) / 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaMemcpyAsync(&cnt, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-  }
-  float ms = 0.f;
-  if (small_ms >= 0.f)
-    ms = small_ms;
-  else
-    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-  uint64_t valid = 0;
-  {  // bits beyond n are 0 (the kernels write whole words from ballots of active lanes)
-    const size_t nb = (n + 7) / 8;
-    size_t i = 0;
-    for (; i + 8 <= nb; i += 8)
-    {
-      uint64_t w;
-      memcpy(&w, valid_bitmap + i, 8);
-      valid += (uint64_t)__builtin_popcountll(w);
-    }
-    for (; i < nb; ++i)
-      valid += (uint64_t)__builtin_popcount(valid_bitmap[i]);
-  }
-  c->stats.n_states = n;
-  c->stats.n_valid = valid;
-  c->stats.n_rechecked = (flags & B200SV_CHECK_FP64) ? 0 : cnt;
-  c->stats.check_ms = ms;
-  c->stats_pending = false;
-  return B200SV_OK;
+    return checkSmall(c, q, n, flags, valid_bitmap);
+  if (int rc = checkHostEnqueue(c, q, n, flags, valid_bitmap))
+    return rc;
+  return checkHostFinish(c, n, flags, valid_bitmap);
 }
 
 int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to, size_t n_edges, double max_segment_length,
@@ -2464,7 +2690,7 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
   if (n_edges == 0)
     return B200SV_OK;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const size_t V = c->robot.group_var_index.size();
   cudaStream_t s = c->stream;
   CU(c, c->d_edges.ensure(2 * n_edges * V));
@@ -2583,7 +2809,7 @@ int b200sv_collision_gradients(b200sv_ctx* c, const double* q, size_t n, double*
   if (n == 0)
     return B200SV_OK;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const size_t V = c->robot.group_var_index.size(), S = (size_t)c->n_spheres, L = (size_t)c->cm.n_glinks;
   cudaStream_t s = c->stream;
   CU(c, c->d_q.ensure(n * V));
@@ -2666,7 +2892,7 @@ int b200sv_check_contacts(b200sv_ctx* c, const double* q, size_t n, uint32_t fla
   if (n == 0)
     return B200SV_OK;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const size_t V = c->robot.group_var_index.size(), S = (size_t)c->n_spheres, L = (size_t)c->cm.n_glinks;
   cudaStream_t s = c->stream;
   std::vector<int32_t> slot(c->glink_slot.begin(), c->glink_slot.end());
@@ -2725,6 +2951,419 @@ int b200sv_check_contacts(b200sv_ctx* c, const double* q, size_t n, uint32_t fla
   return B200SV_OK;
 }
 
+int b200sv_check_batch_f32(b200sv_ctx* c, const float* q, size_t n, uint32_t flags, uint8_t* valid_bitmap)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (n && (!q || !valid_bitmap))
+    return fail(c, B200SV_ERR_INVALID, "null host pointer");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  enterCtx(c);
+  if (int rc = checkHostEnqueue(c, q, n, flags, valid_bitmap, true))
+    return rc;
+  return checkHostFinish(c, n, flags, valid_bitmap);
+}
+
+// ---- DistanceFieldCacheEntry updates without re-creating the context (a15) ---------------------------------------------
+static int rederiveTables(b200sv_ctx* c)
+{
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (c->copy_stream)
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+  const int compact_before = c->compact_bytes;
+  int rc = buildTables(c);
+  if (rc != B200SV_OK)
+    return rc;
+  if (c->compact_bytes != compact_before)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "the update changes the compact field's element size");
+  c->edge_factor_cached.clear();
+  c->edge_cont_cached.clear();
+  return uploadTables(c);
+}
+
+int b200sv_set_acm_masks(b200sv_ctx* c, const uint8_t* self_enabled, const uint8_t* intra_enabled)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (!self_enabled || !intra_enabled)
+    return fail(c, B200SV_ERR_INVALID, "null mask");
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t n = (size_t)c->cm.n_glinks;
+  const std::vector<uint8_t> keep_s = c->cm.self_enabled, keep_i = c->cm.intra_enabled;
+  c->cm.self_enabled.assign(self_enabled, self_enabled + n);
+  c->cm.intra_enabled.assign(intra_enabled, intra_enabled + n * n);
+  if (c->device < 0)
+    return buildTables(c);
+  enterCtx(c);
+  int rc = rederiveTables(c);
+  if (rc != B200SV_OK)
+  {  // keep the context usable with the masks it had
+    c->cm.self_enabled = keep_s;
+    c->cm.intra_enabled = keep_i;
+    const std::string msg = c->err;
+    if (buildTables(c) == B200SV_OK)
+      uploadTables(c);
+    c->err = msg;
+  }
+  return rc;
+}
+
+int b200sv_set_base_state(b200sv_ctx* c, const double* base_positions, int rebuild_self_field)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (!base_positions)
+    return fail(c, B200SV_ERR_INVALID, "null base state");
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->robot.base_positions.assign(base_positions, base_positions + c->robot.n_vars);
+  if (c->device < 0)
+    return buildTables(c);
+  enterCtx(c);
+  int rc = rederiveTables(c);
+  if (rc != B200SV_OK || !rebuild_self_field)
+    return rc;
+  if (c->self_local.empty() && !c->self_points.empty())
+    return fail(c, B200SV_ERR_UNSUPPORTED, "the self field's link points are not known to this context");
+  // the self field of the new cache entry: the non-group links' interior points at the new state (:907-953)
+  poseSelfPoints(c->robot, c->robot.base_positions, c->self_local, c->self_points);
+  Field& F = c->fields[B200SV_FIELD_SELF];
+  CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
+  const size_t n = c->self_points.size() / 3;
+  if (n)
+  {
+    CU(c, c->d_points.ensure(3 * n));
+    CU(c, cudaMemcpyAsync(c->d_points.p, c->self_points.data(), 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = addOrRemove(c, B200SV_FIELD_SELF, c->d_points.p, n, true, c->stream)) != B200SV_OK)
+      return rc;
+  }
+  return rebuildField(c, B200SV_FIELD_SELF);
+}
+
+int b200sv_set_self_link_points(b200sv_ctx* c, int32_t link_index, const double* xyz_link_frame, size_t n_points)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (link_index < 0 || link_index >= c->robot.n_links || (n_points && !xyz_link_frame))
+    return fail(c, B200SV_ERR_INVALID, "bad link index or null points");
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (auto& lp : c->self_local)
+    if (lp.first == link_index)
+    {
+      lp.second.assign(xyz_link_frame, xyz_link_frame + 3 * n_points);
+      return B200SV_OK;
+    }
+  c->self_local.push_back({ link_index, std::vector<double>(xyz_link_frame, xyz_link_frame + 3 * n_points) });
+  return B200SV_OK;
+}
+
+// ---- field replication across contexts / processes -----------------------------------------------------------------------
+// layout of an exported field: [occupancy words | d2 uint16 | this field's compact elements], each part 256-byte aligned
+static size_t exportParts(const b200sv_ctx* c, size_t* occ_bytes, size_t* d2_off, size_t* cmp_off)
+{
+  const size_t ob = (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4;
+  const size_t a = (ob + 255) & ~(size_t)255, b = (c->n_voxels * 2 + 255) & ~(size_t)255;
+  if (occ_bytes) *occ_bytes = ob;
+  if (d2_off) *d2_off = a;
+  if (cmp_off) *cmp_off = a + b;
+  return a + b + ((c->n_voxels * (size_t)c->compact_bytes + 255) & ~(size_t)255);
+}
+
+int b200sv_field_export_size(const b200sv_ctx* c, size_t* n_bytes)
+{
+  if (!c || !n_bytes)
+    return B200SV_ERR_INVALID;
+  *n_bytes = exportParts(c, nullptr, nullptr, nullptr);
+  return B200SV_OK;
+}
+
+static int fieldTransfer(b200sv_ctx* c, int which, uint8_t* d_buf, void* cuda_stream, bool to_buf)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!d_buf)
+    return fail(c, B200SV_ERR_INVALID, "null device buffer");
+  if (c->fields[which].nd2)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "signed fields are rebuilt per context, not replicated");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  if ((rc = enterUser(c, s)) != B200SV_OK)
+    return rc;
+  size_t ob, d2_off, cmp_off;
+  exportParts(c, &ob, &d2_off, &cmp_off);
+  Field& F = c->fields[which];
+  if (to_buf)
+  {
+    CU(c, cudaMemcpyAsync(d_buf, F.occ, ob, cudaMemcpyDeviceToDevice, s));
+    CU(c, cudaMemcpyAsync(d_buf + d2_off, F.d2, c->n_voxels * 2, cudaMemcpyDeviceToDevice, s));
+  }
+  else
+  {
+    CU(c, cudaMemcpyAsync(F.occ, d_buf, ob, cudaMemcpyDeviceToDevice, s));
+    CU(c, cudaMemcpyAsync(F.d2, d_buf + d2_off, c->n_voxels * 2, cudaMemcpyDeviceToDevice, s));
+  }
+  // this field's elements of the interleaved compact field
+  CU(c, launchCompactCopy(F.compact, d_buf + cmp_off, c->n_voxels, c->compact_bytes, to_buf, s));
+  return leaveUser(c, s);
+}
+
+int b200sv_field_export_device(b200sv_ctx* c, int which, void* d_buf, void* cuda_stream)
+{
+  return c ? fieldTransfer(c, which, static_cast<uint8_t*>(d_buf), cuda_stream, true) : B200SV_ERR_INVALID;
+}
+
+int b200sv_field_import_device(b200sv_ctx* c, int which, const void* d_buf, void* cuda_stream)
+{
+  return c ? fieldTransfer(c, which, static_cast<uint8_t*>(const_cast<void*>(d_buf)), cuda_stream, false) : B200SV_ERR_INVALID;
+}
+
+// ---- several GPUs behind one handle (states sharded, fields replicated) ---------------------------
+// One context per device; a batch is cut into contiguous blocks (multiples of 32 states, so every block's bitmap is whole
+// words and lands directly in the caller's buffer), all blocks are enqueued before any is waited for, and a field is built
+// ONCE (on the first device) and copied to the others device-to-device (NVLink when peer access is available).
+
+static int multiFail(b200sv_multi* m, int code, const std::string& msg)
+{
+  if (m)
+    m->err = msg;
+  else
+    g_create_error = msg;
+  return code;
+}
+
+static void enablePeers(const std::vector<b200sv_ctx*>& ctx)
+{
+  for (b200sv_ctx* a : ctx)
+    for (b200sv_ctx* b : ctx)
+      if (a->device != b->device)
+      {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, a->device, b->device);
+        if (can)
+        {
+          cudaSetDevice(a->device);
+          if (cudaDeviceEnablePeerAccess(b->device, 0) != cudaSuccess)
+            cudaGetLastError();  // already enabled
+        }
+      }
+}
+
+int b200sv_create_multi_from_urdf(const int* devices, int n_dev, const char* urdf_xml, const char* srdf_xml,
+                                  const char* group_name, const b200sv_field_cfg* field, b200sv_multi** out)
+{
+  if (!devices || n_dev < 1 || n_dev > 64 || !out)
+    return fail(nullptr, B200SV_ERR_INVALID, "bad device list");
+  *out = nullptr;
+  auto* m = new b200sv_multi();
+  for (int i = 0; i < n_dev; ++i)
+  {
+    b200sv_ctx* c = nullptr;
+    const int rc = b200sv_create_from_urdf(devices[i], urdf_xml, srdf_xml, group_name, field, &c);
+    if (rc != B200SV_OK)
+    {
+      for (b200sv_ctx* d : m->ctx)
+        b200sv_destroy(d);
+      delete m;
+      return rc;
+    }
+    m->ctx.push_back(c);
+  }
+  enablePeers(m->ctx);
+  *out = m;
+  return B200SV_OK;
+}
+
+int b200sv_create_multi(const int* devices, int n_dev, const b200sv_robot* robot, const b200sv_collision_model* model,
+                        const b200sv_field_cfg* field, b200sv_multi** out)
+{
+  if (!devices || n_dev < 1 || n_dev > 64 || !out)
+    return fail(nullptr, B200SV_ERR_INVALID, "bad device list");
+  *out = nullptr;
+  auto* m = new b200sv_multi();
+  for (int i = 0; i < n_dev; ++i)
+  {
+    b200sv_ctx* c = nullptr;
+    const int rc = b200sv_create(devices[i], robot, model, field, &c);
+    if (rc != B200SV_OK)
+    {
+      for (b200sv_ctx* d : m->ctx)
+        b200sv_destroy(d);
+      delete m;
+      return rc;
+    }
+    m->ctx.push_back(c);
+  }
+  enablePeers(m->ctx);
+  *out = m;
+  return B200SV_OK;
+}
+
+void b200sv_destroy_multi(b200sv_multi* m)
+{
+  if (!m)
+    return;
+  for (b200sv_ctx* c : m->ctx)
+    b200sv_destroy(c);
+  delete m;
+}
+
+const char* b200sv_multi_last_error(const b200sv_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+int b200sv_multi_device_count(const b200sv_multi* m) { return m ? (int)m->ctx.size() : 0; }
+b200sv_ctx* b200sv_multi_ctx(b200sv_multi* m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+
+// field `which` of context 0 -> every other context, device to device
+int b200sv_multi_field_sync(b200sv_multi* m, int which)
+{
+  if (!m)
+    return B200SV_ERR_INVALID;
+  if (which != B200SV_FIELD_WORLD && which != B200SV_FIELD_SELF)
+    return multiFail(m, B200SV_ERR_INVALID, "field selector must be B200SV_FIELD_WORLD or B200SV_FIELD_SELF");
+  std::lock_guard<std::mutex> lk(m->mu);
+  b200sv_ctx* src = m->ctx[0];
+  std::lock_guard<std::mutex> ls(src->mu);
+  enterCtx(src);
+  if (cudaStreamSynchronize(src->stream) != cudaSuccess)
+    return multiFail(m, B200SV_ERR_CUDA, "source stream failed");
+  const size_t occ_bytes = (size_t)src->grid.nx * src->grid.ny * src->grid.wz * 4;
+  for (size_t i = 1; i < m->ctx.size(); ++i)
+  {
+    b200sv_ctx* dst = m->ctx[i];
+    std::lock_guard<std::mutex> ld(dst->mu);
+    enterCtx(dst);
+    Field &S = src->fields[which], &D = dst->fields[which];
+    cudaError_t e = cudaMemcpyPeerAsync(D.occ, dst->device, S.occ, src->device, occ_bytes, dst->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeerAsync(D.d2, dst->device, S.d2, src->device, src->n_voxels * 2, dst->stream);
+    if (e == cudaSuccess && S.nd2 && D.nd2)
+      e = cudaMemcpyPeerAsync(D.nd2, dst->device, S.nd2, src->device, src->n_voxels * 2, dst->stream);
+    // the interleaved compact field holds BOTH fields; the other one is identical on every device already (every
+    // field change goes through this function), so the whole array can be copied
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeerAsync(dst->d_combined, dst->device, src->d_combined, src->device,
+                              src->n_voxels * 2 * (size_t)src->compact_bytes, dst->stream);
+    if (e != cudaSuccess)
+      return multiFail(m, B200SV_ERR_CUDA, std::string("peer copy of the field: ") + cudaGetErrorString(e));
+  }
+  for (size_t i = 1; i < m->ctx.size(); ++i)
+  {
+    cudaSetDevice(m->ctx[i]->device);
+    if (cudaStreamSynchronize(m->ctx[i]->stream) != cudaSuccess)
+      return multiFail(m, B200SV_ERR_CUDA, "peer copy of the field failed");
+  }
+  return B200SV_OK;
+}
+
+int b200sv_multi_field_add_points(b200sv_multi* m, int which, const double* xyz, size_t n_points)
+{
+  if (!m)
+    return B200SV_ERR_INVALID;
+  int rc = b200sv_field_add_points(m->ctx[0], which, xyz, n_points);
+  if (rc != B200SV_OK)
+    return multiFail(m, rc, m->ctx[0]->err);
+  m->stats.edt_ms = m->ctx[0]->stats.edt_ms;
+  return b200sv_multi_field_sync(m, which);
+}
+
+int b200sv_multi_field_reset(b200sv_multi* m, int which)
+{
+  if (!m)
+    return B200SV_ERR_INVALID;
+  for (b200sv_ctx* c : m->ctx)
+    if (int rc = b200sv_field_reset(c, which))
+      return multiFail(m, rc, c->err);
+  return B200SV_OK;
+}
+
+// Batched check over every device of the handle: block i of the states goes to context i.  q and valid_bitmap are host
+// buffers (pinned memory makes every copy a DMA that overlaps the other devices' work).
+int b200sv_check_batch_multi(b200sv_multi* m, const double* q, size_t n, uint32_t flags, uint8_t* valid_bitmap)
+{
+  if (!m)
+    return B200SV_ERR_INVALID;
+  if (n && (!q || !valid_bitmap))
+    return multiFail(m, B200SV_ERR_INVALID, "null host pointer");
+  if ((flags & 7u) == 0)
+    return multiFail(m, B200SV_ERR_INVALID, "flags select no check");
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(m->mu);
+  const size_t G = m->ctx.size(), V = m->ctx[0]->robot.group_var_index.size();
+  const size_t per = ((n + G - 1) / G + 31) / 32 * 32;  // states per device: whole bitmap words
+  struct Part
+  {
+    b200sv_ctx* c;
+    size_t lo, cnt;
+    bool small;
+  };
+  std::vector<Part> parts;
+  for (size_t g = 0; g < G; ++g)
+  {
+    const size_t lo = std::min(g * per, n), hi = std::min(lo + per, n);
+    if (hi > lo)
+      parts.push_back(Part{ m->ctx[g], lo, hi - lo, hi - lo <= kSmallBatch });
+  }
+  int rc = B200SV_OK;
+  size_t locked = 0;
+  for (; locked < parts.size(); ++locked)
+    parts[locked].c->mu.lock();
+  // enqueue everything, then wait: the devices work concurrently
+  size_t enq = 0;
+  for (; enq < parts.size() && rc == B200SV_OK; ++enq)
+  {
+    Part& p = parts[enq];
+    enterCtx(p.c);
+    if (p.small)
+      continue;  // latency-sized tails run in the second loop
+    rc = checkHostEnqueue(p.c, q + p.lo * V, p.cnt, flags, valid_bitmap + p.lo / 8);
+    if (rc != B200SV_OK)
+      multiFail(m, rc, p.c->err);
+  }
+  uint64_t valid = 0, rechecked = 0;
+  float ms = 0.f;
+  for (size_t i = 0; i < parts.size(); ++i)
+  {
+    Part& p = parts[i];
+    if (rc == B200SV_OK && i < enq)
+    {
+      int r = p.small ? checkSmall(p.c, q + p.lo * V, p.cnt, flags, valid_bitmap + p.lo / 8) :
+                        checkHostFinish(p.c, p.cnt, flags, valid_bitmap + p.lo / 8);
+      if (r != B200SV_OK)
+      {
+        rc = r;
+        multiFail(m, rc, p.c->err);
+      }
+      valid += p.c->stats.n_valid;
+      rechecked += p.c->stats.n_rechecked;
+      ms = std::max(ms, p.c->stats.check_ms);
+    }
+    else if (i < enq && !p.small)
+    {
+      cudaSetDevice(p.c->device);
+      cudaStreamSynchronize(p.c->stream);  // a failed call leaves nothing in flight
+    }
+  }
+  for (size_t i = 0; i < locked; ++i)
+    parts[i].c->mu.unlock();
+  m->stats.n_states = n;
+  m->stats.n_valid = valid;
+  m->stats.n_rechecked = rechecked;
+  m->stats.check_ms = ms;
+  return rc;
+}
+
+int b200sv_multi_get_stats(b200sv_multi* m, b200sv_stats* stats)
+{
+  if (!m || !stats)
+    return B200SV_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  *stats = m->stats;
+  return B200SV_OK;
+}
+
 int b200sv_gather_roofline(b200sv_ctx* c, size_t n_reads, int iters, double* gbs)
 {
   if (!c || !gbs || iters < 1)
@@ -2732,7 +3371,7 @@ int b200sv_gather_roofline(b200sv_ctx* c, size_t n_reads, int iters, double* gbs
   if (needDevice(c))
     return B200SV_ERR_NO_DEVICE;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   const size_t field_bytes = c->n_voxels * 2 * (size_t)c->compact_bytes;
   const unsigned long long n_sectors = field_bytes / 32;
   if (n_sectors == 0)
@@ -2764,7 +3403,7 @@ int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int warps_per_block, int
   if (needDevice(c))
     return B200SV_ERR_NO_DEVICE;
   std::lock_guard<std::mutex> lk(c->mu);
-  cudaSetDevice(c->device);
+  enterCtx(c);
   if (fp32_eps_m > 0.0)
     c->fp32_eps = fp32_eps_m;
   if (warps_per_block > 0)

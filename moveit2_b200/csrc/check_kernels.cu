@@ -686,20 +686,25 @@ __global__ void __launch_bounds__(128) fkKernel(FkArgs a)
       fkState<R>(m, a.q + (first + lane) * h.n_group_vars, Ts + lane * h.state_stride);
     __syncwarp();
     // write-out: lanes stride over (state, model link, element)
+    // (a state's L 4x4 matrices are 128 L contiguous bytes: every warp store is 256 contiguous bytes; no index division)
     const int per_state = a.n_model_links * 16;
-    for (int i = lane; i < cnt * per_state; i += 32)
+    for (int s = 0; s < cnt; ++s)
     {
-      const int s = i / per_state, rem = i - s * per_state;
-      const int l = rem >> 4, e = rem & 15, c = e >> 2, r = e & 3;
-      double v;
-      const int slot = a.link_slot[l];
-      if (r == 3)
-        v = c == 3 ? 1.0 : 0.0;
-      else if (slot >= 0)
-        v = static_cast<double>(Ts[s * h.state_stride + slot * kLinkStrideWords + r * 4 + c]);
-      else
-        v = a.const_T[l * 16 + e];
-      a.out[(first + s) * per_state + rem] = v;
+      const R* Tstate = Ts + s * h.state_stride;
+      double* dst = a.out + (first + s) * per_state;
+      for (int rem = lane; rem < per_state; rem += 32)
+      {
+        const int l = rem >> 4, e = rem & 15, c = e >> 2, r = e & 3;
+        double v;
+        const int slot = __ldg(a.link_slot + l);
+        if (r == 3)
+          v = c == 3 ? 1.0 : 0.0;
+        else if (slot >= 0)
+          v = static_cast<double>(Tstate[slot * kLinkStrideWords + r * 4 + c]);
+        else
+          v = __ldg(a.const_T + l * 16 + e);
+        dst[rem] = v;
+      }
     }
     __syncwarp();
   }
@@ -726,22 +731,24 @@ __global__ void sphereCentersKernel(FkArgs a, double* centers)
   }
 }
 
-// Random 32-byte-sector gather: every thread reads `per_thread` pseudo-random sectors of the field footprint.
+// Random 32-byte-sector gather: every thread reads `per_thread` pseudo-random sectors of the field footprint.  The inner
+// loop is one 32-bit xorshift step (3 shifts + 3 xors), one multiply-shift to map the draw onto [0, n_sectors) (no division)
+// and the load, so the measured rate is the memory system's, not the address generator's (ncu: profiles/r2_gather_*).
 __global__ void gatherKernel(const uint8_t* __restrict__ field, unsigned long long n_sectors, int per_thread,
                              unsigned* sink)
 {
-  unsigned long long x = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull +
-                         0xD1B54A32D192ED03ull;
+  unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B9u + 0x7F4A7C15u;
+  x |= 1u;
+  const unsigned ns = static_cast<unsigned>(n_sectors);  // the launcher keeps the footprint below 2^32 sectors
   unsigned acc = 0;
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < per_thread; ++i)
   {
-    x ^= x >> 12;
-    x ^= x << 25;
-    x ^= x >> 27;
-    const unsigned long long r = x * 0x2545F4914F6CDD1Dull;
-    const unsigned long long sec = (r >> 11) % n_sectors;
-    acc += __ldg(field + sec * 32 + (r & 31));
+    x ^= x << 13;
+    x ^= x >> 17;
+    x ^= x << 5;
+    const unsigned sec = __umulhi(x, ns);  // uniform on [0, ns)
+    acc += __ldg(field + static_cast<size_t>(sec) * 32 + (x & 31u));
   }
   if (acc == 0xffffffffu)
     *sink = acc;
@@ -1070,6 +1077,55 @@ __global__ void __launch_bounds__(128) recheckWarpKernel(CheckArgs<FT> a)
   }
 }
 
+// The latency path of b200sv_check_batch (a single-state checkCollision through the plugin is a batch of 1): ONE launch and no
+// copies.  The states arrive inside the kernel parameters (or, beyond 32 doubles, are read from mapped pinned host memory); one
+// warp per state runs the exact FP64 check -- the arithmetic every FP32 decision is referred to anyway -- and lane 0 stores the
+// state's result byte (1 = valid, 0 = in collision) straight into mapped host memory, where the host is polling for it.
+template <typename FT>
+__global__ void __launch_bounds__(128) latencyCheckKernel(LatencyArgs<FT> a)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
+  const ModelHeader<double>& h = *m.h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  double* T = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(warp) * (a.state_stride + 32);
+  double* qs = T + a.state_stride;  // this warp's copy of its state
+  const bool do_world = (a.flags & 1u) != 0, do_self = (a.flags & 2u) != 0, do_intra = (a.flags & 4u) != 0;
+  const typename Combined<FT>::type* __restrict__ field = static_cast<const typename Combined<FT>::type*>(a.field);
+  const int state = blockIdx.x * warps + warp;
+  if (state >= a.n_states)
+    return;
+  if (lane < h.n_group_vars)
+    qs[lane] = a.use_inline ? a.q_inline[state * h.n_group_vars + lane] : a.q[state * h.n_group_vars + lane];
+  __syncwarp();
+  if (lane == 0)
+    fkState<double>(m, qs, T);
+  __syncwarp();
+  bool hit = false, amb = false;
+  if (do_world | do_self)
+    for (int k = lane; k < h.n_spheres_padded; k += 32)
+      sphereChunk<double, FT, 1>(m, T, k, do_world, do_self, field, true, hit, amb);
+  if (do_intra && !__any_sync(kFull, hit))
+    for (int p = lane; p < h.n_pairs; p += 32)
+    {
+      const PairRec pr = m.pairs[p];
+      const BsRec<double>& A = m.bs[pr.a];
+      double Ta[12], ax, ay, az;
+      load12(T + A.slot * kLinkStrideWords, Ta);
+      posePoint<double>(Ta, A.tx, A.ty, A.tz, ax, ay, az);
+      bool live = false, certain = false;
+      pairCull<double>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr.quirk_free != 0, live, certain);
+      if (live)
+        pairItem<double>(m, T, pr, certain, hit, amb);
+    }
+  const bool any = __any_sync(kFull, hit);
+  if (lane == 0)
+  {
+    a.result[state] = any ? 0 : 1;
+    __threadfence_system();
+  }
+}
+
 // cudaFuncSetAttribute is a host-side driver call: do it when the requirement grows, not on every launch.
 struct SmemGrant
 {
@@ -1126,6 +1182,22 @@ cudaError_t launchRecheckWarp(const CheckArgs<FT>& a, int grid, int state_stride
 }
 template cudaError_t launchRecheckWarp<uint8_t>(const CheckArgs<uint8_t>&, int, int, cudaStream_t);
 template cudaError_t launchRecheckWarp<uint16_t>(const CheckArgs<uint16_t>&, int, int, cudaStream_t);
+
+template <typename FT>
+cudaError_t launchLatencyCheck(const LatencyArgs<FT>& a, cudaStream_t stream)
+{
+  static SmemGrant g;
+  const int block = 128;
+  const size_t smem = ((static_cast<size_t>(a.model_bytes) + 15) & ~static_cast<size_t>(15)) +
+                      static_cast<size_t>(block / 32) * (a.state_stride + 32) * sizeof(double);
+  cudaError_t e = ensureSmem(latencyCheckKernel<FT>, smem, g);
+  if (e != cudaSuccess)
+    return e;
+  latencyCheckKernel<FT><<<(a.n_states + 3) / 4, block, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+template cudaError_t launchLatencyCheck<uint8_t>(const LatencyArgs<uint8_t>&, cudaStream_t);
+template cudaError_t launchLatencyCheck<uint16_t>(const LatencyArgs<uint16_t>&, cudaStream_t);
 
 int checkPerWarpBytes(bool fp64, int state_stride)
 {

@@ -496,6 +496,26 @@ __global__ void updateOccKernel(uint32_t* __restrict__ occ, const uint32_t* __re
   }
 }
 
+template <typename FT>
+__global__ void compactCopyKernel(FT* compact, FT* dense, size_t n, int extract)
+{
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    if (extract)
+      dense[i] = compact[2 * i];
+    else
+      compact[2 * i] = dense[i];
+  }
+}
+
+__global__ void widenStatesKernel(const float* __restrict__ in, double* __restrict__ out, size_t n)
+{
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<double>(in[i]);
+}
+
 int gridFor(size_t n, int block, int cap)
 {
   size_t b = (n + block - 1) / block;
@@ -592,6 +612,26 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
     edtXKernel<uint8_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint8_t*>(compact));
   else
     edtXKernel<uint16_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint16_t*>(compact));
+  return cudaGetLastError();
+}
+
+cudaError_t launchCompactCopy(void* compact, void* dense, size_t n_voxels, int compact_bytes, bool extract, cudaStream_t s)
+{
+  const int grid = gridFor(n_voxels, 256, 148 * 16);
+  if (compact_bytes == 1)
+    compactCopyKernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<uint8_t*>(compact), static_cast<uint8_t*>(dense), n_voxels,
+                                                    extract ? 1 : 0);
+  else
+    compactCopyKernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<uint16_t*>(compact), static_cast<uint16_t*>(dense), n_voxels,
+                                                     extract ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launchWidenStates(const float* in, double* out, size_t n, cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  widenStatesKernel<<<gridFor(n, 256, 148 * 16), 256, 0, s>>>(in, out, n);
   return cudaGetLastError();
 }
 

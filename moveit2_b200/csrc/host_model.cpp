@@ -229,7 +229,7 @@ struct Group
 }  // namespace
 
 bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::string& group_name, double resolution,
-                  HostRobot& robot, HostCollisionModel& cm, std::vector<double>& self_points, std::string& err,
+                  HostRobot& robot, HostCollisionModel& cm, std::vector<double>& self_points, SelfLocalPoints& self_local, std::string& err,
                   bool& parse_error)
 {
   parse_error = true;
@@ -926,16 +926,28 @@ bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::s
   }
 
   // ---- self-field points: links with geometry outside the updated set, posed at the base state (:907-953) ----------------
-  std::vector<Mat4> T;
-  hostForwardKinematics(robot, base, T);
-  self_points.clear();
+  self_local.clear();
   for (const auto& l : links)
   {
     auto d = decomp.find(l.index);
     if (d == decomp.end() || updated.count(l.index))
       continue;
-    const Mat4& Tm = T[l.index];
-    const auto& P = d->second.points;
+    self_local.push_back({ l.index, d->second.points });
+  }
+  poseSelfPoints(robot, base, self_local, self_points);
+  return true;
+}
+
+void poseSelfPoints(const HostRobot& robot, const std::vector<double>& positions, const SelfLocalPoints& self_local,
+                    std::vector<double>& self_points)
+{
+  std::vector<Mat4> T;
+  hostForwardKinematics(robot, positions, T);
+  self_points.clear();
+  for (const auto& lp : self_local)
+  {
+    const Mat4& Tm = T[lp.first];
+    const auto& P = lp.second;
     for (size_t k = 0; k + 2 < P.size(); k += 3)
       for (int r = 0; r < 3; ++r)
       {
@@ -945,6 +957,5 @@ bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::s
         self_points.push_back(s + Mc(Tm, r, 3));
       }
   }
-  return true;
 }
 }  // namespace b200sv

@@ -5,6 +5,7 @@
 #include <array>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "device_model.hpp"
@@ -47,7 +48,13 @@ bool isIdentityTransform(const double* m16);
 
 // URDF + SRDF text -> HostRobot / HostCollisionModel for `group`, plus the self-field points
 // (collision_env_distance_field.cpp:907-953).  SPHERE collision geometry only.  Returns false and sets err.
+// interior lattice points (link frame) of every link with geometry that the group does not move: (link index, xyz...)
+using SelfLocalPoints = std::vector<std::pair<int, std::vector<double>>>;
 bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::string& group, double resolution,
-                  HostRobot& robot, HostCollisionModel& cm, std::vector<double>& self_points, std::string& err,
-                  bool& parse_error);
+                  HostRobot& robot, HostCollisionModel& cm, std::vector<double>& self_points, SelfLocalPoints& self_local,
+                  std::string& err, bool& parse_error);
+// The self field's generating points at `positions` (all model variables): every link's points moved by its global transform
+// (generateDistanceFieldCacheEntry, collision_env_distance_field.cpp:907-953).
+void poseSelfPoints(const HostRobot& robot, const std::vector<double>& positions, const SelfLocalPoints& self_local,
+                    std::vector<double>& self_points);
 }  // namespace b200sv

@@ -56,6 +56,23 @@ cudaError_t launchCheck(const CheckArgs<FT>& a, bool fp64, bool from_list, int g
 // exact pass over the recheck list, one warp per state (latency of a short list)
 template <typename FT>
 cudaError_t launchRecheckWarp(const CheckArgs<FT>& a, int grid, int state_stride, cudaStream_t stream);
+// the latency path: up to 32 states, exact FP64 check, one warp per state, results as bytes in mapped host memory
+template <typename FT>
+struct LatencyArgs
+{
+  const uint8_t* model;  // double blob
+  int model_bytes;
+  const void* field;
+  uint32_t flags;
+  int n_states;
+  int state_stride;      // doubles of link transforms per state (the double blob's)
+  int use_inline;        // the states are q_inline (n_states * n_group_vars <= 32 doubles); else q
+  const double* q;       // device-visible (mapped pinned host) states
+  uint8_t* result;       // device-visible (mapped pinned host) [n_states]: 1 = valid, 0 = in collision
+  double q_inline[32];
+};
+template <typename FT>
+cudaError_t launchLatencyCheck(const LatencyArgs<FT>& a, cudaStream_t stream);
 int checkKernelRegs(bool fp64, bool from_list, int field_bytes);
 int checkPerWarpBytes(bool fp64, int state_stride);  // shared memory one warp of the check kernel needs
 // K5: per-sphere distance / gradient / type (getCollisionGradients), FP64, exact blob
@@ -182,4 +199,9 @@ cudaError_t launchInjectNegD2(const GridDev& g, const int32_t* d_in, uint16_t* n
 cudaError_t launchFillField(const GridDev& g, uint16_t* d2, void* compact, int compact_bytes, cudaStream_t s);
 cudaError_t launchInjectD2(const GridDev& g, const int32_t* d_in, uint32_t* occ, uint16_t* d2, void* compact,
                            int compact_bytes, cudaStream_t s);
+// One field's elements of the interleaved compact field <-> a dense array (field replication across contexts):
+// `compact` is already offset to this field's first element; extract = to the dense array, else from it.
+cudaError_t launchCompactCopy(void* compact, void* dense, size_t n_voxels, int compact_bytes, bool extract, cudaStream_t s);
+// float states -> double states (b200sv_check_batch_f32)
+cudaError_t launchWidenStates(const float* in, double* out, size_t n, cudaStream_t s);
 }  // namespace b200sv

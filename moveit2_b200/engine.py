@@ -303,6 +303,49 @@ class StateValidityEngine:
         self._check(self.L.b200sv_check_batch_device(self.h, C.c_void_p(d_q_ptr), n, int(flags),
                                                      C.c_void_p(d_bitmap_ptr), C.c_void_p(stream)))
 
+    def check_batch_f32(self, q, flags=CHECK_ALL):
+        """float32 states (b200sv_check_batch_f32; not the reference's layout): bool [n], True = valid."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, self.n_group_vars)
+        n = q.shape[0]
+        bm = np.zeros((n + 7) // 8, np.uint8)
+        self._check(self.L.b200sv_check_batch_f32(self.h, C.c_void_p(q.ctypes.data), n, int(flags),
+                                                  C.c_void_p(bm.ctypes.data)))
+        return np.unpackbits(bm, bitorder="little")[:n].astype(bool)
+
+    def check_batch_f32_ptr(self, q_ptr, n, flags, bitmap_ptr):
+        self._check(self.L.b200sv_check_batch_f32(self.h, C.c_void_p(q_ptr), n, int(flags), C.c_void_p(bitmap_ptr)))
+
+    def fk_batch_device(self, d_q_ptr, n, precision, d_out_ptr, stream=0):
+        """Device-resident q -> device-resident [n, n_links, 16] column-major doubles; asynchronous on `stream`."""
+        self._check(self.L.b200sv_fk_batch_device(self.h, C.c_void_p(d_q_ptr), n, int(precision), C.c_void_p(d_out_ptr),
+                                                  C.c_void_p(stream)))
+
+    # ---- cache-entry updates on a live context --------------------------------------------------------------
+    def set_acm_masks(self, self_enabled, intra_enabled):
+        a = np.ascontiguousarray(self_enabled, np.uint8).reshape(self.n_glinks)
+        b = np.ascontiguousarray(intra_enabled, np.uint8).reshape(self.n_glinks * self.n_glinks)
+        self._check(self.L.b200sv_set_acm_masks(self.h, _u8p(a), _u8p(b)))
+
+    def set_base_state(self, base_positions, rebuild_self_field=True):
+        a = np.ascontiguousarray(base_positions, np.float64).reshape(self.n_vars)
+        self._check(self.L.b200sv_set_base_state(self.h, _dp(a), int(bool(rebuild_self_field))))
+
+    def set_self_link_points(self, link_index, xyz_link_frame):
+        a = np.ascontiguousarray(xyz_link_frame, np.float64).reshape(-1, 3)
+        self._check(self.L.b200sv_set_self_link_points(self.h, int(link_index), _dp(a) if len(a) else None, a.shape[0]))
+
+    # ---- field replication ------------------------------------------------------------------------------------
+    def field_export_size(self):
+        n = C.c_size_t(0)
+        self._check(self.L.b200sv_field_export_size(self.h, C.byref(n)))
+        return int(n.value)
+
+    def field_export_device(self, d_buf_ptr, which=FIELD_WORLD, stream=0):
+        self._check(self.L.b200sv_field_export_device(self.h, int(which), C.c_void_p(d_buf_ptr), C.c_void_p(stream)))
+
+    def field_import_device(self, d_buf_ptr, which=FIELD_WORLD, stream=0):
+        self._check(self.L.b200sv_field_import_device(self.h, int(which), C.c_void_p(d_buf_ptr), C.c_void_p(stream)))
+
     def check_motions(self, q_from, q_to, max_segment_length, continuous=None, distance_factor=None,
                       max_states_per_edge=0, flags=CHECK_ALL):
         """Batched edge validation (b200sv_check_motions): (valid bool [M], first_invalid int32 [M], n_states)."""
@@ -366,6 +409,79 @@ class StateValidityEngine:
 
     def set_tuning(self, fp32_eps_m=0.0, warps_per_block=0, blocks_per_sm=0):
         self._check(self.L.b200sv_set_tuning(self.h, float(fp32_eps_m), int(warps_per_block), int(blocks_per_sm)))
+
+
+class _BorrowedEngine(StateValidityEngine):
+    """A context owned by a MultiDeviceEngine: never destroyed on its own."""
+
+    def close(self):
+        self.h = None
+
+
+class MultiDeviceEngine:
+    """Several GPUs of one box behind one handle (b200sv_create_multi*): states sharded, fields built once and replicated."""
+
+    def __init__(self, handle):
+        self.L = _lib.load()
+        self.h = handle
+        self.n_devices = self.L.b200sv_multi_device_count(self.h)
+        self.contexts = [_BorrowedEngine(C.c_void_p(self.L.b200sv_multi_ctx(self.h, i))) for i in range(self.n_devices)]
+        self.n_group_vars = self.contexts[0].n_group_vars
+
+    @classmethod
+    def from_urdf(cls, devices, urdf_xml, srdf_xml, group, size, origin, resolution, max_distance, tolerance=0.0):
+        L = _lib.load()
+        h = C.c_void_p()
+        cfg = field_cfg(size, origin, resolution, max_distance, tolerance)
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = L.b200sv_create_multi_from_urdf(dev, len(devices), urdf_xml.encode(), (srdf_xml or "").encode(),
+                                             group.encode(), C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise B200svError(rc, (L.b200sv_last_error(None) or b"").decode())
+        return cls(h)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200svError(rc, (self.L.b200sv_multi_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            for c in self.contexts:
+                c.close()
+            self.L.b200sv_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def field_add_points(self, points, which=FIELD_WORLD):
+        p = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        self._check(self.L.b200sv_multi_field_add_points(self.h, int(which), _dp(p), p.shape[0]))
+
+    def field_sync(self, which=FIELD_WORLD):
+        self._check(self.L.b200sv_multi_field_sync(self.h, int(which)))
+
+    def field_reset(self, which=FIELD_WORLD):
+        self._check(self.L.b200sv_multi_field_reset(self.h, int(which)))
+
+    def check_batch_ptr(self, q_ptr, n, flags, bitmap_ptr):
+        self._check(self.L.b200sv_check_batch_multi(self.h, C.c_void_p(q_ptr), n, int(flags), C.c_void_p(bitmap_ptr)))
+
+    def check_batch(self, q, flags=CHECK_ALL):
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, self.n_group_vars)
+        n = q.shape[0]
+        bm = np.zeros((n + 7) // 8 + 4, np.uint8)
+        self.check_batch_ptr(q.ctypes.data, n, flags, bm.ctypes.data)
+        return np.unpackbits(bm, bitorder="little")[:n].astype(bool)
+
+    def stats(self):
+        s = _lib.Stats()
+        self._check(self.L.b200sv_multi_get_stats(self.h, C.byref(s)))
+        return dict(n_states=s.n_states, n_valid=s.n_valid, n_rechecked=s.n_rechecked, check_ms=s.check_ms,
+                    edt_ms=s.edt_ms)
 
 
 # ---------------------------------------------------------------------------------------------------------

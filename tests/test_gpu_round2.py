@@ -1,0 +1,298 @@
+"""GPU parity tests of the entry points added in round 2 (run on the B200 box: pytest -m gpu): the full-size C4 rebuild,
+the single-launch latency path, float32 states, cache-entry updates on a live context (ACM masks, base state), field
+replication, several devices behind one handle, device-resident FK."""
+import os
+
+import numpy as np
+import pytest
+
+import moveit2_b200 as mb
+from moveit2_b200 import workloads
+from oracle.collision_model import OracleEnv
+from oracle.df import PropagationDistanceField
+from oracle.robot_model import RobotModel
+
+from util import RES, config_pair, make_pair, read
+
+pytestmark = pytest.mark.gpu
+
+ALL = mb.CHECK_ALL
+
+
+@pytest.fixture(scope="module")
+def c1():
+    eng, env, cloud, q = config_pair("C1")
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    yield eng, env, cloud, q
+    eng.close()
+
+
+def test_edt_c4_full_size_is_the_exact_transform_and_never_above_the_reference():
+    """BASELINE.json configs[3] at FULL size: 5 M points -> 400 x 400 x 200 voxels @ 1 cm, 25-cell truncation (4 y chunks
+    per plane).  All 32 M voxels: occupancy == the reference's (oracle port of addPointsToField), distances == the exact
+    truncated EDT (scipy), GPU <= the reference's propagation everywhere; the differing voxels are counted."""
+    from scipy import ndimage
+    c4 = workloads.CONFIGS["C4"]
+    eng = mb.StateValidityEngine.for_robot("panda", "panda_arm", size=c4["size"], origin=c4["origin"],
+                                           resolution=c4["resolution"], max_distance=c4["max_distance"])
+    pts = workloads.make_cloud("C4")
+    eng.field_add_points(pts)
+    g = eng.field_get_d2()
+    assert g.shape == (400, 400, 200) and eng.max_distance_sq == 625
+    exact = ndimage.distance_transform_edt(g != 0)
+    exact = np.minimum(np.rint(exact * exact).astype(np.int64), eng.max_distance_sq)
+    n_bad = int((g != exact).sum())
+    assert n_bad == 0, "%d of %d voxels differ from the exact truncated EDT" % (n_bad, g.size)
+    del exact
+    sx, sy, sz = c4["size"]
+    ox, oy, oz = c4["origin"]
+    ref = PropagationDistanceField(sx, sy, sz, c4["resolution"], ox - sx / 2, oy - sy / 2, oz - sz / 2, c4["max_distance"])
+    ref.add_points(pts)
+    o = ref.d2()
+    assert np.array_equal(g == 0, o == 0), "occupancy differs from the reference's addPointsToField"
+    assert (g <= o).all(), "GPU above the reference's propagation somewhere"
+    print("C4: %d occupied voxels; %d of %d voxels below the reference's propagation (max delta %d)" %
+          (int((g == 0).sum()), int((g != o).sum()), g.size, int((o - g).max())))
+    # the rebuild is a function of the occupancy set only: a second build from shuffled points gives the same field
+    eng.field_reset()
+    eng.field_add_points(pts[np.random.default_rng(0).permutation(len(pts))])
+    assert np.array_equal(eng.field_get_d2(), g)
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 32])
+def test_latency_path_is_bit_exact(c1, n):
+    """Batches of up to 32 states take ONE kernel launch (latencyCheckKernel, exact FP64, results polled in mapped host
+    memory); same booleans as the oracle and as the large-batch path."""
+    eng, env, cloud, q = c1
+    for start in (0, 100, 977):
+        qs = q[start:start + n]
+        for flags in (ALL, mb.CHECK_WORLD, mb.CHECK_SELF | mb.CHECK_INTRA):
+            ref, _ = env.check(qs, flags)
+            got = eng.check_batch(qs, flags)
+            assert np.array_equal(got, ref == 0)
+            assert eng.stats()["n_states"] == n and eng.stats()["n_valid"] == int(got.sum())
+    big = eng.check_batch(q[:4096], ALL)
+    for i in range(0, 64, 7):
+        assert eng.check_batch(q[i:i + 1], ALL)[0] == big[i]
+
+
+def test_latency_path_many_calls_and_wide_group():
+    """1 000 single-state calls in a row (the buffer and the polling are reused), and a group whose states do not fit the
+    kernel parameters (18 variables x 2 states > 32 doubles: read from mapped host memory)."""
+    eng, env = make_pair("dualarm", "whole_body", (3.0, 3.0, 2.5), (0, 0, 1.0), 0.05, 0.25)
+    cloud = workloads.clutter_cloud(6, 20000, 12, (-1.3, -1.3, 0.1), (1.3, 1.3, 2.0), 0.75)
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    lo, hi = eng.group_bounds()
+    lo, hi = np.maximum(lo, -3.0), np.minimum(hi, 3.0)
+    q = workloads.random_states(3, 1000, lo, hi)
+    ref, _ = env.check(q, ALL)
+    got = np.array([eng.check_batch(q[i:i + 1], ALL)[0] for i in range(len(q))])
+    assert np.array_equal(got, ref == 0) and 0 < got.sum() < len(q)
+    for i in range(0, 90, 3):
+        assert np.array_equal(eng.check_batch(q[i:i + 3], ALL), ref[i:i + 3] == 0)
+    eng.close()
+
+
+def test_float32_states(c1):
+    """b200sv_check_batch_f32: every value is widened on the device, so the result is the oracle's for q = double(float)."""
+    eng, env, cloud, q = c1
+    qf = q.astype(np.float32)
+    ref, _ = env.check(qf.astype(np.float64), ALL)
+    got = eng.check_batch_f32(qf, ALL)
+    assert np.array_equal(got, ref == 0)
+    # ragged sizes around the chunking of the copy pipeline
+    for n in (1, 33, 4097):
+        assert np.array_equal(eng.check_batch_f32(qf[:n], ALL), ref[:n] == 0)
+
+
+def _srdf_without(srdf, a, b):
+    keep = [ln for ln in srdf.splitlines() if not ("disable_collisions" in ln and ('"%s"' % a) in ln and ('"%s"' % b) in ln)]
+    assert len(keep) < len(srdf.splitlines())
+    return "\n".join(keep)
+
+
+def test_acm_change_on_a_live_context():
+    """compareCacheEntryToAllowedCollisionMatrix (collision_env_distance_field.cpp:1314-1370): when the ACM changes the
+    reference regenerates the cache entry.  b200sv_set_acm_masks re-derives the masks in place; the result must equal a
+    FRESH oracle env built with the changed ACM -- and differ from the old one."""
+    urdf, srdf = read(RES, "panda_spheres.urdf"), read(RES, "panda.srdf")
+    geo = ((1.0, 1.0, 1.0), (0.0, 0.0, 0.5), 0.02, 0.25)
+    eng = mb.StateValidityEngine.from_urdf(urdf, srdf, "panda_arm", *geo)
+    env0 = OracleEnv(RobotModel(urdf, srdf), "panda_arm", *geo)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(21, 20000, lo, hi)
+    flags = mb.CHECK_SELF | mb.CHECK_INTRA
+    ref0, _ = env0.check(q, flags)
+    eng.field_set_d2(env0.self_field.d2(), mb.FIELD_SELF)
+    assert np.array_equal(eng.check_batch(q, flags), ref0 == 0)
+    # enable two pairs the SRDF disables: more states collide
+    srdf1 = _srdf_without(_srdf_without(srdf, "panda_link2", "panda_link6"), "panda_leftfinger", "panda_rightfinger")
+    env1 = OracleEnv(RobotModel(urdf, srdf1), "panda_arm", *geo)
+    _, model1 = env1.flat_arrays()
+    eng.set_acm_masks(model1["self_enabled"], model1["intra_enabled"])
+    ref1, _ = env1.check(q, flags)
+    assert (ref1 != ref0).sum() > 0
+    assert np.array_equal(eng.check_batch(q, flags), ref1 == 0)
+    assert np.array_equal(eng.check_batch(q[:16], flags), ref1[:16] == 0)     # the latency path sees the new tables too
+    # and back
+    _, model0 = env0.flat_arrays()
+    eng.set_acm_masks(model0["self_enabled"], model0["intra_enabled"])
+    assert np.array_equal(eng.check_batch(q, flags), ref0 == 0)
+    eng.close()
+
+
+def test_base_state_change_on_a_live_context():
+    """compareCacheEntryToState (:1254-1312): a joint outside the group moved -> new cache entry: constant link transforms
+    and the self field (non-group links' points at the new state, :907-953).  b200sv_set_base_state does it in place; the
+    world field is untouched.  Compared with a FRESH oracle env at the new base state."""
+    urdf, srdf = read(RES, "dualarm_spheres.urdf"), read(RES, "dualarm.srdf")
+    geo = ((3.0, 3.0, 2.5), (0.0, 0.0, 1.0), 0.05, 0.25)
+    eng = mb.StateValidityEngine.from_urdf(urdf, srdf, "left_arm", *geo)
+    model = RobotModel(urdf, srdf)
+    env0 = OracleEnv(model, "left_arm", *geo)
+    cloud = workloads.clutter_cloud(6, 20000, 12, (-1.3, -1.3, 0.1), (1.3, 1.3, 2.0), 0.75)
+    eng.field_add_points(cloud)
+    world_before = eng.field_get_d2()
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(22, 20000, lo, hi)
+    # move every variable outside the group (right arm, torso, ...) inside its bounds
+    base = np.array(env0.base_positions)
+    rng = np.random.default_rng(5)
+    gv = set(int(v) for v in env0.arr["group_var_index"])
+    right = RobotModel(urdf, srdf).groups["right_arm"]
+    for v in right.variable_index_list:
+        if v not in gv:
+            base[v] = rng.uniform(-1.0, 1.0)
+    env1 = OracleEnv(RobotModel(urdf, srdf), "left_arm", *geo, base_positions=base)
+    assert not np.array_equal(env1.self_field.d2(), env0.self_field.d2())
+    eng.set_base_state(base)
+    g_self, o_self = eng.field_get_d2(mb.FIELD_SELF), env1.self_field.d2()
+    assert np.array_equal(g_self == 0, o_self == 0) and (g_self <= o_self).all()
+    assert np.array_equal(eng.field_get_d2(), world_before)
+    assert np.allclose(eng.fk_batch(q[:32]), env1.fk(q[:32]), atol=1e-12)
+    # validity on identical fields
+    env1.world.add_points(cloud)
+    eng.field_set_d2(env1.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(o_self, mb.FIELD_SELF)
+    ref1, _ = env1.check(q, ALL)
+    assert np.array_equal(eng.check_batch(q, ALL), ref1 == 0)
+    env0.world.add_points(cloud)
+    ref0, _ = env0.check(q, ALL)
+    assert (ref0 != ref1).sum() > 0
+    eng.close()
+
+
+def test_field_export_import_between_contexts():
+    torch = pytest.importorskip("torch")
+    eng_a, env, cloud, q = config_pair("C1")
+    eng_b, _, _, _ = config_pair("C1")
+    eng_a.field_add_points(cloud)
+    buf = torch.empty(eng_a.field_export_size(), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for which in (mb.FIELD_WORLD, mb.FIELD_SELF):
+        eng_a.field_export_device(buf.data_ptr(), which, s)
+        eng_b.field_import_device(buf.data_ptr(), which, s)
+    torch.cuda.synchronize()
+    assert np.array_equal(eng_b.field_get_d2(), eng_a.field_get_d2())
+    assert np.array_equal(eng_b.check_batch(q), eng_a.check_batch(q))
+    # the imported occupancy is live: adding points to B continues from it
+    extra = cloud[:10] + 0.07
+    eng_a.field_add_points(extra)
+    eng_b.field_add_points(extra)
+    assert np.array_equal(eng_b.field_get_d2(), eng_a.field_get_d2())
+    eng_a.close()
+    eng_b.close()
+
+
+def test_several_devices_behind_one_handle(c1):
+    """b200sv_create_multi_from_urdf / b200sv_check_batch_multi: states sharded in blocks of whole bitmap words, the field
+    built on the first device and copied to the others.  With one visible GPU the two contexts share it (same code path)."""
+    torch = pytest.importorskip("torch")
+    eng, env, cloud, q = c1
+    n_gpu = torch.cuda.device_count()
+    devices = [0, 1] if n_gpu >= 2 else [0, 0]
+    cfg = workloads.CONFIGS["C1"]
+    me = mb.MultiDeviceEngine.from_urdf(devices, read(RES, "panda_spheres.urdf"), read(RES, "panda.srdf"), cfg["group"],
+                                        cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    assert me.n_devices == 2
+    me.field_add_points(cloud)
+    own = mb.StateValidityEngine.for_robot("panda", "panda_arm", size=cfg["size"], origin=cfg["origin"],
+                                           resolution=cfg["resolution"], max_distance=cfg["max_distance"])
+    own.field_add_points(cloud)
+    for c in me.contexts:                              # every device holds the field device 0 built
+        assert np.array_equal(c.field_get_d2(), own.field_get_d2())
+    qq = np.concatenate([q] * 3)[:25000 + 13]           # ragged: the second block is shorter, the tail is not a whole word
+    want = own.check_batch(qq)
+    assert np.array_equal(me.check_batch(qq), want)
+    assert me.stats()["n_states"] == len(qq) and me.stats()["n_valid"] == int(want.sum())
+    for n in (1, 31, 33, 64, 4096, 8193):
+        assert np.array_equal(me.check_batch(qq[:n]), want[:n])
+    # validity against the oracle on the reference's own field, injected into context 0 and replicated
+    for which, f in ((mb.FIELD_WORLD, env.world), (mb.FIELD_SELF, env.self_field)):
+        me.contexts[0].field_set_d2(f.d2(), which)
+        me.field_sync(which)
+    ref, _ = env.check(q, ALL)
+    assert np.array_equal(me.check_batch(q), ref == 0)
+    own.close()
+    me.close()
+
+
+def test_fk_batch_device_resident(c1):
+    torch = pytest.importorskip("torch")
+    eng, env, cloud, q = c1
+    n = 5000
+    d_q = torch.from_numpy(q[:n]).cuda()
+    out = torch.empty((n, eng.n_links, 16), dtype=torch.float64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for prec, tol in ((64, 1e-12), (32, 1e-5)):
+        eng.fk_batch_device(d_q.data_ptr(), n, prec, out.data_ptr(), s)
+        torch.cuda.synchronize()
+        t = out.cpu().numpy().reshape(n, eng.n_links, 4, 4).transpose(0, 1, 3, 2)
+        assert np.abs(t - env.fk(q[:n])).max() < tol
+
+
+def test_device_entry_points_are_ordered_against_the_context_stream(c1):
+    """A device-resident check on the caller's stream followed at once by host-buffer calls (the context's own stream) and
+    by another device-resident check on a second caller stream: all share the context's recheck list and counter; the
+    library orders them with events.  Every result must be the oracle's."""
+    torch = pytest.importorskip("torch")
+    eng, env, cloud, q = c1
+    ref, _ = env.check(q, ALL)
+    d_q = torch.from_numpy(q).cuda()
+    n = len(q)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    bm1 = torch.zeros(4 * ((n + 31) // 32), dtype=torch.uint8, device="cuda")
+    bm2 = torch.zeros_like(bm1)
+    torch.cuda.synchronize()
+    for _ in range(20):
+        eng.check_batch_device(d_q.data_ptr(), n, ALL, bm1.data_ptr(), s1.cuda_stream)
+        host = eng.check_batch(q[:5000], ALL)
+        eng.check_batch_device(d_q.data_ptr(), n, ALL, bm2.data_ptr(), s2.cuda_stream)
+        one = eng.check_batch(q[:1], ALL)
+        torch.cuda.synchronize()
+        for bm in (bm1, bm2):
+            got = np.unpackbits(bm.cpu().numpy(), bitorder="little")[:n].astype(bool)
+            assert np.array_equal(got, ref == 0)
+        assert np.array_equal(host, ref[:5000] == 0) and one[0] == (ref[0] == 0)
+
+
+def test_c_program_drives_two_devices(tmp_path):
+    """tests/c_multi_check.c, plain C99 against include/b200sv.h: two devices (or one device twice) behind one handle."""
+    import subprocess
+    torch = pytest.importorskip("torch")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "moveit2_b200")
+    exe = str(tmp_path / "c_multi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-O1", "-I", os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "c_multi_check.c"), "-L", libdir, "-lb200sv", "-lm",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, os.path.join(RES, "panda_spheres.urdf"), os.path.join(RES, "panda.srdf"),
+                          str(torch.cuda.device_count())], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c multi ok" in out.stdout
+    print(out.stdout.strip())
