@@ -181,6 +181,12 @@ int b200sv_field_remove_points(b200sv_ctx* ctx, int which, const double* xyz, si
  * are not voxels of old_xyz are added (a voxel in both is left as it is), then the field is rebuilt. */
 int b200sv_field_update_points(b200sv_ctx* ctx, int which, const double* old_xyz, size_t n_old, const double* new_xyz,
                                size_t n_new);
+/* Several occupancy changes, ONE transform: between begin and end every add / remove / update / add_shape call only edits the
+ * occupancy bits; end runs the EDT once if anything changed.  (CollisionEnvDistanceField::updateDistanceObject,
+ * collision_env_distance_field.cpp:1713-1725, removes an object's old points and adds its new ones -- two propagations in
+ * the reference, one rebuild here.)  Reads of the field inside the bracket see the state before it. */
+int b200sv_field_begin_update(b200sv_ctx* ctx, int which);
+int b200sv_field_end_update(b200sv_ctx* ctx, int which);
 /* DistanceField::addShapeToField for a shapes::Sphere (distance_field.cpp:208-238): the interior lattice points of
  * findInternalPointsConvex (find_internal_points.cpp:39-64; bodies::Sphere::containsPoint = |c - p|^2 <= r^2) are marked on
  * the device and the field is rebuilt.  This is the construction of the reference's fixture moveit_core/test_big.df

@@ -82,6 +82,8 @@ def load():
         "b200sv_get_group_bounds": (C.c_int, [vp, dp, dp]),
         "b200sv_get_sphere_thresholds": (C.c_int, [vp, ip]),
         "b200sv_field_reset": (C.c_int, [vp, C.c_int]),
+        "b200sv_field_begin_update": (C.c_int, [vp, C.c_int]),
+        "b200sv_field_end_update": (C.c_int, [vp, C.c_int]),
         "b200sv_field_add_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_field_remove_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_field_add_sphere": (C.c_int, [vp, C.c_int, dp, C.c_double]),

@@ -3,6 +3,11 @@
 // DistanceFieldCacheEntry / GroupStateRepresentation (collision_env_distance_field.cpp:710-958, 1157-1252).
 #include "collision_env_b200.hpp"
 
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
 #include <moveit/robot_model/robot_model.hpp>
 #include <moveit/robot_state/robot_state.hpp>
 #include <moveit/utils/logger.hpp>
@@ -69,12 +74,15 @@ CollisionEnvB200::CollisionEnvB200(const CollisionEnvB200& other, const WorldPtr
   getWorld()->notifyObserverAllObjects(observer_handle_, World::CREATE);
 }
 
+CollisionEnvB200::GroupContext::~GroupContext()
+{
+  if (ctx)
+    b200sv_destroy(ctx);  // runs when the last holder drops the shared_ptr: never under a thread that is still checking
+}
+
 CollisionEnvB200::~CollisionEnvB200()
 {
   getWorld()->removeObserver(observer_handle_);
-  for (auto& kv : contexts_)
-    if (kv.second && kv.second->ctx)
-      b200sv_destroy(kv.second->ctx);
 }
 
 void CollisionEnvB200::initialize()
@@ -96,44 +104,166 @@ void CollisionEnvB200::initialize()
   }
 }
 
-std::shared_ptr<CollisionEnvB200::GroupContext>
-CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::RobotState& state,
-                             const AllowedCollisionMatrix* acm) const
+// ---- generateDistanceFieldCacheEntry, the part that depends on (state, ACM): enable masks + attached bodies (:735-866) ----
+void CollisionEnvB200::flattenModel(const moveit::core::JointModelGroup* jmg, const moveit::core::RobotState& state,
+                                    const AllowedCollisionMatrix* acm, FlatModel& out) const
 {
-  const moveit::core::JointModelGroup* jmg = robot_model_->getJointModelGroup(group_name);
-  if (!jmg)
+  const std::vector<const moveit::core::LinkModel*>& glinks = jmg->getUpdatedLinkModels();
+  const int n = static_cast<int>(glinks.size());
+  out.glink_index.assign(n, 0);
+  out.sphere_start.assign(1, 0);
+  out.self_enabled.assign(n, 1);
+  out.intra_enabled.assign(static_cast<std::size_t>(n) * n, 0);
+  out.sphere_xyzr.clear();
+  out.bounding_sphere.assign(4 * static_cast<std::size_t>(n), 0.0);
+  std::vector<uint8_t>& self_enabled = out.self_enabled;
+  std::vector<uint8_t>& intra_enabled = out.intra_enabled;
+  for (int i = 0; i < n; ++i)
   {
-    RCLCPP_WARN(getLogger(), "No group %s", group_name.c_str());  // :716-720
-    return nullptr;
+    const std::string& name = glinks[i]->getName();
+    out.glink_index[i] = static_cast<int32_t>(glinks[i]->getLinkIndex());
+    auto bd = link_body_decomposition_index_map_.find(name);
+    if (glinks[i]->getShapes().empty() || bd == link_body_decomposition_index_map_.end())
+    {
+      self_enabled[i] = 0;
+      out.sphere_start.push_back(out.sphere_start.back());
+      continue;
+    }
+    AllowedCollision::Type t;
+    if (acm && acm->getEntry(name, name, t) && t == AllowedCollision::ALWAYS)
+      self_enabled[i] = 0;
+    for (int j = 0; j < n; ++j)
+      intra_enabled[static_cast<std::size_t>(i) * n + j] = 1;
+    for (int j = i + 1; j < n; ++j)
+      if (name == glinks[j]->getName() ||
+          (acm && acm->getEntry(name, glinks[j]->getName(), t) && t == AllowedCollision::ALWAYS))
+        intra_enabled[static_cast<std::size_t>(i) * n + j] = 0;
+    const BodyDecompositionConstPtr& d = link_body_decomposition_vector_[bd->second];
+    for (const CollisionSphere& cs : d->getCollisionSpheres())
+      out.sphere_xyzr.insert(out.sphere_xyzr.end(),
+                             { cs.relative_vec_.x(), cs.relative_vec_.y(), cs.relative_vec_.z(), cs.radius_ });
+    out.sphere_start.push_back(static_cast<int32_t>(out.sphere_xyzr.size() / 4));
+    const bodies::BoundingSphere& bs = d->getRelativeBoundingSphere();
+    out.bounding_sphere[4 * i + 0] = bs.center.x();
+    out.bounding_sphere[4 * i + 1] = bs.center.y();
+    out.bounding_sphere[4 * i + 2] = bs.center.z();
+    out.bounding_sphere[4 * i + 3] = bs.radius;
   }
-  std::scoped_lock lock(mutex_);
-  auto it = contexts_.find(group_name);
-  if (it != contexts_.end())
+  // ---- attached bodies: dfce->attached_body_names_ follow the links (:798-822, 840-866) -------------------------------
+  // One entry per SHAPE of each body attached to a group link; the entry repeats the link's index (that is how
+  // libb200sv recognises it), its spheres and bounding sphere are expressed in the LINK frame
+  // (AttachedBody::getShapePosesInLinkFrame() * BodyDecomposition-relative coordinates).  Masks as the reference sets
+  // them: (link, body) is disabled by an ALWAYS entry or a touch link ONLY for the link the body hangs on; body-body by
+  // an ALWAYS entry; shapes of one body never test each other.
+  struct BodyEntry
   {
-    // compareCacheEntryToState: any non-group variable moved by more than EPSILON invalidates the entry
-    bool same = true;
-    for (std::size_t i = 0; i < it->second->non_group_indices.size() && same; ++i)
-      same = std::fabs(state.getVariablePosition(it->second->non_group_indices[i]) -
-                       it->second->non_group_values[i]) <= STATE_EPSILON;
-    // (the ACM comparison of compareCacheEntryToAllowedCollisionMatrix, :1293-1370, goes here: entries between
-    //  updated links; omitted entries keep the cached masks)
-    if (same)
-      return it->second;
-    b200sv_destroy(it->second->ctx);
-    contexts_.erase(it);
+    int link_i;  // index into glinks
+    std::string name;
+    std::vector<double> xyzr;
+    double bs[4];
+  };
+  std::vector<BodyEntry> body_entries;
+  std::string& sig = out.attached_signature;
+  sig.clear();
+  char num[64];
+  for (int i = 0; i < n; ++i)
+  {
+    std::vector<const moveit::core::AttachedBody*> attached;
+    state.getAttachedBodies(attached, glinks[i]);
+    for (const moveit::core::AttachedBody* att : attached)
+    {
+      // what compareCacheEntryToState looks at for attached bodies (:1293-1312): which bodies, on which links, their
+      // touch links and shapes -- plus the shape poses in the link frame, which the baked-in spheres depend on
+      sig += glinks[i]->getName() + "<" + att->getName() + ":";
+      for (const std::string& tl : att->getTouchLinks())
+        sig += tl + ",";
+      const EigenSTL::vector_Isometry3d& poses = att->getShapePosesInLinkFrame();
+      for (std::size_t k = 0; k < att->getShapes().size(); ++k)
+      {
+        const BodyDecomposition d(att->getShapes()[k], resolution_, 0.0);
+        BodyEntry e;
+        e.link_i = i;
+        e.name = att->getName();
+        for (const CollisionSphere& cs : d.getCollisionSpheres())
+        {
+          const Eigen::Vector3d c = poses[k] * cs.relative_vec_;
+          e.xyzr.insert(e.xyzr.end(), { c.x(), c.y(), c.z(), cs.radius_ });
+        }
+        const Eigen::Vector3d bc = poses[k] * d.getRelativeBoundingSphere().center;
+        e.bs[0] = bc.x(); e.bs[1] = bc.y(); e.bs[2] = bc.z(); e.bs[3] = d.getRelativeBoundingSphere().radius;
+        snprintf(num, sizeof(num), "|%d;%zu;", static_cast<int>(att->getShapes()[k]->type), e.xyzr.size());
+        sig += num;
+        for (int r = 0; r < 3; ++r)
+          for (int col = 0; col < 4; ++col)
+          {
+            snprintf(num, sizeof(num), "%.9g,", poses[k](r, col));
+            sig += num;
+          }
+        body_entries.push_back(std::move(e));
+      }
+      sig += ">";
+    }
   }
+  out.entry_names.clear();
+  out.entry_is_attached.clear();
+  for (int i = 0; i < n; ++i)
+  {
+    out.entry_names.push_back(glinks[i]->getName());
+    out.entry_is_attached.push_back(false);
+  }
+  if (!body_entries.empty())
+  {
+    const int nb = static_cast<int>(body_entries.size()), nt = n + nb;
+    std::vector<uint8_t> intra2(static_cast<std::size_t>(nt) * nt, 0);
+    for (int i = 0; i < n; ++i)
+    {
+      for (int j = 0; j < n; ++j)
+        intra2[static_cast<std::size_t>(i) * nt + j] = intra_enabled[static_cast<std::size_t>(i) * n + j];
+      if (!glinks[i]->getShapes().empty())
+        for (int b = 0; b < nb; ++b)
+          intra2[static_cast<std::size_t>(i) * nt + n + b] = 1;  // all_true
+    }
+    for (int b = 0; b < nb; ++b)
+    {
+      const BodyEntry& e = body_entries[b];
+      const moveit::core::AttachedBody* att = state.getAttachedBody(e.name);
+      const std::string& link_name = glinks[e.link_i]->getName();
+      AllowedCollision::Type t;
+      if ((acm && acm->getEntry(link_name, e.name, t) && t == AllowedCollision::ALWAYS) ||
+          att->getTouchLinks().count(link_name))
+        intra2[static_cast<std::size_t>(e.link_i) * nt + n + b] = 0;
+      out.glink_index.push_back(static_cast<int32_t>(glinks[e.link_i]->getLinkIndex()));
+      self_enabled.push_back(!(acm && acm->getEntry(e.name, e.name, t) && t == AllowedCollision::ALWAYS));
+      for (int b2 = b + 1; b2 < nb; ++b2)
+        intra2[static_cast<std::size_t>(n + b) * nt + n + b2] =
+            !(body_entries[b2].name == e.name ||
+              (acm && acm->getEntry(e.name, body_entries[b2].name, t) && t == AllowedCollision::ALWAYS));
+      out.sphere_xyzr.insert(out.sphere_xyzr.end(), e.xyzr.begin(), e.xyzr.end());
+      out.sphere_start.push_back(static_cast<int32_t>(out.sphere_xyzr.size() / 4));
+      out.bounding_sphere.insert(out.bounding_sphere.end(), e.bs, e.bs + 4);
+      out.entry_names.push_back(e.name);
+      out.entry_is_attached.push_back(true);
+    }
+    intra_enabled.swap(intra2);
+  }
+}
 
-  // ---- b200sv_robot: RobotModel in link-index order + the group's variable layout ----------------------------------
+// ---- the context itself: RobotModel + group layout + collision model -> b200sv_create; self-field link points; world ----
+std::shared_ptr<CollisionEnvB200::GroupContext>
+CollisionEnvB200::createContext(const moveit::core::JointModelGroup* jmg, const moveit::core::RobotState& state,
+                                const FlatModel& fm) const
+{
+  // b200sv_robot: RobotModel in link-index order + the group's variable layout
   const auto& links = robot_model_->getLinkModels();
   const int n_links = static_cast<int>(links.size());
   std::vector<int32_t> parent(n_links), joint_type(n_links), first_var(n_links);
   std::vector<double> axis(3 * n_links, 0.0), origin(16 * n_links);
   for (const moveit::core::LinkModel* l : links)
   {
-    const int i = l->getLinkIndex();
+    const int i = static_cast<int>(l->getLinkIndex());
     const moveit::core::JointModel* j = l->getParentJointModel();
-    parent[i] = l->getParentLinkModel() ? l->getParentLinkModel()->getLinkIndex() : -1;
-    first_var[i] = j->getVariableCount() ? j->getFirstVariableIndex() : 0;
+    parent[i] = l->getParentLinkModel() ? static_cast<int32_t>(l->getParentLinkModel()->getLinkIndex()) : -1;
+    first_var[i] = j->getVariableCount() ? static_cast<int32_t>(j->getFirstVariableIndex()) : 0;
     Eigen::Vector3d a(1, 0, 0);
     switch (j->getType())
     {
@@ -159,8 +289,8 @@ CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::
   std::vector<double> mimic_factor, mimic_offset;
   for (const moveit::core::JointModel* jm : jmg->getMimicJointModels())  // RobotState::updateMimicJoints(group)
   {
-    mimic_dst.push_back(jm->getFirstVariableIndex());
-    mimic_src.push_back(jm->getMimic()->getFirstVariableIndex());
+    mimic_dst.push_back(static_cast<int32_t>(jm->getFirstVariableIndex()));
+    mimic_src.push_back(static_cast<int32_t>(jm->getMimic()->getFirstVariableIndex()));
     mimic_factor.push_back(jm->getMimicFactor());
     mimic_offset.push_back(jm->getMimicOffset());
   }
@@ -181,137 +311,18 @@ CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::
   r.mimic_factor = mimic_factor.data();
   r.mimic_offset = mimic_offset.data();
 
-  // ---- b200sv_collision_model: generateDistanceFieldCacheEntry (:735-838) ---------------------------------------------
-  const std::vector<const moveit::core::LinkModel*>& glinks = jmg->getUpdatedLinkModels();
-  const int n = static_cast<int>(glinks.size());
-  std::vector<int32_t> glink_index(n), sphere_start(1, 0);
-  std::vector<uint8_t> self_enabled(n, 1), intra_enabled(static_cast<std::size_t>(n) * n, 0);
-  std::vector<double> sphere_xyzr, bounding_sphere(4 * n, 0.0);
-  for (int i = 0; i < n; ++i)
-  {
-    const std::string& name = glinks[i]->getName();
-    glink_index[i] = glinks[i]->getLinkIndex();
-    auto bd = link_body_decomposition_index_map_.find(name);
-    if (glinks[i]->getShapes().empty() || bd == link_body_decomposition_index_map_.end())
-    {
-      self_enabled[i] = 0;
-      sphere_start.push_back(sphere_start.back());
-      continue;
-    }
-    AllowedCollision::Type t;
-    if (acm && acm->getEntry(name, name, t) && t == AllowedCollision::ALWAYS)
-      self_enabled[i] = 0;
-    for (int j = 0; j < n; ++j)
-      intra_enabled[static_cast<std::size_t>(i) * n + j] = 1;
-    for (int j = i + 1; j < n; ++j)
-      if (name == glinks[j]->getName() ||
-          (acm && acm->getEntry(name, glinks[j]->getName(), t) && t == AllowedCollision::ALWAYS))
-        intra_enabled[static_cast<std::size_t>(i) * n + j] = 0;
-    const BodyDecompositionConstPtr& d = link_body_decomposition_vector_[bd->second];
-    for (const CollisionSphere& cs : d->getCollisionSpheres())
-    {
-      sphere_xyzr.insert(sphere_xyzr.end(), { cs.relative_vec_.x(), cs.relative_vec_.y(), cs.relative_vec_.z(), cs.radius_ });
-    }
-    sphere_start.push_back(static_cast<int32_t>(sphere_xyzr.size() / 4));
-    const bodies::BoundingSphere& bs = d->getRelativeBoundingSphere();
-    bounding_sphere[4 * i + 0] = bs.center.x();
-    bounding_sphere[4 * i + 1] = bs.center.y();
-    bounding_sphere[4 * i + 2] = bs.center.z();
-    bounding_sphere[4 * i + 3] = bs.radius;
-  }
-  // ---- attached bodies: dfce->attached_body_names_ follow the links (:798-822, 840-866) -------------------------------
-  // One entry per SHAPE of each body attached to a group link; the entry repeats the link's index (that is how
-  // libb200sv recognises it), its spheres and bounding sphere are expressed in the LINK frame
-  // (AttachedBody::getShapePosesInLinkFrame() * BodyDecomposition-relative coordinates).  Masks as the reference sets
-  // them: (link, body) is disabled by an ALWAYS entry or a touch link ONLY for the link the body hangs on; body-body by
-  // an ALWAYS entry; shapes of one body never test each other.
-  struct BodyEntry
-  {
-    int link_i;  // index into glinks
-    std::string name;
-    std::vector<double> xyzr;
-    double bs[4];
-  };
-  std::vector<BodyEntry> body_entries;
-  for (int i = 0; i < n; ++i)
-  {
-    std::vector<const moveit::core::AttachedBody*> attached;
-    state.getAttachedBodies(attached, glinks[i]);
-    for (const moveit::core::AttachedBody* att : attached)
-    {
-      const EigenSTL::vector_Isometry3d& poses = att->getShapePosesInLinkFrame();
-      for (std::size_t k = 0; k < att->getShapes().size(); ++k)
-      {
-        const BodyDecomposition d(att->getShapes()[k], resolution_, 0.0);
-        BodyEntry e;
-        e.link_i = i;
-        e.name = att->getName();
-        for (const CollisionSphere& cs : d.getCollisionSpheres())
-        {
-          const Eigen::Vector3d c = poses[k] * cs.relative_vec_;
-          e.xyzr.insert(e.xyzr.end(), { c.x(), c.y(), c.z(), cs.radius_ });
-        }
-        const Eigen::Vector3d bc = poses[k] * d.getRelativeBoundingSphere().center;
-        e.bs[0] = bc.x(); e.bs[1] = bc.y(); e.bs[2] = bc.z(); e.bs[3] = d.getRelativeBoundingSphere().radius;
-        body_entries.push_back(std::move(e));
-      }
-    }
-  }
-  if (!body_entries.empty())
-  {
-    const int nb = static_cast<int>(body_entries.size()), nt = n + nb;
-    std::vector<uint8_t> intra2(static_cast<std::size_t>(nt) * nt, 0);
-    for (int i = 0; i < n; ++i)
-    {
-      for (int j = 0; j < n; ++j)
-        intra2[static_cast<std::size_t>(i) * nt + j] = intra_enabled[static_cast<std::size_t>(i) * n + j];
-      if (!glinks[i]->getShapes().empty())
-        for (int b = 0; b < nb; ++b)
-          intra2[static_cast<std::size_t>(i) * nt + n + b] = 1;  // all_true
-    }
-    for (int b = 0; b < nb; ++b)
-    {
-      const BodyEntry& e = body_entries[b];
-      const moveit::core::AttachedBody* att = state.getAttachedBody(e.name);
-      const std::string& link_name = glinks[e.link_i]->getName();
-      AllowedCollision::Type t;
-      if ((acm && acm->getEntry(link_name, e.name, t) && t == AllowedCollision::ALWAYS) ||
-          att->getTouchLinks().count(link_name))
-        intra2[static_cast<std::size_t>(e.link_i) * nt + n + b] = 0;
-      glink_index.push_back(glinks[e.link_i]->getLinkIndex());
-      self_enabled.push_back(!(acm && acm->getEntry(e.name, e.name, t) && t == AllowedCollision::ALWAYS));
-      for (int b2 = b + 1; b2 < nb; ++b2)
-        intra2[static_cast<std::size_t>(n + b) * nt + n + b2] =
-            !(body_entries[b2].name == e.name ||
-              (acm && acm->getEntry(e.name, body_entries[b2].name, t) && t == AllowedCollision::ALWAYS));
-      sphere_xyzr.insert(sphere_xyzr.end(), e.xyzr.begin(), e.xyzr.end());
-      sphere_start.push_back(static_cast<int32_t>(sphere_xyzr.size() / 4));
-      bounding_sphere.insert(bounding_sphere.end(), e.bs, e.bs + 4);
-    }
-    intra_enabled.swap(intra2);
-  }
   b200sv_collision_model m{};
-  m.n_glinks = static_cast<int32_t>(glink_index.size());
-  m.glink_index = glink_index.data();
-  m.self_enabled = self_enabled.data();
-  m.intra_enabled = intra_enabled.data();
-  m.sphere_start = sphere_start.data();
-  m.sphere_xyzr = sphere_xyzr.data();
-  m.bounding_sphere = bounding_sphere.data();
+  m.n_glinks = static_cast<int32_t>(fm.glink_index.size());
+  m.glink_index = fm.glink_index.data();
+  m.self_enabled = fm.self_enabled.data();
+  m.intra_enabled = fm.intra_enabled.data();
+  m.sphere_start = fm.sphere_start.data();
+  m.sphere_xyzr = fm.sphere_xyzr.data();
+  m.bounding_sphere = fm.bounding_sphere.data();
 
   const b200sv_field_cfg f = fieldCfg(size_, origin_, resolution_, max_propogation_distance_, collision_tolerance_,
                                       use_signed_distance_field_);
   auto gc = std::make_shared<GroupContext>();
-  for (int i = 0; i < n; ++i)
-  {
-    gc->entry_names.push_back(glinks[i]->getName());
-    gc->entry_is_attached.push_back(false);
-  }
-  for (const BodyEntry& e : body_entries)
-  {
-    gc->entry_names.push_back(e.name);
-    gc->entry_is_attached.push_back(true);
-  }
   int device = 0;  // one process per GPU: honour CUDA_VISIBLE_DEVICES / the launcher's LOCAL_RANK
   if (const char* lr = std::getenv("LOCAL_RANK"))
     device = std::atoi(lr);
@@ -331,8 +342,9 @@ CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::
       gc->non_group_indices.push_back(static_cast<int>(v));
       gc->non_group_values.push_back(state.getVariablePosition(static_cast<int>(v)));
     }
-  // self field: interior points of the links the group does not update, posed at `state` (:907-953)
-  EigenSTL::vector_Vector3d self_points;
+  // self field (:907-953): the interior points of the links the group does not update go to the library ONCE, in the link
+  // frame; b200sv_set_base_state poses them at the cached state and rebuilds the self field -- now and whenever a joint
+  // outside the group moves
   for (const moveit::core::LinkModel* lm : robot_model_->getLinkModelsWithCollisionGeometry())
   {
     if (jmg->isLinkUpdated(lm->getName()))
@@ -340,14 +352,109 @@ CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::
     auto bd = link_body_decomposition_index_map_.find(lm->getName());
     if (bd == link_body_decomposition_index_map_.end())
       continue;
-    const Eigen::Isometry3d& T = state.getFrameTransform(lm->getName());
-    for (const Eigen::Vector3d& p : link_body_decomposition_vector_[bd->second]->getCollisionPoints())
-      self_points.push_back(T * p);
+    const EigenSTL::vector_Vector3d& pts = link_body_decomposition_vector_[bd->second]->getCollisionPoints();
+    std::vector<double> flat;
+    flat.reserve(3 * pts.size());
+    for (const Eigen::Vector3d& p : pts)
+      flat.insert(flat.end(), { p.x(), p.y(), p.z() });
+    if (b200sv_set_self_link_points(gc->ctx, static_cast<int32_t>(lm->getLinkIndex()), flat.data(), pts.size()) != B200SV_OK)
+    {
+      RCLCPP_ERROR(getLogger(), "b200sv_set_self_link_points failed: %s", b200sv_last_error(gc->ctx));
+      return nullptr;
+    }
   }
-  if (!self_points.empty())
-    b200sv_field_add_points(gc->ctx, B200SV_FIELD_SELF, self_points[0].data(), self_points.size());
-  replayWorld(gc->ctx);
-  contexts_[group_name] = gc;
+  if (b200sv_set_base_state(gc->ctx, state.getVariablePositions(), 1) != B200SV_OK)
+  {
+    RCLCPP_ERROR(getLogger(), "b200sv_set_base_state failed: %s", b200sv_last_error(gc->ctx));
+    return nullptr;
+  }
+  gc->self_enabled = fm.self_enabled;
+  gc->intra_enabled = fm.intra_enabled;
+  gc->attached_signature = fm.attached_signature;
+  gc->entry_names = fm.entry_names;
+  gc->entry_is_attached = fm.entry_is_attached;
+  return gc;
+}
+
+// ---- getDistanceFieldCacheEntry (:177-233): reuse the cached entry when it matches (state outside the group, ACM, attached
+// bodies), otherwise bring it up to date.  The reference regenerates the whole entry; here only what changed is re-derived:
+//   attached bodies differ  -> a new context (the sphere tables change shape)
+//   a non-group joint moved -> b200sv_set_base_state: constant transforms + self field
+//   the ACM's masks differ  -> b200sv_set_acm_masks
+std::shared_ptr<CollisionEnvB200::GroupContext>
+CollisionEnvB200::getContext(const std::string& group_name, const moveit::core::RobotState& state,
+                             const AllowedCollisionMatrix* acm, std::unique_lock<std::mutex>& lock) const
+{
+  const moveit::core::JointModelGroup* jmg = robot_model_->getJointModelGroup(group_name);
+  if (!jmg)
+  {
+    RCLCPP_WARN(getLogger(), "No group %s", group_name.c_str());  // :716-720
+    return nullptr;
+  }
+  FlatModel fm;
+  flattenModel(jmg, state, acm, fm);
+  std::shared_ptr<GroupContext> gc;
+  std::size_t world_version = 0;
+  {
+    std::scoped_lock map_lock(mutex_);
+    auto it = contexts_.find(group_name);
+    if (it != contexts_.end())
+      gc = it->second;
+    world_version = world_version_;
+  }
+  if (gc)
+  {
+    lock = std::unique_lock<std::mutex>(gc->mutex);
+    if (gc->attached_signature != fm.attached_signature)
+    {  // compareCacheEntryToState, attached-body part (:1293-1312): different bodies -> a new entry
+      lock.unlock();
+      gc.reset();
+    }
+  }
+  if (!gc)
+  {
+    gc = createContext(jmg, state, fm);
+    if (!gc)
+      return nullptr;
+    lock = std::unique_lock<std::mutex>(gc->mutex);
+    gc->world_version = static_cast<std::size_t>(-1);
+    std::scoped_lock map_lock(mutex_);
+    contexts_[group_name] = gc;  // the entry it replaces lives on until its last user is done
+  }
+  else
+  {
+    // compareCacheEntryToState (:1254-1291): any variable outside the group moved by more than EPSILON
+    bool same = true;
+    for (std::size_t i = 0; i < gc->non_group_indices.size() && same; ++i)
+      same = std::fabs(state.getVariablePosition(gc->non_group_indices[i]) - gc->non_group_values[i]) <= STATE_EPSILON;
+    if (!same)
+    {
+      if (b200sv_set_base_state(gc->ctx, state.getVariablePositions(), 1) != B200SV_OK)
+      {
+        RCLCPP_ERROR(getLogger(), "b200sv_set_base_state failed: %s", b200sv_last_error(gc->ctx));
+        return nullptr;
+      }
+      for (std::size_t i = 0; i < gc->non_group_indices.size(); ++i)
+        gc->non_group_values[i] = state.getVariablePosition(gc->non_group_indices[i]);
+    }
+    // compareCacheEntryToAllowedCollisionMatrix (:1314-1370): the entry's enable masks against the ones this ACM gives
+    if (gc->self_enabled != fm.self_enabled || gc->intra_enabled != fm.intra_enabled)
+    {
+      if (b200sv_set_acm_masks(gc->ctx, fm.self_enabled.data(), fm.intra_enabled.data()) != B200SV_OK)
+      {
+        RCLCPP_ERROR(getLogger(), "b200sv_set_acm_masks failed: %s", b200sv_last_error(gc->ctx));
+        return nullptr;
+      }
+      gc->self_enabled = fm.self_enabled;
+      gc->intra_enabled = fm.intra_enabled;
+    }
+  }
+  if (gc->world_version != world_version)
+  {  // a context created after the world was filled, or one that missed updates: replay what the world holds
+    if (!replayWorld(gc->ctx))
+      return nullptr;
+    gc->world_version = world_version;
+  }
   return gc;
 }
 
@@ -385,28 +492,36 @@ bool devicePrimitive(const shapes::Shape* shape, const Eigen::Isometry3d& pose, 
 }
 }  // namespace
 
-void CollisionEnvB200::replayWorld(b200sv_ctx* ctx) const
+bool CollisionEnvB200::replayWorld(b200sv_ctx* ctx) const
 {
   EigenSTL::vector_Vector3d all;
-  for (const auto& kv : world_points_)
-    all.insert(all.end(), kv.second.points.begin(), kv.second.points.end());
-  b200sv_field_reset(ctx, B200SV_FIELD_WORLD);
-  if (!all.empty())
-    b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, all[0].data(), all.size());
-  for (const auto& kv : world_points_)
-    for (const b200sv_shape& sh : kv.second.shapes)
-      b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &sh, 0);
+  std::vector<b200sv_shape> shapes;
+  {
+    std::scoped_lock map_lock(mutex_);
+    for (const auto& kv : world_points_)
+    {
+      all.insert(all.end(), kv.second.points.begin(), kv.second.points.end());
+      shapes.insert(shapes.end(), kv.second.shapes.begin(), kv.second.shapes.end());
+    }
+  }
+  // everything the world holds, ONE transform at the end
+  bool ok = b200sv_field_reset(ctx, B200SV_FIELD_WORLD) == B200SV_OK &&
+            b200sv_field_begin_update(ctx, B200SV_FIELD_WORLD) == B200SV_OK;
+  if (ok && !all.empty())
+    ok = b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, all[0].data(), all.size()) == B200SV_OK;
+  for (std::size_t i = 0; ok && i < shapes.size(); ++i)
+    ok = b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &shapes[i], 0) == B200SV_OK;
+  ok = b200sv_field_end_update(ctx, B200SV_FIELD_WORLD) == B200SV_OK && ok;
+  if (!ok)
+    RCLCPP_ERROR(getLogger(), "replaying the world into the field failed: %s", b200sv_last_error(ctx));
+  return ok;
 }
 
 void CollisionEnvB200::notifyObjectChange(const ObjectConstPtr& obj, World::Action action)
 {
   // updateDistanceObject (:1730-1779): subtract what the object contributed, add its new decomposition
-  std::scoped_lock lock(mutex_);
-  WorldObjectRecord old_rec;
-  auto cur = world_points_.find(obj->id_);
-  if (cur != world_points_.end())
-    std::swap(old_rec, cur->second);
-  WorldObjectRecord new_rec;
+  WorldObjectRecord old_rec, new_rec;
+  std::vector<std::shared_ptr<GroupContext>> live;
   if (action != World::DESTROY && getWorld()->hasObject(obj->id_))
   {
     World::ObjectConstPtr object = getWorld()->getObject(obj->id_);
@@ -419,31 +534,53 @@ void CollisionEnvB200::notifyObjectChange(const ObjectConstPtr& obj, World::Acti
         PosedBodyPointDecomposition pts(static_cast<const shapes::OcTree*>(shape.get())->octree);  // types.cpp:355-365
         new_rec.points.insert(new_rec.points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
       }
-      else if (devicePrimitive(shape.get(), getWorld()->getGlobalShapeTransform(obj->id_, i), prim))
+      else if (devicePrimitive(shape.get(), getWorld()->getGlobalShapeTransform(obj->id_, static_cast<int>(i)), prim))
         new_rec.shapes.push_back(prim);
       else
       {
         BodyDecompositionConstPtr bd = std::make_shared<const BodyDecomposition>(shape, resolution_, 0.0);
-        PosedBodyPointDecomposition pts(bd, getWorld()->getGlobalShapeTransform(obj->id_, i));
+        PosedBodyPointDecomposition pts(bd, getWorld()->getGlobalShapeTransform(obj->id_, static_cast<int>(i)));
         new_rec.points.insert(new_rec.points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
       }
     }
-    world_points_[obj->id_] = new_rec;
   }
-  else
-    world_points_.erase(obj->id_);
-  for (auto& kv : contexts_)
+  std::size_t version_before = 0, version_after = 0;
   {
-    b200sv_ctx* ctx = kv.second->ctx;
-    // removePointsFromField, then addPointsToField (:1713-1725)
-    if (!old_rec.points.empty())
-      b200sv_field_remove_points(ctx, B200SV_FIELD_WORLD, old_rec.points[0].data(), old_rec.points.size());
-    for (const b200sv_shape& sh : old_rec.shapes)
-      b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &sh, 1);
-    if (!new_rec.points.empty())
-      b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, new_rec.points[0].data(), new_rec.points.size());
-    for (const b200sv_shape& sh : new_rec.shapes)
-      b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &sh, 0);
+    std::scoped_lock lock(mutex_);
+    auto cur = world_points_.find(obj->id_);
+    if (cur != world_points_.end())
+      std::swap(old_rec, cur->second);
+    if (action != World::DESTROY && getWorld()->hasObject(obj->id_))
+      world_points_[obj->id_] = new_rec;
+    else
+      world_points_.erase(obj->id_);
+    version_before = world_version_;
+    version_after = ++world_version_;
+    for (auto& kv : contexts_)
+      live.push_back(kv.second);
+  }
+  for (const std::shared_ptr<GroupContext>& gc : live)
+  {
+    std::scoped_lock ctx_lock(gc->mutex);
+    if (gc->world_version != version_before)
+      continue;  // it missed an earlier change: the next check replays the whole world into it
+    b200sv_ctx* ctx = gc->ctx;
+    // removePointsFromField, then addPointsToField (:1713-1725) -- as ONE rebuild of the field
+    bool ok = b200sv_field_begin_update(ctx, B200SV_FIELD_WORLD) == B200SV_OK;
+    if (ok && !old_rec.points.empty())
+      ok = b200sv_field_remove_points(ctx, B200SV_FIELD_WORLD, old_rec.points[0].data(), old_rec.points.size()) == B200SV_OK;
+    for (std::size_t i = 0; ok && i < old_rec.shapes.size(); ++i)
+      ok = b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &old_rec.shapes[i], 1) == B200SV_OK;
+    if (ok && !new_rec.points.empty())
+      ok = b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, new_rec.points[0].data(), new_rec.points.size()) == B200SV_OK;
+    for (std::size_t i = 0; ok && i < new_rec.shapes.size(); ++i)
+      ok = b200sv_field_add_shape(ctx, B200SV_FIELD_WORLD, &new_rec.shapes[i], 0) == B200SV_OK;
+    ok = b200sv_field_end_update(ctx, B200SV_FIELD_WORLD) == B200SV_OK && ok;
+    if (ok)
+      gc->world_version = version_after;
+    else
+      RCLCPP_ERROR(getLogger(), "world update of the field failed (the next check replays the world): %s",
+                   b200sv_last_error(ctx));
   }
 }
 
@@ -455,8 +592,7 @@ void CollisionEnvB200::setWorld(const WorldPtr& world)
   {
     std::scoped_lock lock(mutex_);
     world_points_.clear();
-    for (auto& kv : contexts_)
-      b200sv_field_reset(kv.second->ctx, B200SV_FIELD_WORLD);
+    ++world_version_;  // every context replays the (new) world at its next check
   }
   CollisionEnv::setWorld(world);
   observer_handle_ = getWorld()->addObserver(
@@ -468,12 +604,17 @@ bool CollisionEnvB200::checkCollisionBatch(const CollisionRequest& req, const mo
                                            const AllowedCollisionMatrix* acm, const double* q, std::size_t n_states,
                                            uint8_t* valid_bitmap, uint32_t flags) const
 {
-  std::shared_ptr<GroupContext> gc = getContext(req.group_name, base_state, acm);
+  // An engine failure must never validate a state: the bitmap is cleared first (every state "in collision") and only a
+  // successful check overwrites it.
+  std::fill(valid_bitmap, valid_bitmap + (n_states + 7) / 8, static_cast<uint8_t>(0));
+  std::unique_lock<std::mutex> ctx_lock;
+  std::shared_ptr<GroupContext> gc = getContext(req.group_name, base_state, acm, ctx_lock);
   if (!gc)
     return false;
   if (b200sv_check_batch(gc->ctx, q, n_states, flags, valid_bitmap) != B200SV_OK)
   {
     RCLCPP_ERROR(getLogger(), "b200sv_check_batch failed: %s", b200sv_last_error(gc->ctx));
+    std::fill(valid_bitmap, valid_bitmap + (n_states + 7) / 8, static_cast<uint8_t>(0));
     return false;
   }
   return true;
@@ -490,9 +631,15 @@ void CollisionEnvB200::checkSingle(const CollisionRequest& req, CollisionResult&
   state.copyJointGroupPositions(jmg, q.data());
   if (req.contacts)
   {  // the contacts the reference would report, in its order and under its limits (:298-339, 571-638, 1589-1629)
-    std::shared_ptr<GroupContext> gc = getContext(req.group_name, state, acm);
-    if (!gc || res.contact_count >= req.max_contacts)
+    if (res.contact_count >= req.max_contacts)
       return;
+    std::unique_lock<std::mutex> ctx_lock;
+    std::shared_ptr<GroupContext> gc = getContext(req.group_name, state, acm, ctx_lock);
+    if (!gc)
+    {
+      res.collision = true;  // fail closed: no context (no device, robot too large, CUDA error) is not "collision-free"
+      return;
+    }
     const uint32_t left = static_cast<uint32_t>(req.max_contacts - res.contact_count);
     std::vector<b200sv_contact> cons(left);
     uint8_t coll = 0;
@@ -501,6 +648,7 @@ void CollisionEnvB200::checkSingle(const CollisionRequest& req, CollisionResult&
                               &count, cons.data()) != B200SV_OK)
     {
       RCLCPP_ERROR(getLogger(), "b200sv_check_contacts failed: %s", b200sv_last_error(gc->ctx));
+      res.collision = true;  // fail closed
       return;
     }
     res.collision = res.collision || coll;
@@ -525,8 +673,10 @@ void CollisionEnvB200::checkSingle(const CollisionRequest& req, CollisionResult&
     }
     return;
   }
+  // checkCollisionBatch clears the bit on every failure path, so an engine failure reads as "in collision" (fail closed)
   uint8_t bit = 0;
-  if (checkCollisionBatch(req, state, acm, q.data(), 1, &bit, flags) && !(bit & 1))
+  checkCollisionBatch(req, state, acm, q.data(), 1, &bit, flags);
+  if (!(bit & 1))
     res.collision = true;
 }
 

@@ -1,7 +1,9 @@
 // MoveIt 2 side of the drop-in: a collision_detection::CollisionEnv whose distance-field checks run on a B200
 // through libb200sv.so (include/b200sv.h).  Compiled only where MoveIt 2 headers exist (see CMakeLists.txt in
-// this directory); it cannot be built in the authoring image (no ROS 2 / Eigen / geometric_shapes there), so it is
-// exercised by reading, not by CI.  INTEGRATION.md walks through it.
+// this directory).  The authoring image has no ROS 2 / Eigen / geometric_shapes, so there it is compiled against minimal
+// stand-in declarations (tests/mock_moveit/, tests/test_adapter_compiles.py: g++ -std=c++17 -Wall -Werror -c): every
+// member it calls, every override and every const-qualification is checked by a compiler; it is not linked or run.
+// INTEGRATION.md walks through it.
 //
 // Mirrors collision_detection::CollisionEnvDistanceField
 // (moveit_core/collision_distance_field/include/moveit/collision_distance_field/collision_env_distance_field.hpp:57-310):
@@ -69,24 +71,48 @@ public:
                            uint8_t* valid_bitmap, uint32_t flags = B200SV_CHECK_ALL) const;
 
 private:
+  /// One DistanceFieldCacheEntry's worth of state on the device.  Owns its b200sv context: the context is destroyed when
+  /// the LAST holder of the shared_ptr lets go, so a thread that is still inside a check keeps it alive even if the
+  /// cache has moved on.  `mutex` is held from "configure for this (state, ACM)" to "check done": two threads whose
+  /// states differ outside the group cannot reconfigure the context under each other.
   struct GroupContext
   {
+    ~GroupContext();
     b200sv_ctx* ctx = nullptr;
-    std::vector<double> non_group_values;  // compareCacheEntryToState (collision_env_distance_field.cpp:1254-1291)
-    std::vector<int> non_group_indices;
-    AllowedCollisionMatrix acm;
-    std::vector<std::string> entry_names;  // dfce entries: the links, then one per shape of every attached body
+    std::mutex mutex;
+    // what the context is currently configured for (compareCacheEntryToState / ...ToAllowedCollisionMatrix,
+    // collision_env_distance_field.cpp:1254-1370)
+    std::vector<int> non_group_indices;      // dfce->state_check_indices_
+    std::vector<double> non_group_values;    // dfce->state_values_
+    std::vector<uint8_t> self_enabled, intra_enabled;  // the masks the ACM produced
+    std::string attached_signature;          // names, touch links, shapes and link-frame poses of the attached bodies
+    std::vector<std::string> entry_names;    // dfce entries: the links, then one per shape of every attached body
     std::vector<bool> entry_is_attached;
+    std::size_t world_version = 0;           // which state of world_points_ its world field holds
   };
+  /// What generateDistanceFieldCacheEntry derives from (group, state, ACM): the flat collision model
+  struct FlatModel
+  {
+    std::vector<int32_t> glink_index, sphere_start;
+    std::vector<uint8_t> self_enabled, intra_enabled;
+    std::vector<double> sphere_xyzr, bounding_sphere;
+    std::vector<std::string> entry_names;
+    std::vector<bool> entry_is_attached;
+    std::string attached_signature;
+  };
+  void flattenModel(const moveit::core::JointModelGroup* jmg, const moveit::core::RobotState& state,
+                    const AllowedCollisionMatrix* acm, FlatModel& out) const;
+  std::shared_ptr<GroupContext> createContext(const moveit::core::JointModelGroup* jmg,
+                                              const moveit::core::RobotState& state, const FlatModel& fm) const;
   void initialize();
-  /// Flatten RobotModel + JointModelGroup + ACM + BodyDecompositions into b200sv_robot / b200sv_collision_model
-  /// and create the context (generateDistanceFieldCacheEntry, collision_env_distance_field.cpp:710-958).
+  /// getDistanceFieldCacheEntry (collision_env_distance_field.cpp:177-233): the group's context, configured for
+  /// (state outside the group, ACM, attached bodies).  Returns it LOCKED (`lock` owns GroupContext::mutex) or nullptr.
   std::shared_ptr<GroupContext> getContext(const std::string& group, const moveit::core::RobotState& state,
-                                           const AllowedCollisionMatrix* acm) const;
+                                           const AllowedCollisionMatrix* acm, std::unique_lock<std::mutex>& lock) const;
   void checkSingle(const CollisionRequest& req, CollisionResult& res, const moveit::core::RobotState& state,
                    const AllowedCollisionMatrix* acm, uint32_t flags) const;
   void notifyObjectChange(const ObjectConstPtr& obj, World::Action action);
-  void replayWorld(b200sv_ctx* ctx) const;
+  bool replayWorld(b200sv_ctx* ctx) const;
 
   Eigen::Vector3d size_, origin_;
   double resolution_, collision_tolerance_, max_propogation_distance_;
@@ -102,7 +128,8 @@ private:
     std::vector<b200sv_shape> shapes;
   };
   std::map<std::string, WorldObjectRecord> world_points_;
-  mutable std::mutex mutex_;
+  std::size_t world_version_ = 0;  // bumped by every world change
+  mutable std::mutex mutex_;       // guards contexts_ and world_points_ (never held across a device call of a check)
   mutable std::map<std::string, std::shared_ptr<GroupContext>> contexts_;
   World::ObserverHandle observer_handle_;
 };

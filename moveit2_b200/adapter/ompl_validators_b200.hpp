@@ -12,8 +12,10 @@
 //     si->setMotionValidator(std::make_shared<b200::B200MotionValidator>(si, this, ctx));
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <utility>
 #include <vector>
 
@@ -37,11 +39,15 @@ struct GroupMetric
 {
   std::vector<uint8_t> continuous;
   std::vector<double> factor;
+  bool one_dof_joints_only = true;  // planar / floating joints: b200sv_check_motions refuses them (their metric is not
+                                    // per-variable); the validators then fall back to state-by-state b200sv_check_batch
   explicit GroupMetric(const moveit::core::JointModelGroup* jmg)
   {
     for (const moveit::core::JointModel* jm : jmg->getJointModels())
       for (std::size_t v = 0; v < jm->getVariableCount(); ++v)
       {
+        if (jm->getType() == moveit::core::JointModel::PLANAR || jm->getType() == moveit::core::JointModel::FLOATING)
+          one_dof_joints_only = false;
         continuous.push_back(jm->getType() == moveit::core::JointModel::REVOLUTE &&
                              static_cast<const moveit::core::RevoluteJointModel*>(jm)->isContinuous());
         factor.push_back(jm->getMimic() ? 0.0 : jm->getDistanceFactor());
@@ -57,11 +63,19 @@ public:
   {
     // longest_valid_segment_fraction * getMaximumExtent (model_based_planning_context.cpp:294-317)
     max_segment_ = si->getStateSpace()->getLongestValidSegmentLength();
+    n_vars_ = pc->getJointModelGroup()->getVariableCount();
+    const ompl::base::StateSpacePtr space = si->getStateSpace();
+    distance_ = [space](const ompl::base::State* a, const ompl::base::State* b) { return space->distance(a, b); };
   }
 
   // `s1` is assumed valid, as OMPL's DiscreteMotionValidator assumes
   bool checkMotion(const ompl::base::State* s1, const ompl::base::State* s2) const override
   {
+    if (!metric_.one_dof_joints_only)
+    {
+      std::pair<ompl::base::State*, double> ignored(nullptr, 0.0);
+      return checkMotion(s1, s2, ignored);
+    }
     uint8_t bit = 0;
     const bool ok = b200sv_check_motions(ctx_, values(s1), values(s2), 1, max_segment_, metric_.continuous.data(),
                                          metric_.factor.data(), 0, B200SV_CHECK_ALL, &bit, nullptr, nullptr) == B200SV_OK &&
@@ -75,6 +89,8 @@ public:
   bool checkMotion(const ompl::base::State* s1, const ompl::base::State* s2,
                    std::pair<ompl::base::State*, double>& last_valid) const override
   {
+    if (!metric_.one_dof_joints_only)
+      return checkMotionStateByState(s1, s2, last_valid);
     uint8_t bit = 0;
     int32_t first_invalid = -1;
     uint64_t nd = 0;
@@ -105,9 +121,43 @@ private:
   {
     return s->as<ModelBasedStateSpace::StateType>()->values;  // the layout b200sv expects: no copy
   }
+  // Groups with planar / floating joints: the state space interpolates (slerp etc.), the device checks the nd states of
+  // the edge as ONE batch.  Fails closed: any error reads as "edge invalid".
+  bool checkMotionStateByState(const ompl::base::State* s1, const ompl::base::State* s2,
+                               std::pair<ompl::base::State*, double>& last_valid) const
+  {
+    const double len = distance_ ? distance_(s1, s2) : 0.0;
+    const std::size_t nd = std::max<std::size_t>(1, static_cast<std::size_t>(std::ceil(len / max_segment_)));
+    std::vector<double> q(nd * n_vars_);
+    std::vector<ModelBasedStateSpace::StateType> scratch(1);
+    std::vector<double> tmp(n_vars_);
+    scratch[0].values = tmp.data();
+    for (std::size_t j = 1; j <= nd; ++j)
+    {
+      si_->getStateSpace()->interpolate(s1, s2, static_cast<double>(j) / nd, &scratch[0]);
+      std::copy(tmp.begin(), tmp.end(), q.begin() + (j - 1) * n_vars_);
+    }
+    std::vector<uint8_t> bits((nd + 7) / 8, 0);
+    const bool called = b200sv_check_batch(ctx_, q.data(), nd, B200SV_CHECK_ALL, bits.data()) == B200SV_OK;
+    std::size_t first_bad = nd;
+    for (std::size_t j = 0; j < nd && first_bad == nd; ++j)
+      if (!called || !((bits[j >> 3] >> (j & 7)) & 1))
+        first_bad = j;
+    const bool ok = first_bad == nd;
+    if (!ok)
+    {
+      last_valid.second = static_cast<double>(first_bad) / nd;
+      if (last_valid.first)
+        si_->getStateSpace()->interpolate(s1, s2, last_valid.second, last_valid.first);
+    }
+    (ok ? valid_ : invalid_)++;
+    return ok;
+  }
   b200sv_ctx* ctx_;
   GroupMetric metric_;
   double max_segment_;
+  std::size_t n_vars_ = 0;
+  std::function<double(const ompl::base::State*, const ompl::base::State*)> distance_;  // StateSpace::distance
 };
 
 // StateValidityChecker::isValid over b200sv_check_batch (a batch of one on the latency path), plus the batched form.

@@ -29,7 +29,8 @@ struct Field
   uint16_t* d2 = nullptr;     // min(d^2, max_d2)
   uint16_t* nd2 = nullptr;    // signed fields only: negative_distance_square_ (distance to the nearest free voxel)
   void* compact = nullptr;    // this field's half of the interleaved compact field (base + which elements)
-  bool dirty = false;
+  bool dirty = false;         // occupancy changed inside a begin/end_update bracket: the EDT is owed
+  bool deferred = false;      // inside b200sv_field_begin_update .. b200sv_field_end_update
 };
 
 template <typename T>
@@ -1422,6 +1423,11 @@ int edtPasses(b200sv_ctx* c, Field& F, cudaStream_t s)
 int rebuildField(b200sv_ctx* c, int which)
 {
   Field& F = c->fields[which];
+  if (F.deferred)
+  {  // several occupancy changes, ONE transform (b200sv_field_end_update runs it)
+    F.dirty = true;
+    return B200SV_OK;
+  }
   CU(c, cudaEventRecord(c->ev0, c->stream));
   if (int rc = edtPasses(c, F, c->stream))
     return rc;
@@ -1981,6 +1987,31 @@ int b200sv_field_reset(b200sv_ctx* c, int which)
     CU(c, cudaMemsetAsync(F.nd2, 0, c->n_voxels * 2, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return B200SV_OK;
+}
+
+int b200sv_field_begin_update(b200sv_ctx* c, int which)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->fields[which].deferred = true;
+  return B200SV_OK;
+}
+
+int b200sv_field_end_update(b200sv_ctx* c, int which)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  enterCtx(c);
+  Field& F = c->fields[which];
+  F.deferred = false;
+  if (!F.dirty)
+    return B200SV_OK;
+  F.dirty = false;
+  return rebuildField(c, which);
 }
 
 static int pointsHost(b200sv_ctx* c, int which, const double* xyz, size_t n, bool set)
@@ -2687,6 +2718,18 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
     return B200SV_ERR_NO_DEVICE;
   if (n_states_checked)
     *n_states_checked = 0;
+  // JointModelGroup::distance / interpolate are per-variable and linear only for 1-DOF joints.  A planar joint measures
+  // Euclidean xy distance plus a weighted angle, a floating joint translation plus quaternion arc and interpolates by
+  // slerp (planar_joint_model.cpp:198-225, floating_joint_model.cpp:110-160): the edge kernels do not restate those, and
+  // interpolating quaternion variables linearly would check states OMPL never visits -- refuse instead of approximating.
+  for (int l = 0; l < c->robot.n_links; ++l)
+    if (c->robot.joint_type[l] == PLANAR || c->robot.joint_type[l] == FLOATING)
+      for (int k = 0; k < jointVarCount(c->robot.joint_type[l]); ++k)
+        if (std::find(c->robot.group_var_index.begin(), c->robot.group_var_index.end(), c->robot.first_var[l] + k) !=
+            c->robot.group_var_index.end())
+          return fail(c, B200SV_ERR_UNSUPPORTED,
+                      "b200sv_check_motions: the group has a planar or floating joint; their distance / interpolation "
+                      "(Euclidean + angle, slerp) is not implemented -- validate such edges state by state");
   if (n_edges == 0)
     return B200SV_OK;
   std::lock_guard<std::mutex> lk(c->mu);

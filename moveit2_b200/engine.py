@@ -204,6 +204,13 @@ class StateValidityEngine:
     def field_reset(self, which=FIELD_WORLD):
         self._check(self.L.b200sv_field_reset(self.h, which))
 
+    def field_begin_update(self, which=FIELD_WORLD):
+        """Bracket several occupancy edits; field_end_update runs the EDT once."""
+        self._check(self.L.b200sv_field_begin_update(self.h, which))
+
+    def field_end_update(self, which=FIELD_WORLD):
+        self._check(self.L.b200sv_field_end_update(self.h, which))
+
     def field_add_points(self, points, which=FIELD_WORLD):
         p = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
         self._check(self.L.b200sv_field_add_points(self.h, which, _dp(p), p.shape[0]))

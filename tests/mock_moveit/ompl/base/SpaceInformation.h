@@ -1,0 +1,3 @@
+// forwards to the one mock header (tests/mock_moveit/mock_moveit_all.hpp): test infrastructure
+#pragma once
+#include "mock_moveit_all.hpp"
