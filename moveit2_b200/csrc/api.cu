@@ -1260,7 +1260,7 @@ b200sv_ctx::LaunchCfg chooseCfg(const b200sv_ctx* c, bool fp64, bool from_list, 
   b200sv_ctx::LaunchCfg best;
   const int regs = ((fast ? fastCheckKernelRegs(c->compact_bytes, (int)c->robot.group_var_index.size()) : checkKernelRegs(fp64, from_list, c->compact_bytes)) + 7) & ~7;
   const int reg_warps = 65536 / (regs * 32);
-  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast, c->fast_n_reps, (int)c->robot.group_var_index.size(), c->fast_n_linkpairs) :
+  const long pw = fast ? fastCheckPerWarpBytes(c->state_stride_fast, c->fast_n_reps, (int)c->robot.group_var_index.size(), c->fast_n_linkpairs, c->fast_wide) :
                          checkPerWarpBytes(fp64, fp64 ? c->state_stride_d : c->state_stride_f);
   for (int b = 1; b <= 4; ++b)
   {
@@ -1322,7 +1322,7 @@ int uploadTables(b200sv_ctx* c)
                                             (size_t)c->fast_t_rows * 128 * sizeof(float)));
     if (getenv("B200SV_VERBOSE"))
       fprintf(stderr, "b200sv: fast kernel: %d words of transforms per state, %d bytes per warp, %d warps x %d CTAs per SM, blob %zu bytes\n",
-              c->state_stride_fast, fastCheckPerWarpBytes(c->fast_t_global ? 0 : c->state_stride_fast, c->fast_n_reps, (int)c->robot.group_var_index.size(), c->fast_n_linkpairs),
+              c->state_stride_fast, fastCheckPerWarpBytes(c->fast_t_global ? 0 : c->state_stride_fast, c->fast_n_reps, (int)c->robot.group_var_index.size(), c->fast_n_linkpairs, c->fast_wide),
               c->cfg_fast.warps, c->cfg_fast.blocks_per_sm, c->blob_fast.size());
     if (c->cfg_fast.warps < 1)
       c->fast_ok = false;  // the generic kernel's limits decide below whether the robot fits at all

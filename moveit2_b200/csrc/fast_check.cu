@@ -256,19 +256,51 @@ __device__ __forceinline__ void pairItem(const FModel& m, const TStore<kGlobal>&
 constexpr int kRepStride = 34;
 __device__ __host__ inline int repBytes(int n_clusters) { return (3 * n_clusters * kRepStride * 2 + 15) & ~15; }
 
-// The work queue of the pair phase and the staged states of the FK phase share one region (never live together).
-__device__ __host__ inline int queueBytes(int n_group_vars)
+// The work queue of the pair phase.  The wide instance (no TMA staging) also keeps the tile's states there during the FK
+// phase: the two are never live together.
+__device__ __host__ inline int queueBytes(int n_group_vars, bool wide)
 {
-  const int stage = 32 * n_group_vars * 8;
+  const int stage = wide ? 32 * n_group_vars * 8 : 0;
   return stage > kQueueCap * 4 ? stage : kQueueCap * 4;
 }
+// The staged states of the other instances: two buffers of one tile each (32 * V doubles), filled by 1-D bulk copies
+// (cp.async.bulk, the TMA engine) that complete on the two mbarriers behind them.
+__device__ __host__ inline int stageOneBytes(int n_group_vars) { return (32 * n_group_vars * 8 + 15) & ~15; }
+__device__ __host__ inline int stageBytes(int n_group_vars, bool wide) { return wide ? 0 : 2 * stageOneBytes(n_group_vars) + 16; }
 
 constexpr int kQcCap = 512;   // hierarchical cull: (state, cluster pair) candidates of one batch of link-pair survivors
 
-__device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs)
+__device__ __host__ inline int fastPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs, bool wide)
 {
-  return 32 * state_stride * 4 + repBytes(n_clusters) + queueBytes(n_group_vars) + 16 +
+  return 32 * state_stride * 4 + repBytes(n_clusters) + queueBytes(n_group_vars, wide) + stageBytes(n_group_vars, wide) + 16 +
          (n_linkpairs > 0 ? (kQueueCap + kQcCap) * 4 : 0);
+}
+
+// ---- 1-D bulk copies global -> shared memory through the TMA engine, completion on an mbarrier (sm_90+ PTX) ----------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+  // one thread: announce the bytes, then start the copy; the barrier's phase completes when they have landed
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)),
+               "l"(src), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity)
+{
+  unsigned ok = 0;
+  const uint32_t a = smemAddr(bar);
+  do
+  {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+  } while (!ok);
 }
 
 // Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
@@ -292,8 +324,10 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   const fast::Header& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int t_words = kTG ? 0 : h.state_stride;  // shared-memory words of transforms per state
+  constexpr bool kWide = kV == 0;
   uint8_t* wbase = smem + (kHier ? h.off_pairs : h.total_bytes) +
-                   static_cast<size_t>(warp) * fastPerWarpBytes(t_words, h.n_clusters, h.n_group_vars, kHier ? h.n_linkpairs : 0);
+                   static_cast<size_t>(warp) *
+                       fastPerWarpBytes(t_words, h.n_clusters, h.n_group_vars, kHier ? h.n_linkpairs : 0, kWide);
   float* Ts = reinterpret_cast<float*>(wbase);
   TStore<kTG> ts;
   ts.base = kTG ? a.t_scratch + (static_cast<size_t>(blockIdx.x) * warps + warp) * (static_cast<size_t>(h.t_rows) * 128) : Ts;
@@ -302,8 +336,12 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   __half* rep_y = rep_x + h.n_clusters * kRepStride;
   __half* rep_z = rep_y + h.n_clusters * kRepStride;
   uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_x) + repBytes(h.n_clusters));
-  double* stage = reinterpret_cast<double*>(queue);  // the tile's states [state][var], FK phase only
-  unsigned* words = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(queue) + queueBytes(h.n_group_vars));  // [0] hit, [1] amb
+  // the tile's states [state][var]: the wide instance stages them in the queue region (FK phase only), the others in two
+  // buffers behind it that the TMA engine fills one tile ahead
+  uint8_t* stage_base = reinterpret_cast<uint8_t*>(queue) + queueBytes(h.n_group_vars, kWide);
+  const int stage_one = stageOneBytes(h.n_group_vars);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + 2 * stage_one);  // [2], non-wide only
+  unsigned* words = reinterpret_cast<unsigned*>(stage_base + stageBytes(h.n_group_vars, kWide));  // [0] hit, [1] amb
   uint32_t* q0 = words + 4;        // hierarchical cull only: (state, link pair) survivors of level 0
   uint32_t* qc = q0 + kQueueCap;   //                         (state, cluster pair) candidates
   const bool do_fields = (a.flags & 3u) != 0, do_intra = (a.flags & 4u) != 0;
@@ -317,40 +355,56 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   const unsigned long long n = a.n_states;
   const unsigned long long n_tiles = (n + 31) / 32;
   const int V = h.n_group_vars;
-  // The states of a tile are ONE contiguous run of 32 * V doubles: every lane reads V of them, coalesced, one tile
-  // AHEAD (they stream from HBM exactly once), and parks them in shared memory when their tile starts.
-  double qn[kV > 0 ? kV : 1];
-  auto fetchTile = [&](unsigned long long t) {
+  // The states of a tile are ONE contiguous run of 32 * V doubles.  One 1-D bulk copy (cp.async.bulk: the TMA engine, no
+  // registers, no LSU instructions) brings a whole tile into this warp's second stage buffer while the current tile is
+  // worked on; it completes on an mbarrier the warp polls when it gets there.  They stream from HBM exactly once.
+  // Only whole tiles whose bytes are a multiple of 16 at a 16-byte aligned address go that way; the last, ragged tile
+  // (and every tile of a misaligned batch) is read with plain loads when its turn comes.
+  const unsigned tile_bytes = static_cast<unsigned>(32 * V * 8);
+  const bool tma_ok = !kWide && (reinterpret_cast<uintptr_t>(a.q) & 15u) == 0;
+  auto tileByTma = [&](unsigned long long t) { return tma_ok && (t + 1) * 32 <= n; };
+  auto fetchTile = [&](unsigned long long t, int buf) {
     const double* __restrict__ src = a.q + t * 32 * V;
-    const unsigned long long left = n - t * 32;
-    const int avail = static_cast<int>(left < 32 ? left : 32) * V;
-    if constexpr (kV > 0)
+    if constexpr (!kWide)
     {
-#pragma unroll
-      for (int j = 0; j < kV; ++j)
+      if (tileByTma(t) && lane == 0)
       {
-        const int e = j * 32 + lane;
-        qn[j] = (j < V && e < avail) ? __ldg(src + e) : 0.0;
+        // the buffer was read with ordinary loads a tile ago: order those before the async proxy's writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bulkLoad(stage_base + buf * stage_one, src, tile_bytes, mbar + buf);
       }
     }
     else
     {  // wide instance: one 128-byte line per lane and pass, into L2
+      const unsigned long long left = n - t * 32;
+      const int avail = static_cast<int>(left < 32 ? left : 32) * V;
       for (int e = lane * 16; e < avail; e += 32 * 16)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(src + e));
     }
   };
-  const unsigned long long tile0 = static_cast<unsigned long long>(blockIdx.x) * warps + warp;
-  if (tile0 < n_tiles)
-    fetchTile(tile0);
-  for (unsigned long long tile = tile0; tile < n_tiles; tile += static_cast<unsigned long long>(gridDim.x) * warps)
+  if constexpr (!kWide)
   {
-    if constexpr (kV > 0)
+    if (lane == 0)
     {
-#pragma unroll
-      for (int j = 0; j < kV; ++j)
-        if (j < V)
-          stage[j * 32 + lane] = qn[j];
+      mbarInit(mbar, 1);
+      mbarInit(mbar + 1, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncwarp();
+  }
+  const unsigned long long tile0 = static_cast<unsigned long long>(blockIdx.x) * warps + warp;
+  const unsigned long long tile_step = static_cast<unsigned long long>(gridDim.x) * warps;
+  if (tile0 < n_tiles)
+    fetchTile(tile0, 0);
+  unsigned it = 0;  // tiles this warp has started: buffer = it & 1, barrier parity = (it >> 1) & 1
+  for (unsigned long long tile = tile0; tile < n_tiles; tile += tile_step, ++it)
+  {
+    const int buf = kWide ? 0 : static_cast<int>(it & 1u);
+    double* stage = reinterpret_cast<double*>(kWide ? reinterpret_cast<uint8_t*>(queue) : stage_base + buf * stage_one);
+    if (tile + tile_step < n_tiles)
+      fetchTile(tile + tile_step, buf ^ 1);  // the other buffer's last reader was the previous tile (done: __syncwarp below)
+    if (!kWide && tileByTma(tile))
+      mbarWait(mbar + buf, (it >> 1) & 1u);
     else
     {
       const double* __restrict__ src = a.q + tile * 32 * V;
@@ -358,12 +412,7 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
       const int avail = static_cast<int>(left < 32 ? left : 32) * V;
       for (int e = lane; e < 32 * V; e += 32)
         stage[e] = e < avail ? __ldg(src + e) : 0.0;
-    }
-    __syncwarp();
-    {
-      const unsigned long long nt = tile + static_cast<unsigned long long>(gridDim.x) * warps;
-      if (nt < n_tiles)
-        fetchTile(nt);
+      __syncwarp();
     }
     const unsigned long long first = tile * 32;
     const int cnt = static_cast<int>(n - first < 32 ? n - first : 32);
@@ -839,9 +888,9 @@ cudaError_t ensure(K kernel, size_t smem_bytes, Grant& g)
 }
 }  // namespace
 
-int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs)
+int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs, bool wide)
 {
-  return fastPerWarpBytes(state_stride, n_clusters, n_group_vars, n_linkpairs);
+  return fastPerWarpBytes(state_stride, n_clusters, n_group_vars, n_linkpairs, wide);
 }
 int fastCheckMaxVars() { return kWideMaxVars; }
 int fastCheckRegisterPrefetchVars() { return kMaxVars; }  // beyond this (or with a planar joint) the wide instance runs

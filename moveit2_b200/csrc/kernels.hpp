@@ -131,7 +131,7 @@ cudaError_t launchContacts(const ContactArgs& a, int grid, int block, size_t sme
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
 int fastCheckKernelRegs(int field_bytes, int n_group_vars);
-int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs);
+int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs, bool wide);
 int fastCheckMaxVars();
 int fastCheckRegisterPrefetchVars();
 int fastCheckMaxWarps(int n_group_vars);  // __launch_bounds__ of the fast kernel instance that takes the group
