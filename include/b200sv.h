@@ -217,6 +217,30 @@ typedef struct b200sv_shape
   double pose[12];
 } b200sv_shape;
 int b200sv_field_add_shape(b200sv_ctx* ctx, int which, const b200sv_shape* shape, int remove);
+/* A convex mesh (bodies::ConvexMesh of geometric_shapes) decomposed on the device: the caller -- who owns the mesh and the
+ * convex-hull code -- passes the hull's planes, the library lays out findInternalPointsConvex's lattice around the bounding
+ * sphere and keeps the points on the inner side of every plane (ConvexMesh::containsPoint -> isPointInsidePlanes:
+ * normal . (i_pose * p) + w - 1e-9 <= 0; geometric_shapes is un-vendored in the reference, parity unpinned).
+ *   planes           [n_planes * 4] unit normal x, y, z and w in the body's base frame (w as the library recomputes it from a
+ *                    scaled + padded vertex of the plane)
+ *   bounding_sphere  centre (body frame) and radius: ConvexMesh::computeBoundingSphere
+ *   lattice_frame, pose, remove: as b200sv_field_add_shape */
+typedef struct b200sv_convex
+{
+  int32_t n_planes;
+  int32_t lattice_frame;
+  const double* planes;
+  double bounding_sphere[4];
+  double pose[12];
+} b200sv_convex;
+int b200sv_field_add_convex(b200sv_ctx* ctx, int which, const b200sv_convex* body, int remove);
+/* DistanceField::addOcTreeToField (distance_field.cpp:240-291) behind octomap's leaf iteration, which stays with the caller
+ * (octomap is its dependency): leaves [n_leaves * 4] = centre x, y, z and size of every OCCUPIED leaf inside the field's
+ * bounding box.  A leaf no larger than a cell marks its centre's voxel, a larger one the lattice the reference fills it with
+ * (x = cx - c .. cx + c in accumulated steps of the resolution, c = ceil(size / resolution) * resolution / 2).  Rebuilds.
+ * (World octrees of CollisionEnvDistanceField go through PosedBodyPointDecomposition(octree) instead, types.cpp:355-365:
+ * every tree node's centre as a point -- that is b200sv_field_add_points.) */
+int b200sv_field_add_octree_leaves(b200sv_ctx* ctx, int which, const double* leaves, size_t n_leaves);
 /* Same two with xyz already in device memory, asynchronous on `cuda_stream` (a cudaStream_t). */
 int b200sv_field_add_points_device(b200sv_ctx* ctx, int which, const double* d_xyz, size_t n_points,
                                    void* cuda_stream);

@@ -43,6 +43,11 @@ SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_BOX = 1, 2, 4
 LATTICE_WORLD, LATTICE_BODY = 0, 1
 
 
+class Convex(C.Structure):
+    _fields_ = [("n_planes", C.c_int32), ("lattice_frame", C.c_int32), ("planes", C.POINTER(C.c_double)),
+                ("bounding_sphere", C.c_double * 4), ("pose", C.c_double * 12)]
+
+
 class Info(C.Structure):
     _fields_ = [("n_links", C.c_int32), ("n_vars", C.c_int32), ("n_group_vars", C.c_int32),
                 ("n_glinks", C.c_int32), ("n_spheres", C.c_int32), ("n_link_pairs", C.c_int32),
@@ -88,6 +93,8 @@ def load():
         "b200sv_field_remove_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_field_add_sphere": (C.c_int, [vp, C.c_int, dp, C.c_double]),
         "b200sv_field_add_shape": (C.c_int, [vp, C.c_int, C.POINTER(Shape), C.c_int]),
+        "b200sv_field_add_convex": (C.c_int, [vp, C.c_int, C.POINTER(Convex), C.c_int]),
+        "b200sv_field_add_octree_leaves": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_field_update_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t, dp, C.c_size_t]),
         "b200sv_field_add_points_device": (C.c_int, [vp, C.c_int, vp, C.c_size_t, vp]),
         "b200sv_field_get_d2": (C.c_int, [vp, C.c_int, ip]),

@@ -2191,6 +2191,87 @@ int b200sv_field_add_shape(b200sv_ctx* c, int which, const b200sv_shape* sh, int
   return rebuildField(c, which);
 }
 
+int b200sv_field_add_convex(b200sv_ctx* c, int which, const b200sv_convex* cv, int remove)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!cv || cv->n_planes < 1 || !cv->planes)
+    return fail(c, B200SV_ERR_INVALID, "null convex body or no planes");
+  if (cv->lattice_frame != B200SV_LATTICE_WORLD && cv->lattice_frame != B200SV_LATTICE_BODY)
+    return fail(c, B200SV_ERR_INVALID, "lattice_frame must be B200SV_LATTICE_WORLD or B200SV_LATTICE_BODY");
+  if (!(cv->bounding_sphere[3] >= 0.0))
+    return fail(c, B200SV_ERR_INVALID, "negative bounding radius");
+  const bool body_frame = cv->lattice_frame == B200SV_LATTICE_BODY;
+  ConvexDev b{};
+  b.n_planes = cv->n_planes;
+  b.posed = body_frame ? 1 : 0;
+  double R[9], t[3];
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int k = 0; k < 3; ++k)
+    {
+      R[3 * r + k] = cv->pose[4 * r + k];
+      b.P[3 * r + k] = cv->pose[4 * r + k];
+    }
+    t[r] = cv->pose[4 * r + 3];
+    b.P[9 + r] = cv->pose[4 * r + 3];
+  }
+  // i_pose_ = pose_.inverse() for an isometry: [R^T | -(R^T t)]; the identity when the lattice is laid out around the body
+  double centre[3];
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int k = 0; k < 3; ++k)
+      b.ipose[3 * r + k] = body_frame ? (r == k ? 1.0 : 0.0) : R[3 * k + r];
+    b.ipose[9 + r] = body_frame ? 0.0 : -((R[0 + r] * t[0] + R[3 + r] * t[1]) + R[6 + r] * t[2]);
+    // the lattice is laid out around the body's bounding sphere (computeBoundingSphere: pose_ * mesh centre)
+    centre[r] = body_frame ? cv->bounding_sphere[r] :
+                             ((R[3 * r] * cv->bounding_sphere[0] + R[3 * r + 1] * cv->bounding_sphere[1]) +
+                              R[3 * r + 2] * cv->bounding_sphere[2]) + t[r];
+  }
+  std::lock_guard<std::mutex> lk(c->mu);
+  enterCtx(c);
+  const double res = c->cfg.resolution, radius = cv->bounding_sphere[3];
+  std::vector<double> host;  // axes, then the planes
+  int cnt[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    const double e = centre[k] + radius + res;
+    int n = 0;
+    for (double v = floor((centre[k] - radius - res) / res) * res; v <= e; v += res, ++n)
+      host.push_back(v);
+    cnt[k] = n;
+  }
+  if ((double)cnt[0] * cnt[1] * cnt[2] > 4.0e9)
+    return fail(c, B200SV_ERR_INVALID, "body spans more than 4e9 lattice points");
+  const size_t n_axes = host.size();
+  host.insert(host.end(), cv->planes, cv->planes + 4 * (size_t)cv->n_planes);
+  CU(c, c->d_points.ensure(host.size() + 1));
+  CU(c, cudaMemcpyAsync(c->d_points.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(c, launchConvexLattice(c->d_points.p, cnt[0], cnt[1], cnt[2], c->d_points.p + n_axes, b, c->grid, c->fields[which].occ,
+                            remove == 0, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));  // `host` lives on this stack frame
+  return rebuildField(c, which);
+}
+
+int b200sv_field_add_octree_leaves(b200sv_ctx* c, int which, const double* leaves, size_t n_leaves)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (n_leaves && !leaves)
+    return fail(c, B200SV_ERR_INVALID, "null leaf array");
+  std::lock_guard<std::mutex> lk(c->mu);
+  enterCtx(c);
+  if (n_leaves)
+  {
+    CU(c, c->d_points.ensure(4 * n_leaves));
+    CU(c, cudaMemcpyAsync(c->d_points.p, leaves, 4 * n_leaves * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, launchOctreeLeaves(c->d_points.p, n_leaves, c->cfg.resolution, c->grid, c->fields[which].occ, c->stream));
+  }
+  return rebuildField(c, which);
+}
+
 int b200sv_field_add_points_device(b200sv_ctx* c, int which, const double* d_xyz, size_t n, void* cuda_stream)
 {
   int rc = checkWhich(c, which);

@@ -503,6 +503,89 @@ __global__ void bodyLatticeKernel(const double* __restrict__ axes, int nxs, int 
   }
 }
 
+// bodies::ConvexMesh::containsPoint as geometric_shapes' published bodies.cpp has it (un-vendored in the reference: parity
+// unpinned): the point goes to the body's base frame (i_pose_ * p) and must lie on the inner side of every plane of the hull,
+// plane_normal . p + w - 1e-9 <= 0 (isPointInsidePlanes; w is the caller's, recomputed from a scaled + padded vertex as the
+// library does).  The bounding-box pre-test of the library is implied by the planes of a closed hull.  Explicit round-to-
+// nearest double operations, left to right, no FMA (the order the numpy restatement in oracle/ uses).
+__global__ void convexLatticeKernel(const double* __restrict__ axes, int nxs, int nys, int nzs,
+                                    const double* __restrict__ planes, ConvexDev b, GridDev g, uint32_t* __restrict__ occ, int set)
+{
+  const size_t total = static_cast<size_t>(nxs) * nys * nzs;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    const int iz = static_cast<int>(i % nzs);
+    const size_t t = i / nzs;
+    const int iy = static_cast<int>(t % nys), ix = static_cast<int>(t / nys);
+    double px = axes[ix], py = axes[nxs + iy], pz = axes[nxs + nys + iz];
+    const double bx = __dadd_rn(dot3rn(b.ipose[0], b.ipose[1], b.ipose[2], px, py, pz), b.ipose[9]);
+    const double by = __dadd_rn(dot3rn(b.ipose[3], b.ipose[4], b.ipose[5], px, py, pz), b.ipose[10]);
+    const double bz = __dadd_rn(dot3rn(b.ipose[6], b.ipose[7], b.ipose[8], px, py, pz), b.ipose[11]);
+    bool inside = true;
+    for (int k = 0; k < b.n_planes && inside; ++k)
+    {
+      const double dist = __dsub_rn(__dadd_rn(dot3rn(__ldg(planes + 4 * k), __ldg(planes + 4 * k + 1), __ldg(planes + 4 * k + 2),
+                                                     bx, by, bz),
+                                              __ldg(planes + 4 * k + 3)),
+                                    1e-9);
+      inside = !(dist > 0.0);
+    }
+    if (!inside)
+      continue;
+    if (b.posed)
+    {
+      const double qx = __dadd_rn(dot3rn(b.P[0], b.P[1], b.P[2], px, py, pz), b.P[9]);
+      const double qy = __dadd_rn(dot3rn(b.P[3], b.P[4], b.P[5], px, py, pz), b.P[10]);
+      const double qz = __dadd_rn(dot3rn(b.P[6], b.P[7], b.P[8], px, py, pz), b.P[11]);
+      px = qx;
+      py = qy;
+      pz = qz;
+    }
+    const int x = static_cast<int>(floor((px - g.om[0]) * g.oo)), y = static_cast<int>(floor((py - g.om[1]) * g.oo)),
+              z = static_cast<int>(floor((pz - g.om[2]) * g.oo));
+    if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz)
+      continue;
+    uint32_t* w = occ + (static_cast<size_t>(x) * g.ny + y) * g.wz + (z >> 5);
+    if (set)
+      atomicOr(w, 1u << (z & 31));
+    else
+      atomicAnd(w, ~(1u << (z & 31)));
+  }
+}
+
+// DistanceField::getOcTreePoints (distance_field.cpp:240-284), the part after octomap's leaf iteration (which stays with the
+// caller: octomap is its dependency): an occupied leaf no larger than a cell contributes its centre; a larger one the lattice
+// x = cx - c, x <= cx + c, x += resolution (accumulated, as the reference's loops) with c = ceil(size / resolution) *
+// resolution / 2, on all three axes.  Every point then marks its voxel (addPointsToField).  One thread per leaf.
+__global__ void octreeLeavesKernel(const double* __restrict__ leaves, size_t n, double res, GridDev g,
+                                   uint32_t* __restrict__ occ)
+{
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    const double cx = leaves[4 * i], cy = leaves[4 * i + 1], cz = leaves[4 * i + 2], size = leaves[4 * i + 3];
+    auto mark = [&](double px, double py, double pz) {
+      const int x = static_cast<int>(floor((px - g.om[0]) * g.oo)), y = static_cast<int>(floor((py - g.om[1]) * g.oo)),
+                z = static_cast<int>(floor((pz - g.om[2]) * g.oo));
+      if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz)
+        return;
+      atomicOr(occ + (static_cast<size_t>(x) * g.ny + y) * g.wz + (z >> 5), 1u << (z & 31));
+    };
+    if (size <= res)
+    {
+      mark(cx, cy, cz);
+      continue;
+    }
+    const double c = __ddiv_rn(__dmul_rn(ceil(__ddiv_rn(size, res)), res), 2.0);
+    const double ex = __dadd_rn(cx, c), ey = __dadd_rn(cy, c), ez = __dadd_rn(cz, c);
+    for (double x = __dsub_rn(cx, c); x <= ex; x = __dadd_rn(x, res))
+      for (double y = __dsub_rn(cy, c); y <= ey; y = __dadd_rn(y, res))
+        for (double z = __dsub_rn(cz, c); z <= ez; z = __dadd_rn(z, res))
+          mark(x, y, z);
+  }
+}
+
 // updatePointsInField (propagation_distance_field.cpp:130-175): occ' = (occ - (old \ new)) + (new \ old), word by word
 __global__ void updateOccKernel(uint32_t* __restrict__ occ, const uint32_t* __restrict__ old_bits,
                                 const uint32_t* __restrict__ new_bits, size_t n_words)
@@ -569,6 +652,25 @@ cudaError_t launchBodyLattice(const double* d_axes, int nxs, int nys, int nzs, c
   if (total == 0)
     return cudaSuccess;
   bodyLatticeKernel<<<gridFor(total, 256, 148 * 16), 256, 0, s>>>(d_axes, nxs, nys, nzs, body, g, occ, set ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launchConvexLattice(const double* d_axes, int nxs, int nys, int nzs, const double* d_planes, const ConvexDev& body,
+                                const GridDev& g, uint32_t* occ, bool set, cudaStream_t s)
+{
+  const size_t total = static_cast<size_t>(nxs) * nys * nzs;
+  if (total == 0)
+    return cudaSuccess;
+  convexLatticeKernel<<<gridFor(total, 256, 148 * 16), 256, 0, s>>>(d_axes, nxs, nys, nzs, d_planes, body, g, occ, set ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launchOctreeLeaves(const double* d_leaves, size_t n, double resolution, const GridDev& g, uint32_t* occ,
+                               cudaStream_t s)
+{
+  if (n == 0)
+    return cudaSuccess;
+  octreeLeavesKernel<<<gridFor(n, 128, 148 * 16), 128, 0, s>>>(d_leaves, n, resolution, g, occ);
   return cudaGetLastError();
 }
 

@@ -189,6 +189,19 @@ cudaError_t launchSphereShape(const double* d_axes, int nxs, int nys, int nzs, c
 cudaError_t launchBodyLattice(const double* d_axes, int nxs, int nys, int nzs, const BodyDev& body, const GridDev& g,
                               uint32_t* occ, bool set, cudaStream_t s);
 cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint32_t* new_bits, size_t n_words, cudaStream_t s);
+// bodies::ConvexMesh (geometric_shapes): interior lattice points of a convex polytope given by its planes.
+//   d_axes   lattice axis values (host-accumulated), d_planes [n_planes][4] = unit normal, w (inside: n.p + w - 1e-9 <= 0)
+//   ipose    the body's inverse pose, rows of [R^T | -R^T t] (i_pose_ * p); post/posed as in BodyDev
+struct ConvexDev
+{
+  int n_planes, posed;
+  double ipose[12], P[12];
+};
+cudaError_t launchConvexLattice(const double* d_axes, int nxs, int nys, int nzs, const double* d_planes, const ConvexDev& body,
+                                const GridDev& g, uint32_t* occ, bool set, cudaStream_t s);
+// DistanceField::getOcTreePoints (distance_field.cpp:240-284) for leaves the caller enumerated: d_leaves [n][4] = centre, size
+cudaError_t launchOctreeLeaves(const double* d_leaves, size_t n, double resolution, const GridDev& g, uint32_t* occ,
+                               cudaStream_t s);
 // exact truncated EDT of the occupancy bitmap -> d2 (uint16, min(d^2, max_d2)) and this field's half of the
 // INTERLEAVED compact field (element 2 * voxel; `compact` arrives offset by 0 = world / 1 = self; uint8:
 // min(d^2, 255), uint16: d^2).  tmp: uint16 [nx*ny*nz] scratch.  invert: the transform of the complement (the

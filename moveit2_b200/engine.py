@@ -238,6 +238,25 @@ class StateValidityEngine:
                 sh.pose[4 * r + k] = float(m[r, k])
         self._check(self.L.b200sv_field_add_shape(self.h, which, C.byref(sh), int(bool(remove))))
 
+    def field_add_convex(self, planes, bounding_sphere, pose, which=FIELD_WORLD, lattice_frame=_lib.LATTICE_WORLD,
+                         remove=False):
+        """A convex mesh given by its hull planes [n, 4] (unit normal, w), decomposed on the device."""
+        pl = np.ascontiguousarray(planes, np.float64).reshape(-1, 4)
+        cv = _lib.Convex()
+        cv.n_planes, cv.lattice_frame, cv.planes = pl.shape[0], int(lattice_frame), _dp(pl)
+        for k in range(4):
+            cv.bounding_sphere[k] = float(bounding_sphere[k])
+        m = np.asarray(pose, np.float64)
+        for r in range(3):
+            for k in range(4):
+                cv.pose[4 * r + k] = float(m[r, k])
+        self._check(self.L.b200sv_field_add_convex(self.h, which, C.byref(cv), int(bool(remove))))
+
+    def field_add_octree_leaves(self, leaves, which=FIELD_WORLD):
+        """Occupied octree leaves [n, 4] = centre xyz, size (DistanceField::addOcTreeToField behind octomap's iteration)."""
+        a = np.ascontiguousarray(leaves, np.float64).reshape(-1, 4)
+        self._check(self.L.b200sv_field_add_octree_leaves(self.h, which, _dp(a) if len(a) else None, a.shape[0]))
+
     def field_update_points(self, old_points, new_points, which=FIELD_WORLD):
         """PropagationDistanceField::updatePointsInField."""
         a = np.ascontiguousarray(old_points, np.float64).reshape(-1, 3)

@@ -123,6 +123,71 @@ def find_internal_points_body(shape_type, dims, pose, resolution, lattice_frame=
     return P
 
 
+def find_internal_points_convex_planes(planes, bounding_sphere, pose, resolution, lattice_frame="world"):
+    """findInternalPointsConvex (find_internal_points.cpp:39-64) for a bodies::ConvexMesh given by the planes of its hull,
+    restated from geometric_shapes' published bodies.cpp (un-vendored in the reference: parity unpinned):
+    containsPoint(p) = isPointInsidePlanes(i_pose_ * p): for every plane, normal . ip + w - 1e-9 <= 0 (the bounding-box
+    pre-test is implied by a closed hull).  planes [n, 4] = unit normal, w; bounding_sphere = centre (body frame), radius
+    (computeBoundingSphere).  lattice_frame as in find_internal_points_body."""
+    pose = np.asarray(pose, np.float64)
+    R, t = pose[:3, :3], pose[:3, 3]
+    res = float(resolution)
+    planes = np.asarray(planes, np.float64).reshape(-1, 4)
+    bc, radius = np.asarray(bounding_sphere[:3], np.float64), float(bounding_sphere[3])
+    body = lattice_frame == "body"
+    if body:
+        c = bc
+        iR, it = np.eye(3), np.zeros(3)
+    else:
+        c = np.array([(R[r, 0] * bc[0] + R[r, 1] * bc[1]) + R[r, 2] * bc[2] + t[r] for r in range(3)])
+        iR = R.T.copy()
+        it = np.array([-((R[0, r] * t[0] + R[1, r] * t[1]) + R[2, r] * t[2]) for r in range(3)])
+
+    def axis(ck):
+        v = math.floor((ck - radius - res) / res) * res
+        e = ck + radius + res
+        out = []
+        while v <= e:
+            out.append(v)
+            v += res
+        return np.array(out)
+
+    X, Y, Z = np.meshgrid(axis(c[0]), axis(c[1]), axis(c[2]), indexing="ij")
+    B = [((iR[r, 0] * X + iR[r, 1] * Y) + iR[r, 2] * Z) + it[r] for r in range(3)]
+    inside = np.ones(X.shape, bool)
+    for n in planes:
+        dist = (((n[0] * B[0] + n[1] * B[1]) + n[2] * B[2]) + n[3]) - 1e-9
+        inside &= ~(dist > 0.0)
+    P = np.stack([X[inside], Y[inside], Z[inside]], axis=1)
+    if body:
+        P = np.stack([(R[r, 0] * P[:, 0] + R[r, 1] * P[:, 1] + R[r, 2] * P[:, 2]) + t[r] for r in range(3)], axis=1)
+    return P
+
+
+def octree_leaf_points(leaves, resolution):
+    """DistanceField::getOcTreePoints (distance_field/src/distance_field.cpp:240-284) behind octomap's leaf iteration:
+    leaves [n, 4] = centre, size of every occupied leaf inside the field's bounding box.  A leaf no larger than a cell gives
+    its centre; a larger one the lattice of the reference's three `x += resolution_` loops (accumulated)."""
+    res = float(resolution)
+    out = []
+    for cx, cy, cz, size in np.asarray(leaves, np.float64).reshape(-1, 4):
+        if size <= res:
+            out.append((cx, cy, cz))
+            continue
+        ceil_val = math.ceil(size / res) * res / 2.0
+
+        def axis(c):
+            v, vals = c - ceil_val, []
+            while v <= c + ceil_val:
+                vals.append(v)
+                v += res
+            return vals
+
+        xs, ys, zs = axis(cx), axis(cy), axis(cz)
+        out.extend((x, y, z) for x in xs for y in ys for z in zs)
+    return np.array(out, np.float64).reshape(-1, 3)
+
+
 def merge_bounding_spheres(spheres):
     """geometric_shapes bodies::mergeBoundingSpheres, restated from the published source (parity unpinned)."""
     if not spheres:

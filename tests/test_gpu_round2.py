@@ -342,3 +342,66 @@ def test_field_update_bracket_runs_one_transform():
     assert np.array_equal(eng_a.field_get_d2(), eng_b.field_get_d2())
     eng_a.close()
     eng_b.close()
+
+
+def _pose(rpy, xyz):
+    cr, sr, cp, sp, cy, sy = np.cos(rpy[0]), np.sin(rpy[0]), np.cos(rpy[1]), np.sin(rpy[1]), np.cos(rpy[2]), np.sin(rpy[2])
+    T = np.eye(4)
+    T[:3, :3] = np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                          [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr], [-sp, cp * sr, cp * cr]])
+    T[:3, 3] = xyz
+    return T
+
+
+def _hull_planes_of_a_skewed_wedge():
+    """A closed convex polytope with faces in general position: 7 unit-normal planes around (0.02, -0.01, 0.03)."""
+    rng = np.random.default_rng(12)
+    n = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [0.6, 0.5, 0.62]], np.float64)
+    n += 0.15 * rng.standard_normal(n.shape)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    centre = np.array([0.02, -0.01, 0.03])
+    offs = np.array([0.11, 0.09, 0.07, 0.10, 0.06, 0.08, 0.05])
+    w = -(n @ centre) - offs                       # n . p + w <= 0  <=>  n . (p - centre) <= offs
+    return np.concatenate([n, w[:, None]], axis=1), np.array([centre[0], centre[1], centre[2], 0.2])
+
+
+@pytest.mark.parametrize("frame", ["world", "body"])
+def test_field_add_convex_equals_the_restated_containment(frame):
+    """b200sv_field_add_convex (bodies::ConvexMesh::containsPoint over findInternalPointsConvex's lattice, on the device)
+    against the numpy restatement, voxel for voxel; then removed again."""
+    from oracle.collision_model import find_internal_points_convex_planes
+    planes, bs = _hull_planes_of_a_skewed_wedge()
+    pose = _pose((0.3, -0.7, 1.1), (0.12, -0.08, 0.55))
+    eng, env = make_pair("panda", "panda_arm", (1, 1, 1), (0, 0, 0.5), 0.01, 0.25)
+    lf = mb.LATTICE_WORLD if frame == "world" else mb.LATTICE_BODY
+    eng.field_add_convex(planes, bs, pose, lattice_frame=lf)
+    pts = find_internal_points_convex_planes(planes, bs, pose, 0.01, frame)
+    assert len(pts) > 500
+    env.world.add_points(pts)
+    g, o = eng.field_get_d2(), env.world.d2()
+    assert int((o == 0).sum()) > 300 and np.array_equal(g == 0, o == 0)
+    eng.field_add_convex(planes, bs, pose, lattice_frame=lf, remove=True)
+    assert int((eng.field_get_d2() == 0).sum()) == 0
+    eng.close()
+
+
+def test_field_add_octree_leaves_equals_the_restated_expansion():
+    """DistanceField::addOcTreeToField behind octomap's leaf iteration: leaves of 1, 2, 4 and 8 cells, some sticking out of
+    the field; the lattice of a large leaf is the reference's accumulated `x += resolution_` loops."""
+    from oracle.collision_model import octree_leaf_points
+    rng = np.random.default_rng(13)
+    res = 0.02
+    leaves = []
+    for size_cells, count in ((1, 400), (2, 60), (4, 20), (8, 6)):
+        size = res * size_cells
+        # octomap leaf centres sit on the (float) grid of their depth
+        c = (np.floor(rng.uniform([-0.55, -0.55, -0.05], [0.55, 0.55, 1.05], size=(count, 3)) / size) + 0.5) * size
+        c = c.astype(np.float32).astype(np.float64)          # octomap::point3d holds floats
+        leaves.append(np.concatenate([c, np.full((count, 1), size)], axis=1))
+    leaves = np.concatenate(leaves)
+    eng, env = make_pair("panda", "panda_arm", (1, 1, 1), (0, 0, 0.5), res, 0.25)
+    eng.field_add_octree_leaves(leaves)
+    env.world.add_points(octree_leaf_points(leaves, res))
+    g, o = eng.field_get_d2(), env.world.d2()
+    assert int((o == 0).sum()) > 2000 and np.array_equal(g == 0, o == 0)
+    eng.close()
