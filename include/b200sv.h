@@ -388,6 +388,16 @@ int b200sv_multi_field_add_points(b200sv_multi* m, int which, const double* xyz,
 int b200sv_check_batch_multi(b200sv_multi* m, const double* q, size_t n_states, uint32_t flags, uint8_t* valid_bitmap);
 int b200sv_multi_get_stats(b200sv_multi* m, b200sv_stats* stats);
 
+/* ---- the FP32 error budget -------------------------------------------------------------------------------------------- */
+/* The fast pass decides in FP32; every decision carries a budget eps (metres) and whatever could flip within it is decided
+ * by the exact FP64 pass.  eps_derived is the worst-case FP32 error of a posed sphere centre, derived from the model (chain
+ * depth, joint origins, joint ranges, field extent: see deriveFp32Eps in csrc/api.cu); eps_used is what the tables were built
+ * with (= eps_derived unless b200sv_set_tuning or B200SV_FP32_EPS fixed it). */
+int b200sv_get_fp32_budget(const b200sv_ctx* ctx, double* eps_used_m, double* eps_derived_m);
+/* The probe that holds the budget to account: the fast kernel's own FK and sphere posing (same device function), no checks;
+ * centres [n * n_spheres * 3] in metres.  tests/ compares them with the FP64 centres (b200sv_sphere_centers). */
+int b200sv_debug_fast_centres(b200sv_ctx* ctx, const double* q, size_t n_states, double* centres);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------------ */
 /* Random 32-byte-sector gather over the world field's footprint: the "gather-bandwidth roofline" the check
  * kernel is compared against.  Reports sectors/s * 32 B as GB/s. */

@@ -84,6 +84,10 @@ struct b200sv_ctx
   int state_stride_fast = 0, fast_t_rows = 0, fast_n_linkpairs = 0, fast_n_reps = 0;
   bool fast_t_global = false;  // link transforms in an L2-resident scratch instead of shared memory (large robots)
   int fast_smem_blob_bytes = 0;  // bytes of the fast blob the kernel copies to shared memory
+  std::vector<int> fast_hot_sphere;  // fast blob: Hot record -> sphere (dfce order), -1 = padding
+  double fp32_eps_derived = 0.0;  // worst-case FP32 error of a posed sphere centre (m), from the model (deriveFp32Eps)
+  std::vector<double> fp32_link_eps;  // the same per device link (the fast kernel's cell-face margin is per link)
+  bool fp32_eps_user = false;     // b200sv_set_tuning fixed the budget
   bool fast_wide = false;        // the group takes the wide instance of the fast kernel (> 16 variables or a planar joint)
   float* d_t_scratch = nullptr;
   int n_dev_links = 0, n_spheres = 0, n_bs = 0, n_pairs = 0, n_link_pairs = 0;
@@ -557,6 +561,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     c.state_stride_fast += 4;
   // spheres -> Hot entries, per link padded to the unroll
   std::vector<fast::Hot> hot;
+  c.fast_hot_sphere.clear();
   std::vector<fast::Link> fl(nl);
   const bool bytes8 = c.compact_bytes == 1;
   int in_regs = -2;
@@ -638,6 +643,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     F.h0 = (int)hot.size();
     for (int k = L.s0; k < L.s1 && k < n_spheres; ++k)
     {
+      c.fast_hot_sphere.push_back(k);
       const SphereRec<double>& S = spheres[k];
       fast::Hot H{};
       H.x = (float)S.x;
@@ -649,12 +655,19 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     }
     while (((int)hot.size() - F.h0) % unroll)
     {  // padding: posed like a real sphere (at the link origin), thresholds 0: never collides
+      c.fast_hot_sphere.push_back(-1);
       fast::Hot H{};
       H.t = bytes8 ? 0x01000100u : 0u;
       hot.push_back(H);
     }
     F.h1 = (int)hot.size();
     F.c0 = F.c1 = 0;
+    // the link's own cell-face margin (cells): its spheres' worst-case FP32 error + the rounding of the magic-add index
+    {
+      const int nmax_l = std::max(c.grid.nx, std::max(c.grid.ny, c.grid.nz));
+      const double e = l < (int)c.fp32_link_eps.size() ? c.fp32_link_eps[l] : c.fp32_eps;
+      F.pad3 = (float)std::min(margin, e * c.grid.oo + nmax_l * ldexp(1.0, -22));
+    }
     fl[l] = F;
   }
   // Level-1 cull in half precision: cluster centres are parked relative to rep_base (the first root's origin).
@@ -966,6 +979,96 @@ int validateModel(b200sv_ctx* c)
   return B200SV_OK;
 }
 
+// Worst-case FP32 error (metres) of a sphere centre posed by the fast kernel, from the model: the budget every FP32 decision
+// carries (a decision that could flip within it goes to the exact pass).  First-order forward analysis of what the kernel
+// computes, u = 2^-24 the unit roundoff, all magnitudes in metres (the kernel works in cells = metres * 1/res, a pure scale):
+//   rotation block of link l     E_R[l] = E_R[parent] + joint term
+//        every link              4 u   an entry of T_parent * M is three FMAs (partial sums <= 1) + the rounded constants
+//        revolute / planar       + 4 u (M = A0 + s A1 + (1 - c) A2: two FMAs, constants) + e_trig + (|q|max + 1) u (q
+//                                narrowed to float; 1 - c)
+//        floating                + 24 u        quaternion normalisation and the nine products
+//   origin of link l             E_p[l] = E_p[parent] + sqrt(3) E_R[parent] |t_l| + 3 u (P + sqrt(3) |t_l|) + u |t_l|
+//        t_l = the joint origin's translation (+ travel for prismatic / planar / floating joints), P = the largest
+//        coordinate magnitude the kernel holds (field extent + reach): three FMAs with partial sums <= P, rounded constants
+//   sphere s of link l           E[s] = E_p[l] + sqrt(3) E_R[l] |offset_s| + 3 u (P + sqrt(3) |offset_s|) + u |offset_s| + u P
+//        (the last term: the margin-lowered translation column is rounded once more)
+// e_trig = 2^-22: sincosf's documented 2 ulp on values <= 1.  Links the host folds into an ancestor only shorten the chain.
+// link_eps[l] = the largest E[s] over the link's spheres: the kernel tests cell-face proximity with a per-link margin.
+double deriveFp32Eps(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, const std::vector<VarRec>& vars,
+                     const std::vector<SphereRec<double>>& spheres, std::vector<double>& link_eps)
+{
+  const double u = ldexp(1.0, -24), r3 = sqrt(3.0), e_trig = ldexp(1.0, -22);
+  const size_t nl = links.size();
+  const bool have_bounds = c.robot.group_lower.size() == c.robot.group_var_index.size();
+  auto qmax = [&](int var, bool angle) {
+    const VarRec& v = vars[var];
+    double m = fabs(v.b);
+    if (v.k >= 0)
+    {
+      const double lo = have_bounds ? c.robot.group_lower[v.k] : (angle ? -2.0 * M_PI : -2.0);
+      const double hi = have_bounds ? c.robot.group_upper[v.k] : (angle ? 2.0 * M_PI : 2.0);
+      const double lim = angle ? 2.0 * M_PI : 1e3;  // unbounded (continuous / planar travel): angles wrap, travel is checked
+      m = fabs(v.a) * std::min(lim, std::max(fabs(lo), fabs(hi))) + fabs(v.b);
+    }
+    return m;
+  };
+  std::vector<double> ER(nl, 0.0), EP(nl, 0.0), reach(nl, 0.0), tl(nl, 0.0), travel(nl, 0.0);
+  double reach_max = 0.0;
+  for (size_t l = 0; l < nl; ++l)
+  {
+    const LinkRec<double>& L = links[l];
+    tl[l] = L.has_origin ? sqrt(L.o[3] * L.o[3] + L.o[7] * L.o[7] + L.o[11] * L.o[11]) : 0.0;
+    if (L.type == PRISMATIC)
+      travel[l] = qmax(L.var, false);
+    else if (L.type == PLANAR)
+      travel[l] = qmax(L.var, false) + qmax(L.var + 1, false);
+    else if (L.type == FLOATING)
+      travel[l] = qmax(L.var, false) + qmax(L.var + 1, false) + qmax(L.var + 2, false);
+    travel[l] = std::min(travel[l], 4.0);  // beyond the assumed travel the kernel itself defers to the exact pass
+    reach[l] = (L.parent >= 0 ? reach[L.parent] + tl[l] : 0.0) + travel[l];
+    reach_max = std::max(reach_max, reach[l]);
+  }
+  double off_max = 0.0;
+  for (const SphereRec<double>& S : spheres)
+    off_max = std::max(off_max, sqrt(S.x * S.x + S.y * S.y + S.z * S.z));
+  const double extent = c.cfg.resolution * std::max(c.grid.nx, std::max(c.grid.ny, c.grid.nz));
+  double root_off = 0.0;  // a root's origin relative to the field corner
+  for (size_t l = 0; l < nl; ++l)
+    if (links[l].parent < 0)
+      for (int k = 0; k < 3; ++k)
+        root_off = std::max(root_off, fabs((links[l].has_origin ? links[l].o[4 * k + 3] : 0.0) - c.grid.om[k]));
+  const double P = std::max(extent, root_off) + reach_max + off_max;
+  double worst = 0.0;
+  for (size_t l = 0; l < nl; ++l)
+  {
+    const LinkRec<double>& L = links[l];
+    const double er_p = L.parent >= 0 ? ER[L.parent] : 0.0, ep_p = L.parent >= 0 ? EP[L.parent] : 0.0;
+    double joint = 4.0 * u;
+    if (L.type == REVOLUTE)
+      joint += 4.0 * u + e_trig + (qmax(L.var, true) + 1.0) * u;
+    else if (L.type == PLANAR)
+      joint += 4.0 * u + e_trig + (qmax(L.var + 2, true) + 1.0) * u;
+    else if (L.type == FLOATING)
+      joint += 24.0 * u;
+    const double t = tl[l] + travel[l];
+    ER[l] = er_p + joint;
+    EP[l] = ep_p + r3 * er_p * t + 3.0 * u * (P + r3 * t) + u * t;
+  }
+  link_eps.assign(nl, 0.0);
+  for (size_t l = 0; l < nl; ++l)
+    link_eps[l] = EP[l] + 4.0 * u * P;  // a link without spheres still poses cluster centres
+  for (const SphereRec<double>& S : spheres)
+  {
+    if (S.slot < 0 || S.slot >= (int)nl)
+      continue;
+    const double off = sqrt(S.x * S.x + S.y * S.y + S.z * S.z);
+    const double e = EP[S.slot] + r3 * ER[S.slot] * off + 3.0 * u * (P + r3 * off) + u * off + u * P;
+    link_eps[S.slot] = std::max(link_eps[S.slot], e);
+    worst = std::max(worst, e);
+  }
+  return worst;
+}
+
 int buildTables(b200sv_ctx* c)
 {
   const HostRobot& r = c->robot;
@@ -1240,6 +1343,19 @@ int buildTables(b200sv_ctx* c)
     fprintf(stderr, "b200sv: %d device links, %d spheres, %d clusters, %d cluster pairs in %d groups (%d link pairs)\n",
             c->n_dev_links, c->n_spheres, c->n_bs, c->n_pairs, (int)groups.size(), n_link_pairs);
   // ---- FP32 uncertainty budget (see DESIGN.md "precision") -------------------------------------------------------------
+  // derived from the model (deriveFp32Eps) unless b200sv_set_tuning / B200SV_FP32_EPS fixed it
+  c->fp32_eps_derived = deriveFp32Eps(*c, links, vars, spheres, c->fp32_link_eps);
+  {
+    const char* e = getenv("B200SV_FP32_EPS");
+    if (!c->fp32_eps_user && !(e && atof(e) > 0.0))
+      c->fp32_eps = c->fp32_eps_derived;
+    else
+    {  // a fixed budget applies to every link alike
+      if (!c->fp32_eps_user)
+        c->fp32_eps = atof(e);
+      c->fp32_link_eps.assign(links.size(), c->fp32_eps);
+    }
+  }
   const double eps = c->fp32_eps;
   const int nmax = std::max(c->grid.nx, std::max(c->grid.ny, c->grid.nz));
   const double margin = eps * c->grid.oo + nmax * ldexp(1.0, -22);
@@ -3488,6 +3604,64 @@ int b200sv_multi_get_stats(b200sv_multi* m, b200sv_stats* stats)
   return B200SV_OK;
 }
 
+int b200sv_get_fp32_budget(const b200sv_ctx* c, double* eps_used_m, double* eps_derived_m)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (eps_used_m)
+    *eps_used_m = c->fp32_eps;
+  if (eps_derived_m)
+    *eps_derived_m = c->fp32_eps_derived;
+  return B200SV_OK;
+}
+
+int b200sv_debug_fast_centres(b200sv_ctx* c, const double* q, size_t n, double* centres)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (n && (!q || !centres))
+    return fail(c, B200SV_ERR_INVALID, "null host pointer");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (!c->fast_ok)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "the group does not take the fast FP32 kernel");
+  if (n == 0)
+    return B200SV_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  enterCtx(c);
+  const size_t V = c->robot.group_var_index.size();
+  const auto* h = reinterpret_cast<const fast::Header*>(c->blob_fast.data());
+  const size_t n_hot = c->fast_hot_sphere.size(), S = (size_t)c->n_spheres;
+  DevBuf<float> scratch, out;
+  CU(c, c->d_q.ensure(n * V));
+  CU(c, scratch.ensure(n * (size_t)std::max(h->state_stride, 1)));
+  CU(c, out.ensure(n * n_hot * 3));
+  CU(c, cudaMemcpyAsync(c->d_q.p, q, n * V * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  cudaError_t e = launchFastCentres(c->d_blob_fast, (int)c->blob_fast.size(), c->d_q.p, n, (int)V, c->fast_wide, scratch.p, out.p,
+                                    (int)n_hot, c->stream);
+  std::vector<float> host(n * n_hot * 3);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(host.data(), out.p, host.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(c->stream);
+  scratch.release();
+  out.release();
+  if (e != cudaSuccess)
+    return fail(c, B200SV_ERR_CUDA, std::string("fast centres probe: ") + cudaGetErrorString(e));
+  // cells -> metres: p = om + f * res (the inverse of VoxelGrid::getCellFromLocation's affine map, in double)
+  const double res = c->cfg.resolution;
+  for (size_t i = 0; i < n; ++i)
+    for (size_t k = 0; k < n_hot; ++k)
+    {
+      const int sp = c->fast_hot_sphere[k];
+      if (sp < 0 || (size_t)sp >= S)
+        continue;
+      for (int a = 0; a < 3; ++a)
+        centres[(i * S + sp) * 3 + a] = c->grid.om[a] + (double)host[(i * n_hot + k) * 3 + a] * res;
+    }
+  return B200SV_OK;
+}
+
 int b200sv_gather_roofline(b200sv_ctx* c, size_t n_reads, int iters, double* gbs)
 {
   if (!c || !gbs || iters < 1)
@@ -3529,7 +3703,10 @@ int b200sv_set_tuning(b200sv_ctx* c, double fp32_eps_m, int warps_per_block, int
   std::lock_guard<std::mutex> lk(c->mu);
   enterCtx(c);
   if (fp32_eps_m > 0.0)
+  {
     c->fp32_eps = fp32_eps_m;
+    c->fp32_eps_user = true;
+  }
   if (warps_per_block > 0)
     c->tune_warps = warps_per_block;
   if (blocks_per_sm > 0)

@@ -121,7 +121,8 @@ struct alignas(16) Link
   double a, b;
   float ot[3];
   int range_check;  // 1: a prismatic joint upstream: verify the parked cluster centres stay within Header::rep_limit
-  float a0[9], a1[9], a2[9], pad3;
+  float a0[9], a1[9], a2[9];
+  float pad3;  // the link's cell-face margin in cells (its spheres' worst-case FP32 error; <= Header::margin)
 };
 static_assert(sizeof(Link) == 176, "fast::Link layout");
 

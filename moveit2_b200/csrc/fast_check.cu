@@ -303,6 +303,96 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity)
   } while (!ok);
 }
 
+// One link of the FK chain: T (the parent's transform on entry) becomes T_parent * [M | mt], M = A0 + sin q A1 + (1 - cos q) A2
+// from the link's host-built constants (see the file header).  Shared by the check kernel and fastCentresKernel (the FP32
+// error-budget probe), so both run the same arithmetic by construction.
+template <int kV>
+__device__ __forceinline__ void fastLinkStep(const int4& m0, const int4* Li, const float4* Lf, const float4& o, double q_cur,
+                                             const double* qrow, float* T)
+{
+  if (m0.x != fast::kAlias)  // an alias link is posed by its anchor's transform as it is (host-folded geometry)
+  {
+    const double2 ab = reinterpret_cast<const double2*>(Li)[2];
+    const float4 c0 = Lf[4], c1 = Lf[5], c2 = Lf[6];  // a0[0..8], a1[0..2]
+    float M[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x };
+    float mt[3] = { o.x, o.y, o.z };
+    if (m0.x != FIXED)
+    {
+      // setJointGroupPositions / updateMimicJoints in double, then narrowed (k < 0: a = 0, the value is b)
+      const float qf = static_cast<float>(ab.x * q_cur + ab.y);
+      if (m0.x == REVOLUTE)
+      {
+        const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];  // a1[3..8], a2[0..8]
+        const float A1[9] = { c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w, c4.x, c4.y };
+        const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
+        float s, c;
+        sincosf(qf, &s, &c);
+        const float t = 1.f - c;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+          M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
+      }
+      else if (kV == 0 && m0.x == PLANAR)
+      {  // variables k, k + 1, k + 2 of the group state = x, y, theta (the host checked a = 1, b = 0 for all three);
+         // [O | ot] * [Rz(theta) | (x, y, 0)] = [A0 + s A1 + t A2 (axis z) | ot + x O(:,0) + y O(:,1)]
+        const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];
+        const float A1[9] = { c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w, c4.x, c4.y };
+        const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
+        const float px = static_cast<float>(qrow[m0.y]), py = static_cast<float>(qrow[m0.y + 1]);
+        const float th = static_cast<float>(qrow[m0.y + 2]);
+        mt[0] = fmaf(px, M[0], fmaf(py, M[1], mt[0]));
+        mt[1] = fmaf(px, M[3], fmaf(py, M[4], mt[1]));
+        mt[2] = fmaf(px, M[6], fmaf(py, M[7], mt[2]));
+        float s, c;
+        sincosf(th, &s, &c);
+        const float t = 1.f - c;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+          M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
+      }
+      else if (kV == 0 && m0.x == FLOATING)
+      {  // variables k .. k + 6 = translation, then the quaternion x, y, z, w, normalised by the joint
+         // (floating_joint_model.cpp:231-236); [O | ot] * [R(q) | p] = [O R(q) | ot + O p]
+        const float px = static_cast<float>(qrow[m0.y]), py = static_cast<float>(qrow[m0.y + 1]),
+                    pz = static_cast<float>(qrow[m0.y + 2]);
+        float x = static_cast<float>(qrow[m0.y + 3]), y = static_cast<float>(qrow[m0.y + 4]),
+              z = static_cast<float>(qrow[m0.y + 5]), w = static_cast<float>(qrow[m0.y + 6]);
+        const float inv = 1.f / sqrtf(fmaf(x, x, fmaf(y, y, fmaf(z, z, w * w))));
+        x *= inv; y *= inv; z *= inv; w *= inv;
+        const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+        const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y,
+                    tyz = tz * y, tzz = tz * z;
+        const float Rq[9] = { 1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx,
+                              txz - twy, tyz + twx, 1.f - (txx + tyy) };
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+        {
+          const float o0 = M[3 * r], o1 = M[3 * r + 1], o2 = M[3 * r + 2];
+          mt[r] = fmaf(o0, px, fmaf(o1, py, fmaf(o2, pz, mt[r])));
+          M[3 * r + 0] = fmaf(o0, Rq[0], fmaf(o1, Rq[3], o2 * Rq[6]));
+          M[3 * r + 1] = fmaf(o0, Rq[1], fmaf(o1, Rq[4], o2 * Rq[7]));
+          M[3 * r + 2] = fmaf(o0, Rq[2], fmaf(o1, Rq[5], o2 * Rq[8]));
+        }
+      }
+      else
+      {  // PRISMATIC
+        mt[0] = fmaf(qf, c2.y, mt[0]);
+        mt[1] = fmaf(qf, c2.z, mt[1]);
+        mt[2] = fmaf(qf, c2.w, mt[2]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+    {
+      const float p0 = T[4 * r + 0], p1 = T[4 * r + 1], p2 = T[4 * r + 2];
+      T[4 * r + 0] = fmaf(p0, M[0], fmaf(p1, M[3], p2 * M[6]));
+      T[4 * r + 1] = fmaf(p0, M[1], fmaf(p1, M[4], p2 * M[7]));
+      T[4 * r + 2] = fmaf(p0, M[2], fmaf(p1, M[5], p2 * M[8]));
+      T[4 * r + 3] = fmaf(p0, mt[0], fmaf(p1, mt[1], fmaf(p2, mt[2], T[4 * r + 3])));
+    }
+  }
+}
+
 // Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
 // kV: group variables the register prefetch covers.  Groups of at most kSmallVars variables (an arm) get their own
 // instance: 16 prefetch registers fewer, and launch bounds that fit 3 CTAs x 6 warps per SM at 96 registers instead of
@@ -350,7 +440,7 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   const unsigned lt_mask = (1u << lane) - 1u;
   const int nz = h.nz, nynz = h.nynz;
   const unsigned idx_bias = h.idx_bias;
-  const float two_m = h.two_margin;
+  float two_m = h.two_margin;  // per link: twice the link's own cell-face margin (set in the link loop)
 
   const unsigned long long n = a.n_states;
   const unsigned long long n_tiles = (n + 31) / 32;
@@ -519,87 +609,7 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
         load12(h.ident, T);
       else if (m0.z != fast::kParentPrev)
         ts.load(m0.z, lane, T);
-      if (m0.x != fast::kAlias)  // an alias link is posed by its anchor's transform as it is (host-folded geometry)
-      {
-        const double2 ab = reinterpret_cast<const double2*>(Li)[2];
-        const float4 c0 = Lf[4], c1 = Lf[5], c2 = Lf[6];  // a0[0..8], a1[0..2]
-        float M[9] = { c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x };
-        float mt[3] = { o.x, o.y, o.z };
-        if (m0.x != FIXED)
-        {
-          // setJointGroupPositions / updateMimicJoints in double, then narrowed (k < 0: a = 0, the value is b)
-          const float qf = static_cast<float>(ab.x * q_cur + ab.y);
-          if (m0.x == REVOLUTE)
-          {
-            const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];  // a1[3..8], a2[0..8]
-            const float A1[9] = { c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w, c4.x, c4.y };
-            const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
-            float s, c;
-            sincosf(qf, &s, &c);
-            const float t = 1.f - c;
-#pragma unroll
-            for (int i = 0; i < 9; ++i)
-              M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
-          }
-          else if (kV == 0 && m0.x == PLANAR)
-          {  // variables k, k + 1, k + 2 of the group state = x, y, theta (the host checked a = 1, b = 0 for all three);
-             // [O | ot] * [Rz(theta) | (x, y, 0)] = [A0 + s A1 + t A2 (axis z) | ot + x O(:,0) + y O(:,1)]
-            const float4 c3 = Lf[7], c4 = Lf[8], c5 = Lf[9], c6 = Lf[10];
-            const float A1[9] = { c2.y, c2.z, c2.w, c3.x, c3.y, c3.z, c3.w, c4.x, c4.y };
-            const float A2[9] = { c4.z, c4.w, c5.x, c5.y, c5.z, c5.w, c6.x, c6.y, c6.z };
-            const float px = static_cast<float>(qrow[m0.y]), py = static_cast<float>(qrow[m0.y + 1]);
-            const float th = static_cast<float>(qrow[m0.y + 2]);
-            mt[0] = fmaf(px, M[0], fmaf(py, M[1], mt[0]));
-            mt[1] = fmaf(px, M[3], fmaf(py, M[4], mt[1]));
-            mt[2] = fmaf(px, M[6], fmaf(py, M[7], mt[2]));
-            float s, c;
-            sincosf(th, &s, &c);
-            const float t = 1.f - c;
-#pragma unroll
-            for (int i = 0; i < 9; ++i)
-              M[i] = fmaf(t, A2[i], fmaf(s, A1[i], M[i]));
-          }
-          else if (kV == 0 && m0.x == FLOATING)
-          {  // variables k .. k + 6 = translation, then the quaternion x, y, z, w, normalised by the joint
-             // (floating_joint_model.cpp:231-236); [O | ot] * [R(q) | p] = [O R(q) | ot + O p]
-            const float px = static_cast<float>(qrow[m0.y]), py = static_cast<float>(qrow[m0.y + 1]),
-                        pz = static_cast<float>(qrow[m0.y + 2]);
-            float x = static_cast<float>(qrow[m0.y + 3]), y = static_cast<float>(qrow[m0.y + 4]),
-                  z = static_cast<float>(qrow[m0.y + 5]), w = static_cast<float>(qrow[m0.y + 6]);
-            const float inv = 1.f / sqrtf(fmaf(x, x, fmaf(y, y, fmaf(z, z, w * w))));
-            x *= inv; y *= inv; z *= inv; w *= inv;
-            const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
-            const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y,
-                        tyz = tz * y, tzz = tz * z;
-            const float Rq[9] = { 1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx,
-                                  txz - twy, tyz + twx, 1.f - (txx + tyy) };
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-            {
-              const float o0 = M[3 * r], o1 = M[3 * r + 1], o2 = M[3 * r + 2];
-              mt[r] = fmaf(o0, px, fmaf(o1, py, fmaf(o2, pz, mt[r])));
-              M[3 * r + 0] = fmaf(o0, Rq[0], fmaf(o1, Rq[3], o2 * Rq[6]));
-              M[3 * r + 1] = fmaf(o0, Rq[1], fmaf(o1, Rq[4], o2 * Rq[7]));
-              M[3 * r + 2] = fmaf(o0, Rq[2], fmaf(o1, Rq[5], o2 * Rq[8]));
-            }
-          }
-          else
-          {  // PRISMATIC
-            mt[0] = fmaf(qf, c2.y, mt[0]);
-            mt[1] = fmaf(qf, c2.z, mt[1]);
-            mt[2] = fmaf(qf, c2.w, mt[2]);
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-        {
-          const float p0 = T[4 * r + 0], p1 = T[4 * r + 1], p2 = T[4 * r + 2];
-          T[4 * r + 0] = fmaf(p0, M[0], fmaf(p1, M[3], p2 * M[6]));
-          T[4 * r + 1] = fmaf(p0, M[1], fmaf(p1, M[4], p2 * M[7]));
-          T[4 * r + 2] = fmaf(p0, M[2], fmaf(p1, M[5], p2 * M[8]));
-          T[4 * r + 3] = fmaf(p0, mt[0], fmaf(p1, mt[1], fmaf(p2, mt[2], T[4 * r + 3])));
-        }
-      }
+      fastLinkStep<kV>(m0, Li, Lf, o, q_cur, qrow, T);
       if (m0.w >= 0)
         ts.store(m0.w, lane, T);
       if (do_intra && m1.z < m1.w)
@@ -622,7 +632,11 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
       if (!do_fields)
         continue;
       // the centre minus `margin` per axis, from a translation column lowered by margin (clamp bounds likewise)
-      const float tmx = T[3] - h.margin, tmy = T[7] - h.margin, tmz = T[11] - h.margin;
+      // (the margin is the LINK's: the worst-case FP32 error of its spheres, from the host; the clamp bounds are the
+      //  global margin's, which is the largest)
+      const float ml = Lf[10].w;
+      two_m = ml + ml;
+      const float tmx = T[3] - ml, tmy = T[7] - ml, tmz = T[11] - ml;
       int k0 = m1.x;
       for (; k0 + 4 <= m1.y; k0 += 4)
         chunk(k0, T, tmx, tmy, tmz, std::integral_constant<int, 4>());
@@ -869,6 +883,52 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   }
 }
 
+// The FP32 error-budget probe: the fast kernel's FK (fastLinkStep, the same function) and sphere posing for one state per
+// thread, no checks; writes every Hot record's posed centre in cells (margin removed).  Transforms live in a global scratch
+// laid out like the shared-memory form ([state][state_stride words]).
+template <int kV>
+__global__ void fastCentresKernel(const uint8_t* __restrict__ model, int model_bytes, const double* __restrict__ q,
+                                  unsigned long long n, float* scratch, float* __restrict__ out, int n_hot)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  const FModel m = loadFast<false>(model, model_bytes, smem);
+  const fast::Header& h = *m.h;
+  const unsigned long long state = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (state >= n)
+    return;
+  TStore<false> ts;
+  ts.base = scratch + state * static_cast<unsigned long long>(h.state_stride);
+  ts.stride = 0;
+  const double* qrow = q + state * h.n_group_vars;
+  float T[12];
+  for (int l = 0; l < h.n_links; ++l)
+  {
+    const int4* Li = reinterpret_cast<const int4*>(m.links + l);
+    const float4* Lf = reinterpret_cast<const float4*>(m.links + l);
+    const int4 m0 = Li[0];
+    const int4 m1 = Li[1];
+    const float4 o = Lf[3];
+    const double q_cur = m0.y >= 0 ? qrow[m0.y] : 0.0;
+    if (m0.z == fast::kParentRoot)
+      load12(h.ident, T);
+    else if (m0.z != fast::kParentPrev)
+      ts.load(m0.z, 0, T);
+    fastLinkStep<kV>(m0, Li, Lf, o, q_cur, qrow, T);
+    if (m0.w >= 0)
+      ts.store(m0.w, 0, T);
+    const float ml = Lf[10].w;
+    const float tmx = T[3] - ml, tmy = T[7] - ml, tmz = T[11] - ml;
+    for (int k = m1.x; k < m1.y; ++k)
+    {
+      const float4 hr = reinterpret_cast<const float4*>(m.hot)[k];
+      float* dst = out + (state * n_hot + k) * 3;
+      dst[0] = fmaf(T[0], hr.x, fmaf(T[1], hr.y, fmaf(T[2], hr.z, tmx))) + ml;
+      dst[1] = fmaf(T[4], hr.x, fmaf(T[5], hr.y, fmaf(T[6], hr.z, tmy))) + ml;
+      dst[2] = fmaf(T[8], hr.x, fmaf(T[9], hr.y, fmaf(T[10], hr.z, tmz))) + ml;
+    }
+  }
+}
+
 struct Grant
 {
   size_t granted[16] = { 0 };
@@ -926,6 +986,25 @@ int fastCheckKernelRegs(int field_bytes, int n_group_vars)
       all(uint16_t(), std::integral_constant<int, 0>());
   }
   return regs;
+}
+
+cudaError_t launchFastCentres(const uint8_t* model, int model_bytes, const double* q, unsigned long long n, int n_group_vars,
+                              bool wide, float* scratch, float* out, int n_hot, cudaStream_t stream)
+{
+  static Grant g[3];
+  const size_t smem = (static_cast<size_t>(model_bytes) + 15) & ~static_cast<size_t>(15);
+  const int block = 128;
+  const unsigned grid = static_cast<unsigned>((n + block - 1) / block);
+  auto go = [&](auto kernel, Grant& gr) {
+    const cudaError_t e = ensure(kernel, smem, gr);
+    if (e != cudaSuccess)
+      return e;
+    kernel<<<grid, block, smem, stream>>>(model, model_bytes, q, n, scratch, out, n_hot);
+    return cudaGetLastError();
+  };
+  if (wide)
+    return go(fastCentresKernel<0>, g[2]);
+  return n_group_vars <= kSmallVars ? go(fastCentresKernel<kSmallVars>, g[0]) : go(fastCentresKernel<kMaxVars>, g[1]);
 }
 
 template <typename FT>

@@ -130,6 +130,9 @@ cudaError_t launchContacts(const ContactArgs& a, int grid, int block, size_t sme
 // fast_check.cu: the FP32 pass for groups of fixed / revolute / prismatic joints (a.model = the fast blob)
 template <typename FT>
 cudaError_t launchFastCheck(const CheckArgs<FT>& a, int grid, int block, size_t smem_bytes, cudaStream_t stream);
+// FP32 error-budget probe: the fast kernel's FK + sphere posing alone, every Hot record's centre in cells
+cudaError_t launchFastCentres(const uint8_t* model, int model_bytes, const double* q, unsigned long long n, int n_group_vars,
+                              bool wide, float* scratch, float* out, int n_hot, cudaStream_t stream);
 int fastCheckKernelRegs(int field_bytes, int n_group_vars);
 int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs, bool wide);
 int fastCheckMaxVars();

@@ -428,6 +428,19 @@ class StateValidityEngine:
                                                  _u8p(col), _ip(cnt), con.ctypes.data_as(C.c_void_p)))
         return col, cnt, con
 
+    def fp32_budget(self):
+        """(eps the tables were built with, eps derived from the model), metres."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        self._check(self.L.b200sv_get_fp32_budget(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def debug_fast_centres(self, q):
+        """Sphere centres [n, n_spheres, 3] (metres) as the FAST kernel's FP32 arithmetic poses them."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, self.n_group_vars)
+        out = np.zeros((q.shape[0], max(self.n_spheres, 1), 3))
+        self._check(self.L.b200sv_debug_fast_centres(self.h, _dp(q), q.shape[0], _dp(out)))
+        return out[:, : self.n_spheres]
+
     def gather_roofline(self, n_reads=1 << 28, iters=3):
         g = C.c_double(0.0)
         self._check(self.L.b200sv_gather_roofline(self.h, n_reads, iters, C.byref(g)))

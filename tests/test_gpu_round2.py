@@ -405,3 +405,56 @@ def test_field_add_octree_leaves_equals_the_restated_expansion():
     g, o = eng.field_get_d2(), env.world.d2()
     assert int((o == 0).sum()) > 2000 and np.array_equal(g == 0, o == 0)
     eng.close()
+
+
+@pytest.mark.parametrize("robot,group", [("panda", "panda_arm"), ("dualarm", "arms"), ("dualarm", "whole_body")])
+def test_fp32_budget_is_derived_and_covers_the_fast_kernels_error(robot, group):
+    """The budget every FP32 decision carries is derived from the model (b200sv_get_fp32_budget; deriveFp32Eps: chain depth,
+    joint origins and ranges, field extent), not a constant.  The fast kernel's own FK + posing (b200sv_debug_fast_centres
+    runs the same device function) must stay within it on random states and on the corners of the joint box."""
+    eng, env = make_pair(robot, group, (3.0, 3.0, 2.5), (0, 0, 1.0), 0.02, 0.25)
+    used, derived = eng.fp32_budget()
+    assert used == derived and 1e-6 < derived < 2e-4
+    lo, hi = eng.group_bounds()
+    lo, hi = np.maximum(lo, -2.0 * np.pi), np.minimum(hi, 2.0 * np.pi)
+    q = workloads.random_states(77, 3000, lo, hi)
+    nc = 2 ** min(len(lo), 7)
+    q[:nc] = np.array([[hi[k] if (i >> (k % 7)) & 1 else lo[k] for k in range(len(lo))] for i in range(nc)])
+    fast = eng.debug_fast_centres(q)
+    exact = np.stack([env.sphere_centers(q[i]) for i in range(len(q))])      # the oracle's FP64 centres
+    err = np.abs(fast - exact).max()
+    print("%s/%s: worst FP32 centre error %.3e m, budget %.3e m (%.2f of it)" % (robot, group, err, used, err / used))
+    assert err <= used
+    eng.close()
+
+
+def test_device_entry_points_stay_inside_their_buffers(c1):
+    """compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer_unavailable.txt), so the out-of-bounds check is
+    done by hand: every caller-owned device buffer is surrounded by canary words that must survive the call, for ragged
+    sizes (bitmap words: whole 32-bit words are written, nothing beyond; FK output: exactly n * n_links * 16 doubles)."""
+    torch = pytest.importorskip("torch")
+    eng, env, cloud, q = c1
+    s = torch.cuda.current_stream().cuda_stream
+    guard = 64
+    for n in (1, 31, 32, 33, 1000, 4097):
+        d_q = torch.from_numpy(q[:n]).cuda()
+        words = (n + 31) // 32
+        bm = torch.full((guard + 4 * words + guard,), 0xA5, dtype=torch.uint8, device="cuda")
+        eng.check_batch_device(d_q.data_ptr(), n, ALL, bm.data_ptr() + guard, s)
+        out = torch.full((guard + n * eng.n_links * 16 + guard,), -7.25, dtype=torch.float64, device="cuda")
+        eng.fk_batch_device(d_q.data_ptr(), n, 32, out.data_ptr() + 8 * guard, s)
+        torch.cuda.synchronize()
+        b = bm.cpu().numpy()
+        assert (b[:guard] == 0xA5).all() and (b[guard + 4 * words:] == 0xA5).all()
+        ref, _ = env.check(q[:n], ALL)
+        assert np.array_equal(np.unpackbits(b[guard:guard + 4 * words], bitorder="little")[:n].astype(bool), ref == 0)
+        o = out.cpu().numpy()
+        assert (o[:guard] == -7.25).all() and (o[guard + n * eng.n_links * 16:] == -7.25).all()
+        assert not (o[guard:guard + n * eng.n_links * 16] == -7.25).any()
+    # field export: exactly field_export_size bytes
+    size = eng.field_export_size()
+    buf = torch.full((guard + size + guard,), 0x5A, dtype=torch.uint8, device="cuda")
+    eng.field_export_device(buf.data_ptr() + guard, mb.FIELD_WORLD, s)
+    torch.cuda.synchronize()
+    b = buf.cpu().numpy()
+    assert (b[:guard] == 0x5A).all() and (b[guard + size:] == 0x5A).all()
