@@ -462,11 +462,11 @@ def main():
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch over 1 M states, from the committed
                      # ncu --set full capture, scaled to n: the 16 MB field and the transform scratch are L2-resident,
                      # DRAM sees the states streaming in once
-                     "traffic": 69.06 * n if args.workload == "C2" else None,
-                     "traffic_source": "profiles/r1_fast_v14_summary.txt (ncu --set full, 1 launch)",
+                     "traffic": 70.21 * n if args.workload == "C2" else None,
+                     "traffic_source": "profiles/r2_fast_v15_summary.txt (ncu --set full, 1 launch: 65.58 MB read + 4.63 MB written)",
                      "peak_source": peak_src, "algorithmic_bytes_per_state": b_state,
                      "binding": "NOT DRAM: the field is L2-resident (ncu: dram 2 %, L2 hit 93 %); the kernel is bound by "
-                                "instruction issue (67 %) and the L1TEX data pipe (69 %) -- frac is algorithmic sector "
+                                "instruction issue (67 %) and the L1TEX data pipe (66 %) -- frac is algorithmic sector "
                                 "bytes over the HBM copy peak, the north star's figure is roofline_l1_gather",
                      "kernel": "fastCheckKernel<uint8_t,true> (+ the exact recheck launch recheckWarpKernel<uint8_t>)"},
         "roofline_l1_gather": {"bound": "l1tex-gather", "achieved": gather_achieved, "peak": gather_gbs,

@@ -1457,7 +1457,7 @@ int uploadTables(b200sv_ctx* c)
   {
     const char* e = getenv("B200SV_LATENCY");
     c->latency_ok = !(e && atoi(e) == 0) && c->robot.group_var_index.size() <= 32 &&
-                    (size_t)align16((int)c->blob_d.size()) + 4 * ((size_t)c->state_stride_d + 32) * 8 <= (size_t)c->smem_optin;
+                    (size_t)align16((int)c->blob_d.size()) + 4 * ((size_t)c->state_stride_d + 32 + 2 * (size_t)c->n_dev_links) * 8 <= (size_t)c->smem_optin;
   }
   c->cfg_f = chooseCfg(c, false, false, (int)c->blob_f.size());
   c->cfg_d = chooseCfg(c, true, false, (int)c->blob_d.size());
@@ -2777,6 +2777,7 @@ static int checkLatency(b200sv_ctx* c, const double* q, size_t n, uint32_t flags
     a.flags = flags & 7u;
     a.n_states = (int)n;
     a.state_stride = c->state_stride_d;
+    a.n_links = c->n_dev_links;
     a.use_inline = n * V <= 32 ? 1 : 0;
     a.q = reinterpret_cast<const double*>(c->d_lat);
     a.result = c->d_lat + q_bytes;

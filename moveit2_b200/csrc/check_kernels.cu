@@ -160,8 +160,10 @@ __device__ __forceinline__ R varValue(const VarRec& v, const double* __restrict_
 }
 
 // Phase 1: FK of one state into shared memory.  T: this state's transform block (link stride kLinkStrideWords).
+// sc (optional): sin / cos of every revolute / planar link's angle, [2 l] and [2 l + 1], computed beforehand (the latency
+// kernel lets 32 lanes do that in parallel: the libm-grade FP64 sincos is most of a link's serial time).
 template <typename R>
-__device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restrict__ qrow, R* T)
+__device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restrict__ qrow, R* T, const R* sc = nullptr)
 {
   const int n_links = m.h->n_links;
   for (int l = 0; l < n_links; ++l)
@@ -193,9 +195,14 @@ __device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restri
     {
       case REVOLUTE:
       {  // revolute_joint_model.cpp:250-287
-        const R q = varValue<R>(m.vars[L.var], qrow);
         R s, c;
-        sincosR(q, &s, &c);
+        if (sc)
+        {
+          s = sc[2 * l];
+          c = sc[2 * l + 1];
+        }
+        else
+          sincosR(varValue<R>(m.vars[L.var], qrow), &s, &c);
         const R x = L.ax[0], y = L.ax[1], z = L.ax[2];
         const R t = R(1) - c;
         const R txy = t * (x * y), txz = t * (x * z), tyz = t * (y * z);
@@ -227,9 +234,14 @@ __device__ __forceinline__ void fkState(const Smem<R>& m, const double* __restri
       case PLANAR:
       {  // planar_joint_model.cpp:345-349: Translation(x, y, 0) * AngleAxis(theta, UnitZ)
         const R px = varValue<R>(m.vars[L.var], qrow), py = varValue<R>(m.vars[L.var + 1], qrow);
-        const R th = varValue<R>(m.vars[L.var + 2], qrow);
         R s, c;
-        sincosR(th, &s, &c);
+        if (sc)
+        {
+          s = sc[2 * l];
+          c = sc[2 * l + 1];
+        }
+        else
+          sincosR(varValue<R>(m.vars[L.var + 2], qrow), &s, &c);
         R J[12] = { c, -s, R(0), px, s, c, R(0), py, R(0), R(0), (R(1) - c) + c, R(0) };
         mulAffine<R>(A, J, O);
         break;
@@ -1079,34 +1091,43 @@ __global__ void __launch_bounds__(128) recheckWarpKernel(CheckArgs<FT> a)
 
 // The latency path of b200sv_check_batch (a single-state checkCollision through the plugin is a batch of 1): ONE launch and no
 // copies.  The states arrive inside the kernel parameters (or, beyond 32 doubles, are read from mapped pinned host memory); one
-// warp per state runs the exact FP64 check -- the arithmetic every FP32 decision is referred to anyway -- and lane 0 stores the
+// CTA per state runs the exact FP64 check -- the arithmetic every FP32 decision is referred to anyway -- and lane 0 stores the
 // state's result byte (1 = valid, 0 = in collision) straight into mapped host memory, where the host is polling for it.
 template <typename FT>
 __global__ void __launch_bounds__(128) latencyCheckKernel(LatencyArgs<FT> a)
 {
+  // ONE STATE PER CTA: what is left after the launch is a chain of dependent latencies (blob -> sin / cos -> FK chain ->
+  // field gathers -> pair tests -> the result's trip over PCIe), so the four warps shorten every link of that chain they can:
+  // the joints' sines and cosines in parallel, the spheres in ONE pass of 128 lanes, the cluster pairs in two.
   extern __shared__ __align__(16) uint8_t smem[];
   const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
   const ModelHeader<double>& h = *m.h;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  double* T = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(warp) * (a.state_stride + 32);
-  double* qs = T + a.state_stride;  // this warp's copy of its state
+  double* T = reinterpret_cast<double*>(smem + h.total_bytes);
+  double* qs = T + a.state_stride;  // the state
+  double* sc = qs + 32;             // sin, cos per link
   const bool do_world = (a.flags & 1u) != 0, do_self = (a.flags & 2u) != 0, do_intra = (a.flags & 4u) != 0;
   const typename Combined<FT>::type* __restrict__ field = static_cast<const typename Combined<FT>::type*>(a.field);
-  const int state = blockIdx.x * warps + warp;
-  if (state >= a.n_states)
-    return;
-  if (lane < h.n_group_vars)
-    qs[lane] = a.use_inline ? a.q_inline[state * h.n_group_vars + lane] : a.q[state * h.n_group_vars + lane];
-  __syncwarp();
-  if (lane == 0)
-    fkState<double>(m, qs, T);
-  __syncwarp();
+  const int state = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < h.n_group_vars)
+    qs[tid] = a.use_inline ? a.q_inline[state * h.n_group_vars + tid] : a.q[state * h.n_group_vars + tid];
+  __syncthreads();
+  for (int l = tid; l < h.n_links; l += blockDim.x)
+  {
+    const LinkRec<double>& L = m.links[l];
+    if (L.type == REVOLUTE || L.type == PLANAR)
+      sincos(varValue<double>(m.vars[L.var + (L.type == PLANAR ? 2 : 0)], qs), &sc[2 * l], &sc[2 * l + 1]);
+  }
+  __syncthreads();
+  if (tid == 0)
+    fkState<double>(m, qs, T, sc);
+  __syncthreads();
   bool hit = false, amb = false;
   if (do_world | do_self)
-    for (int k = lane; k < h.n_spheres_padded; k += 32)
+    for (int k = tid; k < h.n_spheres_padded; k += blockDim.x)
       sphereChunk<double, FT, 1>(m, T, k, do_world, do_self, field, true, hit, amb);
-  if (do_intra && !__any_sync(kFull, hit))
-    for (int p = lane; p < h.n_pairs; p += 32)
+  if (do_intra && !__syncthreads_or(hit ? 1 : 0))
+    for (int p = tid; p < h.n_pairs; p += blockDim.x)
     {
       const PairRec pr = m.pairs[p];
       const BsRec<double>& A = m.bs[pr.a];
@@ -1118,8 +1139,8 @@ __global__ void __launch_bounds__(128) latencyCheckKernel(LatencyArgs<FT> a)
       if (live)
         pairItem<double>(m, T, pr, certain, hit, amb);
     }
-  const bool any = __any_sync(kFull, hit);
-  if (lane == 0)
+  const int any = __syncthreads_or(hit ? 1 : 0);
+  if (tid == 0)
   {
     a.result[state] = any ? 0 : 1;
     __threadfence_system();
@@ -1189,11 +1210,11 @@ cudaError_t launchLatencyCheck(const LatencyArgs<FT>& a, cudaStream_t stream)
   static SmemGrant g;
   const int block = 128;
   const size_t smem = ((static_cast<size_t>(a.model_bytes) + 15) & ~static_cast<size_t>(15)) +
-                      static_cast<size_t>(block / 32) * (a.state_stride + 32) * sizeof(double);
+                      static_cast<size_t>(a.state_stride + 32 + 2 * a.n_links) * sizeof(double);
   cudaError_t e = ensureSmem(latencyCheckKernel<FT>, smem, g);
   if (e != cudaSuccess)
     return e;
-  latencyCheckKernel<FT><<<(a.n_states + 3) / 4, block, smem, stream>>>(a);
+  latencyCheckKernel<FT><<<a.n_states, block, smem, stream>>>(a);
   return cudaGetLastError();
 }
 template cudaError_t launchLatencyCheck<uint8_t>(const LatencyArgs<uint8_t>&, cudaStream_t);

@@ -66,6 +66,7 @@ struct LatencyArgs
   uint32_t flags;
   int n_states;
   int state_stride;      // doubles of link transforms per state (the double blob's)
+  int n_links;           // device links (the double blob's): sin / cos scratch per warp
   int use_inline;        // the states are q_inline (n_states * n_group_vars <= 32 doubles); else q
   const double* q;       // device-visible (mapped pinned host) states
   uint8_t* result;       // device-visible (mapped pinned host) [n_states]: 1 = valid, 0 = in collision
