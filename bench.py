@@ -570,6 +570,44 @@ def main():
         line["cpu_baseline"] = None
         edt_cpu = None
 
+    # ---- the cloud SURVEY.md 8d wrote down literally (half uniform in the volume): a reported side case ----------------------
+    if not args.no_parity and args.workload == "C2":
+        cfg_s = workloads.CONFIGS["C2S"]
+        eng_s = mb.StateValidityEngine.for_robot(cfg_s["robot"], cfg_s["group"], size=cfg_s["size"], origin=cfg_s["origin"],
+                                                 resolution=cfg_s["resolution"], max_distance=cfg_s["max_distance"], device=local)
+        cloud_s = workloads.make_cloud("C2S")
+        eng_s.field_add_points(cloud_s)
+        ns = 1_000_000
+        qs_host = workloads.random_states(cfg_s["states"]["seed"], ns, lo, hi)
+        d_qs = torch.from_numpy(qs_host).to(dev)
+        bm_s = torch.zeros(4 * ((ns + 31) // 32), dtype=torch.uint8, device=dev)
+        ts = []
+        for i in range(8):
+            flush.fill_(i)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            eng_s.check_batch_device(d_qs.data_ptr(), ns, flags, bm_s.data_ptr(), stream.cuda_stream)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(ev0.elapsed_time(ev1))
+        ms_s = float(np.median(ts[3:]))
+        env_s = oracle_env(cfg_s, cloud_s)
+        eng_s.field_set_d2(env_s.world.d2(), mb.FIELD_WORLD)
+        eng_s.field_set_d2(env_s.self_field.d2(), mb.FIELD_SELF)
+        nsp = 200_000
+        col_s, _ = env_s.check(qs_host[:nsp], 7, faithful=False, threads=all_host_threads())
+        val_s = eng_s.check_batch(qs_host[:nsp], flags)
+        line["survey_c2"] = {"workload": "C2 with SURVEY.md 8d's literal cloud: 250 000 points uniform in the 8 m^3 volume + 250 000 "
+                                         "on 20 random boxes, no keep-out",
+                             "value": ns / (ms_s * 1e-3), "unit": "states/s", "ms_per_step": ms_s,
+                             "valid_fraction": float(val_s.mean()), "validity_states_compared": nsp,
+                             "validity_mismatches": int((val_s == col_s.astype(bool)).sum()),
+                             "note": "at this density nearly every random arm state collides and stops gathering early: "
+                                     "a degenerate workload for a validity kernel, which is why the headline uses surface "
+                                     "clutter (moveit2_b200/workloads.py)"}
+        del d_qs, env_s
+        eng_s.close()
+
     # ---- EDT voxels/s on C4 -----------------------------------------------------------------------------------------------
     if not args.no_edt:
         c4 = workloads.CONFIGS["C4"]

@@ -309,8 +309,9 @@ int b200sv_check_motions(b200sv_ctx* ctx, const double* q_from, const double* q_
  * un-normalised centre difference, :644-709), world field (ENVIRONMENT = 3, :1645-1681); field distances are
  * sqrt(d2) * resolution with central-difference gradients times the reference's INTEGER inv_twice_resolution_
  * (distance_field.cpp:73-97, distance_field.hpp:614); distances >= max_propagation_distance are not recorded.
- * FP64, the reference's operation order.  Not restated: the per-link PosedDistanceFields of getSelfProximityGradients,
- * which the reference consults only when an ACM was passed (:386).
+ * FP64, the reference's operation order.  The per-link PosedDistanceFields of getSelfProximityGradients (:386-411), which the
+ * reference consults when the cache entry's ACM is not empty, are reproduced once b200sv_set_gradient_link_mask switched
+ * them on (see "per-link PosedDistanceFields" below).
  *   distances         [n * n_spheres]      DBL_MAX where nothing was recorded (GradientInfo::distances)
  *   gradients         [n * n_spheres * 3]  0 where nothing was recorded (the reference leaves those uninitialised)
  *   types             [n * n_spheres]      CollisionType: NONE 0, SELF 1, INTRA 2, ENVIRONMENT 3
@@ -387,6 +388,28 @@ int b200sv_multi_field_add_points(b200sv_multi* m, int which, const double* xyz,
 /* b200sv_check_batch over all devices: block i of the states goes to context i; pinned host buffers make every copy a DMA. */
 int b200sv_check_batch_multi(b200sv_multi* m, const double* q, size_t n_states, uint32_t flags, uint8_t* valid_bitmap);
 int b200sv_multi_get_stats(b200sv_multi* m, b200sv_stats* stats);
+
+/* ---- per-link PosedDistanceFields of the gradient path ---------------------------------------------------------------- */
+/* getSelfProximityGradients (collision_env_distance_field.cpp:386-411) also consults, for every entry i, the
+ * PosedDistanceField of every OTHER link j whose name differs and for which the cache entry's ACM has no entry other than
+ * NEVER -- but only when that ACM is not empty (CHOMP creates its GroupStateRepresentation with the scene's ACM,
+ * chomp_optimizer.cpp:102, so for CHOMP it is).  A link's field is a PropagationDistanceField of the size of its bounding
+ * sphere's diameter, cornered at the sphere's centre - size / 2 IN THE LINK FRAME, filled with the link's interior points
+ * (getGroupStateRepresentation :1177-1197).  The query is PosedDistanceField::getDistanceGradient exactly as written
+ * (collision_distance_field_types.hpp:163-176): the point is rotated by the pose's rotation transposed WITHOUT subtracting
+ * the translation, the gradient comes back as pose * g WITH the translation added; consequently an out-of-bounds query ends
+ * the entry's sphere loop (types.cpp:104).  b200sv_collision_gradients reproduces that when a mask is set.
+ *   b200sv_set_link_field        the field of entry `glink` as the caller built it (a MoveIt workspace: the reference's own
+ *                                PosedDistanceField, voxel by voxel): size and corner as above, d2 [nx * ny * nz] squared cell
+ *                                distances with n = int(size / resolution); d2 = NULL: the link has none
+ *   b200sv_build_link_fields     URDF path: every entry's field built on the device (exact EDT of the link's interior points)
+ *   b200sv_get_link_field        dims (0 0 0: none), corner, and -- if d2 is not NULL -- the voxels
+ *   b200sv_set_gradient_link_mask  enabled [n_glinks * n_glinks]: entry i consults link j's field; NULL = the ACM is empty,
+ *                                no field is consulted (the default) */
+int b200sv_set_link_field(b200sv_ctx* ctx, int32_t glink, const double* size, const double* corner, const int32_t* d2);
+int b200sv_build_link_fields(b200sv_ctx* ctx);
+int b200sv_get_link_field(b200sv_ctx* ctx, int32_t glink, int32_t* dims, double* corner, int32_t* d2);
+int b200sv_set_gradient_link_mask(b200sv_ctx* ctx, const uint8_t* enabled);
 
 /* ---- the FP32 error budget -------------------------------------------------------------------------------------------- */
 /* The fast pass decides in FP32; every decision carries a budget eps (metres) and whatever could flip within it is decided

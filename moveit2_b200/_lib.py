@@ -133,6 +133,10 @@ def load():
         "b200sv_multi_field_add_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_check_batch_multi": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp]),
         "b200sv_multi_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
+        "b200sv_set_link_field": (C.c_int, [vp, C.c_int32, dp, dp, ip]),
+        "b200sv_build_link_fields": (C.c_int, [vp]),
+        "b200sv_get_link_field": (C.c_int, [vp, C.c_int32, ip, dp, ip]),
+        "b200sv_set_gradient_link_mask": (C.c_int, [vp, u8p]),
         "b200sv_get_fp32_budget": (C.c_int, [vp, dp, dp]),
         "b200sv_debug_fast_centres": (C.c_int, [vp, dp, C.c_size_t, dp]),
         "b200sv_gather_roofline": (C.c_int, [vp, C.c_size_t, C.c_int, dp]),

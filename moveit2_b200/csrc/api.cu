@@ -142,6 +142,19 @@ struct b200sv_ctx
   DevBuf<uint32_t> d_edge_state_bits, d_edge_bits;
   DevBuf<int32_t> d_edge_first;
   DevBuf<uint8_t> d_edge_cont;
+  // per-link PosedDistanceFields of the gradient path (GroupStateRepresentation::link_distance_fields_)
+  struct LinkField
+  {
+    uint16_t* d2 = nullptr;
+    int n[3] = { 0, 0, 0 };
+    double corner[3] = { 0, 0, 0 };
+  };
+  std::vector<LinkField> link_fields;        // [n_glinks]
+  std::vector<uint8_t> lf_enabled;           // [n_glinks^2]; empty: the ACM is empty, the fields are not consulted
+  DevBuf<uint8_t> d_lf_enabled;
+  LinkFieldDev* d_lf = nullptr;
+  bool lf_dirty = true;
+  SelfLocalPoints link_points;               // URDF path: link-frame interior points of every link with geometry
   // K5 outputs
   DevBuf<double> d_g_dist, d_g_grad, d_g_closest, d_g_centers;
   DevBuf<uint8_t> d_g_types, d_g_self;
@@ -1865,7 +1878,7 @@ int b200sv_create_from_urdf(int device, const char* urdf_xml, const char* srdf_x
   std::string err;
   bool parse_error = false;
   if (!loadUrdfSrdf(urdf_xml, srdf_xml ? srdf_xml : "", group_name, field->resolution, c->robot, c->cm, c->self_points,
-                    c->self_local, err, parse_error))
+                    c->self_local, c->link_points, err, parse_error))
   {
     delete c;
     return fail(nullptr, parse_error ? B200SV_ERR_PARSE : B200SV_ERR_INVALID, err);
@@ -1928,6 +1941,10 @@ void b200sv_destroy(b200sv_ctx* c)
   c->d_edge_cont.release();
   c->d_g_dist.release(); c->d_g_grad.release(); c->d_g_closest.release(); c->d_g_centers.release();
   c->d_g_types.release(); c->d_g_self.release();
+  for (auto& lf : c->link_fields)
+    if (lf.d2) cudaFree(lf.d2);
+  if (c->d_lf) cudaFree(c->d_lf);
+  c->d_lf_enabled.release();
   c->d_c_start.release(); c->d_c_slot.release(); c->d_c_count.release(); c->d_c_bs.release(); c->d_c_intra.release();
   c->d_c_coll.release(); c->d_c_out.release();
   if (c->d_link_slot) cudaFree(c->d_link_slot);
@@ -3084,6 +3101,43 @@ int b200sv_collision_gradients(b200sv_ctx* c, const double* q, size_t n, double*
     CU(c, cudaMemcpy(c->d_sqrt_table, table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   a.sqrt_table = c->d_sqrt_table;
+  // the per-link posed fields, when the caller switched them on (b200sv_set_gradient_link_mask)
+  a.lf = nullptr;
+  if (!c->lf_enabled.empty() && c->link_fields.size() == L)
+  {
+    if (c->lf_dirty)
+    {
+      std::vector<LinkFieldDev> host(L);
+      for (size_t g = 0; g < L; ++g)
+      {
+        host[g].d2 = c->link_fields[g].d2;
+        for (int k = 0; k < 3; ++k)
+        {
+          host[g].n[k] = c->link_fields[g].n[k];
+          host[g].om[k] = c->link_fields[g].corner[k] - 0.5 * c->cfg.resolution;
+        }
+      }
+      if (!c->d_lf)
+        CU(c, cudaMalloc(&c->d_lf, L * sizeof(LinkFieldDev)));
+      CU(c, cudaMemcpyAsync(c->d_lf, host.data(), L * sizeof(LinkFieldDev), cudaMemcpyHostToDevice, s));
+      CU(c, c->d_lf_enabled.ensure(L * L));
+      CU(c, cudaMemcpyAsync(c->d_lf_enabled.p, c->lf_enabled.data(), L * L, cudaMemcpyHostToDevice, s));
+      CU(c, cudaStreamSynchronize(s));  // `host` lives on this stack frame
+      c->lf_dirty = false;
+    }
+    std::vector<int32_t> slot(L);
+    for (size_t g = 0; g < L; ++g)
+      slot[g] = c->glink_slot[g];
+    CU(c, c->d_c_start.ensure(L + 1));
+    CU(c, c->d_c_slot.ensure(L));
+    CU(c, cudaMemcpyAsync(c->d_c_start.p, c->cm.sphere_start.data(), (L + 1) * 4, cudaMemcpyHostToDevice, s));
+    CU(c, cudaMemcpyAsync(c->d_c_slot.p, slot.data(), L * 4, cudaMemcpyHostToDevice, s));
+    CU(c, cudaStreamSynchronize(s));
+    a.lf = c->d_lf;
+    a.lf_enabled = c->d_lf_enabled.p;
+    a.sphere_start = c->d_c_start.p;
+    a.glink_slot = c->d_c_slot.p;
+  }
   a.resolution = c->cfg.resolution;
   // DistanceField::inv_twice_resolution_ is declared int (distance_field.hpp:614): 1 / (2 res) truncated
   a.inv_twice_resolution = (double)(int)(1.0 / (2.0 * c->cfg.resolution));
@@ -3602,6 +3656,183 @@ int b200sv_multi_get_stats(b200sv_multi* m, b200sv_stats* stats)
     return B200SV_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
   *stats = m->stats;
+  return B200SV_OK;
+}
+
+// ---- per-link PosedDistanceFields (getGroupStateRepresentation :1177-1197, getSelfProximityGradients :386-411) ----------
+static int linkFieldDims(const b200sv_ctx* c, const double* size, int n[3])
+{
+  const double oo = 1.0 / c->cfg.resolution;
+  for (int k = 0; k < 3; ++k)
+  {
+    n[k] = (int)(size[k] * oo);  // VoxelGrid::resize (voxel_grid.hpp:384)
+    if (n[k] < 1)
+      return 0;
+  }
+  return 1;
+}
+
+int b200sv_set_link_field(b200sv_ctx* c, int32_t glink, const double* size, const double* corner, const int32_t* d2)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (glink < 0 || glink >= c->cm.n_glinks || !size || !corner)
+    return fail(c, B200SV_ERR_INVALID, "bad entry index or null geometry");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (c->cfg.use_signed_distance_field)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "per-link fields of a signed context are not implemented");
+  std::lock_guard<std::mutex> lk(c->mu);
+  enterCtx(c);
+  c->link_fields.resize((size_t)c->cm.n_glinks);
+  b200sv_ctx::LinkField& F = c->link_fields[(size_t)glink];
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (F.d2)
+    cudaFree(F.d2);
+  F = b200sv_ctx::LinkField();
+  c->lf_dirty = true;
+  if (!d2)
+    return B200SV_OK;  // the link has no field (no geometry)
+  int n[3];
+  if (!linkFieldDims(c, size, n))
+    return fail(c, B200SV_ERR_INVALID, "link field has no cells along one axis");
+  const size_t nv = (size_t)n[0] * n[1] * n[2];
+  CU(c, cudaMalloc(&F.d2, nv * 2));
+  CU(c, c->d_i32.ensure(nv));
+  CU(c, cudaMemcpyAsync(c->d_i32.p, d2, nv * 4, cudaMemcpyHostToDevice, c->stream));
+  GridDev g = c->grid;
+  g.nx = n[0];
+  g.ny = n[1];
+  g.nz = n[2];
+  CU(c, launchInjectNegD2(g, c->d_i32.p, F.d2, c->stream));  // clamps to [0, max_d2], narrows to 16 bits
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 3; ++k)
+  {
+    F.n[k] = n[k];
+    F.corner[k] = corner[k];
+  }
+  return B200SV_OK;
+}
+
+int b200sv_get_link_field(b200sv_ctx* c, int32_t glink, int32_t* dims, double* corner, int32_t* d2)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (glink < 0 || glink >= c->cm.n_glinks || !dims)
+    return fail(c, B200SV_ERR_INVALID, "bad entry index or null dims");
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  std::lock_guard<std::mutex> lk(c->mu);
+  enterCtx(c);
+  dims[0] = dims[1] = dims[2] = 0;
+  if ((size_t)glink >= c->link_fields.size() || !c->link_fields[(size_t)glink].d2)
+    return B200SV_OK;
+  const b200sv_ctx::LinkField& F = c->link_fields[(size_t)glink];
+  for (int k = 0; k < 3; ++k)
+  {
+    dims[k] = F.n[k];
+    if (corner)
+      corner[k] = F.corner[k];
+  }
+  if (d2)
+  {
+    const size_t nv = (size_t)F.n[0] * F.n[1] * F.n[2];
+    std::vector<uint16_t> h(nv);
+    CU(c, cudaMemcpyAsync(h.data(), F.d2, nv * 2, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < nv; ++i)
+      d2[i] = h[i];
+  }
+  return B200SV_OK;
+}
+
+int b200sv_build_link_fields(b200sv_ctx* c)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  if (needDevice(c))
+    return B200SV_ERR_NO_DEVICE;
+  if (c->link_points.empty())
+    return fail(c, B200SV_ERR_UNSUPPORTED, "the links' interior points are known on the URDF path only: use b200sv_set_link_field");
+  if (c->cfg.use_signed_distance_field)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "per-link fields of a signed context are not implemented");
+  std::lock_guard<std::mutex> lk(c->mu);
+  enterCtx(c);
+  const int L = c->cm.n_glinks;
+  c->link_fields.resize((size_t)L);
+  c->lf_dirty = true;
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int g = 0; g < L; ++g)
+  {
+    b200sv_ctx::LinkField& F = c->link_fields[(size_t)g];
+    if (F.d2)
+      cudaFree(F.d2);
+    F = b200sv_ctx::LinkField();
+    if (c->cm.sphere_start[g + 1] <= c->cm.sphere_start[g])
+      continue;
+    const std::vector<double>* pts = nullptr;
+    for (const auto& lp : c->link_points)
+      if (lp.first == c->cm.glink_index[g])
+        pts = &lp.second;
+    if (!pts)
+      continue;
+    // size = the bounding sphere's diameter, corner = its centre - size / 2, in the link frame (:1177-1188)
+    const double* bs = &c->cm.bounding_sphere[4 * (size_t)g];
+    const double diameter = 2 * bs[3];
+    const double size[3] = { diameter, diameter, diameter };
+    int n[3];
+    if (!linkFieldDims(c, size, n))
+      continue;
+    GridDev gl = c->grid;
+    gl.nx = n[0];
+    gl.ny = n[1];
+    gl.nz = n[2];
+    gl.wz = (gl.nz + 31) / 32;
+    for (int k = 0; k < 3; ++k)
+    {
+      F.corner[k] = bs[k] - 0.5 * size[k];
+      gl.om[k] = F.corner[k] - 0.5 * c->cfg.resolution;
+      F.n[k] = n[k];
+    }
+    const size_t nv = (size_t)n[0] * n[1] * n[2], occ_words = (size_t)n[0] * n[1] * gl.wz, np = pts->size() / 3;
+    uint32_t* occ = nullptr;
+    uint16_t* tmp = nullptr;
+    CU(c, cudaMalloc(&F.d2, nv * 2));
+    CU(c, cudaMalloc(&occ, occ_words * 4));
+    CU(c, cudaMalloc(&tmp, nv * 2));
+    CU(c, cudaMemsetAsync(occ, 0, occ_words * 4, c->stream));
+    cudaError_t e = cudaSuccess;
+    if (np)
+    {
+      e = c->d_points.ensure(3 * np);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(c->d_points.p, pts->data(), 3 * np * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess)
+        e = launchScatter(c->d_points.p, np, gl, occ, true, c->stream);
+    }
+    if (e == cudaSuccess)
+      e = launchEdt(gl, occ, tmp, F.d2, nullptr, c->compact_bytes, c->sm_count, c->stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(c->stream);
+    cudaFree(occ);
+    cudaFree(tmp);
+    if (e != cudaSuccess)
+      return fail(c, B200SV_ERR_CUDA, std::string("building a link field: ") + cudaGetErrorString(e));
+  }
+  return B200SV_OK;
+}
+
+int b200sv_set_gradient_link_mask(b200sv_ctx* c, const uint8_t* enabled)
+{
+  if (!c)
+    return B200SV_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t L = (size_t)c->cm.n_glinks;
+  if (enabled)
+    c->lf_enabled.assign(enabled, enabled + L * L);
+  else
+    c->lf_enabled.clear();
+  c->lf_dirty = true;
   return B200SV_OK;
 }
 

@@ -821,6 +821,61 @@ __device__ __forceinline__ void fieldGradients(const GradArgs& a, const uint16_t
   }
 }
 
+// PosedDistanceField::getCollisionSphereGradients (collision_distance_field_types.cpp:87-147) on link j's field for the
+// spheres [s0, s1) of one entry, with PosedDistanceField::getDistanceGradient (types.hpp:163-176) exactly as written:
+// rel_pos = pose.linear().transpose() * p (the translation is not subtracted), grad = pose * g (the translation is added),
+// so an out-of-bounds query returns the link's translation as its gradient, `grad.norm() > 0` (:104) holds for every link
+// away from the origin and the loop ends there.  Tj: rows of [R | t] of link j.  Explicit round-to-nearest operations in
+// the reference's (Eigen's) order, no FMA.
+__device__ __forceinline__ void posedFieldGradients(const GradArgs& a, const LinkFieldDev& F, const double* Tj, int s0, int s1,
+                                                    const double* cen, double* dist_out, double* grad_out, uint8_t* type_out,
+                                                    double& closest, double oo_res)
+{
+  for (int k = s0; k < s1; ++k)
+  {
+    const double p0 = cen[3 * k], p1 = cen[3 * k + 1], p2 = cen[3 * k + 2];
+    int g[3];
+    bool inb = true;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax)
+    {
+      const double rel = __dadd_rn(__dadd_rn(__dmul_rn(Tj[0 + ax], p0), __dmul_rn(Tj[4 + ax], p1)), __dmul_rn(Tj[8 + ax], p2));
+      g[ax] = static_cast<int>(floor((rel - F.om[ax]) * oo_res));
+      inb = inb && !(g[ax] < 1 || g[ax] >= F.n[ax] - 1);
+    }
+    double dist = a.max_distance, gl0 = 0.0, gl1 = 0.0, gl2 = 0.0;
+    if (inb)
+    {
+      const size_t sy = static_cast<size_t>(F.n[2]), sx = sy * F.n[1];
+      const size_t i0 = (static_cast<size_t>(g[0]) * F.n[1] + g[1]) * F.n[2] + g[2];
+      gl0 = (cellDistance(a, F.d2, nullptr, i0 + sx) - cellDistance(a, F.d2, nullptr, i0 - sx)) * a.inv_twice_resolution;
+      gl1 = (cellDistance(a, F.d2, nullptr, i0 + sy) - cellDistance(a, F.d2, nullptr, i0 - sy)) * a.inv_twice_resolution;
+      gl2 = (cellDistance(a, F.d2, nullptr, i0 + 1) - cellDistance(a, F.d2, nullptr, i0 - 1)) * a.inv_twice_resolution;
+      dist = cellDistance(a, F.d2, nullptr, i0);
+    }
+    double gr[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      gr[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Tj[4 * r], gl0), __dmul_rn(Tj[4 * r + 1], gl1)), __dmul_rn(Tj[4 * r + 2], gl2)),
+                        Tj[4 * r + 3]);
+    if (!inb && sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gr[0], gr[0]), __dmul_rn(gr[1], gr[1])), __dmul_rn(gr[2], gr[2]))) > 0.0)
+      return;  // "out of bounds": the reference returns here, the entry's remaining spheres are not looked at
+    if (dist < a.max_propagation)
+    {
+      if (dist < closest)
+        closest = dist;
+      if (dist < dist_out[k])
+      {
+        type_out[k] = 1;  // SELF
+        dist_out[k] = dist;
+        grad_out[3 * k] = gr[0];
+        grad_out[3 * k + 1] = gr[1];
+        grad_out[3 * k + 2] = gr[2];
+      }
+    }
+  }
+}
+
 // kLocal: the per-state working arrays (distances, gradients, types, centres, closest) live in LOCAL memory -- which the
 // hardware interleaves by lane, so the warp's accesses are coalesced and L1/L2 resident -- and are copied to the caller's
 // state-major arrays once at the end.  Working on the state-major arrays directly (a warp's 32 rows are S * 8 bytes apart)
@@ -860,6 +915,22 @@ __global__ void __launch_bounds__(128) gradientKernel(GradArgs a)
   // closest_distance per dfce link; links are runs of clusters with the same glink id (BsRec::pad)
   for (int g = 0; g < a.n_glinks; ++g)
     closest[g] = 1.7976931348623157e308;
+  // getSelfProximityGradients (:355-428): per entry, the other links' posed fields first (only with a non-empty ACM), then
+  // the cache entry's self field.  Entries are independent of each other, so doing all the posed fields first keeps the order
+  // that matters (within an entry).
+  if (a.lf != nullptr)
+    for (int g = 0; g < a.n_glinks; ++g)
+    {
+      const int s0 = a.sphere_start[g], s1 = a.sphere_start[g + 1];
+      if (s1 <= s0 || !a.self_enabled[g])
+        continue;
+      for (int j = 0; j < a.n_glinks; ++j)
+      {
+        if (!a.lf_enabled[g * a.n_glinks + j] || a.lf[j].d2 == nullptr)
+          continue;
+        posedFieldGradients(a, a.lf[j], T + a.glink_slot[j] * kLinkStrideWords, s0, s1, cen, D, G, Ty, closest[g], h.oo_res);
+      }
+    }
   for (int c = 0; c < h.n_bs; ++c)
   {  // self field
     const BsRec<double>& C = m.bs[c];

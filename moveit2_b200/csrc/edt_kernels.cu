@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(256) scatterKernel(const double* __restrict__ 
   }
 }
 
+// i / d by multiply-high with magic = ceil(2^32 / d); d = 1 has no 32-bit magic (2^32): the launcher passes 0 for it
+__device__ __forceinline__ unsigned divByMagic(unsigned i, unsigned magic) { return magic ? __umulhi(i, magic) : i; }
+
 // One CTA per (x plane, y chunk).  Shared memory: occupancy words of rows [y0-R, y1+R), then their SQUARED z distances
 // as uint16 (row stride nzp = nz rounded up to 8: a thread takes 8 consecutive z with one 128-bit access).  Squares,
 // because the y pass then is two packed 16-bit instructions per candidate row and voxel pair: VIMNMX.U16x2 (min of the
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(1024) edtZYKernel(GridDev g, const uint32_t* _
     const int nzb = nzp >> 3;
     for (int i = threadIdx.x; i < rows * nzb; i += blockDim.x)
     {
-      const int r = static_cast<int>(__umulhi(static_cast<unsigned>(i), nz8_magic));  // i / nzb
+      const int r = static_cast<int>(divByMagic(static_cast<unsigned>(i), nz8_magic));  // i / nzb
       const int kb = i - r * nzb;
       const int w = kb >> 2, o = (kb & 3) * 8;
       const uint32_t cur = bits[r * wz + w], e = ends[r * wz + w];
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(1024) edtZYKernel(GridDev g, const uint32_t* _
   const uint4* gz4 = reinterpret_cast<const uint4*>(gz);
   for (int i = threadIdx.x; i < (y1 - y0) * nz8; i += blockDim.x)
   {
-    const int yy = static_cast<int>(__umulhi(static_cast<unsigned>(i), nz8_magic));  // i / nz8
+    const int yy = static_cast<int>(divByMagic(static_cast<unsigned>(i), nz8_magic));  // i / nz8
     const int zc = i - yy * nz8;
     const uint4* ctr = gz4 + (yy + R) * nz8 + zc;  // row yy + R of the haloed block
     uint4 best = *ctr;
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* 
   const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= plane8)
     return;
-  const int y = static_cast<int>(__umulhi(p, nz8_magic));  // p / nz8
+  const int y = static_cast<int>(divByMagic(p, nz8_magic));  // p / nz8
   const int zc = static_cast<int>(p) - y * nz8;
   const bool shell_y = y == 0 || y == g.ny - 1;
   const int R = g.R, max_d2 = g.max_d2;

@@ -229,7 +229,8 @@ struct Group
 }  // namespace
 
 bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::string& group_name, double resolution,
-                  HostRobot& robot, HostCollisionModel& cm, std::vector<double>& self_points, SelfLocalPoints& self_local, std::string& err,
+                  HostRobot& robot, HostCollisionModel& cm, std::vector<double>& self_points, SelfLocalPoints& self_local,
+                  SelfLocalPoints& link_points, std::string& err,
                   bool& parse_error)
 {
   parse_error = true;
@@ -927,12 +928,15 @@ bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::s
 
   // ---- self-field points: links with geometry outside the updated set, posed at the base state (:907-953) ----------------
   self_local.clear();
+  link_points.clear();
   for (const auto& l : links)
   {
     auto d = decomp.find(l.index);
-    if (d == decomp.end() || updated.count(l.index))
+    if (d == decomp.end())
       continue;
-    self_local.push_back({ l.index, d->second.points });
+    link_points.push_back({ l.index, d->second.points });
+    if (!updated.count(l.index))
+      self_local.push_back({ l.index, d->second.points });
   }
   poseSelfPoints(robot, base, self_local, self_points);
   return true;

@@ -52,7 +52,7 @@ bool isIdentityTransform(const double* m16);
 using SelfLocalPoints = std::vector<std::pair<int, std::vector<double>>>;
 bool loadUrdfSrdf(const std::string& urdf, const std::string& srdf, const std::string& group, double resolution,
                   HostRobot& robot, HostCollisionModel& cm, std::vector<double>& self_points, SelfLocalPoints& self_local,
-                  std::string& err, bool& parse_error);
+                  SelfLocalPoints& link_points, std::string& err, bool& parse_error);
 // The self field's generating points at `positions` (all model variables): every link's points moved by its global transform
 // (generateDistanceFieldCacheEntry, collision_env_distance_field.cpp:907-953).
 void poseSelfPoints(const HostRobot& robot, const std::vector<double>& positions, const SelfLocalPoints& self_local,

@@ -76,6 +76,13 @@ template <typename FT>
 cudaError_t launchLatencyCheck(const LatencyArgs<FT>& a, cudaStream_t stream);
 int checkKernelRegs(bool fp64, bool from_list, int field_bytes);
 int checkPerWarpBytes(bool fp64, int state_stride);  // shared memory one warp of the check kernel needs
+// One link's PosedDistanceField on the device: 16-bit d^2 on its own small grid in the LINK frame
+struct LinkFieldDev
+{
+  const uint16_t* d2;  // nullptr: the link has no field
+  int n[3];
+  double om[3];        // VoxelGrid origin_minus_ = corner - resolution / 2
+};
 // K5: per-sphere distance / gradient / type (getCollisionGradients), FP64, exact blob
 struct GradArgs
 {
@@ -89,6 +96,12 @@ struct GradArgs
   const uint16_t* nd2_self;
   const uint8_t* self_enabled;  // [n_glinks]
   int n_glinks, n_spheres, state_stride;  // state_stride: doubles of link transforms per state (the double blob's)
+  // per-link PosedDistanceFields (GroupStateRepresentation::link_distance_fields_): consulted for entry i and link j where
+  // lf_enabled[i * n_glinks + j]; lf == nullptr: the cache entry's ACM is empty, none is consulted
+  const struct LinkFieldDev* lf;   // [n_glinks]
+  const uint8_t* lf_enabled;       // [n_glinks * n_glinks]
+  const int32_t* sphere_start;     // [n_glinks + 1]
+  const int32_t* glink_slot;       // [n_glinks] device-link slot of each entry's link
   const double* sqrt_table;  // [max_d2 + 1]: sqrt(double(i)) * resolution (PropagationDistanceField::sqrt_table_)
   double resolution, inv_twice_resolution, max_distance, max_propagation;
   double* distances;  // [n * n_spheres]

@@ -428,6 +428,34 @@ class StateValidityEngine:
                                                  _u8p(col), _ip(cnt), con.ctypes.data_as(C.c_void_p)))
         return col, cnt, con
 
+    # ---- per-link PosedDistanceFields of the gradient path ---------------------------------------------------
+    def set_link_field(self, glink, size, corner, d2):
+        sz = np.ascontiguousarray(size, np.float64).reshape(3)
+        co = np.ascontiguousarray(corner, np.float64).reshape(3)
+        a = None if d2 is None else np.ascontiguousarray(d2, np.int32).reshape(-1)
+        self._check(self.L.b200sv_set_link_field(self.h, int(glink), _dp(sz), _dp(co), _ip(a) if a is not None else None))
+
+    def build_link_fields(self):
+        self._check(self.L.b200sv_build_link_fields(self.h))
+
+    def get_link_field(self, glink):
+        """(d2 [nx, ny, nz] int32 or None, corner)"""
+        dims, corner = np.zeros(3, np.int32), np.zeros(3)
+        self._check(self.L.b200sv_get_link_field(self.h, int(glink), _ip(dims), _dp(corner), None))
+        if dims[0] == 0:
+            return None, corner
+        d2 = np.zeros(tuple(int(v) for v in dims), np.int32)
+        self._check(self.L.b200sv_get_link_field(self.h, int(glink), _ip(dims), _dp(corner), _ip(d2)))
+        return d2, corner
+
+    def set_gradient_link_mask(self, enabled):
+        """enabled [n_glinks, n_glinks] (entry i consults link j's field) or None (the ACM is empty: none consulted)."""
+        if enabled is None:
+            self._check(self.L.b200sv_set_gradient_link_mask(self.h, None))
+        else:
+            a = np.ascontiguousarray(enabled, np.uint8).reshape(self.n_glinks * self.n_glinks)
+            self._check(self.L.b200sv_set_gradient_link_mask(self.h, _u8p(a)))
+
     def fp32_budget(self):
         """(eps the tables were built with, eps derived from the model), metres."""
         a, b = C.c_double(0.0), C.c_double(0.0)

@@ -83,6 +83,13 @@ CONFIGS = {
                 max_distance=0.25, cloud=dict(seed=6, n_points=200_000, n_boxes=30, lo=(-1.3, -1.3, 0.1),
                                               hi=(1.3, 1.3, 2.0), keepout_radius=0.75),
                 states=dict(seed=4, n=10_000_000)),
+    # C2S: C2 with the cloud SURVEY.md 8d wrote down literally -- half the points uniform in the field VOLUME, half on the
+    # surfaces of 20 random boxes (no keep-out around the robot, no floor).  At that density nearly every random arm state
+    # collides (see the module docstring), so it is a reported side case (bench key `survey_c2`), not the headline.
+    "C2S": dict(robot="panda", group="panda_arm", size=(2.0, 2.0, 2.0), origin=(0.0, 0.0, 0.5), resolution=0.01,
+                max_distance=0.25, cloud=dict(seed=3, n_points=500_000, n_boxes=20, lo=(-0.9, -0.9, -0.4),
+                                              hi=(0.9, 0.9, 1.4), keepout_radius=0.0, uniform_fraction=0.5),
+                states=dict(seed=2, n=1_000_000)),
     # C4: EDT rebuild only -- 5 M points uniform in a 4 x 4 x 2 m box, 400 x 400 x 200 voxels at 1 cm
     "C4": dict(size=(4.0, 4.0, 2.0), origin=(0.0, 0.0, 1.0), resolution=0.01, max_distance=0.25,
                cloud=dict(seed=5, n_points=5_000_000)),
@@ -101,4 +108,10 @@ def make_cloud(name):
     c = cfg["cloud"]
     if "n_boxes" not in c:
         return uniform_cloud(c["seed"], c["n_points"], cfg["size"], cfg["origin"])
+    if c.get("uniform_fraction"):
+        n_uni = int(c["n_points"] * c["uniform_fraction"])
+        uni = uniform_cloud(c["seed"], n_uni, cfg["size"], cfg["origin"])
+        box = clutter_cloud(c["seed"] + 1, c["n_points"] - n_uni, c["n_boxes"], c["lo"], c["hi"], c.get("keepout_radius", 0.0),
+                            floor=False)
+        return np.ascontiguousarray(np.concatenate([uni, box], axis=0))
     return clutter_cloud(c["seed"], c["n_points"], c["n_boxes"], c["lo"], c["hi"], c.get("keepout_radius", 0.28))

@@ -79,6 +79,9 @@ def _declare(L):
     L.orc_state_margin.argtypes = [vp, vp, vp, vp, dp, dp, c.c_int]
     L.orc_collision_gradients.argtypes = [vp, vp, vp, vp, dp, dp, c.c_size_t, dp, dp, c.POINTER(c.c_uint8), dp]
     L.orc_collision_gradients.restype = None
+    L.orc_collision_gradients_lf.argtypes = [vp, vp, vp, vp, dp, dp, c.c_size_t, dp, dp, c.POINTER(c.c_uint8), dp,
+                                             c.POINTER(vp), c.POINTER(c.c_uint8)]
+    L.orc_collision_gradients_lf.restype = None
     L.orc_check_contacts.argtypes = [vp, vp, vp, vp, dp, dp, c.c_size_t, c.c_int, c.c_uint, c.c_uint,
                                      c.POINTER(c.c_uint8), ip, vp]
     L.orc_check_contacts.restype = None

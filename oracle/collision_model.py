@@ -519,12 +519,57 @@ class OracleEnv:
         return self.L.orc_state_margin(C.byref(self.robot), C.byref(self.cm), self.world.h, self.self_field.h,
                                        _p(self.base_positions, C.c_double), _p(q1, C.c_double), int(flags))
 
-    def collision_gradients(self, q):
-        """getCollisionGradients for every state: (distances [n, S], gradients [n, S, 3], types [n, S], closest [n, L])."""
+    def build_link_fields(self):
+        """The per-link PosedDistanceFields of the GroupStateRepresentation (collision_env_distance_field.cpp:1177-1197):
+        for every updated link with geometry a PropagationDistanceField of size diameter^3 of its bounding sphere, corner =
+        bounding-sphere centre - size / 2 IN THE LINK FRAME (the posed decomposition is still at the identity when the
+        field is built), filled with the link's interior points.  Also the matrix of (i, j) pairs getSelfProximityGradients
+        consults them for (:386-411): names differ and the ACM has no entry for the pair other than NEVER."""
+        from .df import PropagationDistanceField
+        gl = self.group.updated_links
+        n = len(gl)
+        acm = AllowedCollisionMatrix(self.model.srdf)
+        self.link_fields = []
+        for l in gl:
+            d = self.decomp.get(l.name)
+            if d is None:
+                self.link_fields.append(None)
+                continue
+            diameter = 2 * d.bs_radius
+            size = np.array([diameter, diameter, diameter])
+            origin = np.asarray(d.bs_center, np.float64) - 0.5 * size
+            f = PropagationDistanceField(size[0], size[1], size[2], self.resolution, origin[0], origin[1], origin[2],
+                                         self.max_prop)
+            f.add_points(d.points)
+            f.size, f.corner = size, origin
+            self.link_fields.append(f)
+        en = np.zeros((int(self.cm.n_glinks), int(self.cm.n_glinks)), np.uint8)
+        for i in range(n):
+            for j in range(n):
+                if gl[i].name != gl[j].name and not acm.always(gl[i].name, gl[j].name):
+                    en[i, j] = 1
+        self.lf_enabled = en
+        return self.link_fields, en
+
+    def collision_gradients(self, q, with_link_fields=False):
+        """getCollisionGradients for every state: (distances [n, S], gradients [n, S, 3], types [n, S], closest [n, L]).
+        with_link_fields: the cache entry carries a non-empty ACM, so getSelfProximityGradients also consults the other
+        links' PosedDistanceFields (build_link_fields)."""
         q = np.ascontiguousarray(q, np.float64).reshape(-1, max(self.group.variable_count, 1))
         n, S, L = q.shape[0], self.n_spheres, int(self.cm.n_glinks)
         d, g = np.zeros((n, S)), np.zeros((n, S, 3))
         t, c = np.zeros((n, S), np.uint8), np.zeros((n, L))
+        if with_link_fields:
+            if not hasattr(self, "link_fields"):
+                self.build_link_fields()
+            arr = (C.c_void_p * L)(*[(f.h if f is not None else None) for f in self.link_fields] +
+                                   [None] * (L - len(self.link_fields)))
+            en = np.ascontiguousarray(self.lf_enabled, np.uint8)
+            self.L.orc_collision_gradients_lf(C.byref(self.robot), C.byref(self.cm), self.world.h, self.self_field.h,
+                                              _p(self.base_positions, C.c_double), _p(q, C.c_double), C.c_size_t(n),
+                                              _p(d, C.c_double), _p(g, C.c_double), _p(t, C.c_uint8), _p(c, C.c_double),
+                                              arr, _p(en, C.c_uint8))
+            return d, g, t, c
         self.L.orc_collision_gradients(C.byref(self.robot), C.byref(self.cm), self.world.h, self.self_field.h,
                                        _p(self.base_positions, C.c_double), _p(q, C.c_double), C.c_size_t(n),
                                        _p(d, C.c_double), _p(g, C.c_double), _p(t, C.c_uint8), _p(c, C.c_double))

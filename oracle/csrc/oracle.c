@@ -1108,9 +1108,65 @@ static void sphere_gradients(const orc_pdf* f, const orc_collision_model* cm, in
   }
 }
 
+/* PosedDistanceField::getCollisionSphereGradients (collision_distance_field_types.cpp:87-147) on the PosedDistanceField of link
+ * j for the spheres of entry i, with PosedDistanceField::getDistanceGradient (collision_distance_field_types.hpp:163-176)
+ * EXACTLY as written there:
+ *   rel_pos = pose_.linear().transpose() * p        -- the pose's translation is NOT subtracted
+ *   grad    = pose_ * (gx, gy, gz)                  -- an isometry times a vector: the translation IS added
+ * so an out-of-bounds query returns the link's translation as its "gradient", grad.norm() > 0 (types.cpp:104) is true for
+ * every link away from the world origin, and the loop over the entry's spheres ends there ("return true"), without looking
+ * at the spheres after it.  Tj: link j's global transform, 4x4 column-major. */
+static void sphere_gradients_posed(const orc_pdf* f, const double* Tj, const orc_collision_model* cm, int i,
+                                   const double* centers, double* dist_out, double* grad_out, uint8_t* type_out, double* closest)
+{
+  for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1]; ++k)
+  {
+    const double* c = centers + 3 * k;
+    double rel[3], gl[3], grad[3];
+    int inb;
+    for (int a = 0; a < 3; ++a) /* (R^T p)_a = R(0,a) p0 + R(1,a) p1 + R(2,a) p2 */
+      rel[a] = (M(Tj, 0, a) * c[0] + M(Tj, 1, a) * c[1]) + M(Tj, 2, a) * c[2];
+    double dist = orc_pdf_get_distance_gradient(f, rel[0], rel[1], rel[2], gl, &inb);
+    for (int a = 0; a < 3; ++a) /* linear() * g + translation() */
+      grad[a] = ((M(Tj, a, 0) * gl[0] + M(Tj, a, 1) * gl[1]) + M(Tj, a, 2) * gl[2]) + M(Tj, a, 3);
+    if (!inb && sqrt((grad[0] * grad[0] + grad[1] * grad[1]) + grad[2] * grad[2]) > 0.0)
+      return; /* "out of bounds": return true */
+    if (dist < cm->max_propagation_distance)
+    {
+      if (dist < closest[i])
+        closest[i] = dist;
+      if (dist < dist_out[k])
+      {
+        type_out[k] = 1; /* SELF */
+        dist_out[k] = dist;
+        grad_out[3 * k] = grad[0];
+        grad_out[3 * k + 1] = grad[1];
+        grad_out[3 * k + 2] = grad[2];
+      }
+    }
+  }
+}
+
+void orc_collision_gradients_lf(const orc_robot* r, const orc_collision_model* cm, const orc_pdf* world, const orc_pdf* self,
+                                const double* base_positions, const double* q, size_t n, double* distances,
+                                double* gradients, uint8_t* types, double* closest, const orc_pdf* const* link_fields,
+                                const uint8_t* lf_enabled);
+
 void orc_collision_gradients(const orc_robot* r, const orc_collision_model* cm, const orc_pdf* world, const orc_pdf* self,
                              const double* base_positions, const double* q, size_t n, double* distances, double* gradients,
                              uint8_t* types, double* closest)
+{
+  orc_collision_gradients_lf(r, cm, world, self, base_positions, q, n, distances, gradients, types, closest, NULL, NULL);
+}
+
+/* link_fields [n_glinks] (NULL entries: no geometry) and lf_enabled [n_glinks * n_glinks]: the per-link PosedDistanceFields
+ * of the GroupStateRepresentation (collision_env_distance_field.cpp:1190-1197) and, for entry i, which links j they are
+ * consulted for -- getSelfProximityGradients :386-411: only when the cache entry's ACM is not empty, j's name differs from
+ * i's, and the ACM has no entry (i, j) other than NEVER.  Both NULL: the ACM is empty (:386 false). */
+void orc_collision_gradients_lf(const orc_robot* r, const orc_collision_model* cm, const orc_pdf* world, const orc_pdf* self,
+                                const double* base_positions, const double* q, size_t n, double* distances,
+                                double* gradients, uint8_t* types, double* closest, const orc_pdf* const* link_fields,
+                                const uint8_t* lf_enabled)
 {
   const int L = cm->n_glinks, S = cm->sphere_start[L];
   orc_scratch s;
@@ -1137,8 +1193,15 @@ void orc_collision_gradients(const orc_robot* r, const orc_collision_model* cm, 
       }
     }
     for (int i = 0; i < L; ++i)
-      if (cm->has_geometry[i] && cm->self_enabled[i] && self)
-        sphere_gradients(self, cm, i, s.centers, 1, D, G, Ty, Cl);
+      if (cm->has_geometry[i] && cm->self_enabled[i])
+      { /* getSelfProximityGradients :355-428: the other links' posed fields first, then the cache entry's self field */
+        if (link_fields && lf_enabled)
+          for (int j = 0; j < L; ++j)
+            if (lf_enabled[(size_t)i * L + j] && link_fields[j])
+              sphere_gradients_posed(link_fields[j], s.link_T + 16 * cm->glink_index[j], cm, i, s.centers, D, G, Ty, Cl);
+        if (self)
+          sphere_gradients(self, cm, i, s.centers, 1, D, G, Ty, Cl);
+      }
     for (int i = 0; i < L; ++i)
       for (int j = i + 1; j < L; ++j)
       {

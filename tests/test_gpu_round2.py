@@ -458,3 +458,69 @@ def test_device_entry_points_stay_inside_their_buffers(c1):
     torch.cuda.synchronize()
     b = buf.cpu().numpy()
     assert (b[:guard] == 0x5A).all() and (b[guard + size:] == 0x5A).all()
+
+
+def test_collision_gradients_with_per_link_posed_fields(c1):
+    """getSelfProximityGradients with a non-empty ACM (collision_env_distance_field.cpp:386-411; what CHOMP runs: its
+    GroupStateRepresentation is created with the scene's ACM, chomp_optimizer.cpp:102): every entry also consults the
+    PosedDistanceFields of the other links, through PosedDistanceField::getDistanceGradient EXACTLY as written (rotation
+    transposed without the translation in, translation added to the gradient out, an out-of-bounds query ends the entry's
+    sphere loop).  The reference's own link fields (oracle: its propagation) are injected; same bar as the plain test."""
+    eng, env, cloud, q = c1
+    n = 2000
+    fields, enabled = env.build_link_fields()
+    for g, f in enumerate(fields):
+        if f is None:
+            eng.set_link_field(g, (0.1, 0.1, 0.1), (0, 0, 0), None)
+        else:
+            eng.set_link_field(g, f.size, f.corner, f.d2())
+            back, corner = eng.get_link_field(g)
+            assert back.shape == f.num_cells and np.array_equal(back, f.d2()) and np.allclose(corner, f.corner)
+    eng.set_gradient_link_mask(enabled)
+    try:
+        d, g, t, c, loc = eng.collision_gradients(q[:n])
+        rd, rg, rt, rc = env.collision_gradients(q[:n], with_link_fields=True)
+        pd, pg, pt, pc = env.collision_gradients(q[:n])
+        changed = int((rd != pd).sum())
+        assert changed > 100, "the posed fields should change some entries of the test scene (%d)" % changed
+        both_none = (t == 0) & (rt == 0)
+        close = np.isclose(d, rd, rtol=0, atol=1e-9) | both_none
+        assert close.mean() > 0.9999, "%d of %d sphere distances differ" % ((~close).sum(), close.size)
+        same = close & (t == rt)
+        assert same.mean() > 0.9995
+        assert np.allclose(g[same], rg[same], rtol=0, atol=1e-9)
+        assert np.isclose(c, rc, rtol=0, atol=1e-9).mean() > 0.999
+        # the entries the posed fields changed are reproduced too, not just the untouched majority
+        touched = (rd != pd) & ~both_none
+        assert np.isclose(d[touched], rd[touched], rtol=0, atol=1e-9).mean() > 0.99
+        assert np.allclose(g[touched & same], rg[touched & same], rtol=0, atol=1e-9)
+    finally:
+        eng.set_gradient_link_mask(None)
+    # switched off again: the plain result
+    d0 = eng.collision_gradients(q[:200])[0]
+    assert np.isclose(d0, env.collision_gradients(q[:200])[0], rtol=0, atol=1e-9).mean() > 0.9999
+
+
+def test_link_fields_built_on_the_device_are_the_exact_transform():
+    """b200sv_build_link_fields (URDF path): every link's field from its interior lattice points with the device EDT --
+    same geometry as the reference's (size = bounding-sphere diameter, corner = centre - size / 2, n = int(size / res)),
+    occupancy equal to the reference's, distances the exact truncated transform (<= the reference's propagation)."""
+    from scipy import ndimage
+    eng, env = make_pair("panda", "panda_arm", (1, 1, 1), (0, 0, 0.5), 0.02, 0.25)
+    fields, _ = env.build_link_fields()
+    eng.build_link_fields()
+    seen = 0
+    for g, f in enumerate(fields):
+        d2, corner = eng.get_link_field(g)
+        if f is None:
+            assert d2 is None
+            continue
+        o = f.d2()
+        assert d2.shape == f.num_cells and np.allclose(corner, f.corner, atol=1e-12)
+        assert np.array_equal(d2 == 0, o == 0) and (d2 <= o).all()
+        if (d2 == 0).any():
+            exact = np.minimum(np.rint(ndimage.distance_transform_edt(d2 != 0) ** 2).astype(np.int64), eng.max_distance_sq)
+            assert np.array_equal(d2, exact)
+        seen += 1
+    assert seen >= 8
+    eng.close()

@@ -46,6 +46,10 @@ assert np.array_equal(eng.check_batch(q[:32]), v[:32])
 eng.check_motions(q[:100], q[100:200], 0.05 * float(np.sum(hi - lo)))
 eng.check_motions(q[:3], q[3:6], 0.05 * float(np.sum(hi - lo)))
 eng.collision_gradients(q[:200])
+eng.build_link_fields()                                # per-link PosedDistanceFields (tiny grids through the same EDT kernels)
+eng.set_gradient_link_mask(np.ones((eng.n_glinks, eng.n_glinks), np.uint8) - np.eye(eng.n_glinks, dtype=np.uint8))
+eng.collision_gradients(q[:200])
+eng.set_gradient_link_mask(None)
 eng.check_contacts(q[:200], max_contacts=4, max_contacts_per_pair=2)
 eng.fk_batch(q[:100], 32)
 eng.fk_batch(q[:100], 64)
