@@ -26,7 +26,7 @@ class CollisionModel(C.Structure):
     _fields_ = [("n_glinks", C.c_int32), ("glink_index", C.POINTER(C.c_int32)),
                 ("self_enabled", C.POINTER(C.c_uint8)), ("intra_enabled", C.POINTER(C.c_uint8)),
                 ("sphere_start", C.POINTER(C.c_int32)), ("sphere_xyzr", C.POINTER(C.c_double)),
-                ("bounding_sphere", C.POINTER(C.c_double))]
+                ("bounding_sphere", C.POINTER(C.c_double)), ("body_id", C.POINTER(C.c_int32))]
 
 
 class FieldCfg(C.Structure):

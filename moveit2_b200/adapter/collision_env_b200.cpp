@@ -158,6 +158,7 @@ void CollisionEnvB200::flattenModel(const moveit::core::JointModelGroup* jmg, co
   struct BodyEntry
   {
     int link_i;  // index into glinks
+    int body;    // which attached body (its shapes share the id: b200sv_collision_model::body_id)
     std::string name;
     std::vector<double> xyzr;
     double bs[4];
@@ -166,6 +167,7 @@ void CollisionEnvB200::flattenModel(const moveit::core::JointModelGroup* jmg, co
   std::string& sig = out.attached_signature;
   sig.clear();
   char num[64];
+  int n_bodies = 0;
   for (int i = 0; i < n; ++i)
   {
     std::vector<const moveit::core::AttachedBody*> attached;
@@ -183,6 +185,7 @@ void CollisionEnvB200::flattenModel(const moveit::core::JointModelGroup* jmg, co
         const BodyDecomposition d(att->getShapes()[k], resolution_, 0.0);
         BodyEntry e;
         e.link_i = i;
+        e.body = n_bodies;
         e.name = att->getName();
         for (const CollisionSphere& cs : d.getCollisionSpheres())
         {
@@ -202,10 +205,12 @@ void CollisionEnvB200::flattenModel(const moveit::core::JointModelGroup* jmg, co
         body_entries.push_back(std::move(e));
       }
       sig += ">";
+      ++n_bodies;
     }
   }
   out.entry_names.clear();
   out.entry_is_attached.clear();
+  out.body_id.assign(n, -1);
   for (int i = 0; i < n; ++i)
   {
     out.entry_names.push_back(glinks[i]->getName());
@@ -243,6 +248,7 @@ void CollisionEnvB200::flattenModel(const moveit::core::JointModelGroup* jmg, co
       out.bounding_sphere.insert(out.bounding_sphere.end(), e.bs, e.bs + 4);
       out.entry_names.push_back(e.name);
       out.entry_is_attached.push_back(true);
+      out.body_id.push_back(e.body);
     }
     intra_enabled.swap(intra2);
   }
@@ -319,6 +325,7 @@ CollisionEnvB200::createContext(const moveit::core::JointModelGroup* jmg, const 
   m.sphere_start = fm.sphere_start.data();
   m.sphere_xyzr = fm.sphere_xyzr.data();
   m.bounding_sphere = fm.bounding_sphere.data();
+  m.body_id = fm.body_id.data();  // multi-shape bodies: the library proves its per-shape cull equals the reference's or refuses
 
   const b200sv_field_cfg f = fieldCfg(size_, origin_, resolution_, max_propogation_distance_, collision_tolerance_,
                                       use_signed_distance_field_);

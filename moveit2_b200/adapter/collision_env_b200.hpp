@@ -93,7 +93,7 @@ private:
   /// What generateDistanceFieldCacheEntry derives from (group, state, ACM): the flat collision model
   struct FlatModel
   {
-    std::vector<int32_t> glink_index, sphere_start;
+    std::vector<int32_t> glink_index, sphere_start, body_id;
     std::vector<uint8_t> self_enabled, intra_enabled;
     std::vector<double> sphere_xyzr, bounding_sphere;
     std::vector<std::string> entry_names;

@@ -1332,6 +1332,26 @@ int buildTables(b200sv_ctx* c)
             const double ob = sqrt((B.x - B.tx) * (B.x - B.tx) + (B.y - B.ty) * (B.y - B.ty) + (B.z - B.tz) * (B.z - B.tz));
             const double dmax = A.tr + B.tr + oa + ob + 1e-3;
             const int quirk_free = dmax * dmax < (A.r + B.r) - 1e-3 ? 1 : 0;
+            // A body of several shapes is culled as a whole by the reference (any shape's bounding sphere near => all its
+            // spheres tested, :455-507) and shape by shape here.  Where the cull provably passes whenever the clusters are
+            // close enough to matter the two coincide; where it does not, refuse rather than differ.
+            if (!quirk_free && !m.body_id.empty())
+            {
+              auto multi = [&](int e) {
+                if (m.body_id[e] < 0)
+                  return false;
+                int cnt = 0;
+                for (int k = 0; k < m.n_glinks; ++k)
+                  cnt += m.body_id[k] == m.body_id[e];
+                return cnt > 1;
+              };
+              if (multi(i) || multi(j))
+                return fail(c, B200SV_ERR_UNSUPPORTED,
+                            "an attached body of several shapes meets bounding spheres large enough for the reference's "
+                            "squared-distance cull (collision_distance_field_types.cpp:416-417) to reject spheres in reach: "
+                            "the reference culls such a body as a whole, this library shape by shape, and the answers could "
+                            "differ -- attach the body as one shape or with smaller bounding spheres");
+            }
             pairs.push_back(PairRec{ ca, cb, quirk_free, 0 });
           }
       G.p1 = (int)pairs.size();
@@ -1864,6 +1884,8 @@ int b200sv_create(int device, const b200sv_robot* robot, const b200sv_collision_
   }
   m.sphere_xyzr.assign(model->sphere_xyzr, model->sphere_xyzr + 4 * (size_t)ns);
   m.bounding_sphere.assign(model->bounding_sphere, model->bounding_sphere + 4 * (size_t)n);
+  if (model->body_id)
+    m.body_id.assign(model->body_id, model->body_id + n);
   c->cfg = *field;
   return finishCreate(c, device, out);
 }

@@ -39,6 +39,7 @@ struct HostCollisionModel
   std::vector<int32_t> sphere_start;   // n_glinks+1
   std::vector<double> sphere_xyzr;     // n_spheres*4
   std::vector<double> bounding_sphere; // n_glinks*4
+  std::vector<int32_t> body_id;        // n_glinks or empty: -1 for links, shapes of one attached body share an id
 };
 
 // RobotState::updateLinkTransformsInternal in double (robot_state.cpp:793-848): all links, link-index order.

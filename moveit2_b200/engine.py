@@ -108,6 +108,7 @@ class StateValidityEngine:
         m.sphere_start = _ip(arr(model, "sphere_start", np.int32))
         m.sphere_xyzr = _dp(arr(model, "sphere_xyzr", np.float64))
         m.bounding_sphere = _dp(arr(model, "bounding_sphere", np.float64))
+        m.body_id = _ip(arr(model, "body_id", np.int32)) if model.get("body_id") is not None else None
         cfg = field_cfg(size, origin, resolution, max_distance, tolerance)
         h = C.c_void_p()
         rc = L.b200sv_create(int(device), C.byref(r), C.byref(m), C.byref(cfg), C.byref(h))

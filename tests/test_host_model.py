@@ -173,3 +173,45 @@ def test_header_is_plain_c_and_links(resources, tmp_path):
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "c abi ok" in out.stdout and "no CPU fallback" in out.stdout
+
+
+def test_multi_shape_attached_bodies_are_proved_equivalent_or_refused():
+    """The reference culls a multi-shape attached body as a whole (any shape's bounding sphere near => all its spheres are
+    tested, collision_env_distance_field.cpp:455-507); the library culls shape by shape.  With body ids in the model the
+    library proves the two coincide (the cull provably passes whenever spheres are in reach) -- the ordinary case -- and
+    refuses a model where the reference's squared-distance-vs-radius-sum quirk could make them differ (bounding radii of a
+    metre), instead of silently answering differently.  Host-only context: no GPU needed."""
+    import moveit2_b200 as mb
+    from oracle.collision_model import OracleEnv
+    from oracle.robot_model import RobotModel
+    res = os.path.join(ROOT, "moveit2_b200", "resources")
+    with open(os.path.join(res, "panda_spheres.urdf")) as f:
+        urdf = f.read()
+    with open(os.path.join(res, "panda.srdf")) as f:
+        srdf = f.read()
+
+    def build(length):
+        # a rod of two shapes, each `length` long: bounding radius length / 2, spheres out to its ends
+        env = OracleEnv(RobotModel(urdf, srdf), "panda_arm", (1, 1, 1), (0, 0, 0.5), 0.02, 0.25)
+        step = length / 6.0
+        rod = [((0.0, 0.0, 0.20 + step * (k + 0.5)), 0.025) for k in range(12)]
+        bodies = [dict(link="panda_hand", name="rod", spheres=rod[:6], bs_center=(0, 0, 0.20 + 0.5 * length),
+                       bs_radius=0.5 * length, touch_links={"panda_hand"}),
+                  dict(link="panda_hand", name="rod", spheres=rod[6:], bs_center=(0, 0, 0.20 + 1.5 * length),
+                       bs_radius=0.5 * length, touch_links={"panda_hand"})]
+        env.attach_bodies(bodies)
+        robot, model = env.flat_arrays()
+        n0 = len(env.group.updated_links)
+        model["body_id"] = np.array([-1] * n0 + [0, 0], np.int32)
+        return robot, model
+
+    robot, model = build(0.3)                      # ordinary: proved equivalent, the context is created
+    eng = mb.StateValidityEngine.from_arrays(robot, model, (1, 1, 1), (0, 0, 0.5), 0.02, 0.25, device=mb.DEVICE_NONE)
+    assert eng.n_glinks == len(model["glink_index"])
+    eng.close()
+    robot, model = build(2.0)                      # bounding radii of a metre: the quirk can cull spheres in reach
+    with pytest.raises(mb.B200svError) as e:
+        mb.StateValidityEngine.from_arrays(robot, model, (1, 1, 1), (0, 0, 0.5), 0.02, 0.25, device=mb.DEVICE_NONE)
+    assert e.value.code == -3 and "as a whole" in str(e.value)
+    model.pop("body_id")                           # without body ids every entry is a body of its own: accepted, unchecked
+    mb.StateValidityEngine.from_arrays(robot, model, (1, 1, 1), (0, 0, 0.5), 0.02, 0.25, device=mb.DEVICE_NONE).close()
