@@ -266,7 +266,14 @@ __device__ __host__ inline int queueBytes(int n_group_vars, bool wide)
 // The staged states of the other instances: two buffers of one tile each (32 * V doubles), filled by 1-D bulk copies
 // (cp.async.bulk, the TMA engine) that complete on the two mbarriers behind them.
 __device__ __host__ inline int stageOneBytes(int n_group_vars) { return (32 * n_group_vars * 8 + 15) & ~15; }
-__device__ __host__ inline int stageBytes(int n_group_vars, bool wide) { return wide ? 0 : 2 * stageOneBytes(n_group_vars) + 16; }
+// Small groups (an arm) double-buffer: the next tile arrives while the current one is worked on.  Larger groups come with
+// robots whose parked cluster centres already take 20 KB of shared memory per warp and run at 7-8 warps per SM: they keep
+// ONE stage buffer, refilled after the FK phase has read the tile's last joint value (the copy overlaps the pair phase).
+__device__ __host__ inline int stageCount(int n_group_vars) { return n_group_vars <= 8 ? 2 : 1; }
+__device__ __host__ inline int stageBytes(int n_group_vars, bool wide)
+{
+  return wide ? 0 : stageCount(n_group_vars) * stageOneBytes(n_group_vars) + 16;
+}
 
 constexpr int kQcCap = 512;   // hierarchical cull: (state, cluster pair) candidates of one batch of link-pair survivors
 
@@ -430,7 +437,8 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   // buffers behind it that the TMA engine fills one tile ahead
   uint8_t* stage_base = reinterpret_cast<uint8_t*>(queue) + queueBytes(h.n_group_vars, kWide);
   const int stage_one = stageOneBytes(h.n_group_vars);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + 2 * stage_one);  // [2], non-wide only
+  constexpr bool kDouble = kV > 0 && kV <= kSmallVars;  // = stageCount(V) == 2 for the groups this instance takes
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(stage_base + (kDouble ? 2 : 1) * stage_one);  // [2], non-wide only
   unsigned* words = reinterpret_cast<unsigned*>(stage_base + stageBytes(h.n_group_vars, kWide));  // [0] hit, [1] amb
   uint32_t* q0 = words + 4;        // hierarchical cull only: (state, link pair) survivors of level 0
   uint32_t* qc = q0 + kQueueCap;   //                         (state, cluster pair) candidates
@@ -489,12 +497,12 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   unsigned it = 0;  // tiles this warp has started: buffer = it & 1, barrier parity = (it >> 1) & 1
   for (unsigned long long tile = tile0; tile < n_tiles; tile += tile_step, ++it)
   {
-    const int buf = kWide ? 0 : static_cast<int>(it & 1u);
+    const int buf = kDouble ? static_cast<int>(it & 1u) : 0;
     double* stage = reinterpret_cast<double*>(kWide ? reinterpret_cast<uint8_t*>(queue) : stage_base + buf * stage_one);
-    if (tile + tile_step < n_tiles)
+    if ((kDouble || kWide) && tile + tile_step < n_tiles)
       fetchTile(tile + tile_step, buf ^ 1);  // the other buffer's last reader was the previous tile (done: __syncwarp below)
     if (!kWide && tileByTma(tile))
-      mbarWait(mbar + buf, (it >> 1) & 1u);
+      mbarWait(mbar + buf, kDouble ? (it >> 1) & 1u : it & 1u);
     else
     {
       const double* __restrict__ src = a.q + tile * 32 * V;
@@ -648,6 +656,12 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
       hacc |= Cmp<FT>::hit(pv[u], pt[u]);
     if (slot_a >= 0)
       resolveSlot();
+    if constexpr (!kDouble && !kWide)
+    {  // single stage buffer: every lane has read its last joint value; the next tile's copy runs under the pair phase
+      __syncwarp();
+      if (tile + tile_step < n_tiles)
+        fetchTile(tile + tile_step, 0);
+    }
     bool hit = hacc != 0u, amb = aacc != 0u;
     // ---- intra-group sphere pairs ---------------------------------------------------------------------------------------
     if (do_intra && h.n_pairs > 0 && __any_sync(kFull, active && !hit))
