@@ -93,16 +93,16 @@ typedef struct b200sv_collision_model
   const int32_t* sphere_start;  /* [n_glinks+1] range of each link's collision spheres; empty range = no geometry */
   const double* sphere_xyzr;    /* [n_spheres*4] CollisionSphere::relative_vec_ (link frame) and radius_ */
   const double* bounding_sphere; /* [n_glinks*4] BodyDecomposition::getRelativeBoundingSphere() centre, radius */
-  const int32_t* body_id;       /* [n_glinks] or NULL.  -1 for links; the entries (shapes) of ONE attached body share an id.
-                                   The reference culls a (link, body) or (body, body) pair as a whole: if ANY shape's bounding
-                                   sphere passes doBoundingSpheresIntersect, ALL of the body's spheres are tested
-                                   (collision_env_distance_field.cpp:455-507); this library culls shape by shape.  The two
-                                   differ only where the reference's squared-distance-vs-radius-sum test (types.cpp:416-417)
-                                   can reject spheres that are close enough to collide, i.e. bounding radii summing to
-                                   about a metre or more.  With body_id given, b200sv_create PROVES for every pair that
-                                   involves a multi-shape body that this cannot happen and otherwise refuses the model
-                                   (B200SV_ERR_UNSUPPORTED) instead of answering differently from the reference.  NULL:
-                                   every attached entry is treated as a body of its own, unchecked. */
+  const int32_t* body_id;       /* [n_glinks] or NULL.  -1 for links; the entries (shapes) of ONE attached body share an id
+                                   and must ride on one link.  The reference culls a (link, body) or (body, body) pair as a
+                                   whole: if ANY shape's bounding sphere passes doBoundingSpheresIntersect, ALL of the
+                                   body's spheres are tested (collision_env_distance_field.cpp:455-507).  The entries here
+                                   are per shape, so with body_id given every pair that involves a several-shape body is
+                                   either PROVED to pass that test whenever its spheres are in reach (the ordinary case:
+                                   the squared-distance-vs-radius-sum test of types.cpp:416-417 only rejects near spheres
+                                   when bounding radii sum to about a metre) or carries the other shapes' bounding spheres
+                                   and evaluates the any-shape rule as the reference does.  NULL: every attached entry is
+                                   a body of its own. */
 } b200sv_collision_model;
 
 /* Constructor arguments of CollisionEnvDistanceField (collision_env_distance_field.hpp:49-84): the world and the

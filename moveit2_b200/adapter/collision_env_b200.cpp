@@ -325,7 +325,7 @@ CollisionEnvB200::createContext(const moveit::core::JointModelGroup* jmg, const 
   m.sphere_start = fm.sphere_start.data();
   m.sphere_xyzr = fm.sphere_xyzr.data();
   m.bounding_sphere = fm.bounding_sphere.data();
-  m.body_id = fm.body_id.data();  // multi-shape bodies: the library proves its per-shape cull equals the reference's or refuses
+  m.body_id = fm.body_id.data();  // multi-shape bodies are culled as a whole, as the reference does (:455-507)
 
   const b200sv_field_cfg f = fieldCfg(size_, origin_, resolution_, max_propogation_distance_, collision_tolerance_,
                                       use_signed_distance_field_);

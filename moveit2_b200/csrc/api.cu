@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -159,7 +160,7 @@ struct b200sv_ctx
   DevBuf<double> d_g_dist, d_g_grad, d_g_closest, d_g_centers;
   DevBuf<uint8_t> d_g_types, d_g_self;
   // contacts
-  DevBuf<int32_t> d_c_start, d_c_slot, d_c_count;
+  DevBuf<int32_t> d_c_start, d_c_slot, d_c_count, d_c_body;
   DevBuf<double> d_c_bs;
   DevBuf<uint8_t> d_c_intra, d_c_coll;
   DevBuf<b200sv_contact_rec> d_c_out;
@@ -274,8 +275,8 @@ int sphereThreshold(double radius, double res, double max_prop, double tol, int 
 template <typename R>
 void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, const std::vector<VarRec>& vars,
                const std::vector<SphereRec<double>>& spheres, const std::vector<BsRec<double>>& bs,
-               const std::vector<PairRec>& pairs, const std::vector<GroupRec>& groups, double margin, double pair_eps,
-               double bs_eps, double tight_eps, std::vector<uint8_t>& out)
+               const std::vector<PairRec>& pairs, const std::vector<GroupRec>& groups, const std::vector<AltRec>& alts,
+               double margin, double pair_eps, double bs_eps, double tight_eps, std::vector<uint8_t>& out)
 {
   ModelHeader<R> h{};
   h.n_links = (int)links.size();
@@ -299,6 +300,9 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
   off = align16(off + (int)(pairs.size() * sizeof(PairRec)));
   h.off_groups = off;
   off = align16(off + (int)(groups.size() * sizeof(GroupRec)));
+  h.off_alts = off;
+  h.n_alts = (int)alts.size();
+  off = align16(off + (int)(alts.size() * sizeof(AltRec)));
   h.total_bytes = off;
   h.state_stride = sizeof(R) == 4 ? c.state_stride_f : c.state_stride_d;
   h.link_stride = kLinkStrideWords;
@@ -361,6 +365,8 @@ void buildBlob(const b200sv_ctx& c, const std::vector<LinkRec<double>>& links, c
     memcpy(out.data() + h.off_pairs, pairs.data(), pairs.size() * sizeof(PairRec));
   if (!groups.empty())
     memcpy(out.data() + h.off_groups, groups.data(), groups.size() * sizeof(GroupRec));
+  if (!alts.empty())
+    memcpy(out.data() + h.off_alts, alts.data(), alts.size() * sizeof(AltRec));
 }
 
 // Smallest IEEE half >= x (x > 0), as bits; +inf when x exceeds the half range.
@@ -394,8 +400,8 @@ unsigned halfBitsUp(double x)
 // generic blobs are built from.  All constants are evaluated in double and narrowed once.
 bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, const std::vector<VarRec>& vars,
                    const std::vector<SphereRec<double>>& spheres_in, int n_spheres, const std::vector<BsRec<double>>& bs_in,
-                   const std::vector<PairRec>& pairs, const std::vector<GroupRec>& groups, double margin, double pair_eps,
-                   double bs_eps, double tight_eps)
+                   const std::vector<PairRec>& pairs, const std::vector<GroupRec>& groups, const std::vector<AltRec>& alts,
+                   double margin, double pair_eps, double bs_eps, double tight_eps)
 {
   c.blob_fast.clear();
   c.fast_wide = (int)c.robot.group_var_index.size() > fastCheckRegisterPrefetchVars();
@@ -837,15 +843,28 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     P.quirk = -1;
     if (!pairs[p].quirk_free)
     {
-      fast::Quirk Q{};
-      Q.ax = (float)A.x; Q.ay = (float)A.y; Q.az = (float)A.z;
-      Q.bx = (float)B.x; Q.by = (float)B.y; Q.bz = (float)B.z;
-      Q.lim_v2 = (float)((A.r + B.r) * oo * oo);
-      Q.eps_v2 = (float)(bs_eps * oo * oo);
-      Q.a_off = offA;
-      Q.b_off = offB;
-      P.quirk = (int)fq.size();
-      fq.push_back(Q);
+      auto record = [&](const BsRec<double>& U, const BsRec<double>& V, int next) {
+        fast::Quirk Q{};
+        Q.ax = (float)U.x; Q.ay = (float)U.y; Q.az = (float)U.z;
+        Q.bx = (float)V.x; Q.by = (float)V.y; Q.bz = (float)V.z;
+        Q.lim_v2 = (float)((U.r + V.r) * oo * oo);
+        Q.eps_v2 = (float)(bs_eps * oo * oo);
+        Q.a_off = offA;
+        Q.b_off = offB;
+        Q.next = next;
+        fq.push_back(Q);
+        return (int)fq.size() - 1;
+      };
+      // the pair's own bounding spheres head the chain; the other shapes of a several-shape body follow.  All shapes of a
+      // body ride on one link (checked in buildTables), so the records of a chain share the pair's two transforms.
+      int next = -1;
+      for (int alt = pairs[p].alt0; alt >= 0; alt = alts[alt].next)
+      {
+        if (store_off[tslot(bs[alts[alt].a].slot)] != offA || store_off[tslot(bs[alts[alt].b].slot)] != offB)
+          return false;
+        next = record(bs[alts[alt].a], bs[alts[alt].b], next);
+      }
+      P.quirk = record(A, B, next);
     }
     fp[q] = P;
     if (hier)
@@ -1303,6 +1322,25 @@ int buildTables(b200sv_ctx* c)
       s0 = s1;
     }
   }
+  // Shapes of one attached body (entries that share a body_id): the reference culls such a body as a whole.
+  std::vector<std::vector<int>> shapes_of(m.n_glinks);
+  for (int i = 0; i < m.n_glinks; ++i)
+  {
+    if (clusters_of_glink[i].empty())
+      continue;
+    shapes_of[i].push_back(i);
+    if (m.body_id.empty() || m.body_id[i] < 0)
+      continue;
+    for (int k = 0; k < m.n_glinks; ++k)
+      if (k != i && m.body_id[k] == m.body_id[i] && !clusters_of_glink[k].empty())
+      {
+        if (m.glink_index[k] != m.glink_index[i])
+          return fail(c, B200SV_ERR_INVALID, "entries that share a body_id must be attached to the same link");
+        shapes_of[i].push_back(k);
+      }
+  }
+  std::vector<AltRec> alts;
+  std::map<std::pair<int, int>, int> alt_chain_of;  // (glink i, glink j) -> head of its AltRec chain
   // cluster pairs of every enabled link pair, grouped by the first cluster
   std::vector<PairRec> pairs;
   std::vector<GroupRec> groups;
@@ -1332,27 +1370,28 @@ int buildTables(b200sv_ctx* c)
             const double ob = sqrt((B.x - B.tx) * (B.x - B.tx) + (B.y - B.ty) * (B.y - B.ty) + (B.z - B.tz) * (B.z - B.tz));
             const double dmax = A.tr + B.tr + oa + ob + 1e-3;
             const int quirk_free = dmax * dmax < (A.r + B.r) - 1e-3 ? 1 : 0;
-            // A body of several shapes is culled as a whole by the reference (any shape's bounding sphere near => all its
-            // spheres tested, :455-507) and shape by shape here.  Where the cull provably passes whenever the clusters are
-            // close enough to matter the two coincide; where it does not, refuse rather than differ.
-            if (!quirk_free && !m.body_id.empty())
+            // A body of several shapes is culled as a whole by the reference: any (shape, shape) combination whose
+            // bounding spheres pass lets ALL the body's spheres be tested (:455-507).  The entries here are per shape,
+            // so a pair the proof above does not cover carries the other combinations as a chain.
+            int alt0 = -1;
+            if (!quirk_free && (shapes_of[i].size() > 1 || shapes_of[j].size() > 1))
             {
-              auto multi = [&](int e) {
-                if (m.body_id[e] < 0)
-                  return false;
-                int cnt = 0;
-                for (int k = 0; k < m.n_glinks; ++k)
-                  cnt += m.body_id[k] == m.body_id[e];
-                return cnt > 1;
-              };
-              if (multi(i) || multi(j))
-                return fail(c, B200SV_ERR_UNSUPPORTED,
-                            "an attached body of several shapes meets bounding spheres large enough for the reference's "
-                            "squared-distance cull (collision_distance_field_types.cpp:416-417) to reject spheres in reach: "
-                            "the reference culls such a body as a whole, this library shape by shape, and the answers could "
-                            "differ -- attach the body as one shape or with smaller bounding spheres");
+              auto it = alt_chain_of.find({ i, j });
+              if (it == alt_chain_of.end())
+              {
+                int head = -1;
+                for (int u : shapes_of[i])
+                  for (int v : shapes_of[j])
+                    if (u != i || v != j)
+                    {
+                      alts.push_back(AltRec{ clusters_of_glink[u][0], clusters_of_glink[v][0], head, 0 });
+                      head = (int)alts.size() - 1;
+                    }
+                it = alt_chain_of.emplace(std::make_pair(i, j), head).first;
+              }
+              alt0 = it->second;
             }
-            pairs.push_back(PairRec{ ca, cb, quirk_free, 0 });
+            pairs.push_back(PairRec{ ca, cb, quirk_free, alt0 });
           }
       G.p1 = (int)pairs.size();
       if (G.p1 > G.p0)
@@ -1395,9 +1434,10 @@ int buildTables(b200sv_ctx* c)
   const double pair_eps = 2.0 * eps + 1e-7;
   const double bs_eps = 4.0 * eps * (sqrt(max_rs) + 0.05) + 1e-7;
   const double tight_eps = 4.0 * eps + 1e-6;
-  buildBlob<float>(*c, links, vars, spheres, bs, pairs, groups, margin, pair_eps, bs_eps, tight_eps, c->blob_f);
-  buildBlob<double>(*c, links, vars, spheres, bs, pairs, groups, 0.0, 0.0, 0.0, 1e-9, c->blob_d);
-  c->fast_ok = buildFastBlob(*c, links, vars, spheres, c->n_spheres, bs, pairs, groups, margin, pair_eps, bs_eps, tight_eps);
+  buildBlob<float>(*c, links, vars, spheres, bs, pairs, groups, alts, margin, pair_eps, bs_eps, tight_eps, c->blob_f);
+  buildBlob<double>(*c, links, vars, spheres, bs, pairs, groups, alts, 0.0, 0.0, 0.0, 1e-9, c->blob_d);
+  c->fast_ok =
+      buildFastBlob(*c, links, vars, spheres, c->n_spheres, bs, pairs, groups, alts, margin, pair_eps, bs_eps, tight_eps);
   return B200SV_OK;
 }
 
@@ -1967,7 +2007,7 @@ void b200sv_destroy(b200sv_ctx* c)
     if (lf.d2) cudaFree(lf.d2);
   if (c->d_lf) cudaFree(c->d_lf);
   c->d_lf_enabled.release();
-  c->d_c_start.release(); c->d_c_slot.release(); c->d_c_count.release(); c->d_c_bs.release(); c->d_c_intra.release();
+  c->d_c_start.release(); c->d_c_slot.release(); c->d_c_count.release(); c->d_c_bs.release(); c->d_c_intra.release(); c->d_c_body.release();
   c->d_c_coll.release(); c->d_c_out.release();
   if (c->d_link_slot) cudaFree(c->d_link_slot);
   if (c->d_const_T) cudaFree(c->d_const_T);
@@ -3229,6 +3269,11 @@ int b200sv_check_contacts(b200sv_ctx* c, const double* q, size_t n, uint32_t fla
   CU(c, cudaMemcpyAsync(c->d_c_start.p, c->cm.sphere_start.data(), (L + 1) * 4, cudaMemcpyHostToDevice, s));
   CU(c, cudaMemcpyAsync(c->d_c_slot.p, slot.data(), L * 4, cudaMemcpyHostToDevice, s));
   CU(c, cudaMemcpyAsync(c->d_c_bs.p, c->cm.bounding_sphere.data(), L * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  std::vector<int32_t> body(L, -1);
+  if (!c->cm.body_id.empty())
+    body.assign(c->cm.body_id.begin(), c->cm.body_id.end());
+  CU(c, c->d_c_body.ensure(L));
+  CU(c, cudaMemcpyAsync(c->d_c_body.p, body.data(), L * 4, cudaMemcpyHostToDevice, s));
   CU(c, cudaMemcpyAsync(c->d_g_self.p, c->cm.self_enabled.data(), L, cudaMemcpyHostToDevice, s));
   CU(c, cudaMemcpyAsync(c->d_c_intra.p, c->cm.intra_enabled.data(), L * L, cudaMemcpyHostToDevice, s));
   CU(c, cudaMemsetAsync(c->d_c_out.p, 0xff, n * max_contacts * sizeof(b200sv_contact_rec), s));
@@ -3246,6 +3291,7 @@ int b200sv_check_contacts(b200sv_ctx* c, const double* q, size_t n, uint32_t fla
   a.sphere_start = c->d_c_start.p;
   a.glink_slot = c->d_c_slot.p;
   a.glink_bs = c->d_c_bs.p;
+  a.body_id = c->d_c_body.p;
   a.self_enabled = c->d_g_self.p;
   a.intra = c->d_c_intra.p;
   a.centers = c->d_g_centers.p;

@@ -64,6 +64,7 @@ struct Smem
   const BsRec<R>* bs;
   const PairRec* pairs;
   const GroupRec* groups;
+  const AltRec* alts;
 };
 
 __device__ __forceinline__ void sincosR(float x, float* s, float* c) { sincosf(x, s, c); }
@@ -309,6 +310,7 @@ __device__ __forceinline__ Smem<R> loadModel(const uint8_t* __restrict__ g_model
   m.bs = reinterpret_cast<const BsRec<R>*>(smem + m.h->off_bs);
   m.pairs = reinterpret_cast<const PairRec*>(smem + m.h->off_pairs);
   m.groups = reinterpret_cast<const GroupRec*>(smem + m.h->off_groups);
+  m.alts = reinterpret_cast<const AltRec*>(smem + m.h->off_alts);
   return m;
 }
 
@@ -428,7 +430,7 @@ __device__ __forceinline__ void sphereChunk(const Smem<R>& m, const R* T, int k0
 // of cluster a, Ta: its link transform (both shared by the whole group of pairs).
 template <typename R>
 __device__ __forceinline__ void pairCull(const Smem<R>& m, const R* T, const BsRec<R>& A, const R* Ta, R ax, R ay, R az,
-                                         const BsRec<R>& B, bool quirk_free, bool& live, bool& certain)
+                                         const BsRec<R>& B, const PairRec& pr, bool& live, bool& certain)
 {
   constexpr bool kExact = sizeof(R) == 8;
   const ModelHeader<R>& h = *m.h;
@@ -443,25 +445,41 @@ __device__ __forceinline__ void pairCull(const Smem<R>& m, const R* T, const BsR
   live = certain = false;
   if ((fx * fx + fy * fy + fz * fz) < rt * rt)
   {
-    if (quirk_free)
+    if (pr.quirk_free)
     {  // the host proved: whenever these two tight spheres are this close, the reference's cull below passes
       live = certain = true;
       return;
     }
     // doBoundingSpheresIntersect (types.cpp:408-418) on the LINKS' bounding spheres, quirk kept: SQUARED centre
     // distance against the plain radius sum
-    R px, py, pz, qx, qy, qz;
-    posePoint<R>(Ta, A.x, A.y, A.z, px, py, pz);
-    posePoint<R>(Tb, B.x, B.y, B.z, qx, qy, qz);
-    const R ex = px - qx, ey = py - qy, ez = pz - qz;
-    const R d2 = ex * ex + ey * ey + ez * ez;
-    const R rs = A.r + B.r;
-    if (kExact)
-      live = certain = d2 < rs;
-    else
+    auto boundsMeet = [&](const R* Tp, const BsRec<R>& P, const R* Tq, const BsRec<R>& Q) {
+      R px, py, pz, qx, qy, qz;
+      posePoint<R>(Tp, P.x, P.y, P.z, px, py, pz);
+      posePoint<R>(Tq, Q.x, Q.y, Q.z, qx, qy, qz);
+      const R ex = px - qx, ey = py - qy, ez = pz - qz;
+      const R d2 = ex * ex + ey * ey + ez * ez;
+      const R rs = P.r + Q.r;
+      if (kExact)
+      {
+        live |= d2 < rs;
+        certain |= d2 < rs;
+      }
+      else
+      {
+        live |= d2 < rs + h.bs_eps;
+        certain |= d2 < rs - h.bs_eps;
+      }
+    };
+    boundsMeet(Ta, A, Tb, B);
+    // a body of several shapes: any (shape, shape) combination passing lets the whole body through
+    // (collision_env_distance_field.cpp:455-507); rare, and only reached by tight spheres that are already near
+    for (int alt = pr.alt0; alt >= 0 && !certain; alt = m.alts[alt].next)
     {
-      live = d2 < rs + h.bs_eps;
-      certain = d2 < rs - h.bs_eps;
+      const BsRec<R>&P = m.bs[m.alts[alt].a], &Q = m.bs[m.alts[alt].b];
+      R Tp[12], Tq[12];
+      load12(T + P.slot * kLinkStrideWords, Tp);
+      load12(T + Q.slot * kLinkStrideWords, Tq);
+      boundsMeet(Tp, P, Tq, Q);
     }
   }
 }
@@ -632,7 +650,7 @@ __global__ void __launch_bounds__(512, 1) checkKernel(CheckArgs<FT> a)
           if (mine)
           {
             const PairRec pr = m.pairs[p];
-            pairCull<R>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr.quirk_free != 0, live, certain);
+            pairCull<R>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr, live, certain);
           }
           const unsigned mk = __ballot_sync(kFull, live);
           if (live)
@@ -1068,20 +1086,34 @@ __global__ void __launch_bounds__(128) contactKernel(ContactArgs a)
     {
       if (a.sphere_start[i + 1] <= a.sphere_start[i])
         continue;
-      double ci[3];
-      posePoint<double>(T + a.glink_slot[i] * kLinkStrideWords, a.glink_bs[4 * i], a.glink_bs[4 * i + 1], a.glink_bs[4 * i + 2], ci[0],
-                        ci[1], ci[2]);
       for (int j = i + 1; j < L && !done; ++j)
       {
         if (a.sphere_start[j + 1] <= a.sphere_start[j] || !a.intra[static_cast<size_t>(i) * L + j])
           continue;
-        double cj[3];
-        posePoint<double>(T + a.glink_slot[j] * kLinkStrideWords, a.glink_bs[4 * j], a.glink_bs[4 * j + 1], a.glink_bs[4 * j + 2],
-                          cj[0], cj[1], cj[2]);
-        const double ex = ci[0] - cj[0], ey = ci[1] - cj[1], ez = ci[2] - cj[2];
         // doBoundingSpheresIntersect, quirk kept: squared centre distance against the plain radius sum (types.cpp:416-417)
-        if (!(__dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)) <
-              (a.glink_bs[4 * i + 3] + a.glink_bs[4 * j + 3])))
+        auto boundsMeet = [&](int u, int v) {
+          double cu[3], cv[3];
+          posePoint<double>(T + a.glink_slot[u] * kLinkStrideWords, a.glink_bs[4 * u], a.glink_bs[4 * u + 1], a.glink_bs[4 * u + 2],
+                            cu[0], cu[1], cu[2]);
+          posePoint<double>(T + a.glink_slot[v] * kLinkStrideWords, a.glink_bs[4 * v], a.glink_bs[4 * v + 1], a.glink_bs[4 * v + 2],
+                            cv[0], cv[1], cv[2]);
+          const double ex = cu[0] - cv[0], ey = cu[1] - cv[1], ez = cu[2] - cv[2];
+          return __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)) <
+                 (a.glink_bs[4 * u + 3] + a.glink_bs[4 * v + 3]);
+        };
+        bool meet = boundsMeet(i, j);
+        // a body of several shapes passes as a whole when ANY of its shapes does (collision_env_distance_field.cpp:455-507)
+        const int bi = a.body_id[i], bj = a.body_id[j];
+        if (!meet && (bi >= 0 || bj >= 0))
+          for (int u = 0; u < L && !meet; ++u)
+          {
+            if ((u != i && (bi < 0 || a.body_id[u] != bi)) || a.sphere_start[u + 1] <= a.sphere_start[u])
+              continue;
+            for (int v = 0; v < L && !meet; ++v)
+              if ((v == j || (bj >= 0 && a.body_id[v] == bj)) && a.sphere_start[v + 1] > a.sphere_start[v])
+                meet = boundsMeet(u, v);
+          }
+        if (!meet)
           continue;
         int num_pair = 0;
         for (int k = a.sphere_start[i]; k < a.sphere_start[i + 1] && num_pair < static_cast<int>(a.max_per_pair) && !done; ++k)
@@ -1149,7 +1181,7 @@ __global__ void __launch_bounds__(128) recheckWarpKernel(CheckArgs<FT> a)
         load12(T + A.slot * kLinkStrideWords, Ta);
         posePoint<double>(Ta, A.tx, A.ty, A.tz, ax, ay, az);
         bool live = false, certain = false;
-        pairCull<double>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr.quirk_free != 0, live, certain);
+        pairCull<double>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr, live, certain);
         if (live)
           pairItem<double>(m, T, pr, certain, hit, amb);
       }
@@ -1206,7 +1238,7 @@ __global__ void __launch_bounds__(128) latencyCheckKernel(LatencyArgs<FT> a)
       load12(T + A.slot * kLinkStrideWords, Ta);
       posePoint<double>(Ta, A.tx, A.ty, A.tz, ax, ay, az);
       bool live = false, certain = false;
-      pairCull<double>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr.quirk_free != 0, live, certain);
+      pairCull<double>(m, T, A, Ta, ax, ay, az, m.bs[pr.b], pr, live, certain);
       if (live)
         pairItem<double>(m, T, pr, certain, hit, amb);
     }

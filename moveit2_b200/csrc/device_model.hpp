@@ -57,6 +57,16 @@ struct alignas(16) PairRec
 {
   int a, b;         // BsRec indices
   int quirk_free;   // 1: tight spheres this close imply the reference's link-level cull passes (proved on the host)
+  int alt0;         // -1, or the head of an AltRec chain: further bounding-sphere pairs any ONE of which passes the cull
+};
+
+// An attached body of several shapes is culled as a whole by the reference: ANY shape's bounding sphere passing
+// doBoundingSpheresIntersect lets ALL the body's spheres be tested (collision_env_distance_field.cpp:455-507).  The ABI
+// carries one entry per shape, so a pair that involves such a body chains the other (shape, shape) combinations here.
+struct alignas(16) AltRec
+{
+  int a, b;  // BsRec indices (any cluster of the entry: the link-level bounding sphere is the same for all of them)
+  int next;  // -1 ends the chain
   int pad;
 };
 
@@ -73,7 +83,7 @@ struct ModelHeader
   int off_links, off_vars, off_spheres, off_bs, off_pairs, total_bytes;
   int state_stride, link_stride;  // shared-memory strides (in R) of a state's / a link's transform
   int nx, ny, nz, n_groups;
-  int off_groups, n_spheres_padded, pad1, pad2;  // spheres are padded to a multiple of 4 with thr = 0 dummies
+  int off_groups, n_spheres_padded, off_alts, n_alts;  // spheres are padded to a multiple of 4 with thr = 0 dummies
   R om[3];      // VoxelGrid::origin_minus_
   R oo_res;     // VoxelGrid::oo_resolution_
   R margin;     // FP32 pass: voxel-coordinate uncertainty (cells); 0 in the FP64 pass
@@ -184,7 +194,9 @@ struct alignas(16) Quirk
 {
   float ax, ay, az, lim_v2;
   float bx, by, bz, eps_v2;
-  int a_off, b_off, pad0, pad1;
+  int a_off, b_off;
+  int next;  // -1, or the next record of an any-shape chain (AltRec above): the cull passes if ANY record of the chain does
+  int pad1;
 };
 
 struct alignas(16) Header

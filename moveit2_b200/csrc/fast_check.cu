@@ -210,15 +210,25 @@ __device__ __forceinline__ void pairItem(const FModel& m, const TStore<kGlobal>&
   bool cert = true;
   if (p1.y >= 0)
   {
-    const fast::Quirk Q = m.quirks[p1.y];
-    float ax, ay, az, bx, by, bz;
-    pose(Ta, Q.ax, Q.ay, Q.az, ax, ay, az);
-    pose(Tb, Q.bx, Q.by, Q.bz, bx, by, bz);
-    const float ex = ax - bx, ey = ay - by, ez = az - bz;
-    const float d2 = ex * ex + ey * ey + ez * ez;
-    if (!(d2 < Q.lim_v2 + Q.eps_v2))
+    // the cull passes if ANY record of the chain does: one record for a pair of links, one per (shape, shape)
+    // combination when an attached body of several shapes is involved (collision_env_distance_field.cpp:455-507; the
+    // shapes of a body ride on one link, so every record is posed with this pair's two transforms)
+    bool maybe = false;
+    cert = false;
+    for (int qi = p1.y; qi >= 0 && !cert; )
+    {
+      const fast::Quirk Q = m.quirks[qi];
+      float ax, ay, az, bx, by, bz;
+      pose(Ta, Q.ax, Q.ay, Q.az, ax, ay, az);
+      pose(Tb, Q.bx, Q.by, Q.bz, bx, by, bz);
+      const float ex = ax - bx, ey = ay - by, ez = az - bz;
+      const float d2 = ex * ex + ey * ey + ez * ez;
+      maybe |= d2 < Q.lim_v2 + Q.eps_v2;
+      cert = d2 < Q.lim_v2 - Q.eps_v2;
+      qi = Q.next;
+    }
+    if (!maybe)
       return;
-    cert = d2 < Q.lim_v2 - Q.eps_v2;
   }
   float bx[kC], by[kC], bz[kC], br[kC];
 #pragma unroll

@@ -132,6 +132,7 @@ struct ContactArgs
   const int32_t* sphere_start;   // [n_glinks + 1]
   const int32_t* glink_slot;     // [n_glinks] device-link slot
   const double* glink_bs;        // [n_glinks * 4] link-frame bounding sphere
+  const int32_t* body_id;        // [n_glinks] -1 for links, shapes of one attached body share an id
   const uint8_t* self_enabled;   // [n_glinks]
   const uint8_t* intra;          // [n_glinks * n_glinks]
   double* centers;               // [n * n_spheres * 3] scratch

@@ -42,7 +42,8 @@ class OrcCollisionModel(C.Structure):
                 ("sphere_rel", C.POINTER(C.c_double)), ("sphere_radius", C.POINTER(C.c_double)),
                 ("bs_center", C.POINTER(C.c_double)), ("bs_radius", C.POINTER(C.c_double)),
                 ("point_start", C.POINTER(C.c_int32)), ("point_rel", C.POINTER(C.c_double)),
-                ("max_propagation_distance", C.c_double), ("collision_tolerance", C.c_double)]
+                ("max_propagation_distance", C.c_double), ("collision_tolerance", C.c_double),
+                ("body_id", C.POINTER(C.c_int32))]
 
 
 def _p(a, t):
@@ -425,6 +426,10 @@ class OracleEnv:
         bs_c = list(a["bs_center"].reshape(-1, 3)[:n0])
         bs_r = list(a["bs_radius"][:n0])
         pt_start = list(a["point_start"])
+        # entries named alike are the shapes of ONE body: the reference keeps it as one entry whose bounding spheres are
+        # tested shape by shape and whose spheres pass as a whole (collision_env_distance_field.cpp:455-507)
+        body_names = [body["name"] for body in bodies]
+        a["body_id"] = np.array([-1] * n0 + [body_names.index(nm) for nm in body_names], np.int32)
         for b, body in enumerate(bodies):
             ip = names.index(body["link"])
             glink.append(gl[ip].index)
@@ -433,7 +438,8 @@ class OracleEnv:
             if acm.always(body["link"], body["name"]) or body["link"] in body.get("touch_links", ()):
                 intra[ip, n0 + b] = 0
             for b2 in range(b + 1, len(bodies)):
-                if acm.always(body["name"], bodies[b2]["name"]):
+                # shapes of one body are one entry in the reference: never tested against each other (i == j is skipped)
+                if bodies[b2]["name"] == body["name"] or acm.always(body["name"], bodies[b2]["name"]):
                     intra[n0 + b, n0 + b2] = 0
             for cxyz, rad in body["spheres"]:
                 sph_rel.append(np.asarray(cxyz, np.float64))
@@ -457,7 +463,7 @@ class OracleEnv:
                                     _p(a["sphere_start"], C.c_int32), _p(a["sphere_rel"], C.c_double),
                                     _p(a["sphere_radius"], C.c_double), _p(a["bs_center"], C.c_double),
                                     _p(a["bs_radius"], C.c_double), _p(a["point_start"], C.c_int32),
-                                    _p(a["point_rel"], C.c_double), self.max_prop, self.tol)
+                                    _p(a["point_rel"], C.c_double), self.max_prop, self.tol, _p(a["body_id"], C.c_int32))
 
     def flat_arrays(self):
         """(robot, model) dicts in the layout of b200sv_robot / b200sv_collision_model (include/b200sv.h)."""
@@ -475,6 +481,8 @@ class OracleEnv:
         model = dict(n_glinks=n, glink_index=a["glink_index"], self_enabled=a["self_enabled"].astype(np.uint8),
                      intra_enabled=a["intra_enabled"], sphere_start=a["sphere_start"], sphere_xyzr=xyzr,
                      bounding_sphere=bsph)
+        if "body_id" in a:
+            model["body_id"] = a["body_id"]
         return robot, model
 
     def compute_self_points(self):

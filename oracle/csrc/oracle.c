@@ -796,6 +796,8 @@ typedef struct
   const double* point_rel;
   double max_propagation_distance; /* max_propogation_distance_ */
   double collision_tolerance;      /* collision_tolerance_ */
+  const int32_t* body_id;          /* NULL, or [n_glinks]: -1 for links; the entries that are the SHAPES of one attached body
+                                      share an id (the reference keeps such a body as ONE entry of several decompositions) */
 } orc_collision_model;
 
 enum { ORC_CHECK_WORLD = 1, ORC_CHECK_SELF = 2, ORC_CHECK_INTRA = 4 };
@@ -809,6 +811,38 @@ static inline void transform_point(const double* T, const double* p, double* o)
     s += M(T, r, 2) * p[2];
     o[r] = s + M(T, r, 3);
   }
+}
+
+/* The link-level cull of getIntraGroupCollisions (collision_env_distance_field.cpp:452-507).  Two links: one
+ * doBoundingSpheresIntersect (types.cpp:408-418, reference quirk kept: SQUARED centre distance against the plain radius
+ * sum).  An attached body is tested shape by shape and passes AS A WHOLE as soon as any of its shapes' bounding spheres
+ * passes (:461-505: all_ok turns false on the first hit; every sphere of the body is then tested).  Entries here are per
+ * shape, so for an entry of a several-shape body the test runs over all entries with its body_id. */
+static int bounds_pass(const orc_collision_model* cm, const double* bs_centers, int i, int j)
+{
+  const double* ci = bs_centers + 3 * i;
+  const double* cj = bs_centers + 3 * j;
+  const double ex = ci[0] - cj[0], ey = ci[1] - cj[1], ez = ci[2] - cj[2];
+  return (ex * ex + ey * ey + ez * ez) < (cm->bs_radius[i] + cm->bs_radius[j]);
+}
+static int bounds_meet(const orc_collision_model* cm, const double* bs_centers, int i, int j)
+{
+  if (bounds_pass(cm, bs_centers, i, j))
+    return 1;
+  if (!cm->body_id)
+    return 0;
+  const int bi = cm->body_id[i], bj = cm->body_id[j];
+  if (bi < 0 && bj < 0)
+    return 0;
+  for (int u = 0; u < cm->n_glinks; ++u)
+  {
+    if (!(u == i || (bi >= 0 && cm->body_id[u] == bi)) || !cm->has_geometry[u])
+      continue;
+    for (int v = 0; v < cm->n_glinks; ++v)
+      if ((v == j || (bj >= 0 && cm->body_id[v] == bj)) && cm->has_geometry[v] && bounds_pass(cm, bs_centers, u, v))
+        return 1;
+  }
+  return 0;
 }
 
 /* getCollisionSphereCollision (bool overload): collision_distance_field_types.cpp:211-236 */
@@ -907,12 +941,7 @@ static int check_state(const orc_robot* r, const orc_collision_model* cm, const 
           continue;
         if (!cm->intra_enabled[(size_t)i * L + j])
           continue;
-        const double* ci = s->bs_centers + 3 * i;
-        const double* cj = s->bs_centers + 3 * j;
-        const double ex = ci[0] - cj[0], ey = ci[1] - cj[1], ez = ci[2] - cj[2];
-        const double d2 = ex * ex + ey * ey + ez * ez;
-        /* reference quirk: SQUARED centre distance against the plain radius sum (types.cpp:416-417) */
-        if (!(d2 < (cm->bs_radius[i] + cm->bs_radius[j])))
+        if (!bounds_meet(cm, s->bs_centers, i, j))
           continue;
         for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1]; ++k)
           for (int l = cm->sphere_start[j]; l < cm->sphere_start[j + 1]; ++l)
@@ -1048,10 +1077,7 @@ double orc_state_margin(const orc_robot* r, const orc_collision_model* cm, const
       {
         if (!cm->has_geometry[i] || !cm->has_geometry[j] || !cm->intra_enabled[(size_t)i * L + j])
           continue;
-        const double* ci = s.bs_centers + 3 * i;
-        const double* cj = s.bs_centers + 3 * j;
-        const double ex = ci[0] - cj[0], ey = ci[1] - cj[1], ez = ci[2] - cj[2];
-        if (!((ex * ex + ey * ey + ez * ez) < (cm->bs_radius[i] + cm->bs_radius[j])))
+        if (!bounds_meet(cm, s.bs_centers, i, j))
           continue;
         for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1]; ++k)
           for (int l = cm->sphere_start[j]; l < cm->sphere_start[j + 1]; ++l)
@@ -1338,10 +1364,7 @@ void orc_check_contacts(const orc_robot* r, const orc_collision_model* cm, const
           {
             if (!cm->has_geometry[i] || !cm->has_geometry[j] || !cm->intra_enabled[(size_t)i * L + j])
               continue;
-            const double* ci = s.bs_centers + 3 * i;
-            const double* cj = s.bs_centers + 3 * j;
-            const double ex = ci[0] - cj[0], ey = ci[1] - cj[1], ez = ci[2] - cj[2];
-            if (!((ex * ex + ey * ey + ez * ez) < (cm->bs_radius[i] + cm->bs_radius[j])))
+            if (!bounds_meet(cm, s.bs_centers, i, j))
               continue;
             int num_pair = 0; /* res.contacts has no entry for this pair yet: every state starts from an empty result */
             for (int k = cm->sphere_start[i]; k < cm->sphere_start[i + 1] && num_pair < (int)max_contacts_per_pair && !done; ++k)

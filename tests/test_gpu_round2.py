@@ -524,3 +524,49 @@ def test_link_fields_built_on_the_device_are_the_exact_transform():
         seen += 1
     assert seen >= 8
     eng.close()
+
+
+# ---- an attached body of several shapes is culled as a whole (collision_env_distance_field.cpp:455-507) -------------------
+def _pole_env(with_body_ids):
+    """A 4 m pole held by the hand, modelled as two shapes of ONE body: the pole itself (bounding radius 2 m, its collision
+    spheres near the hand) and a small collar.  With bounding radii this large the reference's squared-distance-vs-radius-sum
+    cull (types.cpp:416-417) rejects the pole's own bounding sphere although its spheres touch a link -- but the collar's
+    passes, and then the reference tests ALL the body's spheres."""
+    env = OracleEnv(RobotModel(read(RES, "panda_spheres.urdf"), read(RES, "panda.srdf")), "panda_arm", (1, 1, 1), (0, 0, 0.5),
+                    0.02, 0.25)
+    touch = {"panda_hand", "panda_leftfinger", "panda_rightfinger"}
+    pole = [((0.0, 0.0, 0.25 + 0.05 * k), 0.025) for k in range(8)]
+    env.attach_bodies([dict(link="panda_hand", name="pole", spheres=pole, bs_center=(0, 0, 2.2), bs_radius=2.0, touch_links=touch),
+                       dict(link="panda_hand", name="pole", spheres=[((0, 0, 0.3), 0.025)], bs_center=(0, 0, 0.3),
+                            bs_radius=0.1, touch_links=touch)])
+    robot, model = env.flat_arrays()
+    if not with_body_ids:
+        env.cm.body_id = None   # every entry a body of its own: culled shape by shape
+        model.pop("body_id")
+    eng = mb.StateValidityEngine.from_arrays(robot, model, (1, 1, 1), (0, 0, 0.5), 0.02, 0.25)
+    return eng, env
+
+
+def test_a_body_of_several_shapes_is_culled_as_a_whole():
+    eng, env = _pole_env(True)
+    eng0, env0 = _pole_env(False)
+    lo, hi = env.joint_bounds()
+    q = workloads.random_states(77, 200_000, lo, hi)
+    I = mb.CHECK_INTRA
+    whole, _ = env.check(q, I)
+    by_shape, _ = env0.check(q, I)
+    # the two rules differ on this body, one-sidedly: the whole-body rule tests more spheres
+    assert ((whole != 0) & (by_shape == 0)).sum() > 500 and not ((whole == 0) & (by_shape != 0)).any()
+    for mode in (0, mb.CHECK_FP64):
+        assert np.array_equal(eng.check_batch(q, I | mode), whole == 0), mode
+        assert np.array_equal(eng0.check_batch(q, I | mode), by_shape == 0), mode
+    assert np.array_equal(eng.check_batch(q[:5], I), whole[:5] == 0)   # the single-launch latency path
+    differ = np.flatnonzero(whole != by_shape)[:64]
+    assert np.array_equal(eng.check_batch(q[differ][:8], I), whole[differ][:8] == 0)
+    col, cnt, _ = eng.check_contacts(q[differ], I, 4, 2)
+    rcol, rcnt, _ = env.check_contacts(q[differ], I, 4, 2)
+    assert np.array_equal(col, rcol) and np.array_equal(cnt, rcnt) and col.all()
+    ok = eng.check_motions(q[differ[:-1]], q[differ[1:]], 0.05, flags=I)[0]
+    eng.close()
+    eng0.close()
+    assert not ok.any()   # both end states of every edge collide

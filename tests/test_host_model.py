@@ -175,12 +175,13 @@ def test_header_is_plain_c_and_links(resources, tmp_path):
     assert "c abi ok" in out.stdout and "no CPU fallback" in out.stdout
 
 
-def test_multi_shape_attached_bodies_are_proved_equivalent_or_refused():
+def test_multi_shape_attached_bodies_carry_the_whole_body_cull():
     """The reference culls a multi-shape attached body as a whole (any shape's bounding sphere near => all its spheres are
-    tested, collision_env_distance_field.cpp:455-507); the library culls shape by shape.  With body ids in the model the
-    library proves the two coincide (the cull provably passes whenever spheres are in reach) -- the ordinary case -- and
-    refuses a model where the reference's squared-distance-vs-radius-sum quirk could make them differ (bounding radii of a
-    metre), instead of silently answering differently.  Host-only context: no GPU needed."""
+    tested, collision_env_distance_field.cpp:455-507); the ABI carries one entry per shape plus body ids.  Ordinary bodies:
+    the library proves per pair that the cull passes whenever spheres are in reach and needs nothing more; bounding radii of
+    a metre (where the reference's squared-distance-vs-radius-sum quirk can cull spheres in reach) get the other shapes'
+    bounding spheres chained to the pair (GPU parity: test_a_body_of_several_shapes_is_culled_as_a_whole).  Shapes of one
+    body must ride on one link.  Host-only contexts: no GPU needed."""
     import moveit2_b200 as mb
     from oracle.collision_model import OracleEnv
     from oracle.robot_model import RobotModel
@@ -202,16 +203,16 @@ def test_multi_shape_attached_bodies_are_proved_equivalent_or_refused():
         env.attach_bodies(bodies)
         robot, model = env.flat_arrays()
         n0 = len(env.group.updated_links)
-        model["body_id"] = np.array([-1] * n0 + [0, 0], np.int32)
+        assert list(model["body_id"]) == [-1] * n0 + [0, 0]
         return robot, model
 
-    robot, model = build(0.3)                      # ordinary: proved equivalent, the context is created
-    eng = mb.StateValidityEngine.from_arrays(robot, model, (1, 1, 1), (0, 0, 0.5), 0.02, 0.25, device=mb.DEVICE_NONE)
-    assert eng.n_glinks == len(model["glink_index"])
-    eng.close()
-    robot, model = build(2.0)                      # bounding radii of a metre: the quirk can cull spheres in reach
+    for length in (0.3, 2.0):
+        robot, model = build(length)
+        eng = mb.StateValidityEngine.from_arrays(robot, model, (1, 1, 1), (0, 0, 0.5), 0.02, 0.25, device=mb.DEVICE_NONE)
+        assert eng.n_glinks == len(model["glink_index"])
+        eng.close()
+    model["glink_index"] = model["glink_index"].copy()
+    model["glink_index"][-1] = model["glink_index"][-3]   # the second shape on another link than the first
     with pytest.raises(mb.B200svError) as e:
         mb.StateValidityEngine.from_arrays(robot, model, (1, 1, 1), (0, 0, 0.5), 0.02, 0.25, device=mb.DEVICE_NONE)
-    assert e.value.code == -3 and "as a whole" in str(e.value)
-    model.pop("body_id")                           # without body ids every entry is a body of its own: accepted, unchecked
-    mb.StateValidityEngine.from_arrays(robot, model, (1, 1, 1), (0, 0, 0.5), 0.02, 0.25, device=mb.DEVICE_NONE).close()
+    assert e.value.code == -1 and "same link" in str(e.value)
