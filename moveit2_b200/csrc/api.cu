@@ -30,6 +30,7 @@ struct Field
   uint16_t* d2 = nullptr;     // min(d^2, max_d2)
   uint16_t* nd2 = nullptr;    // signed fields only: negative_distance_square_ (distance to the nearest free voxel)
   void* compact = nullptr;    // this field's half of the interleaved compact field (base + which elements)
+  uint8_t* plane_busy = nullptr;  // [nx] nonzero: plane x of this field's compact elements may hold a non-free value
   bool dirty = false;         // occupancy changed inside a begin/end_update bracket: the EDT is owed
   bool deferred = false;      // inside b200sv_field_begin_update .. b200sv_field_end_update
 };
@@ -1588,8 +1589,10 @@ int allocFields(b200sv_ctx* c)
     CU(c, cudaMalloc(&F.occ, occ_bytes));
     CU(c, cudaMalloc(&F.d2, c->n_voxels * 2));
     F.compact = static_cast<uint8_t*>(c->d_combined) + (size_t)w * c->compact_bytes;
+    CU(c, cudaMalloc(&F.plane_busy, (size_t)g.nx * kPlaneBusyStride));
     CU(c, cudaMemsetAsync(F.occ, 0, occ_bytes, c->stream));
     CU(c, launchFillField(g, F.d2, F.compact, c->compact_bytes, c->stream));
+    CU(c, cudaMemsetAsync(F.plane_busy, 0, (size_t)g.nx * kPlaneBusyStride, c->stream));
     if (c->cfg.use_signed_distance_field)
     {  // reset(): negative_distance_square_ = 0 everywhere (propagation_distance_field.cpp:506-524)
       CU(c, cudaMalloc(&F.nd2, c->n_voxels * 2));
@@ -1603,7 +1606,10 @@ int allocFields(b200sv_ctx* c)
 // The positive transform, and for a signed field (propagate_negative_) the transform of the complement
 int edtPasses(b200sv_ctx* c, Field& F, cudaStream_t s)
 {
-  CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.d2, F.compact, c->compact_bytes, c->sm_count, s));
+  // the x pass writes whole {world, self} words where the OTHER field's plane is all free (no merge read)
+  Field& other = c->fields[&F == &c->fields[0] ? 1 : 0];
+  CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.d2, F.compact, c->compact_bytes, c->sm_count, s, false, F.plane_busy,
+                  other.plane_busy));
   if (F.nd2)
     CU(c, launchEdt(c->grid, F.occ, c->d_tmp, F.nd2, nullptr, c->compact_bytes, c->sm_count, s, true));
   return B200SV_OK;
@@ -1986,6 +1992,8 @@ void b200sv_destroy(b200sv_ctx* c)
       cudaFree(F.nd2);
     if (F.occ)
       cudaFree(F.occ);
+    if (F.plane_busy)
+      cudaFree(F.plane_busy);
   }
   if (c->d_combined) cudaFree(c->d_combined);
   if (c->d_tmp) cudaFree(c->d_tmp);
@@ -2178,6 +2186,7 @@ int b200sv_field_reset(b200sv_ctx* c, int which)
   Field& F = c->fields[which];
   CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
   CU(c, launchFillField(c->grid, F.d2, F.compact, c->compact_bytes, c->stream));
+  CU(c, cudaMemsetAsync(F.plane_busy, 0, (size_t)c->grid.nx * kPlaneBusyStride, c->stream));
   if (F.nd2)
     CU(c, cudaMemsetAsync(F.nd2, 0, c->n_voxels * 2, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -2554,6 +2563,7 @@ int b200sv_field_set_d2(b200sv_ctx* c, int which, const int32_t* d2)
   CU(c, cudaMemcpyAsync(c->d_i32.p, d2, c->n_voxels * 4, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
   CU(c, launchInjectD2(c->grid, c->d_i32.p, F.occ, F.d2, F.compact, c->compact_bytes, c->stream));
+  CU(c, cudaMemsetAsync(F.plane_busy, 1, (size_t)c->grid.nx * kPlaneBusyStride, c->stream));  // injected values: any plane may be busy
   CU(c, cudaStreamSynchronize(c->stream));
   return B200SV_OK;
 }
@@ -3471,6 +3481,8 @@ static int fieldTransfer(b200sv_ctx* c, int which, uint8_t* d_buf, void* cuda_st
   }
   // this field's elements of the interleaved compact field
   CU(c, launchCompactCopy(F.compact, d_buf + cmp_off, c->n_voxels, c->compact_bytes, to_buf, s));
+  if (!to_buf)
+    CU(c, cudaMemsetAsync(F.plane_busy, 1, (size_t)c->grid.nx * kPlaneBusyStride, s));
   return leaveUser(c, s);
 }
 
@@ -3608,6 +3620,10 @@ int b200sv_multi_field_sync(b200sv_multi* m, int which)
     if (e == cudaSuccess)
       e = cudaMemcpyPeerAsync(dst->d_combined, dst->device, src->d_combined, src->device,
                               src->n_voxels * 2 * (size_t)src->compact_bytes, dst->stream);
+    // both fields' plane flags travel with the array they describe
+    for (int w = 0; w < 2 && e == cudaSuccess; ++w)
+      e = cudaMemcpyPeerAsync(dst->fields[w].plane_busy, dst->device, src->fields[w].plane_busy, src->device,
+                              (size_t)src->grid.nx * kPlaneBusyStride, dst->stream);
     if (e != cudaSuccess)
       return multiFail(m, B200SV_ERR_CUDA, std::string("peer copy of the field: ") + cudaGetErrorString(e));
   }

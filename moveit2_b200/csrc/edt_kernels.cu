@@ -95,10 +95,12 @@ __device__ __forceinline__ unsigned divByMagic(unsigned i, unsigned magic) { ret
 // `invert`: transform of the COMPLEMENT (distance to the nearest free voxel of the grid = negative_distance_square_ of the
 // signed field, propagateNegative :446-504); cells outside the grid are not free.
 __global__ void __launch_bounds__(1024) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
-                                                  int chunk, int n_chunks, unsigned nz8_magic, int invert)
+                                                  int chunk, int n_chunks, unsigned nz8_magic, int invert, uint8_t* own_busy)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   const int x = blockIdx.x / n_chunks, ci = blockIdx.x - x * n_chunks;
+  if (own_busy != nullptr && ci == 0 && threadIdx.x == 0)
+    own_busy[static_cast<size_t>(x) * kPlaneBusyStride] = 0;  // the x pass (next launch) raises it again where the plane is not free
   const int y0 = ci * chunk, y1 = min(g.ny, y0 + chunk);
   const int ya = y0 - g.R, rows = (y1 - y0) + 2 * g.R;  // haloed row range [ya, ya + rows)
   const int nzp = (g.nz + 7) & ~7;
@@ -253,13 +255,25 @@ __device__ __forceinline__ bool onShell(const GridDev& g, size_t i)
   return x == 0 || x == g.nx - 1 || y == 0 || y == g.ny - 1 || z == 0 || z == g.nz - 1;
 }
 
+// Raise plane x's flag if any thread of the CTA holds a non-free element: ONE store per CTA (a CTA works on one plane),
+// and the flags sit kPlaneBusyStride bytes apart -- thousands of threads share each flag, and same-address (or same-line)
+// traffic serialises in L2.  Called by every thread of the CTA that has not exited.
+__device__ __forceinline__ void raiseBusy(uint8_t* own_busy, int x, bool mine)
+{
+  if (own_busy == nullptr)
+    return;  // uniform
+  if (__syncthreads_or(mine ? 1 : 0) != 0 && threadIdx.x == 0)
+    own_busy[static_cast<size_t>(x) * kPlaneBusyStride] = 1;
+}
+
 // x pass, 8 consecutive z per thread (16-byte loads / stores); requires nz % 8 == 0.  The compact field is
 // interleaved {world, self} per voxel: this field owns every other element, so its 8 elements are merged into the
 // 16 (uint8) or 32 (uint16) bytes they share with the other field (read-modify-write; fields are built one at a time
 // on one stream).
 template <typename FT>
 __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* __restrict__ in, uint16_t* __restrict__ d2,
-                                                    FT* compact, unsigned nz8_magic)
+                                                    FT* compact, unsigned nz8_magic, uint8_t* own_busy,
+                                                    const uint8_t* __restrict__ other_busy)
 {
   // grid: x = tiles of the (y, z/8) plane, y = x planes
   const int nz8 = g.nz >> 3;
@@ -316,24 +330,53 @@ __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* 
         bw[3] = (bw[3] & 0x0000ffffu) | (static_cast<uint32_t>(max_d2) << 16);
     }
     // our 8 elements of the interleaved {world, self} compact field: element 2 * (8 i + j) counted from `compact`
-    // (already offset by 0 = world / 1 = self); the other field's elements in between are kept (read-modify-write)
+    // (already offset by 0 = world / 1 = self).  Where the other field's plane is known to be all "free" the whole words
+    // are written; elsewhere the other field's elements in between are kept (read-modify-write).
+    const bool second = (reinterpret_cast<uintptr_t>(compact) & (2 * sizeof(FT) - 1)) != 0;
+    const bool other_free = other_busy != nullptr && other_busy[static_cast<size_t>(x) * kPlaneBusyStride] == 0;  // uniform over the CTA
     if (sizeof(FT) == 1)
     {
-      const bool second = (reinterpret_cast<uintptr_t>(compact) & 1u) != 0;
-      const uint32_t sh = second ? 8u : 0u, keep = ~(0x00ff00ffu << sh);
+      const uint32_t sh = second ? 8u : 0u, osh = 8u - sh, keep = ~(0x00ff00ffu << sh);
+      const uint32_t freeb = static_cast<uint32_t>(min(max_d2, 255)) * 0x00010001u;
       uint4* q = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(compact) - (second ? 1 : 0)) + i;
-      uint4 v = *q;  // voxel pair per 32-bit word: bytes { world, self, world, self }
-      v.x = (v.x & keep) | (__vminu2(bw[0], 0x00ff00ffu) << sh);
-      v.y = (v.y & keep) | (__vminu2(bw[1], 0x00ff00ffu) << sh);
-      v.z = (v.z & keep) | (__vminu2(bw[2], 0x00ff00ffu) << sh);
-      v.w = (v.w & keep) | (__vminu2(bw[3], 0x00ff00ffu) << sh);
+      const uint4 own = make_uint4(__vminu2(bw[0], 0x00ff00ffu), __vminu2(bw[1], 0x00ff00ffu), __vminu2(bw[2], 0x00ff00ffu),
+                                   __vminu2(bw[3], 0x00ff00ffu));
+      raiseBusy(own_busy, x, ((own.x ^ freeb) | (own.y ^ freeb) | (own.z ^ freeb) | (own.w ^ freeb)) != 0u);
+      uint4 v;  // voxel pair per 32-bit word: bytes { world, self, world, self }
+      if (other_free)
+        v = make_uint4(freeb << osh, freeb << osh, freeb << osh, freeb << osh);
+      else
+      {
+        v = *q;
+        v.x &= keep; v.y &= keep; v.z &= keep; v.w &= keep;
+      }
+      v.x |= own.x << sh;
+      v.y |= own.y << sh;
+      v.z |= own.z << sh;
+      v.w |= own.w << sh;
       *q = v;
     }
     else
     {
+      const uint32_t freew = static_cast<uint32_t>(max_d2) * 0x00010001u;
+      raiseBusy(own_busy, x, ((bw[0] ^ freew) | (bw[1] ^ freew) | (bw[2] ^ freew) | (bw[3] ^ freew)) != 0u);
+      if (other_free)
+      {  // voxel per 32-bit word: { world, self }
+        const uint32_t fo = static_cast<uint32_t>(max_d2) << (second ? 0 : 16);
+        uint32_t w[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        compact[2 * (8 * i + j)] = static_cast<FT>((bw[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        for (int j = 0; j < 8; ++j)
+          w[j] = (((bw[j >> 1] >> (16 * (j & 1))) & 0xffffu) << (second ? 16 : 0)) | fo;
+        uint4* q = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(compact) - (second ? 1 : 0)) + 2 * i;
+        q[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      else
+      {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          compact[2 * (8 * i + j)] = static_cast<FT>((bw[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+      }
     }
   }
 }
@@ -684,7 +727,8 @@ cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint3
 }
 
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
-                      int compact_bytes, int sm_count, cudaStream_t s, bool invert)
+                      int compact_bytes, int sm_count, cudaStream_t s, bool invert, uint8_t* own_busy,
+                      const uint8_t* other_busy)
 {
   // y chunks: small enough for several CTAs per SM (a haloed slab = occupancy words + squared z distances in shared
   // memory), large enough that the 2R halo rows stay a modest overhead
@@ -716,7 +760,9 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
   const unsigned nz8 = static_cast<unsigned>(nzp / 8);
   const unsigned nz8_magic = static_cast<unsigned>(((1ull << 32) + nz8 - 1) / nz8);  // i / nz8 = umulhi(i, magic), i < 2^16
   static const int zy_threads = getenv("B200SV_EDT_THREADS") ? atoi(getenv("B200SV_EDT_THREADS")) : 512;
-  edtZYKernel<<<g.nx * n_chunks, zy_threads, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic, invert ? 1 : 0);
+  if (compact == nullptr)
+    own_busy = nullptr;
+  edtZYKernel<<<g.nx * n_chunks, zy_threads, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic, invert ? 1 : 0, own_busy);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
@@ -725,11 +771,20 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
   if (g.nz % 8 == 0 && plane8 * nz8 < (1ull << 32))  // the second condition keeps p / nz8 = umulhi(p, magic) exact
   {
     const dim3 grid(static_cast<unsigned>((plane8 + 255) / 256), static_cast<unsigned>(std::min(g.nx, 65535)));
+    static const bool no_rmw_skip = getenv("B200SV_EDT_RMW") != nullptr;  // A/B: always merge, as before
+    if (no_rmw_skip)
+      other_busy = nullptr;
     if (compact_bytes == 1)
-      edtXKernelVec<uint8_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint8_t*>(compact), nz8_magic);
+      edtXKernelVec<uint8_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint8_t*>(compact), nz8_magic, own_busy, other_busy);
     else
-      edtXKernelVec<uint16_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint16_t*>(compact), nz8_magic);
+      edtXKernelVec<uint16_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint16_t*>(compact), nz8_magic, own_busy, other_busy);
     return cudaGetLastError();
+  }
+  if (own_busy != nullptr && compact != nullptr)
+  {  // the scalar x pass below does not track the planes: everything may be busy
+    e = cudaMemsetAsync(own_busy, 1, static_cast<size_t>(g.nx) * kPlaneBusyStride, s);
+    if (e != cudaSuccess)
+      return e;
   }
   const int grid = gridFor(total, 256, sm_count * 32);
   if (compact_bytes == 1)

@@ -224,8 +224,13 @@ cudaError_t launchOctreeLeaves(const double* d_leaves, size_t n, double resoluti
 // INTERLEAVED compact field (element 2 * voxel; `compact` arrives offset by 0 = world / 1 = self; uint8:
 // min(d^2, 255), uint16: d^2).  tmp: uint16 [nx*ny*nz] scratch.  invert: the transform of the complement (the
 // negative half of a signed field; pass compact = nullptr, it has no compact copy).
+constexpr int kPlaneBusyStride = 32;  // bytes between two planes' flags (one L2 sector each)
+// own_busy / other_busy: [nx * kPlaneBusyStride] flags per x plane (the first byte of each stride), nonzero = this / the OTHER field's compact elements of that plane are not
+// all "free" (nullptr: unknown).  The x pass clears and sets own_busy, and where the other field's plane is free it writes
+// whole {world, self} words instead of merging into them (no read of the interleaved field).
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
-                      int compact_bytes, int sm_count, cudaStream_t s, bool invert = false);
+                      int compact_bytes, int sm_count, cudaStream_t s, bool invert = false, uint8_t* own_busy = nullptr,
+                      const uint8_t* other_busy = nullptr);
 cudaError_t launchInjectNegD2(const GridDev& g, const int32_t* d_in, uint16_t* nd2, cudaStream_t s);
 cudaError_t launchFillField(const GridDev& g, uint16_t* d2, void* compact, int compact_bytes, cudaStream_t s);
 cudaError_t launchInjectD2(const GridDev& g, const int32_t* d_in, uint32_t* occ, uint16_t* d2, void* compact,

@@ -570,3 +570,61 @@ def test_a_body_of_several_shapes_is_culled_as_a_whole():
     eng.close()
     eng0.close()
     assert not ok.any()   # both end states of every edge collide
+
+
+# ---- the interleaved {world, self} compact field stays consistent whichever field is rebuilt, in whatever order -----------
+def _compact_of(eng, which, torch):
+    """This field's elements of the compact field (what the check kernel gathers), read back through the export buffer."""
+    buf = torch.empty(eng.field_export_size(), dtype=torch.uint8, device="cuda")
+    eng.field_export_device(buf.data_ptr(), which, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    nv = int(np.prod(eng.num_cells))
+    nx, ny, wz = eng.num_cells[0], eng.num_cells[1], (eng.num_cells[2] + 31) // 32
+    off = ((nx * ny * wz * 4 + 255) & ~255) + ((nv * 2 + 255) & ~255)
+    return buf[off:off + nv].cpu().numpy().reshape(eng.num_cells)
+
+
+def _expected_compact(d2, max_d2):
+    want = np.minimum(d2, 255).astype(np.uint8)   # 8-bit elements: min(d^2, 255)
+    free = min(max_d2, 255)
+    want[0, :, :] = want[-1, :, :] = want[:, 0, :] = want[:, -1, :] = want[:, :, 0] = want[:, :, -1] = free  # the shell
+    return want
+
+
+def test_compact_field_survives_rebuilds_of_either_field_in_any_order():
+    """The x pass of a rebuild writes whole {world, self} words where the OTHER field's x plane is known to be free and merges
+    elsewhere: after every step both fields' compact elements must still be min(d^2, 255) of their own d2."""
+    torch = pytest.importorskip("torch")
+    urdf, srdf = read(RES, "dualarm_spheres.urdf"), read(RES, "dualarm.srdf")
+    geo = ((3.0, 3.0, 2.5), (0.0, 0.0, 1.0), 0.05, 0.25)
+    eng = mb.StateValidityEngine.from_urdf(urdf, srdf, "left_arm", *geo)
+    assert eng.info.field_bytes_per_voxel == 1
+    max_d2 = eng.max_distance_sq
+    env = OracleEnv(RobotModel(urdf, srdf), "left_arm", *geo)
+
+    def both_ok(tag):
+        for which in (mb.FIELD_WORLD, mb.FIELD_SELF):
+            got = _compact_of(eng, which, torch)
+            assert np.array_equal(got, _expected_compact(eng.field_get_d2(which), max_d2)), (tag, which)
+
+    both_ok("created: self built, world free")
+    assert (eng.field_get_d2(mb.FIELD_SELF) == 0).any()
+    # a world cloud in ONE corner: most x planes of the world field stay free
+    cloud = workloads.clutter_cloud(6, 20000, 4, (0.6, 0.6, 0.1), (1.3, 1.3, 1.0), 0.0, floor=False)
+    eng.field_add_points(cloud)
+    both_ok("world built next to a busy self field")
+    base = np.array(env.base_positions)
+    gv = set(int(v) for v in env.arr["group_var_index"])
+    for v in RobotModel(urdf, srdf).groups["right_arm"].variable_index_list:
+        if v not in gv:
+            base[v] = 0.7
+    eng.set_base_state(base)
+    both_ok("self rebuilt next to a partly busy world field")
+    eng.field_reset()
+    both_ok("world reset")
+    eng.field_add_points(cloud[:100] - np.array([1.5, 1.5, 0.0]))
+    both_ok("world rebuilt in the opposite corner")
+    eng.field_set_d2(eng.field_get_d2(mb.FIELD_SELF), mb.FIELD_WORLD)   # injected values: every plane may be busy
+    eng.set_base_state(env.base_positions)
+    both_ok("self rebuilt next to an injected world field")
+    eng.close()
