@@ -1699,11 +1699,11 @@ int finishCreate(b200sv_ctx* c, int device, b200sv_ctx** out)
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_go, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_go, getenv("B200SV_TRACE") ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming) != cudaSuccess)
     return bail(fail(c, B200SV_ERR_CUDA, "stream/event creation failed"));
   for (int i = 0; i < b200sv_ctx::kMaxChunks; ++i)
-    if (cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess)
+    if (cudaEventCreateWithFlags(&c->ev_chunk[i], getenv("B200SV_TRACE") ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(c, B200SV_ERR_CUDA, "event creation failed"));
   if ((rc = uploadTables(c)) != B200SV_OK)
     return bail(rc);
@@ -1803,33 +1803,68 @@ int runCheck(b200sv_ctx* c, const double* d_q, size_t n, uint32_t flags, uint32_
 }
 
 // Host-buffer entry: the H2D copy of the states is cut into chunks on a second stream so the check of chunk i
-// overlaps the copy of chunk i + 1 (PCIe is the longer of the two for 56-byte states).
+// overlaps the copy of chunk i + 1.  The check kernel is a persistent grid in which every warp takes tiles of 32 states
+// (one state per lane, ~36 us per tile on C2): a launch costs whole ROUNDS of the grid, so a chunk that is not a multiple
+// of the wave (grid x warps x 32 states) pays for a round it only partly uses -- uniform 128 Ki-state chunks spent twice
+// the kernel time of one launch over the batch (B200SV_TRACE=1 prints the timeline).  Chunks are therefore whole waves:
+// 1, 2, 3, then 4 (or more, to stay within kMaxChunks) waves (the first copy cannot overlap anything, so it is short; later chunks amortise launch and DMA
+// set-up), one wave before the end (the last kernel cannot overlap anything either), and the ragged remainder last --
+// the rounds add up to those of a single launch.  Sizes are multiples of 32 so bitmap words do not straddle chunks.
+std::vector<size_t> chunkPlan(size_t n, size_t wave)
+{
+  std::vector<size_t> plan;
+  if (const char* e = getenv("B200SV_CHUNK"))
+  {  // experiments: uniform chunks of this many states
+    size_t chunk = std::max<size_t>(32, (size_t)atol(e) & ~(size_t)31);
+    while ((n + chunk - 1) / chunk > (size_t)b200sv_ctx::kMaxChunks)
+      chunk *= 2;
+    for (size_t base = 0; base < n; base += chunk)
+      plan.push_back(std::min(chunk, n - base));
+    return plan;
+  }
+  wave = std::max<size_t>(32, wave & ~(size_t)31);
+  const size_t full = n / wave, rest = n % wave;
+  if (full == 0)
+    return { n };
+  const size_t tail = full >= 3 ? 1 : 0;
+  size_t body = full - tail;
+  const size_t mid = std::max<size_t>(4, (body + 22) / 23);  // 3 ramp chunks + at most 24 of these + 2: within kMaxChunks
+  for (size_t step = 1; body > 0; ++step)
+  {
+    const size_t t = std::min(step <= 3 ? step : mid, body);
+    plan.push_back(t * wave);
+    body -= t;
+  }
+  if (tail)
+    plan.push_back(wave);
+  if (rest)
+    plan.push_back(rest);
+  return plan;
+}
+
 template <typename FT>
 int runCheckHost(b200sv_ctx* c, const void* h_q_any, size_t n, uint32_t flags, bool f32 = false)
 {
   const double* h_q = static_cast<const double*>(h_q_any);
   const float* h_qf = static_cast<const float*>(h_q_any);
   const size_t V = c->robot.group_var_index.size();
-  size_t chunk = 131072;                               // states; a multiple of 32 so bitmap words do not straddle
-  if (const char* e = getenv("B200SV_CHUNK"))
-    chunk = std::max<size_t>(32, (size_t)atol(e) & ~(size_t)31);
-  while ((n + chunk - 1) / chunk > b200sv_ctx::kMaxChunks - 4)
-    chunk *= 2;
+  const b200sv_ctx::LaunchCfg& lc = (flags & B200SV_CHECK_FP64) ? c->cfg_d : (c->fast_ok && !c->fast_disabled) ? c->cfg_fast : c->cfg_f;
+  const std::vector<size_t> plan = chunkPlan(n, (size_t)c->sm_count * lc.blocks_per_sm * lc.warps * 32);
   const bool fp64 = (flags & B200SV_CHECK_FP64) != 0;
+  // B200SV_TRACE=1: print when every chunk's copy and kernel finished (debug; adds events and a synchronisation)
+  static const bool trace = getenv("B200SV_TRACE") != nullptr;
+  static cudaEvent_t tr_k[b200sv_ctx::kMaxChunks + 1] = { nullptr };
+  if (trace && !tr_k[0])
+    for (auto& e : tr_k)
+      cudaEventCreate(&e);
   if (!fp64)
     CU(c, cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream));
   CU(c, cudaEventRecord(c->ev_go, c->stream));
   CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_go, 0));  // earlier work on the compute stream may still read d_q
-  int i = 0;
-  size_t m = 0;
-  for (size_t base = 0; base < n; base += m, ++i)
+  size_t base = 0;
+  for (size_t i = 0; i < plan.size(); base += plan[i], ++i)
   {
-    // The copies are the longer leg, so what is left after the LAST copy lands is pure tail: the last chunks shrink
-    // (1/2, 1/4, 1/8, 1/8 of a chunk) and with them the kernel time that cannot overlap anything.
-    const size_t left = n - base;
-    m = std::min(chunk, left);
-    if (left <= chunk && left > chunk / 8 && i < b200sv_ctx::kMaxChunks - 1)
-      m = std::min(left, std::max<size_t>((left / 2 + 31) & ~(size_t)31, (chunk / 8) & ~(size_t)31));
+    const size_t m = plan[i];
     if (f32)
       CU(c, cudaMemcpyAsync(c->d_qf.p + base * V, h_qf + base * V, m * V * sizeof(float), cudaMemcpyHostToDevice,
                             c->copy_stream));
@@ -1843,10 +1878,27 @@ int runCheckHost(b200sv_ctx* c, const void* h_q_any, size_t n, uint32_t flags, b
     int rc = launchMain<FT>(c, c->d_q.p, c->d_bitmap.p, base, m, flags, c->stream);
     if (rc != B200SV_OK)
       return rc;
+    if (trace)
+      cudaEventRecord(tr_k[i], c->stream);
   }
-  if (!fp64)
-    return launchRecheck<FT>(c, c->d_q.p, c->d_bitmap.p, n, flags, c->stream);
-  return B200SV_OK;
+  int rc = fp64 ? B200SV_OK : launchRecheck<FT>(c, c->d_q.p, c->d_bitmap.p, n, flags, c->stream);
+  if (trace)
+  {
+    cudaEventRecord(tr_k[plan.size()], c->stream);
+    cudaStreamSynchronize(c->stream);
+    fprintf(stderr, "[b200sv trace] %s, %zu states:", f32 ? "f32" : "f64", n);
+    for (size_t i = 0; i < plan.size(); ++i)
+    {
+      float tc = 0.f, tk = 0.f;
+      cudaEventElapsedTime(&tc, c->ev_go, c->ev_chunk[i]);
+      cudaEventElapsedTime(&tk, c->ev_go, tr_k[i]);
+      fprintf(stderr, " [%zu: copied %.0f us, checked %.0f us]", plan[i], tc * 1e3, tk * 1e3);
+    }
+    float tr = 0.f;
+    cudaEventElapsedTime(&tr, c->ev_go, tr_k[plan.size()]);
+    fprintf(stderr, " recheck done %.0f us\n", tr * 1e3);
+  }
+  return rc;
 }
 
 // batched FK of device-resident states into device-resident 4x4 column-major doubles, all model links
