@@ -507,7 +507,8 @@ def main():
     del d_T, d_qf
     # batched edge validation: 2 states in, ~34 checked on the device
     ne = 100_000
-    ea, eb = q_host[:ne], q_host[ne:2 * ne]
+    q_pin_np = q_pin.numpy()   # the edges' end states come from pinned host memory, like the e2e leg's states
+    ea, eb = q_pin_np[:ne], q_pin_np[ne:2 * ne]
     seg = 0.01 * float(np.sum(hi - lo))
     for _ in range(2):
         eng.check_motions(ea, eb, seg)
@@ -517,7 +518,7 @@ def main():
     dt = (time.perf_counter() - t0) / 3
     line["e2e_edges"] = {"edges_per_s": ne / dt, "states_per_s": n_exp / dt, "edges": ne, "states_checked": int(n_exp),
                          "h2d_bytes_per_call": 2 * ne * V * 8, "d2h_bytes_per_call": ne // 8 + 4 * ne, "ms_per_call": 1e3 * dt,
-                         "entry": "b200sv_check_motions (host edges in, validity bitmap + first invalid index out)"}
+                         "entry": "b200sv_check_motions (pinned host edges in, validity bitmap + first invalid index out)"}
     # single-state latency through the host entry point (OMPL's per-state isValid through the plugin)
     lat = {}
     for nb in (1, 32):

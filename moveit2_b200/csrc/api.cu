@@ -3133,6 +3133,8 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
   CU(c, cudaMemcpyAsync(small ? static_cast<void*>(h_res) : static_cast<void*>(&total), c->d_edge_offset.p + n_edges, sizeof(total),
                         cudaMemcpyDeviceToHost, s));
   CU(c, cudaStreamSynchronize(s));  // the state batch is sized by the edges' lengths
+  static const bool trace = getenv("B200SV_TRACE") != nullptr;
+  const auto t_counted = std::chrono::steady_clock::now();
   if (small)
     memcpy(&total, h_res, sizeof(total));
   if (total >= (1ull << 32))
@@ -3169,6 +3171,11 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
     CU(c, cudaStreamSynchronize(s));
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   }
+  if (trace)
+    fprintf(stderr, "[b200sv trace] check_motions: %zu edges -> %llu states; edges on the device and counted after %.0f us, all "
+                    "done after %.0f us (device span %.0f us)\n", n_edges, total,
+            std::chrono::duration<double, std::micro>(t_counted - t_small).count(),
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_small).count(), ms * 1e3);
   if (n_states_checked)
     *n_states_checked = total;
   c->stats.n_states = total;

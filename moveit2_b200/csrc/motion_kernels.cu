@@ -56,98 +56,95 @@ __global__ void motionCountKernel(MotionArgs a)
   }
 }
 
-// single-CTA exclusive scan of count[0..n) into offset[0..n]; n is a batch of edges, not of states
-__global__ void motionScanKernel(const unsigned* __restrict__ count, unsigned long long* __restrict__ offset, size_t n)
+// single-CTA exclusive scan of count[0..n) into offset[0..n]; n is a batch of edges, not of states.  Every thread owns a
+// contiguous run of ceil(n / blockDim) counts: it sums them, the block scans the 1024 sums once, and the thread writes its
+// run's offsets -- two barriers in all instead of four per 1024 elements.
+__global__ void __launch_bounds__(1024) motionScanKernel(const unsigned* __restrict__ count, unsigned long long* __restrict__ offset,
+                                                         size_t n)
 {
   __shared__ unsigned long long warp_sums[32];
-  __shared__ unsigned long long carry;
-  if (threadIdx.x == 0)
-    carry = 0ull;
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (size_t base = 0; base < n; base += blockDim.x)
+  const size_t per = (n + blockDim.x - 1) / blockDim.x;
+  const size_t i0 = min(n, threadIdx.x * per), i1 = min(n, i0 + per);
+  unsigned long long mine = 0ull;
+  for (size_t i = i0; i < i1; ++i)
+    mine += count[i];
+  unsigned long long x = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1)
   {
-    const size_t i = base + threadIdx.x;
-    unsigned long long v = i < n ? count[i] : 0ull;
-    unsigned long long x = v;
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d)
+      x += y;
+  }
+  if (lane == 31)
+    warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0)
+  {
+    unsigned long long s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0ull;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1)
     {
-      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, s, d);
       if (lane >= d)
-        x += y;
+        s += y;
     }
-    if (lane == 31)
-      warp_sums[warp] = x;
-    __syncthreads();
-    if (warp == 0)
-    {
-      unsigned long long s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0ull;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
-      {
-        const unsigned long long y = __shfl_up_sync(0xffffffffu, s, d);
-        if (lane >= d)
-          s += y;
-      }
-      warp_sums[lane] = s;  // inclusive
-    }
-    __syncthreads();
-    const unsigned long long before = carry + (warp ? warp_sums[warp - 1] : 0ull) + (x - v);
-    if (i < n)
-      offset[i] = before;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1)
-      carry += warp_sums[(blockDim.x >> 5) - 1];
-    __syncthreads();
+    warp_sums[lane] = s;  // inclusive
   }
-  if (threadIdx.x == 0)
-    offset[n] = carry;
+  __syncthreads();
+  unsigned long long run = (warp ? warp_sums[warp - 1] : 0ull) + (x - mine);
+  for (size_t i = i0; i < i1; ++i)
+  {
+    offset[i] = run;
+    run += count[i];
+  }
+  if (threadIdx.x == blockDim.x - 1)
+    offset[n] = warp_sums[(blockDim.x >> 5) - 1];
 }
 
-// one thread per generated state: binary search of its edge, then JointModelGroup::interpolate
-__global__ void motionExpandKernel(MotionArgs a, double* __restrict__ q_out, unsigned long long n_states)
+// one WARP per edge, one lane per generated state (no search for the state's edge; the lanes of a warp write one contiguous
+// run of the batch): JointModelGroup::interpolate
+__global__ void __launch_bounds__(256) motionExpandKernel(MotionArgs a, double* __restrict__ q_out, unsigned long long n_states)
 {
-  for (unsigned long long s = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; s < n_states;
-       s += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+  const int lane = threadIdx.x & 31;
+  const size_t warps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+  for (size_t e = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5; e < a.n_edges; e += warps)
   {
-    size_t lo = 0, hi = a.n_edges;  // offset[lo] <= s < offset[hi]
-    while (hi - lo > 1)
+    const unsigned c = a.count[e];
+    const unsigned long long s0 = a.offset[e];
+    const double* f = a.q_from + e * a.n_vars;
+    const double* t = a.q_to + e * a.n_vars;
+    for (unsigned j = 1u + lane; j <= c; j += 32u)  // 1 .. c
     {
-      const size_t mid = (lo + hi) >> 1;
-      if (a.offset[mid] <= s)
-        lo = mid;
-      else
-        hi = mid;
-    }
-    const unsigned c = a.count[lo];
-    const unsigned j = static_cast<unsigned>(s - a.offset[lo]) + 1u;  // 1 .. c
-    const double* f = a.q_from + lo * a.n_vars;
-    const double* t = a.q_to + lo * a.n_vars;
-    double* o = q_out + s * a.n_vars;
-    if (j == c)
-    {
-      for (int k = 0; k < a.n_vars; ++k)
-        o[k] = t[k];  // s2 itself
-      continue;
-    }
-    const double tt = static_cast<double>(j) / static_cast<double>(c);
-    for (int k = 0; k < a.n_vars; ++k)
-    {
-      double diff = __dsub_rn(t[k], f[k]);
-      double v;
-      if (a.continuous && a.continuous[k] && fabs(diff) > kPi)
-      {  // revolute_joint_model.cpp:147-167
-        diff = diff > 0.0 ? __dsub_rn(2.0 * kPi, diff) : __dsub_rn(-2.0 * kPi, diff);
-        v = __dsub_rn(f[k], __dmul_rn(diff, tt));
-        if (v > kPi)
-          v = __dsub_rn(v, 2.0 * kPi);
-        else if (v < -kPi)
-          v = __dadd_rn(v, 2.0 * kPi);
+      const unsigned long long s = s0 + (j - 1u);
+      if (s >= n_states)
+        break;
+      double* o = q_out + s * a.n_vars;
+      if (j == c)
+      {
+        for (int k = 0; k < a.n_vars; ++k)
+          o[k] = t[k];  // s2 itself
+        continue;
       }
-      else
-        v = __dadd_rn(f[k], __dmul_rn(diff, tt));
-      o[k] = v;
+      const double tt = static_cast<double>(j) / static_cast<double>(c);
+      for (int k = 0; k < a.n_vars; ++k)
+      {
+        double diff = __dsub_rn(t[k], f[k]);
+        double v;
+        if (a.continuous && a.continuous[k] && fabs(diff) > kPi)
+        {  // revolute_joint_model.cpp:147-167
+          diff = diff > 0.0 ? __dsub_rn(2.0 * kPi, diff) : __dsub_rn(-2.0 * kPi, diff);
+          v = __dsub_rn(f[k], __dmul_rn(diff, tt));
+          if (v > kPi)
+            v = __dsub_rn(v, 2.0 * kPi);
+          else if (v < -kPi)
+            v = __dadd_rn(v, 2.0 * kPi);
+        }
+        else
+          v = __dadd_rn(f[k], __dmul_rn(diff, tt));
+        o[k] = v;
+      }
     }
   }
 }
@@ -195,8 +192,8 @@ cudaError_t launchMotionExpand(const MotionArgs& a, double* d_q, unsigned long l
 {
   if (n_states == 0)
     return cudaSuccess;
-  const unsigned long long blocks = (n_states + 255) / 256;
-  motionExpandKernel<<<static_cast<int>(blocks < 65535ull ? blocks : 65535ull), 256, 0, s>>>(a, d_q, n_states);
+  const unsigned long long blocks = (static_cast<unsigned long long>(a.n_edges) + 7) / 8;  // 8 warps = 8 edges per CTA
+  motionExpandKernel<<<static_cast<int>(blocks < 148ull * 64 ? (blocks ? blocks : 1) : 148ull * 64), 256, 0, s>>>(a, d_q, n_states);
   return cudaGetLastError();
 }
 
