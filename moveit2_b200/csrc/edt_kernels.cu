@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "kernels.hpp"
 
@@ -86,6 +88,33 @@ __global__ void __launch_bounds__(256) scatterKernel(const double* __restrict__ 
 // i / d by multiply-high with magic = ceil(2^32 / d); d = 1 has no 32-bit magic (2^32): the launcher passes 0 for it
 __device__ __forceinline__ unsigned divByMagic(unsigned i, unsigned magic) { return magic ? __umulhi(i, magic) : i; }
 
+// Tables of the z pass (see edtZYKernel): 256 + 2 (R + 2) rows of 8 uint16 squared distances, a function of R alone.
+__global__ void edtLutKernel(int R, uint4* __restrict__ lut)
+{
+  const int cap = R + 1;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 256 + 2 * (cap + 1); t += gridDim.x * blockDim.x)
+  {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+      int d;
+      if (t < 256)
+      {  // nearest set bit of pattern t to bit j
+        const uint32_t lo = static_cast<uint32_t>(t) & ((2u << j) - 1u), hi = static_cast<uint32_t>(t) >> j;
+        d = min(lo ? j - 31 + __clz(lo) : cap, hi ? __ffs(hi) - 1 : cap);
+      }
+      else if (t < 256 + cap + 1)
+        d = (t - 256) + j;        // below[dL]
+      else
+        d = (t - 256 - cap - 1) + 7 - j;  // above[dR]
+      d = min(d, cap);
+      v[j] = static_cast<uint32_t>(d * d);
+    }
+    lut[t] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+  }
+}
+
 // One CTA per (x plane, y chunk).  Shared memory: occupancy words of rows [y0-R, y1+R), then their SQUARED z distances
 // as uint16 (row stride nzp = nz rounded up to 8: a thread takes 8 consecutive z with one 128-bit access).  Squares,
 // because the y pass then is two packed 16-bit instructions per candidate row and voxel pair: VIMNMX.U16x2 (min of the
@@ -95,7 +124,8 @@ __device__ __forceinline__ unsigned divByMagic(unsigned i, unsigned magic) { ret
 // `invert`: transform of the COMPLEMENT (distance to the nearest free voxel of the grid = negative_distance_square_ of the
 // signed field, propagateNegative :446-504); cells outside the grid are not free.
 __global__ void __launch_bounds__(1024) edtZYKernel(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
-                                                  int chunk, int n_chunks, unsigned nz8_magic, int invert, uint8_t* own_busy)
+                                                  int chunk, int n_chunks, unsigned nz8_magic, int invert, uint8_t* own_busy,
+                                                  const uint4* __restrict__ lut)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   const int x = blockIdx.x / n_chunks, ci = blockIdx.x - x * n_chunks;
@@ -112,30 +142,9 @@ __global__ void __launch_bounds__(1024) edtZYKernel(GridDev g, const uint32_t* _
   uint4* lut_below = lut_within + 256;
   uint4* lut_above = lut_below + (g.R + 2);
   uint32_t* ends = reinterpret_cast<uint32_t*>(lut_above + (g.R + 2));  // [rows * wz]: see the z pass, step (a)
-  {
-    const int cap = g.R + 1;
-    for (int t = threadIdx.x; t < 256 + 2 * (cap + 1); t += blockDim.x)
-    {
-      uint32_t v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-      {
-        int d;
-        if (t < 256)
-        {  // nearest set bit of pattern t to bit j
-          const uint32_t lo = static_cast<uint32_t>(t) & ((2u << j) - 1u), hi = static_cast<uint32_t>(t) >> j;
-          d = min(lo ? j - 31 + __clz(lo) : cap, hi ? __ffs(hi) - 1 : cap);
-        }
-        else if (t < 256 + cap + 1)
-          d = (t - 256) + j;        // below[dL]
-        else
-          d = (t - 256 - cap - 1) + 7 - j;  // above[dR]
-        d = min(d, cap);
-        v[j] = static_cast<uint32_t>(d * d);
-      }
-      lut_within[t] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-    }
-  }
+  // the tables depend on R only: built once per (device, R) by edtLutKernel, copied in here (5 KB, L2-resident)
+  for (int t = threadIdx.x; t < 256 + 2 * (g.R + 2); t += blockDim.x)
+    lut_within[t] = lut[t];
   {
     const uint32_t* src = occ + (static_cast<size_t>(x) * g.ny + ya) * wz;  // rows are contiguous in the bitmap
     const int lo = max(0, -ya) * wz, hi = min(rows, g.ny - ya) * wz;
@@ -726,6 +735,30 @@ cudaError_t launchUpdateOcc(uint32_t* occ, const uint32_t* old_bits, const uint3
   return cudaGetLastError();
 }
 
+// The z pass's tables, one per (device, R), built on first use and kept for the life of the process (a few KB each).
+const uint4* edtLut(int dev, int R, cudaStream_t s)
+{
+  struct Entry { int dev, R; uint4* d; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  for (const Entry& e : cache)
+    if (e.dev == dev && e.R == R)
+      return e.d;
+  uint4* d = nullptr;
+  if (cudaMalloc(&d, (256 + 2 * static_cast<size_t>(R + 2)) * sizeof(uint4)) != cudaSuccess)
+    return nullptr;
+  edtLutKernel<<<2, 256, 0, s>>>(R, d);
+  // other streams (other contexts on this device) may read the table right after this returns
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+  {
+    cudaFree(d);
+    return nullptr;
+  }
+  cache.push_back(Entry{ dev, R, d });
+  return d;
+}
+
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
                       int compact_bytes, int sm_count, cudaStream_t s, bool invert, uint8_t* own_busy,
                       const uint8_t* other_busy)
@@ -762,7 +795,10 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
   static const int zy_threads = getenv("B200SV_EDT_THREADS") ? atoi(getenv("B200SV_EDT_THREADS")) : 512;
   if (compact == nullptr)
     own_busy = nullptr;
-  edtZYKernel<<<g.nx * n_chunks, zy_threads, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic, invert ? 1 : 0, own_busy);
+  const uint4* lut = edtLut(dev, g.R, s);
+  if (lut == nullptr)
+    return cudaErrorMemoryAllocation;
+  edtZYKernel<<<g.nx * n_chunks, zy_threads, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic, invert ? 1 : 0, own_busy, lut);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
