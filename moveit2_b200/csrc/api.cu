@@ -83,7 +83,8 @@ struct b200sv_ctx
   uint8_t *d_blob_f = nullptr, *d_blob_d = nullptr, *d_blob_fast = nullptr;
   bool fast_ok = false;      // the group's joints are all FIXED / REVOLUTE / PRISMATIC: fast_check.cu runs the FP32 pass
   bool fast_disabled = false;  // B200SV_FAST=0: force the generic FP32 kernel (A/B measurements)
-  int state_stride_fast = 0, fast_t_rows = 0, fast_n_linkpairs = 0, fast_n_reps = 0;
+  int state_stride_fast = 0, fast_t_rows = 0, fast_n_linkpairs = 0, fast_n_reps = 0, fast_n_reps_global = 0;
+  uint8_t* d_rep_scratch = nullptr;  // hierarchical cull: per resident warp, the cluster-level parked centres
   bool fast_t_global = false;  // link transforms in an L2-resident scratch instead of shared memory (large robots)
   int fast_smem_blob_bytes = 0;  // bytes of the fast blob the kernel copies to shared memory
   std::vector<int> fast_hot_sphere;  // fast blob: Hot record -> sphere (dfce order), -1 = padding
@@ -815,6 +816,19 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
       linkRange(bs[i].slot, body_rep[body]);
     }
   }
+  // Where a centre is parked (hierarchical cull): the link-level ones in shared memory rows 0 .. n_parked - 1, the cluster-level
+  // ones in the warp's global scratch at their own index.  Without the hierarchy every centre is in shared memory at its index.
+  std::vector<int> slot_of_rep(n_rep, -1);
+  int n_parked = n_rep;
+  if (hier)
+  {
+    n_parked = 0;
+    for (int b = 0; b < n_bodies; ++b)
+      if (body_rep[b] >= 0)
+        slot_of_rep[body_rep[b]] = n_parked++;
+  }
+  for (int r2 = 0; r2 < n_rep; ++r2)
+    cl[r2].slot = hier ? slot_of_rep[r2] : r2;
   // cluster pairs, ordered by (body a, body b) when the cull is hierarchical so a link pair's cluster pairs are contiguous
   std::vector<int> order(pairs.size());
   for (size_t p = 0; p < pairs.size(); ++p)
@@ -871,7 +885,7 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
     if (hier)
     {
       const int ba = A.pad, bb = B.pad;
-      const unsigned ab = (unsigned)body_rep[ba] | ((unsigned)body_rep[bb] << 16);
+      const unsigned ab = (unsigned)slot_of_rep[body_rep[ba]] | ((unsigned)slot_of_rep[body_rep[bb]] << 16);  // shared-memory rows
       if (flp.empty() || flp.back().ab != ab || flp.back().ncp >= 16)
       {
         fast::LinkPair L{};
@@ -916,12 +930,14 @@ bool buildFastBlob(b200sv_ctx& c, const std::vector<LinkRec<double>>& links_in, 
   c.fast_n_linkpairs = h.n_linkpairs;
   // with the hierarchical cull the pair tables stay in global memory: shared memory holds the blob up to off_pairs
   c.fast_smem_blob_bytes = h.n_linkpairs > 0 ? h.off_pairs : off;
-  c.fast_n_reps = n_rep;
+  c.fast_n_reps = n_parked;                  // rows of the per-warp shared-memory arrays
+  c.fast_n_reps_global = hier ? n_rep : 0;   // rows of the per-warp global scratch (hierarchical cull)
   h.total_bytes = off;
   h.state_stride = c.state_stride_fast;
   h.t_rows = 3 * std::max(1, n_stored);
   c.fast_t_rows = h.t_rows;
   h.n_clusters = (int)cl.size();
+  h.n_parked = n_parked;
   h.nz = c.grid.nz;
   h.nynz = c.grid.ny * c.grid.nz;
   h.idx_bias = 0u - 0x4B400000u * (unsigned)(h.nynz + h.nz + 1);
@@ -1510,6 +1526,12 @@ int uploadTables(b200sv_ctx* c)
     if (c->fast_t_global)
       CU(c, cudaMalloc(&c->d_t_scratch, (size_t)c->sm_count * c->cfg_fast.blocks_per_sm * c->cfg_fast.warps *
                                             (size_t)c->fast_t_rows * 128 * sizeof(float)));
+    if (c->d_rep_scratch)
+      cudaFree(c->d_rep_scratch);
+    c->d_rep_scratch = nullptr;
+    if (c->fast_n_reps_global > 0 && c->cfg_fast.warps >= 1)
+      CU(c, cudaMalloc(&c->d_rep_scratch, (size_t)c->sm_count * c->cfg_fast.blocks_per_sm * c->cfg_fast.warps *
+                                              (size_t)fastCheckRepBytes(c->fast_n_reps_global)));
     if (getenv("B200SV_VERBOSE"))
       fprintf(stderr, "b200sv: fast kernel: %d words of transforms per state, %d bytes per warp, %d warps x %d CTAs per SM, blob %zu bytes\n",
               c->state_stride_fast, fastCheckPerWarpBytes(c->fast_t_global ? 0 : c->state_stride_fast, c->fast_n_reps, (int)c->robot.group_var_index.size(), c->fast_n_linkpairs, c->fast_wide),
@@ -1756,6 +1778,7 @@ int launchMain(b200sv_ctx* c, const double* d_q0, uint32_t* d_bitmap0, size_t ba
     a.model = c->d_blob_fast;
     a.model_bytes = (int)c->blob_fast.size();
     a.t_scratch = c->fast_t_global ? c->d_t_scratch : nullptr;
+    a.rep_scratch = c->d_rep_scratch;
     a.hier = c->fast_n_linkpairs > 0;
     a.n_group_vars = (int)c->robot.group_var_index.size();
     a.wide = c->fast_wide ? 1 : 0;
@@ -2058,6 +2081,7 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->d_blob_d) cudaFree(c->d_blob_d);
   if (c->d_blob_fast) cudaFree(c->d_blob_fast);
   if (c->d_t_scratch) cudaFree(c->d_t_scratch);
+  if (c->d_rep_scratch) cudaFree(c->d_rep_scratch);
   c->d_edges.release(); c->d_edge_q.release(); c->d_edge_aux.release(); c->d_edge_count.release();
   c->d_edge_offset.release(); c->d_edge_state_bits.release(); c->d_edge_bits.release(); c->d_edge_first.release();
   c->d_edge_cont.release();

@@ -152,7 +152,8 @@ constexpr int kPSphereStride = 5;   // PSphere entries per cluster row: 80 bytes
 // ([cluster][x, y, z][lane]) for the level-1 cull of the pair phase.
 struct alignas(16) Cluster
 {
-  float tx, ty, tz, pad;
+  float tx, ty, tz;
+  int slot;  // hierarchical cull only: >= 0 = row of the shared-memory arrays (a link-level centre), -1 = global scratch, row = index
 };
 
 // Pair phase: sphere k of cluster c is PSphere[kPSphereStride * c + k].  Padding entries have r_v = -1e30: their
@@ -212,7 +213,9 @@ struct alignas(16) Header
   int n_linkpairs, off_linkpairs;  // hierarchical cull (many cluster pairs): LinkPair records; 0 = level 1 directly
   float lo[3], margin;      // clamp of (centre - margin) to [0.5 - margin, n - 0.5 - margin]: a centre outside the
   float hi[3], two_margin;  // field lands in the 1-cell border shell, where nothing collides
-  float pair_eps_v, tight_eps_v, pad0, pad1;
+  float pair_eps_v, tight_eps_v, pad0;
+  int n_parked;  // centres parked in SHARED memory: every cluster, or with the hierarchical cull only the link-level ones (the
+                 // cluster-level centres then live in a per-warp global scratch: Cluster::slot says where an entry goes)
   float rep_base[3];  // cluster centres are parked relative to this point (cells): small magnitudes for half
   float rep_limit;    // the level-1 slack assumes |centre - rep_base| < rep_limit per axis
   float ident[12];    // identity 3x4: the "parent transform" of a root link

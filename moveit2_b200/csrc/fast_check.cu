@@ -39,10 +39,10 @@ namespace
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kU = B200SV_FAST_UNROLL;  // Hot ranges are padded per link to a multiple of this (the tail chunk)
 #ifndef B200SV_FAST_THREADS
-#define B200SV_FAST_THREADS 256
+#define B200SV_FAST_THREADS 512
 #endif
 #ifndef B200SV_FAST_MINBLOCKS
-#define B200SV_FAST_MINBLOCKS 2
+#define B200SV_FAST_MINBLOCKS 1
 #endif
 #ifndef B200SV_MAXVARS
 #define B200SV_MAXVARS 16
@@ -265,6 +265,8 @@ __device__ __forceinline__ void pairItem(const FModel& m, const TStore<kGlobal>&
 // states share one 32-bit word (the cull works on half2 = two states at a time).
 constexpr int kRepStride = 34;
 __device__ __host__ inline int repBytes(int n_clusters) { return (3 * n_clusters * kRepStride * 2 + 15) & ~15; }
+// the hierarchical cull's cluster-level centres in global scratch: [cluster][32 states] of { x | y << 16, z } halves
+__device__ __host__ inline int globalRepBytes(int n_clusters) { return n_clusters * 32 * 8; }
 
 // The work queue of the pair phase.  The wide instance (no TMA staging) also keeps the tile's states there during the FK
 // phase: the two are never live together.
@@ -413,7 +415,9 @@ __device__ __forceinline__ void fastLinkStep(const int4& m0, const int4* Li, con
 // Dynamic shared memory: [fast blob][per warp: transforms | cluster centres | work queue | hit word, amb word]
 // kV: group variables the register prefetch covers.  Groups of at most kSmallVars variables (an arm) get their own
 // instance: 16 prefetch registers fewer, and launch bounds that fit 3 CTAs x 6 warps per SM at 96 registers instead of
-// 2 x 8 at 128 (+4.7 % on C2, measured; the 16-variable instance loses with the tighter bounds).
+// 16 warps at 128 (+4.7 % on C2, measured; the 16-variable instance loses with the tighter bounds).  The larger instance
+// runs as ONE CTA of up to 16 warps per SM (512 threads): the model blob is staged once instead of twice, which is what let
+// the 280-sphere dual arm reach 16 warps (+4.5 % over 2 x 7; C3 +1.6 %, the 18-variable whole body +4.4 %).
 // kV == 0 is the WIDE instance: groups with more than 16 variables or with a planar joint (a mobile base: the dual arm's
 // whole_body group has 18).  No register prefetch -- the next tile's states are pulled into L2 one tile ahead and read at the
 // start of their tile -- and the link loop knows PLANAR joints (Translation(x, y, 0) * Rz(theta), planar_joint_model.cpp:345-349).
@@ -434,15 +438,21 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
   constexpr bool kWide = kV == 0;
   uint8_t* wbase = smem + (kHier ? h.off_pairs : h.total_bytes) +
                    static_cast<size_t>(warp) *
-                       fastPerWarpBytes(t_words, h.n_clusters, h.n_group_vars, kHier ? h.n_linkpairs : 0, kWide);
+                       fastPerWarpBytes(t_words, h.n_parked, h.n_group_vars, kHier ? h.n_linkpairs : 0, kWide);
   float* Ts = reinterpret_cast<float*>(wbase);
   TStore<kTG> ts;
   ts.base = kTG ? a.t_scratch + (static_cast<size_t>(blockIdx.x) * warps + warp) * (static_cast<size_t>(h.t_rows) * 128) : Ts;
   ts.stride = h.state_stride;
   __half* rep_x = reinterpret_cast<__half*>(Ts + 32 * t_words);  // [cluster][kRepStride]
-  __half* rep_y = rep_x + h.n_clusters * kRepStride;
-  __half* rep_z = rep_y + h.n_clusters * kRepStride;
-  uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_x) + repBytes(h.n_clusters));
+  __half* rep_y = rep_x + h.n_parked * kRepStride;
+  __half* rep_z = rep_y + h.n_parked * kRepStride;
+  // hierarchical cull: only the link-level centres are in shared memory (level 0 reads them for every link pair and state);
+  // the cluster-level centres, read once per level-1 candidate, live in this warp's global scratch (L1 / L2) -- they were
+  // 14 of the 26 KB of shared memory a warp of the 280-sphere dual arm took, i.e. 8 instead of 14 warps per SM
+  uint2* grep = kHier ? reinterpret_cast<uint2*>(a.rep_scratch + (static_cast<size_t>(blockIdx.x) * warps + warp) *
+                                                                    static_cast<size_t>(globalRepBytes(h.n_clusters)))
+                      : nullptr;  // [cluster][state] = { x | y << 16, z }: ONE 8-byte load per centre and candidate
+  uint32_t* queue = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(rep_x) + repBytes(h.n_parked));
   // the tile's states [state][var]: the wide instance stages them in the queue region (FK phase only), the others in two
   // buffers behind it that the TMA engine fills one tile ahead
   uint8_t* stage_base = reinterpret_cast<uint8_t*>(queue) + queueBytes(h.n_group_vars, kWide);
@@ -642,9 +652,26 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
           const float z = fmaf(T[8], cc.x, fmaf(T[9], cc.y, fmaf(T[10], cc.z, tbz)));
           if (__float_as_int(o.w) != 0 && fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z)) >= h.rep_limit)
             aacc = 1u;  // beyond the travel the host assumed for prismatic joints: the exact pass decides
-          rep_x[c * kRepStride + lane] = __float2half_rn(x);
-          rep_y[c * kRepStride + lane] = __float2half_rn(y);
-          rep_z[c * kRepStride + lane] = __float2half_rn(z);
+          if constexpr (kHier)
+          {
+            const int slot = __float_as_int(cc.w);  // Cluster::slot
+            if (slot >= 0)
+            {
+              rep_x[slot * kRepStride + lane] = __float2half_rn(x);
+              rep_y[slot * kRepStride + lane] = __float2half_rn(y);
+              rep_z[slot * kRepStride + lane] = __float2half_rn(z);
+            }
+            else
+              grep[c * 32 + lane] = make_uint2(static_cast<uint32_t>(__half_as_ushort(__float2half_rn(x))) |
+                                                   (static_cast<uint32_t>(__half_as_ushort(__float2half_rn(y))) << 16),
+                                               static_cast<uint32_t>(__half_as_ushort(__float2half_rn(z))));
+          }
+          else
+          {
+            rep_x[c * kRepStride + lane] = __float2half_rn(x);
+            rep_y[c * kRepStride + lane] = __float2half_rn(y);
+            rep_z[c * kRepStride + lane] = __float2half_rn(z);
+          }
         }
       }
       if (!do_fields)
@@ -832,9 +859,11 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
             const int s = cand & 31;
             const uint4 pc = reinterpret_cast<const uint4*>(m.pairs)[cand >> 5];
             const int ca = pc.y & 0xffffu, cb = pc.y >> 16;
-            const __half dx = __hsub(rep_x[ca * kRepStride + s], rep_x[cb * kRepStride + s]);
-            const __half dy = __hsub(rep_y[ca * kRepStride + s], rep_y[cb * kRepStride + s]);
-            const __half dz = __hsub(rep_z[ca * kRepStride + s], rep_z[cb * kRepStride + s]);
+            const uint2 ga = grep[ca * 32 + s], gb = grep[cb * 32 + s];
+            const __half2 dxy = __hsub2(*reinterpret_cast<const __half2*>(&ga.x), *reinterpret_cast<const __half2*>(&gb.x));
+            const __half dx = __low2half(dxy), dy = __high2half(dxy);
+            const __half dz = __hsub(__ushort_as_half(static_cast<unsigned short>(ga.y)),
+                                     __ushort_as_half(static_cast<unsigned short>(gb.y)));
             const __half dd = __hfma(dz, dz, __hfma(dy, dy, __hmul(dx, dx)));
             const bool live = have && __hlt(dd, __ushort_as_half(static_cast<unsigned short>(pc.x)));
             const unsigned mk = __ballot_sync(kFull, live);
@@ -976,6 +1005,7 @@ int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, in
 {
   return fastPerWarpBytes(state_stride, n_clusters, n_group_vars, n_linkpairs, wide);
 }
+int fastCheckRepBytes(int n_rows) { return globalRepBytes(n_rows); }
 int fastCheckMaxVars() { return kWideMaxVars; }
 int fastCheckRegisterPrefetchVars() { return kMaxVars; }  // beyond this (or with a planar joint) the wide instance runs
 int fastCheckMaxWarps(int n_group_vars) { return fastThreads(n_group_vars <= kSmallVars ? kSmallVars : kMaxVars) / 32; }

@@ -33,6 +33,7 @@ struct CheckArgs
   const uint32_t* list;  // exact pass from list (in)
   const unsigned* list_count;
   float* t_scratch;      // fast pass only: global-memory home of the link transforms (null: shared memory)
+  uint8_t* rep_scratch;  // fast pass, hierarchical cull only: per-warp home of the CLUSTER-level parked centres (halves)
   int hier;              // fast pass only: the blob carries LinkPair records (hierarchical cull)
   int n_group_vars;      // fast pass only: selects the kernel instance (register prefetch of the states)
   int wide;              // fast pass only: the wide instance (more than 16 variables, or a planar joint in the group)
@@ -150,6 +151,7 @@ cudaError_t launchFastCentres(const uint8_t* model, int model_bytes, const doubl
                               bool wide, float* scratch, float* out, int n_hot, cudaStream_t stream);
 int fastCheckKernelRegs(int field_bytes, int n_group_vars);
 int fastCheckPerWarpBytes(int state_stride, int n_clusters, int n_group_vars, int n_linkpairs, bool wide);
+int fastCheckRepBytes(int n_rows);  // bytes of one warp's global scratch of parked cluster centres (hierarchical cull)
 int fastCheckMaxVars();
 int fastCheckRegisterPrefetchVars();
 int fastCheckMaxWarps(int n_group_vars);  // __launch_bounds__ of the fast kernel instance that takes the group
