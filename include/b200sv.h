@@ -279,7 +279,12 @@ int b200sv_get_self_points(const b200sv_ctx* ctx, double* xyz, size_t cap_points
 int b200sv_fk_batch(b200sv_ctx* ctx, const double* q, size_t n_states, int precision_bits, double* link_T);
 /* Batched PlanningScene::checkCollision over n group-state vectors.  valid_bitmap: ceil(n/8) bytes (host),
  * bit (i % 8) of byte (i / 8) is 1 iff state i is collision-free under the selected checks.
- * Timed region of the end-to-end benchmark: H2D of q, kernels, D2H of the bitmap. */
+ * Timed region of the end-to-end benchmark: H2D of q, kernels, D2H of the bitmap.
+ * Small batches take short cuts that change the latency, never the answer: up to 32 states are ONE kernel launch with the
+ * states in the launch parameters and the results polled in mapped host memory; ONE state (a planner's per-state isValid)
+ * is answered by a kernel that stays resident on the context's stream for 200 us after its last answer (B200SV_LINGER_US;
+ * B200SV_LINGER=0 turns it off) and is fed through a mailbox in mapped host memory, so back-to-back calls pay no launch.
+ * Every other entry point of the context asks that kernel to leave first; it never outlives 20 ms. */
 int b200sv_check_batch(b200sv_ctx* ctx, const double* q, size_t n_states, uint32_t flags, uint8_t* valid_bitmap);
 /* Same with q and the bitmap resident in device memory; asynchronous on `cuda_stream`.
  * d_valid_bitmap must hold 4*ceil(n/32) bytes (whole 32-bit words are written). */

@@ -1196,25 +1196,18 @@ __global__ void __launch_bounds__(128) recheckWarpKernel(CheckArgs<FT> a)
 // copies.  The states arrive inside the kernel parameters (or, beyond 32 doubles, are read from mapped pinned host memory); one
 // CTA per state runs the exact FP64 check -- the arithmetic every FP32 decision is referred to anyway -- and lane 0 stores the
 // state's result byte (1 = valid, 0 = in collision) straight into mapped host memory, where the host is polling for it.
+// One state by one CTA of 128 threads, exact FP64: qs holds the state; returns nonzero when the state is in collision.
+// What is left after the launch is a chain of dependent latencies (sin / cos -> FK chain -> field gathers -> pair tests),
+// so the four warps shorten every link of that chain they can: the joints' sines and cosines in parallel, the spheres in
+// ONE pass of 128 lanes, the cluster pairs in two.
 template <typename FT>
-__global__ void __launch_bounds__(128) latencyCheckKernel(LatencyArgs<FT> a)
+__device__ __forceinline__ int oneStateByCta(const Smem<double>& m, double* T, const double* qs, double* sc, const void* field_v,
+                                             uint32_t flags)
 {
-  // ONE STATE PER CTA: what is left after the launch is a chain of dependent latencies (blob -> sin / cos -> FK chain ->
-  // field gathers -> pair tests -> the result's trip over PCIe), so the four warps shorten every link of that chain they can:
-  // the joints' sines and cosines in parallel, the spheres in ONE pass of 128 lanes, the cluster pairs in two.
-  extern __shared__ __align__(16) uint8_t smem[];
-  const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
   const ModelHeader<double>& h = *m.h;
-  double* T = reinterpret_cast<double*>(smem + h.total_bytes);
-  double* qs = T + a.state_stride;  // the state
-  double* sc = qs + 32;             // sin, cos per link
-  const bool do_world = (a.flags & 1u) != 0, do_self = (a.flags & 2u) != 0, do_intra = (a.flags & 4u) != 0;
-  const typename Combined<FT>::type* __restrict__ field = static_cast<const typename Combined<FT>::type*>(a.field);
-  const int state = blockIdx.x;
+  const bool do_world = (flags & 1u) != 0, do_self = (flags & 2u) != 0, do_intra = (flags & 4u) != 0;
+  const typename Combined<FT>::type* __restrict__ field = static_cast<const typename Combined<FT>::type*>(field_v);
   const int tid = threadIdx.x;
-  if (tid < h.n_group_vars)
-    qs[tid] = a.use_inline ? a.q_inline[state * h.n_group_vars + tid] : a.q[state * h.n_group_vars + tid];
-  __syncthreads();
   for (int l = tid; l < h.n_links; l += blockDim.x)
   {
     const LinkRec<double>& L = m.links[l];
@@ -1242,11 +1235,95 @@ __global__ void __launch_bounds__(128) latencyCheckKernel(LatencyArgs<FT> a)
       if (live)
         pairItem<double>(m, T, pr, certain, hit, amb);
     }
-  const int any = __syncthreads_or(hit ? 1 : 0);
+  return __syncthreads_or(hit ? 1 : 0);
+}
+
+template <typename FT>
+__global__ void __launch_bounds__(128) latencyCheckKernel(LatencyArgs<FT> a)
+{
+  // ONE STATE PER CTA
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
+  const ModelHeader<double>& h = *m.h;
+  double* T = reinterpret_cast<double*>(smem + h.total_bytes);
+  double* qs = T + a.state_stride;  // the state
+  double* sc = qs + 32;             // sin, cos per link
+  const int state = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < h.n_group_vars)
+    qs[tid] = a.use_inline ? a.q_inline[state * h.n_group_vars + tid] : a.q[state * h.n_group_vars + tid];
+  __syncthreads();
+  const int any = oneStateByCta<FT>(m, T, qs, sc, a.field, a.flags);
   if (tid == 0)
   {
     a.result[state] = any ? 0 : 1;
     __threadfence_system();
+  }
+}
+
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One CTA that answers its first request (state in the parameters), then keeps polling the mailbox for the next one until
+// nothing has arrived for linger_ns, the host asks it to quit, or life_ns have passed since the launch.  The model blob is
+// staged into shared memory once.  Thread 0 polls (one 16-byte read of {req, quit} over PCIe per round); a new request's
+// state is then read by V lanes at once (one more round trip), and the answer is ONE 8-byte store the host is polling for.
+template <typename FT>
+__global__ void __launch_bounds__(128) lingerCheckKernel(LingerArgs<FT> a)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ unsigned long long s_req;
+  const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
+  const ModelHeader<double>& h = *m.h;
+  double* T = reinterpret_cast<double*>(smem + h.total_bytes);
+  double* qs = T + a.state_stride;
+  double* sc = qs + 32;
+  const int tid = threadIdx.x;
+  const unsigned long long t_start = globalTimerNs();
+  unsigned long long t_last = t_start, served = a.first_req >> 3;
+  unsigned long long req = a.first_req;
+  if (tid < h.n_group_vars)
+    qs[tid] = a.q_inline[tid];
+  __syncthreads();
+  for (;;)
+  {
+    const int any = oneStateByCta<FT>(m, T, qs, sc, a.field, static_cast<uint32_t>(req & 7u));
+    if (tid == 0)
+    {
+      *reinterpret_cast<volatile unsigned long long*>(&a.mail->done) = ((req >> 3) << 8) | (any ? 0ull : 1ull);
+      __threadfence_system();
+      served = req >> 3;
+      t_last = globalTimerNs();
+      // wait for the next request
+      unsigned long long next = 0ull;
+      for (;;)
+      {
+        const unsigned long long now = globalTimerNs();
+        if (now - t_start > a.life_ns)
+          break;  // whatever the host does: the host stops posting to a kernel this old and launches a new one
+        unsigned long long r, qt;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r), "=l"(qt) : "l"(&a.mail->req) : "memory");
+        if ((r >> 3) > served)
+        {
+          next = r;
+          break;
+        }
+        if (qt == a.epoch || now - t_last > a.linger_ns)
+          break;
+      }
+      s_req = next;
+    }
+    __syncthreads();
+    req = s_req;
+    if (req == 0ull)
+      break;
+    if (tid < h.n_group_vars)
+      qs[tid] = *reinterpret_cast<const volatile double*>(&a.mail->q[tid]);
+    __syncthreads();
   }
 }
 
@@ -1322,6 +1399,21 @@ cudaError_t launchLatencyCheck(const LatencyArgs<FT>& a, cudaStream_t stream)
 }
 template cudaError_t launchLatencyCheck<uint8_t>(const LatencyArgs<uint8_t>&, cudaStream_t);
 template cudaError_t launchLatencyCheck<uint16_t>(const LatencyArgs<uint16_t>&, cudaStream_t);
+
+template <typename FT>
+cudaError_t launchLingerCheck(const LingerArgs<FT>& a, cudaStream_t stream)
+{
+  static SmemGrant g;
+  const size_t smem = ((static_cast<size_t>(a.model_bytes) + 15) & ~static_cast<size_t>(15)) +
+                      static_cast<size_t>(a.state_stride + 32 + 2 * a.n_links) * sizeof(double);
+  cudaError_t e = ensureSmem(lingerCheckKernel<FT>, smem, g);
+  if (e != cudaSuccess)
+    return e;
+  lingerCheckKernel<FT><<<1, 128, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+template cudaError_t launchLingerCheck<uint8_t>(const LingerArgs<uint8_t>&, cudaStream_t);
+template cudaError_t launchLingerCheck<uint16_t>(const LingerArgs<uint16_t>&, cudaStream_t);
 
 int checkPerWarpBytes(bool fp64, int state_stride)
 {

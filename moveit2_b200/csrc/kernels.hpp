@@ -75,6 +75,34 @@ struct LatencyArgs
 };
 template <typename FT>
 cudaError_t launchLatencyCheck(const LatencyArgs<FT>& a, cudaStream_t stream);
+
+// The same check for ONE state at a time, by a kernel that stays resident for a short while after it has answered: a planner
+// validates states back to back (OMPL's per-state isValid), and every call after the first finds the kernel already
+// running -- no launch, the request and the answer travel through a mailbox in mapped pinned host memory.
+struct LingerMailbox  // mapped pinned host memory, 16-byte aligned
+{
+  unsigned long long req;   // host -> kernel: (sequence number << 3) | check flags of the newest request
+  unsigned long long quit;  // host -> kernel: the epoch of the kernel that should exit now
+  unsigned long long done;  // kernel -> host: (sequence number << 8) | result (1 = valid, 0 = in collision)
+  unsigned long long pad;
+  double q[32];             // the request's state
+};
+template <typename FT>
+struct LingerArgs
+{
+  const uint8_t* model;  // double blob
+  int model_bytes;
+  const void* field;
+  int state_stride, n_links;
+  LingerMailbox* mail;               // device-visible
+  unsigned long long first_req;      // the request this launch answers first (its state is q_inline)
+  unsigned long long epoch;          // exit when mail->quit == epoch
+  unsigned long long linger_ns;      // exit this long after the last answer
+  unsigned long long life_ns;        // exit this long after the launch, whatever happens
+  double q_inline[32];
+};
+template <typename FT>
+cudaError_t launchLingerCheck(const LingerArgs<FT>& a, cudaStream_t stream);
 int checkKernelRegs(bool fp64, bool from_list, int field_bytes);
 int checkPerWarpBytes(bool fp64, int state_stride);  // shared memory one warp of the check kernel needs
 // One link's PosedDistanceField on the device: 16-bit d^2 on its own small grid in the LINK frame

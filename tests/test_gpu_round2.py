@@ -628,3 +628,62 @@ def test_compact_field_survives_rebuilds_of_either_field_in_any_order():
     eng.set_base_state(env.base_positions)
     both_ok("self rebuilt next to an injected world field")
     eng.close()
+
+
+# ---- single states back to back: the resident kernel and its mailbox ------------------------------------------------------
+def test_single_states_back_to_back_through_the_resident_kernel():
+    """n = 1 calls are answered by a kernel that stays resident for a short while (b200sv_check_batch -> checkLinger): every
+    answer equals the oracle's, other entry points in between make the kernel step aside (field rebuilds change what it must
+    read), and after an idle gap the next call simply launches a new one."""
+    import time
+    eng, env, cloud, q = config_pair("C1", n_states=3000)
+    env.world.add_points(cloud)
+    eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+    eng.field_set_d2(env.self_field.d2(), mb.FIELD_SELF)
+    ref, _ = env.check(q, ALL)
+    got = np.array([eng.check_batch(q[i:i + 1], ALL)[0] for i in range(1500)])
+    assert np.array_equal(got, ref[:1500] == 0)
+    assert eng.stats()["n_states"] == 1
+    for flags in (mb.CHECK_WORLD, mb.CHECK_SELF, mb.CHECK_INTRA):
+        r, _ = env.check(q[:200], flags)
+        assert np.array_equal(np.array([eng.check_batch(q[i:i + 1], flags)[0] for i in range(200)]), r == 0), flags
+    # the world changes between single-state calls: the resident kernel must not answer from the old field
+    extra = workloads.clutter_cloud(9, 1500, 3, (-0.4, -0.4, 0.2), (0.4, 0.4, 0.9), 0.15, floor=False)
+    env.world.add_points(extra)
+    for i in range(1500, 1600):
+        if i == 1550:
+            eng.field_set_d2(env.world.d2(), mb.FIELD_WORLD)
+            ref2, _ = env.check(q, ALL)
+            assert (ref2[1550:1700] != ref[1550:1700]).any(), "the added cloud should change some answers"
+        want = (ref if i < 1550 else ref2)[i] == 0
+        assert eng.check_batch(q[i:i + 1], ALL)[0] == want, i
+    # batches, edges and device-stream calls in between; idle gaps longer than the kernel's linger window
+    for i in range(1600, 1700):
+        if i % 10 == 0:
+            assert np.array_equal(eng.check_batch(q[:300], ALL), ref2[:300] == 0)
+        if i % 25 == 0:
+            time.sleep(0.002)
+        assert eng.check_batch(q[i:i + 1], ALL)[0] == (ref2[i] == 0), i
+    eng.close()
+
+
+def test_resident_kernels_of_two_contexts_from_two_threads():
+    import threading
+    pairs = [config_pair("C1", n_states=600) for _ in range(2)]
+    out = [None, None]
+
+    def work(k):
+        eng, env, cloud, q = pairs[k]
+        eng.field_add_points(cloud[: 1000 * (k + 1)])
+        batch = eng.check_batch(q, ALL)
+        single = np.array([eng.check_batch(q[i:i + 1], ALL)[0] for i in range(len(q))])
+        out[k] = np.array_equal(batch, single)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=120)
+    assert out == [True, True]
+    for eng, _, _, _ in pairs:
+        eng.close()

@@ -80,6 +80,46 @@ int main(int argc, char** argv)
     qsort(t, 400, sizeof(double), cmp);
     printf(", \"n=%d\": {\"median_us\": %.1f, \"p90_us\": %.1f}", sizes[k], t[200], t[360]);
   }
+  {
+    /* single states the way a planner issues them: a different state every call, back to back; then the same with a pause
+     * that lets the resident kernel expire before every call; then the answers against ONE batch call over the same states */
+    static double ts[2000];
+    static uint8_t one[8], other[8], all[4096 / 8];
+    int bad = 0;
+    struct timespec pause = { 0, 1000000 };  /* 1 ms */
+    for (i = 0; i < 2000; ++i)
+    {
+      const double t0 = now_us();
+      if (b200sv_check_batch(ctx, q + 7 * (i % 4096), 1, B200SV_CHECK_ALL, one) != B200SV_OK)
+        return 6;
+      ts[i] = now_us() - t0;
+    }
+    qsort(ts, 2000, sizeof(double), cmp);
+    printf(", \"n=1, a new state every call, back to back\": {\"median_us\": %.1f, \"p90_us\": %.1f, \"p99_us\": %.1f}", ts[1000],
+           ts[1800], ts[1980]);
+    for (i = 0; i < 200; ++i)
+    {
+      double t0;
+      nanosleep(&pause, NULL);
+      t0 = now_us();
+      if (b200sv_check_batch(ctx, q + 7 * (i % 4096), 1, B200SV_CHECK_ALL, one) != B200SV_OK)
+        return 6;
+      ts[i] = now_us() - t0;
+    }
+    qsort(ts, 200, sizeof(double), cmp);
+    printf(", \"n=1, 1 ms idle before every call\": {\"median_us\": %.1f, \"p90_us\": %.1f}", ts[100], ts[180]);
+    if (b200sv_check_batch(ctx, q, 4096, B200SV_CHECK_ALL, all) != B200SV_OK)
+      return 7;
+    for (i = 0; i < 4096; ++i)
+    {
+      if (b200sv_check_batch(ctx, q + 7 * i, 1, B200SV_CHECK_ALL, one) != B200SV_OK)
+        return 8;
+      bad += (one[0] & 1) != ((all[i >> 3] >> (i & 7)) & 1);
+      if ((i & 255) == 255)  /* other entry points in between: the resident kernel must step aside and come back */
+        b200sv_check_batch(ctx, q, 64, B200SV_CHECK_ALL, other);
+    }
+    printf(", \"single_state_answers_differing_from_the_batch\": %d", bad);
+  }
   printf("}\n");
   b200sv_destroy(ctx);
   return 0;
