@@ -174,6 +174,8 @@ struct b200sv_ctx
   uint8_t* d_lat = nullptr;        // its device-side address
   bool latency_ok = false;         // the exact blob + 4 warps of transforms fit shared memory, V <= 32
   // single states back to back: a kernel that stays resident for a short while and is fed through a mailbox (checkLinger)
+  uint8_t* h_edge_lat = nullptr;    // mapped pinned memory of the few-edges path: the edges' ends, then result bytes
+  uint8_t* d_edge_lat = nullptr;
   LingerMailbox* h_mail = nullptr;  // mapped pinned
   LingerMailbox* d_mail = nullptr;
   unsigned long long mail_seq = 0, linger_epoch = 0;
@@ -2098,6 +2100,7 @@ void b200sv_destroy(b200sv_ctx* c)
   if (c->h_small) cudaFreeHost(c->h_small);
   if (c->h_count) cudaFreeHost(c->h_count);
   if (c->h_mail) cudaFreeHost(c->h_mail);
+  if (c->h_edge_lat) cudaFreeHost(c->h_edge_lat);
   if (c->h_lat) cudaFreeHost(c->h_lat);
   if (c->d_small) cudaFree(c->d_small);
   if (c->d_blob_f) cudaFree(c->d_blob_f);
@@ -3196,6 +3199,139 @@ int b200sv_check_batch(b200sv_ctx* c, const double* q, size_t n, uint32_t flags,
   return checkHostFinish(c, n, flags, valid_bitmap);
 }
 
+// A few edges, ONE launch (an OMPL MotionValidator validates one edge per checkMotion, and the general path below costs two
+// stream synchronisations: the batch is sized on the device).  Here the host sizes it -- the state counts are the arithmetic of
+// motionCountKernel, operation for operation -- and launches one CTA per visited state (edgeLatencyKernel); the ends travel in
+// the launch parameters (one edge) or are read from mapped host memory, the result bytes are polled there.
+// Returns 1 when the call does not qualify (more than 1 024 states, a group of more than 32 variables): the general path takes it.
+constexpr unsigned kEdgeLatencyStates = 1024;  // measured break-even with the general path: ~1 400 states (64 edges)
+static int checkMotionsLatency(b200sv_ctx* c, const double* q_from, const double* q_to, size_t n_edges, double max_segment_length,
+                               const uint8_t* var_continuous, const double* var_distance_factor, uint32_t max_states_per_edge,
+                               uint32_t flags, uint8_t* valid_bitmap, int32_t* first_invalid, uint64_t* n_states_checked)
+{
+  const double kPi = 3.14159265358979323846;
+  const size_t V = c->robot.group_var_index.size();
+  if (V > 32 || n_edges > (size_t)kEdgeLatencyEdges)
+    return 1;
+  uint32_t offsets[kEdgeLatencyEdges + 1];
+  offsets[0] = 0;
+  for (size_t e = 0; e < n_edges; ++e)
+  {
+    const double *f = q_from + e * V, *t = q_to + e * V;
+    double d = 0.0;
+    for (size_t k = 0; k < V; ++k)
+    {
+      const double w = var_distance_factor ? var_distance_factor[k] : 1.0;
+      if (w == 0.0)
+        continue;
+      double dk = fabs(f[k] - t[k]);
+      if (var_continuous && var_continuous[k])
+      {
+        dk = fmod(dk, 2.0 * kPi);
+        dk = dk > kPi ? 2.0 * kPi - dk : dk;
+      }
+      const volatile double prod = w * dk;  // two roundings, as __dadd_rn(d, __dmul_rn(w, dk)) on the device
+      d = d + prod;
+    }
+    const double nd = ceil(d / max_segment_length);
+    unsigned cnt = nd < 1.0 ? 1u : (nd > 4.0e9 ? 0xffffffffu : static_cast<unsigned>(nd));
+    if (max_states_per_edge && cnt > max_states_per_edge)
+      cnt = max_states_per_edge;
+    if (cnt > kEdgeLatencyStates || offsets[e] + cnt > kEdgeLatencyStates)
+      return 1;
+    offsets[e + 1] = offsets[e] + cnt;
+  }
+  const unsigned total = offsets[n_edges];
+  const size_t ends_cap = 2 * (size_t)kEdgeLatencyEdges * 32 * sizeof(double);
+  if (!c->h_edge_lat)
+  {
+    CU(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_edge_lat), ends_cap + kEdgeLatencyStates, cudaHostAllocMapped));
+    CU(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_edge_lat), c->h_edge_lat, 0));
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  volatile uint8_t* res = c->h_edge_lat + ends_cap;
+  for (unsigned i = 0; i < total; ++i)
+    res[i] = 0xff;
+  auto fill = [&](auto& a) {
+    a.model = c->d_blob_d;
+    a.model_bytes = (int)c->blob_d.size();
+    a.field = c->d_combined;
+    a.flags = flags & 7u;
+    a.state_stride = c->state_stride_d;
+    a.n_links = c->n_dev_links;
+    a.n_edges = (int)n_edges;
+    a.n_vars = (int)V;
+    a.cont_mask = 0u;
+    for (size_t k = 0; k < V; ++k)
+      if (var_continuous && var_continuous[k])
+        a.cont_mask |= 1u << k;
+    a.use_inline = n_edges == 1 ? 1 : 0;
+    a.ends = reinterpret_cast<const double*>(c->d_edge_lat);
+    a.result = c->d_edge_lat + ends_cap;
+    memcpy(a.offsets, offsets, (n_edges + 1) * sizeof(uint32_t));
+    if (a.use_inline)
+    {
+      memcpy(a.ends_inline, q_from, V * sizeof(double));
+      memcpy(a.ends_inline + V, q_to, V * sizeof(double));
+    }
+    else
+    {
+      memcpy(c->h_edge_lat, q_from, n_edges * V * sizeof(double));
+      memcpy(c->h_edge_lat + n_edges * V * sizeof(double), q_to, n_edges * V * sizeof(double));
+    }
+  };
+  if (c->compact_bytes == 1)
+  {
+    EdgeLatencyArgs<uint8_t> a{};
+    fill(a);
+    CU(c, launchEdgeLatencyCheck<uint8_t>(a, c->stream));
+  }
+  else
+  {
+    EdgeLatencyArgs<uint16_t> a{};
+    fill(a);
+    CU(c, launchEdgeLatencyCheck<uint16_t>(a, c->stream));
+  }
+  bool done = false;
+  for (long spin = 0; spin < 4000000L && !done; ++spin)
+  {
+    done = true;
+    for (unsigned i = total; i-- > 0;)  // CTAs finish roughly in order: the last byte turns last
+      if (res[i] == 0xff)
+      {
+        done = false;
+        break;
+      }
+  }
+  if (!done)
+  {
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (unsigned i = 0; i < total; ++i)
+      if (res[i] == 0xff)
+        return fail(c, B200SV_ERR_CUDA, "few-edges path: the kernel finished without writing a result");
+  }
+  memset(valid_bitmap, 0, (n_edges + 7) / 8);
+  for (size_t e = 0; e < n_edges; ++e)
+  {
+    int bad = -1;
+    for (unsigned i = offsets[e]; i < offsets[e + 1] && bad < 0; ++i)
+      if (res[i] == 0)
+        bad = (int)(i - offsets[e]) + 1;  // j of the first invalid state, 1 .. count
+    if (bad < 0)
+      valid_bitmap[e >> 3] |= (uint8_t)(1u << (e & 7));
+    if (first_invalid)
+      first_invalid[e] = bad;
+  }
+  if (n_states_checked)
+    *n_states_checked = total;
+  c->stats.n_states = total;
+  c->stats.n_valid = 0;
+  c->stats.n_rechecked = total;  // every state of this path is decided by the exact FP64 arithmetic
+  c->stats.check_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  c->stats_pending = false;
+  return B200SV_OK;
+}
+
 int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to, size_t n_edges, double max_segment_length,
                          const uint8_t* var_continuous, const double* var_distance_factor, uint32_t max_states_per_edge,
                          uint32_t flags, uint8_t* valid_bitmap, int32_t* first_invalid, uint64_t* n_states_checked)
@@ -3228,6 +3364,14 @@ int b200sv_check_motions(b200sv_ctx* c, const double* q_from, const double* q_to
     return B200SV_OK;
   std::lock_guard<std::mutex> lk(c->mu);
   enterCtx(c);
+  static const bool edge_latency_on = !(getenv("B200SV_EDGE_LATENCY") && atoi(getenv("B200SV_EDGE_LATENCY")) == 0);
+  if (edge_latency_on && n_edges <= (size_t)kEdgeLatencyEdges && c->latency_ok && !(flags & B200SV_CHECK_FP64))
+  {
+    const int rc = checkMotionsLatency(c, q_from, q_to, n_edges, max_segment_length, var_continuous, var_distance_factor,
+                                       max_states_per_edge, flags, valid_bitmap, first_invalid, n_states_checked);
+    if (rc != 1)
+      return rc;
+  }
   const size_t V = c->robot.group_var_index.size();
   cudaStream_t s = c->stream;
   CU(c, c->d_edges.ensure(2 * n_edges * V));

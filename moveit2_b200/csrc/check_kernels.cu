@@ -1261,6 +1261,58 @@ __global__ void __launch_bounds__(128) latencyCheckKernel(LatencyArgs<FT> a)
   }
 }
 
+// One CTA per visited state of a few edges: state j / c of edge e by JointModelGroup::interpolate (joint_model_group.cpp:474-486;
+// continuous revolute joints along the shorter arc, revolute_joint_model.cpp:138-171) -- the arithmetic of motionExpandKernel,
+// roundings included -- then the exact check.
+template <typename FT>
+__global__ void __launch_bounds__(128) edgeLatencyKernel(EdgeLatencyArgs<FT> a)
+{
+  constexpr double kPi = 3.14159265358979323846;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Smem<double> m = loadModel<double>(a.model, a.model_bytes, smem);
+  const ModelHeader<double>& h = *m.h;
+  double* T = reinterpret_cast<double*>(smem + h.total_bytes);
+  double* qs = T + a.state_stride;
+  double* sc = qs + 32;
+  const int tid = threadIdx.x;
+  const unsigned s = blockIdx.x;
+  int e = 0;
+  while (e + 1 < a.n_edges && a.offsets[e + 1] <= s)
+    ++e;
+  const unsigned c = a.offsets[e + 1] - a.offsets[e], j = s - a.offsets[e] + 1u;  // 1 .. c
+  if (tid < a.n_vars)
+  {
+    const double f = a.use_inline ? a.ends_inline[tid] : a.ends[static_cast<size_t>(e) * a.n_vars + tid];
+    const double t = a.use_inline ? a.ends_inline[a.n_vars + tid]
+                                  : a.ends[(static_cast<size_t>(a.n_edges) + e) * a.n_vars + tid];
+    double v = t;  // j == c: s2 itself
+    if (j != c)
+    {
+      const double tt = static_cast<double>(j) / static_cast<double>(c);
+      double diff = __dsub_rn(t, f);
+      if (((a.cont_mask >> tid) & 1u) && fabs(diff) > kPi)
+      {
+        diff = diff > 0.0 ? __dsub_rn(2.0 * kPi, diff) : __dsub_rn(-2.0 * kPi, diff);
+        v = __dsub_rn(f, __dmul_rn(diff, tt));
+        if (v > kPi)
+          v = __dsub_rn(v, 2.0 * kPi);
+        else if (v < -kPi)
+          v = __dadd_rn(v, 2.0 * kPi);
+      }
+      else
+        v = __dadd_rn(f, __dmul_rn(diff, tt));
+    }
+    qs[tid] = v;
+  }
+  __syncthreads();
+  const int any = oneStateByCta<FT>(m, T, qs, sc, a.field, a.flags);
+  if (tid == 0)
+  {
+    a.result[s] = any ? 0 : 1;
+    __threadfence_system();
+  }
+}
+
 __device__ __forceinline__ unsigned long long globalTimerNs()
 {
   unsigned long long t;
@@ -1399,6 +1451,21 @@ cudaError_t launchLatencyCheck(const LatencyArgs<FT>& a, cudaStream_t stream)
 }
 template cudaError_t launchLatencyCheck<uint8_t>(const LatencyArgs<uint8_t>&, cudaStream_t);
 template cudaError_t launchLatencyCheck<uint16_t>(const LatencyArgs<uint16_t>&, cudaStream_t);
+
+template <typename FT>
+cudaError_t launchEdgeLatencyCheck(const EdgeLatencyArgs<FT>& a, cudaStream_t stream)
+{
+  static SmemGrant g;
+  const size_t smem = ((static_cast<size_t>(a.model_bytes) + 15) & ~static_cast<size_t>(15)) +
+                      static_cast<size_t>(a.state_stride + 32 + 2 * a.n_links) * sizeof(double);
+  cudaError_t e = ensureSmem(edgeLatencyKernel<FT>, smem, g);
+  if (e != cudaSuccess)
+    return e;
+  edgeLatencyKernel<FT><<<a.offsets[a.n_edges], 128, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+template cudaError_t launchEdgeLatencyCheck<uint8_t>(const EdgeLatencyArgs<uint8_t>&, cudaStream_t);
+template cudaError_t launchEdgeLatencyCheck<uint16_t>(const EdgeLatencyArgs<uint16_t>&, cudaStream_t);
 
 template <typename FT>
 cudaError_t launchLingerCheck(const LingerArgs<FT>& a, cudaStream_t stream)

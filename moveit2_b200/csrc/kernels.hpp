@@ -87,6 +87,27 @@ struct LingerMailbox  // mapped pinned host memory, 16-byte aligned
   unsigned long long pad;
   double q[32];             // the request's state
 };
+// A few edges (an OMPL MotionValidator validates ONE per checkMotion): the host sizes the batch itself, one CTA per visited
+// state interpolates its own state from the edge's ends and runs the exact check; result bytes polled in mapped host memory.
+constexpr int kEdgeLatencyEdges = 64;
+template <typename FT>
+struct EdgeLatencyArgs
+{
+  const uint8_t* model;  // double blob
+  int model_bytes;
+  const void* field;
+  uint32_t flags;
+  int state_stride, n_links, n_edges, n_vars;
+  uint32_t cont_mask;        // bit k: group variable k is a continuous revolute joint (interpolated along the shorter arc)
+  int use_inline;            // one edge: its ends are ends_inline (from, then to); else `ends`
+  const double* ends;        // device-visible (mapped pinned host) [2 * n_edges * n_vars]: all from rows, then all to rows
+  uint8_t* result;           // device-visible (mapped pinned host) [offsets[n_edges]]: 1 = valid, 0 = in collision
+  uint32_t offsets[kEdgeLatencyEdges + 1];  // exclusive scan of the edges' state counts
+  double ends_inline[64];
+};
+template <typename FT>
+cudaError_t launchEdgeLatencyCheck(const EdgeLatencyArgs<FT>& a, cudaStream_t stream);
+
 template <typename FT>
 struct LingerArgs
 {

@@ -687,3 +687,44 @@ def test_resident_kernels_of_two_contexts_from_two_threads():
     assert out == [True, True]
     for eng, _, _, _ in pairs:
         eng.close()
+
+
+# ---- a few edges per call: ONE launch, the batch sized on the host --------------------------------------------------------
+def test_a_few_edges_per_call_take_one_launch_and_equal_the_oracle(c1):
+    """b200sv_check_motions with up to 64 edges (an OMPL MotionValidator validates one per checkMotion): the host computes the
+    edges' state counts itself and launches one CTA per visited state.  Same answers as the oracle's edge restatement and as
+    the general (device-sized) path, continuous joints, passive variables and the per-edge cap included."""
+    from oracle import motion
+    eng, env, cloud, q = c1
+    lo, hi = eng.group_bounds()
+    V = len(lo)
+    rng = np.random.default_rng(11)
+    m = 192
+    a = rng.uniform(lo, hi, size=(m, V))
+    b = np.where(rng.random((m, 1)) < 0.5, rng.uniform(lo, hi, size=(m, V)), np.clip(a + rng.normal(0, 0.05, size=(m, V)), lo, hi))
+    b[5] = a[5]                                   # a zero-length edge: one state (its end)
+    a[:, 0] = rng.uniform(-np.pi, np.pi, m)
+    b[:, 0] = rng.uniform(-np.pi, np.pi, m)
+    cont = np.zeros(V, np.uint8)
+    cont[0] = 1
+    fac = np.ones(V)
+    fac[3] = 0.0
+    L = 0.01 * float(np.sum(hi - lo))
+    for args in ((None, None, 0), (cont, fac, 0), (cont, fac, 5)):
+        rv, rf, rn = motion.check_motions(env, a, b, L, *args)
+        big_v, big_f, big_n = eng.check_motions(a, b, L, *args)          # 192 edges: the general path
+        assert big_n == rn and np.array_equal(big_v, rv) and np.array_equal(big_f, rf)
+        for per_call in (1, 7, 64):
+            got_v, got_f, got_n = [], [], 0
+            for i0 in range(0, m, per_call):
+                v, f, n = eng.check_motions(a[i0:i0 + per_call], b[i0:i0 + per_call], L, *args)
+                got_v.append(v)
+                got_f.append(f)
+                got_n += n
+            assert got_n == rn, (per_call, args[2])
+            assert np.array_equal(np.concatenate(got_v), rv) and np.array_equal(np.concatenate(got_f), rf), (per_call, args[2])
+    assert 0 < rv.sum() < m
+    # an edge too long for the few-edges path (more than 1024 states) silently takes the general one
+    v, f, n = eng.check_motions(a[:1], b[:1], L / 4000.0)
+    rv1, rf1, rn1 = motion.check_motions(env, a[:1], b[:1], L / 4000.0)
+    assert n == rn1 and n > 4096 and np.array_equal(v, rv1) and np.array_equal(f, rf1)
