@@ -532,7 +532,25 @@ def main():
             eng.check_batch_ptr(qq.ctypes.data, nb, flags, bmp.ctypes.data)
             ts.append(time.perf_counter() - t1)
         lat["n=%d" % nb] = {"median_us": 1e6 * float(np.median(ts)), "p90_us": 1e6 * float(np.percentile(ts, 90))}
-    lat["how"] = "wall clock around b200sv_check_batch from Python ctypes (adds ~1 us), pageable host buffers"
+    # a new state every call, back to back (a planner's per-state isValid): the resident kernel answers without a launch
+    ts = []
+    for i in range(1000):
+        qq = q_host[i:i + 1]
+        t1 = time.perf_counter()
+        eng.check_batch_ptr(qq.ctypes.data, 1, flags, bmp.ctypes.data)
+        ts.append(time.perf_counter() - t1)
+    lat["n=1, a new state every call"] = {"median_us": 1e6 * float(np.median(ts)), "p90_us": 1e6 * float(np.percentile(ts, 90))}
+    # ONE edge per b200sv_check_motions call (an OMPL MotionValidator::checkMotion): one launch, the batch sized on the host
+    ts, n_exp1 = [], 0
+    for i in range(300):
+        t1 = time.perf_counter()
+        _, _, n1 = eng.check_motions(q_host[i:i + 1], q_host[1000 + i:1001 + i], seg)
+        ts.append(time.perf_counter() - t1)
+        n_exp1 += n1
+    lat["one edge per check_motions call"] = {"median_us": 1e6 * float(np.median(ts[20:])), "p90_us": 1e6 * float(np.percentile(ts[20:], 90)),
+                                              "states_per_edge": n_exp1 / 300.0}
+    lat["how"] = ("wall clock around b200sv_check_batch / b200sv_check_motions from Python ctypes and numpy (adds 1-3 us; "
+                  "tools/c_latency.c and tools/c_edge_latency.c measure from C), pageable host buffers")
     line["latency"] = lat
 
     # ---- parity inside the run + CPU baseline (rank 0, bounded) ----------------------------------------------------------
