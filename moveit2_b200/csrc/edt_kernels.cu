@@ -28,6 +28,14 @@ namespace b200sv
 {
 namespace
 {
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may become
+// resident while the kernel before it in the stream drains -- its CTAs run their prologue and then block in depWait()
+// until that kernel has completed and its writes are visible.  Nothing of the context's global state may be read OR
+// written before depWait().  depLaunch() lets the NEXT kernel's CTAs in once every CTA of this one has called it.
+// Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void depWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void depLaunch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __global__ void __launch_bounds__(256) scatterKernel(const double* __restrict__ xyz, size_t n, GridDev g,
                                                      uint32_t* __restrict__ occ, int set)
 {
@@ -35,6 +43,7 @@ __global__ void __launch_bounds__(256) scatterKernel(const double* __restrict__ 
   // every lane picks up its own point (stride 3 doubles: conflict-free).  Reading xyz[3 i + k] straight from global memory
   // touched every sector three times.
   __shared__ double sh[8][96];
+  depLaunch();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t n_tiles = (n + 31) / 32;
   const size_t stride = static_cast<size_t>(gridDim.x) * 8;
@@ -77,6 +86,105 @@ __global__ void __launch_bounds__(256) scatterKernel(const double* __restrict__ 
     const int z = static_cast<int>(floor((pz - g.om[2]) * g.oo));
     if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz)
       continue;  // isCellValid (voxel_grid.hpp:405-408)
+    uint32_t* w = occ + (static_cast<size_t>(x) * g.ny + y) * g.wz + (z >> 5);
+    if (set)
+      atomicOr(w, 1u << (z & 31));
+    else
+      atomicAnd(w, ~(1u << (z & 31)));
+  }
+}
+
+// ---- 1-D bulk copies global -> shared memory through the TMA engine, completion on an mbarrier (sm_90+ PTX) ----------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)),
+               "l"(src), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity)
+{
+  unsigned ok = 0;
+  const uint32_t a = smemAddr(bar);
+  do
+  {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+// scatterKernel with the point tiles staged by the TMA engine: every warp owns kScatterStages buffers of one tile (32 points =
+// 768 bytes) and keeps kScatterStages - 1 bulk copies in flight, so the atomics of a tile never wait for its points (the
+// register prefetch of scatterKernel covers one tile: ncu still showed long_scoreboard as its first stall).  Whole tiles of
+// a 16-byte aligned cloud only; the ragged last tile is read with plain loads by the warp whose turn it is.
+constexpr int kScatterStages = 4;
+__global__ void __launch_bounds__(256) scatterKernelTma(const double* __restrict__ xyz, size_t n, GridDev g,
+                                                        uint32_t* __restrict__ occ, int set)
+{
+  __shared__ __align__(16) double sh[8][kScatterStages][96];
+  __shared__ uint64_t bars[8][kScatterStages];
+  depLaunch();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t n_tiles = (n + 31) / 32, n_full = n / 32;
+  const size_t stride = static_cast<size_t>(gridDim.x) * 8;
+  const size_t t0 = blockIdx.x * static_cast<size_t>(8) + warp;
+  if (lane == 0)
+  {
+    for (int b = 0; b < kScatterStages; ++b)
+      mbarInit(&bars[warp][b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto fetch = [&](size_t it) {  // lane 0 only
+    const size_t t = t0 + it * stride;
+    if (t < n_full)
+      bulkLoad(sh[warp][it % kScatterStages], xyz + 96 * t, 768u, &bars[warp][it % kScatterStages]);
+  };
+  if (lane == 0)
+    for (int it = 0; it < kScatterStages - 1; ++it)
+      fetch(it);
+  size_t it = 0;
+  for (size_t t = t0; t < n_tiles; t += stride, ++it)
+  {
+    const int b = static_cast<int>(it % kScatterStages);
+    if (lane == 0)
+    {
+      // the buffer about to be refilled was read with ordinary loads an iteration ago: order those before the async writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fetch(it + kScatterStages - 1);
+    }
+    double px, py, pz;
+    bool have = true;
+    if (t < n_full)
+    {
+      mbarWait(&bars[warp][b], static_cast<unsigned>((it / kScatterStages) & 1));
+      px = sh[warp][b][3 * lane];
+      py = sh[warp][b][3 * lane + 1];
+      pz = sh[warp][b][3 * lane + 2];
+    }
+    else
+    {
+      const size_t i = 32 * t + lane;
+      have = i < n;
+      px = have ? xyz[3 * i] : 0.0;
+      py = have ? xyz[3 * i + 1] : 0.0;
+      pz = have ? xyz[3 * i + 2] : 0.0;
+    }
+    __syncwarp();
+    if (!have)
+      continue;
+    const int x = static_cast<int>(floor((px - g.om[0]) * g.oo));
+    const int y = static_cast<int>(floor((py - g.om[1]) * g.oo));
+    const int z = static_cast<int>(floor((pz - g.om[2]) * g.oo));
+    if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz)
+      continue;
     uint32_t* w = occ + (static_cast<size_t>(x) * g.ny + y) * g.wz + (z >> 5);
     if (set)
       atomicOr(w, 1u << (z & 31));
@@ -255,6 +363,165 @@ __global__ void __launch_bounds__(1024) edtZYKernel(GridDev g, const uint32_t* _
   }
 }
 
+// The z + y passes tiled (x plane) x (y chunk) x (z range): with the whole y extent of a plane in one CTA (the usual case)
+// no halo row is transformed twice -- the first version cut a plane into y chunks of 4R rows and ran the z pass on 2R halo
+// rows per chunk, 1.5x the z work -- and a z range of a few 8-voxel items keeps the slab small enough for four 512-thread
+// CTAs per SM.  The z pass of an item needs the occupancy words within R of it, nothing else of the row.
+//   shared memory: bits [rows_in][nw] | ends [rows_in][nwo] | gz [chunk + 2R][zi] x 16 bytes | the z pass's tables
+// rows of gz outside the grid are filled with "nothing within R" instead of being computed from zero bits.
+struct ZYPlan
+{
+  int chunk, n_chunks, n_zs;        // y rows per CTA, CTAs per plane along y, z ranges per row
+  int zi_max, nw_max, nwo_max, rows_in_max;  // layout maxima over all CTAs
+};
+
+__device__ __forceinline__ unsigned smallMagic(unsigned d) { return d <= 1u ? 0u : 0xffffffffu / d + 1u; }  // i / d for i < 2^16
+
+__global__ void __launch_bounds__(512, 4) edtZYKernel2(GridDev g, const uint32_t* __restrict__ occ, uint16_t* __restrict__ out,
+                                                       ZYPlan p, int invert, uint8_t* own_busy, const uint4* __restrict__ lut)
+{
+  extern __shared__ __align__(16) uint8_t smem[];
+  depLaunch();
+  int b = blockIdx.x;
+  const int zs = b % p.n_zs;
+  b /= p.n_zs;
+  const int ci = b % p.n_chunks, x = b / p.n_chunks;
+  const int R = g.R, cap = R + 1;
+  const int nz8 = (g.nz + 7) >> 3;
+  const int i0 = (zs * nz8) / p.n_zs, i1 = ((zs + 1) * nz8) / p.n_zs, zi = i1 - i0;  // this CTA's items [i0, i1) of a row
+  const int y0 = ci * p.chunk, y1 = min(g.ny, y0 + p.chunk), ny_c = y1 - y0;
+  const int ya = y0 - R, rows_g = ny_c + 2 * R;                     // gz row j <-> y = ya + j
+  const int ra = max(0, ya), rb = min(g.ny, y1 + R), n_in = rb - ra;  // the rows of it inside the grid
+  const int w_lo = max(0, (8 * i0 - R) >> 5), w_hi = min(g.wz - 1, (8 * i1 - 1 + R) >> 5), nw = w_hi - w_lo + 1;
+  const int wo_lo = (8 * i0) >> 5, wo_hi = (8 * i1 - 1) >> 5, nwo = wo_hi - wo_lo + 1;  // words the items live in
+  uint32_t* bits = reinterpret_cast<uint32_t*>(smem);
+  uint32_t* ends = bits + ((p.rows_in_max * p.nw_max + 3) & ~3);
+  uint4* gz4 = reinterpret_cast<uint4*>(ends + ((p.rows_in_max * p.nwo_max + 3) & ~3));
+  uint4* lut_within = gz4 + static_cast<size_t>(p.chunk + 2 * R) * p.zi_max;
+  const uint4* lut_below = lut_within + 256;
+  const uint4* lut_above = lut_below + (R + 2);
+  const unsigned m_nw = smallMagic(nw), m_nwo = smallMagic(nwo), m_zi = smallMagic(zi);
+  // prologue: nothing here depends on the kernels before this one (the tables are a function of R alone)
+  for (int t = threadIdx.x; t < 256 + 2 * (R + 2); t += blockDim.x)
+    lut_within[t] = lut[t];
+  {
+    const uint32_t capv = static_cast<uint32_t>(cap * cap) * 0x10001u;
+    const uint4 capq = make_uint4(capv, capv, capv, capv);
+    const int below = ra - ya, above = rows_g - (rb - ya);  // rows of gz before / behind the grid
+    for (int i = threadIdx.x; i < (below + above) * zi; i += blockDim.x)
+    {
+      const int r = static_cast<int>(divByMagic(static_cast<unsigned>(i), m_zi)), kb = i - r * zi;
+      const int j = r < below ? r : (rb - ya) + (r - below);
+      gz4[j * zi + kb] = capq;
+    }
+  }
+  depWait();
+  if (own_busy != nullptr && ci == 0 && zs == 0 && threadIdx.x == 0)
+    own_busy[static_cast<size_t>(x) * kPlaneBusyStride] = 0;  // the x pass (next launch) raises it again where the plane is not free
+  {
+    const uint32_t* src = occ + (static_cast<size_t>(x) * g.ny + ra) * g.wz + w_lo;
+    const uint32_t last = (g.nz & 31) ? (1u << (g.nz & 31)) - 1u : 0xffffffffu;  // bits of a row's last word inside the grid
+    for (int i = threadIdx.x; i < n_in * nw; i += blockDim.x)
+    {
+      const int r = static_cast<int>(divByMagic(static_cast<unsigned>(i), m_nw)), w = i - r * nw;
+      uint32_t v = src[r * g.wz + w];
+      if (invert)
+        v = ~v & ((w_lo + w == g.wz - 1) ? last : 0xffffffffu);
+      bits[i] = v;
+    }
+  }
+  __syncthreads();
+  // (a) per word the items live in: distance of its bit 0 / bit 31 to the nearest set bit in the words below / above
+  for (int i = threadIdx.x; i < n_in * nwo; i += blockDim.x)
+  {
+    const int r = static_cast<int>(divByMagic(static_cast<unsigned>(i), m_nwo)), wq = i - r * nwo;
+    const int w = wo_lo - w_lo + wq;
+    const uint32_t* row = bits + r * nw;
+    int dl = cap, dr = cap;
+    for (int ww = w - 1, off = 1; ww >= 0 && off <= R; --ww, off += 32)
+    {
+      const uint32_t v = row[ww];
+      if (v)
+      {
+        dl = min(cap, off + __clz(v));
+        break;
+      }
+    }
+    for (int ww = w + 1, off = 1; ww < nw && off <= R; ++ww, off += 32)
+    {
+      const uint32_t v = row[ww];
+      if (v)
+      {
+        dr = min(cap, off + __ffs(v) - 1);
+        break;
+      }
+    }
+    ends[i] = static_cast<uint32_t>(dl) | (static_cast<uint32_t>(dr) << 16);
+  }
+  __syncthreads();
+  // (b) per item (occupancy byte): three table rows, as in edtZYKernel
+  {
+    uint4* gzin = gz4 + (ra - ya) * zi;
+    for (int i = threadIdx.x; i < n_in * zi; i += blockDim.x)
+    {
+      const int r = static_cast<int>(divByMagic(static_cast<unsigned>(i), m_zi)), kb = i - r * zi;
+      const int item = i0 + kb, w = item >> 2, o = (item & 3) * 8;
+      const uint32_t cur = bits[r * nw + (w - w_lo)], e = ends[r * nwo + (w - wo_lo)];
+      const uint32_t low = o ? (cur & ((1u << o) - 1u)) : 0u, high = o < 24 ? (cur >> (o + 8)) : 0u;
+      const int dl = low ? o - 31 + __clz(low) : o + static_cast<int>(e & 0xffffu);
+      const int dr = high ? __ffs(high) : 24 - o + static_cast<int>(e >> 16);
+      const uint4 a = lut_within[(cur >> o) & 0xffu], bb = lut_below[min(dl, cap)], c = lut_above[min(dr, cap)];
+      uint4 q;
+      q.x = __vminu2(__vminu2(a.x, bb.x), c.x);
+      q.y = __vminu2(__vminu2(a.y, bb.y), c.y);
+      q.z = __vminu2(__vminu2(a.z, bb.z), c.z);
+      q.w = __vminu2(__vminu2(a.w, bb.w), c.w);
+      gzin[i] = q;
+    }
+  }
+  __syncthreads();
+  // y pass: 8 voxels per thread, outward scan, one termination test per two candidate distances
+  const bool vec_out = (g.nz & 7) == 0;  // then every (x, y) row of `out` starts 16-byte aligned
+  uint16_t* out_x = out + static_cast<size_t>(x) * g.ny * g.nz;
+  for (int i = threadIdx.x; i < ny_c * zi; i += blockDim.x)
+  {
+    const int yy = static_cast<int>(divByMagic(static_cast<unsigned>(i), m_zi)), zc = i - yy * zi;
+    const uint4* pa = gz4 + R * zi + i;  // row yy + R of the haloed block, item zc
+    const uint4* pb = pa;
+    uint4 best = *pa;
+    uint32_t k2p = 0x10001u, inc = 3u * 0x10001u;  // k^2 in both halves; (k + 1)^2 - k^2
+    auto rowPair = [&]() {
+      pa -= zi;
+      pb += zi;
+      const uint4 a = *pa, bb = *pb;
+      best.x = __viaddmin_u16x2(__vminu2(a.x, bb.x), k2p, best.x);
+      best.y = __viaddmin_u16x2(__vminu2(a.y, bb.y), k2p, best.y);
+      best.z = __viaddmin_u16x2(__vminu2(a.z, bb.z), k2p, best.z);
+      best.w = __viaddmin_u16x2(__vminu2(a.w, bb.w), k2p, best.w);
+      k2p += inc;
+      inc += 2u * 0x10001u;
+    };
+    for (int k = 1; k <= R; k += 2)
+    {
+      const uint32_t w2 = __vmaxu2(__vmaxu2(best.x, best.y), __vmaxu2(best.z, best.w));
+      if (__vmaxu2(w2, k2p) == k2p)
+        break;  // k^2 >= every best: every further candidate is at least k^2 away
+      rowPair();
+      if (k < R)
+        rowPair();
+    }
+    const int off = (y0 + yy) * g.nz + (i0 + zc) * 8;
+    if (vec_out)
+      *reinterpret_cast<uint4*>(out_x + off) = best;
+    else
+    {
+      const uint32_t bw[4] = { best.x, best.y, best.z, best.w };
+      for (int j = 0; j < 8 && (i0 + zc) * 8 + j < g.nz; ++j)
+        out_x[off + j] = static_cast<uint16_t>(bw[j >> 1] >> (16 * (j & 1)));
+    }
+  }
+}
+
 // voxel i = (x * ny + y) * nz + z lies in the outermost cell layer of the grid
 __device__ __forceinline__ bool onShell(const GridDev& g, size_t i)
 {
@@ -285,9 +552,11 @@ __global__ void __launch_bounds__(256) edtXKernelVec(GridDev g, const uint16_t* 
                                                     const uint8_t* __restrict__ other_busy)
 {
   // grid: x = tiles of the (y, z/8) plane, y = x planes
+  depLaunch();
   const int nz8 = g.nz >> 3;
   const unsigned plane8 = static_cast<unsigned>(g.ny) * nz8;
   const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+  depWait();  // the intermediate comes from the z + y kernel right before this one (programmatic dependent launch)
   if (p >= plane8)
     return;
   const int y = static_cast<int>(divByMagic(p, nz8_magic));  // p / nz8
@@ -686,7 +955,13 @@ cudaError_t launchScatter(const double* d_xyz, size_t n, const GridDev& g, uint3
 {
   if (n == 0)
     return cudaSuccess;
-  scatterKernel<<<gridFor(n, 256, 148 * 16), 256, 0, s>>>(d_xyz, n, g, occ, set ? 1 : 0);
+  static const int variant = getenv("B200SV_SCATTER") ? atoi(getenv("B200SV_SCATTER")) : 0;
+  static const int grid_env = getenv("B200SV_SCATTER_GRID") ? atoi(getenv("B200SV_SCATTER_GRID")) : 0;
+  const int grid = gridFor(n, 256, grid_env > 0 ? grid_env : 148 * 16);
+  if (variant == 1 && (reinterpret_cast<uintptr_t>(d_xyz) & 15u) == 0)
+    scatterKernelTma<<<grid, 256, 0, s>>>(d_xyz, n, g, occ, set ? 1 : 0);
+  else
+    scatterKernel<<<grid, 256, 0, s>>>(d_xyz, n, g, occ, set ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -759,15 +1034,124 @@ const uint4* edtLut(int dev, int R, cudaStream_t s)
   return d;
 }
 
+// Tiling of the z + y kernel: y rows per CTA (the whole extent when it fits: no halo rows) and z ranges per row, chosen by a
+// small cost model -- thread-instructions per CTA from the measured per-item costs of the phases, CTAs per SM from shared
+// memory (at most four of 512 threads), whole waves of the grid.  B200SV_EDT_CHUNK / B200SV_EDT_ZS override.
+namespace
+{
+size_t zyPlanBytes(const GridDev& g, ZYPlan& p)
+{
+  const int nz8 = (g.nz + 7) / 8;
+  p.n_chunks = (g.ny + p.chunk - 1) / p.chunk;
+  p.zi_max = (nz8 + p.n_zs - 1) / p.n_zs;
+  p.rows_in_max = std::min(g.ny, p.chunk + 2 * g.R);
+  p.nw_max = std::min(g.wz, (8 * p.zi_max + 2 * g.R + 30) / 32 + 1);
+  p.nwo_max = std::min(g.wz, (8 * p.zi_max + 30) / 32 + 1);
+  const size_t lut = (256 + 2 * static_cast<size_t>(g.R + 2)) * 16;
+  return static_cast<size_t>((p.rows_in_max * p.nw_max + 3) & ~3) * 4 + static_cast<size_t>((p.rows_in_max * p.nwo_max + 3) & ~3) * 4 +
+         static_cast<size_t>(p.chunk + 2 * g.R) * p.zi_max * 16 + lut;
+}
+
+ZYPlan planZY(const GridDev& g, int sm_count, size_t* smem_out)
+{
+  static const int chunk_env = getenv("B200SV_EDT_CHUNK") ? atoi(getenv("B200SV_EDT_CHUNK")) : 0;
+  static const int zs_env = getenv("B200SV_EDT_ZS") ? atoi(getenv("B200SV_EDT_ZS")) : 0;
+  const int nz8 = (g.nz + 7) / 8;
+  ZYPlan best{};
+  double best_cost = 0.0;
+  size_t best_bytes = 0;
+  for (int parts = 1; parts <= g.ny; ++parts)
+  {
+    int chunk = (g.ny + parts - 1) / parts;
+    if (chunk_env > 0)
+      chunk = std::min(chunk_env, g.ny);
+    if (parts > 1 && chunk < std::min(g.ny, std::max(2 * g.R, 16)) && best.chunk != 0)
+      break;  // halo rows would outnumber the rows they serve
+    for (int n_zs = 1; n_zs <= nz8; ++n_zs)
+    {
+      if (zs_env > 0 && n_zs != std::min(zs_env, nz8))
+        continue;
+      ZYPlan p{};
+      p.chunk = chunk;
+      p.n_zs = n_zs;
+      const size_t bytes = zyPlanBytes(g, p);
+      if (bytes > 200 * 1024)
+        continue;
+      const int per_sm = static_cast<int>(std::min<size_t>(4, (227 * 1024) / (bytes + 1024)));
+      const long n_ctas = static_cast<long>(g.nx) * p.n_chunks * n_zs;
+      const long waves = (n_ctas + static_cast<long>(sm_count) * per_sm - 1) / (static_cast<long>(sm_count) * per_sm);
+      // thread-instructions of one CTA: z pass 59 per item, y pass 120, word ends 62 per word, loads, fixed costs
+      const double rows_in = std::min(g.ny, chunk + 2 * g.R), zi = static_cast<double>(nz8) / n_zs;
+      const double work = rows_in * zi * 59 + chunk * zi * 120 + rows_in * p.nwo_max * 62 + rows_in * p.nw_max * 10 + 6000;
+      // CTAs on an SM share its issue slots; fewer than 32 warps per SM hide latency badly
+      const double cost = static_cast<double>(waves) * per_sm * work * (per_sm >= 2 ? 1.0 : 1.5);
+      if (best.chunk == 0 || cost < best_cost)
+      {
+        best = p;
+        best_cost = cost;
+        best_bytes = bytes;
+      }
+    }
+    if (chunk_env > 0)
+      break;
+  }
+  *smem_out = best_bytes;
+  return best;
+}
+}  // namespace
+
 cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint16_t* d2, void* compact,
                       int compact_bytes, int sm_count, cudaStream_t s, bool invert, uint8_t* own_busy,
                       const uint8_t* other_busy)
 {
-  // y chunks: small enough for several CTAs per SM (a haloed slab = occupancy words + squared z distances in shared
-  // memory), large enough that the 2R halo rows stay a modest overhead
   if (g.R > 180)
     return cudaErrorInvalidConfiguration;  // (R+1)^2 + R^2 must fit 16 bits
   const int nzp = (g.nz + 7) & ~7;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  const unsigned nz8 = static_cast<unsigned>(nzp / 8);
+  const unsigned nz8_magic = static_cast<unsigned>(((1ull << 32) + nz8 - 1) / nz8);  // i / nz8 = umulhi(i, magic), i < 2^16
+  if (compact == nullptr)
+    own_busy = nullptr;
+  const uint4* lut = edtLut(dev, g.R, s);
+  if (lut == nullptr)
+    return cudaErrorMemoryAllocation;
+  static const bool use_pdl = !(getenv("B200SV_EDT_PDL") && atoi(getenv("B200SV_EDT_PDL")) == 0);
+  static const bool zy_v1 = getenv("B200SV_EDT_ZY") && atoi(getenv("B200SV_EDT_ZY")) == 1;
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaError_t e = cudaSuccess;
+  if (!zy_v1)
+  {
+    size_t smem = 0;
+    const ZYPlan plan = planZY(g, sm_count, &smem);
+    if (plan.chunk == 0)
+      return cudaErrorInvalidConfiguration;  // not even one row block fits: grid too deep for this kernel
+    static size_t granted2[16] = { 0 };  // the attribute is per device
+    if (smem > granted2[dev])
+    {
+      e = cudaFuncSetAttribute(edtZYKernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess)
+        return e;
+      granted2[dev] = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(g.nx) * plan.n_chunks * plan.n_zs);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cfg.attrs = pdl_attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, edtZYKernel2, g, occ, tmp, plan, invert ? 1 : 0, own_busy, lut);
+    if (e != cudaSuccess)
+      return e;
+  }
+  else
+  {
+  // y chunks: small enough for several CTAs per SM (a haloed slab = occupancy words + squared z distances in shared
+  // memory), large enough that the 2R halo rows stay a modest overhead
   const size_t per_row = static_cast<size_t>(g.wz) * 8 + static_cast<size_t>(nzp) * 2;  // bits, word ends, squared z distances
   const long max_rows = static_cast<long>((200 * 1024 - (256 + 2 * (g.R + 2)) * 16) / per_row);
   if (max_rows < 2L * g.R + 1)
@@ -780,28 +1164,19 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
   const size_t smem = ((static_cast<size_t>(chunk + 2 * g.R) * g.wz * 4 + 15) & ~static_cast<size_t>(15)) +
                       static_cast<size_t>(chunk + 2 * g.R) * nzp * 2 + lut_bytes;
   static size_t granted[16] = { 0 };  // the attribute is per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 15;
   if (smem > granted[dev])
   {
-    cudaError_t e = cudaFuncSetAttribute(edtZYKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    e = cudaFuncSetAttribute(edtZYKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess)
       return e;
     granted[dev] = smem;
   }
-  const unsigned nz8 = static_cast<unsigned>(nzp / 8);
-  const unsigned nz8_magic = static_cast<unsigned>(((1ull << 32) + nz8 - 1) / nz8);  // i / nz8 = umulhi(i, magic), i < 2^16
   static const int zy_threads = getenv("B200SV_EDT_THREADS") ? atoi(getenv("B200SV_EDT_THREADS")) : 512;
-  if (compact == nullptr)
-    own_busy = nullptr;
-  const uint4* lut = edtLut(dev, g.R, s);
-  if (lut == nullptr)
-    return cudaErrorMemoryAllocation;
   edtZYKernel<<<g.nx * n_chunks, zy_threads, smem, s>>>(g, occ, tmp, chunk, n_chunks, nz8_magic, invert ? 1 : 0, own_busy, lut);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess)
     return e;
+  }
   const size_t total = static_cast<size_t>(g.nx) * g.ny * g.nz;
   const unsigned long long plane8 = static_cast<unsigned long long>(g.ny) * nz8;
   if (g.nz % 8 == 0 && plane8 * nz8 < (1ull << 32))  // the second condition keeps p / nz8 = umulhi(p, magic) exact
@@ -810,11 +1185,18 @@ cudaError_t launchEdt(const GridDev& g, const uint32_t* occ, uint16_t* tmp, uint
     static const bool no_rmw_skip = getenv("B200SV_EDT_RMW") != nullptr;  // A/B: always merge, as before
     if (no_rmw_skip)
       other_busy = nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cfg.attrs = pdl_attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    const uint16_t* tmp_in = tmp;
     if (compact_bytes == 1)
-      edtXKernelVec<uint8_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint8_t*>(compact), nz8_magic, own_busy, other_busy);
-    else
-      edtXKernelVec<uint16_t><<<grid, 256, 0, s>>>(g, tmp, d2, static_cast<uint16_t*>(compact), nz8_magic, own_busy, other_busy);
-    return cudaGetLastError();
+      return cudaLaunchKernelEx(&cfg, edtXKernelVec<uint8_t>, g, tmp_in, d2, static_cast<uint8_t*>(compact), nz8_magic, own_busy,
+                                other_busy);
+    return cudaLaunchKernelEx(&cfg, edtXKernelVec<uint16_t>, g, tmp_in, d2, static_cast<uint16_t*>(compact), nz8_magic, own_busy,
+                              other_busy);
   }
   if (own_busy != nullptr && compact != nullptr)
   {  // the scalar x pass below does not track the planes: everything may be busy

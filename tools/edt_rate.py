@@ -32,4 +32,6 @@ for i in range(reps):
     times.append(ev0.elapsed_time(ev1))
 nv = int(np.prod(e4.num_cells))
 ms = float(np.median(times[min(3, reps - 1):]))
-print("%s: %d points -> %d voxels: %.4f ms = %.3g voxels/s" % (name, len(pts), nv, ms, nv / ms * 1e3))
+g4 = e4.field_get_d2()
+print("%s: %d points -> %d voxels: %.4f ms = %.3g voxels/s  (min %.4f; d2 checksum %d, %d occupied)" %
+      (name, len(pts), nv, ms, nv / ms * 1e3, min(times), int(g4.astype(np.int64).sum()), int((g4 == 0).sum())))
