@@ -197,6 +197,35 @@ int b200sv_field_update_points(b200sv_ctx* ctx, int which, const double* old_xyz
  * the reference, one rebuild here.)  Reads of the field inside the bracket see the state before it. */
 int b200sv_field_begin_update(b200sv_ctx* ctx, int which);
 int b200sv_field_end_update(b200sv_ctx* ctx, int which);
+/* ---- which propagation a field runs --------------------------------------------------------------------------------------
+ * B200SV_PROPAGATION_EXACT (default): every change rebuilds the field with the exact truncated Euclidean transform.  Its
+ *   values are never above the reference's and differ from them in a fraction of a percent of the voxels, because
+ *   PropagationDistanceField::propagatePositive (propagation_distance_field.cpp:390-444) hands closest points along a
+ *   direction-limited neighbourhood in queue order and can miss the true nearest obstacle.
+ * B200SV_PROPAGATION_REFERENCE: the field keeps the reference's per-voxel record (distance_square_, closest_point_,
+ *   update_direction_, propagation_distance_field.hpp:82-116) and its bucket queue on the device, and b200sv_field_add_points
+ *   / remove_points / update_points / add_points_device run addNewObstacleVoxels (:221-301), removeObstacleVoxels (:303-388)
+ *   and propagatePositive in data-parallel phases whose outcome is the serial queue's: every voxel's squared distance equals
+ *   the reference's after the same sequence of calls with the same point arrays (the order of the points and of the calls
+ *   matters, as it does in the reference).  Milliseconds per call instead of a tenth of one.  Unsigned fields only; the
+ *   shape / octree / .df / set_d2 / import entry points and b200sv_set_base_state(.., rebuild_self_field = 1) on the self
+ *   field refuse with B200SV_ERR_UNSUPPORTED while a field is in this mode (feed their points through add_points), and
+ *   begin/end_update brackets are refused too (the reference propagates per call).
+ * Switching the mode resets the field. */
+#define B200SV_PROPAGATION_EXACT 0
+#define B200SV_PROPAGATION_REFERENCE 1
+int b200sv_field_set_propagation(b200sv_ctx* ctx, int which, int mode);
+typedef struct b200sv_propagation_stats
+{
+  uint64_t rounds;               /* data-parallel rounds so far (at least one per non-empty bucket and call) */
+  uint64_t hazard_rounds;        /* rounds cut short because an offer changed a voxel queued later in the same bucket */
+  uint64_t queue_entries;        /* bucket-queue entries drained so far */
+  uint64_t backward_offers;      /* accepted offers into a bucket at or below the one being drained (:426-437 pushes them
+                                    behind the loop: never run in that call) */
+  uint64_t queued_for_next_call; /* such entries still waiting in the queue, as in the reference */
+} b200sv_propagation_stats;
+int b200sv_field_propagation_stats(b200sv_ctx* ctx, int which, b200sv_propagation_stats* out);
+
 /* DistanceField::addShapeToField for a shapes::Sphere (distance_field.cpp:208-238): the interior lattice points of
  * findInternalPointsConvex (find_internal_points.cpp:39-64; bodies::Sphere::containsPoint = |c - p|^2 <= r^2) are marked on
  * the device and the field is rebuilt.  This is the construction of the reference's fixture moveit_core/test_big.df

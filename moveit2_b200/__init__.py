@@ -7,4 +7,4 @@ adapter/ (the MoveIt-side C++ plugin shim), resources/ (benchmark robot descript
 from .engine import (B200svError, CollisionEnvB200, CollisionRequest, CollisionResult,  # noqa: F401
                      MultiDeviceEngine, StateValidityEngine)
 from ._lib import (CHECK_ALL, CHECK_FP64, CHECK_INTRA, CHECK_SELF, CHECK_WORLD, DEVICE_NONE, FIELD_SELF,  # noqa: F401
-                   FIELD_WORLD, LATTICE_BODY, LATTICE_WORLD, SHAPE_BOX, SHAPE_CYLINDER, SHAPE_SPHERE)
+                   FIELD_WORLD, LATTICE_BODY, LATTICE_WORLD, PROPAGATION_EXACT, PROPAGATION_REFERENCE, SHAPE_BOX, SHAPE_CYLINDER, SHAPE_SPHERE)

@@ -41,6 +41,7 @@ class Shape(C.Structure):
 
 SHAPE_SPHERE, SHAPE_CYLINDER, SHAPE_BOX = 1, 2, 4
 LATTICE_WORLD, LATTICE_BODY = 0, 1
+PROPAGATION_EXACT, PROPAGATION_REFERENCE = 0, 1
 
 
 class Convex(C.Structure):
@@ -58,6 +59,11 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_states", C.c_uint64), ("n_valid", C.c_uint64), ("n_rechecked", C.c_uint64),
                 ("check_ms", C.c_float), ("edt_ms", C.c_float)]
+
+
+class PropagationStats(C.Structure):
+    _fields_ = [("rounds", C.c_uint64), ("hazard_rounds", C.c_uint64), ("queue_entries", C.c_uint64),
+                ("backward_offers", C.c_uint64), ("queued_for_next_call", C.c_uint64)]
 
 
 _lib = None
@@ -87,6 +93,8 @@ def load():
         "b200sv_get_group_bounds": (C.c_int, [vp, dp, dp]),
         "b200sv_get_sphere_thresholds": (C.c_int, [vp, ip]),
         "b200sv_field_reset": (C.c_int, [vp, C.c_int]),
+        "b200sv_field_set_propagation": (C.c_int, [vp, C.c_int, C.c_int]),
+        "b200sv_field_propagation_stats": (C.c_int, [vp, C.c_int, C.POINTER(PropagationStats)]),
         "b200sv_field_begin_update": (C.c_int, [vp, C.c_int]),
         "b200sv_field_end_update": (C.c_int, [vp, C.c_int]),
         "b200sv_field_add_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200sv.so")
-SOURCES = ["api.cu", "check_kernels.cu", "fast_check.cu", "edt_kernels.cu", "motion_kernels.cu", "host_model.cpp"]
+SOURCES = ["api.cu", "check_kernels.cu", "fast_check.cu", "edt_kernels.cu", "propagation.cu", "motion_kernels.cu", "host_model.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
               "-fPIC,-Wall,-Wno-unknown-pragmas", "-shared", "--expt-relaxed-constexpr", "-lz"]
 

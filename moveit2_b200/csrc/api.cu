@@ -34,6 +34,7 @@ struct Field
   uint8_t* plane_busy = nullptr;  // [nx] nonzero: plane x of this field's compact elements may hold a non-free value
   bool dirty = false;         // occupancy changed inside a begin/end_update bracket: the EDT is owed
   bool deferred = false;      // inside b200sv_field_begin_update .. b200sv_field_end_update
+  PropField* prop = nullptr;  // B200SV_PROPAGATION_REFERENCE: the reference's voxel records and bucket queue (propagation.cu)
 };
 
 template <typename T>
@@ -1663,6 +1664,10 @@ int edtPasses(b200sv_ctx* c, Field& F, cudaStream_t s)
 int rebuildField(b200sv_ctx* c, int which)
 {
   Field& F = c->fields[which];
+  if (F.prop)
+    return fail(c, B200SV_ERR_UNSUPPORTED,
+                "this field reproduces the reference's propagation (b200sv_field_set_propagation): only reset, add_points, "
+                "remove_points and update_points change it");
   if (F.deferred)
   {  // several occupancy changes, ONE transform (b200sv_field_end_update runs it)
     F.dirty = true;
@@ -2093,6 +2098,8 @@ void b200sv_destroy(b200sv_ctx* c)
       cudaFree(F.occ);
     if (F.plane_busy)
       cudaFree(F.plane_busy);
+    propDestroy(F.prop);
+    F.prop = nullptr;
   }
   if (c->d_combined) cudaFree(c->d_combined);
   if (c->d_tmp) cudaFree(c->d_tmp);
@@ -2278,6 +2285,76 @@ static int checkWhich(b200sv_ctx* c, int which)
   return needDevice(c);
 }
 
+// entry points that edit the occupancy bits directly have no meaning for a field in reference-propagation mode
+static int notInReferenceMode(b200sv_ctx* c, int which)
+{
+  if (c->fields[which].prop)
+    return fail(c, B200SV_ERR_UNSUPPORTED,
+                "this field reproduces the reference's propagation (b200sv_field_set_propagation): only reset, add_points, "
+                "remove_points and update_points change it");
+  return B200SV_OK;
+}
+
+// the propagation's distances become the field every kernel reads: occupancy bits, d2, this field's compact elements
+static int publishPropagation(b200sv_ctx* c, int which, cudaStream_t s)
+{
+  Field& F = c->fields[which];
+  CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, s));
+  CU(c, launchInjectD2(c->grid, propDistances(F.prop), F.occ, F.d2, F.compact, c->compact_bytes, s));
+  CU(c, cudaMemsetAsync(F.plane_busy, 1, (size_t)c->grid.nx * kPlaneBusyStride, s));
+  return B200SV_OK;
+}
+
+int b200sv_field_set_propagation(b200sv_ctx* c, int which, int mode)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (mode != B200SV_PROPAGATION_EXACT && mode != B200SV_PROPAGATION_REFERENCE)
+    return fail(c, B200SV_ERR_INVALID, "mode must be B200SV_PROPAGATION_EXACT or B200SV_PROPAGATION_REFERENCE");
+  if (mode == B200SV_PROPAGATION_REFERENCE && c->cfg.use_signed_distance_field)
+    return fail(c, B200SV_ERR_UNSUPPORTED, "reference propagation is implemented for unsigned fields (the reference's default)");
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    enterCtx(c);
+    Field& F = c->fields[which];
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (mode == B200SV_PROPAGATION_REFERENCE && !F.prop)
+    {
+      cudaError_t e = propCreate(c->grid, &F.prop);
+      if (e != cudaSuccess)
+        return fail(c, e == cudaErrorInvalidConfiguration ? B200SV_ERR_UNSUPPORTED : B200SV_ERR_CUDA,
+                    std::string("reference propagation: ") + cudaGetErrorString(e));
+      F.deferred = F.dirty = false;
+    }
+    else if (mode == B200SV_PROPAGATION_EXACT && F.prop)
+    {
+      propDestroy(F.prop);
+      F.prop = nullptr;
+    }
+  }
+  return b200sv_field_reset(c, which);  // either way the field starts empty in its new mode
+}
+
+int b200sv_field_propagation_stats(b200sv_ctx* c, int which, b200sv_propagation_stats* out)
+{
+  int rc = checkWhich(c, which);
+  if (rc)
+    return rc;
+  if (!out)
+    return fail(c, B200SV_ERR_INVALID, "null output");
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->fields[which].prop)
+    return fail(c, B200SV_ERR_INVALID, "the field is not in reference-propagation mode");
+  const PropStats& st = propStats(c->fields[which].prop);
+  out->rounds = st.rounds;
+  out->hazard_rounds = st.hazard_rounds;
+  out->queue_entries = st.entries;
+  out->backward_offers = st.backward_offers;
+  out->queued_for_next_call = st.queued_for_next_call;
+  return B200SV_OK;
+}
+
 int b200sv_field_reset(b200sv_ctx* c, int which)
 {
   int rc = checkWhich(c, which);
@@ -2286,6 +2363,8 @@ int b200sv_field_reset(b200sv_ctx* c, int which)
   std::lock_guard<std::mutex> lk(c->mu);
   enterCtx(c);
   Field& F = c->fields[which];
+  if (F.prop)
+    CU(c, propReset(F.prop, c->stream));
   CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
   CU(c, launchFillField(c->grid, F.d2, F.compact, c->compact_bytes, c->stream));
   CU(c, cudaMemsetAsync(F.plane_busy, 0, (size_t)c->grid.nx * kPlaneBusyStride, c->stream));
@@ -2299,6 +2378,8 @@ int b200sv_field_begin_update(b200sv_ctx* c, int which)
 {
   int rc = checkWhich(c, which);
   if (rc)
+    return rc;
+  if ((rc = notInReferenceMode(c, which)) != B200SV_OK)
     return rc;
   std::lock_guard<std::mutex> lk(c->mu);
   c->fields[which].deferred = true;
@@ -2329,6 +2410,23 @@ static int pointsHost(b200sv_ctx* c, int which, const double* xyz, size_t n, boo
     return fail(c, B200SV_ERR_INVALID, "null point array");
   std::lock_guard<std::mutex> lk(c->mu);
   enterCtx(c);
+  if (c->fields[which].prop)
+  {  // addPointsToField / removePointsFromField as the reference runs them, call by call
+    PropField* pf = c->fields[which].prop;
+    CU(c, c->d_points.ensure(3 * n + 3));
+    if (n)
+      CU(c, cudaMemcpyAsync(c->d_points.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaEventRecord(c->ev0, c->stream));
+    CU(c, set ? propAddPoints(pf, c->d_points.p, n, c->stream) : propRemovePoints(pf, c->d_points.p, n, c->stream));
+    if ((rc = publishPropagation(c, which, c->stream)) != B200SV_OK)
+      return rc;
+    CU(c, cudaEventRecord(c->ev1, c->stream));
+    CU(c, cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->stats.edt_ms = ms;
+    return B200SV_OK;
+  }
   if (n)
   {
     CU(c, c->d_points.ensure(3 * n));
@@ -2358,6 +2456,21 @@ int b200sv_field_update_points(b200sv_ctx* c, int which, const double* old_xyz, 
     return fail(c, B200SV_ERR_INVALID, "null point array");
   std::lock_guard<std::mutex> lk(c->mu);
   enterCtx(c);
+  if (c->fields[which].prop)
+  {
+    CU(c, c->d_points.ensure(3 * (n_old + n_new) + 3));
+    double* d_old = c->d_points.p;
+    double* d_new = c->d_points.p + 3 * n_old;
+    if (n_old)
+      CU(c, cudaMemcpyAsync(d_old, old_xyz, 3 * n_old * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (n_new)
+      CU(c, cudaMemcpyAsync(d_new, new_xyz, 3 * n_new * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(c, propUpdatePoints(c->fields[which].prop, d_old, n_old, d_new, n_new, c->stream));
+    if ((rc = publishPropagation(c, which, c->stream)) != B200SV_OK)
+      return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return B200SV_OK;
+  }
   const size_t n_words = (size_t)c->grid.nx * c->grid.ny * c->grid.wz;
   if (2 * n_words * 4 > c->n_voxels * 2)
     return fail(c, B200SV_ERR_UNSUPPORTED, "grid too shallow for the update scratch (nz < 16)");
@@ -2384,6 +2497,8 @@ int b200sv_field_add_sphere(b200sv_ctx* c, int which, const double* center, doub
 {
   int rc = checkWhich(c, which);
   if (rc)
+    return rc;
+  if ((rc = notInReferenceMode(c, which)) != B200SV_OK)
     return rc;
   if (!center || !(radius >= 0.0))
     return fail(c, B200SV_ERR_INVALID, "null centre or negative radius");
@@ -2416,6 +2531,8 @@ int b200sv_field_add_shape(b200sv_ctx* c, int which, const b200sv_shape* sh, int
 {
   int rc = checkWhich(c, which);
   if (rc)
+    return rc;
+  if ((rc = notInReferenceMode(c, which)) != B200SV_OK)
     return rc;
   if (!sh)
     return fail(c, B200SV_ERR_INVALID, "null shape");
@@ -2502,6 +2619,8 @@ int b200sv_field_add_convex(b200sv_ctx* c, int which, const b200sv_convex* cv, i
   int rc = checkWhich(c, which);
   if (rc)
     return rc;
+  if ((rc = notInReferenceMode(c, which)) != B200SV_OK)
+    return rc;
   if (!cv || cv->n_planes < 1 || !cv->planes)
     return fail(c, B200SV_ERR_INVALID, "null convex body or no planes");
   if (cv->lattice_frame != B200SV_LATTICE_WORLD && cv->lattice_frame != B200SV_LATTICE_BODY)
@@ -2565,6 +2684,8 @@ int b200sv_field_add_octree_leaves(b200sv_ctx* c, int which, const double* leave
   int rc = checkWhich(c, which);
   if (rc)
     return rc;
+  if ((rc = notInReferenceMode(c, which)) != B200SV_OK)
+    return rc;
   if (n_leaves && !leaves)
     return fail(c, B200SV_ERR_INVALID, "null leaf array");
   std::lock_guard<std::mutex> lk(c->mu);
@@ -2587,6 +2708,13 @@ int b200sv_field_add_points_device(b200sv_ctx* c, int which, const double* d_xyz
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   if ((rc = enterUser(c, s)) != B200SV_OK)
     return rc;
+  if (c->fields[which].prop)
+  {  // not asynchronous in this mode: the propagation synchronises the stream once per round
+    CU(c, propAddPoints(c->fields[which].prop, d_xyz, n, s));
+    if ((rc = publishPropagation(c, which, s)) != B200SV_OK)
+      return rc;
+    return leaveUser(c, s);
+  }
   if ((rc = addOrRemove(c, which, d_xyz, n, true, s)) != B200SV_OK)
     return rc;
   if ((rc = edtPasses(c, c->fields[which], s)) != B200SV_OK)
@@ -2656,6 +2784,8 @@ int b200sv_field_set_d2(b200sv_ctx* c, int which, const int32_t* d2)
   int rc = checkWhich(c, which);
   if (rc)
     return rc;
+  if ((rc = notInReferenceMode(c, which)) != B200SV_OK)
+    return rc;
   if (!d2)
     return fail(c, B200SV_ERR_INVALID, "null input");
   std::lock_guard<std::mutex> lk(c->mu);
@@ -2713,6 +2843,8 @@ int b200sv_field_read_df(b200sv_ctx* c, int which, const uint8_t* bytes, size_t 
 {
   int rc = checkWhich(c, which);
   if (rc)
+    return rc;
+  if ((rc = notInReferenceMode(c, which)) != B200SV_OK)
     return rc;
   if (!bytes)
     return fail(c, B200SV_ERR_INVALID, "null input");
@@ -3820,6 +3952,8 @@ static int fieldTransfer(b200sv_ctx* c, int which, uint8_t* d_buf, void* cuda_st
     return fail(c, B200SV_ERR_INVALID, "null device buffer");
   if (c->fields[which].nd2)
     return fail(c, B200SV_ERR_UNSUPPORTED, "signed fields are rebuilt per context, not replicated");
+  if (!to_buf && (rc = notInReferenceMode(c, which)) != B200SV_OK)
+    return rc;  // (exporting such a field is fine: its values replicate like any other's)
   std::lock_guard<std::mutex> lk(c->mu);
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   if ((rc = enterUser(c, s)) != B200SV_OK)

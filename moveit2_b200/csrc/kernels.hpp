@@ -286,6 +286,24 @@ cudaError_t launchInjectNegD2(const GridDev& g, const int32_t* d_in, uint16_t* n
 cudaError_t launchFillField(const GridDev& g, uint16_t* d2, void* compact, int compact_bytes, cudaStream_t s);
 cudaError_t launchInjectD2(const GridDev& g, const int32_t* d_in, uint32_t* occ, uint16_t* d2, void* compact,
                            int compact_bytes, cudaStream_t s);
+// ---- the reference's own propagation, reproduced phase-parallel (propagation.cu) -----------------------------------------
+// A PropField holds PropagationDistanceField's per-voxel record (distance_square_, closest_point_, update_direction_) and its
+// bucket queue for one field of a context; every call below leaves the squared distances in propDistances() (int32, one per
+// voxel, voxel_grid.hpp:425 order), ready for launchInjectD2.  All calls synchronise `s` many times.
+struct PropField;
+struct PropStats
+{
+  unsigned long long rounds, hazard_rounds, entries, backward_offers, hazard_offers, queued_for_next_call, flood_pops_batches;
+};
+cudaError_t propCreate(const GridDev& g, PropField** out);
+void propDestroy(PropField* f);
+cudaError_t propReset(PropField* f, cudaStream_t s);                                          // reset() :506-524
+cudaError_t propAddPoints(PropField* f, const double* d_xyz, size_t n, cudaStream_t s);      // addPointsToField :177-196
+cudaError_t propRemovePoints(PropField* f, const double* d_xyz, size_t n, cudaStream_t s);   // removePointsFromField :198-219
+cudaError_t propUpdatePoints(PropField* f, const double* d_old, size_t n_old, const double* d_new, size_t n_new,
+                             cudaStream_t s);                                                // updatePointsInField :130-175
+const int32_t* propDistances(const PropField* f);
+const PropStats& propStats(const PropField* f);
 // One field's elements of the interleaved compact field <-> a dense array (field replication across contexts):
 // `compact` is already offset to this field's first element; extract = to the dense array, else from it.
 cudaError_t launchCompactCopy(void* compact, void* dense, size_t n_voxels, int compact_bytes, bool extract, cudaStream_t s);

@@ -1,0 +1,947 @@
+// The reference's OWN propagation, reproduced on the device: PropagationDistanceField's bucket-queue wavefront
+// (distance_field/src/propagation_distance_field.cpp:177-444) evaluated in data-parallel phases whose result is the serial
+// queue's, voxel for voxel -- including what makes that result differ from the exact transform of edt_kernels.cu
+// (closest points only travel along the queue's direction-limited neighbourhoods, ties go to whoever was queued first,
+// entries pushed behind the bucket being drained are dropped or stay queued for the NEXT call).
+//
+// Serial semantics restated (propagatePositive :390-444).  Bucket i is a FIFO of voxel locations.  Draining it, every entry
+// reads its voxel's CURRENT (closest point, update direction), walks the neighbourhood of that direction (26 cells in bucket 0,
+// the non-opposing axis steps from bucket 1 on) and OFFERS each neighbour the distance to its own closest point; an offer is
+// accepted iff it is strictly below the neighbour's distance at that moment, and an accepted offer appends the neighbour to
+// bucket[new distance].  Number the offers of one bucket key = position * S + slot (S = 26 or 6).  Then
+//   * an offer is accepted  <=>  it is below the target's distance before the bucket AND below every offer to the same
+//     target with a smaller key (accepted or not: a rejected offer was not below something smaller still);
+//   * the target's final state is the accepted offer of smallest distance; its queue entries are all accepted offers, in
+//     key order within each destination bucket
+// PROVIDED no entry's own state changes while its bucket is drained.  That can happen (an offer may go "backwards" to a
+// voxel whose own entry sits later in the same bucket): such a HAZARD is detected, the bucket is cut right before the
+// earliest position a hazard touches, the part before the cut is applied -- it is unaffected, by induction over positions --
+// and the rest is redone as another ROUND with the updated states.  A round is therefore: stamp the entries' positions,
+// compute all offers and their acceptance (read-only), apply them up to the cut, sort the accepted offers by destination
+// bucket (stable: key order is kept) straight into the queue pool, un-stamp.  One host synchronisation per round.
+//
+// The removal flood (removeObstacleVoxels :303-388) is a depth-first walk whose visiting order decides the order of the
+// bucket-0 entries it queues, i.e. later ties: it runs as ONE warp (27 lanes = the 27 neighbours of the voxel on top of
+// the stack), exactly in the reference's order.
+//
+// This mode exists for parity with the reference's numbers; it costs milliseconds where the exact transform costs
+// a tenth of one.  cub's radix sort (CUDA toolkit headers) does the stable partition.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.hpp"
+
+namespace b200sv
+{
+namespace
+{
+constexpr uint32_t kNone = 0xffffffffu;
+constexpr uint16_t kNoKey = 0xffffu;
+constexpr int kInitialDirection = 13;  // getDirectionNumber(0, 0, 0)
+
+// neighbourhoods_[n][direction] (:526-582), the slot of a step in them, their sizes
+struct NeighbourTables
+{
+  int8_t nb[2][27][26][3];
+  int8_t cnt[2][27];
+  int8_t slot[2][27][27];  // [n][source direction][direction number of the step] -> index in nb, or -1
+};
+__constant__ NeighbourTables c_nb;
+
+NeighbourTables makeTables()
+{
+  NeighbourTables t;
+  std::memset(&t, 0, sizeof(t));
+  for (int n = 0; n < 2; ++n)
+    for (int dx = -1; dx <= 1; ++dx)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dz = -1; dz <= 1; ++dz)
+        {
+          const int dn = (dx + 1) * 9 + (dy + 1) * 3 + dz + 1;
+          for (int k = 0; k < 27; ++k)
+            t.slot[n][dn][k] = -1;
+          int cnt = 0;
+          for (int tx = -1; tx <= 1; ++tx)
+            for (int ty = -1; ty <= 1; ++ty)
+              for (int tz = -1; tz <= 1; ++tz)
+              {
+                if (tx == 0 && ty == 0 && tz == 0)
+                  continue;
+                if (n >= 1)
+                {
+                  if (std::abs(tx) + std::abs(ty) + std::abs(tz) != 1)
+                    continue;
+                  if (dx * tx < 0 || dy * ty < 0 || dz * tz < 0)
+                    continue;
+                }
+                t.nb[n][dn][cnt][0] = static_cast<int8_t>(tx);
+                t.nb[n][dn][cnt][1] = static_cast<int8_t>(ty);
+                t.nb[n][dn][cnt][2] = static_cast<int8_t>(tz);
+                t.slot[n][dn][(tx + 1) * 9 + (ty + 1) * 3 + tz + 1] = static_cast<int8_t>(cnt);
+                ++cnt;
+              }
+          t.cnt[n][dn] = static_cast<int8_t>(cnt);
+        }
+  return t;
+}
+
+// closest point as three 16-bit fields holding coordinate + 1 (0 = the reference's UNINITIALIZED -1)
+__host__ __device__ inline uint64_t packPoint(int x, int y, int z)
+{
+  return (static_cast<uint64_t>(x + 1) << 32) | (static_cast<uint64_t>(y + 1) << 16) | static_cast<uint64_t>(z + 1);
+}
+constexpr uint64_t kPointMask = 0xffffffffffffull;
+__device__ inline void unpackPoint(uint64_t p, int& x, int& y, int& z)
+{
+  x = static_cast<int>((p >> 32) & 0xffffu) - 1;
+  y = static_cast<int>((p >> 16) & 0xffffu) - 1;
+  z = static_cast<int>(p & 0xffffu) - 1;
+}
+
+struct Dims
+{
+  int nx, ny, nz;
+};
+__device__ inline void coordsOf(const Dims& g, uint32_t v, int& x, int& y, int& z)
+{
+  const uint32_t plane = static_cast<uint32_t>(g.ny) * g.nz;
+  x = static_cast<int>(v / plane);
+  const uint32_t r = v - static_cast<uint32_t>(x) * plane;
+  y = static_cast<int>(r / g.nz);
+  z = static_cast<int>(r - static_cast<uint32_t>(y) * g.nz);
+}
+__device__ inline bool validCell(const Dims& g, int x, int y, int z)
+{
+  return x >= 0 && y >= 0 && z >= 0 && x < g.nx && y < g.ny && z < g.nz;
+}
+__device__ inline uint32_t refOf(const Dims& g, int x, int y, int z)
+{
+  return (static_cast<uint32_t>(x) * g.ny + y) * g.nz + z;
+}
+__device__ inline long long sq3(int ax, int ay, int az)
+{
+  return static_cast<long long>(ax) * ax + static_cast<long long>(ay) * ay + static_cast<long long>(az) * az;
+}
+
+struct State
+{
+  int32_t* dist;     // distance_square_
+  uint64_t* cp;      // closest_point_
+  uint8_t* dir;      // update_direction_
+  uint32_t* first;   // position of a voxel's first entry in the round being processed (kNone: none)
+  uint32_t* lastp1;  // position + 1 of its last entry (0: none)
+};
+
+__global__ void resetKernel(State s, size_t n, int max_d2)
+{  // reset() :506-524
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    s.dist[i] = max_d2;
+    s.cp[i] = 0;
+    s.dir[i] = 0;
+    s.first[i] = kNone;
+    s.lastp1[i] = 0;
+  }
+}
+
+struct Seg
+{
+  unsigned long long start;
+  uint32_t len, out;
+};
+__global__ void gatherKernel(const uint32_t* __restrict__ pool, const Seg* __restrict__ segs, int n_segs, uint32_t* __restrict__ L)
+{
+  for (int k = blockIdx.y; k < n_segs; k += gridDim.y)
+  {
+    const Seg sg = segs[k];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < sg.len; j += gridDim.x * blockDim.x)
+      L[sg.out + j] = pool[sg.start + j];
+  }
+}
+
+// round control block on the device
+struct RoundCtl
+{
+  uint32_t cut;        // earliest position a hazard touches (init: the round's end)
+  uint32_t hazards;    // accepted offers that touched a later entry of their own round
+  uint32_t backward;   // accepted offers to a bucket at or below the one being drained
+  uint32_t pad;
+};
+
+__global__ void stampKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t b, State s)
+{
+  const uint32_t p = a + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= b)
+    return;
+  const uint32_t v = L[p];
+  atomicMin(&s.first[v], p);
+  atomicMax(&s.lastp1[v], p + 1);
+}
+__global__ void unstampKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t b, State s)
+{
+  const uint32_t p = a + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= b)
+    return;
+  const uint32_t v = L[p];
+  s.first[v] = kNone;
+  s.lastp1[v] = 0;
+}
+
+// every offer of entries [a, b) of bucket i: rec_key = its distance if it is accepted (kNoKey otherwise), rec_val = the target,
+// rec_cp = the closest point it carries | the direction number of the step << 48.  Reads the state, writes none of it.
+template <int S>
+__global__ void __launch_bounds__(256) offerKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t b, int bucket, Dims g,
+                                                   int max_d2, State s, uint16_t* __restrict__ rec_key,
+                                                   uint32_t* __restrict__ rec_val, uint64_t* __restrict__ rec_cp, RoundCtl* ctl)
+{
+  constexpr int D = S == 26 ? 0 : 1;
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t n_rec = static_cast<size_t>(b - a) * S;
+  if (idx >= n_rec)
+    return;
+  const uint32_t p = a + static_cast<uint32_t>(idx / S);
+  const int slot = static_cast<int>(idx % S);
+  uint16_t key_out = kNoKey;
+  const uint32_t v = L[p];
+  const int dv = s.dir[v];
+  if (dv <= 26 && slot < c_nb.cnt[D][dv])
+  {
+    const int ex = c_nb.nb[D][dv][slot][0], ey = c_nb.nb[D][dv][slot][1], ez = c_nb.nb[D][dv][slot][2];
+    int vx, vy, vz;
+    coordsOf(g, v, vx, vy, vz);
+    const int tx = vx + ex, ty = vy + ey, tz = vz + ez;
+    if (validCell(g, tx, ty, tz))
+    {
+      const uint64_t cpv = s.cp[v];
+      int cx, cy, cz;
+      unpackPoint(cpv, cx, cy, cz);
+      const long long nd = sq3(cx - tx, cy - ty, cz - tz);
+      const uint32_t t = refOf(g, tx, ty, tz);
+      if (nd <= max_d2 && nd < s.dist[t])
+      {
+        bool acc = true;
+        const unsigned long long key = static_cast<unsigned long long>(p) * S + slot;
+        // the other entries of this round that make an offer to t: all of t's neighbours u = t - step
+        for (int k = 0; k < 27 && acc; ++k)
+        {
+          const int sx = k / 9 - 1, sy = (k / 3) % 3 - 1, sz = k % 3 - 1;
+          if (k == 13 || (D == 1 && abs(sx) + abs(sy) + abs(sz) != 1))
+            continue;
+          const int ux = tx - sx, uy = ty - sy, uz = tz - sz;
+          if (!validCell(g, ux, uy, uz))
+            continue;
+          const uint32_t u = refOf(g, ux, uy, uz);
+          const uint32_t fp = s.first[u];
+          if (fp == kNone)
+            continue;
+          const int du = s.dir[u];
+          if (du > 26)
+            continue;
+          const int slot_u = c_nb.slot[D][du][k];
+          if (slot_u < 0)
+            continue;
+          const unsigned long long key_u = static_cast<unsigned long long>(fp) * S + slot_u;
+          if (key_u >= key)
+            continue;
+          int ux2, uy2, uz2;
+          unpackPoint(s.cp[u], ux2, uy2, uz2);
+          const long long nd_u = sq3(ux2 - tx, uy2 - ty, uz2 - tz);
+          if (nd_u <= max_d2 && nd_u <= nd)
+            acc = false;
+        }
+        if (acc)
+        {
+          key_out = static_cast<uint16_t>(nd);
+          rec_val[idx] = t;
+          rec_cp[idx] = (cpv & kPointMask) | (static_cast<uint64_t>((ex + 1) * 9 + (ey + 1) * 3 + ez + 1) << 48);
+          const uint32_t lp1 = s.lastp1[t];
+          if (lp1 > p + 1)
+          {  // t still has an entry behind this one: its state would change under it
+            const uint32_t ft = s.first[t];
+            atomicMin(&ctl->cut, ft > p ? ft : p + 1);
+            atomicAdd(&ctl->hazards, 1u);
+          }
+        }
+      }
+    }
+  }
+  rec_key[idx] = key_out;
+}
+
+template <int S>
+__global__ void applyMinKernel(uint32_t a, size_t n_rec, const uint16_t* __restrict__ rec_key, const uint32_t* __restrict__ rec_val,
+                               State s, const RoundCtl* ctl)
+{
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= n_rec)
+    return;
+  const uint16_t k = rec_key[idx];
+  if (k == kNoKey || a + static_cast<uint32_t>(idx / S) >= ctl->cut)
+    return;
+  atomicMin(&s.dist[rec_val[idx]], static_cast<int32_t>(k));
+}
+
+// the accepted offer of smallest distance is the target's state; keys become the sort keys of the queue entries
+template <int S>
+__global__ void applyStateKernel(uint32_t a, size_t n_rec, int bucket, uint16_t* __restrict__ rec_key,
+                                 const uint32_t* __restrict__ rec_val, const uint64_t* __restrict__ rec_cp, State s, RoundCtl* ctl)
+{
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= n_rec)
+    return;
+  const uint16_t k = rec_key[idx];
+  if (k == kNoKey)
+    return;
+  if (a + static_cast<uint32_t>(idx / S) >= ctl->cut)
+  {
+    rec_key[idx] = kNoKey;  // behind the cut: redone in the next round
+    return;
+  }
+  const uint32_t t = rec_val[idx];
+  if (s.dist[t] == static_cast<int32_t>(k))
+  {
+    const uint64_t r = rec_cp[idx];
+    s.cp[t] = r & kPointMask;
+    s.dir[t] = static_cast<uint8_t>(r >> 48);
+  }
+  if (static_cast<int>(k) <= bucket)
+    atomicAdd(&ctl->backward, 1u);
+  if (static_cast<int>(k) == bucket)
+    rec_key[idx] = kNoKey;  // pushed behind the end captured before the loop (:398), cleared with the bucket (:441)
+}
+
+// runs of equal keys in the sorted records -> [start, end) per destination bucket
+__global__ void runsKernel(const uint16_t* __restrict__ keys, size_t n, uint32_t* __restrict__ starts, uint32_t* __restrict__ ends)
+{
+  const size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (j >= n)
+    return;
+  const uint16_t k = keys[j];
+  if (k == kNoKey)
+    return;
+  if (j == 0 || keys[j - 1] != k)
+    starts[k] = static_cast<uint32_t>(j);
+  if (j + 1 == n || keys[j + 1] != k)
+    ends[k] = static_cast<uint32_t>(j + 1);
+}
+
+__global__ void roundInitKernel(RoundCtl* ctl, uint32_t cut, uint32_t* starts, uint32_t* ends, int n_buckets)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0)
+    ctl->cut = cut;
+  if (j < n_buckets)
+  {
+    starts[j] = 0;
+    ends[j] = 0;
+  }
+}
+
+// ---- point lists -> voxel lists -----------------------------------------------------------------------------------------
+// worldToGrid (voxel_grid.hpp:395-407) in double, as scatterKernel.  mode 0: addPointsToField (:177-196) keeps valid points
+// whose voxel is not an obstacle yet; mode 1: removePointsFromField (:198-219) keeps every valid point.
+__global__ void pointsToVoxelsKernel(const double* __restrict__ xyz, size_t n, GridDev gd, const int32_t* __restrict__ dist, int mode,
+                                     uint16_t* __restrict__ rec_key, uint32_t* __restrict__ rec_val)
+{
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n)
+    return;
+  const int x = static_cast<int>(floor((xyz[3 * i] - gd.om[0]) * gd.oo));
+  const int y = static_cast<int>(floor((xyz[3 * i + 1] - gd.om[1]) * gd.oo));
+  const int z = static_cast<int>(floor((xyz[3 * i + 2] - gd.om[2]) * gd.oo));
+  uint16_t k = kNoKey;
+  uint32_t v = 0;
+  if (x >= 0 && y >= 0 && z >= 0 && x < gd.nx && y < gd.ny && z < gd.nz)
+  {
+    v = (static_cast<uint32_t>(x) * gd.ny + y) * gd.nz + z;
+    if (mode == 1 || dist[v] > 0)
+      k = 0;
+  }
+  rec_key[i] = k;
+  rec_val[i] = v;
+}
+
+// addNewObstacleVoxels :221-243 / removeObstacleVoxels :303-330: the listed voxels' own records
+__global__ void markVoxelsKernel(const uint32_t* __restrict__ vox, uint32_t n, Dims g, State s, int dist_value)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const uint32_t v = vox[i];
+  int x, y, z;
+  coordsOf(g, v, x, y, z);
+  s.dist[v] = dist_value;
+  s.cp[v] = packPoint(x, y, z);
+  s.dir[v] = kInitialDirection;
+}
+
+// removeObstacleVoxels' flood (:332-384), one warp, the reference's order.  stack: [sp] entries; out: bucket-0 entries.
+struct FloodCtl
+{
+  unsigned long long sp, out_n;
+};
+__global__ void floodKernel(Dims g, int max_d2, State s, uint32_t* stack, uint32_t* out, unsigned long long out_cap, FloodCtl* ctl)
+{
+  const int lane = threadIdx.x;
+  unsigned long long sp = ctl->sp, out_n = ctl->out_n;
+  const int ex = lane / 9 - 1, ey = (lane / 3) % 3 - 1, ez = lane % 3 - 1;  // direction_number_to_direction_[lane]
+  while (sp > 0 && out_n + 27 <= out_cap)
+  {
+    const uint32_t loc = stack[sp - 1];
+    --sp;
+    int lx, ly, lz;
+    coordsOf(g, loc, lx, ly, lz);
+    bool push_stack = false, push_bucket = false;
+    uint32_t nv = 0;
+    if (lane < 27)
+    {
+      const int nx = lx + ex, ny = ly + ey, nz = lz + ez;
+      if (validCell(g, nx, ny, nz))
+      {
+        nv = refOf(g, nx, ny, nz);
+        uint64_t cpn = s.cp[nv];
+        int cx, cy, cz;
+        unpackPoint(cpn, cx, cy, cz);
+        if (!validCell(g, cx, cy, cz))
+        {  // :350-354: an uninitialised closest point becomes the voxel itself
+          cx = nx;
+          cy = ny;
+          cz = nz;
+          s.cp[nv] = packPoint(nx, ny, nz);
+        }
+        if (s.dist[refOf(g, cx, cy, cz)] != 0)
+        {  // the closest point is no obstacle any more
+          if (s.dist[nv] != max_d2)
+          {
+            s.dist[nv] = max_d2;
+            s.cp[nv] = packPoint(nx, ny, nz);
+            s.dir[nv] = kInitialDirection;
+            push_stack = true;
+          }
+        }
+        else
+        {
+          s.dir[nv] = kInitialDirection;
+          push_bucket = true;
+        }
+      }
+    }
+    const unsigned ms = __ballot_sync(0xffffffffu, push_stack), mb = __ballot_sync(0xffffffffu, push_bucket);
+    const unsigned lt = (1u << lane) - 1u;
+    if (push_stack)
+      stack[sp + __popc(ms & lt)] = nv;
+    if (push_bucket)
+      out[out_n + __popc(mb & lt)] = nv;
+    sp += __popc(ms);
+    out_n += __popc(mb);
+    __syncwarp();
+  }
+  if (lane == 0)
+  {
+    ctl->sp = sp;
+    ctl->out_n = out_n;
+  }
+}
+
+// ---- updatePointsInField (:130-175): VoxelSets ordered by z, y, x (propagation_distance_field.hpp:60-75) -----------------
+__global__ void pointsToSetKeysKernel(const double* __restrict__ xyz, size_t n, GridDev gd, uint32_t* __restrict__ keys, uint32_t* bits)
+{
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n)
+    return;
+  const int x = static_cast<int>(floor((xyz[3 * i] - gd.om[0]) * gd.oo));
+  const int y = static_cast<int>(floor((xyz[3 * i + 1] - gd.om[1]) * gd.oo));
+  const int z = static_cast<int>(floor((xyz[3 * i + 2] - gd.om[2]) * gd.oo));
+  uint32_t k = kNone;
+  if (x >= 0 && y >= 0 && z >= 0 && x < gd.nx && y < gd.ny && z < gd.nz)
+  {
+    k = (static_cast<uint32_t>(z) * gd.ny + y) * gd.nx + x;
+    atomicOr(&bits[k >> 5], 1u << (k & 31));
+  }
+  keys[i] = k;
+}
+// sorted set keys -> records: kept iff first of its run, not in the other set, and (filter_obstacles) not an obstacle already
+__global__ void setDifferenceKernel(const uint32_t* __restrict__ keys, size_t n, GridDev gd, const uint32_t* __restrict__ other_bits,
+                                    const int32_t* __restrict__ dist, int filter_obstacles, uint16_t* __restrict__ rec_key,
+                                    uint32_t* __restrict__ rec_val)
+{
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n)
+    return;
+  const uint32_t k = keys[i];
+  uint16_t out = kNoKey;
+  uint32_t v = 0;
+  if (k != kNone && (i == 0 || keys[i - 1] != k) && !((other_bits[k >> 5] >> (k & 31)) & 1u))
+  {
+    const uint32_t x = k % gd.nx, r = k / gd.nx, y = r % gd.ny, z = r / gd.ny;
+    v = (x * gd.ny + y) * gd.nz + z;
+    if (!filter_obstacles || dist[v] != 0)
+      out = 0;
+  }
+  rec_key[i] = out;
+  rec_val[i] = v;
+}
+
+template <typename T>
+struct Buf
+{
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n, bool keep = false, size_t keep_n = 0, cudaStream_t s = nullptr)
+  {
+    if (n <= cap)
+      return cudaSuccess;
+    const size_t want = std::max<size_t>(std::max<size_t>(n, 4096), keep ? cap * 2 : 0);
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    if (e != cudaSuccess)
+      return e;
+    if (p)
+    {
+      if (keep && keep_n)
+      {
+        e = cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess)
+          e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess)
+        {
+          cudaFree(q);
+          return e;
+        }
+      }
+      cudaFree(p);
+    }
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct HostSeg
+{
+  size_t start;
+  uint32_t len;
+};
+}  // namespace
+
+struct PropField
+{
+  GridDev gd;
+  Dims g;
+  size_t n_vox = 0;
+  State st{};
+  std::vector<std::vector<HostSeg>> buckets;  // bucket_queue_: segments of the pool, in push order
+  Buf<uint32_t> pool;                         // queue entries (voxel references)
+  size_t pool_off = 0;
+  Buf<uint32_t> L;  // the bucket being drained, contiguous
+  Buf<uint16_t> key_in, key_out;
+  Buf<uint32_t> val_in, set_keys, set_keys_sorted, stack;
+  Buf<uint64_t> rec_cp;
+  Buf<uint8_t> sort_tmp;
+  Buf<uint32_t> set_bits;
+  Buf<Seg> d_segs;
+  RoundCtl* d_ctl = nullptr;
+  FloodCtl* d_flood = nullptr;
+  uint32_t *d_starts = nullptr, *d_ends = nullptr;
+  // pinned mirror: ctl | starts | ends
+  uint8_t* h_pin = nullptr;
+  Seg* h_segs = nullptr;
+  size_t h_segs_cap = 0;
+  PropStats stats{};
+};
+
+namespace
+{
+#define PCK(x)                    \
+  do                              \
+  {                               \
+    cudaError_t e_ = (x);         \
+    if (e_ != cudaSuccess)        \
+      return e_;                  \
+  } while (0)
+
+inline unsigned blocksFor(size_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+// stable sort of n records by their 16-bit key; values land at `out_vals`
+cudaError_t sortRecords(PropField* f, size_t n, uint32_t* out_vals, cudaStream_t s)
+{
+  size_t tmp = 0;
+  PCK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, f->key_in.p, f->key_out.p, f->val_in.p, out_vals, n, 0, 16, s));
+  PCK(f->sort_tmp.ensure(tmp));
+  return cub::DeviceRadixSort::SortPairs(f->sort_tmp.p, tmp, f->key_in.p, f->key_out.p, f->val_in.p, out_vals, n, 0, 16, s);
+}
+
+cudaError_t ensureRecords(PropField* f, size_t n, bool with_cp)
+{
+  PCK(f->key_in.ensure(n));
+  PCK(f->key_out.ensure(n));
+  PCK(f->val_in.ensure(n));
+  if (with_cp)
+    PCK(f->rec_cp.ensure(n));
+  return cudaSuccess;
+}
+
+// sorted records -> the count of kept ones (key 0); they sit at out_vals[0 .. count)
+cudaError_t keptCount(PropField* f, size_t n, cudaStream_t s, uint32_t* count)
+{
+  const int nb = f->gd.max_d2 + 1;
+  roundInitKernel<<<blocksFor(nb, 256), 256, 0, s>>>(f->d_ctl, 0, f->d_starts, f->d_ends, nb);
+  runsKernel<<<blocksFor(n, 256), 256, 0, s>>>(f->key_out.p, n, f->d_starts, f->d_ends);
+  PCK(cudaGetLastError());
+  PCK(cudaMemcpyAsync(f->h_pin, f->d_ends, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  PCK(cudaStreamSynchronize(s));
+  *count = *reinterpret_cast<uint32_t*>(f->h_pin);
+  return cudaSuccess;
+}
+
+cudaError_t propagate(PropField* f, cudaStream_t s)
+{
+  const int nb = f->gd.max_d2 + 1;
+  constexpr size_t kMaxRecords = size_t(1) << 25;
+  for (int i = 0; i < nb; ++i)
+  {
+    std::vector<HostSeg>& segs = f->buckets[i];
+    if (segs.empty())
+      continue;
+    size_t total = 0;
+    for (const HostSeg& sg : segs)
+      total += sg.len;
+    if (total == 0 || total >= 0xfffffff0ull)
+    {
+      segs.clear();
+      if (total)
+        return cudaErrorInvalidValue;
+      continue;
+    }
+    // the bucket, contiguous; its list is empty from here on: what is pushed into it while it drains never runs (:398, :441)
+    if (segs.size() > f->h_segs_cap)
+    {
+      if (f->h_segs)
+        cudaFreeHost(f->h_segs);
+      f->h_segs = nullptr;
+      f->h_segs_cap = 0;
+      PCK(cudaMallocHost(&f->h_segs, 2 * segs.size() * sizeof(Seg)));
+      f->h_segs_cap = 2 * segs.size();
+    }
+    PCK(f->d_segs.ensure(segs.size()));
+    PCK(f->L.ensure(total));
+    {
+      uint32_t out = 0, longest = 0;
+      for (size_t k = 0; k < segs.size(); ++k)
+      {
+        f->h_segs[k] = Seg{ segs[k].start, segs[k].len, out };
+        out += segs[k].len;
+        longest = std::max(longest, segs[k].len);
+      }
+      PCK(cudaMemcpyAsync(f->d_segs.p, f->h_segs, segs.size() * sizeof(Seg), cudaMemcpyHostToDevice, s));
+      dim3 grid(std::max(1u, std::min(blocksFor(longest, 256), 4096u)), static_cast<unsigned>(std::min<size_t>(segs.size(), 1024)));
+      gatherKernel<<<grid, 256, 0, s>>>(f->pool.p, f->d_segs.p, static_cast<int>(segs.size()), f->L.p);
+      PCK(cudaGetLastError());
+      PCK(cudaStreamSynchronize(s));  // h_segs is reused by the next bucket
+    }
+    segs.clear();
+    f->stats.entries += total;
+    const int S = i == 0 ? 26 : 6;
+    uint32_t a = 0;
+    const uint32_t end = static_cast<uint32_t>(total);
+    while (a < end)
+    {
+      const uint32_t b = static_cast<uint32_t>(std::min<size_t>(end, a + kMaxRecords / S));
+      const size_t n_rec = static_cast<size_t>(b - a) * S;
+      PCK(ensureRecords(f, n_rec, true));
+      PCK(f->pool.ensure(f->pool_off + n_rec, true, f->pool_off, s));
+      roundInitKernel<<<blocksFor(nb, 256), 256, 0, s>>>(f->d_ctl, b, f->d_starts, f->d_ends, nb);
+      stampKernel<<<blocksFor(b - a, 256), 256, 0, s>>>(f->L.p, a, b, f->st);
+      if (S == 26)
+      {
+        offerKernel<26><<<blocksFor(n_rec, 256), 256, 0, s>>>(f->L.p, a, b, i, f->g, f->gd.max_d2, f->st, f->key_in.p, f->val_in.p,
+                                                             f->rec_cp.p, f->d_ctl);
+        applyMinKernel<26><<<blocksFor(n_rec, 256), 256, 0, s>>>(a, n_rec, f->key_in.p, f->val_in.p, f->st, f->d_ctl);
+        applyStateKernel<26><<<blocksFor(n_rec, 256), 256, 0, s>>>(a, n_rec, i, f->key_in.p, f->val_in.p, f->rec_cp.p, f->st, f->d_ctl);
+      }
+      else
+      {
+        offerKernel<6><<<blocksFor(n_rec, 256), 256, 0, s>>>(f->L.p, a, b, i, f->g, f->gd.max_d2, f->st, f->key_in.p, f->val_in.p,
+                                                            f->rec_cp.p, f->d_ctl);
+        applyMinKernel<6><<<blocksFor(n_rec, 256), 256, 0, s>>>(a, n_rec, f->key_in.p, f->val_in.p, f->st, f->d_ctl);
+        applyStateKernel<6><<<blocksFor(n_rec, 256), 256, 0, s>>>(a, n_rec, i, f->key_in.p, f->val_in.p, f->rec_cp.p, f->st, f->d_ctl);
+      }
+      PCK(cudaGetLastError());
+      PCK(sortRecords(f, n_rec, f->pool.p + f->pool_off, s));
+      runsKernel<<<blocksFor(n_rec, 256), 256, 0, s>>>(f->key_out.p, n_rec, f->d_starts, f->d_ends);
+      unstampKernel<<<blocksFor(b - a, 256), 256, 0, s>>>(f->L.p, a, b, f->st);
+      PCK(cudaGetLastError());
+      uint8_t* h = f->h_pin;
+      PCK(cudaMemcpyAsync(h, f->d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, s));
+      PCK(cudaMemcpyAsync(h + sizeof(RoundCtl), f->d_starts, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      PCK(cudaMemcpyAsync(h + sizeof(RoundCtl) + nb * sizeof(uint32_t), f->d_ends, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      PCK(cudaStreamSynchronize(s));
+      const RoundCtl* ctl = reinterpret_cast<const RoundCtl*>(h);
+      const uint32_t* starts = reinterpret_cast<const uint32_t*>(h + sizeof(RoundCtl));
+      const uint32_t* ends = starts + nb;
+      uint32_t pushed = 0;
+      for (int j = 0; j < nb; ++j)
+        if (ends[j] != 0)
+        {
+          f->buckets[j].push_back(HostSeg{ f->pool_off + starts[j], ends[j] - starts[j] });
+          pushed = std::max(pushed, ends[j]);
+        }
+      f->pool_off += pushed;
+      ++f->stats.rounds;
+      if (ctl->cut <= a || ctl->cut > b)
+        return cudaErrorAssert;  // cannot happen: a hazard's position lies behind the entry that raised it
+      if (ctl->cut < b)
+        ++f->stats.hazard_rounds;
+      a = ctl->cut;
+    }
+  }
+  {  // counters, and the pool: entries pushed "backwards" stay queued for the next call (rare), everything else is spent
+    PCK(cudaMemcpyAsync(f->h_pin, f->d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, s));
+    PCK(cudaStreamSynchronize(s));
+    f->stats.backward_offers = reinterpret_cast<const RoundCtl*>(f->h_pin)->backward;
+    f->stats.hazard_offers = reinterpret_cast<const RoundCtl*>(f->h_pin)->hazards;
+    size_t left = 0;
+    for (const auto& b : f->buckets)
+      for (const HostSeg& sg : b)
+        left += sg.len;
+    f->stats.queued_for_next_call = left;
+    if (left == 0)
+      f->pool_off = 0;
+    else
+    {
+      PCK(f->L.ensure(left));
+      size_t out = 0;
+      for (auto& b : f->buckets)
+        for (HostSeg& sg : b)
+        {
+          PCK(cudaMemcpyAsync(f->L.p + out, f->pool.p + sg.start, sg.len * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+          sg.start = out;
+          out += sg.len;
+        }
+      PCK(cudaMemcpyAsync(f->pool.p, f->L.p, left * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      PCK(cudaStreamSynchronize(s));
+      f->pool_off = left;
+    }
+  }
+  return cudaSuccess;
+}
+
+// addNewObstacleVoxels (:221-301, unsigned field) for `count` voxels already at pool[pool_off ..)
+cudaError_t addVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
+{
+  if (count)
+  {
+    markVoxelsKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->pool.p + f->pool_off, count, f->g, f->st, 0);
+    PCK(cudaGetLastError());
+    f->buckets[0].push_back(HostSeg{ f->pool_off, count });
+    f->pool_off += count;
+  }
+  return propagate(f, s);
+}
+
+// removeObstacleVoxels (:303-388, unsigned field) for `count` voxels at pool[pool_off ..) (not consumed as queue entries)
+cudaError_t removeVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
+{
+  const size_t stack_cap = static_cast<size_t>(count) + f->n_vox + 32;
+  PCK(f->stack.ensure(stack_cap));
+  if (count)
+  {
+    PCK(cudaMemcpyAsync(f->stack.p, f->pool.p + f->pool_off, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    markVoxelsKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->stack.p, count, f->g, f->st, f->gd.max_d2);
+    PCK(cudaGetLastError());
+  }
+  FloodCtl fc{ count, 0 };
+  PCK(cudaMemcpyAsync(f->d_flood, &fc, sizeof(fc), cudaMemcpyHostToDevice, s));
+  PCK(cudaStreamSynchronize(s));
+  size_t seg_start = f->pool_off;
+  while (fc.sp > 0)
+  {
+    PCK(f->pool.ensure(f->pool_off + std::max<size_t>(size_t(1) << 20, 64 * fc.sp), true, f->pool_off, s));
+    const unsigned long long room = f->pool.cap - f->pool_off;
+    fc.out_n = 0;
+    PCK(cudaMemcpyAsync(f->d_flood, &fc, sizeof(fc), cudaMemcpyHostToDevice, s));
+    floodKernel<<<1, 32, 0, s>>>(f->g, f->gd.max_d2, f->st, f->stack.p, f->pool.p + f->pool_off, room, f->d_flood);
+    PCK(cudaGetLastError());
+    PCK(cudaMemcpyAsync(f->h_pin, f->d_flood, sizeof(fc), cudaMemcpyDeviceToHost, s));
+    PCK(cudaStreamSynchronize(s));
+    std::memcpy(&fc, f->h_pin, sizeof(fc));
+    f->pool_off += fc.out_n;
+    f->stats.flood_pops_batches++;
+  }
+  // one segment, or several of at most 2^32 - 1 entries
+  for (size_t at = seg_start; at < f->pool_off;)
+  {
+    const uint32_t len = static_cast<uint32_t>(std::min<size_t>(f->pool_off - at, 0x7fffffffu));
+    f->buckets[0].push_back(HostSeg{ at, len });
+    at += len;
+  }
+  return propagate(f, s);
+}
+
+cudaError_t pointsToPool(PropField* f, const double* d_xyz, size_t n, int mode, cudaStream_t s, uint32_t* count)
+{
+  *count = 0;
+  if (n == 0)
+    return cudaSuccess;
+  PCK(ensureRecords(f, n, false));
+  PCK(f->pool.ensure(f->pool_off + n, true, f->pool_off, s));
+  pointsToVoxelsKernel<<<blocksFor(n, 256), 256, 0, s>>>(d_xyz, n, f->gd, f->st.dist, mode, f->key_in.p, f->val_in.p);
+  PCK(cudaGetLastError());
+  PCK(sortRecords(f, n, f->pool.p + f->pool_off, s));
+  return keptCount(f, n, s, count);
+}
+}  // namespace
+
+cudaError_t propCreate(const GridDev& gd, PropField** out)
+{
+  *out = nullptr;
+  if (gd.nx > 65534 || gd.ny > 65534 || gd.nz > 65534 || gd.max_d2 >= 0xffff)
+    return cudaErrorInvalidConfiguration;
+  PropField* f = new PropField();
+  f->gd = gd;
+  f->g = Dims{ gd.nx, gd.ny, gd.nz };
+  f->n_vox = static_cast<size_t>(gd.nx) * gd.ny * gd.nz;
+  f->buckets.resize(gd.max_d2 + 1);
+  const NeighbourTables t = makeTables();
+  cudaError_t e = cudaMemcpyToSymbol(c_nb, &t, sizeof(t));
+  const int nb = gd.max_d2 + 1;
+  if (e == cudaSuccess) e = cudaMalloc(&f->st.dist, f->n_vox * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&f->st.cp, f->n_vox * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMalloc(&f->st.dir, f->n_vox);
+  if (e == cudaSuccess) e = cudaMalloc(&f->st.first, f->n_vox * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&f->st.lastp1, f->n_vox * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_ctl, sizeof(RoundCtl));
+  if (e == cudaSuccess) e = cudaMemset(f->d_ctl, 0, sizeof(RoundCtl));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_flood, sizeof(FloodCtl));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_starts, nb * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_ends, nb * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMallocHost(&f->h_pin, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t) + 64);
+  if (e != cudaSuccess)
+  {
+    propDestroy(f);
+    return e;
+  }
+  *out = f;
+  return cudaSuccess;
+}
+
+void propDestroy(PropField* f)
+{
+  if (!f)
+    return;
+  cudaFree(f->st.dist);
+  cudaFree(f->st.cp);
+  cudaFree(f->st.dir);
+  cudaFree(f->st.first);
+  cudaFree(f->st.lastp1);
+  cudaFree(f->d_ctl);
+  cudaFree(f->d_flood);
+  cudaFree(f->d_starts);
+  cudaFree(f->d_ends);
+  if (f->h_pin)
+    cudaFreeHost(f->h_pin);
+  if (f->h_segs)
+    cudaFreeHost(f->h_segs);
+  f->pool.release();
+  f->L.release();
+  f->key_in.release();
+  f->key_out.release();
+  f->val_in.release();
+  f->set_keys.release();
+  f->set_keys_sorted.release();
+  f->stack.release();
+  f->rec_cp.release();
+  f->sort_tmp.release();
+  f->set_bits.release();
+  f->d_segs.release();
+  delete f;
+}
+
+cudaError_t propReset(PropField* f, cudaStream_t s)
+{  // reset() re-initialises the voxels; the bucket queues are not its business (entries left there stay queued)
+  resetKernel<<<148 * 8, 256, 0, s>>>(f->st, f->n_vox, f->gd.max_d2);
+  return cudaGetLastError();
+}
+
+cudaError_t propAddPoints(PropField* f, const double* d_xyz, size_t n, cudaStream_t s)
+{
+  uint32_t count = 0;
+  PCK(pointsToPool(f, d_xyz, n, 0, s, &count));
+  return addVoxelsAtPool(f, count, s);
+}
+
+cudaError_t propRemovePoints(PropField* f, const double* d_xyz, size_t n, cudaStream_t s)
+{
+  uint32_t count = 0;
+  PCK(pointsToPool(f, d_xyz, n, 1, s, &count));
+  return removeVoxelsAtPool(f, count, s);
+}
+
+cudaError_t propUpdatePoints(PropField* f, const double* d_old, size_t n_old, const double* d_new, size_t n_new, cudaStream_t s)
+{
+  const size_t n_words = (f->n_vox + 31) / 32;
+  PCK(f->set_bits.ensure(2 * n_words));
+  PCK(cudaMemsetAsync(f->set_bits.p, 0, 2 * n_words * sizeof(uint32_t), s));
+  uint32_t* bits[2] = { f->set_bits.p, f->set_bits.p + n_words };
+  const double* pts[2] = { d_old, d_new };
+  const size_t cnt[2] = { n_old, n_new };
+  const size_t n_max = std::max<size_t>(std::max(n_old, n_new), 1);
+  PCK(f->set_keys.ensure(2 * n_max));
+  PCK(f->set_keys_sorted.ensure(2 * n_max));
+  for (int w = 0; w < 2; ++w)
+    if (cnt[w])
+    {
+      pointsToSetKeysKernel<<<blocksFor(cnt[w], 256), 256, 0, s>>>(pts[w], cnt[w], f->gd, f->set_keys.p + w * n_max, bits[w]);
+      PCK(cudaGetLastError());
+      size_t tmp = 0;
+      PCK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, f->set_keys.p + w * n_max, f->set_keys_sorted.p + w * n_max, cnt[w], 0, 32, s));
+      PCK(f->sort_tmp.ensure(tmp));
+      PCK(cub::DeviceRadixSort::SortKeys(f->sort_tmp.p, tmp, f->set_keys.p + w * n_max, f->set_keys_sorted.p + w * n_max, cnt[w], 0, 32, s));
+    }
+  // both differences are taken (and new \ old filtered by "is no obstacle yet") BEFORE anything is removed (:156-172)
+  uint32_t n_rem = 0, n_add = 0;
+  PCK(ensureRecords(f, n_max, false));
+  PCK(f->pool.ensure(f->pool_off + n_old + n_new + 64, true, f->pool_off, s));
+  if (n_old)
+  {
+    setDifferenceKernel<<<blocksFor(n_old, 256), 256, 0, s>>>(f->set_keys_sorted.p, n_old, f->gd, bits[1], f->st.dist, 0, f->key_in.p,
+                                                             f->val_in.p);
+    PCK(cudaGetLastError());
+    PCK(sortRecords(f, n_old, f->pool.p + f->pool_off, s));
+    PCK(keptCount(f, n_old, s, &n_rem));
+  }
+  uint32_t* add_list = nullptr;
+  if (n_new)
+  {
+    setDifferenceKernel<<<blocksFor(n_new, 256), 256, 0, s>>>(f->set_keys_sorted.p + n_max, n_new, f->gd, bits[0], f->st.dist, 1,
+                                                             f->key_in.p, f->val_in.p);
+    PCK(cudaGetLastError());
+    // parked in the set-key buffer while the removal uses the pool
+    add_list = f->set_keys.p;
+    PCK(sortRecords(f, n_new, add_list, s));
+    PCK(keptCount(f, n_new, s, &n_add));
+  }
+  PCK(removeVoxelsAtPool(f, n_rem, s));
+  PCK(f->pool.ensure(f->pool_off + n_add + 64, true, f->pool_off, s));
+  if (n_add)
+    PCK(cudaMemcpyAsync(f->pool.p + f->pool_off, add_list, n_add * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  return addVoxelsAtPool(f, n_add, s);
+}
+
+const int32_t* propDistances(const PropField* f) { return f->st.dist; }
+const PropStats& propStats(const PropField* f) { return f->stats; }
+}  // namespace b200sv

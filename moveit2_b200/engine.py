@@ -205,6 +205,17 @@ class StateValidityEngine:
     def field_reset(self, which=FIELD_WORLD):
         self._check(self.L.b200sv_field_reset(self.h, which))
 
+    def field_set_propagation(self, mode, which=FIELD_WORLD):
+        """_lib.PROPAGATION_EXACT (default: exact truncated EDT) or _lib.PROPAGATION_REFERENCE (the reference's bucket-queue
+        propagation reproduced on the device: distances equal PropagationDistanceField's after the same calls).  Resets the
+        field."""
+        self._check(self.L.b200sv_field_set_propagation(self.h, which, int(mode)))
+
+    def field_propagation_stats(self, which=FIELD_WORLD):
+        st = _lib.PropagationStats()
+        self._check(self.L.b200sv_field_propagation_stats(self.h, which, C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in st._fields_}
+
     def field_begin_update(self, which=FIELD_WORLD):
         """Bracket several occupancy edits; field_end_update runs the EDT once."""
         self._check(self.L.b200sv_field_begin_update(self.h, which))

@@ -1,0 +1,173 @@
+"""GPU parity tests of B200SV_PROPAGATION_REFERENCE (run on the B200 box: pytest -m gpu): the field reproduces
+PropagationDistanceField's bucket-queue propagation (distance_field/src/propagation_distance_field.cpp:177-444) voxel for
+voxel -- compared with the oracle's C restatement after the same sequence of add / remove / update calls, the sizes of
+distance_field/test/test_distance_field.cpp and BASELINE.json's C1, C2 and C4."""
+import numpy as np
+import pytest
+
+import moveit2_b200 as mb
+from moveit2_b200 import workloads
+from oracle.df import PropagationDistanceField
+
+from util import config_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def field_pair(size, origin, resolution, max_distance):
+    eng = mb.StateValidityEngine.for_robot("panda", "panda_arm", size=size, origin=origin, resolution=resolution,
+                                           max_distance=max_distance)
+    eng.field_set_propagation(mb.PROPAGATION_REFERENCE)
+    corner = [o - s / 2 for o, s in zip(origin, size)]
+    ref = PropagationDistanceField(size[0], size[1], size[2], resolution, corner[0], corner[1], corner[2], max_distance)
+    return eng, ref
+
+
+def same(eng, ref, what):
+    g, o = eng.field_get_d2(), ref.d2()
+    bad = int((g != o).sum())
+    assert bad == 0, "%s: %d of %d voxels differ from the reference's propagation (max |delta| %d)" % (
+        what, bad, g.size, int(np.abs(g.astype(np.int64) - o).max()))
+
+
+def test_single_add_equals_the_reference_on_c1():
+    eng, env, cloud, q = config_pair("C1")
+    eng.field_set_propagation(mb.PROPAGATION_REFERENCE)
+    eng.field_add_points(cloud)
+    env.world.add_points(cloud)
+    same(eng, env.world, "C1 cloud")
+    exact_eng, _, _, _ = config_pair("C1")
+    exact_eng.field_add_points(cloud)
+    n_exact_differs = int((exact_eng.field_get_d2() != env.world.d2()).sum())
+    st = eng.field_propagation_stats()
+    print("C1: reference mode equal on all voxels (the exact transform differs in %d); %s" % (n_exact_differs, st))
+    assert st["rounds"] > 0 and st["queue_entries"] > 0
+    exact_eng.close()
+    eng.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_incremental_adds_with_duplicates_and_outside_points(seed):
+    """Several addPointsToField calls: each propagates from the state the one before left (closest points, update
+    directions, entries left in the queue), points outside the grid are skipped, duplicates are queued twice."""
+    rng = np.random.default_rng(seed)
+    size, origin = (0.8, 0.6, 0.5), (0.1, -0.2, 0.3)
+    eng, ref = field_pair(size, origin, 0.02, 0.2)
+    for call in range(5):
+        n = int(rng.integers(1, 400))
+        if call == 3:
+            ctr = rng.uniform(-0.3, 0.3, (8, 3)) * size + origin
+            pts = (ctr[:, None, :] + rng.normal(0, 0.03, (8, 60, 3))).reshape(-1, 3)
+        else:
+            pts = (rng.uniform(-0.6, 0.6, (n, 3)) * size + origin)
+        pts = np.concatenate([pts, pts[: len(pts) // 3]])  # duplicates
+        eng.field_add_points(pts)
+        ref.add_points(pts)
+        same(eng, ref, "seed %d call %d" % (seed, call))
+    eng.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_remove_and_update_points_equal_the_reference(seed):
+    """removePointsFromField (:198-219, :303-388: the depth-first flood from the removed voxels, then propagation from the
+    surviving boundary) and updatePointsInField (:130-175: ordered set differences, remove, add)."""
+    rng = np.random.default_rng(10 + seed)
+    size, origin = (0.6, 0.6, 0.6), (0.0, 0.0, 0.3)
+    eng, ref = field_pair(size, origin, 0.02, 0.16)
+    box = lambda c, h, n: rng.uniform(-1, 1, (n, 3)) * h + c
+    a = box((0.1, 0.0, 0.3), 0.05, 600)
+    b = box((-0.15, 0.1, 0.4), 0.04, 400)
+    c = rng.uniform(-0.5, 0.5, (150, 3)) * size + origin
+    for name, pts in (("a", a), ("b", b), ("c", c)):
+        eng.field_add_points(pts)
+        ref.add_points(pts)
+        same(eng, ref, "add " + name)
+    eng.field_remove_points(a)
+    ref.remove_points(a)
+    same(eng, ref, "remove a")
+    assert int((eng.field_get_d2() == 0).sum()) == int((ref.d2() == 0).sum())
+    # remove points that were never added, duplicates, points outside
+    junk = np.concatenate([rng.uniform(-0.7, 0.7, (50, 3)) * size + origin, c[:20], c[:20]])
+    eng.field_remove_points(junk)
+    ref.remove_points(junk)
+    same(eng, ref, "remove junk")
+    # the object moves: updatePointsInField(old, new)
+    b2 = b + np.array([0.06, -0.04, 0.02])
+    eng.field_update_points(b, b2)
+    ref.update_points(b, b2)
+    same(eng, ref, "update b -> b2")
+    eng.field_update_points(b2, b2[:0])
+    ref.update_points(b2, b2[:0])
+    same(eng, ref, "update b2 -> nothing")
+    eng.field_add_points(a)
+    ref.add_points(a)
+    same(eng, ref, "add a again")
+    # reset() and a fresh add
+    eng.field_reset()
+    ref.reset()
+    same(eng, ref, "reset")
+    eng.field_add_points(c)
+    ref.add_points(c)
+    same(eng, ref, "add c after reset")
+    print(eng.field_propagation_stats())
+    eng.close()
+
+
+def test_validity_with_each_sides_own_fields_is_identical_in_reference_mode():
+    """With the exact transform a handful of states per million differ from the reference when each side checks against
+    its OWN field (the EDT is never above the propagation).  In reference mode both fields are the reference's: no state
+    differs, world and self."""
+    eng, env, cloud, q = config_pair("C1", n_states=200_000)
+    eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_WORLD)
+    eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_SELF)
+    eng.field_add_points(cloud, mb.FIELD_WORLD)
+    eng.field_add_points(env.self_points, mb.FIELD_SELF)
+    env.world.add_points(cloud)
+    assert np.array_equal(eng.field_get_d2(mb.FIELD_WORLD), env.world.d2())
+    assert np.array_equal(eng.field_get_d2(mb.FIELD_SELF), env.self_field.d2())
+    ref, _ = env.check(q, mb.CHECK_ALL)
+    got = eng.check_batch(q, mb.CHECK_ALL)
+    assert np.array_equal(got, ref == 0)
+    eng.close()
+
+
+def test_entry_points_that_edit_bits_refuse_in_reference_mode():
+    eng, ref = field_pair((0.4, 0.4, 0.4), (0.0, 0.0, 0.2), 0.02, 0.1)
+    with pytest.raises(mb.B200svError):
+        eng.field_add_sphere((0.0, 0.0, 0.2), 0.05)
+    with pytest.raises(mb.B200svError):
+        eng.field_set_d2(np.zeros(eng.num_cells, np.int32))
+    with pytest.raises(mb.B200svError):
+        eng.field_begin_update()
+    # back to the exact transform: everything works again, the field starts empty
+    eng.field_set_propagation(mb.PROPAGATION_EXACT)
+    assert int((eng.field_get_d2() == 0).sum()) == 0
+    eng.field_add_sphere((0.0, 0.0, 0.2), 0.05)
+    assert int((eng.field_get_d2() == 0).sum()) > 0
+    eng.close()
+
+
+def test_c2_field_equals_the_reference():
+    """BASELINE.json configs[1]'s field: 500 000 points -> 200^3 voxels @ 1 cm, 25 cells."""
+    c2 = workloads.CONFIGS["C2"]
+    eng, ref = field_pair(c2["size"], c2["origin"], c2["resolution"], c2["max_distance"])
+    pts = workloads.make_cloud("C2")
+    eng.field_add_points(pts)
+    ms = eng.stats()["edt_ms"]
+    ref.add_points(pts)
+    same(eng, ref, "C2")
+    print("C2 field in reference mode: %.1f ms; %s" % (ms, eng.field_propagation_stats()))
+    eng.close()
+
+
+def test_c4_full_size_equals_the_reference():
+    """BASELINE.json configs[3] at full size: 5 M points -> 400 x 400 x 200 voxels, all 32 M voxels equal the reference's."""
+    c4 = workloads.CONFIGS["C4"]
+    eng, ref = field_pair(c4["size"], c4["origin"], c4["resolution"], c4["max_distance"])
+    pts = workloads.make_cloud("C4")
+    eng.field_add_points(pts)
+    ms = eng.stats()["edt_ms"]
+    ref.add_points(pts)
+    same(eng, ref, "C4")
+    print("C4 field in reference mode: %.1f ms; %s" % (ms, eng.field_propagation_stats()))
+    eng.close()
