@@ -17,7 +17,8 @@ Timed regions
          sphere centres + centre voxel only) on all host threads, on a bounded sample of the same workload.
 
 Besides the contract's keys the line carries: `parity` (10 M states vs the oracle on identical fields for the headline
-config and for C3D, the count with each side's OWN fields, EDT voxel counts), `edt` (C4 rebuild, its own roofline),
+config and for C3D, the count with each side's OWN fields, EDT voxel counts, and `reference_mode`: the fields rebuilt by the
+device's reproduction of the reference's propagation -- voxels and verdicts differing from the oracle's, expected 0), `edt` (C4 rebuild, its own roofline),
 `fk` (batched FK alone), `e2e_f32` / `e2e_edges` / `latency` (the other reference-facing entry points end to end),
 `roofline_l1_gather` (the gather microbenchmark denominator) and, at N > 1, `c3_strong` (BASELINE.json configs[2]: the
 10 M-state dual-arm batch sharded over the ranks, with the same batch on ONE rank timed in the same run).
@@ -262,6 +263,38 @@ def parity_leg(mb, workloads, name, eng, cloud, n_want, flags, budget_s=25.0):
     out.update({"validity_states_compared_with_own_fields": int(n_own),
                 "validity_states_differing_with_own_fields": int(own_diff),
                 "of_which_gpu_reports_collision": int(own_more)})
+    # B200SV_PROPAGATION_REFERENCE: both fields rebuilt by the device's reproduction of the reference's bucket-queue
+    # propagation from the same point arrays -- every voxel must equal the oracle's, and so must every state's verdict
+    # with each side's own fields
+    try:
+        eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_WORLD)
+        eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_SELF)
+        eng.field_add_points(cloud, mb.FIELD_WORLD)
+        ref_ms = float(eng.stats()["edt_ms"])
+        eng.field_add_points(env.self_points, mb.FIELD_SELF)
+        r_w, r_s = eng.field_get_d2(mb.FIELD_WORLD), eng.field_get_d2(mb.FIELD_SELF)
+        ref_diff = ref_n = 0
+        for item in chunks:
+            if item is None:
+                continue
+            q, col = item
+            ref_diff += int((eng.check_batch(q, flags) == col.astype(bool)).sum())
+            ref_n += len(q)
+        st = eng.field_propagation_stats(mb.FIELD_WORLD)
+        out["reference_mode"] = {
+            "what": "b200sv_field_set_propagation(B200SV_PROPAGATION_REFERENCE): the reference's propagation reproduced on the "
+                    "device, fields built from the same point arrays as the oracle's",
+            "world_voxels_differing_from_reference_propagation": int((r_w != o_w).sum()),
+            "self_voxels_differing_from_reference_propagation": int((r_s != o_s).sum()),
+            "world_build_ms": ref_ms, "oracle_world_build_s": float(env.world_build_s),
+            "rounds": st["rounds"], "hazard_rounds": st["hazard_rounds"], "queue_entries": st["queue_entries"],
+            "validity_states_compared_with_own_fields": int(ref_n),
+            "validity_states_differing_with_own_fields": int(ref_diff)}
+    finally:  # back to the exact transform and this run's own fields
+        eng.field_set_propagation(mb.PROPAGATION_EXACT, mb.FIELD_WORLD)
+        eng.field_set_propagation(mb.PROPAGATION_EXACT, mb.FIELD_SELF)
+        eng.field_set_d2(own_w, mb.FIELD_WORLD)
+        eng.field_set_d2(own_s, mb.FIELD_SELF)
     return out, env
 
 
