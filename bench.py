@@ -271,7 +271,6 @@ def parity_leg(mb, workloads, name, eng, cloud, n_want, flags, budget_s=25.0):
         eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_SELF)
         eng.field_add_points(cloud, mb.FIELD_WORLD)
         ref_ms = float(eng.stats()["edt_ms"])
-        eng.field_add_points(env.self_points, mb.FIELD_SELF)
         r_w, r_s = eng.field_get_d2(mb.FIELD_WORLD), eng.field_get_d2(mb.FIELD_SELF)
         ref_diff = ref_n = 0
         for item in chunks:

@@ -208,10 +208,11 @@ int b200sv_field_end_update(b200sv_ctx* ctx, int which);
  *   and propagatePositive in data-parallel phases whose outcome is the serial queue's: every voxel's squared distance equals
  *   the reference's after the same sequence of calls with the same point arrays (the order of the points and of the calls
  *   matters, as it does in the reference).  Milliseconds per call instead of a tenth of one.  Unsigned fields only; the
- *   shape / octree / .df / set_d2 / import entry points and b200sv_set_base_state(.., rebuild_self_field = 1) on the self
- *   field refuse with B200SV_ERR_UNSUPPORTED while a field is in this mode (feed their points through add_points), and
- *   begin/end_update brackets are refused too (the reference propagates per call).
- * Switching the mode resets the field. */
+ *   shape / octree / .df / set_d2 / import entry points refuse with B200SV_ERR_UNSUPPORTED while a field is in this mode
+ *   (feed their points through add_points), and begin/end_update brackets are refused too (the reference propagates per
+ *   call).  b200sv_set_base_state(.., rebuild_self_field = 1) builds a self field in this mode as the reference builds a
+ *   new cache entry's: a fresh field, the links' points added in one call.
+ * Switching the mode resets the field; the self field is then refilled from the link points the context holds. */
 #define B200SV_PROPAGATION_EXACT 0
 #define B200SV_PROPAGATION_REFERENCE 1
 int b200sv_field_set_propagation(b200sv_ctx* ctx, int which, int mode);

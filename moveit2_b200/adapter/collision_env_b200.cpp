@@ -65,6 +65,7 @@ CollisionEnvB200::CollisionEnvB200(const CollisionEnvB200& other, const WorldPtr
   resolution_ = other.resolution_;
   collision_tolerance_ = other.collision_tolerance_;
   max_propogation_distance_ = other.max_propogation_distance_;
+  reference_propagation_ = other.reference_propagation_;
   link_body_decomposition_vector_ = other.link_body_decomposition_vector_;
   link_body_decomposition_index_map_ = other.link_body_decomposition_index_map_;
   // contexts are per (group, non-group state, ACM) and own device memory: a child scene builds its own lazily and
@@ -92,6 +93,8 @@ void CollisionEnvB200::initialize()
   resolution_ = DEFAULT_RESOLUTION;
   collision_tolerance_ = DEFAULT_COLLISION_TOLERANCE;
   max_propogation_distance_ = DEFAULT_MAX_PROPOGATION_DISTANCE;
+  if (const char* mode = std::getenv("B200SV_PROPAGATION"))
+    reference_propagation_ = std::string(mode) == "reference";
   // addLinkBodyDecompositions (collision_env_distance_field.cpp:960-979): the reference's own BodyDecomposition,
   // so spheres / interior points / bounding spheres of meshes, boxes and cylinders are the reference's, bit for bit
   for (const moveit::core::LinkModel* link : robot_model_->getLinkModelsWithCollisionGeometry())
@@ -338,6 +341,13 @@ CollisionEnvB200::createContext(const moveit::core::JointModelGroup* jmg, const 
     RCLCPP_ERROR(getLogger(), "b200sv_create failed: %s", b200sv_last_error(nullptr));
     return nullptr;
   }
+  if (reference_propagation_ &&
+      (b200sv_field_set_propagation(gc->ctx, B200SV_FIELD_WORLD, B200SV_PROPAGATION_REFERENCE) != B200SV_OK ||
+       b200sv_field_set_propagation(gc->ctx, B200SV_FIELD_SELF, B200SV_PROPAGATION_REFERENCE) != B200SV_OK))
+  {
+    RCLCPP_ERROR(getLogger(), "b200sv_field_set_propagation failed: %s", b200sv_last_error(gc->ctx));
+    return nullptr;
+  }
   // non-group variables to watch (dfce->state_check_indices_, :886-896)
   std::vector<bool> in_group(robot_model_->getVariableCount(), false);
   for (const moveit::core::JointModel* jm : jmg->getActiveJointModels())
@@ -499,8 +509,38 @@ bool devicePrimitive(const shapes::Shape* shape, const Eigen::Isometry3d& pose, 
 }
 }  // namespace
 
+void CollisionEnvB200::setReferencePropagation(bool on)
+{
+  {
+    std::scoped_lock lock(mutex_);
+    if (on == reference_propagation_)
+      return;
+    reference_propagation_ = on;
+    contexts_.clear();  // their holders keep them alive until their checks return; successors are built in the new mode
+  }
+  // the world's records are re-derived in the new mode's form (device primitives, or the reference's points for every shape)
+  getWorld()->notifyObserverAllObjects(observer_handle_, World::CREATE);
+}
+
 bool CollisionEnvB200::replayWorld(b200sv_ctx* ctx) const
 {
+  if (reference_propagation_)
+  {  // object by object, in the order World::notifyObserverAllObjects walks its map: every addPointsToField call
+     // propagates on top of the state the one before left, as in the reference (:1704-1779)
+    std::vector<EigenSTL::vector_Vector3d> per_object;
+    {
+      std::scoped_lock map_lock(mutex_);
+      for (const auto& kv : world_points_)
+        per_object.push_back(kv.second.points);
+    }
+    bool ok = b200sv_field_reset(ctx, B200SV_FIELD_WORLD) == B200SV_OK;
+    for (std::size_t i = 0; ok && i < per_object.size(); ++i)
+      if (!per_object[i].empty())
+        ok = b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, per_object[i][0].data(), per_object[i].size()) == B200SV_OK;
+    if (!ok)
+      RCLCPP_ERROR(getLogger(), "replaying the world into the field failed: %s", b200sv_last_error(ctx));
+    return ok;
+  }
   EigenSTL::vector_Vector3d all;
   std::vector<b200sv_shape> shapes;
   {
@@ -541,8 +581,10 @@ void CollisionEnvB200::notifyObjectChange(const ObjectConstPtr& obj, World::Acti
         PosedBodyPointDecomposition pts(static_cast<const shapes::OcTree*>(shape.get())->octree);  // types.cpp:355-365
         new_rec.points.insert(new_rec.points.end(), pts.getCollisionPoints().begin(), pts.getCollisionPoints().end());
       }
-      else if (devicePrimitive(shape.get(), getWorld()->getGlobalShapeTransform(obj->id_, static_cast<int>(i)), prim))
-        new_rec.shapes.push_back(prim);
+      else if (!reference_propagation_ &&
+               devicePrimitive(shape.get(), getWorld()->getGlobalShapeTransform(obj->id_, static_cast<int>(i)), prim))
+        new_rec.shapes.push_back(prim);  // (reference mode: every shape takes the reference's own host decomposition below,
+                                         //  so the points and their order are the reference's)
       else
       {
         BodyDecompositionConstPtr bd = std::make_shared<const BodyDecomposition>(shape, resolution_, 0.0);
@@ -572,6 +614,20 @@ void CollisionEnvB200::notifyObjectChange(const ObjectConstPtr& obj, World::Acti
     if (gc->world_version != version_before)
       continue;  // it missed an earlier change: the next check replays the whole world into it
     b200sv_ctx* ctx = gc->ctx;
+    if (reference_propagation_)
+    {  // removePointsFromField, then addPointsToField (:1713-1725), each with its own propagation, as the reference
+      bool ok = old_rec.shapes.empty();  // a record made before the mode was switched: replay instead
+      if (ok && !old_rec.points.empty())
+        ok = b200sv_field_remove_points(ctx, B200SV_FIELD_WORLD, old_rec.points[0].data(), old_rec.points.size()) == B200SV_OK;
+      if (ok && !new_rec.points.empty())
+        ok = b200sv_field_add_points(ctx, B200SV_FIELD_WORLD, new_rec.points[0].data(), new_rec.points.size()) == B200SV_OK;
+      if (ok)
+        gc->world_version = version_after;
+      else
+        RCLCPP_ERROR(getLogger(), "world update of the field failed (the next check replays the world): %s",
+                     b200sv_last_error(ctx));
+      continue;
+    }
     // removePointsFromField, then addPointsToField (:1713-1725) -- as ONE rebuild of the field
     bool ok = b200sv_field_begin_update(ctx, B200SV_FIELD_WORLD) == B200SV_OK;
     if (ok && !old_rec.points.empty())

@@ -61,6 +61,11 @@ public:
   void distanceRobot(const DistanceRequest&, DistanceResult&, const moveit::core::RobotState&) const override {}
   void setWorld(const WorldPtr& world) override;
 
+  /// The world and self fields reproduce PropagationDistanceField's propagation voxel for voxel
+  /// (B200SV_PROPAGATION_REFERENCE) instead of the exact transform.  Takes effect for contexts created afterwards: the
+  /// cached ones are dropped, the world is replayed into their successors object by object, as the reference adds it.
+  void setReferencePropagation(bool on);
+
   // ---- the new batched entry point --------------------------------------------------------------------------
   /// N group-state vectors (layout of RobotState::setJointGroupPositions(group, const double*), row-major N x V)
   /// -> validity bitmap, bit (i % 8) of byte (i / 8) = 1 iff state i passes PlanningScene::checkCollision's checks
@@ -117,6 +122,10 @@ private:
   Eigen::Vector3d size_, origin_;
   double resolution_, collision_tolerance_, max_propogation_distance_;
   bool use_signed_distance_field_ = false;  // DEFAULT_USE_SIGNED_DISTANCE_FIELD (collision_env_distance_field.hpp:52)
+  /// B200SV_PROPAGATION_REFERENCE for the world and self fields: every voxel equals PropagationDistanceField's (tens of
+  /// milliseconds per world change instead of a tenth of one).  Default: the exact transform; the environment variable
+  /// B200SV_PROPAGATION=reference turns it on for a whole process, setReferencePropagation for one environment.
+  bool reference_propagation_ = false;
   std::vector<BodyDecompositionConstPtr> link_body_decomposition_vector_;  // as the reference (:1049-1078)
   std::map<std::string, unsigned int> link_body_decomposition_index_map_;
   // world points currently in the field, per object id (DistanceFieldCacheEntryWorld::posed_body_point_decompositions_)

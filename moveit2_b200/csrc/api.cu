@@ -2333,7 +2333,16 @@ int b200sv_field_set_propagation(b200sv_ctx* c, int which, int mode)
       F.prop = nullptr;
     }
   }
-  return b200sv_field_reset(c, which);  // either way the field starts empty in its new mode
+  rc = b200sv_field_reset(c, which);  // either way the field starts empty in its new mode ...
+  if (rc != B200SV_OK || which != B200SV_FIELD_SELF)
+    return rc;
+  // ... except the self field, which is the context's own: the links' points the context holds are added again
+  std::vector<double> pts;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    pts = c->self_points;
+  }
+  return pts.empty() ? B200SV_OK : b200sv_field_add_points(c, which, pts.data(), pts.size() / 3);
 }
 
 int b200sv_field_propagation_stats(b200sv_ctx* c, int which, b200sv_propagation_stats* out)
@@ -3894,8 +3903,23 @@ int b200sv_set_base_state(b200sv_ctx* c, const double* base_positions, int rebui
   // the self field of the new cache entry: the non-group links' interior points at the new state (:907-953)
   poseSelfPoints(c->robot, c->robot.base_positions, c->self_local, c->self_points);
   Field& F = c->fields[B200SV_FIELD_SELF];
-  CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
   const size_t n = c->self_points.size() / 3;
+  if (F.prop)
+  {  // a new cache entry's self field is a fresh PropagationDistanceField with the links' points added (:931-953)
+    CU(c, c->d_points.ensure(3 * n + 3));
+    if (n)
+      CU(c, cudaMemcpyAsync(c->d_points.p, c->self_points.data(), 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    propDestroy(F.prop);  // fresh: nothing queued from the entry before
+    F.prop = nullptr;
+    CU(c, propCreate(c->grid, &F.prop));
+    CU(c, propReset(F.prop, c->stream));
+    CU(c, propAddPoints(F.prop, c->d_points.p, n, c->stream));
+    if ((rc = publishPropagation(c, B200SV_FIELD_SELF, c->stream)) != B200SV_OK)
+      return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return B200SV_OK;
+  }
+  CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, c->stream));
   if (n)
   {
     CU(c, c->d_points.ensure(3 * n));
