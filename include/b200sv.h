@@ -429,6 +429,9 @@ int b200sv_multi_device_count(const b200sv_multi* m);
 b200sv_ctx* b200sv_multi_ctx(b200sv_multi* m, int i);
 int b200sv_multi_field_sync(b200sv_multi* m, int which);
 int b200sv_multi_field_reset(b200sv_multi* m, int which);
+/* b200sv_field_set_propagation for the handle: the first device builds every field (in the chosen mode), the others receive
+ * its values.  b200sv_multi_field_add_points then yields the reference's voxels on every device. */
+int b200sv_multi_field_set_propagation(b200sv_multi* m, int which, int mode);
 int b200sv_multi_field_add_points(b200sv_multi* m, int which, const double* xyz, size_t n_points);
 /* b200sv_check_batch over all devices: block i of the states goes to context i; pinned host buffers make every copy a DMA. */
 int b200sv_check_batch_multi(b200sv_multi* m, const double* q, size_t n_states, uint32_t flags, uint8_t* valid_bitmap);

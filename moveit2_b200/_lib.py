@@ -138,6 +138,7 @@ def load():
         "b200sv_multi_ctx": (vp, [vp, C.c_int]),
         "b200sv_multi_field_sync": (C.c_int, [vp, C.c_int]),
         "b200sv_multi_field_reset": (C.c_int, [vp, C.c_int]),
+        "b200sv_multi_field_set_propagation": (C.c_int, [vp, C.c_int, C.c_int]),
         "b200sv_multi_field_add_points": (C.c_int, [vp, C.c_int, dp, C.c_size_t]),
         "b200sv_check_batch_multi": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp]),
         "b200sv_multi_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),

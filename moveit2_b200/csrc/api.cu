@@ -4163,6 +4163,18 @@ int b200sv_multi_field_add_points(b200sv_multi* m, int which, const double* xyz,
   return b200sv_multi_field_sync(m, which);
 }
 
+// The field is built on the first device and copied to the others, so only the first context runs a propagation at all:
+// in B200SV_PROPAGATION_REFERENCE it keeps the reference's voxel records, the others receive the values.
+int b200sv_multi_field_set_propagation(b200sv_multi* m, int which, int mode)
+{
+  if (!m)
+    return B200SV_ERR_INVALID;
+  int rc = b200sv_field_set_propagation(m->ctx[0], which, mode);
+  if (rc != B200SV_OK)
+    return multiFail(m, rc, m->ctx[0]->err);
+  return b200sv_multi_field_sync(m, which);
+}
+
 int b200sv_multi_field_reset(b200sv_multi* m, int which)
 {
   if (!m)

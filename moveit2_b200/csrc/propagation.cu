@@ -175,8 +175,21 @@ struct RoundCtl
   uint32_t pad;
 };
 
-__global__ void stampKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t b, State s)
+// positions of the round's entries; block 0 also resets the round's control block and segment table (read by the kernels
+// behind this one)
+__global__ void stampKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t b, State s, RoundCtl* ctl, uint32_t* starts,
+                            uint32_t* ends, int n_buckets)
 {
+  if (blockIdx.x == 0)
+  {
+    if (threadIdx.x == 0)
+      ctl->cut = b;
+    for (int j = threadIdx.x; j < n_buckets; j += blockDim.x)
+    {
+      starts[j] = 0;
+      ends[j] = 0;
+    }
+  }
   const uint32_t p = a + blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= b)
     return;
@@ -184,16 +197,6 @@ __global__ void stampKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t
   atomicMin(&s.first[v], p);
   atomicMax(&s.lastp1[v], p + 1);
 }
-__global__ void unstampKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t b, State s)
-{
-  const uint32_t p = a + blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= b)
-    return;
-  const uint32_t v = L[p];
-  s.first[v] = kNone;
-  s.lastp1[v] = 0;
-}
-
 // every offer of entries [a, b) of bucket i: rec_key = its distance if it is accepted (kNoKey otherwise), rec_val = the target,
 // rec_cp = the closest point it carries | the direction number of the step << 48.  Reads the state, writes none of it.
 template <int S>
@@ -318,9 +321,17 @@ __global__ void applyStateKernel(uint32_t a, size_t n_rec, int bucket, uint16_t*
 }
 
 // runs of equal keys in the sorted records -> [start, end) per destination bucket
-__global__ void runsKernel(const uint16_t* __restrict__ keys, size_t n, uint32_t* __restrict__ starts, uint32_t* __restrict__ ends)
+// (L != nullptr: the first b - a threads also clear their entries' stamps -- the round is over)
+__global__ void runsKernel(const uint16_t* __restrict__ keys, size_t n, uint32_t* __restrict__ starts, uint32_t* __restrict__ ends,
+                           const uint32_t* __restrict__ L = nullptr, uint32_t a = 0, uint32_t b = 0, State s = State{})
 {
   const size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (L != nullptr && j < b - a)
+  {
+    const uint32_t v = L[a + j];
+    s.first[v] = kNone;
+    s.lastp1[v] = 0;
+  }
   if (j >= n)
     return;
   const uint16_t k = keys[j];
@@ -651,7 +662,7 @@ cudaError_t propagate(PropField* f, cudaStream_t s)
       dim3 grid(std::max(1u, std::min(blocksFor(longest, 256), 4096u)), static_cast<unsigned>(std::min<size_t>(segs.size(), 1024)));
       gatherKernel<<<grid, 256, 0, s>>>(f->pool.p, f->d_segs.p, static_cast<int>(segs.size()), f->L.p);
       PCK(cudaGetLastError());
-      PCK(cudaStreamSynchronize(s));  // h_segs is reused by the next bucket
+      // (h_segs is rewritten for the next bucket only after this bucket's rounds, each of which ends in a synchronisation)
     }
     segs.clear();
     f->stats.entries += total;
@@ -664,8 +675,7 @@ cudaError_t propagate(PropField* f, cudaStream_t s)
       const size_t n_rec = static_cast<size_t>(b - a) * S;
       PCK(ensureRecords(f, n_rec, true));
       PCK(f->pool.ensure(f->pool_off + n_rec, true, f->pool_off, s));
-      roundInitKernel<<<blocksFor(nb, 256), 256, 0, s>>>(f->d_ctl, b, f->d_starts, f->d_ends, nb);
-      stampKernel<<<blocksFor(b - a, 256), 256, 0, s>>>(f->L.p, a, b, f->st);
+      stampKernel<<<blocksFor(b - a, 256), 256, 0, s>>>(f->L.p, a, b, f->st, f->d_ctl, f->d_starts, f->d_ends, nb);
       if (S == 26)
       {
         offerKernel<26><<<blocksFor(n_rec, 256), 256, 0, s>>>(f->L.p, a, b, i, f->g, f->gd.max_d2, f->st, f->key_in.p, f->val_in.p,
@@ -682,13 +692,10 @@ cudaError_t propagate(PropField* f, cudaStream_t s)
       }
       PCK(cudaGetLastError());
       PCK(sortRecords(f, n_rec, f->pool.p + f->pool_off, s));
-      runsKernel<<<blocksFor(n_rec, 256), 256, 0, s>>>(f->key_out.p, n_rec, f->d_starts, f->d_ends);
-      unstampKernel<<<blocksFor(b - a, 256), 256, 0, s>>>(f->L.p, a, b, f->st);
+      runsKernel<<<blocksFor(n_rec, 256), 256, 0, s>>>(f->key_out.p, n_rec, f->d_starts, f->d_ends, f->L.p, a, b, f->st);
       PCK(cudaGetLastError());
-      uint8_t* h = f->h_pin;
-      PCK(cudaMemcpyAsync(h, f->d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, s));
-      PCK(cudaMemcpyAsync(h + sizeof(RoundCtl), f->d_starts, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-      PCK(cudaMemcpyAsync(h + sizeof(RoundCtl) + nb * sizeof(uint32_t), f->d_ends, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      uint8_t* h = f->h_pin;  // ctl | starts | ends are one device allocation: one copy
+      PCK(cudaMemcpyAsync(h, f->d_ctl, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       PCK(cudaStreamSynchronize(s));
       const RoundCtl* ctl = reinterpret_cast<const RoundCtl*>(h);
       const uint32_t* starts = reinterpret_cast<const uint32_t*>(h + sizeof(RoundCtl));
@@ -824,11 +831,14 @@ cudaError_t propCreate(const GridDev& gd, PropField** out)
   if (e == cudaSuccess) e = cudaMalloc(&f->st.dir, f->n_vox);
   if (e == cudaSuccess) e = cudaMalloc(&f->st.first, f->n_vox * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&f->st.lastp1, f->n_vox * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_ctl, sizeof(RoundCtl));
-  if (e == cudaSuccess) e = cudaMemset(f->d_ctl, 0, sizeof(RoundCtl));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_ctl, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t));  // ctl | starts | ends
+  if (e == cudaSuccess) e = cudaMemset(f->d_ctl, 0, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t));
+  if (e == cudaSuccess)
+  {
+    f->d_starts = reinterpret_cast<uint32_t*>(f->d_ctl + 1);
+    f->d_ends = f->d_starts + nb;
+  }
   if (e == cudaSuccess) e = cudaMalloc(&f->d_flood, sizeof(FloodCtl));
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_starts, nb * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_ends, nb * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMallocHost(&f->h_pin, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t) + 64);
   if (e != cudaSuccess)
   {
@@ -850,8 +860,6 @@ void propDestroy(PropField* f)
   cudaFree(f->st.lastp1);
   cudaFree(f->d_ctl);
   cudaFree(f->d_flood);
-  cudaFree(f->d_starts);
-  cudaFree(f->d_ends);
   if (f->h_pin)
     cudaFreeHost(f->h_pin);
   if (f->h_segs)

@@ -540,6 +540,9 @@ class MultiDeviceEngine:
         p = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
         self._check(self.L.b200sv_multi_field_add_points(self.h, int(which), _dp(p), p.shape[0]))
 
+    def field_set_propagation(self, mode, which=FIELD_WORLD):
+        self._check(self.L.b200sv_multi_field_set_propagation(self.h, int(which), int(mode)))
+
     def field_sync(self, which=FIELD_WORLD):
         self._check(self.L.b200sv_multi_field_sync(self.h, int(which)))
 

@@ -170,3 +170,60 @@ def test_c4_full_size_equals_the_reference():
     same(eng, ref, "C4")
     print("C4 field in reference mode: %.1f ms; %s" % (ms, eng.field_propagation_stats()))
     eng.close()
+
+
+def test_base_state_change_in_reference_mode_builds_the_self_field_like_a_fresh_cache_entry():
+    """compareCacheEntryToState (:1254-1312) -> a new DistanceFieldCacheEntry with a FRESH self field (:931-953): with both
+    fields in reference mode the context after b200sv_set_base_state equals a fresh oracle env at the new base state voxel
+    for voxel, and so do the verdicts with nothing injected."""
+    from oracle.collision_model import OracleEnv
+    from oracle.robot_model import RobotModel
+    from util import RES, read
+    urdf, srdf = read(RES, "dualarm_spheres.urdf"), read(RES, "dualarm.srdf")
+    geo = ((3.0, 3.0, 2.5), (0.0, 0.0, 1.0), 0.05, 0.25)
+    eng = mb.StateValidityEngine.from_urdf(urdf, srdf, "left_arm", *geo)
+    eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_WORLD)
+    eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_SELF)
+    env0 = OracleEnv(RobotModel(urdf, srdf), "left_arm", *geo)
+    assert np.array_equal(eng.field_get_d2(mb.FIELD_SELF), env0.self_field.d2())
+    cloud = workloads.clutter_cloud(6, 20000, 12, (-1.3, -1.3, 0.1), (1.3, 1.3, 2.0), 0.75)
+    eng.field_add_points(cloud)
+    lo, hi = eng.group_bounds()
+    q = workloads.random_states(22, 20000, lo, hi)
+    base = np.array(env0.base_positions)
+    rng = np.random.default_rng(5)
+    gv = set(int(v) for v in env0.arr["group_var_index"])
+    for v in RobotModel(urdf, srdf).groups["right_arm"].variable_index_list:
+        if v not in gv:
+            base[v] = rng.uniform(-1.0, 1.0)
+    env1 = OracleEnv(RobotModel(urdf, srdf), "left_arm", *geo, base_positions=base)
+    env1.world.add_points(cloud)
+    eng.set_base_state(base)
+    assert np.array_equal(eng.field_get_d2(mb.FIELD_SELF), env1.self_field.d2())
+    assert np.array_equal(eng.field_get_d2(mb.FIELD_WORLD), env1.world.d2())
+    ref1, _ = env1.check(q, mb.CHECK_ALL)
+    assert np.array_equal(eng.check_batch(q, mb.CHECK_ALL), ref1 == 0)
+    eng.close()
+
+
+def test_several_devices_receive_the_reference_field():
+    """b200sv_multi_field_set_propagation: device 0 runs the propagation, every device of the handle checks against the
+    reference's voxels."""
+    torch = pytest.importorskip("torch")
+    from util import RES, read
+    devices = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    eng, env, cloud, q = config_pair("C1", n_states=20_000)
+    eng.close()
+    cfg = workloads.CONFIGS["C1"]
+    me = mb.MultiDeviceEngine.from_urdf(devices, read(RES, "panda_spheres.urdf"), read(RES, "panda.srdf"), cfg["group"],
+                                        cfg["size"], cfg["origin"], cfg["resolution"], cfg["max_distance"])
+    me.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_WORLD)
+    me.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_SELF)
+    me.field_add_points(cloud)
+    env.world.add_points(cloud)
+    for c in me.contexts:
+        assert np.array_equal(c.field_get_d2(mb.FIELD_WORLD), env.world.d2())
+        assert np.array_equal(c.field_get_d2(mb.FIELD_SELF), env.self_field.d2())
+    ref, _ = env.check(q, mb.CHECK_ALL)
+    assert np.array_equal(me.check_batch(q), ref == 0)
+    me.close()
