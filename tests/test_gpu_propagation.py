@@ -227,3 +227,33 @@ def test_several_devices_receive_the_reference_field():
     ref, _ = env.check(q, mb.CHECK_ALL)
     assert np.array_equal(me.check_batch(q), ref == 0)
     me.close()
+
+
+@pytest.mark.parametrize("size,res,maxd", [((0.06, 0.04, 0.02), 0.02, 0.1),      # 3 x 2 x 1 cells, R = 5 > every extent
+                                           ((0.5, 0.5, 0.14), 0.02, 0.02),       # 25 x 25 x 7 cells (nz < 8), R = 1
+                                           ((0.3, 0.2, 0.4), 0.01, 0.3)])        # 30 x 20 x 40 cells, R = 30: 901 buckets
+def test_edge_cases_empty_calls_tiny_grids_radius_one_and_radius_beyond_the_grid(size, res, maxd):
+    origin = (0.05, -0.02, 0.1)
+    eng, ref = field_pair(size, origin, res, maxd)
+    rng = np.random.default_rng(3)
+    none = np.zeros((0, 3))
+    outside = rng.uniform(2.0, 3.0, (20, 3))
+    corner = np.array(origin) - np.array(size) / 2
+    on_faces = np.array([corner, corner + size, corner + np.array(size) * 0.5, corner + [size[0], 0, 0],
+                         corner + 1e-12, corner + np.array(size) - 1e-12])
+    inside = rng.uniform(0, 1, (40, 3)) * size + corner
+    steps = [("add nothing", "add", none), ("remove nothing", "remove", none), ("add outside", "add", outside),
+             ("add faces", "add", on_faces), ("add inside", "add", inside), ("remove outside", "remove", outside),
+             ("remove half", "remove", inside[::2]), ("remove all", "remove", np.concatenate([inside, on_faces])),
+             ("add again", "add", inside[:5])]
+    for what, op, pts in steps:
+        getattr(eng, "field_%s_points" % op)(pts)
+        getattr(ref, "%s_points" % op)(pts)
+        same(eng, ref, what)
+    eng.field_update_points(none, inside)
+    ref.update_points(none, inside)
+    same(eng, ref, "update nothing -> inside")
+    eng.field_update_points(inside, none)
+    ref.update_points(inside, none)
+    same(eng, ref, "update inside -> nothing")
+    eng.close()
