@@ -208,7 +208,8 @@ int b200sv_field_end_update(b200sv_ctx* ctx, int which);
  *   and propagatePositive in data-parallel phases whose outcome is the serial queue's: every voxel's squared distance equals
  *   the reference's after the same sequence of calls with the same point arrays (the order of the points and of the calls
  *   matters, as it does in the reference).  Milliseconds per call instead of a tenth of one.  Unsigned fields only; the
- *   shape / octree / .df / set_d2 / import entry points refuse with B200SV_ERR_UNSUPPORTED while a field is in this mode
+ *   b200sv_field_read_df is readFromStream (:675-760: a reset, then the stream's voxels in x, y, z order).  The
+ *   shape / octree / set_d2 / import entry points refuse with B200SV_ERR_UNSUPPORTED while a field is in this mode
  *   (feed their points through add_points), and begin/end_update brackets are refused too (the reference propagates per
  *   call).  b200sv_set_base_state(.., rebuild_self_field = 1) builds a self field in this mode as the reference builds a
  *   new cache entry's: a fresh field, the links' points added in one call.

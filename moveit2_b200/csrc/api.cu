@@ -2853,8 +2853,6 @@ int b200sv_field_read_df(b200sv_ctx* c, int which, const uint8_t* bytes, size_t 
   int rc = checkWhich(c, which);
   if (rc)
     return rc;
-  if ((rc = notInReferenceMode(c, which)) != B200SV_OK)
-    return rc;
   if (!bytes)
     return fail(c, B200SV_ERR_INVALID, "null input");
   static const char* keys[7] = { "resolution:", "size_x:", "size_y:", "size_z:", "origin_x:", "origin_y:", "origin_z:" };
@@ -2902,6 +2900,15 @@ int b200sv_field_read_df(b200sv_ctx* c, int which, const uint8_t* bytes, size_t 
   Field& F = c->fields[which];
   CU(c, cudaMemcpyAsync(F.occ, occ.data(), occ.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  if (F.prop)
+  {  // readFromStream: initialize() (a reset), then addNewObstacleVoxels of the occupied voxels in x, y, z order (:720-758)
+    CU(c, propReset(F.prop, c->stream));
+    CU(c, propAddOccupancy(F.prop, F.occ, c->stream));
+    if ((rc = publishPropagation(c, which, c->stream)) != B200SV_OK)
+      return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return B200SV_OK;
+  }
   return rebuildField(c, which);
 }
 

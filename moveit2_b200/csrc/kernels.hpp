@@ -302,6 +302,8 @@ cudaError_t propAddPoints(PropField* f, const double* d_xyz, size_t n, cudaStrea
 cudaError_t propRemovePoints(PropField* f, const double* d_xyz, size_t n, cudaStream_t s);   // removePointsFromField :198-219
 cudaError_t propUpdatePoints(PropField* f, const double* d_old, size_t n_old, const double* d_new, size_t n_new,
                              cudaStream_t s);                                                // updatePointsInField :130-175
+// readFromStream's tail (:730-758): every set bit of an occupancy bitmap (launchScatter's layout), in voxel order
+cudaError_t propAddOccupancy(PropField* f, const uint32_t* d_occ, cudaStream_t s);
 const int32_t* propDistances(const PropField* f);
 const PropStats& propStats(const PropField* f);
 // One field's elements of the interleaved compact field <-> a dense array (field replication across contexts):

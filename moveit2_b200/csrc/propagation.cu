@@ -379,6 +379,20 @@ __global__ void pointsToVoxelsKernel(const double* __restrict__ xyz, size_t n, G
   rec_val[i] = v;
 }
 
+// readFromStream (:730-758): the occupied voxels of a bit field in x, y, z order, i.e. by ascending voxel reference
+__global__ void bitsToVoxelsKernel(const uint32_t* __restrict__ occ, Dims g, int wz, uint32_t v0, uint32_t n, uint16_t* __restrict__ rec_key,
+                                   uint32_t* __restrict__ rec_val)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n)
+    return;
+  const uint32_t v = v0 + j;
+  const uint32_t row = v / g.nz, z = v - row * g.nz;
+  const bool set = (occ[static_cast<size_t>(row) * wz + (z >> 5)] >> (z & 31)) & 1u;
+  rec_key[j] = set ? static_cast<uint16_t>(0) : kNoKey;
+  rec_val[j] = v;
+}
+
 // addNewObstacleVoxels :221-243 / removeObstacleVoxels :303-330: the listed voxels' own records
 __global__ void markVoxelsKernel(const uint32_t* __restrict__ vox, uint32_t n, Dims g, State s, int dist_value)
 {
@@ -948,6 +962,26 @@ cudaError_t propUpdatePoints(PropField* f, const double* d_old, size_t n_old, co
   if (n_add)
     PCK(cudaMemcpyAsync(f->pool.p + f->pool_off, add_list, n_add * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
   return addVoxelsAtPool(f, n_add, s);
+}
+
+cudaError_t propAddOccupancy(PropField* f, const uint32_t* d_occ, cudaStream_t s)
+{
+  constexpr size_t kChunk = size_t(1) << 25;
+  uint32_t total = 0;
+  for (size_t v0 = 0; v0 < f->n_vox; v0 += kChunk)
+  {
+    const size_t n = std::min(kChunk, f->n_vox - v0);
+    uint32_t count = 0;
+    PCK(ensureRecords(f, n, false));
+    PCK(f->pool.ensure(f->pool_off + total + n, true, f->pool_off + total, s));
+    bitsToVoxelsKernel<<<blocksFor(n, 256), 256, 0, s>>>(d_occ, f->g, f->gd.wz, static_cast<uint32_t>(v0), static_cast<uint32_t>(n),
+                                                         f->key_in.p, f->val_in.p);
+    PCK(cudaGetLastError());
+    PCK(sortRecords(f, n, f->pool.p + f->pool_off + total, s));
+    PCK(keptCount(f, n, s, &count));
+    total += count;
+  }
+  return addVoxelsAtPool(f, total, s);  // addNewObstacleVoxels: no "already an obstacle" filter on this path
 }
 
 const int32_t* propDistances(const PropField* f) { return f->st.dist; }

@@ -257,3 +257,33 @@ def test_edge_cases_empty_calls_tiny_grids_radius_one_and_radius_beyond_the_grid
     ref.update_points(inside, none)
     same(eng, ref, "update inside -> nothing")
     eng.close()
+
+
+def test_the_references_df_fixture_through_read_df_in_reference_mode():
+    """distance_field/test/resources/test_big.df (65 126 voxels of the r = 0.5 sphere the reference's TestReadWrite writes,
+    committed as occupancy bits in tests/golden/df_golden.npz): readFromStream = reset + addNewObstacleVoxels of the stream's
+    voxels in x, y, z order.  The device field equals the oracle's fed the same voxels in the same order."""
+    import os
+    from oracle.df import write_df_occupancy
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "df_golden.npz"))
+    hdr = {k: float(gold["test_big_header"][i]) for i, k in enumerate(
+        ("resolution", "size_x", "size_y", "size_z", "origin_x", "origin_y", "origin_z"))}
+    n = [int(v) for v in gold["test_big_dims"]]
+    occ = np.unpackbits(gold["test_big_occ_bits"])[: n[0] * n[1] * n[2]].reshape(n).astype(bool)
+    assert int(occ.sum()) == 65126
+    size = (hdr["size_x"], hdr["size_y"], hdr["size_z"])
+    origin = tuple(hdr["origin_%s" % a] + hdr["size_%s" % a] / 2 for a in "xyz")
+    eng, ref = field_pair(size, origin, hdr["resolution"], 0.25)
+    assert eng.num_cells == tuple(n)
+    eng.field_read_df(write_df_occupancy(hdr, occ))
+    ref.add_voxels(np.argwhere(occ).astype(np.int32))
+    same(eng, ref, "test_big.df")
+    assert int((eng.field_get_d2() == 0).sum()) == int(occ.sum())
+    # a second stream on top: the field is reset first, as initialize() does
+    occ2 = np.zeros_like(occ)
+    occ2[3, 4, 5] = occ2[10, 20, 7] = True
+    eng.field_read_df(write_df_occupancy(hdr, occ2))
+    ref.reset()
+    ref.add_voxels(np.argwhere(occ2).astype(np.int32))
+    same(eng, ref, "second stream")
+    eng.close()
