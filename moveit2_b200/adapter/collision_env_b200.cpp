@@ -390,6 +390,13 @@ CollisionEnvB200::createContext(const moveit::core::JointModelGroup* jmg, const 
   gc->attached_signature = fm.attached_signature;
   gc->entry_names = fm.entry_names;
   gc->entry_is_attached = fm.entry_is_attached;
+  gc->sphere_start = fm.sphere_start;
+  gc->body_id = fm.body_id;
+  gc->sphere_radii.resize(fm.sphere_xyzr.size() / 4);
+  for (std::size_t k = 0; k < gc->sphere_radii.size(); ++k)
+    gc->sphere_radii[k] = fm.sphere_xyzr[4 * k + 3];
+  for (int32_t li : fm.glink_index)
+    gc->entry_joint_names.push_back(links[static_cast<std::size_t>(li)]->getParentJointModel()->getName());
   return gc;
 }
 
@@ -680,6 +687,55 @@ bool CollisionEnvB200::checkCollisionBatch(const CollisionRequest& req, const mo
     std::fill(valid_bitmap, valid_bitmap + (n_states + 7) / 8, static_cast<uint8_t>(0));
     return false;
   }
+  return true;
+}
+
+bool CollisionEnvB200::getCollisionGradientsBatch(const CollisionRequest& req, const moveit::core::RobotState& base_state,
+                                                  const AllowedCollisionMatrix* acm, const double* q, std::size_t n_states,
+                                                  std::vector<std::vector<GradientInfo>>& gradients) const
+{
+  gradients.clear();
+  std::unique_lock<std::mutex> ctx_lock;
+  std::shared_ptr<GroupContext> gc = getContext(req.group_name, base_state, acm, ctx_lock);
+  if (!gc)
+    return false;
+  const std::size_t n_entries = gc->entry_names.size();
+  const std::size_t n_spheres = gc->sphere_radii.size();
+  std::vector<double> dist(n_states * n_spheres), grad(3 * n_states * n_spheres), centres(3 * n_states * n_spheres);
+  std::vector<double> closest(n_states * n_entries);
+  std::vector<uint8_t> types(n_states * n_spheres);
+  if (b200sv_collision_gradients(gc->ctx, q, n_states, dist.data(), grad.data(), types.data(), closest.data(),
+                                 centres.data()) != B200SV_OK)
+  {
+    RCLCPP_ERROR(getLogger(), "b200sv_collision_gradients failed: %s", b200sv_last_error(gc->ctx));
+    return false;
+  }
+  // the reference keeps ONE gradients_ entry per attached body; the context holds one entry per shape of it (b200sv.h:
+  // body_id), in order: consecutive entries of one body are appended to the same GradientInfo
+  std::vector<std::size_t> out_of(n_entries);
+  std::size_t n_out = 0;
+  for (std::size_t e = 0; e < n_entries; ++e)
+  {
+    const bool same_body = e > 0 && gc->entry_is_attached[e] && gc->entry_is_attached[e - 1] && gc->body_id[e] == gc->body_id[e - 1];
+    out_of[e] = same_body ? n_out - 1 : n_out++;
+  }
+  gradients.assign(n_states, std::vector<GradientInfo>(n_out));
+  for (std::size_t s = 0; s < n_states; ++s)
+    for (std::size_t e = 0; e < n_entries; ++e)
+    {
+      GradientInfo& g = gradients[s][out_of[e]];
+      g.joint_name = gc->entry_joint_names[e];
+      g.closest_distance = std::min(g.closest_distance, closest[s * n_entries + e]);
+      for (int32_t k = gc->sphere_start[e]; k < gc->sphere_start[e + 1]; ++k)
+      {
+        const std::size_t at = s * n_spheres + static_cast<std::size_t>(k);
+        g.sphere_radii.push_back(gc->sphere_radii[static_cast<std::size_t>(k)]);
+        g.sphere_locations.emplace_back(centres[3 * at], centres[3 * at + 1], centres[3 * at + 2]);
+        g.distances.push_back(dist[at]);
+        g.gradients.emplace_back(grad[3 * at], grad[3 * at + 1], grad[3 * at + 2]);
+        g.types.push_back(static_cast<CollisionType>(types[at]));
+      }
+    }
   return true;
 }
 

@@ -75,6 +75,16 @@ public:
                            const AllowedCollisionMatrix* acm, const double* q, std::size_t n_states,
                            uint8_t* valid_bitmap, uint32_t flags = B200SV_CHECK_ALL) const;
 
+  /// Batched CollisionEnvDistanceField::getCollisionGradients (collision_env_distance_field.cpp:1517-1538) -- the call
+  /// CHOMP makes per trajectory waypoint (chomp_optimizer.cpp:881-915) -- for N group states at once.  gradients[s][e] is
+  /// what gsr->gradients_[e] holds in the reference after the call for state s: one entry per updated link of the group
+  /// (empty for links without geometry, :1198-1231), then one per attached body (all its shapes' spheres, :1236-1251);
+  /// distances DBL_MAX / types NONE where nothing within max_propogation_distance was seen; `collision` stays false (the
+  /// reference's gradient path never raises it).  Returns false (and logs, gradients cleared) on error.
+  bool getCollisionGradientsBatch(const CollisionRequest& req, const moveit::core::RobotState& base_state,
+                                  const AllowedCollisionMatrix* acm, const double* q, std::size_t n_states,
+                                  std::vector<std::vector<GradientInfo>>& gradients) const;
+
 private:
   /// One DistanceFieldCacheEntry's worth of state on the device.  Owns its b200sv context: the context is destroyed when
   /// the LAST holder of the shared_ptr lets go, so a thread that is still inside a check keeps it alive even if the
@@ -93,6 +103,10 @@ private:
     std::string attached_signature;          // names, touch links, shapes and link-frame poses of the attached bodies
     std::vector<std::string> entry_names;    // dfce entries: the links, then one per shape of every attached body
     std::vector<bool> entry_is_attached;
+    // layout of the flat per-sphere outputs (b200sv_collision_gradients): entry e owns spheres [sphere_start[e], [e + 1])
+    std::vector<int32_t> sphere_start, body_id;
+    std::vector<double> sphere_radii;
+    std::vector<std::string> entry_joint_names;  // GradientInfo::joint_name (:1203, :1250)
     std::size_t world_version = 0;           // which state of world_points_ its world field holds
   };
   /// What generateDistanceFieldCacheEntry derives from (group, state, ACM): the flat collision model

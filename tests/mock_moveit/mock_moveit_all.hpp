@@ -5,6 +5,7 @@
 // const violation, a missing override) is a compile error exactly as it would be against the real headers.  Each block
 // names the reference header it stands for (paths relative to /root/reference); signatures are the reference's.
 #pragma once
+#include <cfloat>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -372,6 +373,26 @@ struct CollisionSphere  // :62-73
 {
   Eigen::Vector3d relative_vec_;
   double radius_;
+};
+enum CollisionType  // :75-81
+{
+  NONE = 0,
+  SELF = 1,
+  INTRA = 2,
+  ENVIRONMENT = 3,
+};
+struct GradientInfo  // :84-113
+{
+  GradientInfo() : closest_distance(DBL_MAX), collision(false) {}
+  double closest_distance;
+  bool collision;
+  EigenSTL::vector_Vector3d sphere_locations;
+  std::vector<double> distances;
+  EigenSTL::vector_Vector3d gradients;
+  std::vector<CollisionType> types;
+  std::vector<double> sphere_radii;
+  std::string joint_name;
+  void clear();
 };
 class BodyDecomposition  // :178-240
 {
