@@ -207,7 +207,8 @@ int b200sv_field_end_update(b200sv_ctx* ctx, int which);
  *   / remove_points / update_points / add_points_device run addNewObstacleVoxels (:221-301), removeObstacleVoxels (:303-388)
  *   and propagatePositive in data-parallel phases whose outcome is the serial queue's: every voxel's squared distance equals
  *   the reference's after the same sequence of calls with the same point arrays (the order of the points and of the calls
- *   matters, as it does in the reference).  Milliseconds per call instead of a tenth of one.  Unsigned fields only; the
+ *   matters, as it does in the reference).  Milliseconds per call instead of a tenth of one.  Signed fields run the
+ *   negative half the same way (the flood of :255-298, propagateNegative :446-504).
  *   b200sv_field_read_df is readFromStream (:675-760: a reset, then the stream's voxels in x, y, z order).  The
  *   shape / octree / set_d2 / import entry points refuse with B200SV_ERR_UNSUPPORTED while a field is in this mode
  *   (feed their points through add_points), and begin/end_update brackets are refused too (the reference propagates per

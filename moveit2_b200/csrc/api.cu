@@ -2302,6 +2302,8 @@ static int publishPropagation(b200sv_ctx* c, int which, cudaStream_t s)
   CU(c, cudaMemsetAsync(F.occ, 0, (size_t)c->grid.nx * c->grid.ny * c->grid.wz * 4, s));
   CU(c, launchInjectD2(c->grid, propDistances(F.prop), F.occ, F.d2, F.compact, c->compact_bytes, s));
   CU(c, cudaMemsetAsync(F.plane_busy, 1, (size_t)c->grid.nx * kPlaneBusyStride, s));
+  if (F.nd2)
+    CU(c, launchInjectNegD2(c->grid, propNegativeDistances(F.prop), F.nd2, s));
   return B200SV_OK;
 }
 
@@ -2312,8 +2314,6 @@ int b200sv_field_set_propagation(b200sv_ctx* c, int which, int mode)
     return rc;
   if (mode != B200SV_PROPAGATION_EXACT && mode != B200SV_PROPAGATION_REFERENCE)
     return fail(c, B200SV_ERR_INVALID, "mode must be B200SV_PROPAGATION_EXACT or B200SV_PROPAGATION_REFERENCE");
-  if (mode == B200SV_PROPAGATION_REFERENCE && c->cfg.use_signed_distance_field)
-    return fail(c, B200SV_ERR_UNSUPPORTED, "reference propagation is implemented for unsigned fields (the reference's default)");
   {
     std::lock_guard<std::mutex> lk(c->mu);
     enterCtx(c);
@@ -2321,7 +2321,7 @@ int b200sv_field_set_propagation(b200sv_ctx* c, int which, int mode)
     CU(c, cudaStreamSynchronize(c->stream));
     if (mode == B200SV_PROPAGATION_REFERENCE && !F.prop)
     {
-      cudaError_t e = propCreate(c->grid, &F.prop);
+      cudaError_t e = propCreate(c->grid, c->cfg.use_signed_distance_field != 0, &F.prop);
       if (e != cudaSuccess)
         return fail(c, e == cudaErrorInvalidConfiguration ? B200SV_ERR_UNSUPPORTED : B200SV_ERR_CUDA,
                     std::string("reference propagation: ") + cudaGetErrorString(e));
@@ -3918,7 +3918,7 @@ int b200sv_set_base_state(b200sv_ctx* c, const double* base_positions, int rebui
       CU(c, cudaMemcpyAsync(c->d_points.p, c->self_points.data(), 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     propDestroy(F.prop);  // fresh: nothing queued from the entry before
     F.prop = nullptr;
-    CU(c, propCreate(c->grid, &F.prop));
+    CU(c, propCreate(c->grid, c->cfg.use_signed_distance_field != 0, &F.prop));
     CU(c, propReset(F.prop, c->stream));
     CU(c, propAddPoints(F.prop, c->d_points.p, n, c->stream));
     if ((rc = publishPropagation(c, B200SV_FIELD_SELF, c->stream)) != B200SV_OK)

@@ -295,7 +295,7 @@ struct PropStats
 {
   unsigned long long rounds, hazard_rounds, entries, backward_offers, hazard_offers, queued_for_next_call, flood_pops_batches;
 };
-cudaError_t propCreate(const GridDev& g, PropField** out);
+cudaError_t propCreate(const GridDev& g, bool is_signed, PropField** out);  // is_signed: propagate_negative_ (:48-58)
 void propDestroy(PropField* f);
 cudaError_t propReset(PropField* f, cudaStream_t s);                                          // reset() :506-524
 cudaError_t propAddPoints(PropField* f, const double* d_xyz, size_t n, cudaStream_t s);      // addPointsToField :177-196
@@ -305,6 +305,7 @@ cudaError_t propUpdatePoints(PropField* f, const double* d_old, size_t n_old, co
 // readFromStream's tail (:730-758): every set bit of an occupancy bitmap (launchScatter's layout), in voxel order
 cudaError_t propAddOccupancy(PropField* f, const uint32_t* d_occ, cudaStream_t s);
 const int32_t* propDistances(const PropField* f);
+const int32_t* propNegativeDistances(const PropField* f);  // negative_distance_square_ (signed fields), else nullptr
 const PropStats& propStats(const PropField* f);
 // One field's elements of the interleaved compact field <-> a dense array (field replication across contexts):
 // `compact` is already offset to this field's first element; extract = to the dense array, else from it.

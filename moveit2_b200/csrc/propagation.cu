@@ -139,12 +139,23 @@ struct State
   uint32_t* lastp1;  // position + 1 of its last entry (0: none)
 };
 
-__global__ void resetKernel(State s, size_t n, int max_d2)
-{  // reset() :506-524
+__global__ void resetKernel(State s, size_t n, int max_d2, Dims g, int negative)
+{  // reset() :506-524 and the voxel constructor (propagation_distance_field.hpp:589-598): the negative half starts at
+   // distance 0 with every voxel its own closest free voxel
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
   {
-    s.dist[i] = max_d2;
-    s.cp[i] = 0;
+    if (negative)
+    {
+      int x, y, z;
+      coordsOf(g, static_cast<uint32_t>(i), x, y, z);
+      s.dist[i] = 0;
+      s.cp[i] = packPoint(x, y, z);
+    }
+    else
+    {
+      s.dist[i] = max_d2;
+      s.cp[i] = 0;
+    }
     s.dir[i] = 0;
     s.first[i] = kNone;
     s.lastp1[i] = 0;
@@ -394,15 +405,21 @@ __global__ void bitsToVoxelsKernel(const uint32_t* __restrict__ occ, Dims g, int
 }
 
 // addNewObstacleVoxels :221-243 / removeObstacleVoxels :303-330: the listed voxels' own records
-__global__ void markVoxelsKernel(const uint32_t* __restrict__ vox, uint32_t n, Dims g, State s, int dist_value)
+// (uninit: the negative half of a NEW obstacle voxel -- distance max, closest point UNINITIALIZED, direction untouched, :233-238)
+__global__ void markVoxelsKernel(const uint32_t* __restrict__ vox, uint32_t n, Dims g, State s, int dist_value, int uninit = 0)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
   const uint32_t v = vox[i];
+  s.dist[v] = dist_value;
+  if (uninit)
+  {
+    s.cp[v] = 0;
+    return;
+  }
   int x, y, z;
   coordsOf(g, v, x, y, z);
-  s.dist[v] = dist_value;
   s.cp[v] = packPoint(x, y, z);
   s.dir[v] = kInitialDirection;
 }
@@ -412,7 +429,10 @@ struct FloodCtl
 {
   unsigned long long sp, out_n;
 };
-__global__ void floodKernel(Dims g, int max_d2, State s, uint32_t* stack, uint32_t* out, unsigned long long out_cap, FloodCtl* ctl)
+// neg_style: the same walk over the negative half after obstacles were ADDED (:255-298): a voxel whose closest free voxel
+// became an obstacle goes back to "max, UNINITIALIZED" (its direction is left alone).
+__global__ void floodKernel(Dims g, int max_d2, State s, uint32_t* stack, uint32_t* out, unsigned long long out_cap, FloodCtl* ctl,
+                            int neg_style)
 {
   const int lane = threadIdx.x;
   unsigned long long sp = ctl->sp, out_n = ctl->out_n;
@@ -446,8 +466,13 @@ __global__ void floodKernel(Dims g, int max_d2, State s, uint32_t* stack, uint32
           if (s.dist[nv] != max_d2)
           {
             s.dist[nv] = max_d2;
-            s.cp[nv] = packPoint(nx, ny, nz);
-            s.dir[nv] = kInitialDirection;
+            if (neg_style)
+              s.cp[nv] = 0;
+            else
+            {
+              s.cp[nv] = packPoint(nx, ny, nz);
+              s.dir[nv] = kInitialDirection;
+            }
             push_stack = true;
           }
         }
@@ -572,6 +597,16 @@ struct PropField
   std::vector<std::vector<HostSeg>> buckets;  // bucket_queue_: segments of the pool, in push order
   Buf<uint32_t> pool;                         // queue entries (voxel references)
   size_t pool_off = 0;
+  // signed fields (propagate_negative_): the negative half's records and queue.  The functions below always work on the
+  // members above; swapHalves() makes the negative half the working one and back.
+  bool is_signed = false;
+  struct Half
+  {
+    State st{};
+    std::vector<std::vector<HostSeg>> buckets;
+    Buf<uint32_t> pool;
+    size_t pool_off = 0;
+  } neg;
   Buf<uint32_t> L;  // the bucket being drained, contiguous
   Buf<uint16_t> key_in, key_out;
   Buf<uint32_t> val_in, set_keys, set_keys_sorted, stack;
@@ -600,6 +635,14 @@ namespace
   } while (0)
 
 inline unsigned blocksFor(size_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+void swapHalves(PropField* f)
+{
+  std::swap(f->st, f->neg.st);
+  f->buckets.swap(f->neg.buckets);
+  std::swap(f->pool, f->neg.pool);
+  std::swap(f->pool_off, f->neg.pool_off);
+}
 
 // stable sort of n records by their 16-bit key; values land at `out_vals`
 cudaError_t sortRecords(PropField* f, size_t n, uint32_t* out_vals, cudaStream_t s)
@@ -761,41 +804,19 @@ cudaError_t propagate(PropField* f, cudaStream_t s)
   return cudaSuccess;
 }
 
-// addNewObstacleVoxels (:221-301, unsigned field) for `count` voxels already at pool[pool_off ..)
-cudaError_t addVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
+// the flood from the `count` voxels at the bottom of f->stack over the WORKING half; the bucket-0 entries it queues go to the
+// working pool
+cudaError_t floodFromStack(PropField* f, uint32_t count, int neg_style, cudaStream_t s)
 {
-  if (count)
-  {
-    markVoxelsKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->pool.p + f->pool_off, count, f->g, f->st, 0);
-    PCK(cudaGetLastError());
-    f->buckets[0].push_back(HostSeg{ f->pool_off, count });
-    f->pool_off += count;
-  }
-  return propagate(f, s);
-}
-
-// removeObstacleVoxels (:303-388, unsigned field) for `count` voxels at pool[pool_off ..) (not consumed as queue entries)
-cudaError_t removeVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
-{
-  const size_t stack_cap = static_cast<size_t>(count) + f->n_vox + 32;
-  PCK(f->stack.ensure(stack_cap));
-  if (count)
-  {
-    PCK(cudaMemcpyAsync(f->stack.p, f->pool.p + f->pool_off, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    markVoxelsKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->stack.p, count, f->g, f->st, f->gd.max_d2);
-    PCK(cudaGetLastError());
-  }
   FloodCtl fc{ count, 0 };
-  PCK(cudaMemcpyAsync(f->d_flood, &fc, sizeof(fc), cudaMemcpyHostToDevice, s));
-  PCK(cudaStreamSynchronize(s));
-  size_t seg_start = f->pool_off;
+  const size_t seg_start = f->pool_off;
   while (fc.sp > 0)
   {
     PCK(f->pool.ensure(f->pool_off + std::max<size_t>(size_t(1) << 20, 64 * fc.sp), true, f->pool_off, s));
     const unsigned long long room = f->pool.cap - f->pool_off;
     fc.out_n = 0;
     PCK(cudaMemcpyAsync(f->d_flood, &fc, sizeof(fc), cudaMemcpyHostToDevice, s));
-    floodKernel<<<1, 32, 0, s>>>(f->g, f->gd.max_d2, f->st, f->stack.p, f->pool.p + f->pool_off, room, f->d_flood);
+    floodKernel<<<1, 32, 0, s>>>(f->g, f->gd.max_d2, f->st, f->stack.p, f->pool.p + f->pool_off, room, f->d_flood, neg_style);
     PCK(cudaGetLastError());
     PCK(cudaMemcpyAsync(f->h_pin, f->d_flood, sizeof(fc), cudaMemcpyDeviceToHost, s));
     PCK(cudaStreamSynchronize(s));
@@ -803,14 +824,71 @@ cudaError_t removeVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
     f->pool_off += fc.out_n;
     f->stats.flood_pops_batches++;
   }
-  // one segment, or several of at most 2^32 - 1 entries
+  // one segment, or several of at most 2^31 - 1 entries
   for (size_t at = seg_start; at < f->pool_off;)
   {
     const uint32_t len = static_cast<uint32_t>(std::min<size_t>(f->pool_off - at, 0x7fffffffu));
     f->buckets[0].push_back(HostSeg{ at, len });
     at += len;
   }
-  return propagate(f, s);
+  return cudaSuccess;
+}
+
+// addNewObstacleVoxels (:221-301) for `count` voxels already at pool[pool_off ..)
+cudaError_t addVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
+{
+  if (f->is_signed)
+    PCK(f->stack.ensure(static_cast<size_t>(count) + f->n_vox + 32));
+  if (count)
+  {
+    if (f->is_signed)
+    {  // their negative halves: distance max, closest free voxel unknown; they seed the negative flood below (:233-238)
+      PCK(cudaMemcpyAsync(f->stack.p, f->pool.p + f->pool_off, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      markVoxelsKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->stack.p, count, f->g, f->neg.st, f->gd.max_d2, 1);
+    }
+    markVoxelsKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->pool.p + f->pool_off, count, f->g, f->st, 0);
+    PCK(cudaGetLastError());
+    f->buckets[0].push_back(HostSeg{ f->pool_off, count });
+    f->pool_off += count;
+  }
+  PCK(propagate(f, s));
+  if (!f->is_signed)
+    return cudaSuccess;
+  swapHalves(f);  // :255-300: the voxels whose closest free voxel is gone, then propagateNegative
+  cudaError_t e = floodFromStack(f, count, 1, s);
+  if (e == cudaSuccess)
+    e = propagate(f, s);
+  swapHalves(f);
+  return e;
+}
+
+// removeObstacleVoxels (:303-388) for `count` voxels at pool[pool_off ..) (not consumed as queue entries)
+cudaError_t removeVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
+{
+  PCK(f->stack.ensure(static_cast<size_t>(count) + f->n_vox + 32));
+  if (count)
+  {
+    PCK(cudaMemcpyAsync(f->stack.p, f->pool.p + f->pool_off, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    markVoxelsKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->stack.p, count, f->g, f->st, f->gd.max_d2);
+    PCK(cudaGetLastError());
+    if (f->is_signed)
+    {  // a removed voxel is free again: negative distance 0, queued in the negative bucket 0 (:321-328)
+      PCK(f->neg.pool.ensure(f->neg.pool_off + count, true, f->neg.pool_off, s));
+      PCK(cudaMemcpyAsync(f->neg.pool.p + f->neg.pool_off, f->stack.p, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      markVoxelsKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->stack.p, count, f->g, f->neg.st, 0);
+      PCK(cudaGetLastError());
+      f->neg.buckets[0].push_back(HostSeg{ f->neg.pool_off, count });
+      f->neg.pool_off += count;
+    }
+  }
+  PCK(floodFromStack(f, count, 0, s));
+  PCK(propagate(f, s));
+  if (!f->is_signed)
+    return cudaSuccess;
+  swapHalves(f);
+  const cudaError_t e = propagate(f, s);
+  swapHalves(f);
+  return e;
 }
 
 cudaError_t pointsToPool(PropField* f, const double* d_xyz, size_t n, int mode, cudaStream_t s, uint32_t* count)
@@ -827,7 +905,7 @@ cudaError_t pointsToPool(PropField* f, const double* d_xyz, size_t n, int mode, 
 }
 }  // namespace
 
-cudaError_t propCreate(const GridDev& gd, PropField** out)
+cudaError_t propCreate(const GridDev& gd, bool is_signed, PropField** out)
 {
   *out = nullptr;
   if (gd.nx > 65534 || gd.ny > 65534 || gd.nz > 65534 || gd.max_d2 >= 0xffff)
@@ -845,6 +923,16 @@ cudaError_t propCreate(const GridDev& gd, PropField** out)
   if (e == cudaSuccess) e = cudaMalloc(&f->st.dir, f->n_vox);
   if (e == cudaSuccess) e = cudaMalloc(&f->st.first, f->n_vox * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&f->st.lastp1, f->n_vox * sizeof(uint32_t));
+  f->is_signed = is_signed;
+  if (is_signed)
+  {
+    f->neg.buckets.resize(gd.max_d2 + 1);
+    if (e == cudaSuccess) e = cudaMalloc(&f->neg.st.dist, f->n_vox * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&f->neg.st.cp, f->n_vox * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&f->neg.st.dir, f->n_vox);
+    f->neg.st.first = f->st.first;  // the stamps belong to the round in flight: one set serves both halves
+    f->neg.st.lastp1 = f->st.lastp1;
+  }
   if (e == cudaSuccess) e = cudaMalloc(&f->d_ctl, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t));  // ctl | starts | ends
   if (e == cudaSuccess) e = cudaMemset(f->d_ctl, 0, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t));
   if (e == cudaSuccess)
@@ -872,6 +960,10 @@ void propDestroy(PropField* f)
   cudaFree(f->st.dir);
   cudaFree(f->st.first);
   cudaFree(f->st.lastp1);
+  cudaFree(f->neg.st.dist);
+  cudaFree(f->neg.st.cp);
+  cudaFree(f->neg.st.dir);
+  f->neg.pool.release();
   cudaFree(f->d_ctl);
   cudaFree(f->d_flood);
   if (f->h_pin)
@@ -895,7 +987,9 @@ void propDestroy(PropField* f)
 
 cudaError_t propReset(PropField* f, cudaStream_t s)
 {  // reset() re-initialises the voxels; the bucket queues are not its business (entries left there stay queued)
-  resetKernel<<<148 * 8, 256, 0, s>>>(f->st, f->n_vox, f->gd.max_d2);
+  resetKernel<<<148 * 8, 256, 0, s>>>(f->st, f->n_vox, f->gd.max_d2, f->g, 0);
+  if (f->is_signed)
+    resetKernel<<<148 * 8, 256, 0, s>>>(f->neg.st, f->n_vox, f->gd.max_d2, f->g, 1);
   return cudaGetLastError();
 }
 
@@ -985,5 +1079,6 @@ cudaError_t propAddOccupancy(PropField* f, const uint32_t* d_occ, cudaStream_t s
 }
 
 const int32_t* propDistances(const PropField* f) { return f->st.dist; }
+const int32_t* propNegativeDistances(const PropField* f) { return f->is_signed ? f->neg.st.dist : nullptr; }
 const PropStats& propStats(const PropField* f) { return f->stats; }
 }  // namespace b200sv

@@ -287,3 +287,41 @@ def test_the_references_df_fixture_through_read_df_in_reference_mode():
     ref.add_voxels(np.argwhere(occ2).astype(np.int32))
     same(eng, ref, "second stream")
     eng.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_signed_fields_in_reference_mode_equal_the_reference_on_both_halves(seed):
+    """propagate_negative_ (:48-58): adding obstacle voxels floods the negative half from them (:255-298) and runs
+    propagateNegative (:446-504); removing them queues them in the negative bucket 0 (:321-328).  Both halves equal the
+    oracle's after adds of solid bodies, a removal, an update and a reset."""
+    rng = np.random.default_rng(40 + seed)
+    size, origin, res, maxd = (0.6, 0.5, 0.4), (0.0, 0.1, 0.2), 0.02, 0.14
+    eng = mb.StateValidityEngine.for_robot("panda", "panda_arm", size=size, origin=origin, resolution=res,
+                                           max_distance=maxd, signed=True)
+    eng.field_set_propagation(mb.PROPAGATION_REFERENCE)
+    corner = [o - s_ / 2 for o, s_ in zip(origin, size)]
+    ref = PropagationDistanceField(size[0], size[1], size[2], res, corner[0], corner[1], corner[2], maxd, True)
+
+    def both(what):
+        same(eng, ref, what)
+        g, o = eng.field_get_neg_d2(), ref.neg_d2()
+        bad = int((g != o).sum())
+        assert bad == 0, "%s: %d voxels of the NEGATIVE half differ" % (what, bad)
+
+    def solid(c, h):  # every voxel centre of a box: interior voxels get negative distances
+        ax = [np.arange(c[k] - h[k], c[k] + h[k] + 1e-9, res) for k in range(3)]
+        p = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+        return p[rng.permutation(len(p))]
+
+    a = solid((0.05, 0.1, 0.2), (0.08, 0.06, 0.1))
+    b = solid((-0.15, 0.2, 0.25), (0.05, 0.05, 0.05))
+    eng.field_add_points(a); ref.add_points(a); both("add a")
+    assert int((ref.neg_d2() > 0).sum()) > 50
+    eng.field_add_points(b); ref.add_points(b); both("add b")
+    part = a[: len(a) // 3]
+    eng.field_remove_points(part); ref.remove_points(part); both("remove a third of a")
+    b2 = b + np.array([0.04, -0.02, 0.0])
+    eng.field_update_points(b, b2); ref.update_points(b, b2); both("update b -> b2")
+    eng.field_reset(); ref.reset(); both("reset")
+    eng.field_add_points(b2); ref.add_points(b2); both("add after reset")
+    eng.close()
