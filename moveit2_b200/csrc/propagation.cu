@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -210,21 +211,18 @@ __global__ void stampKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t
 }
 // every offer of entries [a, b) of bucket i: rec_key = its distance if it is accepted (kNoKey otherwise), rec_val = the target,
 // rec_cp = the closest point it carries | the direction number of the step << 48.  Reads the state, writes none of it.
+// One offer: record idx of the round [a, b) of bucket `bucket` (entry a + idx / S, slot idx % S).
 template <int S>
-__global__ void __launch_bounds__(256) offerKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t b, int bucket, Dims g,
-                                                   int max_d2, State s, uint16_t* __restrict__ rec_key,
-                                                   uint32_t* __restrict__ rec_val, uint64_t* __restrict__ rec_cp, RoundCtl* ctl)
+__device__ __forceinline__ void offerBody(size_t idx, const uint32_t* __restrict__ L, uint32_t a, Dims g, int max_d2, const State& s,
+                                          uint16_t* __restrict__ rec_key, uint32_t* __restrict__ rec_val,
+                                          uint64_t* __restrict__ rec_cp, uint32_t* cut, uint32_t* hazards)
 {
   constexpr int D = S == 26 ? 0 : 1;
-  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const size_t n_rec = static_cast<size_t>(b - a) * S;
-  if (idx >= n_rec)
-    return;
   const uint32_t p = a + static_cast<uint32_t>(idx / S);
   const int slot = static_cast<int>(idx % S);
   uint16_t key_out = kNoKey;
   const uint32_t v = L[p];
-  const int dv = s.dir[v];
+  const int dv = __ldcg(s.dir + v);
   if (dv <= 26 && slot < c_nb.cnt[D][dv])
   {
     const int ex = c_nb.nb[D][dv][slot][0], ey = c_nb.nb[D][dv][slot][1], ez = c_nb.nb[D][dv][slot][2];
@@ -233,12 +231,12 @@ __global__ void __launch_bounds__(256) offerKernel(const uint32_t* __restrict__ 
     const int tx = vx + ex, ty = vy + ey, tz = vz + ez;
     if (validCell(g, tx, ty, tz))
     {
-      const uint64_t cpv = s.cp[v];
+      const uint64_t cpv = __ldcg(s.cp + v);
       int cx, cy, cz;
       unpackPoint(cpv, cx, cy, cz);
       const long long nd = sq3(cx - tx, cy - ty, cz - tz);
       const uint32_t t = refOf(g, tx, ty, tz);
-      if (nd <= max_d2 && nd < s.dist[t])
+      if (nd <= max_d2 && nd < __ldcg(s.dist + t))
       {
         bool acc = true;
         const unsigned long long key = static_cast<unsigned long long>(p) * S + slot;
@@ -252,10 +250,10 @@ __global__ void __launch_bounds__(256) offerKernel(const uint32_t* __restrict__ 
           if (!validCell(g, ux, uy, uz))
             continue;
           const uint32_t u = refOf(g, ux, uy, uz);
-          const uint32_t fp = s.first[u];
+          const uint32_t fp = __ldcg(s.first + u);
           if (fp == kNone)
             continue;
-          const int du = s.dir[u];
+          const int du = __ldcg(s.dir + u);
           if (du > 26)
             continue;
           const int slot_u = c_nb.slot[D][du][k];
@@ -265,7 +263,7 @@ __global__ void __launch_bounds__(256) offerKernel(const uint32_t* __restrict__ 
           if (key_u >= key)
             continue;
           int ux2, uy2, uz2;
-          unpackPoint(s.cp[u], ux2, uy2, uz2);
+          unpackPoint(__ldcg(s.cp + u), ux2, uy2, uz2);
           const long long nd_u = sq3(ux2 - tx, uy2 - ty, uz2 - tz);
           if (nd_u <= max_d2 && nd_u <= nd)
             acc = false;
@@ -275,18 +273,30 @@ __global__ void __launch_bounds__(256) offerKernel(const uint32_t* __restrict__ 
           key_out = static_cast<uint16_t>(nd);
           rec_val[idx] = t;
           rec_cp[idx] = (cpv & kPointMask) | (static_cast<uint64_t>((ex + 1) * 9 + (ey + 1) * 3 + ez + 1) << 48);
-          const uint32_t lp1 = s.lastp1[t];
+          const uint32_t lp1 = __ldcg(s.lastp1 + t);
           if (lp1 > p + 1)
           {  // t still has an entry behind this one: its state would change under it
-            const uint32_t ft = s.first[t];
-            atomicMin(&ctl->cut, ft > p ? ft : p + 1);
-            atomicAdd(&ctl->hazards, 1u);
+            const uint32_t ft = __ldcg(s.first + t);
+            atomicMin(cut, ft > p ? ft : p + 1);
+            atomicAdd(hazards, 1u);
           }
         }
       }
     }
   }
   rec_key[idx] = key_out;
+}
+
+
+template <int S>
+__global__ void __launch_bounds__(256) offerKernel(const uint32_t* __restrict__ L, uint32_t a, uint32_t b, int bucket, Dims g,
+                                                   int max_d2, State s, uint16_t* __restrict__ rec_key,
+                                                   uint32_t* __restrict__ rec_val, uint64_t* __restrict__ rec_cp, RoundCtl* ctl)
+{
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<size_t>(b - a) * S)
+    return;
+  offerBody<S>(idx, L, a, g, max_d2, s, rec_key, rec_val, rec_cp, &ctl->cut, &ctl->hazards);
 }
 
 template <int S>
@@ -366,6 +376,284 @@ __global__ void roundInitKernel(RoundCtl* ctl, uint32_t cut, uint32_t* starts, u
   }
 }
 
+// ---- small buckets: the whole loop on the device -------------------------------------------------------------------------
+// A round of a few thousand entries is all latency: ~7 launches and a host synchronisation for microseconds of work.  The
+// resident kernel is ONE CTA that walks buckets and rounds by itself -- the same phases with __syncthreads between them, the
+// queue as a device-side segment table, the stable partition by destination bucket done in shared memory (every warp owns a
+// contiguous range of the round's records: per-warp histograms, a scan over (destination, warp), match_any ranks inside a
+// warp) -- and hands back to the host at the first bucket that is too big for it (or when the pool or the table is full):
+// always BEFORE it touches that bucket, so the host path can take over there.
+#ifndef B200SV_RESIDENT_RECORDS
+#define B200SV_RESIDENT_RECORDS 4096
+#endif
+constexpr int kMaxSeg = 256;            // segments per bucket in the device table ([kMaxSeg][n_buckets], column-major)
+constexpr int kResidentThreads = 1024;
+constexpr int kResidentWarps = kResidentThreads / 32;
+constexpr unsigned kResidentRecords = B200SV_RESIDENT_RECORDS;  // records per round it accepts: beyond a few iterations of the CTA per phase ONE SM has too few loads in flight and the host-driven kernels win
+constexpr int kResidentMaxBuckets = 1600;     // 32 histograms of that many bins fit shared memory
+enum { kResDone = 0, kResTooBig = 1, kResNeedPool = 2, kResSegFull = 3, kResFatal = 4 };
+struct ResidentCtl
+{
+  int status, bucket;
+  unsigned long long pool_off, rounds, hazard_rounds, entries;
+  unsigned hazards, backward, max_cnt, pad;
+};
+struct DevQueue
+{
+  uint32_t* start;  // [kMaxSeg][nb]
+  uint32_t* len;    // [kMaxSeg][nb]
+  uint32_t* cnt;    // [nb]
+};
+
+__global__ void __launch_bounds__(kResidentThreads, 1)
+residentKernel(State st, Dims g, int max_d2, uint32_t* __restrict__ pool, unsigned long long pool_cap, DevQueue q, int i0,
+               uint32_t* __restrict__ L, uint16_t* __restrict__ rec_key, uint32_t* __restrict__ rec_val,
+               uint64_t* __restrict__ rec_cp, ResidentCtl* ctl)
+{
+  extern __shared__ uint32_t rsm[];
+  const int nb = max_d2 + 1;
+  uint32_t* hist = rsm;                       // [kResidentWarps][nb]: counts, then running offsets
+  uint32_t* tot = hist + kResidentWarps * nb;  // [nb] kept records per destination
+  uint32_t* base = tot + nb;                  // [nb] exclusive scan of tot
+  uint32_t* sg_start = base + nb;             // [kMaxSeg] the segments of the bucket being drained
+  uint32_t* sg_out = sg_start + kMaxSeg;      // [kMaxSeg + 1] where each starts in L
+  __shared__ uint32_t s_cut, s_hazards, s_backward, s_maxcnt, s_kept;
+  __shared__ int s_status;
+  __shared__ unsigned long long s_pool_off, s_rounds, s_hazard_rounds, s_entries;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0)
+  {
+    s_hazards = 0;
+    s_backward = 0;
+    s_maxcnt = ctl->max_cnt;
+    s_pool_off = ctl->pool_off;
+    s_rounds = s_hazard_rounds = s_entries = 0;
+    s_status = kResDone;
+  }
+  __syncthreads();
+  int i = i0;
+  for (; i < nb; ++i)
+  {
+    const uint32_t cnt = __ldcg(q.cnt + i);
+    if (cnt == 0)
+      continue;
+    // the bucket's segments and where each lands in L
+    for (uint32_t k = tid; k < cnt; k += kResidentThreads)
+    {
+      sg_start[k] = __ldcg(q.start + static_cast<size_t>(k) * nb + i);
+      sg_out[k + 1] = __ldcg(q.len + static_cast<size_t>(k) * nb + i);
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+      uint32_t out = 0;
+      sg_out[0] = 0;
+      for (uint32_t k = 0; k < cnt; ++k)
+      {
+        const uint32_t l = sg_out[k + 1];
+        out = (out > 0xffffffffu - l) ? 0xffffffffu : out + l;  // saturating: a huge bucket is "too big", not a wrap-around
+        sg_out[k + 1] = out;
+      }
+      const int S0 = i == 0 ? 26 : 6;
+      const unsigned long long need = static_cast<unsigned long long>(out) * S0;
+      s_status = need > kResidentRecords ? kResTooBig
+                 : s_pool_off + need > pool_cap ? kResNeedPool
+                 : s_maxcnt + 8 > static_cast<uint32_t>(kMaxSeg) ? kResSegFull
+                                                                 : kResDone;
+    }
+    __syncthreads();
+    if (s_status != kResDone)
+      break;  // nothing of bucket i was touched
+    const uint32_t total = sg_out[cnt];
+    const int S = i == 0 ? 26 : 6;
+    for (uint32_t j = tid; j < total; j += kResidentThreads)
+    {
+      uint32_t lo = 0, hi = cnt;  // the segment that holds entry j: the last k with sg_out[k] <= j
+      while (hi - lo > 1)
+      {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sg_out[mid] <= j)
+          lo = mid;
+        else
+          hi = mid;
+      }
+      L[j] = __ldcg(pool + sg_start[lo] + (j - sg_out[lo]));
+    }
+    if (tid == 0)
+    {
+      q.cnt[i] = 0;  // what is pushed into the bucket while it drains never runs (:398, :441)
+      s_entries += total;
+    }
+    __syncthreads();
+    uint32_t a = 0;
+    while (a < total)
+    {
+      const uint32_t b = total;
+      const uint32_t n_rec = (b - a) * static_cast<uint32_t>(S);
+      if (tid == 0)
+      {
+        s_cut = b;
+        if (s_maxcnt + 1 > static_cast<uint32_t>(kMaxSeg))
+          s_status = kResFatal;  // eight rounds of one bucket on a nearly full table: see the check above
+      }
+      for (uint32_t p = a + tid; p < b; p += kResidentThreads)
+      {
+        const uint32_t v = L[p];
+        atomicMin(&st.first[v], p);
+        atomicMax(&st.lastp1[v], p + 1);
+      }
+      for (int k = tid; k < (kResidentWarps + 1) * nb; k += kResidentThreads)
+        hist[k] = 0;  // hist and tot
+      __syncthreads();
+      if (s_status == kResFatal)
+        break;
+      if (S == 26)
+        for (uint32_t idx = tid; idx < n_rec; idx += kResidentThreads)
+          offerBody<26>(idx, L, a, g, max_d2, st, rec_key, rec_val, rec_cp, &s_cut, &s_hazards);
+      else
+        for (uint32_t idx = tid; idx < n_rec; idx += kResidentThreads)
+          offerBody<6>(idx, L, a, g, max_d2, st, rec_key, rec_val, rec_cp, &s_cut, &s_hazards);
+      __syncthreads();
+      const uint32_t cut = s_cut;
+      for (uint32_t idx = tid; idx < n_rec; idx += kResidentThreads)
+      {
+        const uint16_t k = rec_key[idx];
+        if (k != kNoKey && a + idx / S < cut)
+          atomicMin(&st.dist[rec_val[idx]], static_cast<int32_t>(k));
+      }
+      __syncthreads();
+      for (uint32_t idx = tid; idx < n_rec; idx += kResidentThreads)
+      {
+        const uint16_t k = rec_key[idx];
+        if (k == kNoKey)
+          continue;
+        if (a + idx / S >= cut)
+        {
+          rec_key[idx] = kNoKey;
+          continue;
+        }
+        const uint32_t t = rec_val[idx];
+        if (__ldcg(st.dist + t) == static_cast<int32_t>(k))
+        {
+          const uint64_t r = rec_cp[idx];
+          st.cp[t] = r & kPointMask;
+          st.dir[t] = static_cast<uint8_t>(r >> 48);
+        }
+        if (static_cast<int>(k) <= i)
+          atomicAdd(&s_backward, 1u);
+        if (static_cast<int>(k) == i)
+          rec_key[idx] = kNoKey;
+      }
+      for (uint32_t p = a + tid; p < b; p += kResidentThreads)
+      {
+        const uint32_t v = L[p];
+        st.first[v] = kNone;
+        st.lastp1[v] = 0;
+      }
+      __syncthreads();
+      // stable partition of the kept records by destination: warp w owns records [w * chunk, (w + 1) * chunk)
+      const uint32_t chunk = ((n_rec + kResidentWarps - 1) / kResidentWarps + 31u) & ~31u;
+      const uint32_t r0 = warp * chunk, r1 = min(n_rec, r0 + chunk);
+      for (uint32_t j = r0 + lane; j < r1; j += 32)
+      {
+        const uint16_t k = rec_key[j];
+        if (k != kNoKey)
+          atomicAdd(&hist[warp * nb + k], 1u);
+      }
+      __syncthreads();
+      for (int d = tid; d < nb; d += kResidentThreads)
+      {
+        uint32_t run = 0;
+        for (int w = 0; w < kResidentWarps; ++w)
+        {
+          const uint32_t t = hist[w * nb + d];
+          hist[w * nb + d] = run;
+          run += t;
+        }
+        tot[d] = run;
+      }
+      __syncthreads();
+      if (warp == 0)
+      {  // exclusive scan of tot: every lane sums a contiguous stretch, the stretches are scanned across the warp
+        const int per = (nb + 31) / 32, d0 = lane * per, d1 = min(nb, d0 + per);
+        uint32_t sum = 0;
+        for (int d = d0; d < d1; ++d)
+          sum += tot[d];
+        uint32_t incl = sum;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o)
+            incl += up;
+        }
+        uint32_t run = incl - sum;
+        for (int d = d0; d < d1; ++d)
+        {
+          base[d] = run;
+          run += tot[d];
+        }
+        if (lane == 31)
+          s_kept = incl;
+      }
+      __syncthreads();
+      const unsigned long long pool_off = s_pool_off;
+      for (uint32_t j0 = r0; j0 < r1; j0 += 32)
+      {
+        const uint32_t j = j0 + lane;
+        const uint16_t k = j < r1 ? rec_key[j] : kNoKey;
+        const bool kept = k != kNoKey;
+        const unsigned mask = __match_any_sync(0xffffffffu, kept ? static_cast<unsigned>(k) : 0x10000u + lane);
+        if (kept)
+        {
+          const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+          pool[pool_off + base[k] + hist[warp * nb + k] + rank] = rec_val[j];
+        }
+        __syncwarp();
+        if (kept && lane == __ffs(mask) - 1)
+          hist[warp * nb + k] += __popc(mask);
+        __syncwarp();
+      }
+      __syncthreads();
+      for (int d = tid; d < nb; d += kResidentThreads)
+      {
+        const uint32_t n = tot[d];
+        if (n)
+        {  // one thread per destination: no two threads touch the same bucket's list
+          const uint32_t c = q.cnt[d];
+          q.start[static_cast<size_t>(c) * nb + d] = static_cast<uint32_t>(pool_off) + base[d];
+          q.len[static_cast<size_t>(c) * nb + d] = n;
+          q.cnt[d] = c + 1;
+          atomicMax(&s_maxcnt, c + 1);
+        }
+      }
+      __syncthreads();
+      if (tid == 0)
+      {
+        s_pool_off = pool_off + s_kept;
+        ++s_rounds;
+        if (cut < b)
+          ++s_hazard_rounds;
+      }
+      a = cut;
+      __syncthreads();
+    }
+    if (s_status == kResFatal)
+      break;
+  }
+  if (tid == 0)
+  {
+    ctl->status = s_status;
+    ctl->bucket = i;
+    ctl->pool_off = s_pool_off;
+    ctl->rounds = s_rounds;
+    ctl->hazard_rounds = s_hazard_rounds;
+    ctl->entries = s_entries;
+    ctl->hazards = s_hazards;
+    ctl->backward = s_backward;
+    ctl->max_cnt = s_maxcnt;
+  }
+}
+
 // ---- point lists -> voxel lists -----------------------------------------------------------------------------------------
 // worldToGrid (voxel_grid.hpp:395-407) in double, as scatterKernel.  mode 0: addPointsToField (:177-196) keeps valid points
 // whose voxel is not an obstacle yet; mode 1: removePointsFromField (:198-219) keeps every valid point.
@@ -429,10 +717,33 @@ struct FloodCtl
 {
   unsigned long long sp, out_n;
 };
-// neg_style: the same walk over the negative half after obstacles were ADDED (:255-298): a voxel whose closest free voxel
-// became an obstacle goes back to "max, UNINITIALIZED" (its direction is left alone).
-__global__ void floodKernel(Dims g, int max_d2, State s, uint32_t* stack, uint32_t* out, unsigned long long out_cap, FloodCtl* ctl,
-                            int neg_style)
+// What the walk does with a voxel it examines depends on nothing the walk itself changes, except "was it reset already":
+//   closest point gone (its voxel is no obstacle any more; an uninitialised closest point counts as the voxel itself)
+//     and distance != max   -> kReset: reset it and walk on from it, the first time it is examined
+//     and distance == max   -> kInert
+//   closest point still an obstacle -> kBoundary: queued in bucket 0, every time it is examined
+// so every voxel is classified up front, in parallel, and the one warp that must walk in the reference's order reads ONE byte
+// per neighbour instead of chasing closest point -> its voxel -> its distance.  What the walk would have written is applied
+// afterwards, in parallel again (applyFloodKernel).
+enum : uint8_t { kInert = 0, kReset = 1, kBoundary = 2, kWasReset = 3, kSeed = 4 };
+__global__ void classifyKernel(State s, Dims g, size_t n, int max_d2, uint8_t* __restrict__ type)
+{
+  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < n; v += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    int cx, cy, cz;
+    unpackPoint(s.cp[v], cx, cy, cz);
+    const uint32_t cpv = validCell(g, cx, cy, cz) ? refOf(g, cx, cy, cz) : static_cast<uint32_t>(v);
+    type[v] = s.dist[cpv] != 0 ? (s.dist[v] != max_d2 ? kReset : kInert) : kBoundary;
+  }
+}
+__global__ void seedTypesKernel(const uint32_t* __restrict__ stack, uint32_t count, uint8_t* __restrict__ type)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count)
+    type[stack[i]] = kSeed;  // the removed / added voxels themselves: inert when examined, but they ARE visited
+}
+// removeObstacleVoxels' walk (:332-384) and the negative half's after an addition (:255-298): one warp, the reference's order
+__global__ void floodKernel(Dims g, uint8_t* __restrict__ type, uint32_t* stack, uint32_t* out, unsigned long long out_cap, FloodCtl* ctl)
 {
   const int lane = threadIdx.x;
   unsigned long long sp = ctl->sp, out_n = ctl->out_n;
@@ -451,36 +762,13 @@ __global__ void floodKernel(Dims g, int max_d2, State s, uint32_t* stack, uint32
       if (validCell(g, nx, ny, nz))
       {
         nv = refOf(g, nx, ny, nz);
-        uint64_t cpn = s.cp[nv];
-        int cx, cy, cz;
-        unpackPoint(cpn, cx, cy, cz);
-        if (!validCell(g, cx, cy, cz))
-        {  // :350-354: an uninitialised closest point becomes the voxel itself
-          cx = nx;
-          cy = ny;
-          cz = nz;
-          s.cp[nv] = packPoint(nx, ny, nz);
-        }
-        if (s.dist[refOf(g, cx, cy, cz)] != 0)
-        {  // the closest point is no obstacle any more
-          if (s.dist[nv] != max_d2)
-          {
-            s.dist[nv] = max_d2;
-            if (neg_style)
-              s.cp[nv] = 0;
-            else
-            {
-              s.cp[nv] = packPoint(nx, ny, nz);
-              s.dir[nv] = kInitialDirection;
-            }
-            push_stack = true;
-          }
-        }
-        else
+        const uint8_t t = type[nv];
+        if (t == kReset)
         {
-          s.dir[nv] = kInitialDirection;
-          push_bucket = true;
+          type[nv] = kWasReset;
+          push_stack = true;
         }
+        push_bucket = t == kBoundary;
       }
     }
     const unsigned ms = __ballot_sync(0xffffffffu, push_stack), mb = __ballot_sync(0xffffffffu, push_bucket);
@@ -498,6 +786,48 @@ __global__ void floodKernel(Dims g, int max_d2, State s, uint32_t* stack, uint32
     ctl->sp = sp;
     ctl->out_n = out_n;
   }
+}
+// what the walk wrote on its way: a reset voxel is "max, itself" (positive half: update direction reset too; negative half:
+// reset to UNINITIALIZED, then set to itself when the voxel examined itself after being popped, :268-272); an uninitialised
+// closest point of ANY voxel examined -- a neighbour of a visited one -- becomes the voxel itself (:350-354)
+__global__ void applyFloodKernel(State s, Dims g, size_t n, int max_d2, const uint8_t* __restrict__ type, int neg_style)
+{
+  for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < n; v += static_cast<size_t>(gridDim.x) * blockDim.x)
+  {
+    int x, y, z;
+    coordsOf(g, static_cast<uint32_t>(v), x, y, z);
+    const uint8_t t = type[v];
+    if (t == kWasReset)
+    {
+      s.dist[v] = max_d2;
+      s.cp[v] = packPoint(x, y, z);
+      if (!neg_style)
+        s.dir[v] = kInitialDirection;
+      continue;
+    }
+    int cx, cy, cz;
+    unpackPoint(s.cp[v], cx, cy, cz);
+    if (validCell(g, cx, cy, cz))
+      continue;
+    bool examined = false;
+    for (int k = 0; k < 27 && !examined; ++k)
+    {
+      const int ux = x + k / 9 - 1, uy = y + (k / 3) % 3 - 1, uz = z + k % 3 - 1;
+      if (validCell(g, ux, uy, uz))
+      {
+        const uint8_t tu = type[refOf(g, ux, uy, uz)];
+        examined = tu == kWasReset || tu == kSeed;
+      }
+    }
+    if (examined)
+      s.cp[v] = packPoint(x, y, z);
+  }
+}
+__global__ void boundaryDirectionKernel(const uint32_t* __restrict__ out, unsigned long long n, State s)
+{
+  const unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    s.dir[out[i]] = kInitialDirection;  // :374 / :292
 }
 
 // ---- updatePointsInField (:130-175): VoxelSets ordered by z, y, x (propagation_distance_field.hpp:60-75) -----------------
@@ -613,6 +943,7 @@ struct PropField
   Buf<uint64_t> rec_cp;
   Buf<uint8_t> sort_tmp;
   Buf<uint32_t> set_bits;
+  Buf<uint8_t> flood_type;  // per voxel: what the removal walk does with it (classifyKernel)
   Buf<Seg> d_segs;
   RoundCtl* d_ctl = nullptr;
   FloodCtl* d_flood = nullptr;
@@ -622,6 +953,13 @@ struct PropField
   Seg* h_segs = nullptr;
   size_t h_segs_cap = 0;
   PropStats stats{};
+  // the resident kernel's side (small buckets): the queue's device-side table, its pinned mirror, the control block
+  bool resident_ok = false;
+  size_t resident_smem = 0;
+  DevQueue dq{};
+  uint32_t* h_q = nullptr;  // pinned: start [kMaxSeg][nb] | len [kMaxSeg][nb] | cnt [nb]
+  ResidentCtl* d_res = nullptr;
+  unsigned long long res_backward = 0, res_hazards = 0;
 };
 
 namespace
@@ -676,24 +1014,22 @@ cudaError_t keptCount(PropField* f, size_t n, cudaStream_t s, uint32_t* count)
   return cudaSuccess;
 }
 
-cudaError_t propagate(PropField* f, cudaStream_t s)
+// one bucket, host-driven: rounds of kernels, one synchronisation each
+cudaError_t drainBucketHost(PropField* f, int i, cudaStream_t s)
 {
   const int nb = f->gd.max_d2 + 1;
   constexpr size_t kMaxRecords = size_t(1) << 25;
-  for (int i = 0; i < nb; ++i)
   {
     std::vector<HostSeg>& segs = f->buckets[i];
     if (segs.empty())
-      continue;
+      return cudaSuccess;
     size_t total = 0;
     for (const HostSeg& sg : segs)
       total += sg.len;
     if (total == 0 || total >= 0xfffffff0ull)
     {
       segs.clear();
-      if (total)
-        return cudaErrorInvalidValue;
-      continue;
+      return total ? cudaErrorInvalidValue : cudaSuccess;
     }
     // the bucket, contiguous; its list is empty from here on: what is pushed into it while it drains never runs (:398, :441)
     if (segs.size() > f->h_segs_cap)
@@ -773,11 +1109,156 @@ cudaError_t propagate(PropField* f, cudaStream_t s)
       a = ctl->cut;
     }
   }
+  return cudaSuccess;
+}
+
+// ---- the resident kernel's host side --------------------------------------------------------------------------------------
+// host lists -> device table (only the columns in use); false: the lists do not fit the table's form right now
+bool uploadQueue(PropField* f, cudaStream_t s, uint32_t* max_cnt, cudaError_t* err)
+{
+  const size_t nb = f->buckets.size();
+  size_t maxc = 0;
+  for (const auto& b : f->buckets)
+    maxc = std::max(maxc, b.size());
+  if (maxc + 8 > static_cast<size_t>(kMaxSeg))
+    return false;
+  uint32_t* h_start = f->h_q;
+  uint32_t* h_len = f->h_q + static_cast<size_t>(kMaxSeg) * nb;
+  uint32_t* h_cnt = h_len + static_cast<size_t>(kMaxSeg) * nb;
+  for (size_t i = 0; i < nb; ++i)
+  {
+    const auto& b = f->buckets[i];
+    h_cnt[i] = static_cast<uint32_t>(b.size());
+    for (size_t k = 0; k < b.size(); ++k)
+    {
+      if (b[k].start + b[k].len > 0xffffffffull)
+        return false;
+      h_start[k * nb + i] = static_cast<uint32_t>(b[k].start);
+      h_len[k * nb + i] = b[k].len;
+    }
+  }
+  *err = cudaMemcpyAsync(f->dq.cnt, h_cnt, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+  if (*err == cudaSuccess && maxc)
+    *err = cudaMemcpyAsync(f->dq.start, h_start, maxc * nb * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+  if (*err == cudaSuccess && maxc)
+    *err = cudaMemcpyAsync(f->dq.len, h_len, maxc * nb * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+  *max_cnt = static_cast<uint32_t>(maxc);
+  return true;
+}
+
+cudaError_t downloadQueue(PropField* f, uint32_t max_cnt, cudaStream_t s)
+{
+  const size_t nb = f->buckets.size();
+  uint32_t* h_start = f->h_q;
+  uint32_t* h_len = f->h_q + static_cast<size_t>(kMaxSeg) * nb;
+  uint32_t* h_cnt = h_len + static_cast<size_t>(kMaxSeg) * nb;
+  const size_t cols = std::min<size_t>(max_cnt, kMaxSeg);
+  PCK(cudaMemcpyAsync(h_cnt, f->dq.cnt, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (cols)
+  {
+    PCK(cudaMemcpyAsync(h_start, f->dq.start, cols * nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PCK(cudaMemcpyAsync(h_len, f->dq.len, cols * nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  }
+  PCK(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < nb; ++i)
+  {
+    auto& b = f->buckets[i];
+    b.clear();
+    for (uint32_t k = 0; k < h_cnt[i] && k < cols; ++k)
+      b.push_back(HostSeg{ h_start[k * nb + i], h_len[k * nb + i] });
+  }
+  return cudaSuccess;
+}
+
+// Buckets from i0 on, on the device, until one is refused or none is left.  *next: the bucket the host has to drain itself
+// (n_buckets: none).  *entered false: the queue does not fit the device table right now, nothing was done.
+cudaError_t runResident(PropField* f, int i0, cudaStream_t s, int* next, bool* entered)
+{
+  const int nb = f->gd.max_d2 + 1;
+  *entered = false;
+  *next = i0;
+  uint32_t max_cnt = 0;
+  cudaError_t e = cudaSuccess;
+  PCK(f->L.ensure(kResidentRecords / 6 + 64));
+  PCK(ensureRecords(f, kResidentRecords, true));
+  PCK(f->pool.ensure(f->pool_off + 4 * static_cast<size_t>(kResidentRecords), true, f->pool_off, s));
+  if (f->pool.cap > 0xffffffffull || !uploadQueue(f, s, &max_cnt, &e))
+    return e;
+  PCK(e);
+  *entered = true;
+  ResidentCtl rc{};
+  int at = i0;
+  for (;;)
+  {
+    rc = ResidentCtl{};
+    rc.pool_off = f->pool_off;
+    rc.max_cnt = max_cnt;
+    std::memcpy(f->h_pin, &rc, sizeof(rc));
+    PCK(cudaMemcpyAsync(f->d_res, f->h_pin, sizeof(rc), cudaMemcpyHostToDevice, s));
+    residentKernel<<<1, kResidentThreads, f->resident_smem, s>>>(f->st, f->g, f->gd.max_d2, f->pool.p, f->pool.cap, f->dq, at, f->L.p,
+                                                                 f->key_in.p, f->val_in.p, f->rec_cp.p, f->d_res);
+    PCK(cudaGetLastError());
+    PCK(cudaMemcpyAsync(f->h_pin, f->d_res, sizeof(rc), cudaMemcpyDeviceToHost, s));
+    PCK(cudaStreamSynchronize(s));
+    std::memcpy(&rc, f->h_pin, sizeof(rc));
+    f->pool_off = rc.pool_off;
+    f->stats.rounds += rc.rounds;
+    f->stats.hazard_rounds += rc.hazard_rounds;
+    f->stats.entries += rc.entries;
+    f->res_backward += rc.backward;
+    f->res_hazards += rc.hazards;
+    max_cnt = rc.max_cnt;
+    if (rc.status != kResNeedPool)
+      break;
+    at = rc.bucket;  // grow the pool (the table's offsets stay valid), go on with the bucket it stopped in front of
+    PCK(f->pool.ensure(std::max(2 * f->pool.cap, f->pool_off + 8 * static_cast<size_t>(kResidentRecords)), true, f->pool_off, s));
+    if (f->pool.cap > 0xffffffffull)
+      break;  // beyond 32-bit offsets: the host path takes it from here
+  }
+  PCK(downloadQueue(f, max_cnt, s));
+  if (rc.status == kResFatal)
+    return cudaErrorInvalidValue;
+  *next = rc.status == kResDone ? nb : rc.bucket;
+  return cudaSuccess;
+}
+
+cudaError_t propagate(PropField* f, cudaStream_t s)
+{
+  const int nb = f->gd.max_d2 + 1;
+  for (int i = 0; i < nb; ++i)
+  {
+    if (f->buckets[i].empty())
+      continue;
+    if (f->resident_ok)
+    {
+      size_t total = 0;
+      for (const HostSeg& sg : f->buckets[i])
+        total += sg.len;
+      if (total * (i == 0 ? 26 : 6) <= kResidentRecords)
+      {
+        int next = i;
+        bool entered = false;
+        PCK(runResident(f, i, s, &next, &entered));
+        if (entered)
+        {
+          if (next >= nb)
+            break;
+          if (next > i)
+          {
+            i = next - 1;  // the loop's ++i lands on the bucket the device refused; its size is looked at again there
+            continue;
+          }
+          // refused the very bucket it was started on (a full pool beyond 32 bits, a full table): the host drains it
+        }
+      }
+    }
+    PCK(drainBucketHost(f, i, s));
+  }
   {  // counters, and the pool: entries pushed "backwards" stay queued for the next call (rare), everything else is spent
     PCK(cudaMemcpyAsync(f->h_pin, f->d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, s));
     PCK(cudaStreamSynchronize(s));
-    f->stats.backward_offers = reinterpret_cast<const RoundCtl*>(f->h_pin)->backward;
-    f->stats.hazard_offers = reinterpret_cast<const RoundCtl*>(f->h_pin)->hazards;
+    f->stats.backward_offers = reinterpret_cast<const RoundCtl*>(f->h_pin)->backward + f->res_backward;
+    f->stats.hazard_offers = reinterpret_cast<const RoundCtl*>(f->h_pin)->hazards + f->res_hazards;
     size_t left = 0;
     for (const auto& b : f->buckets)
       for (const HostSeg& sg : b)
@@ -810,19 +1291,33 @@ cudaError_t floodFromStack(PropField* f, uint32_t count, int neg_style, cudaStre
 {
   FloodCtl fc{ count, 0 };
   const size_t seg_start = f->pool_off;
+  if (count)
+  {
+    PCK(f->flood_type.ensure(f->n_vox));
+    classifyKernel<<<148 * 8, 256, 0, s>>>(f->st, f->g, f->n_vox, f->gd.max_d2, f->flood_type.p);
+    seedTypesKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->stack.p, count, f->flood_type.p);
+    PCK(cudaGetLastError());
+  }
   while (fc.sp > 0)
   {
     PCK(f->pool.ensure(f->pool_off + std::max<size_t>(size_t(1) << 20, 64 * fc.sp), true, f->pool_off, s));
     const unsigned long long room = f->pool.cap - f->pool_off;
     fc.out_n = 0;
     PCK(cudaMemcpyAsync(f->d_flood, &fc, sizeof(fc), cudaMemcpyHostToDevice, s));
-    floodKernel<<<1, 32, 0, s>>>(f->g, f->gd.max_d2, f->st, f->stack.p, f->pool.p + f->pool_off, room, f->d_flood, neg_style);
+    floodKernel<<<1, 32, 0, s>>>(f->g, f->flood_type.p, f->stack.p, f->pool.p + f->pool_off, room, f->d_flood);
     PCK(cudaGetLastError());
     PCK(cudaMemcpyAsync(f->h_pin, f->d_flood, sizeof(fc), cudaMemcpyDeviceToHost, s));
     PCK(cudaStreamSynchronize(s));
     std::memcpy(&fc, f->h_pin, sizeof(fc));
+    if (fc.out_n)
+      boundaryDirectionKernel<<<blocksFor(fc.out_n, 256), 256, 0, s>>>(f->pool.p + f->pool_off, fc.out_n, f->st);
     f->pool_off += fc.out_n;
     f->stats.flood_pops_batches++;
+  }
+  if (count)
+  {
+    applyFloodKernel<<<148 * 8, 256, 0, s>>>(f->st, f->g, f->n_vox, f->gd.max_d2, f->flood_type.p, neg_style);
+    PCK(cudaGetLastError());
   }
   // one segment, or several of at most 2^31 - 1 entries
   for (size_t at = seg_start; at < f->pool_off;)
@@ -942,6 +1437,25 @@ cudaError_t propCreate(const GridDev& gd, bool is_signed, PropField** out)
   }
   if (e == cudaSuccess) e = cudaMalloc(&f->d_flood, sizeof(FloodCtl));
   if (e == cudaSuccess) e = cudaMallocHost(&f->h_pin, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t) + 64);
+  // the resident kernel (small buckets): grids of at most kResidentMaxBuckets buckets, unless B200SV_PROP_RESIDENT=0
+  static const bool resident_off = getenv("B200SV_PROP_RESIDENT") && atoi(getenv("B200SV_PROP_RESIDENT")) == 0;
+  if (e == cudaSuccess && !resident_off && nb <= kResidentMaxBuckets)
+  {
+    f->resident_smem = (static_cast<size_t>(kResidentWarps + 2) * nb + 2 * kMaxSeg + 1) * sizeof(uint32_t);
+    const size_t qn = static_cast<size_t>(kMaxSeg) * nb;
+    if (cudaFuncSetAttribute(residentKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(f->resident_smem)) ==
+        cudaSuccess)
+    {
+      e = cudaMalloc(&f->dq.start, qn * sizeof(uint32_t));
+      if (e == cudaSuccess) e = cudaMalloc(&f->dq.len, qn * sizeof(uint32_t));
+      if (e == cudaSuccess) e = cudaMalloc(&f->dq.cnt, nb * sizeof(uint32_t));
+      if (e == cudaSuccess) e = cudaMalloc(&f->d_res, sizeof(ResidentCtl));
+      if (e == cudaSuccess) e = cudaMallocHost(&f->h_q, (2 * qn + nb) * sizeof(uint32_t));
+      f->resident_ok = e == cudaSuccess;
+    }
+    else
+      cudaGetLastError();  // not enough shared memory on this device: the host path does everything
+  }
   if (e != cudaSuccess)
   {
     propDestroy(f);
@@ -966,6 +1480,12 @@ void propDestroy(PropField* f)
   f->neg.pool.release();
   cudaFree(f->d_ctl);
   cudaFree(f->d_flood);
+  cudaFree(f->dq.start);
+  cudaFree(f->dq.len);
+  cudaFree(f->dq.cnt);
+  cudaFree(f->d_res);
+  if (f->h_q)
+    cudaFreeHost(f->h_q);
   if (f->h_pin)
     cudaFreeHost(f->h_pin);
   if (f->h_segs)
@@ -981,6 +1501,7 @@ void propDestroy(PropField* f)
   f->rec_cp.release();
   f->sort_tmp.release();
   f->set_bits.release();
+  f->flood_type.release();
   f->d_segs.release();
   delete f;
 }
