@@ -269,8 +269,12 @@ def parity_leg(mb, workloads, name, eng, cloud, n_want, flags, budget_s=25.0):
     try:
         eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_WORLD)
         eng.field_set_propagation(mb.PROPAGATION_REFERENCE, mb.FIELD_SELF)
-        eng.field_add_points(cloud, mb.FIELD_WORLD)
-        ref_ms = float(eng.stats()["edt_ms"])
+        ref_ms_all = []
+        for _ in range(3):   # the first build also allocates the mode's buffers; the field is the same every time
+            eng.field_reset(mb.FIELD_WORLD)
+            eng.field_add_points(cloud, mb.FIELD_WORLD)
+            ref_ms_all.append(float(eng.stats()["edt_ms"]))
+        ref_ms = min(ref_ms_all[1:])
         r_w, r_s = eng.field_get_d2(mb.FIELD_WORLD), eng.field_get_d2(mb.FIELD_SELF)
         ref_diff = ref_n = 0
         for item in chunks:
@@ -285,7 +289,8 @@ def parity_leg(mb, workloads, name, eng, cloud, n_want, flags, budget_s=25.0):
                     "device, fields built from the same point arrays as the oracle's",
             "world_voxels_differing_from_reference_propagation": int((r_w != o_w).sum()),
             "self_voxels_differing_from_reference_propagation": int((r_s != o_s).sum()),
-            "world_build_ms": ref_ms, "oracle_world_build_s": float(env.world_build_s),
+            "world_build_ms": ref_ms, "world_build_ms_first_call": ref_ms_all[0],
+            "oracle_world_build_s": float(env.world_build_s),
             "rounds": st["rounds"], "hazard_rounds": st["hazard_rounds"], "queue_entries": st["queue_entries"],
             "validity_states_compared_with_own_fields": int(ref_n),
             "validity_states_differing_with_own_fields": int(ref_diff)}

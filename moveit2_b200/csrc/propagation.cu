@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -878,7 +879,9 @@ struct Buf
   {
     if (n <= cap)
       return cudaSuccess;
-    const size_t want = std::max<size_t>(std::max<size_t>(n, 4096), keep ? cap * 2 : 0);
+    // geometric growth either way: the rounds of a first build grow bucket by bucket, and every cudaFree is a device-wide
+    // synchronisation
+    const size_t want = std::max<size_t>(std::max<size_t>(n, 4096), keep ? cap * 2 : cap + cap / 2);
     T* q = nullptr;
     cudaError_t e = cudaMalloc(&q, want * sizeof(T));
     if (e != cudaSuccess)
@@ -1225,8 +1228,22 @@ cudaError_t runResident(PropField* f, int i0, cudaStream_t s, int* next, bool* e
 cudaError_t propagate(PropField* f, cudaStream_t s)
 {
   const int nb = f->gd.max_d2 + 1;
+  static const bool trace = getenv("B200SV_PROP_TRACE") != nullptr;
   for (int i = 0; i < nb; ++i)
   {
+    const auto t_bucket = std::chrono::steady_clock::now();
+    struct Report
+    {
+      const std::chrono::steady_clock::time_point t0;
+      const int i;
+      const bool on;
+      ~Report()
+      {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (on && ms > 2.0)
+          fprintf(stderr, "[b200sv propagation] bucket %d: %.2f ms\n", i, ms);
+      }
+    } report{ t_bucket, i, trace };
     if (f->buckets[i].empty())
       continue;
     if (f->resident_ok)
