@@ -883,7 +883,12 @@ struct Buf
     // synchronisation
     const size_t want = std::max<size_t>(std::max<size_t>(n, 4096), keep ? cap * 2 : cap + cap / 2);
     T* q = nullptr;
+    static const bool trace = getenv("B200SV_PROP_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMalloc(&q, want * sizeof(T));
+    if (trace)
+      fprintf(stderr, "[b200sv propagation] buffer of %zu-byte elements grows %zu -> %zu (asked %zu): cudaMalloc %.2f ms\n", sizeof(T), cap,
+              want, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     if (e != cudaSuccess)
       return e;
     if (p)
@@ -1022,6 +1027,25 @@ cudaError_t drainBucketHost(PropField* f, int i, cudaStream_t s)
 {
   const int nb = f->gd.max_d2 + 1;
   constexpr size_t kMaxRecords = size_t(1) << 25;
+  static const bool trace = getenv("B200SV_PROP_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  double marks[6] = { 0, 0, 0, 0, 0, 0 };
+  auto mark = [&](int k) {
+    if (trace)
+      marks[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  };
+  struct Dump
+  {
+    const double* m;
+    const int i;
+    const bool on;
+    ~Dump()
+    {
+      if (on && m[5] > 2.0)
+        fprintf(stderr, "[b200sv propagation] bucket %d: buffers %.2f | gather %.2f | round buffers %.2f | kernels queued %.2f | sort queued %.2f | synced %.2f ms\n",
+                i, m[0], m[1], m[2], m[3], m[4], m[5]);
+    }
+  } dump{ marks, i, trace };
   {
     std::vector<HostSeg>& segs = f->buckets[i];
     if (segs.empty())
@@ -1046,6 +1070,7 @@ cudaError_t drainBucketHost(PropField* f, int i, cudaStream_t s)
     }
     PCK(f->d_segs.ensure(segs.size()));
     PCK(f->L.ensure(total));
+    mark(0);
     {
       uint32_t out = 0, longest = 0;
       for (size_t k = 0; k < segs.size(); ++k)
@@ -1061,6 +1086,7 @@ cudaError_t drainBucketHost(PropField* f, int i, cudaStream_t s)
       // (h_segs is rewritten for the next bucket only after this bucket's rounds, each of which ends in a synchronisation)
     }
     segs.clear();
+    mark(1);
     f->stats.entries += total;
     const int S = i == 0 ? 26 : 6;
     uint32_t a = 0;
@@ -1071,6 +1097,7 @@ cudaError_t drainBucketHost(PropField* f, int i, cudaStream_t s)
       const size_t n_rec = static_cast<size_t>(b - a) * S;
       PCK(ensureRecords(f, n_rec, true));
       PCK(f->pool.ensure(f->pool_off + n_rec, true, f->pool_off, s));
+      mark(2);
       stampKernel<<<blocksFor(b - a, 256), 256, 0, s>>>(f->L.p, a, b, f->st, f->d_ctl, f->d_starts, f->d_ends, nb);
       if (S == 26)
       {
@@ -1087,12 +1114,15 @@ cudaError_t drainBucketHost(PropField* f, int i, cudaStream_t s)
         applyStateKernel<6><<<blocksFor(n_rec, 256), 256, 0, s>>>(a, n_rec, i, f->key_in.p, f->val_in.p, f->rec_cp.p, f->st, f->d_ctl);
       }
       PCK(cudaGetLastError());
+      mark(3);
       PCK(sortRecords(f, n_rec, f->pool.p + f->pool_off, s));
+      mark(4);
       runsKernel<<<blocksFor(n_rec, 256), 256, 0, s>>>(f->key_out.p, n_rec, f->d_starts, f->d_ends, f->L.p, a, b, f->st);
       PCK(cudaGetLastError());
       uint8_t* h = f->h_pin;  // ctl | starts | ends are one device allocation: one copy
       PCK(cudaMemcpyAsync(h, f->d_ctl, sizeof(RoundCtl) + 2 * nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       PCK(cudaStreamSynchronize(s));
+      mark(5);
       const RoundCtl* ctl = reinterpret_cast<const RoundCtl*>(h);
       const uint32_t* starts = reinterpret_cast<const uint32_t*>(h + sizeof(RoundCtl));
       const uint32_t* ends = starts + nb;
