@@ -57,6 +57,10 @@ int main(int argc, char** argv)
   rc = b200sv_check_batch(ctx, q, 1, B200SV_CHECK_ALL, &bit);
   if (rc != B200SV_ERR_NO_DEVICE)
     return 6;
+  /* ... and so does the switch to the reference's own propagation (it needs the device) */
+  if (b200sv_field_set_propagation(ctx, B200SV_FIELD_WORLD, B200SV_PROPAGATION_REFERENCE) != B200SV_ERR_NO_DEVICE)
+    return 7;
+  rc = b200sv_check_batch(ctx, q, 1, B200SV_CHECK_ALL, &bit); /* the message printed below is this call's */
   printf("c abi ok: %d links, %d group variables, %d spheres, %d link pairs, field %d x %d x %d, max d2 %d; compute refused: %s\n",
          info.n_links, info.n_group_vars, info.n_spheres, info.n_link_pairs, info.num_cells[0], info.num_cells[1],
          info.num_cells[2], info.max_distance_sq, b200sv_last_error(ctx));
