@@ -737,32 +737,41 @@ __global__ void classifyKernel(State s, Dims g, size_t n, int max_d2, uint8_t* _
     type[v] = s.dist[cpv] != 0 ? (s.dist[v] != max_d2 ? kReset : kInert) : kBoundary;
   }
 }
-__global__ void seedTypesKernel(const uint32_t* __restrict__ stack, uint32_t count, uint8_t* __restrict__ type)
+// the walk's stack holds COORDINATES (packPoint): the one warp that walks would otherwise spend a third of its instructions on
+// the two integer divisions that turn a voxel reference into x, y, z
+__global__ void seedTypesKernel(const uint32_t* __restrict__ seeds, uint32_t count, Dims g, uint8_t* __restrict__ type,
+                                uint64_t* __restrict__ stack)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count)
-    type[stack[i]] = kSeed;  // the removed / added voxels themselves: inert when examined, but they ARE visited
+  if (i >= count)
+    return;
+  const uint32_t v = seeds[i];
+  int x, y, z;
+  coordsOf(g, v, x, y, z);
+  stack[i] = packPoint(x, y, z);
+  type[v] = kSeed;  // the removed / added voxels themselves: inert when examined, but they ARE visited
 }
 // removeObstacleVoxels' walk (:332-384) and the negative half's after an addition (:255-298): one warp, the reference's order
-__global__ void floodKernel(Dims g, uint8_t* __restrict__ type, uint32_t* stack, uint32_t* out, unsigned long long out_cap, FloodCtl* ctl)
+__global__ void floodKernel(Dims g, uint8_t* __restrict__ type, uint64_t* stack, uint32_t* out, unsigned long long out_cap, FloodCtl* ctl)
 {
   const int lane = threadIdx.x;
   unsigned long long sp = ctl->sp, out_n = ctl->out_n;
   const int ex = lane / 9 - 1, ey = (lane / 3) % 3 - 1, ez = lane % 3 - 1;  // direction_number_to_direction_[lane]
   while (sp > 0 && out_n + 27 <= out_cap)
   {
-    const uint32_t loc = stack[sp - 1];
-    --sp;
     int lx, ly, lz;
-    coordsOf(g, loc, lx, ly, lz);
+    unpackPoint(stack[sp - 1], lx, ly, lz);
+    --sp;
     bool push_stack = false, push_bucket = false;
     uint32_t nv = 0;
+    uint64_t nc = 0;
     if (lane < 27)
     {
       const int nx = lx + ex, ny = ly + ey, nz = lz + ez;
       if (validCell(g, nx, ny, nz))
       {
         nv = refOf(g, nx, ny, nz);
+        nc = packPoint(nx, ny, nz);
         const uint8_t t = type[nv];
         if (t == kReset)
         {
@@ -775,7 +784,7 @@ __global__ void floodKernel(Dims g, uint8_t* __restrict__ type, uint32_t* stack,
     const unsigned ms = __ballot_sync(0xffffffffu, push_stack), mb = __ballot_sync(0xffffffffu, push_bucket);
     const unsigned lt = (1u << lane) - 1u;
     if (push_stack)
-      stack[sp + __popc(ms & lt)] = nv;
+      stack[sp + __popc(ms & lt)] = nc;
     if (push_bucket)
       out[out_n + __popc(mb & lt)] = nv;
     sp += __popc(ms);
@@ -952,6 +961,7 @@ struct PropField
   Buf<uint8_t> sort_tmp;
   Buf<uint32_t> set_bits;
   Buf<uint8_t> flood_type;  // per voxel: what the removal walk does with it (classifyKernel)
+  Buf<uint64_t> stack_xyz;  // the walk's stack, as coordinates
   Buf<Seg> d_segs;
   RoundCtl* d_ctl = nullptr;
   FloodCtl* d_flood = nullptr;
@@ -1341,8 +1351,9 @@ cudaError_t floodFromStack(PropField* f, uint32_t count, int neg_style, cudaStre
   if (count)
   {
     PCK(f->flood_type.ensure(f->n_vox));
+    PCK(f->stack_xyz.ensure(static_cast<size_t>(count) + f->n_vox + 32));  // every voxel is pushed at most once more
     classifyKernel<<<148 * 8, 256, 0, s>>>(f->st, f->g, f->n_vox, f->gd.max_d2, f->flood_type.p);
-    seedTypesKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->stack.p, count, f->flood_type.p);
+    seedTypesKernel<<<blocksFor(count, 256), 256, 0, s>>>(f->stack.p, count, f->g, f->flood_type.p, f->stack_xyz.p);
     PCK(cudaGetLastError());
   }
   while (fc.sp > 0)
@@ -1351,7 +1362,7 @@ cudaError_t floodFromStack(PropField* f, uint32_t count, int neg_style, cudaStre
     const unsigned long long room = f->pool.cap - f->pool_off;
     fc.out_n = 0;
     PCK(cudaMemcpyAsync(f->d_flood, &fc, sizeof(fc), cudaMemcpyHostToDevice, s));
-    floodKernel<<<1, 32, 0, s>>>(f->g, f->flood_type.p, f->stack.p, f->pool.p + f->pool_off, room, f->d_flood);
+    floodKernel<<<1, 32, 0, s>>>(f->g, f->flood_type.p, f->stack_xyz.p, f->pool.p + f->pool_off, room, f->d_flood);
     PCK(cudaGetLastError());
     PCK(cudaMemcpyAsync(f->h_pin, f->d_flood, sizeof(fc), cudaMemcpyDeviceToHost, s));
     PCK(cudaStreamSynchronize(s));
@@ -1380,7 +1391,7 @@ cudaError_t floodFromStack(PropField* f, uint32_t count, int neg_style, cudaStre
 cudaError_t addVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
 {
   if (f->is_signed)
-    PCK(f->stack.ensure(static_cast<size_t>(count) + f->n_vox + 32));
+    PCK(f->stack.ensure(static_cast<size_t>(count) + 32));
   if (count)
   {
     if (f->is_signed)
@@ -1407,7 +1418,7 @@ cudaError_t addVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
 // removeObstacleVoxels (:303-388) for `count` voxels at pool[pool_off ..) (not consumed as queue entries)
 cudaError_t removeVoxelsAtPool(PropField* f, uint32_t count, cudaStream_t s)
 {
-  PCK(f->stack.ensure(static_cast<size_t>(count) + f->n_vox + 32));
+  PCK(f->stack.ensure(static_cast<size_t>(count) + 32));
   if (count)
   {
     PCK(cudaMemcpyAsync(f->stack.p, f->pool.p + f->pool_off, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
@@ -1549,6 +1560,7 @@ void propDestroy(PropField* f)
   f->sort_tmp.release();
   f->set_bits.release();
   f->flood_type.release();
+  f->stack_xyz.release();
   f->d_segs.release();
   delete f;
 }
