@@ -18,14 +18,19 @@
 // earliest position a hazard touches, the part before the cut is applied -- it is unaffected, by induction over positions --
 // and the rest is redone as another ROUND with the updated states.  A round is therefore: stamp the entries' positions,
 // compute all offers and their acceptance (read-only), apply them up to the cut, sort the accepted offers by destination
-// bucket (stable: key order is kept) straight into the queue pool, un-stamp.  One host synchronisation per round.
+// bucket (stable: key order is kept) straight into the queue pool, un-stamp.  Big rounds are driven by the host (a handful of
+// kernels, cub's radix sort for the partition, one synchronisation per round); buckets whose round has a few thousand offers
+// at most are drained by ONE resident CTA that walks buckets and rounds by itself (residentKernel below).
 //
 // The removal flood (removeObstacleVoxels :303-388) is a depth-first walk whose visiting order decides the order of the
 // bucket-0 entries it queues, i.e. later ties: it runs as ONE warp (27 lanes = the 27 neighbours of the voxel on top of
-// the stack), exactly in the reference's order.
+// the stack), exactly in the reference's order -- over one pre-classified byte per voxel, since what the walk does with a voxel
+// depends only on the state before the walk; its writes are applied afterwards, in parallel.
+//
+// Signed fields (propagate_negative_) keep a second half of records and a second queue; the same code runs on either half.
 //
 // This mode exists for parity with the reference's numbers; it costs milliseconds where the exact transform costs
-// a tenth of one.  cub's radix sort (CUDA toolkit headers) does the stable partition.
+// a tenth of one.
 #include <cuda_runtime.h>
 
 #include <algorithm>
