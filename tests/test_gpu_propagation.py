@@ -325,3 +325,21 @@ def test_signed_fields_in_reference_mode_equal_the_reference_on_both_halves(seed
     eng.field_reset(); ref.reset(); both("reset")
     eng.field_add_points(b2); ref.add_points(b2); both("add after reset")
     eng.close()
+
+
+@pytest.mark.parametrize("resident", ["1", "0"])
+def test_randomised_campaign_with_and_without_the_resident_kernel(resident):
+    """tools/prop_fuzz.py for a few seconds in a process of its own: random grids, radii, signed / unsigned fields, random
+    add / remove / update / reset sequences, every call compared with the oracle.  B200SV_PROP_RESIDENT=0 keeps every round
+    host-driven, so both ways of draining a bucket are held to the same campaign."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200SV_PROP_RESIDENT=resident)
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "prop_fuzz.py"), "8", "3"], capture_output=True, text=True,
+                         env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    summary = json.loads(out.stdout.strip().splitlines()[-1])
+    assert summary["calls"] > 50 and summary["mismatching_calls"] == 0, (summary, out.stderr[-2000:])
