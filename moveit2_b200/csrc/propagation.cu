@@ -424,6 +424,7 @@ residentKernel(State st, Dims g, int max_d2, uint32_t* __restrict__ pool, unsign
   uint32_t* sg_start = base + nb;             // [kMaxSeg] the segments of the bucket being drained
   uint32_t* sg_out = sg_start + kMaxSeg;      // [kMaxSeg + 1] where each starts in L
   __shared__ uint32_t s_cut, s_hazards, s_backward, s_maxcnt, s_kept;
+  __shared__ int s_dlo, s_dhi;  // destinations this round's kept records go to: only that window of the histograms is live
   __shared__ int s_status;
   __shared__ unsigned long long s_pool_off, s_rounds, s_hazard_rounds, s_entries;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -435,7 +436,11 @@ residentKernel(State st, Dims g, int max_d2, uint32_t* __restrict__ pool, unsign
     s_pool_off = ctl->pool_off;
     s_rounds = s_hazard_rounds = s_entries = 0;
     s_status = kResDone;
+    s_dlo = nb;
+    s_dhi = -1;
   }
+  for (int k = tid; k < (kResidentWarps + 1) * nb; k += kResidentThreads)
+    hist[k] = 0;  // hist and tot: all zero between rounds (a round clears the window it used)
   __syncthreads();
   int i = i0;
   for (; i < nb; ++i)
@@ -508,8 +513,6 @@ residentKernel(State st, Dims g, int max_d2, uint32_t* __restrict__ pool, unsign
         atomicMin(&st.first[v], p);
         atomicMax(&st.lastp1[v], p + 1);
       }
-      for (int k = tid; k < (kResidentWarps + 1) * nb; k += kResidentThreads)
-        hist[k] = 0;  // hist and tot
       __syncthreads();
       if (s_status == kResFatal)
         break;
@@ -560,14 +563,29 @@ residentKernel(State st, Dims g, int max_d2, uint32_t* __restrict__ pool, unsign
       // stable partition of the kept records by destination: warp w owns records [w * chunk, (w + 1) * chunk)
       const uint32_t chunk = ((n_rec + kResidentWarps - 1) / kResidentWarps + 31u) & ~31u;
       const uint32_t r0 = warp * chunk, r1 = min(n_rec, r0 + chunk);
-      for (uint32_t j = r0 + lane; j < r1; j += 32)
       {
-        const uint16_t k = rec_key[j];
-        if (k != kNoKey)
-          atomicAdd(&hist[warp * nb + k], 1u);
+        int lo = nb, hi = -1;
+        for (uint32_t j = r0 + lane; j < r1; j += 32)
+        {
+          const uint16_t k = rec_key[j];
+          if (k != kNoKey)
+          {
+            atomicAdd(&hist[warp * nb + k], 1u);
+            lo = min(lo, static_cast<int>(k));
+            hi = max(hi, static_cast<int>(k));
+          }
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0 && hi >= 0)
+        {
+          atomicMin(&s_dlo, lo);
+          atomicMax(&s_dhi, hi);
+        }
       }
       __syncthreads();
-      for (int d = tid; d < nb; d += kResidentThreads)
+      const int dlo = s_dlo, dhi = s_dhi, nd = dhi - dlo + 1;  // nd <= 0: nothing was kept
+      for (int d = dlo + tid; d <= dhi; d += kResidentThreads)
       {
         uint32_t run = 0;
         for (int w = 0; w < kResidentWarps; ++w)
@@ -580,8 +598,8 @@ residentKernel(State st, Dims g, int max_d2, uint32_t* __restrict__ pool, unsign
       }
       __syncthreads();
       if (warp == 0)
-      {  // exclusive scan of tot: every lane sums a contiguous stretch, the stretches are scanned across the warp
-        const int per = (nb + 31) / 32, d0 = lane * per, d1 = min(nb, d0 + per);
+      {  // exclusive scan of tot over the window: every lane sums a contiguous stretch, the stretches are scanned across the warp
+        const int per = (max(nd, 0) + 31) / 32, d0 = dlo + lane * per, d1 = min(dhi + 1, d0 + per);
         uint32_t sum = 0;
         for (int d = d0; d < d1; ++d)
           sum += tot[d];
@@ -620,7 +638,7 @@ residentKernel(State st, Dims g, int max_d2, uint32_t* __restrict__ pool, unsign
         __syncwarp();
       }
       __syncthreads();
-      for (int d = tid; d < nb; d += kResidentThreads)
+      for (int d = dlo + tid; d <= dhi; d += kResidentThreads)
       {
         const uint32_t n = tot[d];
         if (n)
@@ -631,10 +649,15 @@ residentKernel(State st, Dims g, int max_d2, uint32_t* __restrict__ pool, unsign
           q.cnt[d] = c + 1;
           atomicMax(&s_maxcnt, c + 1);
         }
+        tot[d] = 0;
       }
+      for (int k = tid; k < kResidentWarps * max(nd, 0); k += kResidentThreads)
+        hist[(k / nd) * nb + dlo + k % nd] = 0;  // the window is clean again for the next round
       __syncthreads();
       if (tid == 0)
       {
+        s_dlo = nb;
+        s_dhi = -1;
         s_pool_off = pool_off + s_kept;
         ++s_rounds;
         if (cut < b)
