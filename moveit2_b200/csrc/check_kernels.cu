@@ -717,23 +717,29 @@ __global__ void __launch_bounds__(128) fkKernel(FkArgs a)
     __syncwarp();
     // write-out: lanes stride over (state, model link, element)
     // (a state's L 4x4 matrices are 128 L contiguous bytes: every warp store is 256 contiguous bytes; no index division)
+    // A lane's element of the 4x4 matrix is fixed (rem = lane + 32 k: e = lane & 15), so what the element is -- a constant, or a
+    // word of the state's transform block -- is decided once per pair of links, outside the loop over the tile's states:
+    // the inner loop is one shared-memory load, one conversion, one store.
     const int per_state = a.n_model_links * 16;
-    for (int s = 0; s < cnt; ++s)
+    const int e = lane & 15, c = e >> 2, r = e & 3;
+    double* dst0 = a.out + first * per_state;
+    for (int rem = lane; rem < per_state; rem += 32)
     {
-      const R* Tstate = Ts + s * h.state_stride;
-      double* dst = a.out + (first + s) * per_state;
-      for (int rem = lane; rem < per_state; rem += 32)
+      const int l = rem >> 4;
+      const int slot = __ldg(a.link_slot + l);
+      if (r == 3 || slot < 0)
       {
-        const int l = rem >> 4, e = rem & 15, c = e >> 2, r = e & 3;
-        double v;
-        const int slot = __ldg(a.link_slot + l);
-        if (r == 3)
-          v = c == 3 ? 1.0 : 0.0;
-        else if (slot >= 0)
-          v = static_cast<double>(Tstate[slot * kLinkStrideWords + r * 4 + c]);
-        else
-          v = __ldg(a.const_T + l * 16 + e);
-        dst[rem] = v;
+        const double v = r == 3 ? (c == 3 ? 1.0 : 0.0) : __ldg(a.const_T + l * 16 + e);
+#pragma unroll 8
+        for (int s = 0; s < cnt; ++s)
+          dst0[static_cast<size_t>(s) * per_state + rem] = v;
+      }
+      else
+      {
+        const R* src = Ts + slot * kLinkStrideWords + r * 4 + c;
+#pragma unroll 8
+        for (int s = 0; s < cnt; ++s)
+          dst0[static_cast<size_t>(s) * per_state + rem] = static_cast<double>(src[s * h.state_stride]);
       }
     }
     __syncwarp();
