@@ -31,6 +31,8 @@
 // operation by operation.  The conservative culls only ever skip pairs that cannot collide, so they change no result.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include <cstdint>
 
 #include "device_model.hpp"
@@ -1157,6 +1159,7 @@ __global__ void __launch_bounds__(128) contactKernel(ContactArgs a)
 // the latency of a single state, not throughput.  Lane 0 runs the FP64 forward kinematics into shared memory, then the
 // 32 lanes share the spheres and the cluster pairs of that one state.  Same device functions (same arithmetic) as
 // checkKernel<double, ., true>.
+constexpr int kRecheckScLinks = 64;
 template <typename FT>
 __global__ void __launch_bounds__(128) recheckWarpKernel(CheckArgs<FT> a)
 {
@@ -1165,14 +1168,33 @@ __global__ void __launch_bounds__(128) recheckWarpKernel(CheckArgs<FT> a)
   const ModelHeader<double>& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   double* T = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(warp) * h.state_stride;
+  // sines and cosines of the state's joints, one link per lane, for the chain lane 0 walks (robots of up to kRecheckScLinks
+  // links; beyond that lane 0 computes them on its way, as before)
+  double* sc = reinterpret_cast<double*>(smem + h.total_bytes) + static_cast<size_t>(warps) * h.state_stride +
+               static_cast<size_t>(warp) * 2 * kRecheckScLinks;
+  const bool par_sc = h.n_links <= kRecheckScLinks;
   const bool do_world = (a.flags & 1u) != 0, do_self = (a.flags & 2u) != 0, do_intra = (a.flags & 4u) != 0;
   const typename Combined<FT>::type* __restrict__ field = static_cast<const typename Combined<FT>::type*>(a.field);
+  // launched with programmatic stream serialization: everything above ran while the kernel before this one (the FP32 pass that
+  // fills the list) was draining; nothing it wrote is read before this point.  A no-op for an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const unsigned n = *a.list_count < a.list_cap ? *a.list_count : a.list_cap;
   for (unsigned i = blockIdx.x * warps + warp; i < n; i += gridDim.x * warps)
   {
     const unsigned long long state = a.list[i];
+    const double* qrow = a.q + state * h.n_group_vars;
+    if (par_sc)
+    {
+      for (int l = lane; l < h.n_links; l += 32)
+      {
+        const LinkRec<double>& L = m.links[l];
+        if (L.type == REVOLUTE || L.type == PLANAR)
+          sincos(varValue<double>(m.vars[L.var + (L.type == PLANAR ? 2 : 0)], qrow), &sc[2 * l], &sc[2 * l + 1]);
+      }
+      __syncwarp();
+    }
     if (lane == 0)
-      fkState<double>(m, a.q + state * h.n_group_vars, T);
+      fkState<double>(m, qrow, T, par_sc ? sc : nullptr);
     __syncwarp();
     bool hit = false, amb = false;
     if (do_world | do_self)
@@ -1432,12 +1454,27 @@ cudaError_t launchRecheckWarp(const CheckArgs<FT>& a, int grid, int state_stride
   static SmemGrant g;
   const int block = 128;
   const size_t smem = ((static_cast<size_t>(a.model_bytes) + 15) & ~static_cast<size_t>(15)) +
-                      static_cast<size_t>(block / 32) * state_stride * sizeof(double);
+                      static_cast<size_t>(block / 32) * (state_stride + 2 * kRecheckScLinks) * sizeof(double);
   cudaError_t e = ensureSmem(recheckWarpKernel<FT>, smem, g);
   if (e != cudaSuccess)
     return e;
-  recheckWarpKernel<FT><<<grid, block, smem, stream>>>(a);
-  return cudaGetLastError();
+  static const bool pdl = !(getenv("B200SV_RECHECK_PDL") && atoi(getenv("B200SV_RECHECK_PDL")) == 0);
+  if (!pdl)
+  {
+    recheckWarpKernel<FT><<<grid, block, smem, stream>>>(a);
+    return cudaGetLastError();
+  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, recheckWarpKernel<FT>, a);
 }
 template cudaError_t launchRecheckWarp<uint8_t>(const CheckArgs<uint8_t>&, int, int, cudaStream_t);
 template cudaError_t launchRecheckWarp<uint16_t>(const CheckArgs<uint16_t>&, int, int, cudaStream_t);

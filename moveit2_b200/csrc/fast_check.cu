@@ -431,6 +431,9 @@ __global__ void __launch_bounds__(fastThreads(kV), fastMinBlocks(kV)) fastCheckK
 {
   using Elem = typename Cmp<FT>::Elem;
   extern __shared__ __align__(16) uint8_t smem[];
+  // the exact pass that follows (recheckWarpKernel, launched with programmatic stream serialization) may become resident as
+  // this kernel's CTAs drain: it loads its model into shared memory, then waits (griddepcontrol.wait) for this kernel's end
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const FModel m = loadFast<kHier>(a.model, a.model_bytes, smem);
   const fast::Header& h = *m.h;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
