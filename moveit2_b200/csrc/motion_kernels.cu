@@ -56,33 +56,29 @@ __global__ void motionCountKernel(MotionArgs a)
   }
 }
 
-// single-CTA exclusive scan of count[0..n) into offset[0..n]; n is a batch of edges, not of states.  Every thread owns a
-// contiguous run of ceil(n / blockDim) counts: it sums them, the block scans the 1024 sums once, and the thread writes its
-// run's offsets -- two barriers in all instead of four per 1024 elements.
+// single-CTA exclusive scan of count[0..n) into offset[0..n]; n is a batch of edges, not of states.  Every WARP owns a
+// contiguous stretch of the counts and walks it 32 at a time, so every load and store is one coalesced 128 / 256-byte request
+// (a first version gave every THREAD a contiguous run: 32 lines per request, 98 us for 100 000 edges under ncu): pass 1 sums
+// the stretches, the 32 sums are scanned once, pass 2 scans each stretch with shuffles and a running carry.
 __global__ void __launch_bounds__(1024) motionScanKernel(const unsigned* __restrict__ count, unsigned long long* __restrict__ offset,
                                                          size_t n)
 {
   __shared__ unsigned long long warp_sums[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t per = (n + blockDim.x - 1) / blockDim.x;
-  const size_t i0 = min(n, threadIdx.x * per), i1 = min(n, i0 + per);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const size_t per = ((n + warps - 1) / warps + 31) & ~static_cast<size_t>(31);  // a stretch is whole groups of 32
+  const size_t i0 = min(n, warp * per), i1 = min(n, i0 + per);
   unsigned long long mine = 0ull;
-  for (size_t i = i0; i < i1; ++i)
+  for (size_t i = i0 + lane; i < i1; i += 32)
     mine += count[i];
-  unsigned long long x = mine;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1)
-  {
-    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
-    if (lane >= d)
-      x += y;
-  }
-  if (lane == 31)
-    warp_sums[warp] = x;
+  for (int d = 16; d > 0; d >>= 1)
+    mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  if (lane == 0)
+    warp_sums[warp] = mine;
   __syncthreads();
   if (warp == 0)
   {
-    unsigned long long s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0ull;
+    unsigned long long s = lane < warps ? warp_sums[lane] : 0ull;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1)
     {
@@ -93,14 +89,25 @@ __global__ void __launch_bounds__(1024) motionScanKernel(const unsigned* __restr
     warp_sums[lane] = s;  // inclusive
   }
   __syncthreads();
-  unsigned long long run = (warp ? warp_sums[warp - 1] : 0ull) + (x - mine);
-  for (size_t i = i0; i < i1; ++i)
+  unsigned long long carry = warp ? warp_sums[warp - 1] : 0ull;
+  for (size_t base = i0; base < i1; base += 32)
   {
-    offset[i] = run;
-    run += count[i];
+    const size_t i = base + lane;
+    const unsigned long long c = i < i1 ? count[i] : 0ull;
+    unsigned long long x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d)
+        x += y;
+    }
+    if (i < i1)
+      offset[i] = carry + x - c;
+    carry += __shfl_sync(0xffffffffu, x, 31);
   }
-  if (threadIdx.x == blockDim.x - 1)
-    offset[n] = warp_sums[(blockDim.x >> 5) - 1];
+  if (threadIdx.x == 0)
+    offset[n] = warp_sums[warps - 1];
 }
 
 // one WARP per edge, one lane per generated state (no search for the state's edge; the lanes of a warp write one contiguous
